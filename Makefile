@@ -1,0 +1,36 @@
+# Builds lis_b200/_lib/liblis_b200.so : host C (lis.h API) + sm_100a CUDA kernels, one shared
+# library with a C ABI.  `make` here or __graft_entry__.build().
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CC       := /usr/bin/gcc
+CUDA_INC := /usr/local/cuda/include
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -Iinclude
+CFLAGS   := -O2 -g -fPIC -std=gnu11 -Wall -Wextra -Wno-unused-parameter -ffp-contract=off -Iinclude -Ilis_b200/csrc/host -I$(CUDA_INC)
+OUT      := lis_b200/_lib
+OBJ      := lis_b200/_build
+KSRC     := $(wildcard lis_b200/csrc/kernels/*.cu)
+HSRC     := $(wildcard lis_b200/csrc/host/*.c)
+KOBJ     := $(patsubst lis_b200/csrc/kernels/%.cu,$(OBJ)/k_%.o,$(KSRC))
+HOBJ     := $(patsubst lis_b200/csrc/host/%.c,$(OBJ)/h_%.o,$(HSRC))
+
+.PHONY: all clean drivers
+all: $(OUT)/liblis_b200.so $(OUT)/liblis_b200_shim.so
+
+# the shared test driver (tests/shim/lis_shim.c, public API only) against this library
+$(OUT)/liblis_b200_shim.so: tests/shim/lis_shim.c $(OUT)/liblis_b200.so $(wildcard include/*.h)
+	$(CC) -O2 -g -fPIC -shared -Iinclude -o $@ tests/shim/lis_shim.c -L$(OUT) -llis_b200 -Wl,-rpath,'$$ORIGIN' -lm
+
+$(OBJ)/k_%.o: lis_b200/csrc/kernels/%.cu lis_b200/csrc/kernels/common.cuh include/lis_b200_kernels.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJ)/h_%.o: lis_b200/csrc/host/%.c $(wildcard lis_b200/csrc/host/*.h) $(wildcard include/*.h)
+	@mkdir -p $(OBJ)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(OUT)/liblis_b200.so: $(KOBJ) $(HOBJ)
+	@mkdir -p $(OUT)
+	$(NVCC) $(ARCH) -shared -Xlinker -Bsymbolic -o $@ $^ -cudart shared -lm -ldl -lpthread -lrt
+
+clean:
+	rm -rf $(OBJ) $(OUT)

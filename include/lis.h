@@ -1,0 +1,519 @@
+/*
+ * lis.h -- public C API of lis_b200, a B200-native implementation of the Lis SpMV/Krylov
+ * hot path.  Source-compatible with the subset of Lis 2.1.11's lis.h that the reference
+ * drivers test/test1.c, test3.c, test3b.c, test4.c, test5.c and test/spmvtest{1,2,2b,3,3b}.c
+ * use (reference: include/lis.h:55-283 constants, :513-758 handle types, :824-1045 API,
+ * :1052-1078 error codes and LIS_GET_ISIE), so those files compile unchanged against it.
+ *
+ * Differences a maintainer should know about (details in INTEGRATION.md):
+ *   - LIS_SCALAR is double, LIS_INT is int (the reference's default build); no complex,
+ *     long-double, quad or 64-bit-index variants.
+ *   - vector storage (`v->value`) is CUDA managed memory: host code may read and write it
+ *     between API calls exactly as with the reference, kernels run on it in HBM.
+ *   - matrices keep the caller's host arrays (same ownership rules as the reference) plus a
+ *     private device mirror built on first use.
+ *   - every compute entry point runs on the GPU; without a CUDA device it fails with
+ *     LIS_ERR_DEVICE instead of silently computing on the CPU.
+ */
+#ifndef LIS_B200_LIS_H
+#define LIS_B200_LIS_H
+
+#include <stdio.h>
+#include <stddef.h>
+
+#define LIS_VERSION "2.1.11-b200"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ scalar & index types */
+typedef double LIS_SCALAR;
+typedef double LIS_REAL;
+typedef int LIS_INT;
+typedef unsigned int LIS_UNSIGNED_INT;
+typedef LIS_INT LIS_Comm;            /* no MPI: ranks are processes bootstrapped from the env */
+#define LIS_COMM_WORLD ((LIS_Comm)0x1)
+#ifndef conj
+#define conj(x) (x)
+#endif
+#define _max(a, b) ((a) >= (b) ? (a) : (b))
+#define _min(a, b) ((a) <= (b) ? (a) : (b))
+
+/* ------------------------------------------------------------------ return codes */
+#define LIS_TRUE 1
+#define LIS_FALSE 0
+#define LIS_FAILS (-1)
+#define LIS_SUCCESS 0
+#define LIS_ILL_OPTION 1
+#define LIS_ERR_ILL_ARG 1
+#define LIS_BREAKDOWN 2
+#define LIS_OUT_OF_MEMORY 3
+#define LIS_ERR_OUT_OF_MEMORY 3
+#define LIS_MAXITER 4
+#define LIS_ERR_NOT_IMPLEMENTED 5
+#define LIS_ERR_FILE_IO 6
+#define LIS_ERR_DEVICE 7             /* extension: CUDA device missing or a kernel failed */
+
+/* ------------------------------------------------------------------ enumerations */
+/* storage formats (matrix_type) */
+#define LIS_MATRIX_ASSEMBLING 0
+#define LIS_MATRIX_CSR 1
+#define LIS_MATRIX_CSC 2
+#define LIS_MATRIX_MSR 3
+#define LIS_MATRIX_DIA 4
+#define LIS_MATRIX_CDS 4
+#define LIS_MATRIX_ELL 5
+#define LIS_MATRIX_JAD 6
+#define LIS_MATRIX_BSR 7
+#define LIS_MATRIX_BSC 8
+#define LIS_MATRIX_VBR 9
+#define LIS_MATRIX_COO 10
+#define LIS_MATRIX_DENSE 11
+#define LIS_MATRIX_DNS 11
+#define LIS_MATRIX_RCO 255
+#define LIS_MATRIX_DECIDING_SIZE (-(LIS_MATRIX_RCO + 1))
+#define LIS_MATRIX_NULL (-(LIS_MATRIX_RCO + 2))
+#define LIS_MATRIX_DEFAULT LIS_MATRIX_CSR
+#define LIS_MATRIX_POINT LIS_MATRIX_CSR
+#define LIS_MATRIX_BLOCK LIS_MATRIX_BSR
+
+/* triangular-solve selector of lis_matrix_solve */
+#define LIS_MATRIX_LOWER 0
+#define LIS_MATRIX_UPPER 1
+#define LIS_MATRIX_SSOR 2
+
+/* value insertion */
+#define LIS_INS_VALUE 0
+#define LIS_ADD_VALUE 1
+#define LIS_SUB_VALUE 2
+
+#define LIS_ORIGIN_0 0
+#define LIS_ORIGIN_1 1
+
+/* file formats */
+#define LIS_FMT_AUTO 0
+#define LIS_FMT_PLAIN 1
+#define LIS_FMT_MM 2
+#define LIS_FMT_LIS 3
+#define LIS_FMT_LIS_ASCII 3
+#define LIS_FMT_LIS_BINARY 4
+#define LIS_FMT_FREE 5
+#define LIS_FMT_ITBL 6
+#define LIS_FMT_HB 7
+#define LIS_FMT_MMB 8
+
+/* solvers (the numbering of the reference; only CG, BiCG, BiCGSTAB and GMRES run here) */
+#define LIS_SOLVER_LEN 25
+#define LIS_SOLVER_CG 1
+#define LIS_SOLVER_BICG 2
+#define LIS_SOLVER_CGS 3
+#define LIS_SOLVER_BICGSTAB 4
+#define LIS_SOLVER_BICGSTABL 5
+#define LIS_SOLVER_GPBICG 6
+#define LIS_SOLVER_QMR 7
+#define LIS_SOLVER_TFQMR 7
+#define LIS_SOLVER_ORTHOMIN 8
+#define LIS_SOLVER_GMRES 9
+#define LIS_SOLVER_JACOBI 10
+#define LIS_SOLVER_GS 11
+#define LIS_SOLVER_SOR 12
+#define LIS_SOLVER_BICGSAFE 13
+#define LIS_SOLVER_CR 14
+#define LIS_SOLVER_BICR 15
+#define LIS_SOLVER_CRS 16
+#define LIS_SOLVER_BICRSTAB 17
+#define LIS_SOLVER_GPBICR 18
+#define LIS_SOLVER_BICRSAFE 19
+#define LIS_SOLVER_FGMRES 20
+#define LIS_SOLVER_IDRS 21
+#define LIS_SOLVER_IDR1 22
+#define LIS_SOLVER_MINRES 23
+#define LIS_SOLVER_COCG 24
+#define LIS_SOLVER_COCR 25
+
+/* preconditioners (only NONE, JACOBI, SSOR and user-registered ones run here) */
+#define LIS_PRECON_TYPE_LEN 12
+#define LIS_PRECON_TYPE_NONE 0
+#define LIS_PRECON_TYPE_JACOBI 1
+#define LIS_PRECON_TYPE_ILU 2
+#define LIS_PRECON_TYPE_SSOR 3
+#define LIS_PRECON_TYPE_HYBRID 4
+#define LIS_PRECON_TYPE_IS 5
+#define LIS_PRECON_TYPE_SAI 6
+#define LIS_PRECON_TYPE_SAAMG 7
+#define LIS_PRECON_TYPE_ILUC 8
+#define LIS_PRECON_TYPE_ILUT 9
+#define LIS_PRECON_TYPE_BJACOBI 10
+#define LIS_PRECON_TYPE_ADDS 11
+#define LIS_PRECON_TYPE_USERDEF LIS_PRECON_TYPE_LEN
+#define LIS_PRECONNAME_MAX 10
+#define LIS_PRECON_REGISTER_MAX 10
+
+/* solver->options[] slots and solver->params[] slots (params are addressed as
+ * LIS_PARAMS_x - LIS_OPTIONS_LEN, like in the reference) */
+#define LIS_OPTIONS_LEN 27
+#define LIS_OPTIONS_SOLVER 0
+#define LIS_OPTIONS_PRECON 1
+#define LIS_OPTIONS_MAXITER 2
+#define LIS_OPTIONS_OUTPUT 3
+#define LIS_OPTIONS_RESTART 4
+#define LIS_OPTIONS_ELL 5
+#define LIS_OPTIONS_SCALE 6
+#define LIS_OPTIONS_FILL 7
+#define LIS_OPTIONS_M 8
+#define LIS_OPTIONS_PSOLVER 9
+#define LIS_OPTIONS_PMAXITER 10
+#define LIS_OPTIONS_PRESTART 11
+#define LIS_OPTIONS_PELL 12
+#define LIS_OPTIONS_PPRECON 13
+#define LIS_OPTIONS_ISLEVEL 14
+#define LIS_OPTIONS_INITGUESS_ZEROS 15
+#define LIS_OPTIONS_ADDS 16
+#define LIS_OPTIONS_ADDS_ITER 17
+#define LIS_OPTIONS_PRECISION 18
+#define LIS_OPTIONS_USE_AT 19
+#define LIS_OPTIONS_SWITCH_MAXITER 20
+#define LIS_OPTIONS_SAAMG_UNSYM 21
+#define LIS_OPTIONS_STORAGE 22
+#define LIS_OPTIONS_STORAGE_BLOCK 23
+#define LIS_OPTIONS_CONV_COND 24
+#define LIS_OPTIONS_INIT_SHADOW_RESID 25
+#define LIS_OPTIONS_IDRS_RESTART 26
+
+#define LIS_PARAMS_LEN 15
+#define LIS_PARAMS_RESID (LIS_OPTIONS_LEN + 0)
+#define LIS_PARAMS_OMEGA (LIS_OPTIONS_LEN + 1)
+#define LIS_PARAMS_RELAX (LIS_OPTIONS_LEN + 2)
+#define LIS_PARAMS_DROP (LIS_OPTIONS_LEN + 3)
+#define LIS_PARAMS_ALPHA (LIS_OPTIONS_LEN + 4)
+#define LIS_PARAMS_TAU (LIS_OPTIONS_LEN + 5)
+#define LIS_PARAMS_SIGMA (LIS_OPTIONS_LEN + 6)
+#define LIS_PARAMS_GAMMA (LIS_OPTIONS_LEN + 7)
+#define LIS_PARAMS_SSOR_OMEGA (LIS_OPTIONS_LEN + 8)
+#define LIS_PARAMS_PRESID (LIS_OPTIONS_LEN + 9)
+#define LIS_PARAMS_POMEGA (LIS_OPTIONS_LEN + 10)
+#define LIS_PARAMS_SWITCH_RESID (LIS_OPTIONS_LEN + 11)
+#define LIS_PARAMS_RATE (LIS_OPTIONS_LEN + 12)
+#define LIS_PARAMS_RESID_WEIGHT (LIS_OPTIONS_LEN + 13)
+#define LIS_PARAMS_SAAMG_THETA (LIS_OPTIONS_LEN + 14)
+
+#define LIS_PRINT_NONE 0
+#define LIS_PRINT_MEM 1
+#define LIS_PRINT_OUT 2
+#define LIS_PRINT_ALL 3
+
+#define LIS_SCALE_NONE 0
+#define LIS_SCALE_JACOBI 1
+#define LIS_SCALE_SYMM_DIAG 2
+
+#define LIS_CONV_COND_DEFAULT 0
+#define LIS_CONV_COND_NRM2_R 0
+#define LIS_CONV_COND_NRM2_B 1
+#define LIS_CONV_COND_NRM1_B 2
+
+#define LIS_RESID 0
+#define LIS_RANDOM 1
+
+#define LIS_PRECISION_DEFAULT 0
+#define LIS_PRECISION_DOUBLE 0
+#define LIS_PRECISION_QUAD 1
+#define LIS_PRECISION_SWITCH 2
+
+#define LIS_LABEL_VECTOR 0
+#define LIS_LABEL_MATRIX 1
+
+#define LIS_VECTOR_NULL (-1)
+#define LIS_VECTOR_ASSEMBLING 0
+#define LIS_VECTOR_ASSEMBLED 1
+
+#define LIS_MATRIX_OPTION_LEN 10
+
+/* function-trace hooks of the reference's debug build: no-ops here */
+#define LIS_DEBUG_FUNC_IN
+#define LIS_DEBUG_FUNC_OUT
+
+/* ------------------------------------------------------------------ handle types
+ * Vectors and matrices start with the same header so that lis_vector_duplicate() can take
+ * either (reference: src/vector/lis_vector.c:370-390 checks `label`). */
+#define LIS_B200_OBJECT_HEADER                                                             \
+    LIS_INT label;      /* LIS_LABEL_VECTOR / LIS_LABEL_MATRIX */                          \
+    LIS_INT status;                                                                        \
+    LIS_INT precision;                                                                     \
+    LIS_INT gn;         /* global size */                                                  \
+    LIS_INT n;          /* rows owned by this rank */                                      \
+    LIS_INT np;         /* n + halo entries */                                             \
+    LIS_INT pad;                                                                           \
+    LIS_INT origin;                                                                        \
+    LIS_INT is_copy;                                                                       \
+    LIS_INT is_destroy;                                                                    \
+    LIS_INT is_scaled;                                                                     \
+    LIS_INT my_rank;                                                                       \
+    LIS_INT nprocs;                                                                        \
+    LIS_Comm comm;                                                                         \
+    LIS_INT is;         /* first global row owned */                                       \
+    LIS_INT ie;         /* one past the last global row owned */                           \
+    LIS_INT *ranges;    /* nprocs+1 row offsets */
+
+struct LIS_VECTOR_STRUCT {
+    LIS_B200_OBJECT_HEADER
+    LIS_SCALAR *value;  /* managed memory, np+pad entries */
+    LIS_SCALAR *work;
+    LIS_INT intvalue;
+    /* private to lis_b200 */
+    LIS_INT b200_resident;   /* 1 = pages were last prefetched to the device */
+    size_t b200_capacity;    /* allocated entries */
+    LIS_INT b200_managed;    /* value came from the device allocator */
+};
+typedef struct LIS_VECTOR_STRUCT *LIS_VECTOR;
+
+/* strictly lower / upper part of a split matrix */
+struct LIS_MATRIX_CORE_STRUCT {
+    LIS_INT nnz, ndz, bnr, bnc, nr, nc, bnnz, nnd, maxnzr;
+    LIS_INT *ptr, *row, *col, *index, *bptr, *bindex;
+    LIS_SCALAR *value;
+    LIS_SCALAR *work;
+};
+typedef struct LIS_MATRIX_CORE_STRUCT *LIS_MATRIX_CORE;
+
+/* (block-)diagonal of a split matrix; scalar blocks only */
+struct LIS_MATRIX_DIAG_STRUCT {
+    LIS_B200_OBJECT_HEADER
+    LIS_SCALAR *value;
+    LIS_SCALAR *work;
+    LIS_INT bn, nr;
+    LIS_INT *bns, *ptr;
+    LIS_SCALAR **v_value;
+};
+typedef struct LIS_MATRIX_DIAG_STRUCT *LIS_MATRIX_DIAG;
+
+struct LIS_COMMTABLE_STRUCT;
+typedef struct LIS_COMMTABLE_STRUCT *LIS_COMMTABLE;
+
+struct LIS_MATRIX_STRUCT {
+    LIS_B200_OBJECT_HEADER
+    LIS_INT matrix_type;
+    LIS_INT nnz;        /* CSR, CSC, JAD */
+    LIS_INT ndz;
+    LIS_INT bnr, bnc;   /* BSR block shape */
+    LIS_INT nr, nc;     /* BSR block rows / columns */
+    LIS_INT bnnz;       /* BSR blocks */
+    LIS_INT nnd;        /* DIA diagonals */
+    LIS_INT maxnzr;     /* ELL, JAD */
+    LIS_INT *ptr;       /* CSR, CSC, JAD */
+    LIS_INT *row;       /* JAD permutation */
+    LIS_INT *col;
+    LIS_INT *index;     /* CSR, CSC, DIA offsets, ELL, JAD */
+    LIS_INT *bptr;      /* BSR */
+    LIS_INT *bindex;    /* BSR */
+    LIS_SCALAR *value;
+    LIS_SCALAR *work;
+
+    LIS_MATRIX_CORE L, U;
+    LIS_MATRIX_DIAG D, WD;
+
+    LIS_INT is_block, pad_comm, is_pmat, is_sorted, is_splited, is_save, is_comm, is_fallocated;
+    LIS_INT use_wd;
+    LIS_INT conv_bnr, conv_bnc;
+    LIS_INT *conv_row, *conv_col;
+    LIS_INT options[LIS_MATRIX_OPTION_LEN];
+
+    /* row-wise assembly buffers filled by lis_matrix_set_value */
+    LIS_INT w_annz;
+    LIS_INT *w_nnz;
+    LIS_INT *w_row;
+    LIS_INT **w_index;
+    LIS_SCALAR **w_value;
+
+    LIS_INT *l2g_map;        /* halo slot -> global column */
+    LIS_COMMTABLE commtable;
+
+    void *b200_dev;          /* private: device mirror (lis_b200/csrc/host/lis_device.h) */
+};
+typedef struct LIS_MATRIX_STRUCT *LIS_MATRIX;
+
+struct LIS_SOLVER_STRUCT;
+
+struct LIS_PRECON_STRUCT {
+    LIS_INT precon_type;
+    LIS_MATRIX A;            /* SSOR: the split matrix */
+    LIS_MATRIX Ah;
+    LIS_VECTOR D;            /* Jacobi: 1/diag(A) */
+    LIS_VECTOR *work;
+    struct LIS_SOLVER_STRUCT *solver;
+    LIS_INT worklen;
+    LIS_INT is_copy;
+    void *b200_sweep;        /* private: SSOR level schedule on the device */
+};
+typedef struct LIS_PRECON_STRUCT *LIS_PRECON;
+
+struct LIS_SOLVER_STRUCT {
+    LIS_MATRIX A, Ah;
+    LIS_VECTOR b, x, xx, d;
+    LIS_MATRIX_DIAG WD;
+    LIS_PRECON precon;
+    LIS_VECTOR *work;
+    LIS_REAL *rhistory;
+    LIS_INT worklen;
+    LIS_INT options[LIS_OPTIONS_LEN];
+    LIS_SCALAR params[LIS_PARAMS_LEN];
+    LIS_INT retcode;
+    LIS_INT iter;
+    LIS_INT iter2;
+    LIS_REAL resid;
+    double time, itime, ptime, p_c_time, p_i_time;
+    LIS_INT precision;
+    LIS_REAL bnrm;
+    LIS_REAL tol;
+    LIS_REAL tol_switch;
+    LIS_INT setup;
+};
+typedef struct LIS_SOLVER_STRUCT *LIS_SOLVER;
+
+typedef LIS_INT (*LIS_PRECON_CREATE_XXX)(LIS_SOLVER solver, LIS_PRECON precon);
+typedef LIS_INT (*LIS_PSOLVE_XXX)(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
+typedef LIS_INT (*LIS_PSOLVEH_XXX)(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
+
+/* ------------------------------------------------------------------ library lifetime */
+LIS_INT lis_initialize(int *argc, char **argv[]);
+LIS_INT lis_finalize(void);
+double lis_wtime(void);
+void CHKERR(LIS_INT err);
+LIS_INT lis_printf(LIS_Comm comm, const char *mess, ...);   /* rank 0 only; %D = LIS_INT */
+void *lis_malloc(size_t size, char *tag);
+void *lis_calloc(size_t size, char *tag);
+void *lis_realloc(void *p, size_t size);
+void lis_free(void *p);
+void lis_free2(LIS_INT n, ...);
+LIS_INT lis_is_malloc(void *p);
+void lis_date(char *date);
+
+/* ------------------------------------------------------------------ vectors */
+LIS_INT lis_vector_create(LIS_Comm comm, LIS_VECTOR *vec);
+LIS_INT lis_vector_set_size(LIS_VECTOR vec, LIS_INT local_n, LIS_INT global_n);
+LIS_INT lis_vector_destroy(LIS_VECTOR vec);
+LIS_INT lis_vector_duplicate(void *vin, LIS_VECTOR *vout);
+LIS_INT lis_vector_get_size(LIS_VECTOR v, LIS_INT *local_n, LIS_INT *global_n);
+LIS_INT lis_vector_get_range(LIS_VECTOR v, LIS_INT *is, LIS_INT *ie);
+LIS_INT lis_vector_get_value(LIS_VECTOR v, LIS_INT i, LIS_SCALAR *value);
+LIS_INT lis_vector_get_values(LIS_VECTOR v, LIS_INT start, LIS_INT count, LIS_SCALAR value[]);
+LIS_INT lis_vector_set_value(LIS_INT flag, LIS_INT i, LIS_SCALAR value, LIS_VECTOR v);
+LIS_INT lis_vector_set_values(LIS_INT flag, LIS_INT count, LIS_INT index[], LIS_SCALAR value[], LIS_VECTOR v);
+LIS_INT lis_vector_set_values2(LIS_INT flag, LIS_INT start, LIS_INT count, LIS_SCALAR value[], LIS_VECTOR v);
+LIS_INT lis_vector_print(LIS_VECTOR x);
+LIS_INT lis_vector_scatter(LIS_SCALAR value[], LIS_VECTOR v);
+LIS_INT lis_vector_gather(LIS_VECTOR v, LIS_SCALAR value[]);
+LIS_INT lis_vector_is_null(LIS_VECTOR v);
+
+LIS_INT lis_vector_swap(LIS_VECTOR vsrc, LIS_VECTOR vdst);
+LIS_INT lis_vector_copy(LIS_VECTOR vsrc, LIS_VECTOR vdst);
+LIS_INT lis_vector_axpy(LIS_SCALAR alpha, LIS_VECTOR vx, LIS_VECTOR vy);
+LIS_INT lis_vector_xpay(LIS_VECTOR vx, LIS_SCALAR alpha, LIS_VECTOR vy);
+LIS_INT lis_vector_axpyz(LIS_SCALAR alpha, LIS_VECTOR vx, LIS_VECTOR vy, LIS_VECTOR vz);
+LIS_INT lis_vector_scale(LIS_SCALAR alpha, LIS_VECTOR vx);
+LIS_INT lis_vector_pmul(LIS_VECTOR vx, LIS_VECTOR vy, LIS_VECTOR vz);
+LIS_INT lis_vector_pdiv(LIS_VECTOR vx, LIS_VECTOR vy, LIS_VECTOR vz);
+LIS_INT lis_vector_set_all(LIS_SCALAR alpha, LIS_VECTOR vx);
+LIS_INT lis_vector_abs(LIS_VECTOR vx);
+LIS_INT lis_vector_reciprocal(LIS_VECTOR vx);
+LIS_INT lis_vector_conjugate(LIS_VECTOR vx);
+LIS_INT lis_vector_shift(LIS_SCALAR sigma, LIS_VECTOR vx);
+LIS_INT lis_vector_dot(LIS_VECTOR vx, LIS_VECTOR vy, LIS_SCALAR *value);
+LIS_INT lis_vector_nhdot(LIS_VECTOR vx, LIS_VECTOR vy, LIS_SCALAR *value);
+LIS_INT lis_vector_nrm1(LIS_VECTOR vx, LIS_REAL *value);
+LIS_INT lis_vector_nrm2(LIS_VECTOR vx, LIS_REAL *value);
+LIS_INT lis_vector_nrmi(LIS_VECTOR vx, LIS_REAL *value);
+LIS_INT lis_vector_sum(LIS_VECTOR vx, LIS_SCALAR *value);
+
+/* ------------------------------------------------------------------ matrices */
+LIS_INT lis_matrix_create(LIS_Comm comm, LIS_MATRIX *Amat);
+LIS_INT lis_matrix_destroy(LIS_MATRIX Amat);
+LIS_INT lis_matrix_assemble(LIS_MATRIX A);
+LIS_INT lis_matrix_is_assembled(LIS_MATRIX A);
+LIS_INT lis_matrix_duplicate(LIS_MATRIX Ain, LIS_MATRIX *Aout);
+LIS_INT lis_matrix_set_size(LIS_MATRIX A, LIS_INT local_n, LIS_INT global_n);
+LIS_INT lis_matrix_get_size(LIS_MATRIX A, LIS_INT *local_n, LIS_INT *global_n);
+LIS_INT lis_matrix_get_range(LIS_MATRIX A, LIS_INT *is, LIS_INT *ie);
+LIS_INT lis_matrix_get_nnz(LIS_MATRIX A, LIS_INT *nnz);
+LIS_INT lis_matrix_set_type(LIS_MATRIX A, LIS_INT matrix_type);
+LIS_INT lis_matrix_get_type(LIS_MATRIX A, LIS_INT *matrix_type);
+LIS_INT lis_matrix_set_value(LIS_INT flag, LIS_INT i, LIS_INT j, LIS_SCALAR value, LIS_MATRIX A);
+LIS_INT lis_matrix_malloc(LIS_MATRIX A, LIS_INT nnz_row, LIS_INT nnz[]);
+LIS_INT lis_matrix_get_diagonal(LIS_MATRIX A, LIS_VECTOR d);
+LIS_INT lis_matrix_convert(LIS_MATRIX Ain, LIS_MATRIX Aout);
+LIS_INT lis_matrix_copy(LIS_MATRIX Ain, LIS_MATRIX Aout);
+LIS_INT lis_matrix_set_blocksize(LIS_MATRIX A, LIS_INT bnr, LIS_INT bnc, LIS_INT row[], LIS_INT col[]);
+LIS_INT lis_matrix_unset(LIS_MATRIX A);
+
+/* set_* adopt the caller's arrays without copying; lis_matrix_destroy frees them */
+LIS_INT lis_matrix_malloc_csr(LIS_INT n, LIS_INT nnz, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);
+LIS_INT lis_matrix_set_csr(LIS_INT nnz, LIS_INT *ptr, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
+LIS_INT lis_matrix_malloc_csc(LIS_INT n, LIS_INT nnz, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);
+LIS_INT lis_matrix_set_csc(LIS_INT nnz, LIS_INT *ptr, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
+LIS_INT lis_matrix_malloc_bsr(LIS_INT n, LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT **bptr, LIS_INT **bindex, LIS_SCALAR **value);
+LIS_INT lis_matrix_set_bsr(LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT *bptr, LIS_INT *bindex, LIS_SCALAR *value, LIS_MATRIX A);
+LIS_INT lis_matrix_malloc_ell(LIS_INT n, LIS_INT maxnzr, LIS_INT **index, LIS_SCALAR **value);
+LIS_INT lis_matrix_set_ell(LIS_INT maxnzr, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
+LIS_INT lis_matrix_malloc_jad(LIS_INT n, LIS_INT nnz, LIS_INT maxnzr, LIS_INT **perm, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);
+LIS_INT lis_matrix_set_jad(LIS_INT nnz, LIS_INT maxnzr, LIS_INT *perm, LIS_INT *ptr, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
+LIS_INT lis_matrix_malloc_dia(LIS_INT n, LIS_INT nnd, LIS_INT **index, LIS_SCALAR **value);
+LIS_INT lis_matrix_set_dia(LIS_INT nnd, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
+
+/* ------------------------------------------------------------------ matrix-vector product */
+LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);
+
+/* ------------------------------------------------------------------ linear solvers */
+LIS_INT lis_solver_create(LIS_SOLVER *solver);
+LIS_INT lis_solver_destroy(LIS_SOLVER solver);
+LIS_INT lis_solver_get_iter(LIS_SOLVER solver, LIS_INT *iter);
+LIS_INT lis_solver_get_iterex(LIS_SOLVER solver, LIS_INT *iter, LIS_INT *iter_double, LIS_INT *iter_quad);
+LIS_INT lis_solver_get_time(LIS_SOLVER solver, double *time);
+LIS_INT lis_solver_get_timeex(LIS_SOLVER solver, double *time, double *itime, double *ptime, double *p_c_time, double *p_i_time);
+LIS_INT lis_solver_get_residualnorm(LIS_SOLVER solver, LIS_REAL *residual);
+LIS_INT lis_solver_get_solver(LIS_SOLVER solver, LIS_INT *nsol);
+LIS_INT lis_solver_get_precon(LIS_SOLVER solver, LIS_INT *precon_type);
+LIS_INT lis_solver_get_status(LIS_SOLVER solver, LIS_INT *status);
+LIS_INT lis_solver_get_rhistory(LIS_SOLVER solver, LIS_VECTOR v);
+LIS_INT lis_solver_set_option(char *text, LIS_SOLVER solver);
+LIS_INT lis_solver_set_optionC(LIS_SOLVER solver);
+LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver);
+LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver, LIS_PRECON precon);
+LIS_INT lis_solver_get_solvername(LIS_INT solver, char *solvername);
+LIS_INT lis_solver_get_preconname(LIS_INT precon_type, char *preconname);
+LIS_INT lis_precon_register(char *name, LIS_PRECON_CREATE_XXX pcreate, LIS_PSOLVE_XXX psolve, LIS_PSOLVEH_XXX psolveh);
+LIS_INT lis_precon_register_free(void);
+
+/* ------------------------------------------------------------------ lis_b200 extensions */
+/* drop the device mirror of A after editing A->value / A->index behind the library's back */
+LIS_INT lis_matrix_b200_invalidate(LIS_MATRIX A);
+/* emulated OpenMP thread count of the reference (= SSOR block count); same as passing
+ * `-omp_num_threads N` to lis_initialize.  Returns the previous value. */
+LIS_INT lis_b200_set_num_threads(LIS_INT nthreads);
+/* join a process group explicitly (rank, size, 64-bit job token shared by all ranks) instead
+ * of through RANK / WORLD_SIZE / MASTER_PORT in the environment */
+LIS_INT lis_b200_comm_attach(LIS_INT rank, LIS_INT nranks, unsigned long long token);
+
+/* ------------------------------------------------------------------ file I/O */
+LIS_INT lis_input(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, char *filename);
+LIS_INT lis_input_matrix(LIS_MATRIX A, char *filename);
+LIS_INT lis_input_vector(LIS_VECTOR v, char *filename);
+LIS_INT lis_output_vector(LIS_VECTOR v, LIS_INT format, char *filename);
+LIS_INT lis_output_matrix(LIS_MATRIX A, LIS_INT format, char *path);
+LIS_INT lis_solver_output_rhistory(LIS_SOLVER solver, char *filename);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* contiguous 1-D row partition: rows [is, ie) of n belong to part `id` of `nprocs` */
+#define LIS_GET_ISIE(id, nprocs, n, is, ie)                                                \
+    if ((id) < (n) % (nprocs)) {                                                           \
+        (ie) = (n) / (nprocs) + 1;                                                         \
+        (is) = (ie) * (id);                                                                \
+    } else {                                                                               \
+        (ie) = (n) / (nprocs);                                                             \
+        (is) = (ie) * (id) + (n) % (nprocs);                                               \
+    }                                                                                      \
+    (ie) = (ie) + (is);
+
+#endif /* LIS_B200_LIS_H */

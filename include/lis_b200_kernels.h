@@ -1,0 +1,134 @@
+/*
+ * lis_b200_kernels.h -- the thin C-ABI between the host C library (lis.h API) and the
+ * hand-written sm_100a CUDA kernels.  Plain pointers and sizes only; every pointer named d_*
+ * is a DEVICE (or managed) pointer, `stream` is a cudaStream_t passed as void*.
+ *
+ * Each entry point replaces one OpenMP loop of the reference (Lis 2.1.11); the reference
+ * location is cited per function as  src/...:line  (relative to the reference tree).
+ *
+ * Arithmetic contract (what makes results bit-identical to the reference's CPU path):
+ *   - IEEE fp64, multiply and add rounded separately (no FMA contraction; the reference is
+ *     built -O3 without -march, configure.ac:505), division correctly rounded;
+ *   - every row sum starts from +0.0 and adds products in STORAGE ORDER of the format;
+ *   - dot/nrm2 are the only reassociated operations (fixed, run-to-run deterministic tree).
+ *
+ * All functions return 0 on success or a cudaError_t value (>0) on failure.
+ * Vectors may alias exactly as the reference allows (e.g. axpy x==y is not supported there
+ * either); x and y of an SpMV must not alias.
+ */
+#ifndef LIS_B200_KERNELS_H
+#define LIS_B200_KERNELS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------- */
+/* number of SMs of the current device (grid sizing), <=0 on error */
+int  lisb200_sm_count(void);
+const char *lisb200_error_string(int code);
+
+/* ---- SpMV, y = A x ------------------------------------------------------------------- */
+/* CSR, unsplit order.                                  src/matvec/lis_matvec_csr.c:90-110
+ * rows [0,n); d_ptr has n+1 entries; d_idx/d_val must be readable up to nnz rounded up to a
+ * multiple of 4 entries (the host library pads its device mirrors).                        */
+int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_val,
+                     const double *d_x, double *d_y, void *stream);
+/* CSR, split order  t = D[i]*x[i]; t += L...; t += U...  src/matvec/lis_matvec_csr.c:64-87 */
+int lisb200_spmv_csr_split(int n, const double *d_diag,
+                           const int *d_lptr, const int *d_lidx, const double *d_lval,
+                           const int *d_uptr, const int *d_uidx, const double *d_uval,
+                           const double *d_x, double *d_y, void *stream);
+/* CSR SpMV fused with the dot product <x,y> that follows it in CG (q=Ap; <p,q>).
+ * d_partial: >= lisb200_reduce_slots() doubles of scratch; the reduced scalar is written to
+ * *d_result (device or mapped-host pointer).  Same y bits as lisb200_spmv_csr, same dot
+ * bits as lisb200_dot on (x,y).                                                           */
+int lisb200_spmv_csr_dot(int n, const int *d_ptr, const int *d_idx, const double *d_val,
+                         const double *d_x, double *d_y, double *d_partial,
+                         unsigned int *d_counter, double *d_result, void *stream);
+/* ELL, column-major value[j*ld+i], index[j*ld+i], j<maxnzr  src/matvec/lis_matvec_ell.c:92-130 */
+int lisb200_spmv_ell(int n, int maxnzr, int ld, const int *d_idx, const double *d_val,
+                     const double *d_x, double *d_y, void *stream);
+/* DIA, serial (nprocs=1) layout value[j*ld+i], offsets d_off[j] ascending
+ *                                                      src/matvec/lis_matvec_dia.c:126-174
+ * xlen = number of addressable x entries (n, or np in a row-partitioned matrix).          */
+int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *d_off, const double *d_val,
+                     const double *d_x, double *d_y, void *stream);
+/* JAD, serial layout: d_jptr[maxnzr+1], d_perm[n] (y[perm[i]] = w[i])
+ *                                                      src/matvec/lis_matvec_jad.c:144-198 */
+int lisb200_spmv_jad(int n, int maxnzr, const int *d_jptr, const int *d_perm,
+                     const int *d_idx, const double *d_val,
+                     const double *d_x, double *d_y, void *stream);
+/* BSR bnr x bnc, blocks column-major (value[bc*bnr*bnc + j*bnr + i])
+ *                                      src/matvec/lis_matvec_bsr.c:57-150 and :152-858     */
+int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bptr, const int *d_bidx,
+                     const double *d_val, const double *d_x, double *d_y, void *stream);
+
+/* ---- BLAS-1 elementwise (bit-exact) -------------------- src/vector/lis_vector_opv.c ---- */
+int lisb200_copy   (int n, const double *d_x, double *d_y, void *stream);               /* :136 */
+int lisb200_axpy   (int n, double alpha, const double *d_x, double *d_y, void *stream); /* :176 y += a*x */
+int lisb200_xpay   (int n, const double *d_x, double alpha, double *d_y, void *stream); /* :216 y = x + a*y */
+int lisb200_axpyz  (int n, double alpha, const double *d_x, const double *d_y, double *d_z, void *stream); /* :256 */
+int lisb200_scale  (int n, double alpha, double *d_x, void *stream);                    /* :287 */
+int lisb200_pmul   (int n, const double *d_x, const double *d_y, double *d_z, void *stream); /* :328 (also Jacobi psolve, src/precon/lis_precon_jacobi.c:119-126) */
+int lisb200_pdiv   (int n, const double *d_x, const double *d_y, double *d_z, void *stream); /* :368 */
+int lisb200_set_all(int n, double alpha, double *d_x, void *stream);                    /* :399 */
+int lisb200_abs    (int n, double *d_x, void *stream);                                  /* :430 */
+int lisb200_reciprocal(int n, double *d_x, void *stream);                               /* :460 */
+int lisb200_shift  (int n, double sigma, double *d_x, void *stream);                    /* :522 x -= sigma */
+int lisb200_swap   (int n, double *d_x, double *d_y, void *stream);                     /* :94  */
+
+/* ---- BLAS-1 reductions --------------------------------- src/vector/lis_vector_ops.c ---- */
+/* Number of doubles of scratch a reduction needs in d_partial (per concurrently running
+ * reduction), independent of n.                                                            */
+int lisb200_reduce_slots(void);
+/* kind: 0 dot(x,y) :58, 1 sum x*x (nrm2 before sqrt) :210, 2 nrm1 :278, 3 nrmi (max|x|) :344,
+ * 4 sum :418.  The scalar lands in *d_result (device or mapped-host).  d_counter: one
+ * zero-initialised unsigned int that the kernel resets before exiting.                      */
+int lisb200_reduce(int kind, int n, const double *d_x, const double *d_y,
+                   double *d_partial, unsigned int *d_counter, double *d_result, void *stream);
+/* two dot products sharing one pass: r[0]=<a,b>, r[1]=<a,a>  (BiCGSTAB <t,s>,<t,t>,
+ * src/solver/lis_solver_bicgstab.c:267-268).  Bits equal two separate lisb200_reduce calls. */
+int lisb200_dot2(int n, const double *d_a, const double *d_b,
+                 double *d_partial, unsigned int *d_counter, double *d_result2, void *stream);
+
+/* ---- CG fused updates (bit-identical to the unfused call sequence) ---------------------- */
+/* x += alpha*p ; r += (-alpha)*q ; rr = sum r*r          src/solver/lis_solver_cg.c:205-211 */
+int lisb200_cg_update(int n, double alpha, const double *d_p, const double *d_q,
+                      double *d_x, double *d_r,
+                      double *d_partial, unsigned int *d_counter, double *d_rr, void *stream);
+/* z = r .* dinv ; rho = <r,z>     src/solver/lis_solver_cg.c:173-177 with Jacobi psolve      */
+int lisb200_jacobi_dot(int n, const double *d_r, const double *d_dinv, double *d_z,
+                       double *d_partial, unsigned int *d_counter, double *d_rho, void *stream);
+
+/* ---- matrix helpers ---------------------------------------------------------------------- */
+/* d[i] = first stored entry with index==i, else 0         src/matrix/lis_matrix_csr.c:540-553 */
+int lisb200_csr_get_diagonal(int n, const int *d_ptr, const int *d_idx, const double *d_val,
+                             double *d_d, void *stream);
+
+/* ---- SSOR sweep (level-scheduled, block-per-"thread" like the reference's OpenMP path) --- */
+/* forward:  x[i] = (b[i] - sum_{L, jj>=blk_start} L*x[jj]) * wd[i]
+ * backward: x[i] -= (sum_{U, blk_start<=jj<blk_end} U*x[jj]) * wd[i]
+ *                                                         src/matrix/lis_matrix_csr.c:1578-1628
+ * Rows are processed level by level: d_lvl_rows lists the rows of level l in
+ * [d_lvl_ptr[l], d_lvl_ptr[l+1]) (host array h_lvl_ptr drives the launches).
+ * d_blk_of_row[i] gives [start,end) of the block that owns row i via d_blk_range[2*b..].     */
+int lisb200_ssor_forward_level(int nrows, const int *d_rows,
+                               const int *d_lptr, const int *d_lidx, const double *d_lval,
+                               const double *d_wd, const int *d_rowblk_start,
+                               const double *d_b, double *d_x, void *stream);
+int lisb200_ssor_backward_level(int nrows, const int *d_rows,
+                                const int *d_uptr, const int *d_uidx, const double *d_uval,
+                                const double *d_wd, const int *d_rowblk_start,
+                                const int *d_rowblk_end, double *d_x, void *stream);
+
+/* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
+/* d_ws[i] = d_x[d_export_index[i]] */
+int lisb200_gather(int count, const int *d_index, const double *d_x, double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIS_B200_KERNELS_H */

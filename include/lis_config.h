@@ -1,0 +1,5 @@
+/* lis_config.h -- the reference drivers include this under -DHAVE_CONFIG_H
+ * (e.g. test/test3.c:27-29).  lis_b200 has no configure step; nothing to define. */
+#ifndef LIS_B200_CONFIG_H
+#define LIS_B200_CONFIG_H
+#endif

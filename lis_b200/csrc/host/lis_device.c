@@ -1,0 +1,206 @@
+/*
+ * lis_device.c -- device runtime: stream, scratch, mapped scalars, managed vector storage.
+ * See lis_device.h.  Plain C over the CUDA runtime C API.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime_api.h>
+#include "lis_device.h"
+#include "lis_b200_kernels.h"
+
+typedef struct {
+    int probed, available, device;
+    cudaStream_t stream;
+    int busy;
+    double *partial; size_t partial_slots;
+    unsigned int *counter;
+    double *h_scalar, *d_scalar;
+} lisd_ctx_t;
+
+static lisd_ctx_t g_ctx;
+
+static void lisd_probe(void)
+{
+    if (g_ctx.probed) return;
+    g_ctx.probed = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        g_ctx.available = 0;
+        return;
+    }
+    int dev = 0;
+    const char *lr = getenv("LOCAL_RANK");
+    if (lr && *lr) dev = atoi(lr) % ndev;
+    if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaHostAlloc((void **)&g_ctx.h_scalar, LISD_NSCALARS * sizeof(double), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaHostGetDevicePointer((void **)&g_ctx.d_scalar, g_ctx.h_scalar, 0) != cudaSuccess) { cudaGetLastError(); return; }
+    memset(g_ctx.h_scalar, 0, LISD_NSCALARS * sizeof(double));
+    if (cudaMalloc((void **)&g_ctx.counter, 64) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaMemset(g_ctx.counter, 0, 64);
+    g_ctx.device = dev;
+    g_ctx.available = 1;
+}
+
+int lisd_available(void) { lisd_probe(); return g_ctx.available; }
+int lisd_device_id(void) { lisd_probe(); return g_ctx.device; }
+
+LIS_INT lisd_require(const char *what)
+{
+    if (lisd_available()) return LIS_SUCCESS;
+    LIS_SETERR1(LIS_ERR_DEVICE, "%s needs a CUDA device (sm_100a); lis_b200 has no CPU compute path\n", what);
+    return LIS_ERR_DEVICE;
+}
+
+void *lisd_stream(void) { lisd_probe(); return (void *)g_ctx.stream; }
+void lisd_mark_busy(void) { g_ctx.busy = 1; }
+
+LIS_INT lisd_check(int rc, const char *what)
+{
+    if (rc == 0) return LIS_SUCCESS;
+    if (rc == (int)cudaErrorMemoryAllocation) {
+        LIS_SETERR1(LIS_ERR_OUT_OF_MEMORY, "%s: out of device memory\n", what);
+        return LIS_ERR_OUT_OF_MEMORY;
+    }
+    LIS_SETERR2(LIS_ERR_DEVICE, "%s: CUDA error: %s\n", what, lisb200_error_string(rc));
+    return LIS_ERR_DEVICE;
+}
+
+LIS_INT lisd_sync(void)
+{
+    if (!g_ctx.available || !g_ctx.busy) return LIS_SUCCESS;
+    g_ctx.busy = 0;
+    return lisd_check((int)cudaStreamSynchronize(g_ctx.stream), "stream synchronize");
+}
+
+void lisd_shutdown(void)
+{
+    if (!g_ctx.available) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.partial) cudaFree(g_ctx.partial);
+    if (g_ctx.counter) cudaFree(g_ctx.counter);
+    if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
+    cudaStreamDestroy(g_ctx.stream);
+    memset(&g_ctx, 0, sizeof(g_ctx));
+}
+
+/* ---- memory ---------------------------------------------------------------------------- */
+LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
+{
+    size_t bytes = (count > 0 ? count : 1) * sizeof(LIS_SCALAR);
+    bytes = (bytes + 255) & ~(size_t)255;
+    *value = NULL;
+    if (lisd_available()) {
+        void *p = NULL;
+        cudaError_t e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
+        if (e != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+        *value = (LIS_SCALAR *)p;
+        *managed = 1;
+    } else {
+        /* no device: keep the data-structure API usable (I/O, conversion, tests of the host
+         * logic); every compute entry point still fails with LIS_ERR_DEVICE */
+        *value = (LIS_SCALAR *)malloc(bytes);
+        if (*value == NULL) { LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+        *managed = 0;
+    }
+    return LIS_SUCCESS;
+}
+
+void lisd_free_vector(LIS_SCALAR *value, LIS_INT managed)
+{
+    if (value == NULL) return;
+    if (managed) { lisd_sync(); cudaFree(value); }
+    else free(value);
+}
+
+LIS_INT lisd_malloc(void **p, size_t bytes)
+{
+    *p = NULL;
+    LIS_INT err = lisd_require("device allocation");
+    if (err) return err;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+    return LIS_SUCCESS;
+}
+
+void lisd_free(void *p) { if (p) { lisd_sync(); cudaFree(p); } }
+
+LIS_INT lisd_upload(void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return LIS_SUCCESS;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+    return lisd_check((int)e, "host to device copy");
+}
+
+LIS_INT lisd_download(void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return LIS_SUCCESS;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+    g_ctx.busy = 0;
+    return lisd_check((int)e, "device to host copy");
+}
+
+LIS_INT lisd_memset(void *dst, int byte, size_t bytes)
+{
+    if (bytes == 0) return LIS_SUCCESS;
+    g_ctx.busy = 1;
+    return lisd_check((int)cudaMemsetAsync(dst, byte, bytes, g_ctx.stream), "memset");
+}
+
+/* ---- vector residency ---------------------------------------------------------------------
+ * value[] is managed memory.  Kernels run at full HBM speed once the pages are on the device;
+ * we prefetch explicitly when the host may have touched the vector since the last kernel. */
+LIS_INT lisd_vec_device(LIS_VECTOR v)
+{
+    if (!v->b200_managed) {
+        LIS_SETERR(LIS_ERR_DEVICE, "vector storage is not device accessible\n");
+        return LIS_ERR_DEVICE;
+    }
+    if (v->b200_resident) return LIS_SUCCESS;
+    size_t bytes = v->b200_capacity * sizeof(LIS_SCALAR);
+    cudaError_t e = cudaMemPrefetchAsync(v->value, bytes, g_ctx.device, g_ctx.stream);
+    if (e != cudaSuccess) cudaGetLastError();      /* advisory only: page faults still work */
+    v->b200_resident = 1;
+    g_ctx.busy = 1;
+    return LIS_SUCCESS;
+}
+
+void lisd_vec_host(LIS_VECTOR v)
+{
+    lisd_sync();
+    if (v->b200_managed && v->b200_resident && g_ctx.available) {
+        /* bring the whole vector back in one bulk migration instead of page faults */
+        size_t bytes = v->b200_capacity * sizeof(LIS_SCALAR);
+        if (cudaMemPrefetchAsync(v->value, bytes, cudaCpuDeviceId, g_ctx.stream) == cudaSuccess)
+            cudaStreamSynchronize(g_ctx.stream);
+        else
+            cudaGetLastError();
+    }
+    v->b200_resident = 0;
+}
+
+/* ---- reductions ------------------------------------------------------------------------ */
+double *lisd_partial(size_t slots)
+{
+    if (slots < (size_t)lisb200_reduce_slots()) slots = (size_t)lisb200_reduce_slots();
+    if (slots > g_ctx.partial_slots) {
+        lisd_sync();
+        if (g_ctx.partial) cudaFree(g_ctx.partial);
+        g_ctx.partial = NULL; g_ctx.partial_slots = 0;
+        if (cudaMalloc((void **)&g_ctx.partial, slots * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return NULL;
+        }
+        g_ctx.partial_slots = slots;
+    }
+    return g_ctx.partial;
+}
+
+unsigned int *lisd_counter(void) { return g_ctx.counter; }
+double *lisd_scalar_dev(int slot) { return g_ctx.d_scalar + slot; }
+double lisd_scalar_get(int slot) { return ((volatile double *)g_ctx.h_scalar)[slot]; }

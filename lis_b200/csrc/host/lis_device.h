@@ -1,0 +1,115 @@
+/*
+ * lis_device.h -- private device runtime of lis_b200: one CUDA stream per process (one
+ * process per GPU), scratch for reductions, mapped pinned scalars for dot/nrm2 results,
+ * managed-memory vector storage and device mirrors of the matrix formats.
+ *
+ * Replaces, for the GPU, what the reference gets for free from a single address space:
+ * src/system/lis_memory.c (allocation) and the global reduction scratch lis_vec_tmp
+ * (src/system/lis_init.c:66).
+ */
+#ifndef LIS_B200_DEVICE_H
+#define LIS_B200_DEVICE_H
+
+#include "lislib.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LISD_NSCALARS 64          /* mapped host scalars available to kernels */
+
+/* ---- runtime ---- */
+int   lisd_available(void);                         /* 1 when a CUDA device is usable */
+LIS_INT lisd_require(const char *what);             /* LIS_SUCCESS or LIS_ERR_DEVICE (+message) */
+void *lisd_stream(void);
+void  lisd_mark_busy(void);                         /* a kernel was enqueued */
+LIS_INT lisd_sync(void);                            /* wait for the stream if busy */
+LIS_INT lisd_check(int cuda_rc, const char *what);  /* map a kernel-ABI return code */
+void  lisd_shutdown(void);
+int   lisd_device_id(void);
+
+/* ---- memory ---- */
+LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed);
+void    lisd_free_vector(LIS_SCALAR *value, LIS_INT managed);
+LIS_INT lisd_malloc(void **p, size_t bytes);        /* plain device memory */
+void    lisd_free(void *p);
+LIS_INT lisd_upload(void *dst, const void *src, size_t bytes);      /* H2D, synchronous */
+LIS_INT lisd_download(void *dst, const void *src, size_t bytes);    /* D2H, synchronous */
+LIS_INT lisd_memset(void *dst, int byte, size_t bytes);
+
+/* ---- vectors: residency tracking of managed storage ---- */
+LIS_INT lisd_vec_device(LIS_VECTOR v);              /* make resident before a kernel touches it */
+void    lisd_vec_host(LIS_VECTOR v);                /* host is about to read/write v->value */
+
+/* ---- reductions ---- */
+double       *lisd_partial(size_t slots);           /* device scratch, grown on demand */
+unsigned int *lisd_counter(void);
+double       *lisd_scalar_dev(int slot);            /* device alias of mapped scalar `slot` */
+double        lisd_scalar_get(int slot);            /* host value (after lisd_sync) */
+
+/* ---- matrix device mirror ---- */
+typedef struct lisd_csr {
+    int n, nnz;
+    int *ptr, *idx;
+    double *val;
+} lisd_csr;
+
+typedef struct lisd_matrix {
+    int type;                 /* LIS_MATRIX_* the mirror was built for */
+    int n, np;
+    lisd_csr csr;             /* CSR; for CSC: the row-major (transposed-storage) mirror */
+    /* ELL / DIA / JAD / BSR */
+    int maxnzr, nnd, ld, nr, bnr, bnc, bnnz;
+    int *idx, *off, *jptr, *perm, *bptr, *bidx;
+    double *val;
+    /* split parts */
+    int splited;
+    lisd_csr L, U;
+    double *diag;             /* D */
+    double *wd;               /* WD (scaled + inverted diagonal), when present */
+    void *sweep;              /* SSOR level schedule (lis_precon.c), built on first psolve */
+} lisd_matrix;
+
+LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out);   /* build on first use */
+void    lisd_matrix_drop(LIS_MATRIX A);                     /* invalidate / free */
+LIS_INT lisd_matrix_refresh_wd(LIS_MATRIX A);               /* after WD changed on the host */
+
+/* ---- internal async vector ops (no host sync; the public lis_vector_* wrap these) ---- */
+LIS_INT lisd_copy(LIS_VECTOR x, LIS_VECTOR y);
+LIS_INT lisd_axpy(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y);
+LIS_INT lisd_xpay(LIS_VECTOR x, LIS_SCALAR alpha, LIS_VECTOR y);
+LIS_INT lisd_axpyz(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR z);
+LIS_INT lisd_scale(LIS_SCALAR alpha, LIS_VECTOR x);
+LIS_INT lisd_set_all(LIS_SCALAR alpha, LIS_VECTOR x);
+LIS_INT lisd_pmul(LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR z);
+LIS_INT lisd_reduce(int kind, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *value);  /* syncs, allreduces */
+LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);                 /* async */
+void    lisd_sweep_free(void *sweep);
+
+/* ---- fused steps of the Krylov loops: one launch, one host wait, scalar(s) returned ---- */
+LIS_INT lisd_jacobi_dot(LIS_VECTOR r, LIS_VECTOR dinv, LIS_VECTOR z, LIS_SCALAR *rho);        /* z=r.*dinv; <r,z> */
+LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy);        /* y=Ax; <x,y> */
+LIS_INT lisd_cg_update(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_VECTOR x, LIS_VECTOR r, LIS_REAL *nrm2_r);
+LIS_INT lisd_dot2(LIS_VECTOR a, LIS_VECTOR b, LIS_SCALAR out[2]);                             /* <a,b>, <a,a> */
+/* finish a reduction whose kernel has been enqueued with result slot(s) 0..count-1:
+ * wait, read the mapped scalars, combine across ranks in rank order */
+LIS_INT lisd_reduce_finish(double *vals, int count, int is_max);
+
+/* ---- process group (row-partitioned multi-GPU) ---- */
+int     lisd_rank(void);
+int     lisd_nranks(void);
+LIS_INT lisd_comm_init(void);                       /* reads RANK/WORLD_SIZE/LOCAL_RANK */
+LIS_INT lisd_allreduce_sum(double *vals, int count);/* host scalars, in place, rank-ordered */
+LIS_INT lisd_allreduce_max(double *vals, int count);
+LIS_INT lisd_allgather_int(const int *mine, int count, int *all);
+LIS_INT lisd_allgatherv_host(double *value, const LIS_INT *ranges, int nprocs);  /* in place */
+LIS_INT lisd_commtable_create(LIS_MATRIX A);
+LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout);
+LIS_INT lisd_matrix_g2l(LIS_MATRIX A);              /* global -> local+halo column numbering */
+void    lisd_commtable_destroy(LIS_COMMTABLE t);
+LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x);   /* async on the stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

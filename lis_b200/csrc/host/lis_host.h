@@ -1,0 +1,45 @@
+/* lis_host.h -- private host-side helpers shared by the lis_b200 host sources. */
+#ifndef LIS_B200_HOST_H
+#define LIS_B200_HOST_H
+#include "lislib.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { char *name; char *value; } lis_arg_t;   /* "-name value" from argv, lower-cased */
+const lis_arg_t *lis_host_args(int *count);
+
+void lisd_comm_finalize(void);
+
+/* object header initialisation / copy (label, sizes, partition) */
+void lis_host_header_copy(const void *src, void *dst);
+
+/* CSR-level host helpers used by conversion, split and the SSOR schedule */
+LIS_INT lis_host_csr_from(LIS_MATRIX A, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value, LIS_INT *owned);
+
+LIS_INT lis_host_matrix_check_input(LIS_MATRIX A);
+void    lis_host_matrix_adopt(LIS_MATRIX dst, LIS_MATRIX src);
+LIS_INT lis_host_diag_create(LIS_MATRIX A, LIS_MATRIX_DIAG *Dout);
+LIS_INT lis_host_transpose(LIS_INT n, LIS_INT ncols, const LIS_INT *ptr, const LIS_INT *index, const LIS_SCALAR *value,
+                           LIS_INT **optr, LIS_INT **oindex, LIS_SCALAR **ovalue);
+
+/* emulated OpenMP thread count of the reference (-omp_num_threads N): the SSOR block count */
+int  lis_host_num_threads(void);
+void lis_host_set_num_threads(int n);
+
+/* preconditioner registry / solver helpers */
+LIS_INT lis_host_precon_type_end(void);
+LIS_INT lis_host_precon_lookup(const char *name);
+void    lis_host_print_rhistory(LIS_INT iter, LIS_REAL resid);
+LIS_INT lis_host_solver_malloc_work(LIS_SOLVER solver, LIS_INT worklen, LIS_INT first);
+LIS_INT lis_host_solver_residual(LIS_SOLVER solver, LIS_VECTOR r, LIS_REAL *res);
+LIS_INT lis_host_solver_shadow_residual(LIS_SOLVER solver, LIS_VECTOR r0, LIS_VECTOR rs0);
+
+/* vectors */
+LIS_INT lis_vector_check_same(LIS_VECTOR x, LIS_VECTOR y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

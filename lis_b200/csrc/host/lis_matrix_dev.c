@@ -1,0 +1,294 @@
+/*
+ * lis_matrix_dev.c -- device mirrors of LIS_MATRIX storage and the lis_matvec dispatcher.
+ *
+ * The public arrays of a matrix (A->ptr/index/value, ...) stay where the caller put them
+ * (host memory, same ownership rules as the reference, src/matrix/lis_matrix_csr.c:98-103).
+ * The first kernel that needs the matrix uploads a private copy into HBM; the mirror is
+ * dropped whenever the library itself changes the host arrays (sort, split, merge, convert,
+ * destroy).  A caller who edits A->value behind the library's back after the first SpMV
+ * must call lis_matrix_b200_invalidate(A).
+ *
+ * lis_matvec follows src/matvec/lis_matvec.c:55-187: argument check, halo exchange for
+ * row-partitioned matrices (LIS_MATVEC_SENDRECV, include/lis_matvec.h:31-44), then the
+ * per-format kernel.  Public entry points are host-synchronous because the reference drivers
+ * time them with lis_wtime() (test/spmvtest1.c:219-221).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "lis_device.h"
+#include "lis_host.h"
+#include "lis_b200_kernels.h"
+
+/* ------------------------------------------------------------------ upload helpers */
+static LIS_INT up(void **dst, const void *src, size_t bytes, size_t pad_bytes)
+{
+    LIS_INT err = lisd_malloc(dst, bytes + pad_bytes);
+    if (err) return err;
+    if (pad_bytes) { err = lisd_memset((char *)*dst + bytes, 0, pad_bytes); if (err) return err; }
+    return lisd_upload(*dst, src, bytes);
+}
+
+static void csr_free(lisd_csr *c)
+{
+    lisd_free(c->ptr); lisd_free(c->idx); lisd_free(c->val);
+    memset(c, 0, sizeof(*c));
+}
+
+/* idx/val are padded so that 128-bit loads starting at any multiple of 4 entries stay in
+ * bounds (the CSR kernel rounds its window start down to a multiple of 4) */
+static LIS_INT csr_upload(lisd_csr *c, int n, const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
+{
+    const size_t nnz = (size_t)ptr[n];
+    LIS_INT err;
+    memset(c, 0, sizeof(*c));
+    c->n = n; c->nnz = (int)nnz;
+    err = up((void **)&c->ptr, ptr, ((size_t)n + 1) * sizeof(int), 16);
+    if (!err) err = up((void **)&c->idx, idx, nnz * sizeof(int), 8 * sizeof(int));
+    if (!err) err = up((void **)&c->val, val, nnz * sizeof(double), 8 * sizeof(double));
+    if (err) csr_free(c);
+    return err;
+}
+
+static void mirror_free(lisd_matrix *M)
+{
+    if (M == NULL) return;
+    csr_free(&M->csr); csr_free(&M->L); csr_free(&M->U);
+    lisd_free(M->idx); lisd_free(M->off); lisd_free(M->jptr); lisd_free(M->perm);
+    lisd_free(M->bptr); lisd_free(M->bidx); lisd_free(M->val);
+    lisd_free(M->diag); lisd_free(M->wd);
+    if (M->sweep) lisd_sweep_free(M->sweep);
+    free(M);
+}
+
+void lisd_matrix_drop(LIS_MATRIX A)
+{
+    if (A->b200_dev) { mirror_free((lisd_matrix *)A->b200_dev); A->b200_dev = NULL; }
+}
+
+LIS_INT lis_matrix_b200_invalidate(LIS_MATRIX A)
+{
+    if (!lis_is_malloc(A)) return LIS_ERR_ILL_ARG;
+    lisd_matrix_drop(A);
+    return LIS_SUCCESS;
+}
+
+LIS_INT lisd_matrix_refresh_wd(LIS_MATRIX A)
+{
+    lisd_matrix *M = (lisd_matrix *)A->b200_dev;
+    if (M == NULL || A->WD == NULL) return LIS_SUCCESS;
+    if (M->wd == NULL) {
+        LIS_INT err = lisd_malloc((void **)&M->wd, (size_t)(A->n > 0 ? A->n : 1) * sizeof(double));
+        if (err) return err;
+    }
+    return lisd_upload(M->wd, A->WD->value, (size_t)A->n * sizeof(double));
+}
+
+LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out)
+{
+    LIS_INT err = lisd_require("matrix upload");
+    if (err) return err;
+    lisd_matrix *M = (lisd_matrix *)A->b200_dev;
+    if (M && M->type == A->matrix_type && M->splited == A->is_splited && M->n == A->n) { *out = M; return LIS_SUCCESS; }
+    if (M) lisd_matrix_drop(A);
+    M = (lisd_matrix *)calloc(1, sizeof(lisd_matrix));
+    if (M == NULL) { LIS_SETERR_MEM(sizeof(lisd_matrix)); return LIS_OUT_OF_MEMORY; }
+    const int n = A->n;
+    M->type = A->matrix_type; M->n = n; M->np = A->np; M->splited = A->is_splited;
+    err = LIS_SUCCESS;
+    if (A->is_splited) {
+        if (A->matrix_type != LIS_MATRIX_CSR) { free(M); LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
+        err = csr_upload(&M->L, n, A->L->ptr, A->L->index, A->L->value);
+        if (!err) err = csr_upload(&M->U, n, A->U->ptr, A->U->index, A->U->value);
+        if (!err) err = up((void **)&M->diag, A->D->value, (size_t)n * sizeof(double), 16);
+        if (!err && A->WD) err = up((void **)&M->wd, A->WD->value, (size_t)n * sizeof(double), 16);
+    } else {
+        switch (A->matrix_type) {
+        case LIS_MATRIX_CSR:
+            err = csr_upload(&M->csr, n, A->ptr, A->index, A->value);
+            break;
+        case LIS_MATRIX_CSC: {
+            /* y[idx[j]] += val[j]*x[i] over columns i ascending == row sums in ascending column
+             * order (src/matvec/lis_matvec_csc.c:128-144): the row-major transpose of the CSC
+             * arrays, run through the CSR kernel, adds the same products in the same order */
+            LIS_INT *tp, *ti;
+            LIS_SCALAR *tv;
+            err = lis_host_transpose(n, n, A->ptr, A->index, A->value, &tp, &ti, &tv);
+            if (!err) { err = csr_upload(&M->csr, n, tp, ti, tv); lis_free2(3, tp, ti, tv); }
+            break;
+        }
+        case LIS_MATRIX_ELL: {
+            const size_t cnt = (size_t)n * (size_t)A->maxnzr;
+            M->maxnzr = A->maxnzr; M->ld = n;
+            err = up((void **)&M->idx, A->index, cnt * sizeof(int), 16);
+            if (!err) err = up((void **)&M->val, A->value, cnt * sizeof(double), 16);
+            break;
+        }
+        case LIS_MATRIX_DIA: {
+            const size_t cnt = (size_t)n * (size_t)A->nnd;
+            M->nnd = A->nnd; M->ld = n;
+            err = up((void **)&M->off, A->index, (size_t)A->nnd * sizeof(int), 16);
+            if (!err) err = up((void **)&M->val, A->value, cnt * sizeof(double), 16);
+            break;
+        }
+        case LIS_MATRIX_JAD: {
+            const size_t nnz = (size_t)A->ptr[A->maxnzr];
+            M->maxnzr = A->maxnzr;
+            err = up((void **)&M->jptr, A->ptr, ((size_t)A->maxnzr + 1) * sizeof(int), 16);
+            if (!err) err = up((void **)&M->perm, A->row, (size_t)n * sizeof(int), 16);
+            if (!err) err = up((void **)&M->idx, A->index, nnz * sizeof(int), 16);
+            if (!err) err = up((void **)&M->val, A->value, nnz * sizeof(double), 16);
+            break;
+        }
+        case LIS_MATRIX_BSR: {
+            const size_t cnt = (size_t)A->bnnz * (size_t)A->bnr * (size_t)A->bnc;
+            M->nr = A->nr; M->bnr = A->bnr; M->bnc = A->bnc; M->bnnz = A->bnnz;
+            err = up((void **)&M->bptr, A->bptr, ((size_t)A->nr + 1) * sizeof(int), 16);
+            if (!err) err = up((void **)&M->bidx, A->bindex, (size_t)A->bnnz * sizeof(int), 16);
+            if (!err) err = up((void **)&M->val, A->value, cnt * sizeof(double), 16);
+            break;
+        }
+        default:
+            LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "storage format %D has no B200 kernel (CSR, CSC, ELL, DIA, JAD, BSR do)\n", A->matrix_type);
+            err = LIS_ERR_NOT_IMPLEMENTED;
+        }
+    }
+    if (err) { mirror_free(M); return err; }
+    A->b200_dev = M;
+    *out = M;
+    return LIS_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ y = A x */
+static LIS_INT matvec_launch(LIS_MATRIX A, lisd_matrix *M, const double *x, double *y)
+{
+    void *st = lisd_stream();
+    const int n = A->n;
+    int rc;
+    if (M->splited)
+        rc = lisb200_spmv_csr_split(n, M->diag, M->L.ptr, M->L.idx, M->L.val, M->U.ptr, M->U.idx, M->U.val, x, y, st);
+    else switch (M->type) {
+    case LIS_MATRIX_CSR:
+    case LIS_MATRIX_CSC: rc = lisb200_spmv_csr(n, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st); break;
+    case LIS_MATRIX_ELL: rc = lisb200_spmv_ell(n, M->maxnzr, M->ld, M->idx, M->val, x, y, st); break;
+    case LIS_MATRIX_DIA: rc = lisb200_spmv_dia(n, M->np, M->nnd, M->ld, M->off, M->val, x, y, st); break;
+    case LIS_MATRIX_JAD: rc = lisb200_spmv_jad(n, M->maxnzr, M->jptr, M->perm, M->idx, M->val, x, y, st); break;
+    case LIS_MATRIX_BSR: rc = lisb200_spmv_bsr(n, M->nr, M->bnr, M->bnc, M->bptr, M->bidx, M->val, x, y, st); break;
+    default: LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    lisd_mark_busy();
+    return lisd_check(rc, "lis_matvec");
+}
+
+/* grow x to np entries so the halo has somewhere to land (LIS_MATVEC_SENDRECV) */
+static LIS_INT vec_reserve(LIS_VECTOR x, size_t count)
+{
+    if (x->b200_capacity >= count) return LIS_SUCCESS;
+    LIS_SCALAR *nv;
+    LIS_INT managed, err;
+    err = lisd_alloc_vector(count, &nv, &managed);
+    if (err) return err;
+    if (!managed) { free(nv); LIS_SETERR(LIS_ERR_DEVICE, "no device\n"); return LIS_ERR_DEVICE; }
+    err = lisd_vec_device(x);
+    if (err) return err;
+    err = lisd_memset(nv, 0, count * sizeof(LIS_SCALAR));
+    if (!err) err = lisd_check(lisb200_copy(x->n, x->value, nv, lisd_stream()), "vector grow");
+    if (err) return err;
+    lisd_sync();
+    lisd_free_vector(x->value, x->b200_managed);
+    x->value = nv; x->b200_managed = 1; x->b200_capacity = count; x->b200_resident = 1;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
+{
+    LIS_INT err = lisd_require("lis_matvec");
+    if (err) return err;
+    if (x == y || x->value == y->value) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvec: x and y must not alias\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    lisd_matrix *M;
+    err = lisd_matrix_get(A, &M);
+    if (err) return err;
+    if (A->np > A->n) {
+        err = vec_reserve(x, (size_t)A->np + (size_t)A->pad_comm);
+        if (err) return err;
+    }
+    err = lisd_vec_device(x);
+    if (!err) err = lisd_vec_device(y);
+    if (err) return err;
+    if (A->nprocs > 1 && A->commtable) {
+        err = lisd_halo_exchange(A, x);
+        if (err) return err;
+    }
+    return matvec_launch(A, M, x->value, y->value);
+}
+
+/* y = A x and <x,y> in one pass where a fused kernel exists (unsplit CSR / CSC mirror) */
+LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy)
+{
+    lisd_matrix *M;
+    LIS_INT err = lisd_require("lis_matvec");
+    if (err) return err;
+    err = lisd_matrix_get(A, &M);
+    if (err) return err;
+    const int fusable = !M->splited && (M->type == LIS_MATRIX_CSR || M->type == LIS_MATRIX_CSC);
+    if (!fusable) {
+        err = lisd_matvec(A, x, y);
+        if (err) return err;
+        return lis_vector_dot(x, y, dot_xy);
+    }
+    if (x == y || x->value == y->value) { LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvec: x and y must not alias\n"); return LIS_ERR_ILL_ARG; }
+    if (A->np > A->n) { err = vec_reserve(x, (size_t)A->np + (size_t)A->pad_comm); if (err) return err; }
+    err = lisd_vec_device(x);
+    if (!err) err = lisd_vec_device(y);
+    if (err) return err;
+    if (A->nprocs > 1 && A->commtable) { err = lisd_halo_exchange(A, x); if (err) return err; }
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    err = lisd_check(lisb200_spmv_csr_dot(A->n, M->csr.ptr, M->csr.idx, M->csr.val, x->value, y->value, partial,
+                                          lisd_counter(), lisd_scalar_dev(0), lisd_stream()), "lis_matvec+dot");
+    if (err) return err;
+    return lisd_reduce_finish(dot_xy, 1, 0);
+}
+
+LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
+{
+    LIS_INT err = lis_host_matrix_check_input(A);
+    if (err) return err;
+    if (A->n != x->n || A->n != y->n) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvec: sizes of A, x and y do not match\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    err = lisd_matvec(A, x, y);
+    if (err) return err;
+    return lisd_sync();
+}
+
+/* transposed product: only what BiCG needs, served by a transposed CSR mirror is future
+ * work */
+LIS_INT lis_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
+{
+    (void)A; (void)x; (void)y;
+    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech (transposed SpMV) is outside the B200 hot path\n");
+    return LIS_ERR_NOT_IMPLEMENTED;
+}
+
+/* ---- per-format seam with raw pointers (include/lis_matvec.h:76-205 of the reference).
+ * x and y must be device-accessible: vector storage handed out by this library is. */
+static void raw_matvec(LIS_MATRIX A, LIS_INT type, LIS_SCALAR x[], LIS_SCALAR y[])
+{
+    lisd_matrix *M;
+    if (A->matrix_type != type) { LIS_SETERR(LIS_ERR_ILL_ARG, "matrix storage format does not match the kernel\n"); return; }
+    if (lisd_matrix_get(A, &M)) return;
+    if (matvec_launch(A, M, x, y)) return;
+    lisd_sync();
+}
+void lis_matvec_csr(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_CSR, x, y); }
+void lis_matvec_csc(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_CSC, x, y); }
+void lis_matvec_ell(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_ELL, x, y); }
+void lis_matvec_dia(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_DIA, x, y); }
+void lis_matvec_jad(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_JAD, x, y); }
+void lis_matvec_bsr(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_BSR, x, y); }

@@ -1,0 +1,346 @@
+/*
+ * lis_precon.c -- preconditioner setup and apply for the hot path: none, Jacobi, SSOR and
+ * user-registered ones (the reference's plugin API, lis_precon_register).
+ *
+ * Reference: src/precon/lis_precon.c:58-159 (dispatch tables, create), :410-460 (register),
+ * lis_precon_jacobi.c:60-147, lis_precon_ssor.c:57-115, and the triangular sweep
+ * lis_matrix_solve_csr(..., LIS_MATRIX_SSOR), src/matrix/lis_matrix_csr.c:1572-1630.
+ *
+ * SSOR on the GPU.  The reference's sweep is a sequential dependency chain per block, where
+ * a block is the row range of one OpenMP thread (LIS_GET_ISIE(thread, nthreads, n)) and
+ * couplings that leave the block are dropped; the serial build is the one-block case.  Here
+ * the block count is the emulated thread count (`-omp_num_threads N` on the command line,
+ * lis_initialize; default 1 = the serial reference), and inside the blocks rows are
+ * level-scheduled on the host once per matrix: all rows of a level are independent, one
+ * kernel launch per level, each row still subtracts its products in storage order, so the
+ * result is bit-identical to the CPU sweep with the same block partition.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "lis_device.h"
+#include "lis_host.h"
+#include "lis_b200_kernels.h"
+
+/* ------------------------------------------------------------------ registry */
+typedef struct {
+    LIS_INT precon_type;
+    char name[LIS_PRECONNAME_MAX + 1];
+    LIS_PRECON_CREATE_XXX pcreate;
+    LIS_PSOLVE_XXX psolve;
+    LIS_PSOLVEH_XXX psolveh;
+} lis_precon_reg_t;
+
+static lis_precon_reg_t *g_reg = NULL;
+static LIS_INT g_reg_type = LIS_PRECON_TYPE_USERDEF;
+
+LIS_INT lis_host_precon_type_end(void) { return g_reg_type; }
+
+LIS_INT lis_host_precon_lookup(const char *name)
+{
+    for (LIS_INT i = 0; g_reg && i < g_reg_type - LIS_PRECON_TYPE_USERDEF; i++)
+        if (strcmp(name, g_reg[i].name) == 0) return g_reg[i].precon_type;
+    return -1;
+}
+
+LIS_INT lis_precon_register(char *name, LIS_PRECON_CREATE_XXX pcreate, LIS_PSOLVE_XXX psolve, LIS_PSOLVEH_XXX psolveh)
+{
+    if (g_reg == NULL) {
+        g_reg = (lis_precon_reg_t *)lis_calloc(LIS_PRECON_REGISTER_MAX * sizeof(lis_precon_reg_t), "lis_precon_register::top");
+        if (g_reg == NULL) { LIS_SETERR_MEM(sizeof(lis_precon_reg_t)); return LIS_OUT_OF_MEMORY; }
+    }
+    const LIS_INT k = g_reg_type - LIS_PRECON_TYPE_USERDEF;
+    if (k == LIS_PRECON_REGISTER_MAX) {
+        LIS_SETERR(LIS_FAILS, "lis_precon_resister is max\n");
+        return LIS_FAILS;
+    }
+    g_reg[k].pcreate = pcreate; g_reg[k].psolve = psolve; g_reg[k].psolveh = psolveh;
+    g_reg[k].precon_type = g_reg_type;
+    strncpy(g_reg[k].name, name, LIS_PRECONNAME_MAX);
+    g_reg[k].name[LIS_PRECONNAME_MAX] = '\0';
+    for (char *p = g_reg[k].name; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    g_reg_type++;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_precon_register_free(void)
+{
+    if (g_reg) { lis_free(g_reg); g_reg = NULL; }
+    g_reg_type = LIS_PRECON_TYPE_USERDEF;
+    return LIS_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ create / destroy */
+static LIS_INT create_none(LIS_SOLVER solver, LIS_PRECON precon) { (void)solver; (void)precon; return LIS_SUCCESS; }
+
+/* D = 1/diag(A): src/precon/lis_precon_jacobi.c:60-86 */
+static LIS_INT create_jacobi(LIS_SOLVER solver, LIS_PRECON precon)
+{
+    LIS_INT err = lis_vector_duplicate(solver->A, &precon->D);
+    if (err) return err;
+    err = lis_matrix_get_diagonal(solver->A, precon->D);
+    if (err) return err;
+    return lis_vector_reciprocal(precon->D);
+}
+
+/* split A in place, WD = 1/(omega*D): src/precon/lis_precon_ssor.c:57-95,
+ * src/matrix/lis_matrix_diag.c:663-672 (scale: value = alpha*value), :775-783 (inverse: 1.0/value) */
+static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
+{
+    LIS_MATRIX A = solver->A;
+    const LIS_SCALAR w = solver->params[LIS_PARAMS_SSOR_OMEGA - LIS_OPTIONS_LEN];
+    LIS_INT err = lis_matrix_convert_self(solver);
+    if (err) return err;
+    err = lis_matrix_split(A);
+    if (err) return err;
+    if (A->use_wd != LIS_SOLVER_SOR) {
+        if (!A->WD) {
+            err = lis_host_diag_create(A, &A->WD);
+            if (err) return err;
+        }
+        for (LIS_INT i = 0; i < A->n; i++) {
+            LIS_SCALAR v = A->D->value[i];
+            v = w * v;
+            A->WD->value[i] = 1.0 / v;
+        }
+        A->use_wd = LIS_SOLVER_SOR;
+        err = lisd_matrix_refresh_wd(A);
+        if (err) return err;
+    }
+    precon->A = A;
+    precon->is_copy = LIS_FALSE;
+    return LIS_SUCCESS;
+}
+
+static LIS_INT create_unsupported(LIS_SOLVER solver, LIS_PRECON precon)
+{
+    (void)solver; (void)precon;
+    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is outside the B200 hot path (none, jacobi, ssor and registered ones are available)\n");
+    return LIS_ERR_NOT_IMPLEMENTED;
+}
+
+LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
+{
+    const LIS_INT type = solver->options[LIS_OPTIONS_PRECON];
+    LIS_INT err;
+    *precon = (LIS_PRECON)lis_calloc(sizeof(struct LIS_PRECON_STRUCT), "lis_precon_create::precon");
+    if (*precon == NULL) { LIS_SETERR_MEM(sizeof(struct LIS_PRECON_STRUCT)); return LIS_OUT_OF_MEMORY; }
+    (*precon)->precon_type = type;
+    if (type >= LIS_PRECON_TYPE_USERDEF) {
+        if (type >= g_reg_type || g_reg == NULL) err = create_unsupported(solver, *precon);
+        else err = g_reg[type - LIS_PRECON_TYPE_USERDEF].pcreate(solver, *precon);
+    } else if (type && solver->options[LIS_OPTIONS_ADDS]) {
+        err = create_unsupported(solver, *precon);          /* additive Schwarz: out of scope */
+    } else switch (type) {
+    case LIS_PRECON_TYPE_NONE: err = create_none(solver, *precon); break;
+    case LIS_PRECON_TYPE_JACOBI: err = create_jacobi(solver, *precon); break;
+    case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
+    default: err = create_unsupported(solver, *precon); break;
+    }
+    if (err) { lis_precon_destroy(*precon); *precon = NULL; return err; }
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_precon_destroy(LIS_PRECON precon)
+{
+    if (precon) {
+        if (precon->is_copy && precon->A) lis_matrix_destroy(precon->A);
+        if (precon->D) lis_vector_destroy(precon->D);
+        if (precon->work) {
+            for (LIS_INT i = 0; i < precon->worklen; i++) lis_vector_destroy(precon->work[i]);
+            lis_free(precon->work);
+        }
+        lis_free(precon);
+    }
+    return LIS_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ apply */
+LIS_INT lis_psolve_none(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    (void)solver;
+    return lisd_copy(b, x);
+}
+
+/* x = b .* D (a multiply, not a divide): src/precon/lis_precon_jacobi.c:119-126 */
+LIS_INT lis_psolve_jacobi(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    return lisd_pmul(b, solver->precon->D, x);
+}
+
+LIS_INT lis_psolve_ssor(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    return lis_matrix_solve(solver->precon->A, b, x, LIS_MATRIX_SSOR);
+}
+
+/* the lis_psolve macro of the reference (include/lis_precon.h:32) as a function; async */
+LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    const LIS_INT type = solver->precon->precon_type;
+    switch (type) {
+    case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
+    case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
+    case LIS_PRECON_TYPE_SSOR: return lis_psolve_ssor(solver, b, x);
+    default:
+        if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg)
+            return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolve(solver, b, x);
+        LIS_SETERR_IMP;
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+}
+
+/* ------------------------------------------------------------------ SSOR level schedule */
+typedef struct lisd_sweep {
+    int n, nblocks;
+    int nlev_f, nlev_b;
+    int *h_fptr, *h_bptr;          /* host: level -> [start,end) in rows arrays */
+    int *d_frows, *d_brows;        /* device: rows ordered by level */
+    int *d_blk_start, *d_blk_end;  /* device: per row, the owning block's range */
+} lisd_sweep;
+
+void lisd_sweep_free(void *p)
+{
+    lisd_sweep *S = (lisd_sweep *)p;
+    if (S == NULL) return;
+    free(S->h_fptr); free(S->h_bptr);
+    lisd_free(S->d_frows); lisd_free(S->d_brows); lisd_free(S->d_blk_start); lisd_free(S->d_blk_end);
+    free(S);
+}
+
+/* counting sort of rows by level; returns level pointers */
+static int *order_by_level(int n, const int *lvl, int nlev, int *rows)
+{
+    int *ptr = (int *)calloc((size_t)nlev + 2, sizeof(int));
+    if (!ptr) return NULL;
+    for (int i = 0; i < n; i++) ptr[lvl[i] + 1]++;
+    for (int l = 0; l < nlev; l++) ptr[l + 1] += ptr[l];
+    int *cur = (int *)malloc(((size_t)nlev + 1) * sizeof(int));
+    if (!cur) { free(ptr); return NULL; }
+    memcpy(cur, ptr, ((size_t)nlev + 1) * sizeof(int));
+    for (int i = 0; i < n; i++) rows[cur[lvl[i]]++] = i;
+    free(cur);
+    return ptr;
+}
+
+/* SSOR block count = emulated OpenMP thread count, at most one block per row */
+static int sweep_blocks(int n)
+{
+    int nb = lis_host_num_threads();
+    if (nb < 1) nb = 1;
+    if (nb > n && n > 0) nb = n;
+    return nb;
+}
+
+static LIS_INT sweep_build(LIS_MATRIX A, lisd_sweep **out)
+{
+    const int n = A->n;
+    const int nb = sweep_blocks(n);
+    lisd_sweep *S = (lisd_sweep *)calloc(1, sizeof(lisd_sweep));
+    int *bs = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int *be = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int *lvl = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int *rows = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    LIS_INT err = LIS_OUT_OF_MEMORY;
+    if (!S || !bs || !be || !lvl || !rows) goto fail;
+    S->n = n; S->nblocks = nb;
+    for (int k = 0; k < nb; k++) {
+        LIS_INT is, ie;
+        LIS_GET_ISIE(k, nb, n, is, ie);
+        for (LIS_INT i = is; i < ie; i++) { bs[i] = is; be[i] = ie; }
+    }
+    /* forward: row i waits for every L neighbour inside its block */
+    int nlev = 0;
+    for (int i = 0; i < n; i++) {
+        int l = 0;
+        for (LIS_INT j = A->L->ptr[i]; j < A->L->ptr[i + 1]; j++) {
+            const int jj = A->L->index[j];
+            if (jj < bs[i]) continue;
+            if (lvl[jj] + 1 > l) l = lvl[jj] + 1;
+        }
+        lvl[i] = l;
+        if (l + 1 > nlev) nlev = l + 1;
+    }
+    S->nlev_f = nlev;
+    S->h_fptr = order_by_level(n, lvl, nlev, rows);
+    if (!S->h_fptr) goto fail;
+    err = lisd_malloc((void **)&S->d_frows, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_upload(S->d_frows, rows, sizeof(int) * (size_t)n);
+    if (err) goto fail;
+    /* backward: row i waits for every U neighbour inside its block */
+    nlev = 0;
+    for (int i = n - 1; i >= 0; i--) {
+        int l = 0;
+        for (LIS_INT j = A->U->ptr[i]; j < A->U->ptr[i + 1]; j++) {
+            const int jj = A->U->index[j];
+            if (jj < bs[i] || jj >= be[i]) continue;
+            if (lvl[jj] + 1 > l) l = lvl[jj] + 1;
+        }
+        lvl[i] = l;
+        if (l + 1 > nlev) nlev = l + 1;
+    }
+    S->nlev_b = nlev;
+    S->h_bptr = order_by_level(n, lvl, nlev, rows);
+    err = LIS_OUT_OF_MEMORY;
+    if (!S->h_bptr) goto fail;
+    err = lisd_malloc((void **)&S->d_brows, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_upload(S->d_brows, rows, sizeof(int) * (size_t)n);
+    if (!err) err = lisd_malloc((void **)&S->d_blk_start, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_upload(S->d_blk_start, bs, sizeof(int) * (size_t)n);
+    if (!err) err = lisd_malloc((void **)&S->d_blk_end, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_upload(S->d_blk_end, be, sizeof(int) * (size_t)n);
+    if (err) goto fail;
+    free(bs); free(be); free(lvl); free(rows);
+    *out = S;
+    return LIS_SUCCESS;
+fail:
+    free(bs); free(be); free(lvl); free(rows);
+    lisd_sweep_free(S);
+    if (err == LIS_OUT_OF_MEMORY) LIS_SETERR_MEM(n);
+    return err;
+}
+
+/* x = M^-1 b; async on the library stream */
+LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
+{
+    LIS_INT err = lisd_require("lis_matrix_solve");
+    if (err) return err;
+    if (flag != LIS_MATRIX_SSOR) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_solve: only the SSOR sweep is part of the B200 hot path\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    if (!A->is_splited) { err = lis_matrix_split(A); if (err) return err; }
+    if (A->WD == NULL) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matrix_solve: the scaled diagonal WD is not set up\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    lisd_matrix *M;
+    err = lisd_matrix_get(A, &M);
+    if (err) return err;
+    if (M->wd == NULL) { err = lisd_matrix_refresh_wd(A); if (err) return err; }
+    if (M->sweep == NULL || ((lisd_sweep *)M->sweep)->nblocks != sweep_blocks(A->n)) {
+        lisd_sweep *S;
+        if (M->sweep) { lisd_sweep_free(M->sweep); M->sweep = NULL; }
+        err = sweep_build(A, &S);
+        if (err) return err;
+        M->sweep = S;
+    }
+    lisd_sweep *S = (lisd_sweep *)M->sweep;
+    err = lisd_vec_device(b);
+    if (!err) err = lisd_vec_device(x);
+    if (err) return err;
+    void *st = lisd_stream();
+    lisd_mark_busy();
+    for (int l = 0; l < S->nlev_f; l++) {
+        const int s = S->h_fptr[l], cnt = S->h_fptr[l + 1] - s;
+        err = lisd_check(lisb200_ssor_forward_level(cnt, S->d_frows + s, M->L.ptr, M->L.idx, M->L.val, M->wd,
+                                                    S->d_blk_start, b->value, x->value, st), "SSOR forward sweep");
+        if (err) return err;
+    }
+    for (int l = 0; l < S->nlev_b; l++) {
+        const int s = S->h_bptr[l], cnt = S->h_bptr[l + 1] - s;
+        err = lisd_check(lisb200_ssor_backward_level(cnt, S->d_brows + s, M->U.ptr, M->U.idx, M->U.val, M->wd,
+                                                     S->d_blk_start, S->d_blk_end, x->value, st), "SSOR backward sweep");
+        if (err) return err;
+    }
+    return LIS_SUCCESS;
+}

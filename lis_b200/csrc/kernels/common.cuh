@@ -1,0 +1,106 @@
+// common.cuh -- shared device helpers for the lis_b200 sm_100a kernels.
+//
+// Arithmetic discipline: every fp64 multiply/add that must match the reference's CPU path is
+// spelled with the round-to-nearest intrinsics (__dmul_rn/__dadd_rn/...), which the compiler
+// never contracts into FMA.  The translation units are additionally built with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LISB_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+namespace lisb {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+// streaming (read-once) loads: bypass L1 allocation so the gathered x keeps the L1
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream4(const int4 *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// ---- deterministic block reduction (sum or max) ------------------------------------------
+// Fixed shape: xor-shuffle tree inside each warp, then warp 0 combines the per-warp values
+// with the same tree.  The result is valid in thread 0.
+template <bool kMax>
+__device__ __forceinline__ double combine(double a, double b) {
+    if (kMax) return a > b ? a : b;
+    return __dadd_rn(a, b);
+}
+template <bool kMax>
+__device__ __forceinline__ double warp_reduce(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = combine<kMax>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <bool kMax, int kThreads>
+__device__ __forceinline__ double block_reduce(double v, double *smem /* >= 32 doubles */) {
+    constexpr int nw = kThreads / kWarp;
+    v = warp_reduce<kMax>(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();                       // smem may still be in use by a previous reduction
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? smem[lane] : (kMax ? 0.0 : 0.0);
+        t = warp_reduce<kMax>(t);
+        v = t;
+    }
+    return v;
+}
+
+// ---- grid-level finish: every CTA stores one partial, the last CTA to arrive folds them ---
+// The fold order depends only on (nparts, kThreads), never on which CTA happens to be last:
+// thread t sums partial[t], partial[t+kThreads], ... sequentially, then block_reduce.
+template <bool kMax, int kThreads, int kOut>
+__device__ __forceinline__ void grid_finish(const double (&mine)[kOut], double *partial,
+                                            unsigned int *counter, double *result,
+                                            double *smem, bool sqrt_first = false) {
+    __shared__ bool is_last;
+    const unsigned int nparts = gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kOut; ++k) partial[(size_t)k * nparts + blockIdx.x] = mine[k];
+        __threadfence();
+        unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == nparts - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < kOut; ++k) {
+        double t = 0.0;
+        const volatile double *p = partial + (size_t)k * nparts;
+        for (unsigned int i = threadIdx.x; i < nparts; i += kThreads) t = combine<kMax>(t, p[i]);
+        t = block_reduce<kMax, kThreads>(t, smem);
+        if (threadIdx.x == 0) result[k] = t;
+    }
+    if (threadIdx.x == 0) {
+        *counter = 0u;                      // ready for the next reduction on this stream
+        __threadfence_system();             // result may live in mapped host memory
+    }
+}
+
+}  // namespace lisb

@@ -1,0 +1,362 @@
+// spmv.cu -- y = A x for the six storage formats of the hot path (CSR, ELL, DIA, JAD, BSR;
+// CSC is served by the CSR kernel on a transposed device mirror, see host/lis_matrix_dev.c).
+//
+// Design (B200, HBM-bound, fp64, int32 indices):
+//  * CSR  : "row-block / product-tile" kernel.  A CTA owns kRows consecutive rows, i.e. one
+//           CONTIGUOUS slice of idx[]/val[].  Phase 1 streams that slice with 128-bit coalesced
+//           loads (4 idx + 4 val per thread per step), gathers x through the read-only path and
+//           parks the rounded products in shared memory.  Phase 2 lets thread r walk row r's
+//           products in storage order.  The expensive part (HBM stream + gather) is perfectly
+//           coalesced and load-balanced regardless of row length; the ordered sum is what makes
+//           the result bit-identical to the reference loop (src/matvec/lis_matvec_csr.c:98-109).
+//           Rows longer than a tile simply span several tiles with the accumulator kept in a
+//           register.
+//  * ELL/DIA/JAD : column-major sweeps, thread per row, every load coalesced.
+//  * BSR  : thread per block row, template on (bnr,bnc) for the 4x4 table of the reference.
+#include "common.cuh"
+#include "../../../include/lis_b200_kernels.h"
+
+namespace lisb {
+
+constexpr int kCsrThreads = 256;          // threads per CTA == rows per CTA
+constexpr int kCsrTile    = 2048;         // products per shared-memory tile (16 KB)
+
+// Accumulate, for row `r` of this CTA's row block [r0, rend), the products of one CSR piece
+// (ptr/idx/val) in storage order into `acc`.  All threads of the CTA must call it.
+__device__ __forceinline__ double csr_block_accumulate(
+        double acc, int r0, int rend, int r, bool row_ok,
+        const int *__restrict__ ptr, const int *__restrict__ idx, const double *__restrict__ val,
+        const double *__restrict__ x, double *prod /* kCsrTile doubles of smem */)
+{
+    const int tid = threadIdx.x;
+    const int a0 = __ldg(ptr + r0);
+    const int a1 = __ldg(ptr + rend);
+    int ps = a1, pe = a1;
+    if (row_ok) { ps = __ldg(ptr + r); pe = __ldg(ptr + r + 1); }
+
+    for (int w = a0 & ~3; w < a1; w += kCsrTile) {
+        // ---- phase 1: products of window [w, w+kCsrTile) ∩ [a0, a1) ------------------------
+#pragma unroll
+        for (int k = 0; k < kCsrTile / (4 * kCsrThreads); ++k) {
+            const int j = w + 4 * (tid + k * kCsrThreads);
+            if (j < a1) {            // arrays are readable up to nnz rounded up to 4 entries
+                const int4    c  = ld_stream4(reinterpret_cast<const int4 *>(idx + j));
+                const double2 v0 = ld_stream2(reinterpret_cast<const double2 *>(val + j));
+                const double2 v1 = ld_stream2(reinterpret_cast<const double2 *>(val + j + 2));
+                // entries outside [a0,a1) belong to other CTAs (or are padding): their column
+                // may be anything, so clamp the gather address instead of branching.
+                const bool k0 = (j     >= a0) & (j     < a1);
+                const bool k1 = (j + 1 >= a0) & (j + 1 < a1);
+                const bool k2 = (j + 2 >= a0) & (j + 2 < a1);
+                const bool k3 = (j + 3 >= a0) & (j + 3 < a1);
+                const double x0 = __ldg(x + (k0 ? c.x : 0));
+                const double x1 = __ldg(x + (k1 ? c.y : 0));
+                const double x2 = __ldg(x + (k2 ? c.z : 0));
+                const double x3 = __ldg(x + (k3 ? c.w : 0));
+                double2 p0, p1;
+                p0.x = mul(v0.x, x0); p0.y = mul(v0.y, x1);
+                p1.x = mul(v1.x, x2); p1.y = mul(v1.y, x3);
+                double2 *dst = reinterpret_cast<double2 *>(prod + (j - w));
+                dst[0] = p0; dst[1] = p1;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: ordered row sums ---------------------------------------------------
+        const int wend = w + kCsrTile;
+        const int s = ps > w ? ps : w;
+        const int e = pe < wend ? pe : wend;
+        for (int j = s; j < e; ++j) acc = add(acc, prod[j - w]);
+        __syncthreads();
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kCsrThreads)
+csr_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx,
+           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    __shared__ __align__(16) double prod[kCsrTile];
+    const int r0 = blockIdx.x * kCsrThreads;
+    const int rend = min(r0 + kCsrThreads, n);
+    const int r = r0 + threadIdx.x;
+    const bool ok = r < n;
+    double acc = csr_block_accumulate(0.0, r0, rend, r, ok, ptr, idx, val, x, prod);
+    if (ok) y[r] = acc;
+}
+
+// split order: t = D[i]*x[i]; t += L row; t += U row   (src/matvec/lis_matvec_csr.c:69-86)
+__global__ void __launch_bounds__(kCsrThreads)
+csr_split_kernel(int n, const double *__restrict__ diag,
+                 const int *__restrict__ lptr, const int *__restrict__ lidx, const double *__restrict__ lval,
+                 const int *__restrict__ uptr, const int *__restrict__ uidx, const double *__restrict__ uval,
+                 const double *__restrict__ x, double *__restrict__ y)
+{
+    __shared__ __align__(16) double prod[kCsrTile];
+    const int r0 = blockIdx.x * kCsrThreads;
+    const int rend = min(r0 + kCsrThreads, n);
+    const int r = r0 + threadIdx.x;
+    const bool ok = r < n;
+    double acc = ok ? mul(diag[r], x[r]) : 0.0;
+    acc = csr_block_accumulate(acc, r0, rend, r, ok, lptr, lidx, lval, x, prod);
+    acc = csr_block_accumulate(acc, r0, rend, r, ok, uptr, uidx, uval, x, prod);
+    if (ok) y[r] = acc;
+}
+
+// y = A x and, in the same pass, sum_i x[i]*y[i]  (q = A p ; <p,q> of CG)
+__global__ void __launch_bounds__(kCsrThreads)
+csr_dot_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx,
+               const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+               double *partial, unsigned int *counter, double *result)
+{
+    __shared__ __align__(16) double prod[kCsrTile];
+    __shared__ double red[32];
+    const int r0 = blockIdx.x * kCsrThreads;
+    const int rend = min(r0 + kCsrThreads, n);
+    const int r = r0 + threadIdx.x;
+    const bool ok = r < n;
+    double acc = csr_block_accumulate(0.0, r0, rend, r, ok, ptr, idx, val, x, prod);
+    double d = 0.0;
+    if (ok) { y[r] = acc; d = mul(x[r], acc); }
+    double mine[1] = { block_reduce<false, kCsrThreads>(d, red) };
+    grid_finish<false, kCsrThreads, 1>(mine, partial, counter, result, red);
+}
+
+// ---- ELL -------------------------------------------------------------------------------
+// y[i] = 0; for j<maxnzr: y[i] += value[j*ld+i]*x[index[j*ld+i]]  (lis_matvec_ell.c:110-128)
+__global__ void __launch_bounds__(256)
+ell_kernel(int n, int maxnzr, int ld, const int *__restrict__ idx, const double *__restrict__ val,
+           const double *__restrict__ x, double *__restrict__ y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    int j = 0;
+    for (; j + 4 <= maxnzr; j += 4) {       // 4 independent idx/val streams in flight
+        const size_t o = (size_t)j * ld + i;
+        const int c0 = ld_stream(idx + o), c1 = ld_stream(idx + o + ld);
+        const int c2 = ld_stream(idx + o + 2 * (size_t)ld), c3 = ld_stream(idx + o + 3 * (size_t)ld);
+        const double v0 = ld_stream(val + o), v1 = ld_stream(val + o + ld);
+        const double v2 = ld_stream(val + o + 2 * (size_t)ld), v3 = ld_stream(val + o + 3 * (size_t)ld);
+        const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+        t = add(t, mul(v0, x0)); t = add(t, mul(v1, x1));
+        t = add(t, mul(v2, x2)); t = add(t, mul(v3, x3));
+    }
+    for (; j < maxnzr; ++j) {
+        const size_t o = (size_t)j * ld + i;
+        t = add(t, mul(ld_stream(val + o), __ldg(x + ld_stream(idx + o))));
+    }
+    y[i] = t;
+}
+
+// ---- DIA -------------------------------------------------------------------------------
+// y[i] = 0; for each diagonal j with offset off[j]: rows max(0,-off) <= i < min(n, xlen-off)
+//   y[i] += value[j*ld+i]*x[i+off]                                (lis_matvec_dia.c:150-172)
+constexpr int kDiaMaxOff = 64;
+__global__ void __launch_bounds__(256)
+dia_kernel(int n, int xlen, int nnd, int ld, const int *__restrict__ off,
+           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    __shared__ int soff[kDiaMaxOff];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double t = 0.0;
+    for (int j0 = 0; j0 < nnd; j0 += kDiaMaxOff) {
+        const int nj = min(kDiaMaxOff, nnd - j0);
+        __syncthreads();
+        if (threadIdx.x < nj) soff[threadIdx.x] = off[j0 + threadIdx.x];
+        __syncthreads();
+        if (i < n) {
+#pragma unroll 4
+            for (int j = 0; j < nj; ++j) {
+                const int o = soff[j];
+                const int c = i + o;
+                if (c >= 0 && c < xlen)
+                    t = add(t, mul(ld_stream(val + (size_t)(j0 + j) * ld + i), __ldg(x + c)));
+            }
+        }
+    }
+    if (i < n) y[i] = t;
+}
+
+// ---- JAD -------------------------------------------------------------------------------
+// w[i] = sum_j value[jptr[j]+i]*x[index[jptr[j]+i]] for all j with i < jptr[j+1]-jptr[j];
+// y[perm[i]] = w[i]                                                (lis_matvec_jad.c:171-196)
+__global__ void __launch_bounds__(256)
+jad_kernel(int n, int maxnzr, const int *__restrict__ jptr, const int *__restrict__ perm,
+           const int *__restrict__ idx, const double *__restrict__ val,
+           const double *__restrict__ x, double *__restrict__ y)
+{
+    extern __shared__ int sjp[];            // maxnzr+1 entries (or 0 when it does not fit)
+    const bool cached = (maxnzr + 1) * (int)sizeof(int) <= 16384;
+    if (cached) {
+        for (int j = threadIdx.x; j <= maxnzr; j += blockDim.x) sjp[j] = jptr[j];
+        __syncthreads();
+    }
+    const int *jp = cached ? sjp : jptr;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    // jagged diagonals have non-increasing length, so row i is in diagonals 0..k-1
+    for (int j = 0; j < maxnzr; ++j) {
+        const int s = jp[j];
+        if (i >= jp[j + 1] - s) break;
+        const size_t o = (size_t)s + i;
+        t = add(t, mul(ld_stream(val + o), __ldg(x + ld_stream(idx + o))));
+    }
+    y[perm[i]] = t;
+}
+
+// ---- BSR -------------------------------------------------------------------------------
+// per block row bi: t[0..bnr) = 0; for each block bc (storage order): for j<bnc, for i<bnr:
+//   t[i] += value[bc*bs + j*bnr + i] * x[bindex[bc]*bnc + j]       (lis_matvec_bsr.c:134-146)
+// The unrolled RxC kernels of the reference accumulate each t[i] in exactly this order.
+template <int R, int C>
+__global__ void __launch_bounds__(128)
+bsr_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
+           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nr) return;
+    double t[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) t[i] = 0.0;
+    const int s = __ldg(bptr + bi), e = __ldg(bptr + bi + 1);
+    for (int bc = s; bc < e; ++bc) {
+        const int bj = __ldg(bidx + bc) * C;
+        const double *v = val + (size_t)bc * (R * C);
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const double xj = __ldg(x + bj + j);
+#pragma unroll
+            for (int i = 0; i < R; ++i) t[i] = add(t[i], mul(__ldg(v + j * R + i), xj));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if (bi * R + i < n) y[bi * R + i] = t[i];
+}
+
+// generic block size (bnr or bnc > 4): one thread per scalar row, same per-row order
+__global__ void __launch_bounds__(256)
+bsr_generic_kernel(int n, int nr, int bnr, int bnc, const int *__restrict__ bptr,
+                   const int *__restrict__ bidx, const double *__restrict__ val,
+                   const double *__restrict__ x, double *__restrict__ y)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int bi = row / bnr, i = row - bi * bnr;
+    const int bs = bnr * bnc;
+    double t = 0.0;
+    const int s = __ldg(bptr + bi), e = __ldg(bptr + bi + 1);
+    for (int bc = s; bc < e; ++bc) {
+        const int bj = __ldg(bidx + bc) * bnc;
+        const double *v = val + (size_t)bc * bs + i;
+        for (int j = 0; j < bnc; ++j) t = add(t, mul(__ldg(v + (size_t)j * bnr), __ldg(x + bj + j)));
+    }
+    y[row] = t;
+}
+
+template <int R>
+static int launch_bsr_c(int n, int nr, int bnc, const int *bptr, const int *bidx, const double *val,
+                        const double *x, double *y, cudaStream_t st)
+{
+    const int grid = (nr + 127) / 128;
+    switch (bnc) {
+    case 1: bsr_kernel<R, 1><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 2: bsr_kernel<R, 2><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 3: bsr_kernel<R, 3><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 4: bsr_kernel<R, 4><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    default: return -1;
+    }
+    return 0;
+}
+
+}  // namespace lisb
+
+using namespace lisb;
+
+extern "C" int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_val,
+                                const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0) return 0;
+    const int grid = (n + kCsrThreads - 1) / kCsrThreads;
+    csr_kernel<<<grid, kCsrThreads, 0, (cudaStream_t)stream>>>(n, d_ptr, d_idx, d_val, d_x, d_y);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_spmv_csr_split(int n, const double *d_diag,
+                                      const int *d_lptr, const int *d_lidx, const double *d_lval,
+                                      const int *d_uptr, const int *d_uidx, const double *d_uval,
+                                      const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0) return 0;
+    const int grid = (n + kCsrThreads - 1) / kCsrThreads;
+    csr_split_kernel<<<grid, kCsrThreads, 0, (cudaStream_t)stream>>>(
+        n, d_diag, d_lptr, d_lidx, d_lval, d_uptr, d_uidx, d_uval, d_x, d_y);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_spmv_csr_dot(int n, const int *d_ptr, const int *d_idx, const double *d_val,
+                                    const double *d_x, double *d_y, double *d_partial,
+                                    unsigned int *d_counter, double *d_result, void *stream)
+{
+    if (n <= 0) return 0;
+    const int grid = (n + kCsrThreads - 1) / kCsrThreads;
+    csr_dot_kernel<<<grid, kCsrThreads, 0, (cudaStream_t)stream>>>(
+        n, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_spmv_ell(int n, int maxnzr, int ld, const int *d_idx, const double *d_val,
+                                const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0) return 0;
+    ell_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, maxnzr, ld, d_idx, d_val, d_x, d_y);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *d_off,
+                                const double *d_val, const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0) return 0;
+    dia_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, xlen, nnd, ld, d_off, d_val, d_x, d_y);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_spmv_jad(int n, int maxnzr, const int *d_jptr, const int *d_perm,
+                                const int *d_idx, const double *d_val,
+                                const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0) return 0;
+    size_t sm = (size_t)(maxnzr + 1) * sizeof(int);
+    if (sm > 16384) sm = 0;
+    jad_kernel<<<(n + 255) / 256, 256, sm, (cudaStream_t)stream>>>(n, maxnzr, d_jptr, d_perm, d_idx, d_val, d_x, d_y);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bptr,
+                                const int *d_bidx, const double *d_val,
+                                const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0 || nr <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = -1;
+    if (bnc >= 1 && bnc <= 4) {
+        switch (bnr) {
+        case 1: rc = launch_bsr_c<1>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 2: rc = launch_bsr_c<2>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 3: rc = launch_bsr_c<3>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 4: rc = launch_bsr_c<4>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        default: break;
+        }
+    }
+    if (rc != 0)
+        bsr_generic_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, nr, bnr, bnc, d_bptr, d_bidx, d_val, d_x, d_y);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,66 @@
+"""Regenerates tests/golden/*.npz from the REAL reference (oracle/_ref/libref_shim_serial.so,
+compiled from /root/reference by oracle/Makefile).  Run in the build container:
+    python tests/golden/make_golden.py
+The fixtures are small (a few hundred KB) and committed, because /root/reference does not
+exist on the GPU box."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import harness as H  # noqa: E402
+
+FORMATS = ["csr", "csc", "ell", "dia", "jad", "bsr"]
+
+
+def main():
+    H.ensure_built()
+    ref = H.ref_shim("serial")
+    assert ref is not None, "build oracle/_ref first (needs /root/reference)"
+    cases = {
+        "poisson1d_300": (H.poisson1d(300), False),
+        "poisson3d_7pt_9x8x7_sorted": (H.poisson3d_7pt(9, 8, 7), True),      # spmvtest3.c sorts the rows
+        "poisson3d_27pt_6x6x5": (H.poisson3d_27pt(6, 6, 5), False),
+        "random_400": (H.random_csr(400, 6, 101, values="wide"), False),
+    }
+    for name, ((ptr, idx, val), sort_rows) in cases.items():
+        n = len(ptr) - 1
+        x = H.rand_vec(n, 7, "wide")
+        out = dict(ptr=ptr, idx=idx, val=val, x=x, sort_rows=np.array(sort_rows))
+        for fmt in FORMATS:
+            if fmt == "dia" and name.startswith("random"):
+                continue
+            out[f"y_{fmt}"], _ = ref.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2, sort_rows=sort_rows)
+        np.savez_compressed(os.path.join(HERE, f"spmv_{name}.npz"), **out)
+    # solver fixtures: test/test3.c-style system, b = A*1, serial reference
+    ptr, idx, val = H.poisson3d_7pt(12, 12, 12)
+    n = len(ptr) - 1
+    b, _ = ref.spmv("csr", ptr, idx, val, np.ones(n))
+    out = dict(ptr=ptr, idx=idx, val=val, b=b)
+    for tag, opts in {"cg_jacobi": "-i cg -p jacobi", "cg_ssor": "-i cg -p ssor", "bicgstab_ssor": "-i bicgstab -p ssor",
+                      "bicgstab_jacobi": "-i bicgstab -p jacobi", "gmres30_jacobi": "-i gmres -restart 30 -p jacobi",
+                      "gmres5_ssor": "-i gmres -restart 5 -p ssor -ssor_omega 1.2"}.items():
+        r = ref.solve(ptr, idx, val, b, opts)
+        assert r["status"] == 0, (tag, r)
+        out[f"iter_{tag}"] = np.array(r["iter"]); out[f"opts_{tag}"] = np.array(opts); out[f"rhist_{tag}"] = r["rhistory"]
+        out[f"x_{tag}"] = r["x"]
+        print(tag, r["iter"], r["resid"])
+    np.savez_compressed(os.path.join(HERE, "solve_poisson3d_12.npz"), **out)
+    ptr, idx, val = H.random_csr(1500, 7, 202, band=50)
+    b = H.rand_vec(1500, 203)
+    out = dict(ptr=ptr, idx=idx, val=val, b=b)
+    for tag, opts in {"bicgstab_ssor": "-i bicgstab -p ssor", "gmres20_jacobi": "-i gmres -restart 20 -p jacobi",
+                      "bicgstab_none": "-i bicgstab"}.items():
+        r = ref.solve(ptr, idx, val, b, opts)
+        assert r["status"] == 0, (tag, r)
+        out[f"iter_{tag}"] = np.array(r["iter"]); out[f"opts_{tag}"] = np.array(opts); out[f"rhist_{tag}"] = r["rhistory"]
+        out[f"x_{tag}"] = r["x"]
+        print(tag, r["iter"], r["resid"])
+    np.savez_compressed(os.path.join(HERE, "solve_unsym_1500.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

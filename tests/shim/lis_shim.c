@@ -1,0 +1,364 @@
+/*
+ * lis_shim.c -- one test driver, written against the PUBLIC Lis API only (lis.h + the lislib.h
+ * "friend" API that the reference's own spmvtest drivers use), compiled several times:
+ *   - against the reference sources        -> oracle/_ref/libref_shim_{serial,omp}.so
+ *   - against lis_b200 (include/ + liblis) -> lis_b200/_lib/liblis_b200_shim.so
+ * Tests load the builds side by side with ctypes and hand them the same plain arrays, so a
+ * parity test reads like the reference's test/spmvtest*.c and test/test3.c: build CSR with
+ * lis_matrix_set_csr, convert with lis_matrix_convert, run lis_matvec / lis_solve, compare.
+ *
+ * TEST INFRASTRUCTURE: nothing in the product links this file.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef HAVE_CONFIG_H
+#include "lis_config.h"
+#endif
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "lislib.h"
+
+#define EXPORT __attribute__((visibility("default")))
+
+static int g_started = 0;
+
+/* args: "-name value ..." forwarded to lis_initialize as a synthetic argv */
+EXPORT int shim_begin(const char *args)
+{
+    static char buf[1024];
+    static char *argvv[64];
+    char **argv = argvv;
+    int argc = 1;
+    if (g_started) return 0;
+    argvv[0] = (char *)"shim";
+    if (args) {
+        strncpy(buf, args, sizeof(buf) - 1);
+        for (char *t = strtok(buf, " "); t && argc < 63; t = strtok(NULL, " ")) argvv[argc++] = t;
+    }
+    argvv[argc] = NULL;
+    int err = (int)lis_initialize(&argc, &argv);
+    if (!err) g_started = 1;
+    return err;
+}
+
+EXPORT int shim_end(void)
+{
+    if (!g_started) return 0;
+    g_started = 0;
+    return (int)lis_finalize();
+}
+
+/* 1 = this build is lis_b200, 0 = the reference */
+EXPORT int shim_is_b200(void)
+{
+#ifdef LIS_B200_LIS_H
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+EXPORT int shim_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* thread count of the OpenMP reference == SSOR block count / reduction chunking there;
+ * for lis_b200 the emulated count (SSOR blocks) */
+EXPORT int shim_set_threads(int n)
+{
+#ifdef LIS_B200_LIS_H
+    lis_b200_set_num_threads(n);
+#elif defined(_OPENMP)
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+    return 0;
+}
+
+/* ------------------------------------------------------------------ helpers */
+static LIS_INT make_csr(int n, const int *ptr, const int *idx, const double *val, int sort_rows, LIS_MATRIX *out)
+{
+    LIS_MATRIX A;
+    LIS_INT err, *p, *ix;
+    LIS_SCALAR *v;
+    const int nnz = ptr[n];
+    err = lis_matrix_create(LIS_COMM_WORLD, &A); if (err) return err;
+    err = lis_matrix_set_size(A, 0, n); if (err) return err;
+    p = (LIS_INT *)malloc(sizeof(LIS_INT) * ((size_t)n + 1));
+    ix = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(nnz > 0 ? nnz : 1));
+    v = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(nnz > 0 ? nnz : 1));
+    if (!p || !ix || !v) return LIS_OUT_OF_MEMORY;
+    for (int i = 0; i <= n; i++) p[i] = ptr[i];
+    for (int j = 0; j < nnz; j++) { ix[j] = idx[j]; v[j] = val[j]; }
+    err = lis_matrix_set_csr(nnz, p, ix, v, A); if (err) return err;
+    err = lis_matrix_assemble(A); if (err) return err;
+    if (sort_rows)          /* like test/spmvtest3.c:192-195 */
+        for (int i = 0; i < n; i++) lis_sort_id(A->ptr[i], A->ptr[i + 1] - 1, A->index, A->value);
+    *out = A;
+    return LIS_SUCCESS;
+}
+
+static LIS_INT convert_to(LIS_MATRIX A0, int fmt, int bnr, int bnc, LIS_MATRIX *out)
+{
+    LIS_MATRIX A;
+    LIS_INT err = lis_matrix_duplicate(A0, &A); if (err) return err;
+    err = lis_matrix_set_type(A, fmt); if (err) return err;
+    if (fmt == LIS_MATRIX_BSR && bnr > 0) { err = lis_matrix_set_blocksize(A, bnr, bnc, NULL, NULL); if (err) return err; }
+    err = lis_matrix_convert(A0, A); if (err) return err;
+    *out = A;
+    return LIS_SUCCESS;
+}
+
+static LIS_INT make_vec(LIS_MATRIX A, const double *src, LIS_VECTOR *out)
+{
+    LIS_VECTOR v;
+    LIS_INT err = lis_vector_duplicate(A, &v); if (err) return err;
+    if (src && A->n > 0) { err = lis_vector_scatter((LIS_SCALAR *)src, v); if (err) return err; }
+    *out = v;
+    return LIS_SUCCESS;
+}
+
+static LIS_INT make_vec_n(int n, const double *src, LIS_VECTOR *out)
+{
+    LIS_VECTOR v;
+    LIS_INT err = lis_vector_create(LIS_COMM_WORLD, &v); if (err) return err;
+    err = lis_vector_set_size(v, 0, n); if (err) return err;
+    if (src && n > 0) { err = lis_vector_scatter((LIS_SCALAR *)src, v); if (err) return err; }
+    *out = v;
+    return LIS_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ SpMV
+ * fmt = LIS_MATRIX_* ; split=1 runs lis_matrix_split first (the D,L,U summation order);
+ * iters >= 1 calls of lis_matvec are timed with lis_wtime like test/spmvtest1.c:217-222 */
+EXPORT int shim_spmv(int fmt, int n, const int *ptr, const int *idx, const double *val, int bnr, int bnc,
+                     int sort_rows, int split, const double *x, double *y, int iters, double *seconds)
+{
+    LIS_MATRIX A0 = NULL, A = NULL;
+    LIS_VECTOR vx = NULL, vy = NULL;
+    LIS_INT err;
+    double t = 0.0;
+    err = make_csr(n, ptr, idx, val, sort_rows, &A0); if (err) return (int)err;
+    err = convert_to(A0, fmt, bnr, bnc, &A); if (err) return (int)err;
+    if (split) { err = lis_matrix_split(A); if (err) return (int)err; }
+    err = make_vec(A, x, &vx); if (err) return (int)err;
+    err = make_vec(A, NULL, &vy); if (err) return (int)err;
+    err = lis_matvec(A, vx, vy); if (err) return (int)err;      /* warm-up: first-use upload */
+    for (int k = 0; k < iters; k++) {
+        const double t0 = lis_wtime();
+        err = lis_matvec(A, vx, vy);
+        t += lis_wtime() - t0;
+        if (err) return (int)err;
+    }
+    if (seconds) *seconds = t;
+    if (n > 0) { err = lis_vector_gather(vy, y); if (err) return (int)err; }
+    lis_vector_destroy(vx); lis_vector_destroy(vy);
+    lis_matrix_destroy(A); lis_matrix_destroy(A0);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ converted layouts */
+static LIS_MATRIX g_conv[16];
+static LIS_MATRIX g_conv0[16];
+
+EXPORT int shim_convert_open(int fmt, int n, const int *ptr, const int *idx, const double *val, int bnr, int bnc, int sort_rows)
+{
+    int h;
+    for (h = 0; h < 16 && g_conv[h]; h++) ;
+    if (h == 16) return -1;
+    if (make_csr(n, ptr, idx, val, sort_rows, &g_conv0[h])) return -2;
+    if (convert_to(g_conv0[h], fmt, bnr, bnc, &g_conv[h])) return -3;
+    return h;
+}
+
+/* dims: n, nnz, maxnzr, nnd, nr, bnr, bnc, bnnz, matrix_type */
+EXPORT int shim_convert_dims(int h, int *dims)
+{
+    LIS_MATRIX A = g_conv[h];
+    dims[0] = A->n; dims[1] = A->nnz; dims[2] = A->maxnzr; dims[3] = A->nnd; dims[4] = A->nr;
+    dims[5] = A->bnr; dims[6] = A->bnc; dims[7] = A->bnnz; dims[8] = A->matrix_type;
+    return 0;
+}
+
+/* which: 0 ptr, 1 index, 2 value, 3 row(perm), 4 bptr, 5 bindex; count elements copied */
+EXPORT int shim_convert_copy(int h, int which, void *dst, int count)
+{
+    LIS_MATRIX A = g_conv[h];
+    const void *src = NULL;
+    size_t sz = sizeof(LIS_INT);
+    switch (which) {
+    case 0: src = A->ptr; break;
+    case 1: src = A->index; break;
+    case 2: src = A->value; sz = sizeof(LIS_SCALAR); break;
+    case 3: src = A->row; break;
+    case 4: src = A->bptr; break;
+    case 5: src = A->bindex; break;
+    default: return -1;
+    }
+    if (src == NULL) return -2;
+    memcpy(dst, src, sz * (size_t)count);
+    return 0;
+}
+
+EXPORT int shim_convert_close(int h)
+{
+    lis_matrix_destroy(g_conv[h]); lis_matrix_destroy(g_conv0[h]);
+    g_conv[h] = NULL; g_conv0[h] = NULL;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ BLAS-1
+ * op: 0 axpy(y+=a*x) 1 xpay(y=x+a*y) 2 axpyz(z=a*x+y) 3 scale(x=a*x) 4 copy(y=x) 5 set_all(x=a)
+ *     6 pmul(z=x*y) 7 pdiv(z=x/y) 8 reciprocal(x=1/x) 9 abs 10 shift(x-=a) 11 swap
+ *     20 dot 21 nrm2 22 nrm1 23 nrmi 24 sum
+ * out_a / out_b receive the vectors the op wrote (may be NULL), scalar the reduction */
+EXPORT int shim_vec_op(int op, int n, double alpha, const double *x, const double *y,
+                       double *out_a, double *out_b, double *scalar)
+{
+    LIS_VECTOR vx = NULL, vy = NULL, vz = NULL;
+    LIS_INT err;
+    LIS_SCALAR s = 0.0;
+    LIS_REAL r = 0.0;
+    err = make_vec_n(n, x, &vx); if (err) return (int)err;
+    err = make_vec_n(n, y, &vy); if (err) return (int)err;
+    err = make_vec_n(n, NULL, &vz); if (err) return (int)err;
+    LIS_VECTOR ra = NULL, rb = NULL;
+    switch (op) {
+    case 0: err = lis_vector_axpy(alpha, vx, vy); ra = vy; break;
+    case 1: err = lis_vector_xpay(vx, alpha, vy); ra = vy; break;
+    case 2: err = lis_vector_axpyz(alpha, vx, vy, vz); ra = vz; break;
+    case 3: err = lis_vector_scale(alpha, vx); ra = vx; break;
+    case 4: err = lis_vector_copy(vx, vy); ra = vy; break;
+    case 5: err = lis_vector_set_all(alpha, vx); ra = vx; break;
+    case 6: err = lis_vector_pmul(vx, vy, vz); ra = vz; break;
+    case 7: err = lis_vector_pdiv(vx, vy, vz); ra = vz; break;
+    case 8: err = lis_vector_reciprocal(vx); ra = vx; break;
+    case 9: err = lis_vector_abs(vx); ra = vx; break;
+    case 10: err = lis_vector_shift(alpha, vx); ra = vx; break;
+    case 11: err = lis_vector_swap(vx, vy); ra = vx; rb = vy; break;
+    case 20: err = lis_vector_dot(vx, vy, &s); break;
+    case 21: err = lis_vector_nrm2(vx, &r); s = r; break;
+    case 22: err = lis_vector_nrm1(vx, &r); s = r; break;
+    case 23: err = lis_vector_nrmi(vx, &r); s = r; break;
+    case 24: err = lis_vector_sum(vx, &s); break;
+    default: err = LIS_ERR_ILL_ARG;
+    }
+    if (err) return (int)err;
+    if (scalar) *scalar = s;
+    if (ra && out_a && n > 0) { err = lis_vector_gather(ra, out_a); if (err) return (int)err; }
+    if (rb && out_b && n > 0) { err = lis_vector_gather(rb, out_b); if (err) return (int)err; }
+    lis_vector_destroy(vx); lis_vector_destroy(vy); lis_vector_destroy(vz);
+    return 0;
+}
+
+/* mismatched lengths must fail with LIS_ERR_ILL_ARG (src/vector/lis_vector_opv.c:158-163) */
+EXPORT int shim_vec_mismatch(int op)
+{
+    LIS_VECTOR a, b;
+    LIS_SCALAR s;
+    LIS_INT err;
+    if (make_vec_n(8, NULL, &a) || make_vec_n(9, NULL, &b)) return -1;
+    if (op == 0) err = lis_vector_axpy(1.0, a, b);
+    else if (op == 1) err = lis_vector_xpay(a, 1.0, b);
+    else if (op == 4) err = lis_vector_copy(a, b);
+    else err = lis_vector_dot(a, b, &s);
+    lis_vector_destroy(a); lis_vector_destroy(b);
+    return (int)err;
+}
+
+/* ------------------------------------------------------------------ diagonal / preconditioner apply */
+EXPORT int shim_get_diagonal(int fmt, int n, const int *ptr, const int *idx, const double *val, int bnr, int bnc, double *d)
+{
+    LIS_MATRIX A0, A;
+    LIS_VECTOR v;
+    LIS_INT err;
+    err = make_csr(n, ptr, idx, val, 0, &A0); if (err) return (int)err;
+    err = convert_to(A0, fmt, bnr, bnc, &A); if (err) return (int)err;
+    err = make_vec(A, NULL, &v); if (err) return (int)err;
+    err = lis_matrix_get_diagonal(A, v); if (err) return (int)err;
+    err = lis_vector_gather(v, d); if (err) return (int)err;
+    lis_vector_destroy(v); lis_matrix_destroy(A); lis_matrix_destroy(A0);
+    return 0;
+}
+
+/* x = M^-1 b with the preconditioner selected by `options` ("-p ssor -ssor_omega 1.2" ...) */
+EXPORT int shim_psolve(int n, const int *ptr, const int *idx, const double *val, const char *options,
+                       const double *b, double *x)
+{
+    LIS_MATRIX A;
+    LIS_VECTOR vb, vx;
+    LIS_SOLVER solver;
+    LIS_PRECON precon;
+    LIS_INT err;
+    err = make_csr(n, ptr, idx, val, 0, &A); if (err) return (int)err;
+    err = make_vec(A, b, &vb); if (err) return (int)err;
+    err = make_vec(A, NULL, &vx); if (err) return (int)err;
+    err = lis_solver_create(&solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)options, solver); if (err) return (int)err;
+    solver->A = A;
+    err = lis_precon_create(solver, &precon); if (err) return (int)err;
+    solver->precon = precon;
+    err = lis_psolve(solver, vb, vx); if (err) return (int)err;
+    err = lis_vector_gather(vx, x); if (err) return (int)err;
+    lis_precon_destroy(precon);
+    solver->precon = NULL;
+    lis_solver_destroy(solver);
+    lis_vector_destroy(vb); lis_vector_destroy(vx); lis_matrix_destroy(A);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ lis_solve
+ * out_i: iter, retcode(solver status), lis_solve return value, rhistory length
+ * out_d: resid, time, itime, ptime */
+EXPORT int shim_solve(int fmt, int n, const int *ptr, const int *idx, const double *val, const double *b,
+                      double *x, const char *options, int *out_i, double *out_d, double *rhistory, int rh_cap)
+{
+    LIS_MATRIX A0, A;
+    LIS_VECTOR vb, vx, vh;
+    LIS_SOLVER solver;
+    LIS_INT err, iter = 0, status = 0;
+    LIS_REAL resid = 0.0;
+    double time = 0, itime = 0, ptime = 0, pc = 0, pi = 0;
+    err = make_csr(n, ptr, idx, val, 0, &A0); if (err) return (int)err;
+    err = convert_to(A0, fmt, 0, 0, &A); if (err) return (int)err;
+    lis_matrix_destroy(A0);
+    err = make_vec(A, b, &vb); if (err) return (int)err;
+    err = make_vec(A, x, &vx); if (err) return (int)err;
+    err = lis_solver_create(&solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)"-print mem", solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)options, solver); if (err) return (int)err;
+    err = lis_solve(A, vb, vx, solver);
+    out_i[2] = (int)err;
+    lis_solver_get_iter(solver, &iter);
+    lis_solver_get_status(solver, &status);
+    lis_solver_get_residualnorm(solver, &resid);
+    lis_solver_get_timeex(solver, &time, &itime, &ptime, &pc, &pi);
+    out_i[0] = (int)iter; out_i[1] = (int)status;
+    out_d[0] = resid; out_d[1] = time; out_d[2] = itime; out_d[3] = ptime;
+    out_i[3] = 0;
+    if (!err && rhistory && rh_cap > 0) {
+        int len = (int)iter + 1;
+        if (status != LIS_SUCCESS) len--;
+        if (len > rh_cap) len = rh_cap;
+        if (len > 0) {
+            if (make_vec_n(len, NULL, &vh) == 0) {
+                lis_solver_get_rhistory(solver, vh);
+                lis_vector_gather(vh, rhistory);
+                lis_vector_destroy(vh);
+                out_i[3] = len;
+            }
+        }
+    }
+    if (!err && n > 0) lis_vector_gather(vx, x);
+    lis_solver_destroy(solver);
+    lis_vector_destroy(vb); lis_vector_destroy(vx); lis_matrix_destroy(A);
+    return (int)err;
+}

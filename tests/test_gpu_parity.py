@@ -1,0 +1,272 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path behind the lis.h API
+against the CPU oracle (oracle/lis_oracle.c, itself pinned to the compiled reference in
+test_oracle_vs_reference.py) on the same seeded inputs.
+
+Bars: SpMV in every format, elementwise BLAS-1, Jacobi and SSOR sweeps are BIT-EXACT; dot/nrm2
+(reassociated on the GPU) are bounded by the sequential CPU sum's own error; solvers must
+reproduce the iteration count and follow the residual history."""
+import math
+
+import numpy as np
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+FORMATS = ["csr", "csc", "ell", "dia", "jad", "bsr"]
+
+
+def matrices():
+    yield "poisson1d_1000", H.poisson1d(1000), {}
+    yield "poisson3d_7pt_sorted", H.poisson3d_7pt(17, 13, 11, sort=True), {}
+    yield "poisson3d_7pt_unsorted", H.poisson3d_7pt(12, 9, 10), {}
+    yield "poisson3d_27pt", H.poisson3d_27pt(9, 8, 7), {}
+    yield "random_ragged", H.random_csr(2500, 7, 11, values="wide"), {}
+    yield "random_banded_sorted", H.random_csr(3001, 5, 12, band=40, sorted_rows=True), {}
+    yield "random_empty_rows", H.random_csr(1200, 4, 13, empty_rows=True, diag_dominant=False), {}
+    yield "single_row", (np.array([0, 1], np.int32), np.array([0], np.int32), np.array([3.5])), {}
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_spmv_bit_exact(b200, oracle, fmt):
+    for name, (ptr, idx, val), _ in matrices():
+        n = len(ptr) - 1
+        if fmt == "dia" and name.startswith("random_ragged"):
+            continue                      # n*nnd doubles of dense diagonals: not a DIA matrix
+        for kind in ("uniform", "wide"):
+            x = H.rand_vec(n, 5, kind)
+            y, _ = b200.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2)
+            yo = oracle.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2)
+            H.assert_bits_equal(y, yo, f"{fmt}/{name}/{kind}")
+
+
+@pytest.mark.parametrize("bnr,bnc", [(1, 1), (1, 3), (2, 2), (3, 2), (4, 4), (3, 4), (5, 2), (2, 6)])
+def test_spmv_bsr_block_shapes(b200, oracle, bnr, bnc):
+    ptr, idx, val = H.random_csr(1003, 6, 21)
+    x = H.rand_vec(1003, 6, "wide")
+    y, _ = b200.spmv("bsr", ptr, idx, val, x, bnr=bnr, bnc=bnc)
+    H.assert_bits_equal(y, oracle.spmv("bsr", ptr, idx, val, x, bnr=bnr, bnc=bnc), f"bsr {bnr}x{bnc}")
+
+
+def test_spmv_csr_split_order(b200, oracle):
+    """after lis_matrix_split the product sums D, then L, then U (lis_matvec_csr.c:64-87)"""
+    for name, (ptr, idx, val), _ in matrices():
+        n = len(ptr) - 1
+        x = H.rand_vec(n, 8, "wide")
+        y, _ = b200.spmv("csr", ptr, idx, val, x, split=True)
+        H.assert_bits_equal(y, oracle.spmv("csr", ptr, idx, val, x, split=True), f"split/{name}")
+
+
+def test_spmv_long_rows(b200, oracle):
+    """rows far longer than one shared-memory tile of the CSR kernel"""
+    rng = np.random.default_rng(3)
+    n = 700
+    lens = rng.integers(0, 30, n); lens[5] = 6000; lens[400] = 2049; lens[401] = 2048; lens[699] = 4100
+    ptr = np.zeros(n + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    idx = rng.integers(0, n, ptr[-1]).astype(np.int32)      # duplicates allowed: order still defined
+    val = rng.standard_normal(ptr[-1]) * 10.0 ** rng.integers(-5, 5, ptr[-1])
+    x = H.rand_vec(n, 4, "wide")
+    y, _ = b200.spmv("csr", ptr, idx, val, x)
+    H.assert_bits_equal(y, oracle.spmv("csr", ptr, idx, val, x), "long rows")
+
+
+@pytest.mark.parametrize("op", ["axpy", "xpay", "axpyz", "scale", "copy", "set_all", "pmul", "pdiv", "reciprocal",
+                                "abs", "shift", "swap"])
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 1000, 100003])
+def test_blas1_elementwise_bit_exact(b200, oracle, op, n):
+    x = H.rand_vec(n, 31, "wide"); y = H.rand_vec(n, 32, "wide")
+    a, b_, _ = b200.vec_op(op, x, y, alpha=-0.731)
+    oa, ob, _ = oracle.vec_op(op, x, y, alpha=-0.731)
+    H.assert_bits_equal(a, oa, f"{op} n={n}")
+    if ob is not None:
+        H.assert_bits_equal(b_, ob, f"{op}(b) n={n}")
+
+
+def test_blas1_length_mismatch_is_ill_arg(b200):
+    for op in ("axpy", "xpay", "copy", "dot"):
+        assert b200.vec_mismatch(op) == 1          # LIS_ERR_ILL_ARG, lis_vector_opv.c:158-163
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 100003, 3_000_001])
+def test_reductions_bounded(b200, oracle, n):
+    """dot/nrm2/nrm1/sum are reassociated on the GPU: require an error no worse than the CPU's
+    own sequential sum against a high-precision value; nrmi (max) is exact."""
+    x = H.rand_vec(n, 41); y = H.rand_vec(n, 42)
+    for op in ("dot", "nrm2", "nrm1", "sum"):
+        _, _, g = b200.vec_op(op, x, y)
+        _, _, c = oracle.vec_op(op, x, y)
+        xl, yl = x.astype(np.longdouble), y.astype(np.longdouble)
+        if op == "dot": exact = float(np.sum(xl * yl))
+        elif op == "nrm2": exact = float(np.sqrt(np.sum(xl * xl)))
+        elif op == "nrm1": exact = float(np.sum(np.abs(xl)))
+        else: exact = float(np.sum(xl))
+        scale = float(np.sum(np.abs(xl * yl))) if op == "dot" else (float(np.sum(np.abs(xl))) if op == "sum" else abs(exact))
+        eg, ec = abs(g - exact), abs(c - exact)
+        assert eg <= max(ec, 4 * np.finfo(float).eps * scale), f"{op} n={n}: gpu err {eg:g} cpu err {ec:g}"
+    _, _, g = b200.vec_op("nrmi", x)
+    assert g == np.abs(x).max()
+
+
+def test_reductions_deterministic(b200):
+    x = H.rand_vec(1_000_003, 51); y = H.rand_vec(1_000_003, 52)
+    vals = {b200.vec_op("dot", x, y)[2] for _ in range(5)}
+    assert len(vals) == 1
+
+
+def test_empty_vector(b200):
+    assert b200.vec_op("dot", np.zeros(0), np.zeros(0))[2] == 0.0
+    assert b200.vec_op("nrm2", np.zeros(0))[2] == 0.0
+
+
+def test_get_diagonal(b200, oracle):
+    for name, (ptr, idx, val), _ in matrices():
+        d = oracle.get_diagonal(ptr, idx, val)
+        for fmt in FORMATS:
+            if fmt == "dia" and name.startswith("random_ragged"):
+                continue
+            H.assert_bits_equal(b200.get_diagonal(fmt, ptr, idx, val, bnr=2, bnc=2), d, f"diag {fmt}/{name}")
+
+
+@pytest.mark.parametrize("nthreads", [1, 2, 5, 8])
+def test_psolve_ssor_bit_exact(b200, oracle, nthreads):
+    b200.set_threads(nthreads)
+    try:
+        for name, (ptr, idx, val), _ in matrices():
+            if "empty" in name:
+                continue                  # zero diagonal => inf/nan, not a preconditioner input
+            n = len(ptr) - 1
+            b = H.rand_vec(n, 61, "wide")
+            for omega in (1.0, 1.3):
+                x = b200.psolve(ptr, idx, val, b, f"-p ssor -ssor_omega {omega}")
+                xo = oracle.psolve(ptr, idx, val, b, "ssor", omega=omega, nthreads=nthreads)
+                H.assert_bits_equal(x, xo, f"ssor/{name}/omega={omega}/T={nthreads}")
+    finally:
+        b200.set_threads(1)
+
+
+def test_psolve_jacobi_bit_exact(b200, oracle):
+    for name, (ptr, idx, val), _ in matrices():
+        if "empty" in name:
+            continue
+        n = len(ptr) - 1
+        b = H.rand_vec(n, 62, "wide")
+        H.assert_bits_equal(b200.psolve(ptr, idx, val, b, "-p jacobi"), oracle.psolve(ptr, idx, val, b, "jacobi"),
+                            f"jacobi/{name}")
+
+
+def history_close(h_gpu, h_cpu, what):
+    """Residual histories: same length; relative gap small while the iteration is well
+    conditioned (first three quarters), loose near convergence where the reference differs from
+    ITSELF across thread counts (finding 3)."""
+    assert len(h_gpu) == len(h_cpu), f"{what}: history length {len(h_gpu)} vs {len(h_cpu)}"
+    rel = np.abs(h_gpu - h_cpu) / np.maximum(np.abs(h_cpu), 1e-300)
+    k = max(1, (3 * len(rel)) // 4)
+    assert rel[:k].max() < 1e-9, f"{what}: early history gap {rel[:k].max():g}"
+    assert rel.max() < 1e-2, f"{what}: late history gap {rel.max():g}"
+    return rel
+
+
+SOLVER_CASES = [
+    ("cg", "jacobi", "-i cg -p jacobi", {}),
+    ("cg", "none", "-i cg -p none", {}),
+    ("cg", "ssor", "-i cg -p ssor", {}),
+    ("bicgstab", "none", "-i bicgstab -p none", {}),
+    ("bicgstab", "jacobi", "-i bicgstab -p jacobi", {}),
+    ("bicgstab", "ssor", "-i bicgstab -p ssor", {}),
+    ("gmres", "jacobi", "-i gmres -restart 30 -p jacobi", {"restart": 30}),
+    ("gmres", "ssor", "-i gmres -restart 10 -p ssor", {"restart": 10}),
+]
+
+
+@pytest.mark.parametrize("solver,precon,opts,kw", SOLVER_CASES)
+def test_solvers_match_oracle_poisson(b200, oracle, solver, precon, opts, kw):
+    ptr, idx, val = H.poisson3d_7pt(16, 16, 16)          # test/test3.c rows, b = A*1
+    n = len(ptr) - 1
+    b = oracle.spmv("csr", ptr, idx, val, np.ones(n))
+    for fused in ("1", "0"):
+        import os
+        os.environ["LIS_B200_FUSE"] = fused
+        g = b200.solve(ptr, idx, val, b, opts + " -maxiter 2000")
+        c = oracle.solve(solver, ptr, idx, val, b, precon=precon, maxiter=2000, **kw)
+        assert g["err"] == 0 and g["status"] == c["status"] == 0
+        assert g["iter"] == c["iter"], f"{opts} fused={fused}: {g['iter']} iterations vs {c['iter']}"
+        history_close(g["rhistory"], c["rhistory"], f"{opts} fused={fused}")
+        assert np.abs(g["x"] - 1.0).max() < 1e-8
+    os.environ.pop("LIS_B200_FUSE", None)
+
+
+@pytest.mark.parametrize("solver,precon,opts,kw", [c for c in SOLVER_CASES if c[0] != "cg"])
+def test_solvers_match_oracle_unsymmetric(b200, oracle, solver, precon, opts, kw):
+    ptr, idx, val = H.random_csr(4000, 8, 77, band=60)   # strictly diagonally dominant, unsymmetric
+    n = len(ptr) - 1
+    b = H.rand_vec(n, 78)
+    g = b200.solve(ptr, idx, val, b, opts)
+    c = oracle.solve(solver, ptr, idx, val, b, precon=precon, **kw)
+    assert g["status"] == c["status"] == 0
+    assert g["iter"] == c["iter"], f"{opts}: {g['iter']} iterations vs {c['iter']}"
+    history_close(g["rhistory"], c["rhistory"], opts)
+
+
+def test_ssor_block_count_changes_iterations_like_openmp(b200, oracle):
+    """block-SSOR with T blocks == the reference's OpenMP build with T threads"""
+    ptr, idx, val = H.poisson3d_7pt(16, 16, 16)
+    n = len(ptr) - 1
+    b = oracle.spmv("csr", ptr, idx, val, np.ones(n))
+    iters = {}
+    try:
+        for t in (1, 2, 8):
+            b200.set_threads(t)
+            g = b200.solve(ptr, idx, val, b, "-i bicgstab -p ssor")
+            c = oracle.solve("bicgstab", ptr, idx, val, b, precon="ssor", nthreads=1 if t == 1 else t)
+            iters[t] = g["iter"]
+            # the oracle's dot order also depends on T; only the count must agree
+            assert g["iter"] == c["iter"], f"T={t}: {g['iter']} vs {c['iter']}"
+    finally:
+        b200.set_threads(1)
+
+
+def test_solver_formats_give_same_iterations(b200):
+    ptr, idx, val = H.poisson3d_7pt(12, 12, 12)
+    n = len(ptr) - 1
+    ref = None
+    for fmt in FORMATS:
+        b, _ = b200.spmv("csr", ptr, idx, val, np.ones(n))
+        g = b200.solve(ptr, idx, val, b, "-i cg -p jacobi", fmt=fmt)
+        assert g["status"] == 0
+        ref = ref or g["iter"]
+        assert g["iter"] == ref, fmt
+
+
+def test_solver_status_codes(b200):
+    ptr, idx, val = H.poisson3d_7pt(10, 10, 10)
+    n = len(ptr) - 1
+    b = np.ones(n)
+    g = b200.solve(ptr, idx, val, b, "-i cg -maxiter 3")
+    assert g["err"] == 0 and g["status"] == 4 and g["iter"] == 4        # LIS_MAXITER, iter = maxiter+1
+    g = b200.solve(ptr, idx, val, np.zeros(n), "-i cg")
+    assert g["status"] == 0 and g["iter"] == 1                            # already converged: iter = 1
+    g = b200.solve(ptr, idx, val, b, "-i bicg")
+    assert g["err"] == 5                                                  # LIS_ERR_NOT_IMPLEMENTED
+
+
+def test_golden_vectors(b200):
+    """outputs of the compiled reference, committed under tests/golden/ by make_golden.py"""
+    import os
+    for f in sorted(os.listdir(H.GOLDEN)):
+        if not f.endswith(".npz"):
+            continue
+        g = np.load(os.path.join(H.GOLDEN, f))
+        ptr, idx, val = g["ptr"], g["idx"], g["val"]
+        if "x" in g:
+            for fmt in FORMATS:
+                key = f"y_{fmt}"
+                if key in g:
+                    y, _ = b200.spmv(fmt, ptr, idx, val, g["x"], bnr=2, bnc=2, sort_rows=bool(g["sort_rows"]))
+                    H.assert_bits_equal(y, g[key], f"golden {f} {fmt}")
+        for key in [k for k in g.files if k.startswith("iter_")]:
+            tag = key[5:]
+            opts = str(g[f"opts_{tag}"])
+            r = b200.solve(ptr, idx, val, g["b"], opts)
+            assert r["iter"] == int(g[key]), f"golden {f} {opts}: {r['iter']} vs {int(g[key])}"
+            history_close(r["rhistory"], g[f"rhist_{tag}"], f"golden {f} {opts}")
