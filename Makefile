@@ -1,3 +1,4 @@
+.SILENT:
 # Builds lis_b200/_lib/liblis_b200.so : host C (lis.h API) + sm_100a CUDA kernels, one shared
 # library with a C ABI.  `make` here or __graft_entry__.build().
 NVCC     ?= /usr/local/cuda/bin/nvcc

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- SpMV GFLOP/s (+ achieved HBM GB/s, CG iterations/s) on the 3-D 7-point Poisson
+matrix of the reference's test/spmvtest3.c, 512^3 per GPU, CSR, fp64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl lis_b200|reference] [--grid 512]
+
+A "step" is one y = A x over the whole matrix.  `value` is the device-timed throughput with
+A, x and y resident in HBM (CUDA events on the launching stream, K launches back to back; the
+matrix is ~14 GB, >100x the L2, so no flush is needed between steps).  `e2e` is the same
+product through the public lis.h call (lis_matvec) with HOST buffers: x is copied in from
+pinned host memory and y copied back out every step.  `roofline` is for the CSR kernel against
+the measured HBM copy bandwidth; `cpu_baseline` / `--impl reference` time the reference's own
+OpenMP lis_matvec (compiled from the reference sources into oracle/_ref) on the host cores.
+
+N > 1 (torchrun, one rank per GPU): the grid is 512 x 512 x (512*N), row-partitioned into N
+slabs of 512^3 rows (weak scaling) with the halo planes exchanged before every product.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+_libc = C.CDLL("libc.so.6")
+_libc.malloc.restype = C.c_void_p
+_libc.malloc.argtypes = [C.c_size_t]
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        pw = [float(r[3]) for r in self.rows if len(r) > 3 and r[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ----------------------------------------------------------------------------- matrices
+def poisson7_host(l, m, n, k0=0, k1=None, ktot=None):
+    """test/spmvtest3.c:142-157 rows (then sorted by column, :192-195) for planes [k0,k1) of an
+    l x m x ktot grid... used for the CPU sample; numpy, a few seconds at 256^3."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness
+    return harness.poisson3d_7pt(l, m, n, sort=True)
+
+
+def poisson7_device(torch, L, M, N, i0, i1, dev):
+    """Rows of planes i in [i0, i1) of the L x M x N grid (global size L*M*N, lexicographic
+    ii = i*M*N + j*N + k), sorted by column, global column indices, built with torch on `dev`.
+    Returns (ptr int32 [n+1], idx int32 [nnz], val f64 [nnz])."""
+    mn = M * N
+    ii = torch.arange(i0 * mn, i1 * mn, device=dev, dtype=torch.int64)
+    i = ii // mn
+    j = (ii - i * mn) // N
+    k = ii - i * mn - j * N
+    # ascending column order: -mn, -n, -1, diag, +1, +n, +mn
+    offs = [-mn, -N, -1, 0, 1, N, mn]
+    oks = [i > 0, j > 0, k > 0, None, k < N - 1, j < M - 1, i < L - 1]
+    cnt = torch.ones_like(ii, dtype=torch.int32)
+    for ok in oks:
+        if ok is not None:
+            cnt += ok.to(torch.int32)
+    ptr = torch.zeros(ii.numel() + 1, device=dev, dtype=torch.int64)
+    torch.cumsum(cnt, 0, out=ptr[1:])
+    nnz = int(ptr[-1].item())
+    idx = torch.empty(nnz, device=dev, dtype=torch.int32)
+    val = torch.empty(nnz, device=dev, dtype=torch.float64)
+    pos = ptr[:-1].clone()
+    for off, ok in zip(offs, oks):
+        if ok is None:
+            idx[pos] = (ii + off).to(torch.int32)
+            val[pos] = 6.0
+            pos += 1
+        else:
+            sel = pos[ok]
+            idx[sel] = (ii[ok] + off).to(torch.int32)
+            val[sel] = -1.0
+            pos += ok.to(torch.int64)
+    del i, j, k, pos, cnt
+    return ptr.to(torch.int32), idx, val
+
+
+def host_malloc_array(count, dtype):
+    nbytes = max(int(count), 1) * np.dtype(dtype).itemsize
+    p = _libc.malloc(nbytes)
+    if not p:
+        raise MemoryError(nbytes)
+    buf = (C.c_char * nbytes).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(count)), p
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, grid):
+    """The reference's own CPU lis_matvec (OpenMP build, all host threads) on a bounded sample."""
+    import lis_b200
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_shim_omp.so")
+    kind = "reference"
+    if not os.path.exists(path):
+        return {"impl": "reference", "unavailable": "oracle/_ref/libref_shim_omp.so missing (build with make -C oracle ref where /root/reference exists)"}
+    shim = lis_b200.Shim(path)
+    g = min(grid, args.cpu_grid)
+    ptr, idx, val = poisson7_host(g, g, g)
+    n, nnz = len(ptr) - 1, int(ptr[-1])
+    L = shim.lib
+    L.shim_mv_open.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.shim_mv_step_e2e.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    L.shim_mv_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.shim_mv_set_x.argtypes = [C.c_int, C.c_void_p]
+    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
+    assert h >= 0, h
+    x = np.ones(n)
+    L.shim_mv_set_x(h, x.ctypes.data)
+    sec, nrm = C.c_double(0), C.c_double(0)
+    L.shim_mv_run(h, max(args.warmup, 1), C.byref(sec), C.byref(nrm))
+    L.shim_mv_run(h, args.steps, C.byref(sec), C.byref(nrm))
+    gf = 2.0 * nnz * args.steps / sec.value / 1e9
+    cores = shim.max_threads()
+    sample = f"{g}^3 7-pt CSR (n={n}, nnz={nnz}), {args.steps} lis_matvec calls, OMP threads={cores}"
+    return {"impl": "reference", "metric": "spmv_csr_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec.value / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"spmvtest3 {grid}^3 7-pt Poisson CSR (reference timed on a {g}^3 sample)"},
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "nrm2": nrm.value}
+
+
+# ----------------------------------------------------------------------------- lis_b200 arm
+def time_launches(torch, stream, fn, steps, warmup):
+    """CUDA events on the launching stream around `steps` back-to-back launches."""
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            fn()
+        stream.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def run_b200(args, grid):
+    import torch
+    import lis_b200
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl lis_b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    K = lis_b200.load_kernels()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    # ---- the shard of this rank: planes [rank*grid, (rank+1)*grid) of a (grid*world) x grid x grid box
+    Lg = grid * world
+    t0 = time.time()
+    ptr, idx, val = poisson7_device(torch, Lg, grid, grid, rank * grid, (rank + 1) * grid, dev)
+    n = ptr.numel() - 1; nnz = idx.numel(); gn = Lg * grid * grid
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] built {grid}^3 slab: n={n} nnz={nnz} in {time.time() - t0:.1f}s")
+    stream = torch.cuda.Stream(device=dev)
+    sp = C.c_void_p(stream.cuda_stream)
+    res = {}
+
+    # ---- device-resident kernel timings (N=1 semantics per rank: local columns only)
+    # For world > 1 the device-resident leg uses the local-numbered matrix built by the library
+    # (halo exchange included) -- see the e2e/solver leg below; here: single-GPU kernels.
+    if world == 1:
+        x = torch.rand(n, device=dev, dtype=torch.float64) * 2 - 1
+        y = torch.zeros(n, device=dev, dtype=torch.float64)
+        # padding the kernels may read past nnz (multiple of 4 entries)
+        idx_p = torch.cat([idx, torch.zeros(8, device=dev, dtype=torch.int32)])
+        val_p = torch.cat([val, torch.zeros(8, device=dev, dtype=torch.float64)])
+
+        def csr():
+            rc = K.lisb200_spmv_csr(n, ptr.data_ptr(), idx_p.data_ptr(), val_p.data_ptr(), x.data_ptr(), y.data_ptr(), sp)
+            assert rc == 0, K.lisb200_error_string(rc)
+
+        sampler = ClockSampler(local).start()
+        sec = time_launches(torch, stream, csr, args.steps, args.warmup)
+        clocks = sampler.stop()
+        res["csr_s"] = sec / args.steps
+        y_csr = y.clone()
+        bytes_csr = 12.0 * nnz + 20.0 * n + 4
+        log(f"CSR  {2.0 * nnz / res['csr_s'] / 1e9:8.1f} GFLOP/s  {bytes_csr / res['csr_s'] / 1e9:7.1f} GB/s "
+            f"({bytes_csr / res['csr_s'] / 1e9 / peak_gbs:.3f} of {peak_gbs:.0f})")
+
+        # ELL (7 slots, column-major, pad = (0.0, i)) and DIA (7 diagonals) built on the device
+        # from the same CSR rows; they must reproduce the CSR result bit for bit
+        rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), (ptr[1:] - ptr[:-1]).to(torch.int64))
+        slot = torch.arange(nnz, device=dev, dtype=torch.int64) - ptr[:-1].to(torch.int64)[rows]
+        ell_i = torch.arange(n, device=dev, dtype=torch.int32).repeat(7)
+        ell_v = torch.zeros(7 * n, device=dev, dtype=torch.float64)
+        ell_i[slot * n + rows] = idx
+        ell_v[slot * n + rows] = val
+
+        def ell():
+            rc = K.lisb200_spmv_ell(n, 7, n, ell_i.data_ptr(), ell_v.data_ptr(), x.data_ptr(), y.data_ptr(), sp)
+            assert rc == 0
+
+        res["ell_s"] = time_launches(torch, stream, ell, args.steps, args.warmup) / args.steps
+        assert torch.equal(y.view(torch.int64), y_csr.view(torch.int64)), "ELL result differs from CSR"
+        del ell_i, ell_v
+        offs = torch.tensor([-grid * grid, -grid, -1, 0, 1, grid, grid * grid], device=dev, dtype=torch.int32)
+        dia_v = torch.zeros(7 * n, device=dev, dtype=torch.float64)
+        d_of = torch.searchsorted(offs.to(torch.int64), idx.to(torch.int64) - rows)
+        dia_v[d_of * n + rows] = val
+        del rows, slot, d_of
+
+        def dia():
+            rc = K.lisb200_spmv_dia(n, n, 7, n, offs.data_ptr(), dia_v.data_ptr(), x.data_ptr(), y.data_ptr(), sp)
+            assert rc == 0
+
+        res["dia_s"] = time_launches(torch, stream, dia, args.steps, args.warmup) / args.steps
+        assert torch.equal(y.view(torch.int64), y_csr.view(torch.int64)), "DIA result differs from CSR"
+        del dia_v
+        log(f"ELL  {2.0 * nnz / res['ell_s'] / 1e9:8.1f} GFLOP/s  {(100.0 * n) / res['ell_s'] / 1e9:7.1f} GB/s")
+        log(f"DIA  {2.0 * nnz / res['dia_s'] / 1e9:8.1f} GFLOP/s  {(72.0 * n) / res['dia_s'] / 1e9:7.1f} GB/s")
+        del x, y, idx_p, val_p, y_csr
+    else:
+        clocks = None
+
+    # ---- the public API leg: lis_matrix_set_csr(host arrays) -> lis_matvec with host x / y
+    shim = lis_b200.load_shim()
+    Ls = shim.lib
+    Ls.shim_mv_open.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    Ls.shim_mv_step_e2e.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    Ls.shim_mv_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    Ls.shim_mv_set_x.argtypes = [C.c_int, C.c_void_p]
+    Ls.shim_mv_solve.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    if world > 1:
+        raise SystemExit("multi-GPU leg: see lis_b200 comm layer (not wired in this build)")
+    t0 = time.time()
+    h_ptr, p_ptr = host_malloc_array(n + 1, np.int32)
+    h_idx, p_idx = host_malloc_array(nnz, np.int32)
+    h_val, p_val = host_malloc_array(nnz, np.float64)
+    torch.from_numpy(h_ptr).copy_(ptr); torch.from_numpy(h_idx).copy_(idx); torch.from_numpy(h_val).copy_(val)
+    del ptr, idx, val
+    torch.cuda.empty_cache()
+    h = Ls.shim_mv_open(1, n, p_ptr, p_idx, p_val, 0, 0, 1)        # adopts the malloc'ed arrays
+    assert h >= 0, h
+    hx = torch.empty(n, dtype=torch.float64).pin_memory(); hy = torch.empty(n, dtype=torch.float64).pin_memory()
+    hx.uniform_(-1, 1)
+    log(f"host CSR + lis_matrix_set_csr/assemble in {time.time() - t0:.1f}s")
+    for _ in range(max(args.warmup, 1)):                            # first call uploads the matrix mirror
+        rc = Ls.shim_mv_step_e2e(h, hx.data_ptr(), hy.data_ptr()); assert rc == 0, rc
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = Ls.shim_mv_step_e2e(h, hx.data_ptr(), hy.data_ptr()); assert rc == 0, rc
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the drivers' own measurement: `iters` lis_matvec calls timed with lis_wtime (spmvtest3.c)
+    sec, nrm = C.c_double(0), C.c_double(0)
+    Ls.shim_mv_run(h, args.steps, C.byref(sec), C.byref(nrm))
+    api_s = sec.value / args.steps
+    log(f"lis_matvec (resident vectors, host-synchronous calls): {2.0 * nnz / api_s / 1e9:.1f} GFLOP/s; "
+        f"e2e with host x/y: {2.0 * nnz / e2e_s / 1e9:.1f} GFLOP/s")
+
+    # ---- CG + Jacobi through lis_solve, a bounded number of iterations
+    oi = np.zeros(4, np.int32); od = np.zeros(5, np.float64)
+    cg_iters = args.cg_iters
+    rc = Ls.shim_mv_solve(h, f"-i cg -p jacobi -maxiter {cg_iters} -tol 1e-30".encode(), oi.ctypes.data, od.ctypes.data, None)
+    rc = Ls.shim_mv_solve(h, f"-i cg -p jacobi -maxiter {cg_iters} -tol 1e-30".encode(), oi.ctypes.data, od.ctypes.data, None)
+    cg_it_s = cg_iters / od[2] if od[2] > 0 else None
+    log(f"CG+Jacobi: {cg_iters} iterations in {od[2]:.3f}s solver time -> {cg_it_s:.1f} it/s (lis_solve wall {od[4]:.3f}s)")
+
+    out = None
+    if rank == 0:
+        gf = 2.0 * nnz / res["csr_s"] / 1e9
+        ach = bytes_csr / res["csr_s"] / 1e9
+        out = {
+            "metric": "spmv_csr_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["csr_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"spmvtest3 {grid}^3 7-pt Poisson, CSR, rows sorted (n={n}, nnz={nnz})",
+                       "l2": "inputs (13.9 GB/step) exceed L2 by >100x, no flush between steps", "index": "int32"},
+            "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                    "what": "lis_vector_scatter(pinned host x) + lis_matvec + lis_vector_gather(pinned host y) per step"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "kernel": "lisb::csr_kernel", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": ach / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_csr},
+            "clocks": clocks,
+            "extra": {
+                "ell_gflops": 2.0 * nnz / res["ell_s"] / 1e9, "ell_gbs": 100.0 * n / res["ell_s"] / 1e9,
+                "ell_frac": 100.0 * n / res["ell_s"] / 1e9 / peak_gbs,
+                "dia_gflops": 2.0 * nnz / res["dia_s"] / 1e9, "dia_gbs": 72.0 * n / res["dia_s"] / 1e9,
+                "dia_frac": 72.0 * n / res["dia_s"] / 1e9 / peak_gbs,
+                "lis_matvec_api_gflops": 2.0 * nnz / api_s / 1e9,
+                "cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": cg_iters,
+                "cg_unfused_formula_gbs": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9 if cg_it_s else None,
+                "nrm2_Ax": nrm.value,
+            },
+        }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lis_b200", choices=["lis_b200", "reference"])
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--cpu-grid", type=int, default=256, help="edge of the bounded CPU sample")
+    ap.add_argument("--cg-iters", type=int, default=60)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args, args.grid)), flush=True)
+        return
+    out = run_b200(args, args.grid)
+    if rank == 0 and out is not None:
+        if not args.no_cpu_baseline and args.gpus == 1:
+            try:
+                a2 = argparse.Namespace(**vars(args)); a2.steps = 10; a2.warmup = 2
+                r = run_reference(a2, args.grid)
+                out["cpu_baseline"] = r.get("cpu_baseline", {"unavailable": r.get("unavailable")})
+            except Exception as e:  # the baseline must never take the bench line down
+                out["cpu_baseline"] = {"unavailable": repr(e)}
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

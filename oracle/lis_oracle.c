@@ -463,7 +463,7 @@ void orc_ssor_sweep(int n, const int *lptr, const int *lidx, const double *lval,
 
 typedef struct {
     int n; const int *ptr, *idx; const double *val;
-    int precon, nthreads;
+    int precon, nthreads, ssor_blocks;
     /* jacobi */ double *dinv;
     /* ssor   */ int *lptr, *lidx, *uptr, *uidx; double *lval, *uval, *diag, *wd;
 } orc_sys_t;
@@ -475,6 +475,7 @@ static void sys_setup(orc_sys_t *S, int n, const int *ptr, const int *idx, const
     memset(S, 0, sizeof(*S));
     S->n = n; S->ptr = ptr; S->idx = idx; S->val = val;
     S->precon = s->precon; S->nthreads = s->nthreads > 0 ? s->nthreads : 1;
+    S->ssor_blocks = s->ssor_blocks > 0 ? s->ssor_blocks : S->nthreads;
     if (s->precon == 1) {
         S->dinv = (double *)malloc(sizeof(double) * (size_t)n);
         orc_csr_get_diagonal(n, ptr, idx, val, S->dinv);
@@ -511,7 +512,7 @@ static void sys_psolve(const orc_sys_t *S, const double *b, double *x)
 {
     if (S->precon == 1) orc_pmul(S->n, b, S->dinv, x);
     else if (S->precon == 3)
-        orc_ssor_sweep(S->n, S->lptr, S->lidx, S->lval, S->uptr, S->uidx, S->uval, S->wd, b, x, S->nthreads);
+        orc_ssor_sweep(S->n, S->lptr, S->lidx, S->lval, S->uptr, S->uidx, S->uval, S->wd, b, x, S->ssor_blocks);
     else memcpy(x, b, sizeof(double) * (size_t)S->n);
 }
 

@@ -86,6 +86,9 @@ typedef struct {
     int    iter;
     int    retcode;       /* 0 success, 2 breakdown, 4 maxiter */
     double resid;
+    /* input: SSOR block count; 0 = nthreads (what the reference does).  Setting it apart from
+     * nthreads lets a test vary only the reduction order while the preconditioner stays fixed */
+    int    ssor_blocks;
 } orc_solver_t;
 
 /* x is the initial guess (the reference default zeroes it: pass zeros) and the result.

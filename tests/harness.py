@@ -146,6 +146,34 @@ def rand_vec(n, seed, kind="uniform"):
     raise ValueError(kind)
 
 
+def reference_envelope(oracle, solver, ptr, idx, val, b, *, threads=(1, 2, 3, 4, 6, 8), **kw):
+    """The reference's OWN spread: the same solve with the reduction order of 1..8 OpenMP
+    threads (preconditioner held fixed).  Returns the runs; a GPU result is acceptable where it
+    is as close to the serial run as the reference is to itself."""
+    blocks = kw.pop("ssor_blocks", 1)
+    return [oracle.solve(solver, ptr, idx, val, b, nthreads=t, ssor_blocks=blocks, **kw) for t in threads]
+
+
+def check_against_envelope(g, runs, what, slack=20.0, floor=1e-11):
+    """iteration count inside the reference's own range (equal when the reference is
+    thread-count invariant); residual history within `slack` x the reference's own
+    thread-count spread (+ floor) on the common prefix."""
+    its = [r["iter"] for r in runs]
+    assert all(r["status"] == 0 for r in runs) and g["status"] == 0, f"{what}: status {g['status']}"
+    assert min(its) <= g["iter"] <= max(its), f"{what}: {g['iter']} iterations, reference range {min(its)}..{max(its)} ({its})"
+    base = runs[0]["rhistory"]
+    k = min([len(g["rhistory"])] + [len(r["rhistory"]) for r in runs])
+    assert k >= 2, what
+    spread = np.zeros(k)
+    for r in runs[1:]:
+        spread = np.maximum(spread, np.abs(r["rhistory"][:k] - base[:k]) / np.abs(base[:k]))
+    gap = np.abs(g["rhistory"][:k] - base[:k]) / np.abs(base[:k])
+    bad = np.nonzero(gap > slack * spread + floor)[0]
+    assert bad.size == 0, (f"{what}: history leaves the reference's own envelope at iteration {bad[0]}: "
+                           f"gap {gap[bad[0]]:.3g}, reference spread {spread[bad[0]]:.3g}")
+    return its, gap, spread
+
+
 def bits(a):
     return np.ascontiguousarray(a, np.float64).view(np.uint64)
 
@@ -171,7 +199,7 @@ def exact_dot(x, y):
 class OrcSolver(C.Structure):
     _fields_ = [("precon", C.c_int), ("ssor_omega", C.c_double), ("tol", C.c_double), ("maxiter", C.c_int),
                 ("restart", C.c_int), ("nthreads", C.c_int), ("iter", C.c_int), ("retcode", C.c_int),
-                ("resid", C.c_double)]
+                ("resid", C.c_double), ("ssor_blocks", C.c_int)]
 
 
 class Oracle:
@@ -369,9 +397,9 @@ class Oracle:
         return x
 
     def solve(self, solver, ptr, idx, val, b, *, precon="none", tol=1e-12, maxiter=1000, restart=40, omega=1.0,
-              nthreads=1, x0=None):
+              nthreads=1, ssor_blocks=0, x0=None):
         ptr, idx, val = self._csr(ptr, idx, val); n = len(ptr) - 1
-        s = OrcSolver(self.PRECON[precon], omega, tol, maxiter, restart, nthreads, 0, 0, 0.0)
+        s = OrcSolver(self.PRECON[precon], omega, tol, maxiter, restart, nthreads, 0, 0, 0.0, ssor_blocks)
         x = np.ascontiguousarray(x0 if x0 is not None else np.zeros(n), np.float64).copy()
         rh = np.zeros(maxiter + 2)
         fn = {"cg": self.lib.orc_cg, "bicgstab": self.lib.orc_bicgstab, "gmres": self.lib.orc_gmres}[solver]

@@ -362,3 +362,94 @@ EXPORT int shim_solve(int fmt, int n, const int *ptr, const int *idx, const doub
     lis_vector_destroy(vb); lis_vector_destroy(vx); lis_matrix_destroy(A);
     return (int)err;
 }
+
+/* ------------------------------------------------------------------ bench handles
+ * One matrix + x + y kept alive across steps (bench.py): open once, then time steps.
+ * step_e2e is what a user with HOST buffers does per product: scatter x in, lis_matvec,
+ * gather y out.  Public API only, so the same code times the reference's CPU path. */
+static struct { LIS_MATRIX A; LIS_VECTOR x, y; } g_mv[8];
+
+EXPORT int shim_mv_open(int fmt, int n, int *ptr, int *idx, double *val, int bnr, int bnc, int adopt)
+{
+    int h;
+    LIS_MATRIX A0 = NULL, A = NULL;
+    LIS_INT err;
+    for (h = 0; h < 8 && g_mv[h].A; h++) ;
+    if (h == 8) return -1;
+    if (adopt) {
+        /* take the caller's malloc'ed arrays as they are (lis_matrix_set_csr semantics) */
+        err = lis_matrix_create(LIS_COMM_WORLD, &A0); if (err) return -2;
+        err = lis_matrix_set_size(A0, 0, n); if (err) return -2;
+        err = lis_matrix_set_csr(ptr[n], ptr, idx, val, A0); if (err) return -2;
+        err = lis_matrix_assemble(A0); if (err) return -2;
+    } else {
+        if (make_csr(n, ptr, idx, val, 0, &A0)) return -2;
+    }
+    if (fmt == LIS_MATRIX_CSR) A = A0;
+    else {
+        if (convert_to(A0, fmt, bnr, bnc, &A)) return -3;
+        lis_matrix_destroy(A0);
+    }
+    if (make_vec(A, NULL, &g_mv[h].x) || make_vec(A, NULL, &g_mv[h].y)) return -4;
+    g_mv[h].A = A;
+    return h;
+}
+
+EXPORT int shim_mv_step_e2e(int h, double *host_x, double *host_y)
+{
+    LIS_INT err = lis_vector_scatter(host_x, g_mv[h].x); if (err) return (int)err;
+    err = lis_matvec(g_mv[h].A, g_mv[h].x, g_mv[h].y); if (err) return (int)err;
+    return (int)lis_vector_gather(g_mv[h].y, host_y);
+}
+
+/* `iters` products with resident vectors, wall seconds by lis_wtime (the drivers' own timing) */
+EXPORT int shim_mv_run(int h, int iters, double *seconds, double *nrm2)
+{
+    LIS_INT err = 0;
+    LIS_REAL nr = 0.0;
+    const double t0 = lis_wtime();
+    for (int k = 0; k < iters && !err; k++) err = lis_matvec(g_mv[h].A, g_mv[h].x, g_mv[h].y);
+    *seconds = lis_wtime() - t0;
+    if (!err) err = lis_vector_nrm2(g_mv[h].y, &nr);
+    *nrm2 = nr;
+    return (int)err;
+}
+
+EXPORT int shim_mv_set_x(int h, double *host_x) { return (int)lis_vector_scatter(host_x, g_mv[h].x); }
+
+/* lis_solve on the handle's matrix with b = A*1 (test/test3.c:150-151); returns like shim_solve */
+EXPORT int shim_mv_solve(int h, const char *options, int *out_i, double *out_d, double *host_x)
+{
+    LIS_MATRIX A = g_mv[h].A;
+    LIS_VECTOR u, b, x;
+    LIS_SOLVER solver;
+    LIS_INT err, iter = 0, status = 0;
+    LIS_REAL resid = 0.0;
+    double time = 0, itime = 0, ptime = 0, pc = 0, pi = 0;
+    if (make_vec(A, NULL, &u) || make_vec(A, NULL, &b) || make_vec(A, NULL, &x)) return -1;
+    err = lis_vector_set_all(1.0, u); if (err) return (int)err;
+    err = lis_matvec(A, u, b); if (err) return (int)err;
+    err = lis_solver_create(&solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)options, solver); if (err) return (int)err;
+    const double t0 = lis_wtime();
+    err = lis_solve(A, b, x, solver);
+    if (!err && host_x) err = lis_vector_gather(x, host_x);
+    out_d[4] = lis_wtime() - t0;
+    out_i[2] = (int)err;
+    lis_solver_get_iter(solver, &iter);
+    lis_solver_get_status(solver, &status);
+    lis_solver_get_residualnorm(solver, &resid);
+    lis_solver_get_timeex(solver, &time, &itime, &ptime, &pc, &pi);
+    out_i[0] = (int)iter; out_i[1] = (int)status;
+    out_d[0] = resid; out_d[1] = time; out_d[2] = itime; out_d[3] = ptime;
+    lis_solver_destroy(solver);
+    lis_vector_destroy(u); lis_vector_destroy(b); lis_vector_destroy(x);
+    return (int)err;
+}
+
+EXPORT int shim_mv_close(int h)
+{
+    lis_vector_destroy(g_mv[h].x); lis_vector_destroy(g_mv[h].y); lis_matrix_destroy(g_mv[h].A);
+    g_mv[h].A = NULL; g_mv[h].x = NULL; g_mv[h].y = NULL;
+    return 0;
+}

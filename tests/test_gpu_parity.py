@@ -155,15 +155,15 @@ def test_psolve_jacobi_bit_exact(b200, oracle):
                             f"jacobi/{name}")
 
 
-def history_close(h_gpu, h_cpu, what):
-    """Residual histories: same length; relative gap small while the iteration is well
-    conditioned (first three quarters), loose near convergence where the reference differs from
-    ITSELF across thread counts (finding 3)."""
+def history_close(h_gpu, h_cpu, what, early=1e-9, late=1e-2):
+    """Residual histories of runs with the same iteration count: relative gap small while the
+    iteration is well conditioned (first three quarters), loose near convergence where the
+    reference differs from ITSELF across thread counts (finding 3)."""
     assert len(h_gpu) == len(h_cpu), f"{what}: history length {len(h_gpu)} vs {len(h_cpu)}"
     rel = np.abs(h_gpu - h_cpu) / np.maximum(np.abs(h_cpu), 1e-300)
     k = max(1, (3 * len(rel)) // 4)
-    assert rel[:k].max() < 1e-9, f"{what}: early history gap {rel[:k].max():g}"
-    assert rel.max() < 1e-2, f"{what}: late history gap {rel.max():g}"
+    assert rel[:k].max() < early, f"{what}: early history gap {rel[:k].max():g}"
+    assert rel.max() < late, f"{what}: late history gap {rel.max():g}"
     return rel
 
 
@@ -181,19 +181,26 @@ SOLVER_CASES = [
 
 @pytest.mark.parametrize("solver,precon,opts,kw", SOLVER_CASES)
 def test_solvers_match_oracle_poisson(b200, oracle, solver, precon, opts, kw):
-    ptr, idx, val = H.poisson3d_7pt(16, 16, 16)          # test/test3.c rows, b = A*1
+    """test/test3.c system (b = A*1).  The reference's iteration count depends on its OpenMP
+    thread count through the dot-product order alone (BiCGSTAB 16^3: 38, 40, 39, 39 at 1, 2, 4,
+    8 threads), so the bar is the reference's own envelope: count inside its range -- which is
+    a single value for CG and GMRES here -- and history within its thread-count spread."""
+    import os
+    ptr, idx, val = H.poisson3d_7pt(16, 16, 16)
     n = len(ptr) - 1
     b = oracle.spmv("csr", ptr, idx, val, np.ones(n))
-    for fused in ("1", "0"):
-        import os
-        os.environ["LIS_B200_FUSE"] = fused
-        g = b200.solve(ptr, idx, val, b, opts + " -maxiter 2000")
-        c = oracle.solve(solver, ptr, idx, val, b, precon=precon, maxiter=2000, **kw)
-        assert g["err"] == 0 and g["status"] == c["status"] == 0
-        assert g["iter"] == c["iter"], f"{opts} fused={fused}: {g['iter']} iterations vs {c['iter']}"
-        history_close(g["rhistory"], c["rhistory"], f"{opts} fused={fused}")
-        assert np.abs(g["x"] - 1.0).max() < 1e-8
-    os.environ.pop("LIS_B200_FUSE", None)
+    runs = H.reference_envelope(oracle, solver, ptr, idx, val, b, precon=precon, maxiter=2000, **kw)
+    try:
+        for fused in ("1", "0"):
+            os.environ["LIS_B200_FUSE"] = fused
+            g = b200.solve(ptr, idx, val, b, opts + " -maxiter 2000")
+            assert g["err"] == 0
+            its, _, _ = H.check_against_envelope(g, runs, f"{opts} fused={fused}")
+            if solver != "bicgstab":
+                assert len(set(its)) == 1 and g["iter"] == its[0], f"{opts}: {g['iter']} vs {its}"
+            assert np.abs(g["x"] - 1.0).max() < 1e-8
+    finally:
+        os.environ.pop("LIS_B200_FUSE", None)
 
 
 @pytest.mark.parametrize("solver,precon,opts,kw", [c for c in SOLVER_CASES if c[0] != "cg"])
@@ -202,10 +209,8 @@ def test_solvers_match_oracle_unsymmetric(b200, oracle, solver, precon, opts, kw
     n = len(ptr) - 1
     b = H.rand_vec(n, 78)
     g = b200.solve(ptr, idx, val, b, opts)
-    c = oracle.solve(solver, ptr, idx, val, b, precon=precon, **kw)
-    assert g["status"] == c["status"] == 0
-    assert g["iter"] == c["iter"], f"{opts}: {g['iter']} iterations vs {c['iter']}"
-    history_close(g["rhistory"], c["rhistory"], opts)
+    runs = H.reference_envelope(oracle, solver, ptr, idx, val, b, precon=precon, **kw)
+    H.check_against_envelope(g, runs, opts)
 
 
 def test_ssor_block_count_changes_iterations_like_openmp(b200, oracle):
@@ -218,10 +223,9 @@ def test_ssor_block_count_changes_iterations_like_openmp(b200, oracle):
         for t in (1, 2, 8):
             b200.set_threads(t)
             g = b200.solve(ptr, idx, val, b, "-i bicgstab -p ssor")
-            c = oracle.solve("bicgstab", ptr, idx, val, b, precon="ssor", nthreads=1 if t == 1 else t)
+            runs = H.reference_envelope(oracle, "bicgstab", ptr, idx, val, b, precon="ssor", ssor_blocks=t)
+            H.check_against_envelope(g, runs, f"bicgstab+ssor T={t}")
             iters[t] = g["iter"]
-            # the oracle's dot order also depends on T; only the count must agree
-            assert g["iter"] == c["iter"], f"T={t}: {g['iter']} vs {c['iter']}"
     finally:
         b200.set_threads(1)
 
@@ -268,5 +272,7 @@ def test_golden_vectors(b200):
             tag = key[5:]
             opts = str(g[f"opts_{tag}"])
             r = b200.solve(ptr, idx, val, g["b"], opts)
-            assert r["iter"] == int(g[key]), f"golden {f} {opts}: {r['iter']} vs {int(g[key])}"
-            history_close(r["rhistory"], g[f"rhist_{tag}"], f"golden {f} {opts}")
+            tol_it = 1 if "bicgstab" in opts else 0      # BiCGSTAB: the reference itself moves by +-1..2 with its thread count
+            assert abs(r["iter"] - int(g[key])) <= tol_it, f"golden {f} {opts}: {r['iter']} vs {int(g[key])}"
+            if r["iter"] == int(g[key]):
+                history_close(r["rhistory"], g[f"rhist_{tag}"], f"golden {f} {opts}", early=1e-7)
