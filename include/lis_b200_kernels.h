@@ -36,15 +36,30 @@ const char *lisb200_error_string(int code);
  * multiple of 4 entries (the host library pads its device mirrors).                        */
 int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_val,
                      const double *d_x, double *d_y, void *stream);
+/* CSR, unsplit order, short-row matrices: TMA-staged row blocks (cp.async.bulk of the
+ * ptr/idx/val slices into shared memory by a producer warp, thread-per-row ordered walk).
+ * Same result bits as lisb200_spmv_csr.  lisb200_spmv_csr_tma_plan inspects the HOST row
+ * pointers once and returns 0 with (rows_per_block, tile) when the matrix qualifies, 1 if
+ * not (long or very ragged rows: use lisb200_spmv_csr).  d_ptr must be readable 16 bytes
+ * past its n+1 entries.                                  src/matvec/lis_matvec_csr.c:90-110 */
+int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile);
+int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+                         const double *d_val, const double *d_x, double *d_y, void *stream);
+/* ... fused with <x,y>; d_partial needs lisb200_reduce_slots() doubles (persistent grid) */
+int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+                             const double *d_val, const double *d_x, double *d_y, double *d_partial,
+                             unsigned int *d_counter, double *d_result, void *stream);
 /* CSR, split order  t = D[i]*x[i]; t += L...; t += U...  src/matvec/lis_matvec_csr.c:64-87 */
 int lisb200_spmv_csr_split(int n, const double *d_diag,
                            const int *d_lptr, const int *d_lidx, const double *d_lval,
                            const int *d_uptr, const int *d_uidx, const double *d_uval,
                            const double *d_x, double *d_y, void *stream);
 /* CSR SpMV fused with the dot product <x,y> that follows it in CG (q=Ap; <p,q>).
- * d_partial: >= lisb200_reduce_slots() doubles of scratch; the reduced scalar is written to
- * *d_result (device or mapped-host pointer).  Same y bits as lisb200_spmv_csr, same dot
- * bits as lisb200_dot on (x,y).                                                           */
+ * d_partial: >= lisb200_spmv_csr_dot_slots(n) doubles of scratch (one per CTA); the reduced
+ * scalar is written to *d_result (device or mapped-host pointer).  Same y bits as
+ * lisb200_spmv_csr; the dot is a fixed (deterministic) tree over the rows, not the same
+ * tree as lisb200_reduce, so the two may differ in the last bits.                          */
+int lisb200_spmv_csr_dot_slots(int n);
 int lisb200_spmv_csr_dot(int n, const int *d_ptr, const int *d_idx, const double *d_val,
                          const double *d_x, double *d_y, double *d_partial,
                          unsigned int *d_counter, double *d_result, void *stream);

@@ -46,8 +46,18 @@ static LIS_INT csr_upload(lisd_csr *c, int n, const LIS_INT *ptr, const LIS_INT 
     err = up((void **)&c->ptr, ptr, ((size_t)n + 1) * sizeof(int), 16);
     if (!err) err = up((void **)&c->idx, idx, nnz * sizeof(int), 8 * sizeof(int));
     if (!err) err = up((void **)&c->val, val, nnz * sizeof(double), 8 * sizeof(double));
-    if (err) csr_free(c);
-    return err;
+    if (err) { csr_free(c); return err; }
+    /* kernel choice, once per matrix: short-row matrices take the TMA-staged row-block kernel,
+     * long / very ragged rows the product-tile kernel.  LIS_B200_CSR_KERNEL=tile|tma overrides
+     * (tma only where the plan exists). */
+    {
+        const char *force = getenv("LIS_B200_CSR_KERNEL");
+        int rows = 0, tile = 0;
+        if (!(force && strcmp(force, "tile") == 0) && lisb200_spmv_csr_tma_plan(n, ptr, &rows, &tile) == 0) {
+            c->tma_rows = rows; c->tma_tile = tile;
+        }
+    }
+    return LIS_SUCCESS;
 }
 
 static void mirror_free(lisd_matrix *M)
@@ -169,7 +179,10 @@ static LIS_INT matvec_launch(LIS_MATRIX A, lisd_matrix *M, const double *x, doub
         rc = lisb200_spmv_csr_split(n, M->diag, M->L.ptr, M->L.idx, M->L.val, M->U.ptr, M->U.idx, M->U.val, x, y, st);
     else switch (M->type) {
     case LIS_MATRIX_CSR:
-    case LIS_MATRIX_CSC: rc = lisb200_spmv_csr(n, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st); break;
+    case LIS_MATRIX_CSC:
+        if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(n, M->csr.tma_rows, M->csr.tma_tile, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
+        else rc = lisb200_spmv_csr(n, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
+        break;
     case LIS_MATRIX_ELL: rc = lisb200_spmv_ell(n, M->maxnzr, M->ld, M->idx, M->val, x, y, st); break;
     case LIS_MATRIX_DIA: rc = lisb200_spmv_dia(n, M->np, M->nnd, M->ld, M->off, M->val, x, y, st); break;
     case LIS_MATRIX_JAD: rc = lisb200_spmv_jad(n, M->maxnzr, M->jptr, M->perm, M->idx, M->val, x, y, st); break;
@@ -245,11 +258,16 @@ LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *do
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
     if (A->nprocs > 1 && A->commtable) { err = lisd_halo_exchange(A, x); if (err) return err; }
-    double *partial = lisd_partial(0);
+    double *partial = lisd_partial(M->csr.tma_rows ? 0 : (size_t)lisb200_spmv_csr_dot_slots(A->n));
     if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
     lisd_mark_busy();
-    err = lisd_check(lisb200_spmv_csr_dot(A->n, M->csr.ptr, M->csr.idx, M->csr.val, x->value, y->value, partial,
-                                          lisd_counter(), lisd_scalar_dev(0), lisd_stream()), "lis_matvec+dot");
+    if (M->csr.tma_rows)
+        err = lisd_check(lisb200_spmv_csr_tma_dot(A->n, M->csr.tma_rows, M->csr.tma_tile, M->csr.ptr, M->csr.idx, M->csr.val,
+                                                  x->value, y->value, partial, lisd_counter(), lisd_scalar_dev(0),
+                                                  lisd_stream()), "lis_matvec+dot");
+    else
+        err = lisd_check(lisb200_spmv_csr_dot(A->n, M->csr.ptr, M->csr.idx, M->csr.val, x->value, y->value, partial,
+                                              lisd_counter(), lisd_scalar_dev(0), lisd_stream()), "lis_matvec+dot");
     if (err) return err;
     return lisd_reduce_finish(dot_xy, 1, 0);
 }

@@ -121,6 +121,116 @@ csr_dot_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx,
     grid_finish<false, kCsrThreads, 1>(mine, partial, counter, result, red);
 }
 
+// ---- CSR, short-row matrices: TMA-staged row blocks ------------------------------------------
+// For matrices whose rows are short (stencils, FEM: a block of kRows rows owns at most kTile
+// stored entries -- the host checks that), the idx/val/ptr slices of a row block are
+// brought into shared memory by the TMA bulk-copy engine (no registers, no L1 traffic) by a
+// dedicated producer warp running kStages blocks ahead, and consumer thread r walks row r out
+// of shared memory in storage order, gathering x through the read-only path.  Lanes of a warp
+// own consecutive rows, so for banded matrices the k-th gather of the warp is coalesced --
+// this is what the product-tile kernel above cannot offer (its lanes own consecutive ENTRIES,
+// whose columns jump between the diagonals; measured 93 % L1 utilisation at 0.84 of HBM peak).
+// Persistent: gridDim.x CTAs stride over the row blocks.
+template <int kRows>
+struct CsrTmaSmem {
+    static constexpr int kPtrInts = kRows + 4;
+    static __host__ __device__ size_t stage_bytes(int tile) { return (size_t)tile * 12 + kPtrInts * 4; }
+};
+
+template <int kRows, int kStages, bool kDot>
+__global__ void __launch_bounds__(kRows + 32)
+csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const int *__restrict__ idx,
+               const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+               double *partial, unsigned int *counter, double *result)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    const size_t stage_bytes = CsrTmaSmem<kRows>::stage_bytes(tile);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kRows / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    double dsum = 0.0;
+    if (tid >= kRows) {
+        // ---------------- producer warp: one lane drives the TMA ----------------
+        if (tid == kRows) {
+            int it = 0;
+            for (int b = blockIdx.x; b < nblocks; b += gridDim.x, ++it) {
+                const int s = it % kStages;
+                const int r0 = b * kRows;
+                const int rend = min(r0 + kRows, n);
+                const int a0 = __ldg(ptr + r0), a1 = __ldg(ptr + rend);      // issued before the wait
+                if (it >= kStages) mbar_wait(&empty_bar[s], ((it / kStages) - 1) & 1);
+                unsigned char *st = smem_raw + (size_t)s * stage_bytes;
+                double *sval = reinterpret_cast<double *>(st);
+                int *sidx = reinterpret_cast<int *>(st + (size_t)tile * 8);
+                int *sptr = sidx + tile;
+                const int w = a0 & ~3;
+                const uint32_t cnt = (uint32_t)((a1 - w + 3) & ~3);
+                const uint32_t nptr = (uint32_t)((rend - r0 + 1 + 3) & ~3);
+                mbar_expect_tx(&full_bar[s], cnt * 12u + nptr * 4u);
+                tma_load_1d(sptr, ptr + r0, nptr * 4u, &full_bar[s]);
+                if (cnt) {
+                    tma_load_1d(sidx, idx + w, cnt * 4u, &full_bar[s]);
+                    tma_load_1d(sval, val + w, cnt * 8u, &full_bar[s]);
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers: thread r walks row r ----------------
+        int it = 0;
+        for (int b = blockIdx.x; b < nblocks; b += gridDim.x, ++it) {
+            const int s = it % kStages;
+            unsigned char *st = smem_raw + (size_t)s * stage_bytes;
+            const double *sval = reinterpret_cast<const double *>(st);
+            const int *sidx = reinterpret_cast<const int *>(st + (size_t)tile * 8);
+            const int *sptr = sidx + tile;
+            const int r = b * kRows + tid;
+            mbar_wait(&full_bar[s], (it / kStages) & 1);
+            if (r < n) {
+                const int w = sptr[0] & ~3;
+                int j = sptr[tid] - w;
+                const int e = sptr[tid + 1] - w;
+                double acc = 0.0;
+                for (; j + 4 <= e; j += 4) {          // 4 gathers in flight, sums stay ordered
+                    const int c0 = sidx[j], c1 = sidx[j + 1], c2 = sidx[j + 2], c3 = sidx[j + 3];
+                    const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+                    acc = add(acc, mul(sval[j], x0));
+                    acc = add(acc, mul(sval[j + 1], x1));
+                    acc = add(acc, mul(sval[j + 2], x2));
+                    acc = add(acc, mul(sval[j + 3], x3));
+                }
+                for (; j < e; ++j) acc = add(acc, mul(sval[j], __ldg(x + sidx[j])));
+                y[r] = acc;
+                if (kDot) dsum = add(dsum, mul(__ldg(x + r), acc));
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+        }
+    }
+    if (kDot) {
+        // per-CTA partial of <x,y>: rows of this CTA in block order per thread, then the fixed tree
+        __syncthreads();
+        double v = warp_reduce<false>(dsum);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        double mine[1] = {0.0};
+        if (tid < 32) {
+            constexpr int nw = (kRows + 32) / 32;
+            double t = tid < nw ? red[tid] : 0.0;
+            t = warp_reduce<false>(t);
+            mine[0] = t;
+        }
+        __syncthreads();
+        grid_finish<false, kRows + 32, 1>(mine, partial, counter, result, red);
+    }
+}
+
 // ---- ELL -------------------------------------------------------------------------------
 // y[i] = 0; for j<maxnzr: y[i] += value[j*ld+i]*x[index[j*ld+i]]  (lis_matvec_ell.c:110-128)
 __global__ void __launch_bounds__(256)
@@ -274,6 +384,100 @@ static int launch_bsr_c(int n, int nr, int bnc, const int *bptr, const int *bidx
 
 using namespace lisb;
 
+// ---- TMA row-block variant: plan + launch ---------------------------------------------------
+namespace lisb {
+static int g_sm_count = 0;
+static int sm_count_spmv() {
+    if (g_sm_count <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <int kRows, bool kDot>
+static int launch_csr_tma(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
+                          double *partial, unsigned int *counter, double *result, cudaStream_t st)
+{
+    constexpr int kStages = 2;
+    const size_t smem = kStages * CsrTmaSmem<kRows>::stage_bytes(tile);
+    auto kern = csr_tma_kernel<kRows, kStages, kDot>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    int per_sm = (int)((size_t)(227 * 1024 - 2048) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const int max_by_threads = 2048 / (kRows + 32);
+    if (per_sm > max_by_threads) per_sm = max_by_threads;
+    const int nblocks = (n + kRows - 1) / kRows;
+    int grid = sm_count_spmv() * per_sm;
+    if (grid > nblocks) grid = nblocks;
+    kern<<<grid, kRows + 32, smem, st>>>(n, nblocks, tile, ptr, idx, val, x, y, partial, counter, result);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+}  // namespace lisb
+
+// rows_per_block in {256,128,64}; tile = entries staged per row block (multiple of 4)
+extern "C" int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+                                    const double *d_val, const double *d_x, double *d_y, void *stream)
+{
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (rows_per_block) {
+    case 256: return launch_csr_tma<256, false>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    case 128: return launch_csr_tma<128, false>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    case 64:  return launch_csr_tma<64, false>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    default:  return (int)cudaErrorInvalidValue;
+    }
+}
+
+extern "C" int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+                                        const double *d_val, const double *d_x, double *d_y, double *d_partial,
+                                        unsigned int *d_counter, double *d_result, void *stream)
+{
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (rows_per_block) {
+    case 256: return launch_csr_tma<256, true>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    case 128: return launch_csr_tma<128, true>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    case 64:  return launch_csr_tma<64, true>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    default:  return (int)cudaErrorInvalidValue;
+    }
+}
+
+// smallest plan (rows per block, tile) whose staged slice holds every row block of the matrix;
+// h_ptr is the HOST row-pointer array.  Returns 0 and fills the plan, or 1 when the rows are
+// too long/ragged for this variant (use lisb200_spmv_csr).
+extern "C" int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile)
+{
+    if (n <= 0) return 1;
+    const int cand[3] = {256, 128, 64};
+    for (int c = 0; c < 3; ++c) {
+        const int R = cand[c];
+        long long worst = 0;
+        for (long long r0 = 0; r0 < n; r0 += R) {
+            const long long rend = r0 + R < n ? r0 + R : n;
+            const long long w = h_ptr[r0] & ~3;
+            const long long cnt = ((long long)h_ptr[rend] - w + 3) & ~3LL;
+            if (cnt > worst) worst = cnt;
+        }
+        // at most ~32 entries per row on average inside the worst block, tile <= 8192 entries
+        if (worst <= 8192 && worst <= 32LL * R) {
+            long long t = (worst + 255) & ~255LL;
+            if (t < 256) t = 256;
+            *rows_per_block = R; *tile = (int)t;
+            return 0;
+        }
+    }
+    return 1;
+}
+
 extern "C" int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_val,
                                 const double *d_x, double *d_y, void *stream)
 {
@@ -296,6 +500,8 @@ extern "C" int lisb200_spmv_csr_split(int n, const double *d_diag,
     LISB_CHECK_LAUNCH();
     return 0;
 }
+
+extern "C" int lisb200_spmv_csr_dot_slots(int n) { return n > 0 ? (n + kCsrThreads - 1) / kCsrThreads : 1; }
 
 extern "C" int lisb200_spmv_csr_dot(int n, const int *d_ptr, const int *d_idx, const double *d_val,
                                     const double *d_x, double *d_y, double *d_partial,

@@ -18,9 +18,30 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <unistd.h>
+#include <fcntl.h>
 #include "lislib.h"
 
 #define EXPORT __attribute__((visibility("default")))
+
+/* "-print mem" makes the reference print its solver banner on stdout; keep test logs quiet */
+static int quiet_begin(void)
+{
+    if (getenv("SHIM_VERBOSE")) return -1;
+    fflush(stdout);
+    const int saved = dup(1), devnull = open("/dev/null", O_WRONLY);
+    if (saved < 0 || devnull < 0) return -1;
+    dup2(devnull, 1);
+    close(devnull);
+    return saved;
+}
+static void quiet_end(int saved)
+{
+    if (saved < 0) return;
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+}
 
 static int g_started = 0;
 
@@ -335,7 +356,7 @@ EXPORT int shim_solve(int fmt, int n, const int *ptr, const int *idx, const doub
     err = lis_solver_create(&solver); if (err) return (int)err;
     err = lis_solver_set_option((char *)"-print mem", solver); if (err) return (int)err;
     err = lis_solver_set_option((char *)options, solver); if (err) return (int)err;
-    err = lis_solve(A, vb, vx, solver);
+    { const int q = quiet_begin(); err = lis_solve(A, vb, vx, solver); quiet_end(q); }
     out_i[2] = (int)err;
     lis_solver_get_iter(solver, &iter);
     lis_solver_get_status(solver, &status);

