@@ -19,6 +19,7 @@ typedef struct {
 } lisd_ctx_t;
 
 static lisd_ctx_t g_ctx;
+static void pool_clear(void);
 
 static void lisd_probe(void)
 {
@@ -79,6 +80,7 @@ void lisd_shutdown(void)
 {
     if (!g_ctx.available) return;
     cudaStreamSynchronize(g_ctx.stream);
+    pool_clear();
     if (g_ctx.partial) cudaFree(g_ctx.partial);
     if (g_ctx.counter) cudaFree(g_ctx.counter);
     if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
@@ -86,7 +88,25 @@ void lisd_shutdown(void)
     memset(&g_ctx, 0, sizeof(g_ctx));
 }
 
-/* ---- memory ---------------------------------------------------------------------------- */
+/* ---- memory ----------------------------------------------------------------------------
+ * Vector storage is managed memory (the host may touch v->value between API calls, exactly as
+ * with the reference).  Two things keep it at HBM speed: a fresh block is populated on the
+ * device with one bulk prefetch instead of GPU page faults, and destroyed vectors go to a
+ * small size-keyed pool, because lis_solve creates and destroys its work vectors on every
+ * call (src/solver/lis_solver.c:828,909) and cudaMallocManaged/cudaFree are device-wide
+ * synchronising calls costing milliseconds each. */
+#define LISD_POOL_SLOTS 64
+static struct { void *p; size_t bytes; } g_pool[LISD_POOL_SLOTS];
+static size_t g_pool_bytes = 0;
+static const size_t g_pool_cap = (size_t)48 << 30;      /* at most 48 GB parked */
+
+static void pool_clear(void)
+{
+    for (int i = 0; i < LISD_POOL_SLOTS; i++)
+        if (g_pool[i].p) { cudaFree(g_pool[i].p); g_pool[i].p = NULL; g_pool[i].bytes = 0; }
+    g_pool_bytes = 0;
+}
+
 LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
 {
     size_t bytes = (count > 0 ? count : 1) * sizeof(LIS_SCALAR);
@@ -94,8 +114,20 @@ LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
     *value = NULL;
     if (lisd_available()) {
         void *p = NULL;
-        cudaError_t e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
-        if (e != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+        for (int i = 0; i < LISD_POOL_SLOTS && !p; i++)
+            if (g_pool[i].p && g_pool[i].bytes == bytes) { p = g_pool[i].p; g_pool[i].p = NULL; g_pool_bytes -= bytes; }
+        if (p == NULL) {
+            cudaError_t e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                pool_clear();                                  /* give parked blocks back and retry once */
+                e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
+            }
+            if (e != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+        }
+        /* populate / bring the pages to HBM in one go (advisory: faults still work if it fails) */
+        if (cudaMemPrefetchAsync(p, bytes, g_ctx.device, g_ctx.stream) != cudaSuccess) cudaGetLastError();
+        g_ctx.busy = 1;
         *value = (LIS_SCALAR *)p;
         *managed = 1;
     } else {
@@ -106,6 +138,25 @@ LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
         *managed = 0;
     }
     return LIS_SUCCESS;
+}
+
+void lisd_free_vector_bytes(LIS_SCALAR *value, LIS_INT managed, size_t count)
+{
+    if (value == NULL) return;
+    if (!managed) { free(value); return; }
+    size_t bytes = (count > 0 ? count : 1) * sizeof(LIS_SCALAR);
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (g_ctx.available && g_pool_bytes + bytes <= g_pool_cap) {
+        for (int i = 0; i < LISD_POOL_SLOTS; i++)
+            if (g_pool[i].p == NULL) {
+                /* work queued on the stream may still use the block; stream order protects the
+                 * next owner, who only touches it through the same stream */
+                g_pool[i].p = value; g_pool[i].bytes = bytes; g_pool_bytes += bytes;
+                return;
+            }
+    }
+    lisd_sync();
+    cudaFree(value);
 }
 
 void lisd_free_vector(LIS_SCALAR *value, LIS_INT managed)

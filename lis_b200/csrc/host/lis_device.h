@@ -31,6 +31,7 @@ int   lisd_device_id(void);
 /* ---- memory ---- */
 LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed);
 void    lisd_free_vector(LIS_SCALAR *value, LIS_INT managed);
+void    lisd_free_vector_bytes(LIS_SCALAR *value, LIS_INT managed, size_t count);   /* parks the block in the pool */
 LIS_INT lisd_malloc(void **p, size_t bytes);        /* plain device memory */
 void    lisd_free(void *p);
 LIS_INT lisd_upload(void *dst, const void *src, size_t bytes);      /* H2D, synchronous */

@@ -87,7 +87,7 @@ LIS_INT lis_vector_set_size(LIS_VECTOR vec, LIS_INT local_n, LIS_INT global_n)
 LIS_INT lis_vector_destroy(LIS_VECTOR vec)
 {
     if (lis_is_malloc(vec)) {
-        if (vec->value && vec->is_destroy) lisd_free_vector(vec->value, vec->b200_managed);
+        if (vec->value && vec->is_destroy) lisd_free_vector_bytes(vec->value, vec->b200_managed, vec->b200_capacity);
         if (vec->work) lis_free(vec->work);
         if (vec->ranges) lis_free(vec->ranges);
         lis_free(vec);
