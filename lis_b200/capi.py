@@ -148,9 +148,51 @@ class Shim:
         h = self.lib.shim_convert_open(code, n, ptr, idx, val, bnr, bnc, int(sort_rows))
         if h < 0:
             raise RuntimeError(f"shim_convert_open({fmt}) failed ({h})")
+        return self._grab_handle(h, fmt)
+
+    def input_mm(self, path, fmt="csr"):
+        """lis_input on a Matrix Market file -> (matrix arrays dict, b or None, x or None)."""
+        self.lib.shim_input_open.argtypes = [C.c_char_p, C.c_int, _i32p, _f64p, C.c_int]
+        has = np.zeros(2, np.int32)
+        cap = 1 << 22
+        bx = np.zeros(cap, np.float64)
+        h = self.lib.shim_input_open(path.encode(), FMT[fmt], has, bx, cap)
+        if h < 0:
+            raise RuntimeError(f"lis_input({path}) failed ({h})")
+        out = self._grab_handle(h, fmt)
+        n = out["n"]
+        return out, (bx[:n].copy() if has[0] else None), (bx[n:2 * n].copy() if has[1] else None)
+
+    def assemble(self, n, rows, cols, vals, flags=None, fmt="csr"):
+        """lis_matrix_set_value entry by entry + lis_matrix_assemble -> arrays dict."""
+        self.lib.shim_assemble_open.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, C.c_int]
+        rows = np.ascontiguousarray(rows, np.int32); cols = np.ascontiguousarray(cols, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        flags = np.ascontiguousarray(flags if flags is not None else np.zeros(len(rows)), np.int32)
+        h = self.lib.shim_assemble_open(n, len(rows), rows, cols, vals, flags, FMT[fmt])
+        if h < 0:
+            raise RuntimeError(f"assembly failed ({h})")
+        return self._grab_handle(h, fmt)
+
+    def sort_id(self, keys, vals):
+        self.lib.shim_sort_id.argtypes = [C.c_int, _i32p, _f64p]
+        k = np.ascontiguousarray(keys, np.int32).copy(); v = np.ascontiguousarray(vals, np.float64).copy()
+        self.lib.shim_sort_id(len(k), k, v)
+        return k, v
+
+    def parse_options(self, text):
+        self.lib.shim_parse_options.argtypes = [C.c_char_p, _i32p, _f64p]
+        o = np.zeros(8, np.int32); d = np.zeros(2, np.float64)
+        err = self.lib.shim_parse_options(text.encode(), o, d)
+        keys = ["solver", "precon", "maxiter", "restart", "storage", "output", "conv_cond", "initx_zeros"]
+        return int(err), dict(zip(keys, map(int, o))), dict(tol=float(d[0]), ssor_omega=float(d[1]))
+
+    def _grab_handle(self, h, fmt):
+        n_unused = 0
         dims = np.zeros(9, np.int32)
         self.lib.shim_convert_dims(h, dims)
         d = dict(zip(["n", "nnz", "maxnzr", "nnd", "nr", "bnr", "bnc", "bnnz", "type"], map(int, dims)))
+        n = d["n"]
 
         def grab(which, count, dtype):
             out = np.empty(max(count, 1), dtype)

@@ -412,7 +412,9 @@ void orc_csr_split_count(int n, const int *ptr, const int *idx, int *nnzl, int *
 }
 
 /* src/matrix/lis_matrix_csr.c:903-932: storage order kept inside L and U; the LAST diagonal
- * entry of a row wins; rows without one keep diag = 0 (lis_matrix_diag_duplicateM zero-fills) */
+ * entry of a row wins.  Rows without a stored diagonal: the reference leaves D[i] as whatever
+ * lis_malloc returned (lis_matrix_diag_duplicateM never initialises it) -- undefined there,
+ * defined as 0 here and in lis_b200. */
 void orc_csr_split(int n, const int *ptr, const int *idx, const double *val,
                    int *lptr, int *lidx, double *lval, int *uptr, int *uidx, double *uval, double *diag)
 {

@@ -200,6 +200,62 @@ EXPORT int shim_convert_open(int fmt, int n, const int *ptr, const int *idx, con
     return h;
 }
 
+/* lis_input (Matrix Market) into a handle; b/x presence flags returned in has[0..1] and the
+ * vectors copied to bx (2*n doubles) when present */
+EXPORT int shim_input_open(const char *path, int fmt, int *has, double *bx, int bx_cap)
+{
+    int h;
+    LIS_MATRIX A;
+    LIS_VECTOR b, x;
+    for (h = 0; h < 16 && g_conv[h]; h++) ;
+    if (h == 16) return -1;
+    if (lis_matrix_create(LIS_COMM_WORLD, &A)) return -2;
+    if (fmt != LIS_MATRIX_CSR && lis_matrix_set_type(A, fmt)) return -2;
+    if (lis_vector_create(LIS_COMM_WORLD, &b) || lis_vector_create(LIS_COMM_WORLD, &x)) return -2;
+    { const int q = quiet_begin(); const LIS_INT err = lis_input(A, b, x, (char *)path); quiet_end(q); if (err) return -100 - (int)err; }
+    has[0] = !lis_vector_is_null(b); has[1] = !lis_vector_is_null(x);
+    if (has[0] && bx_cap >= A->n) lis_vector_gather(b, bx);
+    if (has[1] && bx_cap >= 2 * A->n) lis_vector_gather(x, bx + A->n);
+    lis_vector_destroy(b); lis_vector_destroy(x);
+    g_conv[h] = A; g_conv0[h] = NULL;
+    return h;
+}
+
+/* row-wise assembly with lis_matrix_set_value (flag per entry), then lis_matrix_assemble */
+EXPORT int shim_assemble_open(int n, int count, const int *rows, const int *cols, const double *vals, const int *flags, int fmt)
+{
+    int h;
+    LIS_MATRIX A;
+    for (h = 0; h < 16 && g_conv[h]; h++) ;
+    if (h == 16) return -1;
+    if (lis_matrix_create(LIS_COMM_WORLD, &A) || lis_matrix_set_size(A, 0, n)) return -2;
+    if (fmt != LIS_MATRIX_CSR && lis_matrix_set_type(A, fmt)) return -2;
+    for (int k = 0; k < count; k++) {
+        const LIS_INT err = lis_matrix_set_value(flags[k], rows[k], cols[k], vals[k], A);
+        if (err) return -100 - (int)err;
+    }
+    if (lis_matrix_assemble(A)) return -3;
+    g_conv[h] = A; g_conv0[h] = NULL;
+    return h;
+}
+
+EXPORT void shim_sort_id(int n, int *keys, double *vals) { lis_sort_id(0, n - 1, keys, vals); }
+
+/* option parsing: returns solver, precon, maxiter, restart, storage, output, conv_cond, initx_zeros in o[8],
+ * tol and ssor_omega in d[2] */
+EXPORT int shim_parse_options(const char *text, int *o, double *d)
+{
+    LIS_SOLVER s;
+    LIS_INT err = lis_solver_create(&s); if (err) return (int)err;
+    err = lis_solver_set_option((char *)text, s);
+    o[0] = s->options[LIS_OPTIONS_SOLVER]; o[1] = s->options[LIS_OPTIONS_PRECON]; o[2] = s->options[LIS_OPTIONS_MAXITER];
+    o[3] = s->options[LIS_OPTIONS_RESTART]; o[4] = s->options[LIS_OPTIONS_STORAGE]; o[5] = s->options[LIS_OPTIONS_OUTPUT];
+    o[6] = s->options[LIS_OPTIONS_CONV_COND]; o[7] = s->options[LIS_OPTIONS_INITGUESS_ZEROS];
+    d[0] = s->params[LIS_PARAMS_RESID - LIS_OPTIONS_LEN]; d[1] = s->params[LIS_PARAMS_SSOR_OMEGA - LIS_OPTIONS_LEN];
+    lis_solver_destroy(s);
+    return (int)err;
+}
+
 /* dims: n, nnz, maxnzr, nnd, nr, bnr, bnc, bnnz, matrix_type */
 EXPORT int shim_convert_dims(int h, int *dims)
 {
@@ -231,7 +287,8 @@ EXPORT int shim_convert_copy(int h, int which, void *dst, int count)
 
 EXPORT int shim_convert_close(int h)
 {
-    lis_matrix_destroy(g_conv[h]); lis_matrix_destroy(g_conv0[h]);
+    lis_matrix_destroy(g_conv[h]);
+    if (g_conv0[h]) lis_matrix_destroy(g_conv0[h]);
     g_conv[h] = NULL; g_conv0[h] = NULL;
     return 0;
 }

@@ -1,0 +1,225 @@
+"""CPU-side tests (no GPU needed): the C-ABI library loads and exports what include/*.h
+declares, the host logic behind lis.h (conversion layouts, assembly, option parsing, Matrix
+Market input, sorting, error codes) matches the compiled reference, and compute entry points
+fail loudly -- never fall back -- when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import harness as H
+import lis_b200
+
+INCLUDE = os.path.join(H.ROOT, "include")
+
+
+def declared_functions(header):
+    text = open(os.path.join(INCLUDE, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"#define[^\n]*(\\\n[^\n]*)*", "", text)
+    names = set()
+    for m in re.finditer(r"\b(?:LIS_INT|int|double|void|const char \*|void \*)\s*\*?\s*(\w+)\s*\([^;{]*\)\s*;", text):
+        names.add(m.group(1))
+    return {n for n in names if not n.startswith("LIS_") or n == "LIS_MATVEC"} - {"conj"}
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = lis_b200.load_library()
+    missing = []
+    total = 0
+    for header in ("lis.h", "lislib.h", "lis_b200_kernels.h"):
+        for name in sorted(declared_functions(header)):
+            total += 1
+            if not hasattr(lib, name):
+                missing.append(f"{header}:{name}")
+    assert total > 150, total
+    assert not missing, f"declared but not exported: {missing}"
+
+
+def test_kernel_abi_has_no_torch_types():
+    text = open(os.path.join(INCLUDE, "lis_b200_kernels.h")).read()
+    assert "torch" not in text and "at::" not in text and "extern \"C\"" in text
+
+
+def test_no_cpu_fallback_without_device(b200):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the compute path runs")
+    with pytest.raises(RuntimeError, match="Lis error 7"):       # LIS_ERR_DEVICE
+        b200.vec_op("axpy", np.ones(4), np.ones(4), 1.0)
+    ptr, idx, val = H.poisson1d(10)
+    with pytest.raises(RuntimeError, match="Lis error 7"):
+        b200.spmv("csr", ptr, idx, val, np.ones(10))
+
+
+def test_product_does_not_reference_oracle():
+    """the product (library sources, package, headers) must not include, link or load oracle/"""
+    for root in ("lis_b200", "include"):
+        for dp, dn, fn in os.walk(os.path.join(H.ROOT, root)):
+            if "_build" in dp or "_lib" in dp or "__pycache__" in dp:
+                continue
+            for f in fn:
+                if f.endswith((".c", ".h", ".cu", ".cuh", ".py")):
+                    text = open(os.path.join(dp, f)).read()
+                    assert "lis_oracle" not in text and "oracle/_ref" not in text and "orc_" not in text, os.path.join(dp, f)
+    mk = open(os.path.join(H.ROOT, "Makefile")).read()
+    assert "oracle" not in mk
+
+
+# ------------------------------------------------------------------ conversion layouts (host only)
+MATS = {
+    "poisson1d": lambda: H.poisson1d(101),
+    "poisson3d_unsorted": lambda: H.poisson3d_7pt(6, 5, 7),
+    "poisson27": lambda: H.poisson3d_27pt(4, 5, 6),
+    "random": lambda: H.random_csr(257, 5, 3, values="wide"),
+    "random_empty": lambda: H.random_csr(130, 4, 4, empty_rows=True, diag_dominant=False),
+}
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc", "ell", "dia", "jad", "bsr"])
+def test_conversion_layouts_match_oracle_builders(b200, oracle, fmt):
+    """lis_matrix_convert produces the reference's SERIAL layouts (they are what the kernels read)"""
+    for name, mk in MATS.items():
+        ptr, idx, val = mk()
+        if fmt == "dia" and name.startswith("random"):
+            continue
+        got = b200.convert(fmt, ptr, idx, val, bnr=2, bnc=2)
+        if fmt == "csr":
+            exp = dict(ptr=ptr, index=idx, value=val)
+        elif fmt == "bsr":
+            exp = oracle.to_bsr(ptr, idx, val, 2, 2)
+        else:
+            exp = {"ell": oracle.to_ell, "dia": oracle.to_dia, "jad": oracle.to_jad, "csc": oracle.to_csc}[fmt](ptr, idx, val)
+        for key in ("ptr", "index", "value", "row", "bptr", "bindex"):
+            if key in got and key in exp:
+                a = np.asarray(got[key]); e = np.ascontiguousarray(np.asarray(exp[key])[:len(a)], a.dtype)
+                assert np.array_equal(a.view(np.uint8), e.view(np.uint8)), f"{fmt}/{name}/{key}"
+        for key in ("maxnzr", "nnd", "bnnz"):
+            if key in exp:
+                assert got[key] == exp[key], f"{fmt}/{name}/{key}"
+
+
+@pytest.mark.parametrize("fmt", ["csc", "ell", "dia", "jad", "bsr"])
+def test_conversion_layouts_match_reference(b200, ref_serial, fmt):
+    for name, mk in MATS.items():
+        ptr, idx, val = mk()
+        if fmt == "dia" and name.startswith("random"):
+            continue
+        got = b200.convert(fmt, ptr, idx, val, bnr=3, bnc=2)
+        ref = ref_serial.convert(fmt, ptr, idx, val, bnr=3, bnc=2)
+        for key in ("maxnzr", "nnd", "bnnz", "nr", "bnr", "bnc"):
+            assert got[key] == ref[key], f"{fmt}/{name}/{key}"
+        for key in ("ptr", "bptr", "bindex") + (() if fmt == "jad" else ("index", "value")):
+            if key in ref:
+                assert np.array_equal(np.asarray(got[key]).view(np.uint8), np.asarray(ref[key]).view(np.uint8)), f"{fmt}/{name}/{key}"
+        if fmt == "jad":
+            # the order of equal-length rows is a quicksort artefact in the reference: compare per row
+            def rows_of(d):
+                out = {}
+                for i, r in enumerate(d["row"]):
+                    ks = [int(d["ptr"][j]) + i for j in range(d["maxnzr"]) if i < d["ptr"][j + 1] - d["ptr"][j]]
+                    out[int(r)] = (tuple(d["index"][ks]), tuple(d["value"][ks]))
+                return out
+            assert rows_of(got) == rows_of(ref), f"jad/{name}"
+            lens = np.diff(ptr)
+            assert list(lens[got["row"]]) == sorted(lens, reverse=True)
+
+
+def test_set_value_assembly_matches_reference(b200, ref_serial):
+    rng = np.random.default_rng(5)
+    n = 60
+    rows = rng.integers(0, n, 900); cols = rng.integers(0, n, 900); vals = rng.standard_normal(900)
+    flags = rng.integers(0, 2, 900)                       # LIS_INS_VALUE / LIS_ADD_VALUE, duplicates included
+    for fmt in ("csr", "ell", "csc"):
+        a = b200.assemble(n, rows, cols, vals, flags, fmt)
+        r = ref_serial.assemble(n, rows, cols, vals, flags, fmt)
+        for key in ("ptr", "index", "value"):
+            if key in r:
+                assert np.array_equal(np.asarray(a[key]).view(np.uint8), np.asarray(r[key]).view(np.uint8)), f"{fmt}/{key}"
+
+
+def test_matrix_market_input_matches_reference(b200, ref_serial, tmp_path):
+    ptr, idx, val = H.random_csr(40, 4, 8)
+    n = 40
+    b = H.rand_vec(n, 9)
+    lines = ["%%MatrixMarket matrix coordinate real general", "% comment line", f"{n} {n} {ptr[-1]} 1 0"]
+    rng = np.random.default_rng(1)
+    entries = [(i, idx[j], val[j]) for i in range(n) for j in range(ptr[i], ptr[i + 1])]
+    for k in rng.permutation(len(entries)):
+        i, j, v = entries[k]
+        lines.append(f"{i + 1} {j + 1} {v:.20e}")
+    lines += [f"{i + 1} {b[i]:.20e}" for i in range(n)]
+    path = tmp_path / "a.mtx"
+    path.write_text("\n".join(lines) + "\n")
+    sym = tmp_path / "s.mtx"
+    sym.write_text("%%MatrixMarket matrix coordinate real symmetric\n3 3 4\n1 1 2.0\n2 1 -1.0\n3 2 -1.5\n3 3 4.0\n")
+    for p in (path, sym):
+        for fmt in ("csr", "ell"):
+            ga, gb, gx = b200.input_mm(str(p), fmt)
+            ra, rb, rx = ref_serial.input_mm(str(p), fmt)
+            for key in ("ptr", "index", "value"):
+                if key in ra:
+                    assert np.array_equal(np.asarray(ga[key]).view(np.uint8), np.asarray(ra[key]).view(np.uint8)), (p.name, fmt, key)
+            assert (gb is None) == (rb is None) and (gx is None) == (rx is None)
+            if rb is not None:
+                H.assert_bits_equal(gb, rb, "rhs")
+
+
+def test_reference_fixture_testmat(b200):
+    """test/testmat.mtx of the reference, when its tree is present"""
+    path = "/root/reference/test/testmat.mtx"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    a, b, x = b200.input_mm(path)
+    assert a["n"] == 100 and int(a["ptr"][-1]) == 460 and b is not None and x is None
+
+
+def test_option_parsing_matches_reference(b200, ref_serial):
+    texts = ["", "-i cg -p jacobi -maxiter 77 -tol 1e-9", "-i 4 -p 3 -ssor_omega 1.35 -print all",
+             "-I BiCGSTAB -P SSOR -Print MEM", "-i gmres -restart 25 -storage ell -conv_cond nrm2_b",
+             "-initx_zeros false -p none -print 2", "-i 9 -storage 5 -tol 1.0e-8 -maxiter 5"]
+    for t in texts:
+        assert b200.parse_options(t) == ref_serial.parse_options(t), t
+    for bad in ("-i nosuchsolver", "-p nosuchprecon", "-print loud", "-storage xyz"):
+        assert b200.parse_options(bad)[0] == ref_serial.parse_options(bad)[0] == 1, bad     # LIS_ERR_ILL_ARG
+
+
+def test_sort_id_matches_reference(b200, ref_serial):
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 2, 7, 64, 65, 500):
+        keys = rng.permutation(n * 3)[:n]           # distinct keys: the order of duplicates is unspecified
+        vals = rng.standard_normal(n)
+        gk, gv = b200.sort_id(keys, vals)
+        rk, rv = ref_serial.sort_id(keys, vals)
+        assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
+
+
+def test_error_codes_host_side(built):
+    lib = lis_b200.load_library()
+    lib.lis_initialize(None, None)
+    A = C.c_void_p()
+    assert lib.lis_matrix_create(1, C.byref(A)) == 0
+    assert lib.lis_matrix_set_size(A, 5, 3) == 1                  # local > global: LIS_ERR_ILL_ARG
+    assert lib.lis_matrix_set_size(A, -1, 0) == 1
+    assert lib.lis_matrix_set_size(A, 0, 0) == 1
+    assert lib.lis_matrix_set_size(A, 0, 8) == 0
+    assert lib.lis_matrix_set_type(A, 99) == 1
+    assert lib.lis_matrix_set_type(A, 5) == 0
+    lib.lis_matrix_set_value.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    assert lib.lis_matrix_set_value(0, 9, 0, 1.0, A) == 1         # row out of range
+    assert lib.lis_matrix_set_value(0, 0, 0, 1.0, A) == 0
+    assert lib.lis_matrix_assemble(A) == 0
+    assert lib.lis_matrix_set_value(0, 1, 1, 1.0, A) == 1         # already assembled
+    assert lib.lis_is_malloc(A) == 1
+    assert lib.lis_matrix_destroy(A) == 0
+    assert lib.lis_is_malloc(A) == 0
+    v = C.c_void_p()
+    assert lib.lis_vector_create(1, C.byref(v)) == 0
+    assert lib.lis_vector_is_null(v) == 1
+    assert lib.lis_vector_set_size(v, 0, 6) == 0
+    assert lib.lis_vector_is_null(v) == 0
+    lib.lis_vector_set_value.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p]
+    assert lib.lis_vector_set_value(0, 6, 1.0, v) == 1            # index out of range
+    assert lib.lis_vector_destroy(v) == 0
