@@ -172,6 +172,99 @@ def run_reference(args, grid):
             "gpu_launches": 0, "nrm2": nrm.value}
 
 
+# ----------------------------------------------------------------------------- multi-GPU leg
+def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, local, ptr, idx, val, n, nnz, peak_gbs, peak_src):
+    """N ranks, one GPU each: the (grid*N) x grid x grid box row-partitioned into N slabs.  Every
+    product exchanges the two boundary planes with the neighbours (NCCL send/recv into the halo
+    part of x) and every dot/nrm2 all-gathers the per-rank partials.  Device time = CUDA events
+    on the library's stream, maximum over the ranks."""
+    Ls = shim.lib
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C"); f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    Ls.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p]
+    Ls.shim_mv_set_x_local.argtypes = [C.c_int, C.c_void_p]; Ls.shim_mv_get_y_local.argtypes = [C.c_int, C.c_void_p]
+    lib = lis_b200.load_library()
+    lib.lis_b200_comm_attach.argtypes = [C.c_int, C.c_int, C.c_ulonglong]
+    lib.lis_b200_stream.restype = C.c_void_p
+    tok = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        tok[0] = int.from_bytes(os.urandom(7), "little")
+    dist.broadcast(tok, 0)
+    rc = lib.lis_b200_comm_attach(rank, world, int(tok.item())); assert rc == 0, rc
+    t0 = time.time()
+    hp, hi, hv = ptr.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
+    del ptr, idx, val
+    torch.cuda.empty_cache()
+    h = Ls.shim_mv_open_dist(1, n, hp, hi, hv); assert h >= 0, h
+    del hp, hi, hv
+    log(f"[rank {rank}] row-partitioned matrix assembled in {time.time() - t0:.1f}s")
+    hx = torch.empty(n, dtype=torch.float64).pin_memory(); hy = torch.empty(n, dtype=torch.float64).pin_memory()
+    hx.uniform_(-1, 1)
+    assert Ls.shim_mv_set_x_local(h, hx.data_ptr()) == 0
+    stream = torch.cuda.ExternalStream(lib.lis_b200_stream(), device=dev)
+    for _ in range(args.warmup):
+        assert Ls.shim_mv_matvec(h) == 0
+    dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local).start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        assert Ls.shim_mv_matvec(h) == 0
+    e1.record(stream)
+    stream.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_s = float(t.item()) / args.steps
+    # e2e: local slice of x in from pinned host memory, product, local slice of y out
+    dist.barrier(); torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        assert Ls.shim_mv_set_x_local(h, hx.data_ptr()) == 0
+        assert Ls.shim_mv_matvec(h) == 0
+        assert Ls.shim_mv_get_y_local(h, hy.data_ptr()) == 0
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item()) / e2e_steps
+    oi = np.zeros(4, np.int32); od = np.zeros(5, np.float64)
+    Ls.shim_mv_solve.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    opts = f"-i cg -p jacobi -maxiter {args.cg_iters} -tol 1e-30".encode()
+    for _ in range(2):
+        rc = Ls.shim_mv_solve(h, opts, oi.ctypes.data, od.ctypes.data, None)
+        assert rc == 0 and oi[2] == 0, (rc, oi)
+    done = int(oi[0]) - (1 if oi[1] == 4 else 0)
+    t = torch.tensor([od[2]], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cg_it_s = done / float(t.item())
+    nnz_all = torch.tensor([nnz], device=dev, dtype=torch.int64)
+    dist.all_reduce(nnz_all)
+    nnz_g = int(nnz_all.item())
+    lib.lis_finalize()
+    if rank != 0:
+        return None
+    bytes_local = 12.0 * nnz + 20.0 * n + 4
+    gf = 2.0 * nnz_g / step_s / 1e9
+    log(f"{world} GPUs: {gf:.1f} GFLOP/s aggregate, {step_s * 1e3:.3f} ms/product, CG {cg_it_s:.1f} it/s")
+    return {
+        "metric": "spmv_csr_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"spmvtest3 {grid * world}x{grid}x{grid} 7-pt Poisson, CSR, {world} row slabs of {grid}^3 (n={n * world}, nnz={nnz_g})",
+                   "l2": "inputs (13.9 GB/step/GPU) exceed L2 by >100x, no flush between steps", "index": "int32 (local numbering + halo)",
+                   "exchange": "2 boundary planes (2 MiB each) per product via grouped ncclSend/ncclRecv; dot partials via ncclAllGather"},
+        "e2e": {"value": 2.0 * nnz_g / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "what": "per rank: local x slice from pinned host + lis_matvec (halo exchange inside) + local y slice to pinned host"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,2,false> (+ halo pack, NCCL p2p)", "achieved": bytes_local / step_s / 1e9,
+                     "peak": peak_gbs, "unit": "GB/s", "frac": bytes_local / step_s / 1e9 / peak_gbs, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "note": "per GPU, whole product incl. halo exchange"},
+        "clocks": clocks,
+        "extra": {"cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": done,
+                  "cg_unfused_formula_gbs_per_gpu": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9},
+    }
+
+
 # ----------------------------------------------------------------------------- lis_b200 arm
 def time_launches(torch, stream, fn, steps, warmup):
     """CUDA events on the launching stream around `steps` back-to-back launches."""
@@ -302,7 +395,8 @@ def run_b200(args, grid):
     Ls.shim_mv_set_x.argtypes = [C.c_int, C.c_void_p]
     Ls.shim_mv_solve.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if world > 1:
-        raise SystemExit("multi-GPU leg: see lis_b200 comm layer (not wired in this build)")
+        return run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, local, ptr, idx, val, n, nnz,
+                              peak_gbs, peak_src)
     t0 = time.time()
     h_ptr, p_ptr = host_malloc_array(n + 1, np.int32)
     h_idx, p_idx = host_malloc_array(nnz, np.int32)
@@ -317,8 +411,6 @@ def run_b200(args, grid):
     log(f"host CSR + lis_matrix_set_csr/assemble in {time.time() - t0:.1f}s")
     for _ in range(max(args.warmup, 1)):                            # first call uploads the matrix mirror
         rc = Ls.shim_mv_step_e2e(h, hx.data_ptr(), hy.data_ptr()); assert rc == 0, rc
-    if dist is not None:
-        dist.barrier()
     torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()

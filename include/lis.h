@@ -492,6 +492,13 @@ LIS_INT lis_b200_set_num_threads(LIS_INT nthreads);
 /* join a process group explicitly (rank, size, 64-bit job token shared by all ranks) instead
  * of through RANK / WORLD_SIZE / MASTER_PORT in the environment */
 LIS_INT lis_b200_comm_attach(LIS_INT rank, LIS_INT nranks, unsigned long long token);
+/* rank-ordered sum of host scalars over the process group (what every dot/nrm2 does) */
+LIS_INT lis_b200_allreduce_sum(double *vals, LIS_INT count);
+/* sizes and lists of A's halo exchange: out = {halo entries, exported entries, neighbours} */
+LIS_INT lis_b200_commtable_info(LIS_MATRIX A, LIS_INT *out, LIS_INT *import_ptr, LIS_INT *export_ptr, LIS_INT *export_index,
+                                LIS_INT *l2g_map, LIS_INT cap);
+/* the CUDA stream (cudaStream_t) all kernels of this process are enqueued on */
+void *lis_b200_stream(void);
 
 /* ------------------------------------------------------------------ file I/O */
 LIS_INT lis_input(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, char *filename);

@@ -1,30 +1,561 @@
 /*
  * lis_comm.c -- process group for the row-partitioned (multi-GPU) path: one process per GPU.
- * Replaces the MPI layer of the reference (src/matrix/lis_matrix_mpi.c, MPI_Allreduce in
- * src/vector/lis_vector_ops.c:119).  See the multi-rank section below.
+ *
+ * Replaces the MPI layer of the reference: lis_matrix_g2l (src/matrix/lis_matrix_mpi.c:55-420),
+ * lis_commtable_create (:594-826), lis_send_recv (:834-954) and the one-scalar MPI_Allreduce of
+ * every reduction (src/vector/lis_vector_ops.c:119,263).  Same semantics: contiguous 1-D row
+ * partition (LIS_GET_ISIE or caller-given local sizes), columns relabelled local-then-halo
+ * with halo slots ordered by global index, neighbour lists, halo values received straight
+ * into x[n .. np), reductions combined in RANK ORDER so every rank gets the same bits.
+ *
+ * Two planes:
+ *   control (host, setup + small scalars): a POSIX shared-memory segment shared by the ranks
+ *     of one node; generation-counted allgather.  Works without a GPU (CPU tests).
+ *   data (device): NCCL over NVLink -- grouped ncclSend/ncclRecv of the packed halo on the
+ *     library stream, ncclAllGather of the per-rank reduction partials.  libnccl is dlopen'ed
+ *     (no link-time dependency; inside a PyTorch process its bundled NCCL is reused).
+ *
+ * Bootstrap: lis_initialize reads RANK / WORLD_SIZE / LOCAL_RANK (and MASTER_PORT for the
+ * segment name) from the environment, or the host program calls lis_b200_comm_attach(rank,
+ * nranks, token) with a job-unique token.
  */
+#define _GNU_SOURCE
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdint.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <dlfcn.h>
+#include <sched.h>
+#include <time.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <cuda_runtime_api.h>
 #include "lis_device.h"
 #include "lis_host.h"
+#include "lis_b200_kernels.h"
 
-static int g_rank = 0, g_nranks = 1;
+#define LISC_MAXR 16
+#define LISC_SLOT (1u << 20)                 /* bytes per rank per exchange round */
+#define LISC_MAGIC 0x4c49534232303001ull
+#define LISC_TIMEOUT_S 180.0
 
-int lisd_rank(void) { return g_rank; }
-int lisd_nranks(void) { return g_nranks; }
+typedef struct {
+    volatile uint64_t magic;
+    volatile uint64_t token;
+    volatile uint64_t epoch;
+    volatile int32_t nranks;
+    volatile uint64_t seq_in[LISC_MAXR * 8];     /* one cache line per rank */
+    volatile uint64_t seq_out[LISC_MAXR * 8];
+    unsigned char slot[LISC_MAXR][LISC_SLOT];
+} lisc_shm_t;
 
-LIS_INT lisd_comm_init(void) { return LIS_SUCCESS; }
-void lisd_comm_finalize(void) {}
+/* ---- NCCL through dlopen ---- */
+typedef struct { char internal[128]; } lisc_nccl_id;
+typedef void *lisc_nccl_comm;
+typedef int (*fn_ncclGetUniqueId)(lisc_nccl_id *);
+typedef int (*fn_ncclCommInitRank)(lisc_nccl_comm *, int, lisc_nccl_id, int);
+typedef int (*fn_ncclCommDestroy)(lisc_nccl_comm);
+typedef int (*fn_ncclAllGather)(const void *, void *, size_t, int, lisc_nccl_comm, cudaStream_t);
+typedef int (*fn_ncclSend)(const void *, size_t, int, int, lisc_nccl_comm, cudaStream_t);
+typedef int (*fn_ncclRecv)(void *, size_t, int, int, lisc_nccl_comm, cudaStream_t);
+typedef int (*fn_ncclGroup)(void);
+typedef const char *(*fn_ncclGetErrorString)(int);
+#define LISC_NCCL_DOUBLE 8                    /* ncclFloat64 */
 
-LIS_INT lisd_allreduce_sum(double *vals, int count) { (void)vals; (void)count; return LIS_SUCCESS; }
-LIS_INT lisd_allreduce_max(double *vals, int count) { (void)vals; (void)count; return LIS_SUCCESS; }
-LIS_INT lisd_allgather_int(const int *mine, int count, int *all) { memcpy(all, mine, sizeof(int) * (size_t)count); return LIS_SUCCESS; }
-LIS_INT lisd_allgatherv_host(double *value, const LIS_INT *ranges, int nprocs) { (void)value; (void)ranges; (void)nprocs; return LIS_SUCCESS; }
-LIS_INT lisd_matrix_g2l(LIS_MATRIX A) { (void)A; return LIS_SUCCESS; }
-LIS_INT lisd_commtable_create(LIS_MATRIX A) { (void)A; return LIS_SUCCESS; }
-LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout) { (void)Ain; (void)Aout; return LIS_SUCCESS; }
-void lisd_commtable_destroy(LIS_COMMTABLE t) { (void)t; }
-LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x) { (void)A; (void)x; return LIS_SUCCESS; }
-LIS_INT lis_send_recv(LIS_COMMTABLE commtable, LIS_SCALAR x[]) { (void)commtable; (void)x; return LIS_SUCCESS; }
-LIS_INT lis_b200_comm_attach(LIS_INT rank, LIS_INT nranks, unsigned long long token) { (void)rank; (void)token; return nranks == 1 ? LIS_SUCCESS : LIS_ERR_NOT_IMPLEMENTED; }
+static struct {
+    int rank, nranks, attached;
+    char name[96];
+    lisc_shm_t *shm;
+    uint64_t gen;
+    /* data plane */
+    void *dl;
+    lisc_nccl_comm comm;
+    int nccl_ok;
+    fn_ncclGetUniqueId GetUniqueId; fn_ncclCommInitRank CommInitRank; fn_ncclCommDestroy CommDestroy;
+    fn_ncclAllGather AllGather; fn_ncclSend Send; fn_ncclRecv Recv; fn_ncclGroup GroupStart, GroupEnd;
+    fn_ncclGetErrorString GetErrorString;
+    double *d_red, *d_all, *h_all;            /* reduction staging: device partials, gathered, pinned */
+} g = { .rank = 0, .nranks = 1 };
+
+int lisd_rank(void) { return g.rank; }
+int lisd_nranks(void) { return g.nranks; }
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static int spin_until(volatile uint64_t *p, uint64_t want)
+{
+    const double t0 = now_s();
+    for (unsigned it = 0; *p < want; it++) {
+        if ((it & 1023) == 1023) {
+            sched_yield();
+            if (now_s() - t0 > LISC_TIMEOUT_S) return -1;
+        }
+    }
+    __sync_synchronize();
+    return 0;
+}
+
+/* one exchange round: rank k contributes lens[k] (<= LISC_SLOT) bytes, which land at
+ * out + offs[k] on every rank.  Generation counters: seq_in[k] = "k has published round g",
+ * seq_out[k] = "k has finished copying round g" (nobody overwrites a slot before that). */
+static LIS_INT shm_round(const void *mine, void *out, const size_t *lens, const size_t *offs)
+{
+    lisc_shm_t *s = g.shm;
+    const uint64_t gen = ++g.gen;
+    if (lens[g.rank] > LISC_SLOT) { LIS_SETERR(LIS_ERR_ILL_ARG, "control-plane message too large\n"); return LIS_ERR_ILL_ARG; }
+    for (int k = 0; k < g.nranks; k++)
+        if (spin_until(&s->seq_out[k * 8], gen - 1)) goto timeout;
+    if (lens[g.rank]) memcpy(s->slot[g.rank], mine, lens[g.rank]);
+    __sync_synchronize();
+    s->seq_in[g.rank * 8] = gen;
+    for (int k = 0; k < g.nranks; k++)
+        if (spin_until(&s->seq_in[k * 8], gen)) goto timeout;
+    for (int k = 0; k < g.nranks; k++)
+        if (lens[k]) memcpy((char *)out + offs[k], s->slot[k], lens[k]);
+    __sync_synchronize();
+    s->seq_out[g.rank * 8] = gen;
+    return LIS_SUCCESS;
+timeout:
+    LIS_SETERR(LIS_ERR_DEVICE, "process group: a rank did not arrive within the timeout\n");
+    return LIS_ERR_DEVICE;
+}
+
+/* every rank contributes `len` bytes; out receives nranks blocks of `len` */
+static LIS_INT shm_allgather(const void *mine, size_t len, void *out)
+{
+    size_t lens[LISC_MAXR], offs[LISC_MAXR];
+    for (int k = 0; k < g.nranks; k++) { lens[k] = len; offs[k] = (size_t)k * len; }
+    return shm_round(mine, out, lens, offs);
+}
+
+/* variable-length allgather: lens[k] bytes from rank k land at out + offs[k]; any size */
+static LIS_INT shm_allgatherv(const void *mine, void *out, const size_t *lens, const size_t *offs)
+{
+    size_t maxlen = 0;
+    for (int k = 0; k < g.nranks; k++) if (lens[k] > maxlen) maxlen = lens[k];
+    for (size_t done = 0; done < maxlen; done += LISC_SLOT) {
+        size_t cl[LISC_MAXR], co[LISC_MAXR];
+        for (int k = 0; k < g.nranks; k++) {
+            cl[k] = lens[k] > done ? (lens[k] - done < LISC_SLOT ? lens[k] - done : LISC_SLOT) : 0;
+            co[k] = offs[k] + done;
+        }
+        LIS_INT err = shm_round((const char *)mine + (cl[g.rank] ? done : 0), out, cl, co);
+        if (err) return err;
+    }
+    return LIS_SUCCESS;
+}
+
+static void nccl_load(void)
+{
+    if (g.dl) return;
+    g.dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!g.dl) g.dl = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!g.dl) return;
+#define LOAD(field, sym) g.field = (fn_##sym)dlsym(g.dl, #sym)
+    LOAD(GetUniqueId, ncclGetUniqueId); LOAD(CommInitRank, ncclCommInitRank); LOAD(CommDestroy, ncclCommDestroy);
+    LOAD(AllGather, ncclAllGather); LOAD(Send, ncclSend); LOAD(Recv, ncclRecv);
+    g.GroupStart = (fn_ncclGroup)dlsym(g.dl, "ncclGroupStart"); g.GroupEnd = (fn_ncclGroup)dlsym(g.dl, "ncclGroupEnd");
+    LOAD(GetErrorString, ncclGetErrorString);
+#undef LOAD
+}
+
+static LIS_INT nccl_check(int rc, const char *what)
+{
+    if (rc == 0) return LIS_SUCCESS;
+    LIS_SETERR2(LIS_ERR_DEVICE, "%s: NCCL error: %s\n", what, g.GetErrorString ? g.GetErrorString(rc) : "?");
+    return LIS_ERR_DEVICE;
+}
+
+static LIS_INT attach(int rank, int nranks, uint64_t token, int token_is_unique)
+{
+    if (g.attached) return LIS_SUCCESS;
+    if (nranks <= 1) { g.rank = 0; g.nranks = 1; return LIS_SUCCESS; }
+    if (nranks > LISC_MAXR || rank < 0 || rank >= nranks) {
+        LIS_SETERR2(LIS_ERR_ILL_ARG, "process group: rank %D of %D is not supported\n", rank, nranks);
+        return LIS_ERR_ILL_ARG;
+    }
+    snprintf(g.name, sizeof(g.name), "/lisb200_%u_%016llx", (unsigned)getuid(), (unsigned long long)token);
+    const uint64_t start = (uint64_t)time(NULL);
+    if (rank == 0) {
+        shm_unlink(g.name);                                  /* leftovers of a crashed job */
+        const int fd = shm_open(g.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)sizeof(lisc_shm_t)) != 0) {
+            LIS_SETERR1(LIS_ERR_DEVICE, "process group: cannot create shared segment %s\n", g.name);
+            return LIS_ERR_DEVICE;
+        }
+        g.shm = (lisc_shm_t *)mmap(NULL, sizeof(lisc_shm_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (g.shm == MAP_FAILED) { g.shm = NULL; LIS_SETERR(LIS_ERR_DEVICE, "process group: mmap failed\n"); return LIS_ERR_DEVICE; }
+        g.shm->token = token; g.shm->nranks = nranks; g.shm->epoch = start;
+        __sync_synchronize();
+        g.shm->magic = LISC_MAGIC;
+    } else {
+        /* open, map and validate; a segment that is not (yet) the one rank 0 of THIS job made --
+         * missing, half initialised, or left behind by a crashed job that used the same
+         * environment-derived name -- is dropped and looked up again */
+        const double t0 = now_s();
+        for (;;) {
+            const int fd = shm_open(g.name, O_RDWR, 0600);
+            if (fd >= 0) {
+                struct stat st;
+                lisc_shm_t *m = NULL;
+                if (fstat(fd, &st) == 0 && (size_t)st.st_size >= sizeof(lisc_shm_t))
+                    m = (lisc_shm_t *)mmap(NULL, sizeof(lisc_shm_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+                close(fd);
+                if (m && m != MAP_FAILED) {
+                    const double t1 = now_s();
+                    while (m->magic != LISC_MAGIC && now_s() - t1 < 0.5) usleep(500);
+                    if (m->magic == LISC_MAGIC && m->token == token && m->nranks == nranks &&
+                        (token_is_unique || m->epoch + 600 >= start)) { g.shm = m; break; }
+                    munmap(m, sizeof(lisc_shm_t));
+                }
+            }
+            if (now_s() - t0 > LISC_TIMEOUT_S) {
+                LIS_SETERR1(LIS_ERR_DEVICE, "process group: segment %s never became ready\n", g.name);
+                return LIS_ERR_DEVICE;
+            }
+            usleep(2000);
+        }
+    }
+    g.rank = rank; g.nranks = nranks; g.gen = 0; g.attached = 1;
+    /* first exchange doubles as a barrier: afterwards the name is no longer needed */
+    int all[LISC_MAXR];
+    LIS_INT err = lisd_allgather_int(&rank, 1, all);
+    if (err) return err;
+    if (rank == 0) shm_unlink(g.name);
+
+    /* data plane */
+    if (lisd_available()) {
+        nccl_load();
+        lisc_nccl_id id;
+        memset(&id, 0, sizeof(id));
+        int have = g.dl && g.GetUniqueId && g.CommInitRank && g.AllGather && g.Send && g.Recv && g.GroupStart && g.GroupEnd;
+        if (have && rank == 0) have = g.GetUniqueId(&id) == 0;
+        lisc_nccl_id ids[LISC_MAXR];
+        err = shm_allgather(&id, sizeof(id), ids);
+        if (err) return err;
+        int haves[LISC_MAXR];
+        err = lisd_allgather_int(&have, 1, haves);
+        if (err) return err;
+        for (int k = 0; k < nranks; k++) have = have && haves[k];
+        if (have) {
+            err = nccl_check(g.CommInitRank(&g.comm, nranks, ids[0], rank), "ncclCommInitRank");
+            if (err) return err;
+            if (cudaMalloc((void **)&g.d_red, 8 * sizeof(double)) != cudaSuccess ||
+                cudaMalloc((void **)&g.d_all, 8 * LISC_MAXR * sizeof(double)) != cudaSuccess ||
+                cudaHostAlloc((void **)&g.h_all, 8 * LISC_MAXR * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                LIS_SETERR_MEM(8 * LISC_MAXR * sizeof(double));
+                return LIS_ERR_OUT_OF_MEMORY;
+            }
+            g.nccl_ok = 1;
+        } else if (rank == 0) {
+            fprintf(stderr, "lis_b200: NCCL not available, halo exchange is disabled\n");
+        }
+    }
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_b200_comm_attach(LIS_INT rank, LIS_INT nranks, unsigned long long token)
+{
+    return attach((int)rank, (int)nranks, (uint64_t)token, 1);
+}
+
+LIS_INT lisd_comm_init(void)
+{
+    if (g.attached) return LIS_SUCCESS;
+    const char *ws = getenv("WORLD_SIZE"), *rk = getenv("RANK");
+    if (!ws || !rk || atoi(ws) <= 1) return LIS_SUCCESS;
+    const char *port = getenv("MASTER_PORT"), *job = getenv("LIS_B200_JOB");
+    uint64_t token = 1469598103934665603ull;
+    for (const char *p = job ? job : (port ? port : "0"); *p; p++) token = (token ^ (unsigned char)*p) * 1099511628211ull;
+    return attach(atoi(rk), atoi(ws), token, job != NULL);
+}
+
+void lisd_comm_finalize(void)
+{
+    if (!g.attached) return;
+    if (g.nccl_ok) {
+        cudaStreamSynchronize((cudaStream_t)lisd_stream());
+        if (g.CommDestroy) g.CommDestroy(g.comm);
+        cudaFree(g.d_red); cudaFree(g.d_all); cudaFreeHost(g.h_all);
+        g.d_red = g.d_all = g.h_all = NULL;
+        g.nccl_ok = 0;
+    }
+    if (g.shm) { munmap(g.shm, sizeof(lisc_shm_t)); g.shm = NULL; }
+    g.attached = 0; g.rank = 0; g.nranks = 1;
+}
+
+/* ------------------------------------------------------------------ host collectives */
+LIS_INT lisd_allgather_int(const int *mine, int count, int *all)
+{
+    if (g.nranks == 1) { memcpy(all, mine, sizeof(int) * (size_t)count); return LIS_SUCCESS; }
+    return shm_allgather(mine, sizeof(int) * (size_t)count, all);
+}
+
+/* sum / max of `count` host scalars over the ranks, combined in rank order on every rank */
+static LIS_INT allreduce_host(double *vals, int count, int is_max)
+{
+    if (g.nranks == 1) return LIS_SUCCESS;
+    double all[LISC_MAXR * 8];
+    if (count > 8) { LIS_SETERR(LIS_ERR_ILL_ARG, "too many scalars in one reduction\n"); return LIS_ERR_ILL_ARG; }
+    LIS_INT err = shm_allgather(vals, sizeof(double) * (size_t)count, all);
+    if (err) return err;
+    for (int c = 0; c < count; c++) {
+        double t = all[c];
+        for (int k = 1; k < g.nranks; k++) {
+            const double v = all[k * count + c];
+            if (is_max) t = v > t ? v : t; else t = t + v;
+        }
+        vals[c] = t;
+    }
+    return LIS_SUCCESS;
+}
+LIS_INT lisd_allreduce_sum(double *vals, int count) { return allreduce_host(vals, count, 0); }
+LIS_INT lisd_allreduce_max(double *vals, int count) { return allreduce_host(vals, count, 1); }
+LIS_INT lis_b200_allreduce_sum(double *vals, LIS_INT count) { return allreduce_host(vals, (int)count, 0); }
+
+/* device path of a reduction: the kernel left `count` partial scalars in lisd_scalar_dev();
+ * NCCL all-gathers them over NVLink, one pinned copy brings the nranks x count table to the
+ * host, the host folds it in rank order (same bits on every rank) */
+int lisd_reduce_uses_nccl(void) { return g.nranks > 1 && g.nccl_ok; }
+double *lisd_reduce_dev_buffer(void) { return g.d_red; }
+
+LIS_INT lisd_reduce_nccl_finish(double *vals, int count, int is_max)
+{
+    cudaStream_t st = (cudaStream_t)lisd_stream();
+    LIS_INT err = nccl_check(g.AllGather(g.d_red, g.d_all, (size_t)count, LISC_NCCL_DOUBLE, g.comm, st), "ncclAllGather(reduction)");
+    if (err) return err;
+    cudaError_t e = cudaMemcpyAsync(g.h_all, g.d_all, sizeof(double) * (size_t)count * (size_t)g.nranks, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    err = lisd_check((int)e, "reduction read-back");
+    if (err) return err;
+    for (int c = 0; c < count; c++) {
+        double t = g.h_all[c];
+        for (int k = 1; k < g.nranks; k++) {
+            const double v = g.h_all[k * count + c];
+            if (is_max) t = v > t ? v : t; else t = t + v;
+        }
+        vals[c] = t;
+    }
+    return LIS_SUCCESS;
+}
+
+/* value[] holds this rank's slice at ranges[rank]; afterwards every rank holds all of it */
+LIS_INT lisd_allgatherv_host(double *value, const LIS_INT *ranges, int nprocs)
+{
+    if (g.nranks == 1) return LIS_SUCCESS;
+    size_t lens[LISC_MAXR], offs[LISC_MAXR];
+    for (int k = 0; k < nprocs; k++) { lens[k] = sizeof(double) * (size_t)(ranges[k + 1] - ranges[k]); offs[k] = sizeof(double) * (size_t)ranges[k]; }
+    double *mine = (double *)malloc(lens[g.rank] ? lens[g.rank] : 8);
+    if (!mine) { LIS_SETERR_MEM(lens[g.rank]); return LIS_OUT_OF_MEMORY; }
+    memcpy(mine, value + ranges[g.rank], lens[g.rank]);
+    LIS_INT err = shm_allgatherv(mine, value, lens, offs);
+    free(mine);
+    return err;
+}
+
+/* ------------------------------------------------------------------ global -> local numbering */
+static int cmp_int(const void *a, const void *b)
+{
+    const int x = *(const int *)a, y = *(const int *)b;
+    return (x > y) - (x < y);
+}
+
+static int owner_of(const LIS_INT *ranges, int nprocs, int gcol)
+{
+    int lo = 0, hi = nprocs;                  /* ranges[lo] <= gcol < ranges[hi] */
+    while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (ranges[mid] <= gcol) lo = mid; else hi = mid; }
+    return lo;
+}
+
+/* CSR with global columns -> local columns: owned columns become c - is, the others get halo
+ * slots n, n+1, ... in ascending global order (lis_matrix_g2l_csr, :222-320) */
+LIS_INT lisd_matrix_g2l(LIS_MATRIX A)
+{
+    if (A->nprocs == 1 || A->l2g_map != NULL) return LIS_SUCCESS;
+    if (A->matrix_type != LIS_MATRIX_CSR) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "row-partitioned matrices must be handed over in CSR (convert afterwards)\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    const LIS_INT n = A->n, is = A->is, ie = A->ie, nnz = A->ptr[n];
+    LIS_INT nh = 0;
+    for (LIS_INT j = 0; j < nnz; j++) if (A->index[j] < is || A->index[j] >= ie) nh++;
+    int *halo = (int *)malloc(sizeof(int) * (size_t)(nh > 0 ? nh : 1));
+    if (!halo) { LIS_SETERR_MEM(nh); return LIS_OUT_OF_MEMORY; }
+    nh = 0;
+    for (LIS_INT j = 0; j < nnz; j++) if (A->index[j] < is || A->index[j] >= ie) halo[nh++] = A->index[j];
+    qsort(halo, (size_t)nh, sizeof(int), cmp_int);
+    LIS_INT nu = 0;
+    for (LIS_INT k = 0; k < nh; k++) if (k == 0 || halo[k] != halo[k - 1]) halo[nu++] = halo[k];
+    A->l2g_map = (LIS_INT *)lis_malloc(sizeof(LIS_INT) * (size_t)(nu > 0 ? nu : 1), "lis_matrix_g2l::l2g_map");
+    if (!A->l2g_map) { free(halo); LIS_SETERR_MEM(nu); return LIS_OUT_OF_MEMORY; }
+    memcpy(A->l2g_map, halo, sizeof(int) * (size_t)nu);
+    free(halo);
+    for (LIS_INT j = 0; j < nnz; j++) {
+        const LIS_INT c = A->index[j];
+        if (c >= is && c < ie) A->index[j] = c - is;
+        else {
+            const int *hit = (const int *)bsearch(&c, A->l2g_map, (size_t)nu, sizeof(int), cmp_int);
+            A->index[j] = n + (LIS_INT)(hit - A->l2g_map);
+        }
+    }
+    A->np = n + nu;
+    A->is_sorted = LIS_FALSE;
+    lisd_matrix_drop(A);
+    return LIS_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ communication table */
+struct LIS_COMMTABLE_STRUCT {
+    int nranks, rank;
+    int n;                                    /* owned rows: halo values land at x[n ...] */
+    int n_import, n_export;
+    int import_ptr[LISC_MAXR + 1];            /* halo slots owned by rank k: [import_ptr[k], import_ptr[k+1]) */
+    int export_ptr[LISC_MAXR + 1];            /* entries of export_index wanted by rank k */
+    int *export_index;                        /* local row numbers, host */
+    int *d_export_index;                      /* device copy */
+    double *d_ws;                             /* packed send buffer, device */
+    int neibpetot;                            /* number of ranks exchanged with (information) */
+};
+
+void lisd_commtable_destroy(LIS_COMMTABLE t)
+{
+    if (t == NULL) return;
+    free(t->export_index);
+    lisd_free(t->d_export_index);
+    lisd_free(t->d_ws);
+    free(t);
+}
+
+static LIS_INT commtable_to_device(LIS_COMMTABLE t)
+{
+    if (!lisd_available() || t->n_export == 0) return LIS_SUCCESS;
+    LIS_INT err = lisd_malloc((void **)&t->d_export_index, sizeof(int) * (size_t)t->n_export);
+    if (!err) err = lisd_upload(t->d_export_index, t->export_index, sizeof(int) * (size_t)t->n_export);
+    if (!err) err = lisd_malloc((void **)&t->d_ws, sizeof(double) * (size_t)t->n_export);
+    return err;
+}
+
+LIS_INT lisd_commtable_create(LIS_MATRIX A)
+{
+    if (A->nprocs == 1 || A->commtable) return LIS_SUCCESS;
+    const int np_ = A->nprocs, me = A->my_rank;
+    const LIS_INT nh = A->np - A->n;
+    LIS_COMMTABLE t = (LIS_COMMTABLE)calloc(1, sizeof(struct LIS_COMMTABLE_STRUCT));
+    if (!t) { LIS_SETERR_MEM(sizeof(struct LIS_COMMTABLE_STRUCT)); return LIS_OUT_OF_MEMORY; }
+    t->nranks = np_; t->rank = me; t->n = A->n; t->n_import = nh;
+    /* import side: my halo list is sorted by global index, i.e. grouped by owner */
+    for (int k = 0; k <= np_; k++) t->import_ptr[k] = 0;
+    for (LIS_INT h = 0; h < nh; h++) t->import_ptr[owner_of(A->ranges, np_, A->l2g_map[h]) + 1]++;
+    for (int k = 0; k < np_; k++) t->import_ptr[k + 1] += t->import_ptr[k];
+    /* export side: everybody publishes its halo list; I pick what falls into my rows */
+    int counts[LISC_MAXR], mine = (int)nh;
+    LIS_INT err = lisd_allgather_int(&mine, 1, counts);
+    if (err) { free(t); return err; }
+    size_t lens[LISC_MAXR], offs[LISC_MAXR], total = 0;
+    for (int k = 0; k < np_; k++) { lens[k] = sizeof(int) * (size_t)counts[k]; offs[k] = total; total += lens[k]; }
+    int *all = (int *)malloc(total ? total : 4);
+    if (!all) { free(t); LIS_SETERR_MEM(total); return LIS_OUT_OF_MEMORY; }
+    err = shm_allgatherv(A->l2g_map, all, lens, offs);
+    if (err) { free(all); free(t); return err; }
+    int nexp = 0;
+    for (int k = 0; k < np_; k++) {
+        const int *lst = (const int *)((const char *)all + offs[k]);
+        t->export_ptr[k] = nexp;
+        if (k == me) continue;
+        for (int h = 0; h < counts[k]; h++) if (lst[h] >= A->is && lst[h] < A->ie) nexp++;
+    }
+    t->export_ptr[np_] = nexp;
+    t->n_export = nexp;
+    t->export_index = (int *)malloc(sizeof(int) * (size_t)(nexp > 0 ? nexp : 1));
+    if (!t->export_index) { free(all); free(t); LIS_SETERR_MEM(nexp); return LIS_OUT_OF_MEMORY; }
+    nexp = 0;
+    for (int k = 0; k < np_; k++) {
+        const int *lst = (const int *)((const char *)all + offs[k]);
+        if (k == me) continue;
+        for (int h = 0; h < counts[k]; h++) if (lst[h] >= A->is && lst[h] < A->ie) t->export_index[nexp++] = lst[h] - A->is;
+    }
+    free(all);
+    for (int k = 0; k < np_; k++)
+        if (k != me && (t->import_ptr[k + 1] > t->import_ptr[k] || t->export_ptr[k + 1] > t->export_ptr[k])) t->neibpetot++;
+    err = commtable_to_device(t);
+    if (err) { lisd_commtable_destroy(t); return err; }
+    A->commtable = t;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout)
+{
+    const LIS_COMMTABLE s = Ain->commtable;
+    if (s == NULL) return LIS_SUCCESS;
+    LIS_COMMTABLE t = (LIS_COMMTABLE)malloc(sizeof(struct LIS_COMMTABLE_STRUCT));
+    if (!t) { LIS_SETERR_MEM(sizeof(struct LIS_COMMTABLE_STRUCT)); return LIS_OUT_OF_MEMORY; }
+    memcpy(t, s, sizeof(*t));
+    t->d_export_index = NULL; t->d_ws = NULL;
+    t->export_index = (int *)malloc(sizeof(int) * (size_t)(s->n_export > 0 ? s->n_export : 1));
+    if (!t->export_index) { free(t); LIS_SETERR_MEM(s->n_export); return LIS_OUT_OF_MEMORY; }
+    memcpy(t->export_index, s->export_index, sizeof(int) * (size_t)s->n_export);
+    LIS_INT err = commtable_to_device(t);
+    if (err) { lisd_commtable_destroy(t); return err; }
+    Aout->commtable = t;
+    return LIS_SUCCESS;
+}
+
+/* sizes and index lists, for tests and diagnostics: out = {n_import, n_export, neighbours} */
+LIS_INT lis_b200_commtable_info(LIS_MATRIX A, LIS_INT *out, LIS_INT *import_ptr, LIS_INT *export_ptr, LIS_INT *export_index,
+                                LIS_INT *l2g_map, LIS_INT cap)
+{
+    const LIS_COMMTABLE t = A->commtable;
+    for (LIS_INT k = 0; l2g_map && A->l2g_map && k < A->np - A->n && k < cap; k++) l2g_map[k] = A->l2g_map[k];
+    if (t == NULL) { out[0] = out[1] = out[2] = 0; return LIS_SUCCESS; }
+    out[0] = t->n_import; out[1] = t->n_export; out[2] = t->neibpetot;
+    for (int k = 0; k <= t->nranks; k++) { if (import_ptr) import_ptr[k] = t->import_ptr[k]; if (export_ptr) export_ptr[k] = t->export_ptr[k]; }
+    for (int k = 0; export_index && k < t->n_export && k < cap; k++) export_index[k] = t->export_index[k];
+    return LIS_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ halo exchange
+ * pack ws[i] = x[export_index[i]] (one gather kernel), then one NCCL group of sends/receives;
+ * received values land directly in x[n + import_ptr[k] ...].  Asynchronous on the stream. */
+static LIS_INT halo_exchange_raw(LIS_COMMTABLE t, LIS_INT n, double *x)
+{
+    if (t == NULL || g.nranks == 1) return LIS_SUCCESS;
+    if (!g.nccl_ok) { LIS_SETERR(LIS_ERR_DEVICE, "halo exchange needs NCCL (not available in this process group)\n"); return LIS_ERR_DEVICE; }
+    cudaStream_t st = (cudaStream_t)lisd_stream();
+    LIS_INT err;
+    if (t->n_export) {
+        lisd_mark_busy();
+        err = lisd_check(lisb200_gather(t->n_export, t->d_export_index, x, t->d_ws, st), "halo pack");
+        if (err) return err;
+    }
+    err = nccl_check(g.GroupStart(), "ncclGroupStart");
+    if (err) return err;
+    for (int k = 0; k < t->nranks; k++) {
+        if (k == t->rank) continue;
+        const int ne = t->export_ptr[k + 1] - t->export_ptr[k], ni = t->import_ptr[k + 1] - t->import_ptr[k];
+        if (ne) { err = nccl_check(g.Send(t->d_ws + t->export_ptr[k], (size_t)ne, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclSend"); if (err) { g.GroupEnd(); return err; } }
+        if (ni) { err = nccl_check(g.Recv(x + n + t->import_ptr[k], (size_t)ni, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclRecv"); if (err) { g.GroupEnd(); return err; } }
+    }
+    lisd_mark_busy();
+    return nccl_check(g.GroupEnd(), "ncclGroupEnd");
+}
+
+LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x) { return halo_exchange_raw(A->commtable, A->n, x->value); }
+
+/* public seam of the reference (src/matrix/lis_matrix_mpi.c:834): x has np entries, the
+ * halo is received into x[n .. np).  Host-synchronous like every public entry point. */
+LIS_INT lis_send_recv(LIS_COMMTABLE commtable, LIS_SCALAR x[])
+{
+    if (commtable == NULL || g.nranks == 1) return LIS_SUCCESS;
+    LIS_INT err = halo_exchange_raw(commtable, commtable->n, x);
+    if (err) return err;
+    return lisd_sync();
+}

@@ -56,6 +56,7 @@ LIS_INT lisd_require(const char *what)
 }
 
 void *lisd_stream(void) { lisd_probe(); return (void *)g_ctx.stream; }
+void *lis_b200_stream(void) { return lisd_stream(); }
 void lisd_mark_busy(void) { g_ctx.busy = 1; }
 
 LIS_INT lisd_check(int rc, const char *what)
@@ -253,5 +254,11 @@ double *lisd_partial(size_t slots)
 }
 
 unsigned int *lisd_counter(void) { return g_ctx.counter; }
-double *lisd_scalar_dev(int slot) { return g_ctx.d_scalar + slot; }
+/* where a reduction kernel writes its scalar(s): mapped pinned host memory on one rank (the
+ * host reads it right after the stream sync), a device buffer feeding ncclAllGather otherwise */
+double *lisd_scalar_dev(int slot)
+{
+    if (lisd_reduce_uses_nccl()) return lisd_reduce_dev_buffer() + slot;
+    return g_ctx.d_scalar + slot;
+}
 double lisd_scalar_get(int slot) { return ((volatile double *)g_ctx.h_scalar)[slot]; }

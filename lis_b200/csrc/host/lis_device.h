@@ -101,6 +101,9 @@ LIS_INT lisd_reduce_finish(double *vals, int count, int is_max);
 int     lisd_rank(void);
 int     lisd_nranks(void);
 LIS_INT lisd_comm_init(void);                       /* reads RANK/WORLD_SIZE/LOCAL_RANK */
+int     lisd_reduce_uses_nccl(void);
+double *lisd_reduce_dev_buffer(void);
+LIS_INT lisd_reduce_nccl_finish(double *vals, int count, int is_max);
 LIS_INT lisd_allreduce_sum(double *vals, int count);/* host scalars, in place, rank-ordered */
 LIS_INT lisd_allreduce_max(double *vals, int count);
 LIS_INT lisd_allgather_int(const int *mine, int count, int *all);

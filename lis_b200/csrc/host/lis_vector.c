@@ -325,6 +325,7 @@ LIS_INT lisd_pmul(LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR z)
 /* wait for the enqueued reduction kernel, read `count` mapped scalars, combine across ranks */
 LIS_INT lisd_reduce_finish(double *vals, int count, int is_max)
 {
+    if (lisd_reduce_uses_nccl()) return lisd_reduce_nccl_finish(vals, count, is_max);
     LIS_INT err = lisd_sync();
     if (err) return err;
     for (int k = 0; k < count; k++) vals[k] = lisd_scalar_get(k);

@@ -1,0 +1,145 @@
+"""One rank of the multi-process tests (launched by test_multi_rank.py with RANK / WORLD_SIZE /
+MASTER_ADDR / MASTER_PORT set).  gloo carries the harness traffic (token broadcast, result
+gathering); the library's own process group does the work being tested.
+
+mode cpu : host-side logic only -- row partition, global->local numbering, halo lists,
+           rank-ordered host allreduce.  No GPU needed.
+mode gpu : one GPU per rank -- row-partitioned SpMV (halo exchange over NCCL) and solvers,
+           compared by rank 0 with the single-process oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import harness as H  # noqa: E402
+import lis_b200  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tok = torch.zeros(1, dtype=torch.int64)
+    if rank == 0:
+        tok[0] = int.from_bytes(os.urandom(7), "little")
+    dist.broadcast(tok, 0)
+    lib = lis_b200.load_library()
+    lib.lis_b200_comm_attach.argtypes = [C.c_int, C.c_int, C.c_ulonglong]
+    assert lib.lis_b200_comm_attach(rank, world, int(tok[0])) == 0
+    shim = lis_b200.load_shim()
+    L = shim.lib
+
+    l, m, n = 3 * world + 1, 5, 4                      # planes do not divide evenly among the ranks
+    ptr, idx, val = H.poisson3d_7pt(l, m, n)
+    gn = l * m * n
+    # reference partition LIS_GET_ISIE(rank, world, gn)
+    q, r = divmod(gn, world)
+    sizes = [q + 1 if k < r else q for k in range(world)]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    is_, ie = int(starts[rank]), int(starts[rank + 1])
+    lp = (ptr[is_:ie + 1] - ptr[is_]).astype(np.int32)
+    li = np.ascontiguousarray(idx[ptr[is_]:ptr[ie]]); lv = np.ascontiguousarray(val[ptr[is_]:ptr[ie]])
+    nl = ie - is_
+
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C"); f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    # ---- host-side logic through the public API (works without a device)
+    A = C.c_void_p()
+    assert lib.lis_matrix_create(1, C.byref(A)) == 0
+    assert lib.lis_matrix_set_size(A, 0, gn) == 0       # global size given: LIS_GET_ISIE split
+    a, b = C.c_int(), C.c_int()
+    assert lib.lis_matrix_get_range(A, C.byref(a), C.byref(b)) == 0
+    assert (a.value, b.value) == (is_, ie), ((a.value, b.value), (is_, ie))
+    libc = C.CDLL("libc.so.6"); libc.malloc.restype = C.c_void_p; libc.malloc.argtypes = [C.c_size_t]
+
+    def to_malloc(arr):
+        p = libc.malloc(max(arr.nbytes, 8))
+        C.memmove(p, arr.ctypes.data, arr.nbytes)
+        return p
+    lib.lis_matrix_set_csr.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.lis_matrix_set_csr(int(lp[-1]), to_malloc(lp), to_malloc(li), to_malloc(lv), A) == 0
+    assert lib.lis_matrix_assemble(A) == 0
+    lib.lis_b200_commtable_info.argtypes = [C.c_void_p, i32p, i32p, i32p, i32p, i32p, C.c_int]
+    out = np.zeros(3, np.int32); imp = np.zeros(world + 1, np.int32); exp = np.zeros(world + 1, np.int32)
+    cap = 4096
+    ex = np.zeros(cap, np.int32); l2g = np.zeros(cap, np.int32)
+    assert lib.lis_b200_commtable_info(A, out, imp, exp, ex, l2g, cap) == 0
+    # expectation from the global matrix
+    cols = idx[ptr[is_]:ptr[ie]]
+    halo = np.unique(cols[(cols < is_) | (cols >= ie)])
+    assert out[0] == len(halo) and np.array_equal(l2g[:len(halo)], halo), "halo list (l2g_map)"
+    owner = np.searchsorted(starts, halo, side="right") - 1
+    assert np.array_equal(np.diff(imp), np.bincount(owner, minlength=world)), "import_ptr"
+    want_ex = []
+    for k in range(world):
+        if k == rank:
+            continue
+        ck = idx[ptr[starts[k]]:ptr[starts[k + 1]]]
+        hk = np.unique(ck[(ck < starts[k]) | (ck >= starts[k + 1])])
+        want_ex.append(hk[(hk >= is_) & (hk < ie)] - is_)
+    want_ex = np.concatenate(want_ex) if want_ex else np.zeros(0, np.int64)
+    assert out[1] == len(want_ex) and np.array_equal(ex[:len(want_ex)], want_ex), "export_index"
+    # rank-ordered host allreduce: identical bits on every rank
+    vals = np.array([0.1 * (rank + 1) + 1e-17 * rank, float(rank)], np.float64)
+    lib.lis_b200_allreduce_sum.argtypes = [f64p, C.c_int]
+    assert lib.lis_b200_allreduce_sum(vals, 2) == 0
+    expect = 0.0
+    for k in range(world):
+        expect = expect + (0.1 * (k + 1) + 1e-17 * k) if k else 0.1 * (k + 1) + 1e-17 * k
+    assert vals[0] == expect and vals[1] == sum(range(world)), (vals, expect)
+    lib.lis_matrix_destroy(A)
+
+    result = {"rank": rank, "mode": mode}
+    if mode == "gpu":
+        L.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p]
+        L.shim_mv_set_x_local.argtypes = [C.c_int, f64p]; L.shim_mv_get_y_local.argtypes = [C.c_int, f64p]
+        L.shim_mv_dot_xy.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.shim_mv_solve_b.argtypes = [C.c_int, C.c_char_p, f64p, f64p, i32p, f64p, f64p, C.c_int]
+        x = H.rand_vec(gn, 5, "wide")
+        o = H.Oracle()
+        y_full = o.spmv("csr", ptr, idx, val, x)
+        bvec = o.spmv("csr", ptr, idx, val, np.ones(gn))
+        for fmt in ("csr", "ell", "dia", "jad"):
+            h = L.shim_mv_open_dist(lis_b200.FMT[fmt], nl, lp, li, lv)
+            assert h >= 0, (fmt, h)
+            assert L.shim_mv_set_x_local(h, np.ascontiguousarray(x[is_:ie])) == 0
+            for rep in range(2):                        # second product: the halo buffer is reused
+                assert L.shim_mv_matvec(h) == 0
+            yl = np.zeros(nl)
+            assert L.shim_mv_get_y_local(h, yl) == 0
+            H.assert_bits_equal(yl, y_full[is_:ie], f"rank {rank} spmv {fmt}")
+            d = C.c_double()
+            assert L.shim_mv_dot_xy(h, C.byref(d)) == 0
+            assert abs(d.value - float(np.dot(x, y_full))) <= 1e-9 * abs(float(np.dot(np.abs(x), np.abs(y_full))))
+            if fmt == "csr":
+                for opts, solver, pre in (("-i cg -p jacobi", "cg", "jacobi"), ("-i bicgstab -p jacobi", "bicgstab", "jacobi"),
+                                          ("-i gmres -restart 20 -p none", "gmres", "none"), ("-i cg -p ssor", "cg", "ssor")):
+                    xl = np.zeros(nl); oi = np.zeros(4, np.int32); od = np.zeros(4); rh = np.zeros(5000)
+                    rc = L.shim_mv_solve_b(h, opts.encode(), np.ascontiguousarray(bvec[is_:ie]), xl, oi, od, rh, 5000)
+                    assert rc == 0 and oi[1] == 0, (opts, rc, oi)
+                    assert np.abs(xl - 1.0).max() < 1e-8, opts
+                    kw = {"restart": 20} if solver == "gmres" else {}
+                    if pre == "ssor":
+                        # block-SSOR: one block per rank == the OpenMP reference with `world` threads
+                        ref = o.solve(solver, ptr, idx, val, bvec, precon=pre, nthreads=1, ssor_blocks=world, **kw)
+                    else:
+                        ref = o.solve(solver, ptr, idx, val, bvec, precon=pre, **kw)
+                    tol_it = 1 if solver == "bicgstab" else 0
+                    assert abs(int(oi[0]) - ref["iter"]) <= tol_it, (opts, int(oi[0]), ref["iter"])
+                    result[opts] = int(oi[0])
+            L.shim_mv_close(h)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, result)
+    dist.barrier()
+    lib.lis_finalize()
+    if rank == 0:
+        print("MR_OK", gathered)
+
+
+if __name__ == "__main__":
+    main()

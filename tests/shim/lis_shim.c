@@ -473,6 +473,52 @@ EXPORT int shim_mv_open(int fmt, int n, int *ptr, int *idx, double *val, int bnr
     return h;
 }
 
+/* row-partitioned: this rank hands over its n_local rows with GLOBAL column indices
+ * (lis_matrix_set_size(A, n_local, 0), like an MPI rank of the reference would) */
+EXPORT int shim_mv_open_dist(int fmt, int n_local, const int *ptr, const int *idx, const double *val)
+{
+    int h;
+    LIS_MATRIX A0 = NULL, A = NULL;
+    LIS_INT err, *p, *ix;
+    LIS_SCALAR *v;
+    const int nnz = ptr[n_local];
+    for (h = 0; h < 8 && g_mv[h].A; h++) ;
+    if (h == 8) return -1;
+    err = lis_matrix_create(LIS_COMM_WORLD, &A0); if (err) return -2;
+    err = lis_matrix_set_size(A0, n_local, 0); if (err) return -2;
+    p = (LIS_INT *)malloc(sizeof(LIS_INT) * ((size_t)n_local + 1));
+    ix = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(nnz > 0 ? nnz : 1));
+    v = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(nnz > 0 ? nnz : 1));
+    if (!p || !ix || !v) return -2;
+    memcpy(p, ptr, sizeof(LIS_INT) * ((size_t)n_local + 1));
+    memcpy(ix, idx, sizeof(LIS_INT) * (size_t)nnz);
+    memcpy(v, val, sizeof(LIS_SCALAR) * (size_t)nnz);
+    err = lis_matrix_set_csr(nnz, p, ix, v, A0); if (err) return -2;
+    err = lis_matrix_assemble(A0); if (err) return -2;
+    if (fmt == LIS_MATRIX_CSR) A = A0;
+    else {
+        if (convert_to(A0, fmt, 0, 0, &A)) return -3;
+        lis_matrix_destroy(A0);
+    }
+    if (make_vec(A, NULL, &g_mv[h].x) || make_vec(A, NULL, &g_mv[h].y)) return -4;
+    g_mv[h].A = A;
+    return h;
+}
+
+/* local slices in and out (each rank passes / receives only its own rows) */
+EXPORT int shim_mv_set_x_local(int h, double *x_local)
+{
+    LIS_VECTOR x = g_mv[h].x;
+    return (int)lis_vector_set_values2(LIS_INS_VALUE, x->is, x->n, x_local, x);
+}
+EXPORT int shim_mv_get_y_local(int h, double *y_local)
+{
+    LIS_VECTOR y = g_mv[h].y;
+    return (int)lis_vector_get_values(y, y->is, y->n, y_local);
+}
+EXPORT int shim_mv_matvec(int h) { return (int)lis_matvec(g_mv[h].A, g_mv[h].x, g_mv[h].y); }
+EXPORT int shim_mv_dot_xy(int h, double *out) { LIS_SCALAR s = 0; LIS_INT e = lis_vector_dot(g_mv[h].x, g_mv[h].y, &s); *out = s; return (int)e; }
+
 EXPORT int shim_mv_step_e2e(int h, double *host_x, double *host_y)
 {
     LIS_INT err = lis_vector_scatter(host_x, g_mv[h].x); if (err) return (int)err;
@@ -522,6 +568,36 @@ EXPORT int shim_mv_solve(int h, const char *options, int *out_i, double *out_d, 
     out_d[0] = resid; out_d[1] = time; out_d[2] = itime; out_d[3] = ptime;
     lis_solver_destroy(solver);
     lis_vector_destroy(u); lis_vector_destroy(b); lis_vector_destroy(x);
+    return (int)err;
+}
+
+/* lis_solve with a caller-given right-hand side slice; x_local and rhistory returned */
+EXPORT int shim_mv_solve_b(int h, const char *options, const double *b_local, double *x_local, int *out_i, double *out_d,
+                           double *rhistory, int rh_cap)
+{
+    LIS_MATRIX A = g_mv[h].A;
+    LIS_VECTOR b, x;
+    LIS_SOLVER solver;
+    LIS_INT err, iter = 0, status = 0;
+    LIS_REAL resid = 0.0;
+    if (make_vec(A, NULL, &b) || make_vec(A, NULL, &x)) return -1;
+    err = lis_vector_set_values2(LIS_INS_VALUE, b->is, b->n, (LIS_SCALAR *)b_local, b); if (err) return (int)err;
+    err = lis_solver_create(&solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)"-print mem", solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)options, solver); if (err) return (int)err;
+    { const int q = quiet_begin(); err = lis_solve(A, b, x, solver); quiet_end(q); }
+    out_i[2] = (int)err;
+    lis_solver_get_iter(solver, &iter);
+    lis_solver_get_status(solver, &status);
+    lis_solver_get_residualnorm(solver, &resid);
+    out_i[0] = (int)iter; out_i[1] = (int)status; out_d[0] = resid;
+    int len = (int)iter + 1 - (status != LIS_SUCCESS ? 1 : 0);
+    if (len > rh_cap) len = rh_cap;
+    out_i[3] = 0;
+    if (!err && len > 0 && solver->rhistory) { memcpy(rhistory, solver->rhistory, sizeof(double) * (size_t)len); out_i[3] = len; }
+    if (!err) err = lis_vector_get_values(x, x->is, x->n, x_local);
+    lis_solver_destroy(solver);
+    lis_vector_destroy(b); lis_vector_destroy(x);
     return (int)err;
 }
 

@@ -1,0 +1,53 @@
+"""Multi-process tests of the row-partitioned path: world_size 2 (and 3) processes on one host.
+CPU part (always): partition, global->local numbering, halo lists and the rank-ordered host
+allreduce, with gloo carrying the harness traffic.  GPU part (-m gpu, needs >= 2 GPUs):
+SpMV with NCCL halo exchange and the solvers against the single-process oracle."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def launch(world, mode, timeout=300):
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), GLOO_SOCKET_IFNAME="lo")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mr_worker.py"), mode], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(o)
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
+    assert "MR_OK" in outs[0], outs[0][-2000:]
+    return outs[0]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partition_and_halo_lists_cpu(built, world):
+    launch(world, "cpu")
+
+
+@pytest.mark.gpu
+def test_row_partitioned_spmv_and_solvers_2gpu(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    launch(2, "gpu", timeout=600)
