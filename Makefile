@@ -14,8 +14,25 @@ HSRC     := $(wildcard lis_b200/csrc/host/*.c)
 KOBJ     := $(patsubst lis_b200/csrc/kernels/%.cu,$(OBJ)/k_%.o,$(KSRC))
 HOBJ     := $(patsubst lis_b200/csrc/host/%.c,$(OBJ)/h_%.o,$(HSRC))
 
+# the reference's own drivers, compiled UNCHANGED from where they lie in the reference tree
+# against include/ + liblis_b200.so (drop-in check).  Only where the reference tree exists; the
+# binaries travel to the GPU box with the snapshot.
+REF      ?= /root/reference
+DRIVERS  := spmvtest1 spmvtest2 spmvtest2b spmvtest3 spmvtest3b test1 test2 test3 test3b test4 test5
+DRVBIN   := $(patsubst %,$(OUT)/drivers/%,$(DRIVERS))
+
 .PHONY: all clean drivers
+ifneq ($(wildcard $(REF)/test/spmvtest3.c),)
+all: $(OUT)/liblis_b200.so $(OUT)/liblis_b200_shim.so drivers
+drivers: $(DRVBIN)
+$(OUT)/drivers/%: $(REF)/test/%.c $(OUT)/liblis_b200.so $(wildcard include/*.h)
+	@mkdir -p $(OUT)/drivers
+	$(CC) -O2 -DHAVE_CONFIG_H -Iinclude -o $@ $< -L$(OUT) -llis_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
+else
 all: $(OUT)/liblis_b200.so $(OUT)/liblis_b200_shim.so
+drivers:
+	@echo "reference tree $(REF) not present: using prebuilt drivers (if any)"
+endif
 
 # the shared test driver (tests/shim/lis_shim.c, public API only) against this library
 $(OUT)/liblis_b200_shim.so: tests/shim/lis_shim.c $(OUT)/liblis_b200.so $(wildcard include/*.h)

@@ -233,13 +233,50 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
 
 // ---- ELL -------------------------------------------------------------------------------
 // y[i] = 0; for j<maxnzr: y[i] += value[j*ld+i]*x[index[j*ld+i]]  (lis_matvec_ell.c:110-128)
+// Column-major sweep, every idx/val load coalesced.  kPair: a thread owns rows 2t and 2t+1 and
+// moves them with one 64-bit index load and one 128-bit value load per slot (ld even).
+template <bool kPair>
 __global__ void __launch_bounds__(256)
 ell_kernel(int n, int maxnzr, int ld, const int *__restrict__ idx, const double *__restrict__ val,
            const double *__restrict__ x, double *__restrict__ y)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kPair) {
+        const int i = 2 * t;
+        if (i + 1 < n) {
+            double t0 = 0.0, t1 = 0.0;
+            int j = 0;
+            for (; j + 2 <= maxnzr; j += 2) {        // 2 slots x 2 rows in flight
+                const size_t o = (size_t)j * ld + i;
+                const int2 ca = *reinterpret_cast<const int2 *>(idx + o);
+                const int2 cb = *reinterpret_cast<const int2 *>(idx + o + ld);
+                const double2 va = ld_stream2(reinterpret_cast<const double2 *>(val + o));
+                const double2 vb = ld_stream2(reinterpret_cast<const double2 *>(val + o + ld));
+                const double xa0 = __ldg(x + ca.x), xa1 = __ldg(x + ca.y), xb0 = __ldg(x + cb.x), xb1 = __ldg(x + cb.y);
+                t0 = add(t0, mul(va.x, xa0)); t1 = add(t1, mul(va.y, xa1));
+                t0 = add(t0, mul(vb.x, xb0)); t1 = add(t1, mul(vb.y, xb1));
+            }
+            for (; j < maxnzr; ++j) {
+                const size_t o = (size_t)j * ld + i;
+                const int2 c = *reinterpret_cast<const int2 *>(idx + o);
+                const double2 v = ld_stream2(reinterpret_cast<const double2 *>(val + o));
+                t0 = add(t0, mul(v.x, __ldg(x + c.x))); t1 = add(t1, mul(v.y, __ldg(x + c.y)));
+            }
+            *reinterpret_cast<double2 *>(y + i) = make_double2(t0, t1);
+            return;
+        }
+        if (i >= n) return;
+        double tt = 0.0;                               // odd n: the last row alone
+        for (int j = 0; j < maxnzr; ++j) {
+            const size_t o = (size_t)j * ld + i;
+            tt = add(tt, mul(ld_stream(val + o), __ldg(x + ld_stream(idx + o))));
+        }
+        y[i] = tt;
+        return;
+    }
+    const int i = t;
     if (i >= n) return;
-    double t = 0.0;
+    double tt = 0.0;
     int j = 0;
     for (; j + 4 <= maxnzr; j += 4) {       // 4 independent idx/val streams in flight
         const size_t o = (size_t)j * ld + i;
@@ -248,43 +285,57 @@ ell_kernel(int n, int maxnzr, int ld, const int *__restrict__ idx, const double 
         const double v0 = ld_stream(val + o), v1 = ld_stream(val + o + ld);
         const double v2 = ld_stream(val + o + 2 * (size_t)ld), v3 = ld_stream(val + o + 3 * (size_t)ld);
         const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-        t = add(t, mul(v0, x0)); t = add(t, mul(v1, x1));
-        t = add(t, mul(v2, x2)); t = add(t, mul(v3, x3));
+        tt = add(tt, mul(v0, x0)); tt = add(tt, mul(v1, x1));
+        tt = add(tt, mul(v2, x2)); tt = add(tt, mul(v3, x3));
     }
     for (; j < maxnzr; ++j) {
         const size_t o = (size_t)j * ld + i;
-        t = add(t, mul(ld_stream(val + o), __ldg(x + ld_stream(idx + o))));
+        tt = add(tt, mul(ld_stream(val + o), __ldg(x + ld_stream(idx + o))));
     }
-    y[i] = t;
+    y[i] = tt;
 }
 
 // ---- DIA -------------------------------------------------------------------------------
 // y[i] = 0; for each diagonal j with offset off[j]: rows max(0,-off) <= i < min(n, xlen-off)
 //   y[i] += value[j*ld+i]*x[i+off]                                (lis_matvec_dia.c:150-172)
+// kPair: two adjacent rows per thread, one 128-bit value load per diagonal (ld even).
 constexpr int kDiaMaxOff = 64;
+template <bool kPair>
 __global__ void __launch_bounds__(256)
 dia_kernel(int n, int xlen, int nnd, int ld, const int *__restrict__ off,
            const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
 {
     __shared__ int soff[kDiaMaxOff];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double t = 0.0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = kPair ? 2 * t : t;
+    double t0 = 0.0, t1 = 0.0;
     for (int j0 = 0; j0 < nnd; j0 += kDiaMaxOff) {
         const int nj = min(kDiaMaxOff, nnd - j0);
         __syncthreads();
         if (threadIdx.x < nj) soff[threadIdx.x] = off[j0 + threadIdx.x];
         __syncthreads();
-        if (i < n) {
+        if (kPair && i + 1 < n) {
 #pragma unroll 4
             for (int j = 0; j < nj; ++j) {
-                const int o = soff[j];
-                const int c = i + o;
+                const int c = i + soff[j];
+                const bool in0 = c >= 0 && c < xlen, in1 = c + 1 >= 0 && c + 1 < xlen;
+                if (in0 | in1) {
+                    const double2 v = ld_stream2(reinterpret_cast<const double2 *>(val + (size_t)(j0 + j) * ld + i));
+                    if (in0) t0 = add(t0, mul(v.x, __ldg(x + c)));
+                    if (in1) t1 = add(t1, mul(v.y, __ldg(x + c + 1)));
+                }
+            }
+        } else if (i < n) {
+#pragma unroll 4
+            for (int j = 0; j < nj; ++j) {
+                const int c = i + soff[j];
                 if (c >= 0 && c < xlen)
-                    t = add(t, mul(ld_stream(val + (size_t)(j0 + j) * ld + i), __ldg(x + c)));
+                    t0 = add(t0, mul(ld_stream(val + (size_t)(j0 + j) * ld + i), __ldg(x + c)));
             }
         }
     }
-    if (i < n) y[i] = t;
+    if (kPair && i + 1 < n) *reinterpret_cast<double2 *>(y + i) = make_double2(t0, t1);
+    else if (i < n) y[i] = t0;
 }
 
 // ---- JAD -------------------------------------------------------------------------------
@@ -519,7 +570,9 @@ extern "C" int lisb200_spmv_ell(int n, int maxnzr, int ld, const int *d_idx, con
                                 const double *d_x, double *d_y, void *stream)
 {
     if (n <= 0) return 0;
-    ell_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, maxnzr, ld, d_idx, d_val, d_x, d_y);
+    const bool pair = (ld % 2 == 0) && (((uintptr_t)d_idx & 7) == 0) && (((uintptr_t)d_val & 15) == 0) && (((uintptr_t)d_y & 15) == 0);
+    if (pair) ell_kernel<true><<<((n + 1) / 2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, maxnzr, ld, d_idx, d_val, d_x, d_y);
+    else ell_kernel<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, maxnzr, ld, d_idx, d_val, d_x, d_y);
     LISB_CHECK_LAUNCH();
     return 0;
 }
@@ -528,7 +581,9 @@ extern "C" int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *d_o
                                 const double *d_val, const double *d_x, double *d_y, void *stream)
 {
     if (n <= 0) return 0;
-    dia_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, xlen, nnd, ld, d_off, d_val, d_x, d_y);
+    const bool pair = (ld % 2 == 0) && (((uintptr_t)d_val & 15) == 0) && (((uintptr_t)d_y & 15) == 0);
+    if (pair) dia_kernel<true><<<((n + 1) / 2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, xlen, nnd, ld, d_off, d_val, d_x, d_y);
+    else dia_kernel<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, xlen, nnd, ld, d_off, d_val, d_x, d_y);
     LISB_CHECK_LAUNCH();
     return 0;
 }

@@ -112,7 +112,13 @@ def main():
                 assert L.shim_mv_matvec(h) == 0
             yl = np.zeros(nl)
             assert L.shim_mv_get_y_local(h, yl) == 0
-            H.assert_bits_equal(yl, y_full[is_:ie], f"rank {rank} spmv {fmt}")
+            if fmt == "dia":
+                # DIA sums by ascending LOCAL offset, and halo columns are numbered after the owned
+                # ones (as in the reference's MPI build), so the order differs from the one-process
+                # run for rows that touch the lower halo: same products, different rounding
+                assert np.allclose(yl, y_full[is_:ie], rtol=1e-13, atol=1e-13 * np.abs(y_full).max())
+            else:
+                H.assert_bits_equal(yl, y_full[is_:ie], f"rank {rank} spmv {fmt}")
             d = C.c_double()
             assert L.shim_mv_dot_xy(h, C.byref(d)) == 0
             assert abs(d.value - float(np.dot(x, y_full))) <= 1e-9 * abs(float(np.dot(np.abs(x), np.abs(y_full))))
