@@ -45,6 +45,8 @@ int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_
 int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile);
 int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
                          const double *d_val, const double *d_x, double *d_y, void *stream);
+/* tuning hook for experiments: TMA pipeline depth 2, 3 or 4 (0 = default) */
+int lisb200_spmv_csr_tma_tune(int stages);
 /* ... fused with <x,y>; d_partial needs lisb200_reduce_slots() doubles (persistent grid) */
 int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
                              const double *d_val, const double *d_x, double *d_y, double *d_partial,

@@ -138,7 +138,7 @@ struct CsrTmaSmem {
 };
 
 template <int kRows, int kStages, bool kDot>
-__global__ void __launch_bounds__(kRows + 32)
+__global__ void __launch_bounds__(kRows + 32, 1152 / (kRows + 32))
 csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const int *__restrict__ idx,
                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                double *partial, unsigned int *counter, double *result)
@@ -160,11 +160,18 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
         // ---------------- producer warp: one lane drives the TMA ----------------
         if (tid == kRows) {
             int it = 0;
-            for (int b = blockIdx.x; b < nblocks; b += gridDim.x, ++it) {
+            int b = blockIdx.x;
+            // slice bounds of the block after this one are fetched one iteration ahead, so the
+            // producer never sits on a DRAM round trip between "stage free" and "TMA issued"
+            int a0 = 0, a1 = 0;
+            if (b < nblocks) { a0 = __ldg(ptr + b * kRows); a1 = __ldg(ptr + min(b * kRows + kRows, n)); }
+            for (; b < nblocks; b += gridDim.x, ++it) {
                 const int s = it % kStages;
                 const int r0 = b * kRows;
                 const int rend = min(r0 + kRows, n);
-                const int a0 = __ldg(ptr + r0), a1 = __ldg(ptr + rend);      // issued before the wait
+                const int bn = b + gridDim.x;
+                int na0 = 0, na1 = 0;
+                if (bn < nblocks) { na0 = __ldg(ptr + bn * kRows); na1 = __ldg(ptr + min(bn * kRows + kRows, n)); }
                 if (it >= kStages) mbar_wait(&empty_bar[s], ((it / kStages) - 1) & 1);
                 unsigned char *st = smem_raw + (size_t)s * stage_bytes;
                 double *sval = reinterpret_cast<double *>(st);
@@ -179,6 +186,7 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
                     tma_load_1d(sidx, idx + w, cnt * 4u, &full_bar[s]);
                     tma_load_1d(sval, val + w, cnt * 8u, &full_bar[s]);
                 }
+                a0 = na0; a1 = na1;
             }
         }
     } else {
@@ -197,15 +205,24 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
                 int j = sptr[tid] - w;
                 const int e = sptr[tid + 1] - w;
                 double acc = 0.0;
-                for (; j + 4 <= e; j += 4) {          // 4 gathers in flight, sums stay ordered
-                    const int c0 = sidx[j], c1 = sidx[j + 1], c2 = sidx[j + 2], c3 = sidx[j + 3];
-                    const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-                    acc = add(acc, mul(sval[j], x0));
-                    acc = add(acc, mul(sval[j + 1], x1));
-                    acc = add(acc, mul(sval[j + 2], x2));
-                    acc = add(acc, mul(sval[j + 3], x3));
+                // up to kGather gathers of x in flight per thread; tail entries are clamped to
+                // the row's last entry and masked out of the sum, which stays in storage order
+                constexpr int kGather = 8;
+                for (; j < e; j += kGather) {
+                    int c[kGather];
+                    double v[kGather], xv[kGather];
+#pragma unroll
+                    for (int k = 0; k < kGather; ++k) {
+                        const int jj = min(j + k, e - 1);
+                        c[k] = sidx[jj];
+                        v[k] = sval[jj];
+                    }
+#pragma unroll
+                    for (int k = 0; k < kGather; ++k) xv[k] = __ldg(x + c[k]);
+#pragma unroll
+                    for (int k = 0; k < kGather; ++k)
+                        if (j + k < e) acc = add(acc, mul(v[k], xv[k]));
                 }
-                for (; j < e; ++j) acc = add(acc, mul(sval[j], __ldg(x + sidx[j])));
                 y[r] = acc;
                 if (kDot) dsum = add(dsum, mul(__ldg(x + r), acc));
             }
@@ -448,11 +465,12 @@ static int sm_count_spmv() {
     return g_sm_count;
 }
 
-template <int kRows, bool kDot>
-static int launch_csr_tma(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
-                          double *partial, unsigned int *counter, double *result, cudaStream_t st)
+static int g_tma_stages = 0;       // 0 = default; set by lisb200_spmv_csr_tma_tune (experiments)
+
+template <int kRows, int kStages, bool kDot>
+static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
+                            double *partial, unsigned int *counter, double *result, cudaStream_t st)
 {
-    constexpr int kStages = 2;
     const size_t smem = kStages * CsrTmaSmem<kRows>::stage_bytes(tile);
     auto kern = csr_tma_kernel<kRows, kStages, kDot>;
     static size_t configured = 0;
@@ -472,7 +490,24 @@ static int launch_csr_tma(int n, int tile, const int *ptr, const int *idx, const
     LISB_CHECK_LAUNCH();
     return 0;
 }
+
+template <int kRows, bool kDot>
+static int launch_csr_tma(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
+                          double *partial, unsigned int *counter, double *result, cudaStream_t st)
+{
+    switch (g_tma_stages) {
+    case 3: return launch_csr_tma_s<kRows, 3, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    case 4: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    case 6: return launch_csr_tma_s<kRows, 6, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    case 8: return launch_csr_tma_s<kRows, 8, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    case 2: return launch_csr_tma_s<kRows, 2, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    default: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    }
+}
 }  // namespace lisb
+
+// experiments only: pipeline depth of the TMA kernel (2, 3 or 4; 0 restores the default)
+extern "C" int lisb200_spmv_csr_tma_tune(int stages) { lisb::g_tma_stages = stages; return 0; }
 
 // rows_per_block in {256,128,64}; tile = entries staged per row block (multiple of 4)
 extern "C" int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,

@@ -1,0 +1,42 @@
+"""Experiment: rows-per-block x pipeline depth of the TMA CSR kernel on the 512^3 7-pt matrix.
+Run on the GPU box: python profiles/sweep_csr_tma.py [grid]"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import lis_b200  # noqa: E402
+
+grid = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+dev = torch.device("cuda", 0)
+K = lis_b200.load_kernels()
+K.lisb200_spmv_csr_tma_tune.argtypes = [C.c_int]
+ptr, idx, val = bench.poisson7_device(torch, grid, grid, grid, 0, grid, dev)
+n, nnz = ptr.numel() - 1, idx.numel()
+x = torch.rand(n, device=dev, dtype=torch.float64); y = torch.zeros_like(x)
+idx = torch.cat([idx, torch.zeros(8, device=dev, dtype=torch.int32)])
+val = torch.cat([val, torch.zeros(8, device=dev, dtype=torch.float64)])
+ptr = torch.cat([ptr, torch.zeros(4, device=dev, dtype=torch.int32)])
+stream = torch.cuda.Stream(device=dev); sp = C.c_void_p(stream.cuda_stream)
+bytes_csr = 12.0 * nnz + 20.0 * n
+ref = None
+for rows, tile in ((256, 2048), (128, 1024), (64, 512)):
+    for stages in (2, 3, 4, 6, 8):
+        K.lisb200_spmv_csr_tma_tune(stages)
+
+        def f():
+            rc = K.lisb200_spmv_csr_tma(n, rows, tile, ptr.data_ptr(), idx.data_ptr(), val.data_ptr(), x.data_ptr(), y.data_ptr(), sp)
+            assert rc == 0, rc
+        try:
+            s = bench.time_launches(torch, stream, f, 20, 3) / 20
+        except Exception as e:
+            print(rows, tile, stages, "failed", e); continue
+        ok = True
+        if ref is None:
+            ref = y.clone()
+        else:
+            ok = torch.equal(ref.view(torch.int64), y.view(torch.int64))
+        print(f"rows={rows:4d} tile={tile:5d} stages={stages}: {2 * nnz / s / 1e9:8.1f} GFLOP/s {bytes_csr / s / 1e9:8.1f} GB/s same_bits={ok}", flush=True)
