@@ -330,11 +330,11 @@ def run_b200(args, grid):
 
         # the library picks the TMA-staged row-block kernel for short-row matrices such as this
         # one (lisb200_spmv_csr_tma_plan on the host row pointers); time the product-tile kernel too
-        rows_pb, tile = 256, 2048
+        rows_pb, tile, stages = 256, 2048, 4
         ptr_p = torch.cat([ptr, torch.zeros(4, device=dev, dtype=torch.int32)])
 
         def csr_tma():
-            rc = K.lisb200_spmv_csr_tma(n, rows_pb, tile, ptr_p.data_ptr(), idx_p.data_ptr(), val_p.data_ptr(), x.data_ptr(), y.data_ptr(), sp)
+            rc = K.lisb200_spmv_csr_tma(n, rows_pb, tile, stages, ptr_p.data_ptr(), idx_p.data_ptr(), val_p.data_ptr(), x.data_ptr(), y.data_ptr(), sp)
             assert rc == 0, K.lisb200_error_string(rc)
 
         res["csr_tile_s"] = time_launches(torch, stream, csr, args.steps, args.warmup) / args.steps

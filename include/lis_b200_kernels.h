@@ -39,16 +39,14 @@ int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_
 /* CSR, unsplit order, short-row matrices: TMA-staged row blocks (cp.async.bulk of the
  * ptr/idx/val slices into shared memory by a producer warp, thread-per-row ordered walk).
  * Same result bits as lisb200_spmv_csr.  lisb200_spmv_csr_tma_plan inspects the HOST row
- * pointers once and returns 0 with (rows_per_block, tile) when the matrix qualifies, 1 if
+ * pointers once and returns 0 with (rows_per_block, tile, stages) when the matrix qualifies, 1 if
  * not (long or very ragged rows: use lisb200_spmv_csr).  d_ptr must be readable 16 bytes
  * past its n+1 entries.                                  src/matvec/lis_matvec_csr.c:90-110 */
-int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile);
-int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile, int *stages);
+int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                          const double *d_val, const double *d_x, double *d_y, void *stream);
-/* tuning hook for experiments: TMA pipeline depth 2, 3 or 4 (0 = default) */
-int lisb200_spmv_csr_tma_tune(int stages);
 /* ... fused with <x,y>; d_partial needs lisb200_reduce_slots() doubles (persistent grid) */
-int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                              const double *d_val, const double *d_x, double *d_y, double *d_partial,
                              unsigned int *d_counter, double *d_result, void *stream);
 /* CSR, split order  t = D[i]*x[i]; t += L...; t += U...  src/matvec/lis_matvec_csr.c:64-87 */

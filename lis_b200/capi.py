@@ -51,8 +51,8 @@ def load_kernels() -> C.CDLL:
     lib.lisb200_reduce_slots.restype = ci
     sigs = {
         "lisb200_spmv_csr": [ci, vp, vp, vp, vp, vp, vp],
-        "lisb200_spmv_csr_tma": [ci, ci, ci, vp, vp, vp, vp, vp, vp],
-        "lisb200_spmv_csr_tma_dot": [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "lisb200_spmv_csr_tma": [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp],
+        "lisb200_spmv_csr_tma_dot": [ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "lisb200_spmv_csr_split": [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "lisb200_spmv_csr_dot": [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "lisb200_spmv_ell": [ci, ci, ci, vp, vp, vp, vp, vp],

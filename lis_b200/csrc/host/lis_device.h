@@ -53,7 +53,7 @@ typedef struct lisd_csr {
     int n, nnz;
     int *ptr, *idx;
     double *val;
-    int tma_rows, tma_tile;   /* plan of the TMA row-block kernel; tma_rows == 0: product-tile kernel */
+    int tma_rows, tma_tile, tma_stages;   /* plan of the TMA row-block kernel; tma_rows == 0: product-tile kernel */
 } lisd_csr;
 
 typedef struct lisd_matrix {

@@ -52,9 +52,9 @@ static LIS_INT csr_upload(lisd_csr *c, int n, const LIS_INT *ptr, const LIS_INT 
      * (tma only where the plan exists). */
     {
         const char *force = getenv("LIS_B200_CSR_KERNEL");
-        int rows = 0, tile = 0;
-        if (!(force && strcmp(force, "tile") == 0) && lisb200_spmv_csr_tma_plan(n, ptr, &rows, &tile) == 0) {
-            c->tma_rows = rows; c->tma_tile = tile;
+        int rows = 0, tile = 0, stages = 0;
+        if (!(force && strcmp(force, "tile") == 0) && lisb200_spmv_csr_tma_plan(n, ptr, &rows, &tile, &stages) == 0) {
+            c->tma_rows = rows; c->tma_tile = tile; c->tma_stages = stages;
         }
     }
     return LIS_SUCCESS;
@@ -180,7 +180,7 @@ static LIS_INT matvec_launch(LIS_MATRIX A, lisd_matrix *M, const double *x, doub
     else switch (M->type) {
     case LIS_MATRIX_CSR:
     case LIS_MATRIX_CSC:
-        if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(n, M->csr.tma_rows, M->csr.tma_tile, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
+        if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(n, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
         else rc = lisb200_spmv_csr(n, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
         break;
     case LIS_MATRIX_ELL: rc = lisb200_spmv_ell(n, M->maxnzr, M->ld, M->idx, M->val, x, y, st); break;
@@ -262,7 +262,7 @@ LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *do
     if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
     lisd_mark_busy();
     if (M->csr.tma_rows)
-        err = lisd_check(lisb200_spmv_csr_tma_dot(A->n, M->csr.tma_rows, M->csr.tma_tile, M->csr.ptr, M->csr.idx, M->csr.val,
+        err = lisd_check(lisb200_spmv_csr_tma_dot(A->n, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr, M->csr.idx, M->csr.val,
                                                   x->value, y->value, partial, lisd_counter(), lisd_scalar_dev(0),
                                                   lisd_stream()), "lis_matvec+dot");
     else

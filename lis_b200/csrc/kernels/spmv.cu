@@ -465,8 +465,6 @@ static int sm_count_spmv() {
     return g_sm_count;
 }
 
-static int g_tma_stages = 0;       // 0 = default; set by lisb200_spmv_csr_tma_tune (experiments)
-
 template <int kRows, int kStages, bool kDot>
 static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
                             double *partial, unsigned int *counter, double *result, cudaStream_t st)
@@ -479,9 +477,9 @@ static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, con
         if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
-    int per_sm = (int)((size_t)(227 * 1024 - 2048) / (smem + 1024));
+    int per_sm = (int)((size_t)(222 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    const int max_by_threads = 2048 / (kRows + 32);
+    const int max_by_threads = 1152 / (kRows + 32);      // register budget of __launch_bounds__
     if (per_sm > max_by_threads) per_sm = max_by_threads;
     const int nblocks = (n + kRows - 1) / kRows;
     int grid = sm_count_spmv() * per_sm;
@@ -492,58 +490,66 @@ static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, con
 }
 
 template <int kRows, bool kDot>
-static int launch_csr_tma(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
+static int launch_csr_tma(int n, int tile, int stages, const int *ptr, const int *idx, const double *val, const double *x, double *y,
                           double *partial, unsigned int *counter, double *result, cudaStream_t st)
 {
-    switch (g_tma_stages) {
+    switch (stages) {
     case 3: return launch_csr_tma_s<kRows, 3, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
     case 4: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
     case 6: return launch_csr_tma_s<kRows, 6, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
     case 8: return launch_csr_tma_s<kRows, 8, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
     case 2: return launch_csr_tma_s<kRows, 2, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
-    default: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    default: return (int)cudaErrorInvalidValue;
     }
 }
 }  // namespace lisb
 
-// experiments only: pipeline depth of the TMA kernel (2, 3 or 4; 0 restores the default)
-extern "C" int lisb200_spmv_csr_tma_tune(int stages) { lisb::g_tma_stages = stages; return 0; }
 
-// rows_per_block in {256,128,64}; tile = entries staged per row block (multiple of 4)
-extern "C" int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+
+// rows_per_block in {256,128,64}; tile = entries staged per row block (multiple of 4);
+// stages in {2,3,4,6,8} with stages * (12*tile + 4*(rows+4)) <= ~224 KB
+extern "C" int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                                     const double *d_val, const double *d_x, double *d_y, void *stream)
 {
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (rows_per_block) {
-    case 256: return launch_csr_tma<256, false>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
-    case 128: return launch_csr_tma<128, false>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
-    case 64:  return launch_csr_tma<64, false>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    case 256: return launch_csr_tma<256, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    case 128: return launch_csr_tma<128, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    case 64:  return launch_csr_tma<64, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
     default:  return (int)cudaErrorInvalidValue;
     }
 }
 
-extern "C" int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, const int *d_ptr, const int *d_idx,
+extern "C" int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                                         const double *d_val, const double *d_x, double *d_y, double *d_partial,
                                         unsigned int *d_counter, double *d_result, void *stream)
 {
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (rows_per_block) {
-    case 256: return launch_csr_tma<256, true>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
-    case 128: return launch_csr_tma<128, true>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
-    case 64:  return launch_csr_tma<64, true>(n, tile, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    case 256: return launch_csr_tma<256, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    case 128: return launch_csr_tma<128, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    case 64:  return launch_csr_tma<64, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
     default:  return (int)cudaErrorInvalidValue;
     }
 }
 
-// smallest plan (rows per block, tile) whose staged slice holds every row block of the matrix;
-// h_ptr is the HOST row-pointer array.  Returns 0 and fills the plan, or 1 when the rows are
-// too long/ragged for this variant (use lisb200_spmv_csr).
-extern "C" int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile)
+// Plan for the TMA kernel from the HOST row pointers: rows per block R, tile (entries staged per
+// block) and pipeline depth.  What the sweeps say (profiles/r01_sweep_csr_tma.txt):
+//   * ~512 consumer threads per SM keep enough x gathers in flight (7-pt: 512 consumers/4 stages
+//     899 GFLOP/s vs 1024 consumers/2 stages 831; 27-pt: 320 consumers 1013 vs 128 consumers 542);
+//   * beyond that, shared memory is better spent on pipeline depth (>= 3 stages hide the drain
+//     bubble of a stage that all warps of the CTA must release before it is refilled).
+// So: depth = what fits next to 512 consumers' worth of staged rows (2..4), then the R that
+// yields the most resident consumers (ties: larger R).  Returns 0 and fills the plan, or 1 when
+// the rows are too long/ragged for a thread-per-row walk (use lisb200_spmv_csr).
+extern "C" int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_block, int *tile, int *stages)
 {
     if (n <= 0) return 1;
     const int cand[3] = {256, 128, 64};
+    const long long smem_sm = 222 * 1024;
+    long long best_consumers = 0;
     for (int c = 0; c < 3; ++c) {
         const int R = cand[c];
         long long worst = 0;
@@ -553,15 +559,24 @@ extern "C" int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *rows_per_
             const long long cnt = ((long long)h_ptr[rend] - w + 3) & ~3LL;
             if (cnt > worst) worst = cnt;
         }
-        // at most ~32 entries per row on average inside the worst block, tile <= 8192 entries
-        if (worst <= 8192 && worst <= 32LL * R) {
-            long long t = (worst + 255) & ~255LL;
-            if (t < 256) t = 256;
-            *rows_per_block = R; *tile = (int)t;
-            return 0;
+        if (worst > 64LL * R) continue;                             // very ragged: one thread per row would crawl
+        long long t = (worst + 255) & ~255LL;
+        if (t < 256) t = 256;
+        const long long stage = 12 * t + 4 * (R + 4);
+        long long st = smem_sm / (512 * stage / R);                 // depth affordable with 512 consumers resident
+        if (st > 4) st = 4;
+        if (st < 2) st = 2;
+        long long ctas = smem_sm / (st * stage + 1024);
+        const long long by_threads = 1152 / (R + 32);          // launch bound of the kernel
+        if (ctas > by_threads) ctas = by_threads;
+        if (ctas < 1) continue;
+        const long long consumers = ctas * R;
+        if (consumers > best_consumers) {
+            best_consumers = consumers;
+            *rows_per_block = R; *tile = (int)t; *stages = (int)st;
         }
     }
-    return 1;
+    return best_consumers > 0 ? 0 : 1;
 }
 
 extern "C" int lisb200_spmv_csr(int n, const int *d_ptr, const int *d_idx, const double *d_val,
