@@ -139,6 +139,17 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
                                 const double *d_wd, const int *d_rowblk_start,
                                 const int *d_rowblk_end, double *d_x, void *stream);
 
+/* The same sweeps in ONE launch each ("sync-free"): d_order lists the rows level by level, every
+ * level padded to a multiple of 32 slots with -1; d_pptr/d_pidx/d_pval are L (forward) or U
+ * (backward) permuted into that slot order (nslots+1 pointers); d_flag is an n-entry int array
+ * (zero at first use) and `gen` a value never used before on it (the host counts sweeps);
+ * d_ticket one unsigned int of scratch.  Same result bits as the level-launched kernels.      */
+int lisb200_ssor_sweep_syncfree(int forward, int nslots, const int *d_order,
+                                const int *d_pptr, const int *d_pidx, const double *d_pval,
+                                const double *d_wd, const int *d_rowblk_start, const int *d_rowblk_end,
+                                const double *d_b, double *d_x, int *d_flag, int gen,
+                                unsigned int *d_ticket, void *stream);
+
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
 /* d_ws[i] = d_x[d_export_index[i]] */
 int lisb200_gather(int count, const int *d_index, const double *d_x, double *d_out, void *stream);

@@ -190,13 +190,73 @@ LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
 }
 
 /* ------------------------------------------------------------------ SSOR level schedule */
+typedef struct lisd_perm {        /* one direction of the one-launch sweep */
+    int nslots;                   /* levels concatenated, each padded to a multiple of 32 */
+    int *d_order;                 /* slot -> row (or -1) */
+    int *d_pptr, *d_pidx;         /* L or U permuted into slot order */
+    double *d_pval;
+} lisd_perm;
+
 typedef struct lisd_sweep {
     int n, nblocks;
     int nlev_f, nlev_b;
     int *h_fptr, *h_bptr;          /* host: level -> [start,end) in rows arrays */
     int *d_frows, *d_brows;        /* device: rows ordered by level */
     int *d_blk_start, *d_blk_end;  /* device: per row, the owning block's range */
+    lisd_perm pf, pb;              /* one-launch variant */
+    int *d_flag; unsigned int *d_ticket;
+    int gen;
 } lisd_sweep;
+
+static void perm_free(lisd_perm *p)
+{
+    lisd_free(p->d_order); lisd_free(p->d_pptr); lisd_free(p->d_pidx); lisd_free(p->d_pval);
+    memset(p, 0, sizeof(*p));
+}
+
+/* rows[] is level-ordered, lptr[l] its level pointers; builds the padded order and the permuted
+ * copy of the triangular part (ptr/idx/val, host) on the device */
+static LIS_INT perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
+                          const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
+{
+    size_t nslots = 0;
+    for (int l = 0; l < nlev; l++) nslots += (size_t)((lptr[l + 1] - lptr[l] + 31) & ~31);
+    if (nslots > 0x7fffff00u) { LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "SSOR schedule too large\n"); return LIS_ERR_OUT_OF_MEMORY; }
+    int *order = (int *)malloc(sizeof(int) * (nslots ? nslots : 1));
+    int *pptr = (int *)malloc(sizeof(int) * (nslots + 1));
+    const size_t nnz = (size_t)ptr[n];
+    int *pidx = (int *)malloc(sizeof(int) * (nnz ? nnz : 1));
+    double *pval = (double *)malloc(sizeof(double) * (nnz ? nnz : 1));
+    LIS_INT err = LIS_OUT_OF_MEMORY;
+    if (!order || !pptr || !pidx || !pval) { LIS_SETERR_MEM(nnz * 12); goto done; }
+    {
+        size_t k = 0, q = 0;
+        pptr[0] = 0;
+        for (int l = 0; l < nlev; l++) {
+            const int cnt = lptr[l + 1] - lptr[l], padded = (cnt + 31) & ~31;
+            for (int r = 0; r < padded; r++, k++) {
+                if (r < cnt) {
+                    const int i = rows[lptr[l] + r];
+                    order[k] = i;
+                    for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++, q++) { pidx[q] = idx[j]; pval[q] = val[j]; }
+                } else order[k] = -1;
+                pptr[k + 1] = (int)q;
+            }
+        }
+    }
+    P->nslots = (int)nslots;
+    err = lisd_malloc((void **)&P->d_order, sizeof(int) * (nslots ? nslots : 1));
+    if (!err) err = lisd_upload(P->d_order, order, sizeof(int) * nslots);
+    if (!err) err = lisd_malloc((void **)&P->d_pptr, sizeof(int) * (nslots + 1));
+    if (!err) err = lisd_upload(P->d_pptr, pptr, sizeof(int) * (nslots + 1));
+    if (!err) err = lisd_malloc((void **)&P->d_pidx, sizeof(int) * (nnz ? nnz : 1));
+    if (!err) err = lisd_upload(P->d_pidx, pidx, sizeof(int) * nnz);
+    if (!err) err = lisd_malloc((void **)&P->d_pval, sizeof(double) * (nnz ? nnz : 1));
+    if (!err) err = lisd_upload(P->d_pval, pval, sizeof(double) * nnz);
+done:
+    free(order); free(pptr); free(pidx); free(pval);
+    return err;
+}
 
 void lisd_sweep_free(void *p)
 {
@@ -204,6 +264,8 @@ void lisd_sweep_free(void *p)
     if (S == NULL) return;
     free(S->h_fptr); free(S->h_bptr);
     lisd_free(S->d_frows); lisd_free(S->d_brows); lisd_free(S->d_blk_start); lisd_free(S->d_blk_end);
+    perm_free(&S->pf); perm_free(&S->pb);
+    lisd_free(S->d_flag); lisd_free(S->d_ticket);
     free(S);
 }
 
@@ -265,6 +327,7 @@ static LIS_INT sweep_build(LIS_MATRIX A, lisd_sweep **out)
     if (!S->h_fptr) goto fail;
     err = lisd_malloc((void **)&S->d_frows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_frows, rows, sizeof(int) * (size_t)n);
+    if (!err) err = perm_build(&S->pf, n, nlev, S->h_fptr, rows, A->L->ptr, A->L->index, A->L->value);
     if (err) goto fail;
     /* backward: row i waits for every U neighbour inside its block */
     nlev = 0;
@@ -284,6 +347,10 @@ static LIS_INT sweep_build(LIS_MATRIX A, lisd_sweep **out)
     if (!S->h_bptr) goto fail;
     err = lisd_malloc((void **)&S->d_brows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_brows, rows, sizeof(int) * (size_t)n);
+    if (!err) err = perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value);
+    if (!err) err = lisd_malloc((void **)&S->d_flag, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_memset(S->d_flag, 0, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_malloc((void **)&S->d_ticket, 64);
     if (!err) err = lisd_malloc((void **)&S->d_blk_start, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_blk_start, bs, sizeof(int) * (size_t)n);
     if (!err) err = lisd_malloc((void **)&S->d_blk_end, sizeof(int) * (size_t)(n > 0 ? n : 1));
@@ -330,6 +397,19 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
     if (err) return err;
     void *st = lisd_stream();
     lisd_mark_busy();
+    {
+        /* default: one launch per direction; LIS_B200_SSOR=levels keeps the launch-per-level path */
+        const char *e = getenv("LIS_B200_SSOR");
+        if (!(e && strcmp(e, "levels") == 0)) {
+            err = lisd_check(lisb200_ssor_sweep_syncfree(1, S->pf.nslots, S->pf.d_order, S->pf.d_pptr, S->pf.d_pidx, S->pf.d_pval,
+                                                         M->wd, S->d_blk_start, S->d_blk_end, b->value, x->value, S->d_flag,
+                                                         ++S->gen, S->d_ticket, st), "SSOR forward sweep");
+            if (err) return err;
+            return lisd_check(lisb200_ssor_sweep_syncfree(0, S->pb.nslots, S->pb.d_order, S->pb.d_pptr, S->pb.d_pidx, S->pb.d_pval,
+                                                          M->wd, S->d_blk_start, S->d_blk_end, b->value, x->value, S->d_flag,
+                                                          ++S->gen, S->d_ticket, st), "SSOR backward sweep");
+        }
+    }
     for (int l = 0; l < S->nlev_f; l++) {
         const int s = S->h_fptr[l], cnt = S->h_fptr[l + 1] - s;
         err = lisd_check(lisb200_ssor_forward_level(cnt, S->d_frows + s, M->L.ptr, M->L.idx, M->L.val, M->wd,

@@ -169,6 +169,33 @@ def test_psolve_ssor_bit_exact(b200, oracle, nthreads):
         b200.set_threads(1)
 
 
+def test_psolve_ssor_level_launch_path(b200, oracle, monkeypatch):
+    """LIS_B200_SSOR=levels: one launch per level instead of the one-launch sweep; same bits"""
+    monkeypatch.setenv("LIS_B200_SSOR", "levels")
+    for name, (ptr, idx, val), _ in matrices():
+        if "empty" in name:
+            continue
+        b = H.rand_vec(len(ptr) - 1, 63, "wide")
+        for t in (1, 3):
+            b200.set_threads(t)
+            try:
+                H.assert_bits_equal(b200.psolve(ptr, idx, val, b, "-p ssor"), oracle.psolve(ptr, idx, val, b, "ssor", nthreads=t),
+                                    f"ssor-levels/{name}/T={t}")
+            finally:
+                b200.set_threads(1)
+
+
+def test_psolve_ssor_repeated_sweeps(b200, oracle):
+    """the one-launch sweep reuses its flag array across calls (generation counter)"""
+    ptr, idx, val = H.poisson3d_7pt(14, 13, 12)
+    n = len(ptr) - 1
+    b = oracle.spmv("csr", ptr, idx, val, np.ones(n))
+    g = b200.solve(ptr, idx, val, b, "-i cg -p ssor")             # dozens of sweeps on one schedule
+    c = oracle.solve("cg", ptr, idx, val, b, precon="ssor")
+    assert g["iter"] == c["iter"]
+    history_close(g["rhistory"], c["rhistory"], "cg+ssor repeated sweeps")
+
+
 def test_psolve_jacobi_bit_exact(b200, oracle):
     for name, (ptr, idx, val), _ in matrices():
         if "empty" in name:
