@@ -141,14 +141,15 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
 
 /* The same sweeps in ONE launch each ("sync-free"): d_order lists the rows level by level, every
  * level padded to a multiple of 32 slots with -1; d_pptr/d_pidx/d_pval are L (forward) or U
- * (backward) permuted into that slot order (nslots+1 pointers); d_flag is an n-entry int array
- * (zero at first use) and `gen` a value never used before on it (the host counts sweeps);
- * d_ticket one unsigned int of scratch.  Same result bits as the level-launched kernels.      */
-int lisb200_ssor_sweep_syncfree(int forward, int nslots, const int *d_order,
+ * (backward) permuted into that slot order (nslots+1 pointers); d_ticket one unsigned int of
+ * scratch.  forward:  d_out = w,  d_in = b:  w[i] = (b[i] - sum L*w[jj]) * wd[i]
+ *           backward: d_out = x,  d_in = w:  x[i] = w[i] - (sum U*x[jj]) * wd[i]
+ * d_out (n entries, must not alias d_in) is overwritten with a not-ready pattern first and
+ * doubles as the dependency signal.  Same result bits as the level-launched kernels.          */
+int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *d_order,
                                 const int *d_pptr, const int *d_pidx, const double *d_pval,
                                 const double *d_wd, const int *d_rowblk_start, const int *d_rowblk_end,
-                                const double *d_b, double *d_x, int *d_flag, int gen,
-                                unsigned int *d_ticket, void *stream);
+                                const double *d_in, double *d_out, unsigned int *d_ticket, void *stream);
 
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
 /* d_ws[i] = d_x[d_export_index[i]] */

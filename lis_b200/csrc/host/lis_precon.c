@@ -204,8 +204,8 @@ typedef struct lisd_sweep {
     int *d_frows, *d_brows;        /* device: rows ordered by level */
     int *d_blk_start, *d_blk_end;  /* device: per row, the owning block's range */
     lisd_perm pf, pb;              /* one-launch variant */
-    int *d_flag; unsigned int *d_ticket;
-    int gen;
+    double *d_w;                   /* forward-sweep result (input of the backward sweep) */
+    unsigned int *d_ticket;
 } lisd_sweep;
 
 static void perm_free(lisd_perm *p)
@@ -265,7 +265,7 @@ void lisd_sweep_free(void *p)
     free(S->h_fptr); free(S->h_bptr);
     lisd_free(S->d_frows); lisd_free(S->d_brows); lisd_free(S->d_blk_start); lisd_free(S->d_blk_end);
     perm_free(&S->pf); perm_free(&S->pb);
-    lisd_free(S->d_flag); lisd_free(S->d_ticket);
+    lisd_free(S->d_w); lisd_free(S->d_ticket);
     free(S);
 }
 
@@ -348,8 +348,7 @@ static LIS_INT sweep_build(LIS_MATRIX A, lisd_sweep **out)
     err = lisd_malloc((void **)&S->d_brows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_brows, rows, sizeof(int) * (size_t)n);
     if (!err) err = perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value);
-    if (!err) err = lisd_malloc((void **)&S->d_flag, sizeof(int) * (size_t)(n > 0 ? n : 1));
-    if (!err) err = lisd_memset(S->d_flag, 0, sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (!err) err = lisd_malloc((void **)&S->d_w, sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_malloc((void **)&S->d_ticket, 64);
     if (!err) err = lisd_malloc((void **)&S->d_blk_start, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_blk_start, bs, sizeof(int) * (size_t)n);
@@ -401,13 +400,13 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
         /* default: one launch per direction; LIS_B200_SSOR=levels keeps the launch-per-level path */
         const char *e = getenv("LIS_B200_SSOR");
         if (!(e && strcmp(e, "levels") == 0)) {
-            err = lisd_check(lisb200_ssor_sweep_syncfree(1, S->pf.nslots, S->pf.d_order, S->pf.d_pptr, S->pf.d_pidx, S->pf.d_pval,
-                                                         M->wd, S->d_blk_start, S->d_blk_end, b->value, x->value, S->d_flag,
-                                                         ++S->gen, S->d_ticket, st), "SSOR forward sweep");
+            err = lisd_check(lisb200_ssor_sweep_syncfree(1, S->n, S->pf.nslots, S->pf.d_order, S->pf.d_pptr, S->pf.d_pidx, S->pf.d_pval,
+                                                         M->wd, S->d_blk_start, S->d_blk_end, b->value, S->d_w,
+                                                         S->d_ticket, st), "SSOR forward sweep");
             if (err) return err;
-            return lisd_check(lisb200_ssor_sweep_syncfree(0, S->pb.nslots, S->pb.d_order, S->pb.d_pptr, S->pb.d_pidx, S->pb.d_pval,
-                                                          M->wd, S->d_blk_start, S->d_blk_end, b->value, x->value, S->d_flag,
-                                                          ++S->gen, S->d_ticket, st), "SSOR backward sweep");
+            return lisd_check(lisb200_ssor_sweep_syncfree(0, S->n, S->pb.nslots, S->pb.d_order, S->pb.d_pptr, S->pb.d_pidx, S->pb.d_pval,
+                                                          M->wd, S->d_blk_start, S->d_blk_end, S->d_w, x->value,
+                                                          S->d_ticket, st), "SSOR backward sweep");
         }
     }
     for (int l = 0; l < S->nlev_f; l++) {

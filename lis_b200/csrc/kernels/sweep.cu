@@ -58,26 +58,35 @@ ssor_bwd_kernel(int nrows, const int *__restrict__ rows,
 
 // ---- one-launch ("sync-free") sweeps ---------------------------------------------------------
 // Level-by-level launches pay a launch + drain per level (1534 levels for a 512^3 7-point grid,
-// thousands for a random band).  Here the whole sweep is ONE kernel: slot k of `order` holds a
+// thousands for a random band).  Here a whole sweep is ONE kernel: slot k of `order` holds a
 // row (levels concatenated, each padded to a multiple of 32 with -1 so that no warp straddles
 // two levels => lanes of a warp never wait on each other), L/U are stored permuted in that order
-// (coalesced), and a row simply waits for the "done" flag of each neighbour it reads before
-// using it.  CTAs take a ticket at start and process slots in ticket order, so a waiting row's
-// dependencies are always in CTAs that are already running or finished: no deadlock.  Each row
-// still subtracts its products in storage order => same bits as the level-launched sweep and as
-// the reference loop (src/matrix/lis_matrix_csr.c:1578-1628).
-__device__ __forceinline__ int ld_acquire(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// (coalesced), and the output vector itself carries the "done" signal: it is pre-filled with a
+// signalling-NaN pattern that no IEEE operation can produce, and a row polls each neighbour it
+// reads until the pattern is gone (one L2 round trip per dependency hop, 8 neighbours polled
+// at a time).  CTAs take a ticket at start and process slots in ticket order, so a waiting
+// row's dependencies are always in CTAs that are already running or finished: no deadlock.
+// Each row still subtracts its products in storage order => same bits as the level-launched
+// sweep and as the reference loop (src/matrix/lis_matrix_csr.c:1578-1628).
+//   forward : w[i] = (b[i] - sum_{L, in block} L*w[jj]) * wd[i]          (w pre-filled)
+//   backward: x[i] = w[i] - (sum_{U, in block} U*x[jj]) * wd[i]          (x pre-filled)
+constexpr unsigned long long kNotReady = 0x7ff4c0dedeadbeefull;     // sNaN payload: never a result
+
+__device__ __forceinline__ unsigned long long ld_poll(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_publish(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
-__device__ __forceinline__ double ld_cg(const double *p) {      // L2-coherent read of x written by other SMs
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
+
+__global__ void __launch_bounds__(256)
+fill_not_ready_kernel(int n, double *x)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        reinterpret_cast<unsigned long long *>(x)[i] = kNotReady;
 }
 
 template <bool kForward>
@@ -85,7 +94,7 @@ __global__ void __launch_bounds__(128)
 ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
                      const int *__restrict__ pptr, const int *__restrict__ pidx, const double *__restrict__ pval,
                      const double *__restrict__ wd, const int *__restrict__ blk_start, const int *__restrict__ blk_end,
-                     const double *__restrict__ b, double *x, int *flag, int gen, unsigned int *ticket)
+                     const double *__restrict__ in /* b (forward) or w (backward) */, double *out, unsigned int *ticket)
 {
     __shared__ unsigned int vblock;
     if (threadIdx.x == 0) vblock = atomicAdd(ticket, 1u);
@@ -95,66 +104,61 @@ ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
     const int i = order[k];
     if (i < 0) return;
     const int lo = blk_start[i], hi = blk_end[i];
-    double t = kForward ? b[i] : 0.0;
+    double t = kForward ? in[i] : 0.0;
     const int e = pptr[k + 1];
-    for (int j = pptr[k]; j < e; ++j) {
-        const int jj = pidx[j];
-        if (kForward ? (jj < lo) : (jj < lo || jj >= hi)) continue;        // coupling leaves the block: dropped
-        while (ld_acquire(flag + jj) != gen) { }
-        const double xj = ld_cg(x + jj);
-        t = kForward ? sub(t, mul(pval[j], xj)) : add(t, mul(pval[j], xj));
+    constexpr int kBatch = 8;
+    for (int j0 = pptr[k]; j0 < e; j0 += kBatch) {
+        int jj[kBatch];
+        double v[kBatch], xv[kBatch];
+        unsigned int pending = 0, used = 0;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) {
+            const int j = min(j0 + q, e - 1);
+            jj[q] = pidx[j];
+            v[q] = pval[j];
+            const bool inblk = kForward ? (jj[q] >= lo) : (jj[q] >= lo && jj[q] < hi);   // else: coupling dropped
+            if (j0 + q < e && inblk) used |= 1u << q;
+            xv[q] = 0.0;
+        }
+        pending = used;
+        while (pending) {
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q)
+                if (pending & (1u << q)) {
+                    const unsigned long long bits = ld_poll(out + jj[q]);
+                    if (bits != kNotReady) { xv[q] = __longlong_as_double((long long)bits); pending &= ~(1u << q); }
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+            if (used & (1u << q)) t = kForward ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
     }
-    if (kForward) x[i] = mul(t, wd[i]);
-    else x[i] = sub(ld_cg(x + i), mul(t, wd[i]));
-    __threadfence();
-    st_release(flag + i, gen);
+    st_publish(out + i, kForward ? mul(t, wd[i]) : sub(in[i], mul(t, wd[i])));
 }
 
 }  // namespace lisb
 
 using namespace lisb;
 
-extern "C" int lisb200_ssor_sweep_syncfree(int forward, int nslots, const int *d_order,
+extern "C" int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *d_order,
                                            const int *d_pptr, const int *d_pidx, const double *d_pval,
                                            const double *d_wd, const int *d_rowblk_start, const int *d_rowblk_end,
-                                           const double *d_b, double *d_x, int *d_flag, int gen,
-                                           unsigned int *d_ticket, void *stream)
+                                           const double *d_in, double *d_out, unsigned int *d_ticket, void *stream)
 {
-    if (nslots <= 0) return 0;
+    if (nslots <= 0 || n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
+    int fill_grid = (n + 255) / 256;
+    if (fill_grid > 148 * 8) fill_grid = 148 * 8;
+    fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
     const int grid = (nslots + 127) / 128;
     if (forward)
         ssor_syncfree_kernel<true><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
-                                                        d_rowblk_end, d_b, d_x, d_flag, gen, d_ticket);
+                                                        d_rowblk_end, d_in, d_out, d_ticket);
     else
         ssor_syncfree_kernel<false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
-                                                         d_rowblk_end, d_b, d_x, d_flag, gen, d_ticket);
-    LISB_CHECK_LAUNCH();
-    return 0;
-}
-
-extern "C" int lisb200_ssor_forward_level(int nrows, const int *d_rows,
-                                          const int *d_lptr, const int *d_lidx, const double *d_lval,
-                                          const double *d_wd, const int *d_rowblk_start,
-                                          const double *d_b, double *d_x, void *stream)
-{
-    if (nrows <= 0) return 0;
-    ssor_fwd_kernel<<<(nrows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        nrows, d_rows, d_lptr, d_lidx, d_lval, d_wd, d_rowblk_start, d_b, d_x);
-    LISB_CHECK_LAUNCH();
-    return 0;
-}
-
-extern "C" int lisb200_ssor_backward_level(int nrows, const int *d_rows,
-                                           const int *d_uptr, const int *d_uidx, const double *d_uval,
-                                           const double *d_wd, const int *d_rowblk_start,
-                                           const int *d_rowblk_end, double *d_x, void *stream)
-{
-    if (nrows <= 0) return 0;
-    ssor_bwd_kernel<<<(nrows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        nrows, d_rows, d_uptr, d_uidx, d_uval, d_wd, d_rowblk_start, d_rowblk_end, d_x);
+                                                         d_rowblk_end, d_in, d_out, d_ticket);
     LISB_CHECK_LAUNCH();
     return 0;
 }
