@@ -162,3 +162,27 @@ extern "C" int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const
     LISB_CHECK_LAUNCH();
     return 0;
 }
+
+extern "C" int lisb200_ssor_forward_level(int nrows, const int *d_rows,
+                                          const int *d_lptr, const int *d_lidx, const double *d_lval,
+                                          const double *d_wd, const int *d_rowblk_start,
+                                          const double *d_b, double *d_x, void *stream)
+{
+    if (nrows <= 0) return 0;
+    ssor_fwd_kernel<<<(nrows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        nrows, d_rows, d_lptr, d_lidx, d_lval, d_wd, d_rowblk_start, d_b, d_x);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_ssor_backward_level(int nrows, const int *d_rows,
+                                           const int *d_uptr, const int *d_uidx, const double *d_uval,
+                                           const double *d_wd, const int *d_rowblk_start,
+                                           const int *d_rowblk_end, double *d_x, void *stream)
+{
+    if (nrows <= 0) return 0;
+    ssor_bwd_kernel<<<(nrows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        nrows, d_rows, d_uptr, d_uidx, d_uval, d_wd, d_rowblk_start, d_rowblk_end, d_x);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
