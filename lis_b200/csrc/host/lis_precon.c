@@ -70,6 +70,8 @@ LIS_INT lis_precon_register_free(void)
     return LIS_SUCCESS;
 }
 
+LIS_INT lis_host_ssor_prepare(LIS_MATRIX A);
+
 /* ------------------------------------------------------------------ create / destroy */
 static LIS_INT create_none(LIS_SOLVER solver, LIS_PRECON precon) { (void)solver; (void)precon; return LIS_SUCCESS; }
 
@@ -109,7 +111,7 @@ static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
     }
     precon->A = A;
     precon->is_copy = LIS_FALSE;
-    return LIS_SUCCESS;
+    return lis_host_ssor_prepare(A);      /* upload D/L/U and build the level schedule now, not in the first sweep */
 }
 
 static LIS_INT create_unsupported(LIS_SOLVER solver, LIS_PRECON precon)
@@ -365,6 +367,32 @@ fail:
     return err;
 }
 
+/* device mirror of the split matrix + the level schedule for the current block count; built
+ * once per matrix (setup cost, like the reference's lis_matrix_split in lis_precon_create_ssor) */
+static LIS_INT sweep_prepare(LIS_MATRIX A, lisd_matrix **Mout, lisd_sweep **Sout)
+{
+    lisd_matrix *M;
+    LIS_INT err = lisd_matrix_get(A, &M);
+    if (err) return err;
+    if (M->wd == NULL) { err = lisd_matrix_refresh_wd(A); if (err) return err; }
+    if (M->sweep == NULL || ((lisd_sweep *)M->sweep)->nblocks != sweep_blocks(A->n)) {
+        lisd_sweep *S;
+        if (M->sweep) { lisd_sweep_free(M->sweep); M->sweep = NULL; }
+        err = sweep_build(A, &S);
+        if (err) return err;
+        M->sweep = S;
+    }
+    *Mout = M; *Sout = (lisd_sweep *)M->sweep;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_host_ssor_prepare(LIS_MATRIX A)
+{
+    lisd_matrix *M; lisd_sweep *S;
+    if (!lisd_available()) return LIS_SUCCESS;         /* host-only use: the sweep itself will report the missing device */
+    return sweep_prepare(A, &M, &S);
+}
+
 /* x = M^-1 b; async on the library stream */
 LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
 {
@@ -380,17 +408,9 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
         return LIS_ERR_ILL_ARG;
     }
     lisd_matrix *M;
-    err = lisd_matrix_get(A, &M);
+    lisd_sweep *S;
+    err = sweep_prepare(A, &M, &S);
     if (err) return err;
-    if (M->wd == NULL) { err = lisd_matrix_refresh_wd(A); if (err) return err; }
-    if (M->sweep == NULL || ((lisd_sweep *)M->sweep)->nblocks != sweep_blocks(A->n)) {
-        lisd_sweep *S;
-        if (M->sweep) { lisd_sweep_free(M->sweep); M->sweep = NULL; }
-        err = sweep_build(A, &S);
-        if (err) return err;
-        M->sweep = S;
-    }
-    lisd_sweep *S = (lisd_sweep *)M->sweep;
     err = lisd_vec_device(b);
     if (!err) err = lisd_vec_device(x);
     if (err) return err;
