@@ -85,6 +85,10 @@ int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bptr, const i
 int lisb200_copy   (int n, const double *d_x, double *d_y, void *stream);               /* :136 */
 int lisb200_axpy   (int n, double alpha, const double *d_x, double *d_y, void *stream); /* :176 y += a*x */
 int lisb200_xpay   (int n, const double *d_x, double alpha, double *d_y, void *stream); /* :216 y = x + a*y */
+/* axpy whose coefficient is scale * (*d_alpha), *d_alpha written by an earlier reduction on the
+ * same stream (GMRES' Gram-Schmidt: t = <w,v_k>; w += (-t) v_k without a host round trip,
+ * src/solver/lis_solver_gmres.c:225-232).  scale = -1 negates exactly => same bits as axpy(-t). */
+int lisb200_axpy_dev(int n, const double *d_alpha, double scale, const double *d_x, double *d_y, void *stream);
 int lisb200_axpyz  (int n, double alpha, const double *d_x, const double *d_y, double *d_z, void *stream); /* :256 */
 int lisb200_scale  (int n, double alpha, double *d_x, void *stream);                    /* :287 */
 int lisb200_pmul   (int n, const double *d_x, const double *d_y, double *d_z, void *stream); /* :328 (also Jacobi psolve, src/precon/lis_precon_jacobi.c:119-126) */

@@ -16,6 +16,7 @@ typedef struct {
     double *partial; size_t partial_slots;
     unsigned int *counter;
     double *h_scalar, *d_scalar;
+    double *dev_scalars, *h_fetch;     /* device-resident reduction results + pinned landing zone */
 } lisd_ctx_t;
 
 static lisd_ctx_t g_ctx;
@@ -39,6 +40,8 @@ static void lisd_probe(void)
     if (cudaHostAlloc((void **)&g_ctx.h_scalar, LISD_NSCALARS * sizeof(double), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return; }
     if (cudaHostGetDevicePointer((void **)&g_ctx.d_scalar, g_ctx.h_scalar, 0) != cudaSuccess) { cudaGetLastError(); return; }
     memset(g_ctx.h_scalar, 0, LISD_NSCALARS * sizeof(double));
+    if (cudaMalloc((void **)&g_ctx.dev_scalars, LISD_NSCALARS * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaHostAlloc((void **)&g_ctx.h_fetch, LISD_NSCALARS * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return; }
     if (cudaMalloc((void **)&g_ctx.counter, 64) != cudaSuccess) { cudaGetLastError(); return; }
     cudaMemset(g_ctx.counter, 0, 64);
     g_ctx.device = dev;
@@ -85,6 +88,8 @@ void lisd_shutdown(void)
     if (g_ctx.partial) cudaFree(g_ctx.partial);
     if (g_ctx.counter) cudaFree(g_ctx.counter);
     if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
+    if (g_ctx.dev_scalars) cudaFree(g_ctx.dev_scalars);
+    if (g_ctx.h_fetch) cudaFreeHost(g_ctx.h_fetch);
     cudaStreamDestroy(g_ctx.stream);
     memset(&g_ctx, 0, sizeof(g_ctx));
 }
@@ -254,6 +259,18 @@ double *lisd_partial(size_t slots)
 }
 
 unsigned int *lisd_counter(void) { return g_ctx.counter; }
+double *lisd_dev_scalar(int slot) { return g_ctx.dev_scalars + slot; }
+
+/* queue a copy of device scalar slots [first, first+count) to pinned memory; valid after the
+ * next lisd_sync (or any later host-synchronous call); read with lisd_fetched() */
+LIS_INT lisd_dev_scalars_fetch(int first, int count)
+{
+    if (count <= 0) return LIS_SUCCESS;
+    g_ctx.busy = 1;
+    return lisd_check((int)cudaMemcpyAsync(g_ctx.h_fetch + first, g_ctx.dev_scalars + first, sizeof(double) * (size_t)count,
+                                           cudaMemcpyDeviceToHost, g_ctx.stream), "scalar read-back");
+}
+double lisd_fetched(int slot) { return ((volatile double *)g_ctx.h_fetch)[slot]; }
 /* where a reduction kernel writes its scalar(s): mapped pinned host memory on one rank (the
  * host reads it right after the stream sync), a device buffer feeding ncclAllGather otherwise */
 double *lisd_scalar_dev(int slot)

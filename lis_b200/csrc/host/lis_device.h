@@ -47,6 +47,12 @@ double       *lisd_partial(size_t slots);           /* device scratch, grown on 
 unsigned int *lisd_counter(void);
 double       *lisd_scalar_dev(int slot);            /* device alias of mapped scalar `slot` */
 double        lisd_scalar_get(int slot);            /* host value (after lisd_sync) */
+double       *lisd_dev_scalar(int slot);            /* device-resident scalar slot (stays on the GPU) */
+LIS_INT       lisd_dev_scalars_fetch(int first, int count);   /* queue D2H of slots; valid after the next sync */
+double        lisd_fetched(int slot);
+/* <x,y> into device slot `slot` without waiting; y += (scale * slot) * x reading it back on the device */
+LIS_INT       lisd_dot_to_slot(LIS_VECTOR x, LIS_VECTOR y, int slot);
+LIS_INT       lisd_axpy_from_slot(int slot, double scale, LIS_VECTOR x, LIS_VECTOR y);
 
 /* ---- matrix device mirror ---- */
 typedef struct lisd_csr {

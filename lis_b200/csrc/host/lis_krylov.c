@@ -206,6 +206,7 @@ LIS_INT lis_gmres(LIS_SOLVER solver)
     LIS_INT iter, i, j, k, ii = 0, i1 = 0, iih, jj;
     LIS_INT err = LIS_SUCCESS;
     double time, ptime = 0.0;
+    const int mgs_on_device = fuse_enabled() && lisd_nranks() == 1;
 
     LIS_SCALAR *h = (LIS_SCALAR *)lis_malloc(sizeof(LIS_SCALAR) * (size_t)(h_dim + 1) * (size_t)(h_dim + 2), "lis_gmres::h");
     LIS_SCALAR *s = (LIS_SCALAR *)lis_calloc(sizeof(LIS_SCALAR) * (size_t)(m + 2), "lis_gmres::s");
@@ -238,13 +239,26 @@ LIS_INT lis_gmres(LIS_SOLVER solver)
             GCHK(lis_psolve(solver, v[ii], z));
             ptime += lis_wtime() - time;
             GCHK(lisd_matvec(A, z, v[i1]));
-            /* modified Gram-Schmidt */
-            for (k = 0; k < i; k++) {
-                GCHK(lis_vector_dot(v[i1], v[k], &t));
-                h[k + iih] = t;
-                GCHK(lisd_axpy(-t, v[k], v[i1]));
+            /* modified Gram-Schmidt: h[k] = <w,v_k>; w -= h[k] v_k.  On one rank the i dot->axpy
+             * pairs are chained on the device (the axpy reads its coefficient from the slot the dot
+             * wrote) and the host collects h[0..i) with the norm that follows: one wait per Krylov
+             * step instead of i+1.  Same kernels, same bits. */
+            if (mgs_on_device && i <= LISD_NSCALARS) {
+                for (k = 0; k < i; k++) {
+                    GCHK(lisd_dot_to_slot(v[i1], v[k], (int)k));
+                    GCHK(lisd_axpy_from_slot((int)k, -1.0, v[k], v[i1]));
+                }
+                GCHK(lisd_dev_scalars_fetch(0, (int)i));
+                GCHK(lis_vector_nrm2(v[i1], &t));           /* waits for the stream */
+                for (k = 0; k < i; k++) h[k + iih] = lisd_fetched((int)k);
+            } else {
+                for (k = 0; k < i; k++) {
+                    GCHK(lis_vector_dot(v[i1], v[k], &t));
+                    h[k + iih] = t;
+                    GCHK(lisd_axpy(-t, v[k], v[i1]));
+                }
+                GCHK(lis_vector_nrm2(v[i1], &t));
             }
-            GCHK(lis_vector_nrm2(v[i1], &t));
             h[i1 + iih] = t;
             GCHK(lisd_scale(1.0 / t, v[i1]));
             /* Givens rotations on the new Hessenberg column */

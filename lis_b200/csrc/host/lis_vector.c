@@ -376,6 +376,23 @@ LIS_INT lisd_dot2(LIS_VECTOR a, LIS_VECTOR b, LIS_SCALAR out[2])
     return lisd_reduce_finish(out, 2, 0);
 }
 
+/* ---- reductions that stay on the device (single rank): GMRES' modified Gram-Schmidt ---- */
+LIS_INT lisd_dot_to_slot(LIS_VECTOR x, LIS_VECTOR y, int slot)
+{
+    LISD_PREP2(x, y, "lis_vector_dot");
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    return lisd_check(lisb200_reduce(0, x->n, x->value, y->value, partial, lisd_counter(), lisd_dev_scalar(slot), lisd_stream()),
+                      "lis_vector_dot");
+}
+
+LIS_INT lisd_axpy_from_slot(int slot, double scale, LIS_VECTOR x, LIS_VECTOR y)
+{
+    LISD_PREP2(x, y, "lis_vector_axpy");
+    LISD_LAUNCH(lisb200_axpy_dev(x->n, lisd_dev_scalar(slot), scale, x->value, y->value, lisd_stream()), "lis_vector_axpy");
+}
+
 /* reductions: kernel -> mapped host scalar; ranks combined in rank order on the host */
 LIS_INT lisd_reduce(int kind, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *value)
 {

@@ -68,6 +68,17 @@ struct AxpyF {      // y += alpha*x
         reinterpret_cast<double2 *>(y)[i] = yv;
     }
 };
+struct AxpyDevF {   // y += (scale * *alpha_dev) * x : alpha comes from an earlier reduction on the same stream
+    const double *alpha_dev; double scale; const double *x; double *y;
+    __device__ void one(int i) const { const double a = mul(scale, *alpha_dev); y[i] = add(y[i], mul(a, x[i])); }
+    __device__ void vec2(int i) const {
+        const double a = mul(scale, *alpha_dev);
+        double2 xv = reinterpret_cast<const double2 *>(x)[i];
+        double2 yv = reinterpret_cast<double2 *>(y)[i];
+        yv.x = add(yv.x, mul(a, xv.x)); yv.y = add(yv.y, mul(a, xv.y));
+        reinterpret_cast<double2 *>(y)[i] = yv;
+    }
+};
 struct XpayF {      // y = x + alpha*y
     double a; const double *x; double *y;
     __device__ void one(int i) const { y[i] = add(x[i], mul(a, y[i])); }
@@ -345,6 +356,8 @@ extern "C" int lisb200_copy(int n, const double *x, double *y, void *s)
 { return launch_ew(n, CopyF{x, y}, aligned16(x) && aligned16(y), s); }
 extern "C" int lisb200_axpy(int n, double a, const double *x, double *y, void *s)
 { return launch_ew(n, AxpyF{a, x, y}, aligned16(x) && aligned16(y), s); }
+extern "C" int lisb200_axpy_dev(int n, const double *d_alpha, double scale, const double *x, double *y, void *s)
+{ return launch_ew(n, AxpyDevF{d_alpha, scale, x, y}, aligned16(x) && aligned16(y), s); }
 extern "C" int lisb200_xpay(int n, const double *x, double a, double *y, void *s)
 { return launch_ew(n, XpayF{a, x, y}, aligned16(x) && aligned16(y), s); }
 extern "C" int lisb200_axpyz(int n, double a, const double *x, const double *y, double *z, void *s)

@@ -72,6 +72,14 @@ def main():
             rel = np.abs(rg["rhistory"][:k] - rr["rhistory"][:k]) / rr["rhistory"][:k]
             print(f"  iterations {rg['iter']} vs {rr['iter']}; history gap: first quarter {rel[:k // 4].max():.2e}, "
                   f"first half {rel[:k // 2].max():.2e}, all {rel.max():.2e}; |x-1|max {np.abs(rg['x'] - 1).max():.2e}")
+        for blocks in (1, T):
+            g.set_threads(blocks)
+            rs = run(g, f"b200 T={blocks}", ptr, idx, val, b, "-i cg -p ssor -maxiter 5000")
+        g.set_threads(1)
+        if ref:
+            ref.set_threads(T)
+            rr = run(ref, f"ref omp{T}", ptr, idx, val, b, "-i cg -p ssor -maxiter 5000")
+            print(f"  CG+SSOR iterations (blocks={T}) {rs['iter']} vs {rr['iter']}")
     if su_rows:
         print(f"BiCGSTAB + SSOR, unsymmetric banded, n={su_rows}, 70 nnz/row")
         ptr, idx, val = su_matrix(su_rows)
