@@ -180,7 +180,7 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     on the library's stream, maximum over the ranks."""
     Ls = shim.lib
     i32p = np.ctypeslib.ndpointer(np.int32, flags="C"); f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
-    Ls.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p]
+    Ls.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     Ls.shim_mv_set_x_local.argtypes = [C.c_int, C.c_void_p]; Ls.shim_mv_get_y_local.argtypes = [C.c_int, C.c_void_p]
     lib = lis_b200.load_library()
     lib.lis_b200_comm_attach.argtypes = [C.c_int, C.c_int, C.c_ulonglong]
@@ -191,11 +191,19 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     dist.broadcast(tok, 0)
     rc = lib.lis_b200_comm_attach(rank, world, int(tok.item())); assert rc == 0, rc
     t0 = time.time()
-    hp, hi, hv = ptr.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy()
+    # host arrays straight from malloc, adopted by lis_matrix_set_csr (one host copy per rank)
+    h_ptr, p_ptr = host_malloc_array(n + 1, np.int32)
+    h_idx, p_idx = host_malloc_array(nnz, np.int32)
+    h_val, p_val = host_malloc_array(nnz, np.float64)
+    torch.from_numpy(h_ptr).copy_(ptr); torch.from_numpy(h_idx).copy_(idx); torch.from_numpy(h_val).copy_(val)
     del ptr, idx, val
     torch.cuda.empty_cache()
-    h = Ls.shim_mv_open_dist(1, n, hp, hi, hv); assert h >= 0, h
-    del hp, hi, hv
+    h = Ls.shim_mv_open_dist(1, n, p_ptr, p_idx, p_val, 1); assert h >= 0, h
+    if rank == 0:
+        try:
+            log(subprocess.run(["free", "-g"], capture_output=True, text=True).stdout.strip())
+        except Exception:
+            pass
     log(f"[rank {rank}] row-partitioned matrix assembled in {time.time() - t0:.1f}s")
     hx = torch.empty(n, dtype=torch.float64).pin_memory(); hy = torch.empty(n, dtype=torch.float64).pin_memory()
     hx.uniform_(-1, 1)

@@ -129,7 +129,14 @@ LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
                 pool_clear();                                  /* give parked blocks back and retry once */
                 e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
             }
-            if (e != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+            if (e != cudaSuccess) {
+                size_t fr = 0, tot = 0;
+                cudaGetLastError();
+                cudaMemGetInfo(&fr, &tot);
+                LIS_SETERR3(LIS_ERR_OUT_OF_MEMORY, "cudaMallocManaged(%D MiB) failed: %s; device free %D MiB\n",
+                            (LIS_INT)(bytes >> 20), lisb200_error_string((int)e), (LIS_INT)(fr >> 20));
+                return LIS_ERR_OUT_OF_MEMORY;
+            }
         }
         /* populate / bring the pages to HBM in one go (advisory: faults still work if it fails) */
         if (cudaMemPrefetchAsync(p, bytes, g_ctx.device, g_ctx.stream) != cudaSuccess) cudaGetLastError();

@@ -96,7 +96,7 @@ def main():
 
     result = {"rank": rank, "mode": mode}
     if mode == "gpu":
-        L.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p]
+        L.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int]
         L.shim_mv_set_x_local.argtypes = [C.c_int, f64p]; L.shim_mv_get_y_local.argtypes = [C.c_int, f64p]
         L.shim_mv_dot_xy.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.shim_mv_solve_b.argtypes = [C.c_int, C.c_char_p, f64p, f64p, i32p, f64p, f64p, C.c_int]
@@ -105,7 +105,7 @@ def main():
         y_full = o.spmv("csr", ptr, idx, val, x)
         bvec = o.spmv("csr", ptr, idx, val, np.ones(gn))
         for fmt in ("csr", "ell", "dia", "jad"):
-            h = L.shim_mv_open_dist(lis_b200.FMT[fmt], nl, lp, li, lv)
+            h = L.shim_mv_open_dist(lis_b200.FMT[fmt], nl, lp, li, lv, 0)
             assert h >= 0, (fmt, h)
             assert L.shim_mv_set_x_local(h, np.ascontiguousarray(x[is_:ie])) == 0
             for rep in range(2):                        # second product: the halo buffer is reused

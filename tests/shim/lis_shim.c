@@ -475,7 +475,7 @@ EXPORT int shim_mv_open(int fmt, int n, int *ptr, int *idx, double *val, int bnr
 
 /* row-partitioned: this rank hands over its n_local rows with GLOBAL column indices
  * (lis_matrix_set_size(A, n_local, 0), like an MPI rank of the reference would) */
-EXPORT int shim_mv_open_dist(int fmt, int n_local, const int *ptr, const int *idx, const double *val)
+EXPORT int shim_mv_open_dist(int fmt, int n_local, int *ptr, int *idx, double *val, int adopt)
 {
     int h;
     LIS_MATRIX A0 = NULL, A = NULL;
@@ -486,13 +486,16 @@ EXPORT int shim_mv_open_dist(int fmt, int n_local, const int *ptr, const int *id
     if (h == 8) return -1;
     err = lis_matrix_create(LIS_COMM_WORLD, &A0); if (err) return -2;
     err = lis_matrix_set_size(A0, n_local, 0); if (err) return -2;
-    p = (LIS_INT *)malloc(sizeof(LIS_INT) * ((size_t)n_local + 1));
-    ix = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(nnz > 0 ? nnz : 1));
-    v = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(nnz > 0 ? nnz : 1));
-    if (!p || !ix || !v) return -2;
-    memcpy(p, ptr, sizeof(LIS_INT) * ((size_t)n_local + 1));
-    memcpy(ix, idx, sizeof(LIS_INT) * (size_t)nnz);
-    memcpy(v, val, sizeof(LIS_SCALAR) * (size_t)nnz);
+    if (adopt) { p = ptr; ix = idx; v = val; }          /* malloc'ed by the caller, handed over */
+    else {
+        p = (LIS_INT *)malloc(sizeof(LIS_INT) * ((size_t)n_local + 1));
+        ix = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(nnz > 0 ? nnz : 1));
+        v = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(nnz > 0 ? nnz : 1));
+        if (!p || !ix || !v) return -2;
+        memcpy(p, ptr, sizeof(LIS_INT) * ((size_t)n_local + 1));
+        memcpy(ix, idx, sizeof(LIS_INT) * (size_t)nnz);
+        memcpy(v, val, sizeof(LIS_SCALAR) * (size_t)nnz);
+    }
     err = lis_matrix_set_csr(nnz, p, ix, v, A0); if (err) return -2;
     err = lis_matrix_assemble(A0); if (err) return -2;
     if (fmt == LIS_MATRIX_CSR) A = A0;
