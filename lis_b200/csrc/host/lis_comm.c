@@ -423,6 +423,7 @@ struct LIS_COMMTABLE_STRUCT {
     int *export_index;                        /* local row numbers, host */
     int *d_export_index;                      /* device copy */
     double *d_ws;                             /* packed send buffer, device */
+    double *d_wr;                             /* receive buffer, device (plain cudaMalloc: NCCL never sees managed memory) */
     int neibpetot;                            /* number of ranks exchanged with (information) */
 };
 
@@ -432,15 +433,20 @@ void lisd_commtable_destroy(LIS_COMMTABLE t)
     free(t->export_index);
     lisd_free(t->d_export_index);
     lisd_free(t->d_ws);
+    lisd_free(t->d_wr);
     free(t);
 }
 
 static LIS_INT commtable_to_device(LIS_COMMTABLE t)
 {
-    if (!lisd_available() || t->n_export == 0) return LIS_SUCCESS;
-    LIS_INT err = lisd_malloc((void **)&t->d_export_index, sizeof(int) * (size_t)t->n_export);
-    if (!err) err = lisd_upload(t->d_export_index, t->export_index, sizeof(int) * (size_t)t->n_export);
-    if (!err) err = lisd_malloc((void **)&t->d_ws, sizeof(double) * (size_t)t->n_export);
+    LIS_INT err = LIS_SUCCESS;
+    if (!lisd_available()) return LIS_SUCCESS;
+    if (t->n_export) {
+        err = lisd_malloc((void **)&t->d_export_index, sizeof(int) * (size_t)t->n_export);
+        if (!err) err = lisd_upload(t->d_export_index, t->export_index, sizeof(int) * (size_t)t->n_export);
+        if (!err) err = lisd_malloc((void **)&t->d_ws, sizeof(double) * (size_t)t->n_export);
+    }
+    if (!err && t->n_import) err = lisd_malloc((void **)&t->d_wr, sizeof(double) * (size_t)t->n_import);
     return err;
 }
 
@@ -499,7 +505,7 @@ LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout)
     LIS_COMMTABLE t = (LIS_COMMTABLE)malloc(sizeof(struct LIS_COMMTABLE_STRUCT));
     if (!t) { LIS_SETERR_MEM(sizeof(struct LIS_COMMTABLE_STRUCT)); return LIS_OUT_OF_MEMORY; }
     memcpy(t, s, sizeof(*t));
-    t->d_export_index = NULL; t->d_ws = NULL;
+    t->d_export_index = NULL; t->d_ws = NULL; t->d_wr = NULL;
     t->export_index = (int *)malloc(sizeof(int) * (size_t)(s->n_export > 0 ? s->n_export : 1));
     if (!t->export_index) { free(t); LIS_SETERR_MEM(s->n_export); return LIS_OUT_OF_MEMORY; }
     memcpy(t->export_index, s->export_index, sizeof(int) * (size_t)s->n_export);
@@ -524,7 +530,7 @@ LIS_INT lis_b200_commtable_info(LIS_MATRIX A, LIS_INT *out, LIS_INT *import_ptr,
 
 /* ------------------------------------------------------------------ halo exchange
  * pack ws[i] = x[export_index[i]] (one gather kernel), then one NCCL group of sends/receives;
- * received values land directly in x[n + import_ptr[k] ...].  Asynchronous on the stream. */
+ * received values land in a device buffer and are copied into x[n ...].  Asynchronous on the stream. */
 static LIS_INT halo_exchange_raw(LIS_COMMTABLE t, LIS_INT n, double *x)
 {
     if (t == NULL || g.nranks == 1) return LIS_SUCCESS;
@@ -542,10 +548,15 @@ static LIS_INT halo_exchange_raw(LIS_COMMTABLE t, LIS_INT n, double *x)
         if (k == t->rank) continue;
         const int ne = t->export_ptr[k + 1] - t->export_ptr[k], ni = t->import_ptr[k + 1] - t->import_ptr[k];
         if (ne) { err = nccl_check(g.Send(t->d_ws + t->export_ptr[k], (size_t)ne, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclSend"); if (err) { g.GroupEnd(); return err; } }
-        if (ni) { err = nccl_check(g.Recv(x + n + t->import_ptr[k], (size_t)ni, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclRecv"); if (err) { g.GroupEnd(); return err; } }
+        if (ni) { err = nccl_check(g.Recv(t->d_wr + t->import_ptr[k], (size_t)ni, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclRecv"); if (err) { g.GroupEnd(); return err; } }
     }
     lisd_mark_busy();
-    return nccl_check(g.GroupEnd(), "ncclGroupEnd");
+    err = nccl_check(g.GroupEnd(), "ncclGroupEnd");
+    if (err) return err;
+    /* unpack: the halo is contiguous in x (like the reference's copy of wr into x[n+pad..], :946-951) */
+    if (t->n_import)
+        err = lisd_check((int)cudaMemcpyAsync(x + n, t->d_wr, sizeof(double) * (size_t)t->n_import, cudaMemcpyDeviceToDevice, st), "halo unpack");
+    return err;
 }
 
 LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x) { return halo_exchange_raw(A->commtable, A->n, x->value); }
