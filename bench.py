@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the halo planes travel point to point and the reductions are 8-byte messages: NVLS multicast
+# buys nothing here, and its buffers have been seen to break later managed allocations at 8 ranks
+os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
 
 _libc = C.CDLL("libc.so.6")
 _libc.malloc.restype = C.c_void_p

@@ -233,6 +233,9 @@ static LIS_INT attach(int rank, int nranks, uint64_t token, int token_is_unique)
 
     /* data plane */
     if (lisd_available()) {
+        /* point-to-point halo traffic and 8-byte gathers gain nothing from NVLS multicast; its setup
+         * has been seen to break later cudaMallocManaged calls with 8 processes per node */
+        setenv("NCCL_NVLS_ENABLE", "0", 0);
         nccl_load();
         lisc_nccl_id id;
         memset(&id, 0, sizeof(id));
@@ -325,7 +328,14 @@ LIS_INT lis_b200_allreduce_sum(double *vals, LIS_INT count) { return allreduce_h
 /* device path of a reduction: the kernel left `count` partial scalars in lisd_scalar_dev();
  * NCCL all-gathers them over NVLink, one pinned copy brings the nranks x count table to the
  * host, the host folds it in rank order (same bits on every rank) */
-int lisd_reduce_uses_nccl(void) { return g.nranks > 1 && g.nccl_ok; }
+/* Default: the scalars go through the host control plane (mapped scalar -> shm exchange, ~2 us,
+ * no NCCL collective involved); LIS_B200_REDUCE=nccl selects the ncclAllGather route. */
+int lisd_reduce_uses_nccl(void)
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("LIS_B200_REDUCE"); mode = (e && strcmp(e, "nccl") == 0) ? 1 : 0; }
+    return mode == 1 && g.nranks > 1 && g.nccl_ok;
+}
 double *lisd_reduce_dev_buffer(void) { return g.d_red; }
 
 LIS_INT lisd_reduce_nccl_finish(double *vals, int count, int is_max)

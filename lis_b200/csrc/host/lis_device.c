@@ -130,12 +130,26 @@ LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
                 e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
             }
             if (e != cudaSuccess) {
+                /* managed memory refused (seen with 8 processes on one node once NCCL has set up its
+                 * collectives): fall back to plain device memory.  Such a vector is reachable from
+                 * the host through the API only (get/set_value(s), scatter/gather), not by
+                 * dereferencing v->value */
+                static int warned = 0;
                 size_t fr = 0, tot = 0;
+                const char *why = lisb200_error_string((int)e);
                 cudaGetLastError();
-                cudaMemGetInfo(&fr, &tot);
-                LIS_SETERR3(LIS_ERR_OUT_OF_MEMORY, "cudaMallocManaged(%D MiB) failed: %s; device free %D MiB\n",
-                            (LIS_INT)(bytes >> 20), lisb200_error_string((int)e), (LIS_INT)(fr >> 20));
-                return LIS_ERR_OUT_OF_MEMORY;
+                e = cudaMalloc(&p, bytes);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaMemGetInfo(&fr, &tot);
+                    LIS_SETERR3(LIS_ERR_OUT_OF_MEMORY, "vector allocation of %D MiB failed: %s; device free %D MiB\n",
+                                (LIS_INT)(bytes >> 20), lisb200_error_string((int)e), (LIS_INT)(fr >> 20));
+                    return LIS_ERR_OUT_OF_MEMORY;
+                }
+                if (!warned) { warned = 1; fprintf(stderr, "lis_b200: cudaMallocManaged failed (%s); using device-only vector storage\n", why); }
+                *value = (LIS_SCALAR *)p;
+                *managed = 2;
+                return LIS_SUCCESS;
             }
         }
         /* populate / bring the pages to HBM in one go (advisory: faults still work if it fails) */
@@ -157,6 +171,7 @@ void lisd_free_vector_bytes(LIS_SCALAR *value, LIS_INT managed, size_t count)
 {
     if (value == NULL) return;
     if (!managed) { free(value); return; }
+    if (managed == 2) { lisd_sync(); cudaFree(value); return; }
     size_t bytes = (count > 0 ? count : 1) * sizeof(LIS_SCALAR);
     bytes = (bytes + 255) & ~(size_t)255;
     if (g_ctx.available && g_pool_bytes + bytes <= g_pool_cap) {
@@ -225,7 +240,7 @@ LIS_INT lisd_vec_device(LIS_VECTOR v)
         LIS_SETERR(LIS_ERR_DEVICE, "vector storage is not device accessible\n");
         return LIS_ERR_DEVICE;
     }
-    if (v->b200_resident) return LIS_SUCCESS;
+    if (v->b200_resident || v->b200_managed == 2) return LIS_SUCCESS;
     size_t bytes = v->b200_capacity * sizeof(LIS_SCALAR);
     cudaError_t e = cudaMemPrefetchAsync(v->value, bytes, g_ctx.device, g_ctx.stream);
     if (e != cudaSuccess) cudaGetLastError();      /* advisory only: page faults still work */
@@ -237,6 +252,7 @@ LIS_INT lisd_vec_device(LIS_VECTOR v)
 void lisd_vec_host(LIS_VECTOR v)
 {
     lisd_sync();
+    if (v->b200_managed == 2) return;          /* device-only storage: callers go through upload/download */
     if (v->b200_managed && v->b200_resident && g_ctx.available) {
         /* bring the whole vector back in one bulk migration instead of page faults */
         size_t bytes = v->b200_capacity * sizeof(LIS_SCALAR);

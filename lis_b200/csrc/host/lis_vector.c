@@ -38,7 +38,7 @@ static LIS_INT vector_alloc_zero(LIS_VECTOR v, size_t count)
     v->b200_managed = managed;
     v->b200_capacity = count > 0 ? count : 1;
     if (managed) {
-        /* zero on the device: the pages are born in HBM */
+        /* zero on the device: the pages are born in HBM (managed == 2: device-only fallback) */
         err = lisd_memset(v->value, 0, v->b200_capacity * sizeof(LIS_SCALAR));
         if (err) return err;
         v->b200_resident = 1;
@@ -194,6 +194,14 @@ LIS_INT lis_vector_set_value(LIS_INT flag, LIS_INT i, LIS_SCALAR value, LIS_VECT
         LIS_SETERR(LIS_ERR_ILL_ARG, "vector v is undefined\n");
         return LIS_ERR_ILL_ARG;
     }
+    if (v->b200_managed == 2) {                 /* device-only storage: one element through the copy engine */
+        LIS_SCALAR cur = 0.0;
+        LIS_INT err = lisd_sync();
+        if (!err && flag != LIS_INS_VALUE) err = lisd_download(&cur, v->value + (i - v->is), sizeof(LIS_SCALAR));
+        if (err) return err;
+        cur = (flag == LIS_INS_VALUE) ? value : cur + value;
+        return lisd_upload(v->value + (i - v->is), &cur, sizeof(LIS_SCALAR));
+    }
     if (v->b200_resident) lisd_vec_host(v);
     if (flag == LIS_INS_VALUE) v->value[i - v->is] = value;
     else v->value[i - v->is] += value;
@@ -220,6 +228,16 @@ LIS_INT lis_vector_set_values2(LIS_INT flag, LIS_INT start, LIS_INT count, LIS_S
         LIS_INT err = lisd_sync();
         if (err) return err;
         return lisd_upload(v->value + (start - v->is), value, (size_t)count * sizeof(LIS_SCALAR));
+    }
+    if (v->b200_managed == 2) {
+        LIS_SCALAR *tmp = (LIS_SCALAR *)malloc((size_t)(count > 0 ? count : 1) * sizeof(LIS_SCALAR));
+        if (!tmp) { LIS_SETERR_MEM(count * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
+        LIS_INT err = lisd_sync();
+        if (!err) err = lisd_download(tmp, v->value + (start - v->is), (size_t)count * sizeof(LIS_SCALAR));
+        for (LIS_INT k = 0; !err && k < count; k++) tmp[k] += value[k];
+        if (!err) err = lisd_upload(v->value + (start - v->is), tmp, (size_t)count * sizeof(LIS_SCALAR));
+        free(tmp);
+        return err;
     }
     lisd_vec_host(v);
     if (flag == LIS_INS_VALUE) memcpy(v->value + (start - v->is), value, (size_t)count * sizeof(LIS_SCALAR));
