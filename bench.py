@@ -33,6 +33,11 @@ sys.path.insert(0, ROOT)
 # the halo planes travel point to point and the reductions are 8-byte messages: NVLS multicast
 # buys nothing here, and its buffers have been seen to break later managed allocations at 8 ranks
 os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+# one process per GPU: show each rank only its own device (managed vector storage would otherwise
+# be mapped into every visible peer; with 8 ranks x 8 visible GPUs cudaMallocManaged was seen to fail)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "LOCAL_RANK" in os.environ and "CUDA_VISIBLE_DEVICES" not in os.environ:
+    os.environ["CUDA_VISIBLE_DEVICES"] = os.environ["LOCAL_RANK"]
+    os.environ["LIS_B200_PHYSICAL_GPU"] = os.environ["LOCAL_RANK"]
 
 _libc = C.CDLL("libc.so.6")
 _libc.malloc.restype = C.c_void_p
@@ -45,44 +50,74 @@ def log(*a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons of one GPU while the timed region runs, read through NVML in a
+    thread of this process every few ms (nvidia-smi -lms is the fallback: its start-up alone is
+    longer than a 20-step timed region, and eight of them at once stall the launches they watch)."""
+    R = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index: int, period=0.004):
+        self.gpu, self.period = gpu_index, period
+        self.sm, self.reasons, self.power = [], set(), []
+        self._stop = threading.Event()
+        self.thread = None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: match by PCI bus id through torch when possible
+            self.nv = pynvml
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
+                dom = torch.cuda.get_device_properties(gpu_index).pci_domain_id
+                devid = torch.cuda.get_device_properties(gpu_index).pci_device_id
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{devid:02x}.0")
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.R.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        pw = [float(r[3]) for r in self.rows if len(r) > 3 and r[3].replace(".", "", 1).isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+        if self.h is None:
+            return self._smi_once()
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "power_w_max": max(self.power) if self.power else None, "source": "nvml"}
+
+    def _smi_once(self):
+        try:
+            q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                               capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": int(o[0]), "sm_max_mhz": int(o[1]), "power_w_max": float(o[2]),
+                    "reasons": [n for n, v in zip(names, o[3:]) if v.strip().lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi after the timed region (NVML unavailable)"}
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unavailable: {e!r}"], "samples": 0}
 
 
 # ----------------------------------------------------------------------------- matrices
@@ -214,16 +249,20 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     stream = torch.cuda.ExternalStream(lib.lis_b200_stream(), device=dev)
     for _ in range(args.warmup):
         assert Ls.shim_mv_matvec(h) == 0
+    sampler = ClockSampler(local) if rank == 0 else None
     dist.barrier(); torch.cuda.synchronize()
-    sampler = ClockSampler(local).start()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
+    if sampler:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for k in range(args.steps):
         assert Ls.shim_mv_matvec(h) == 0
-    e1.record(stream)
+        evs[k + 1].record(stream)
     stream.synchronize()
-    clocks = sampler.stop()
-    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    clocks = sampler.stop() if sampler else None
+    per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps))
+    log(f"[rank {rank}] per-product ms: min {per[0]:.3f} median {per[len(per) // 2]:.3f} max {per[-1]:.3f}")
+    t = torch.tensor([evs[0].elapsed_time(evs[-1]) * 1e-3], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_s = float(t.item()) / args.steps
     # e2e: local slice of x in from pinned host memory, product, local slice of y out
@@ -297,6 +336,8 @@ def run_b200(args, grid):
     import lis_b200
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if "LIS_B200_PHYSICAL_GPU" in os.environ:
+        local = 0                      # CUDA_VISIBLE_DEVICES narrowed to this rank's GPU
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl lis_b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -480,6 +521,9 @@ def run_b200(args, grid):
 
 
 def main():
+    # keep stdout for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1 too
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -494,7 +538,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference(args, args.grid)), flush=True)
+            print(json.dumps(run_reference(args, args.grid)), file=json_out, flush=True)
         return
     out = run_b200(args, args.grid)
     if rank == 0 and out is not None:
@@ -505,7 +549,7 @@ def main():
                 out["cpu_baseline"] = r.get("cpu_baseline", {"unavailable": r.get("unavailable")})
             except Exception as e:  # the baseline must never take the bench line down
                 out["cpu_baseline"] = {"unavailable": repr(e)}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=json_out, flush=True)
 
 
 if __name__ == "__main__":
