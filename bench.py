@@ -501,7 +501,10 @@ def run_b200(args, grid):
                     "what": "lis_vector_scatter(pinned host x) + lis_matvec + lis_vector_gather(pinned host y) per step"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false>", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": ach / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak_gbs,
+                         "traffic": 14092449000 if grid == 512 else None,
+                         "traffic_source": "dram__bytes_read+write of one launch, ncu --set full (profiles/r01_ncu_summary.txt)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_csr},
             "clocks": clocks,
             "extra": {
