@@ -236,7 +236,9 @@ static LIS_INT attach(int rank, int nranks, uint64_t token, int token_is_unique)
         /* point-to-point halo traffic and 8-byte gathers gain nothing from NVLS multicast; its setup
          * has been seen to break later cudaMallocManaged calls with 8 processes per node */
         setenv("NCCL_NVLS_ENABLE", "0", 0);
-        nccl_load();
+        /* LIS_B200_TRANSPORT=host: do not touch NCCL, stage the halo through host memory */
+        const char *tr = getenv("LIS_B200_TRANSPORT");
+        if (!(tr && strcmp(tr, "host") == 0)) nccl_load();
         lisc_nccl_id id;
         memset(&id, 0, sizeof(id));
         int have = g.dl && g.GetUniqueId && g.CommInitRank && g.AllGather && g.Send && g.Recv && g.GroupStart && g.GroupEnd;
@@ -260,7 +262,7 @@ static LIS_INT attach(int rank, int nranks, uint64_t token, int token_is_unique)
             }
             g.nccl_ok = 1;
         } else if (rank == 0) {
-            fprintf(stderr, "lis_b200: NCCL not available, halo exchange is disabled\n");
+            fprintf(stderr, "lis_b200: NCCL not available, halo exchange is staged through host memory\n");
         }
     }
     return LIS_SUCCESS;
@@ -434,6 +436,10 @@ struct LIS_COMMTABLE_STRUCT {
     int *d_export_index;                      /* device copy */
     double *d_ws;                             /* packed send buffer, device */
     double *d_wr;                             /* receive buffer, device (plain cudaMalloc: NCCL never sees managed memory) */
+    int *peer_export_ptr;                     /* [k*(nranks+1) + j]: export_ptr of rank k (host-staged transport) */
+    int *peer_n_export;                       /* total exported entries of rank k */
+    double *h_stage;                          /* host staging for the transport without NCCL */
+    size_t h_stage_len;
     int neibpetot;                            /* number of ranks exchanged with (information) */
 };
 
@@ -444,6 +450,7 @@ void lisd_commtable_destroy(LIS_COMMTABLE t)
     lisd_free(t->d_export_index);
     lisd_free(t->d_ws);
     lisd_free(t->d_wr);
+    free(t->peer_export_ptr); free(t->peer_n_export); free(t->h_stage);
     free(t);
 }
 
@@ -502,6 +509,13 @@ LIS_INT lisd_commtable_create(LIS_MATRIX A)
     free(all);
     for (int k = 0; k < np_; k++)
         if (k != me && (t->import_ptr[k + 1] > t->import_ptr[k] || t->export_ptr[k + 1] > t->export_ptr[k])) t->neibpetot++;
+    /* every rank's export table: lets the host-staged transport find "what rank k packed for me" */
+    t->peer_export_ptr = (int *)malloc(sizeof(int) * (size_t)np_ * (size_t)(np_ + 1));
+    t->peer_n_export = (int *)malloc(sizeof(int) * (size_t)np_);
+    if (!t->peer_export_ptr || !t->peer_n_export) { lisd_commtable_destroy(t); LIS_SETERR_MEM(np_ * np_); return LIS_OUT_OF_MEMORY; }
+    err = lisd_allgather_int(t->export_ptr, np_ + 1, t->peer_export_ptr);
+    if (err) { lisd_commtable_destroy(t); return err; }
+    for (int k = 0; k < np_; k++) t->peer_n_export[k] = t->peer_export_ptr[k * (np_ + 1) + np_];
     err = commtable_to_device(t);
     if (err) { lisd_commtable_destroy(t); return err; }
     A->commtable = t;
@@ -516,6 +530,12 @@ LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout)
     if (!t) { LIS_SETERR_MEM(sizeof(struct LIS_COMMTABLE_STRUCT)); return LIS_OUT_OF_MEMORY; }
     memcpy(t, s, sizeof(*t));
     t->d_export_index = NULL; t->d_ws = NULL; t->d_wr = NULL;
+    t->h_stage = NULL; t->h_stage_len = 0;
+    t->peer_export_ptr = (int *)malloc(sizeof(int) * (size_t)s->nranks * (size_t)(s->nranks + 1));
+    t->peer_n_export = (int *)malloc(sizeof(int) * (size_t)s->nranks);
+    if (!t->peer_export_ptr || !t->peer_n_export) { free(t->peer_export_ptr); free(t->peer_n_export); free(t); LIS_SETERR_MEM(s->nranks); return LIS_OUT_OF_MEMORY; }
+    memcpy(t->peer_export_ptr, s->peer_export_ptr, sizeof(int) * (size_t)s->nranks * (size_t)(s->nranks + 1));
+    memcpy(t->peer_n_export, s->peer_n_export, sizeof(int) * (size_t)s->nranks);
     t->export_index = (int *)malloc(sizeof(int) * (size_t)(s->n_export > 0 ? s->n_export : 1));
     if (!t->export_index) { free(t); LIS_SETERR_MEM(s->n_export); return LIS_OUT_OF_MEMORY; }
     memcpy(t->export_index, s->export_index, sizeof(int) * (size_t)s->n_export);
@@ -541,10 +561,50 @@ LIS_INT lis_b200_commtable_info(LIS_MATRIX A, LIS_INT *out, LIS_INT *import_ptr,
 /* ------------------------------------------------------------------ halo exchange
  * pack ws[i] = x[export_index[i]] (one gather kernel), then one NCCL group of sends/receives;
  * received values land in a device buffer and are copied into x[n ...].  Asynchronous on the stream. */
+/* transport without NCCL: packed entries -> pinned-less host staging -> control-plane allgatherv ->
+ * pick the segments addressed to this rank -> halo part of x.  Host-synchronous; slower than the
+ * NVLink path but independent of libnccl (and what the CPU-side multi-rank tests exercise). */
+static LIS_INT halo_exchange_staged(LIS_COMMTABLE t, LIS_INT n, double *x)
+{
+    const int np_ = t->nranks, me = t->rank;
+    cudaStream_t st = (cudaStream_t)lisd_stream();
+    size_t lens[LISC_MAXR], offs[LISC_MAXR], total = 0;
+    for (int k = 0; k < np_; k++) { lens[k] = sizeof(double) * (size_t)t->peer_n_export[k]; offs[k] = total; total += lens[k]; }
+    const size_t need = total + sizeof(double) * ((size_t)t->n_export + (size_t)t->n_import + 2);
+    if (need > t->h_stage_len) {
+        free(t->h_stage);
+        t->h_stage = (double *)malloc(need);
+        t->h_stage_len = t->h_stage ? need : 0;
+        if (!t->h_stage) { LIS_SETERR_MEM(need); return LIS_OUT_OF_MEMORY; }
+    }
+    double *all = t->h_stage, *mine = (double *)((char *)t->h_stage + total), *wr = mine + t->n_export + 1;
+    LIS_INT err;
+    if (t->n_export) {
+        lisd_mark_busy();
+        err = lisd_check(lisb200_gather(t->n_export, t->d_export_index, x, t->d_ws, st), "halo pack");
+        if (!err) err = lisd_download(mine, t->d_ws, sizeof(double) * (size_t)t->n_export);
+        if (err) return err;
+    } else {
+        err = lisd_sync();
+        if (err) return err;
+    }
+    err = shm_allgatherv(mine, all, lens, offs);
+    if (err) return err;
+    for (int k = 0; k < np_; k++) {
+        if (k == me) continue;
+        const int ni = t->import_ptr[k + 1] - t->import_ptr[k];
+        if (ni == 0) continue;
+        const double *src = (const double *)((const char *)all + offs[k]) + t->peer_export_ptr[k * (np_ + 1) + me];
+        memcpy(wr + t->import_ptr[k], src, sizeof(double) * (size_t)ni);
+    }
+    if (t->n_import) return lisd_upload(x + n, wr, sizeof(double) * (size_t)t->n_import);
+    return LIS_SUCCESS;
+}
+
 static LIS_INT halo_exchange_raw(LIS_COMMTABLE t, LIS_INT n, double *x)
 {
     if (t == NULL || g.nranks == 1) return LIS_SUCCESS;
-    if (!g.nccl_ok) { LIS_SETERR(LIS_ERR_DEVICE, "halo exchange needs NCCL (not available in this process group)\n"); return LIS_ERR_DEVICE; }
+    if (!g.nccl_ok) return halo_exchange_staged(t, n, x);
     cudaStream_t st = (cudaStream_t)lisd_stream();
     LIS_INT err;
     if (t->n_export) {

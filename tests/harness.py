@@ -28,6 +28,25 @@ def ensure_built() -> None:
             raise RuntimeError("oracle build failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
 
 
+HOSTCHECK_DIR = os.path.join(ROOT, "tests", "hostcheck", "_build")
+
+
+def ensure_hostcheck() -> str:
+    """Build (if needed) the mock-device library: the product's host C code + a CUDA/kernel mock on
+    the oracle (tests/hostcheck).  Test infrastructure; never loaded by the product."""
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostcheck")], capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("hostcheck build failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return HOSTCHECK_DIR
+
+
+def hostcheck_shim():
+    import lis_b200
+    if "hostcheck" not in _ref_cache:
+        _ref_cache["hostcheck"] = lis_b200.Shim(os.path.join(ensure_hostcheck(), "liblis_hostcheck_shim.so"))
+    return _ref_cache["hostcheck"]
+
+
 _ref_cache: dict = {}
 
 

@@ -1,0 +1,187 @@
+/*
+ * mock_device.c -- TEST INFRASTRUCTURE ONLY.  A stand-in for the GPU so that the HOST logic of
+ * lis_b200 (lis.h API, solver control flow, option handling, conversions, SSOR level schedule,
+ * process group / halo bookkeeping) can be exercised on a machine without a CUDA device:
+ *
+ *   tests/hostcheck/_build/liblis_hostcheck.so = lis_b200/csrc/host/*.c  (unchanged product host code)
+ *                                              + this file              (CUDA runtime + kernel C-ABI mocks)
+ *                                              + oracle/lis_oracle.c    (the CPU oracle does the arithmetic)
+ *
+ * It is built by tests/hostcheck/Makefile, loaded only by tests/test_hostcheck*.py, and is
+ * NOT part of the product: lis_b200/_lib/liblis_b200.so never contains or loads any of this,
+ * and still fails with LIS_ERR_DEVICE when there is no GPU.  "Device memory" here is host
+ * memory and every "kernel" runs synchronously through the oracle's sequential loops, so this
+ * build reproduces the SERIAL reference bit for bit -- which is exactly what makes it a sharp
+ * check of the host control flow against the compiled reference.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <cuda_runtime_api.h>
+#include "lis_b200_kernels.h"
+#include "../../oracle/lis_oracle.h"
+
+/* ------------------------------------------------------------------ CUDA runtime */
+cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { (void)d; return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int f) { (void)f; *s = (cudaStream_t)0x1; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void)s; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { (void)s; return cudaSuccess; }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int f) { (void)f; return cudaMalloc(p, n); }
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int f) { (void)f; return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int f) { (void)f; *d = h; return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind k, cudaStream_t st)
+{ (void)k; (void)st; memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { (void)st; memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemPrefetchAsync(const void *p, size_t n, int dev, cudaStream_t st) { (void)p; (void)n; (void)dev; (void)st; return cudaSuccess; }
+cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
+
+/* ------------------------------------------------------------------ kernel C-ABI on the oracle */
+int lisb200_sm_count(void) { return 1; }
+const char *lisb200_error_string(int code) { (void)code; return "mock device error"; }
+int lisb200_reduce_slots(void) { return 16; }
+int lisb200_spmv_csr_dot_slots(int n) { (void)n; return 16; }
+
+int lisb200_spmv_csr(int n, const int *p, const int *i, const double *v, const double *x, double *y, void *s)
+{ (void)s; if (n > 0) orc_spmv_csr(n, p, i, v, x, y); return 0; }
+int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *r, int *t, int *st)
+{ (void)n; (void)h_ptr; (void)r; (void)t; (void)st; return 1; }     /* the mock has one CSR "kernel" */
+int lisb200_spmv_csr_tma(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y, void *s)
+{ (void)r; (void)t; (void)st; return lisb200_spmv_csr(n, p, i, v, x, y, s); }
+int lisb200_spmv_csr_split(int n, const double *d, const int *lp, const int *li, const double *lv,
+                           const int *up, const int *ui, const double *uv, const double *x, double *y, void *s)
+{ (void)s; if (n > 0) orc_spmv_csr_split(n, d, lp, li, lv, up, ui, uv, x, y); return 0; }
+int lisb200_spmv_csr_dot(int n, const int *p, const int *i, const double *v, const double *x, double *y,
+                         double *partial, unsigned int *counter, double *result, void *s)
+{ (void)partial; (void)counter; lisb200_spmv_csr(n, p, i, v, x, y, s); *result = orc_dot(n, x, y, 1); return 0; }
+int lisb200_spmv_csr_tma_dot(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y,
+                             double *partial, unsigned int *counter, double *result, void *s)
+{ (void)r; (void)t; (void)st; return lisb200_spmv_csr_dot(n, p, i, v, x, y, partial, counter, result, s); }
+int lisb200_spmv_ell(int n, int m, int ld, const int *i, const double *v, const double *x, double *y, void *s)
+{
+    (void)s;
+    for (int r = 0; r < n; r++) y[r] = 0.0;
+    for (int j = 0; j < m; j++)
+        for (int r = 0; r < n; r++) y[r] += v[(size_t)j * ld + r] * x[i[(size_t)j * ld + r]];
+    return 0;
+}
+int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *off, const double *v, const double *x, double *y, void *s)
+{
+    (void)s;
+    for (int r = 0; r < n; r++) y[r] = 0.0;
+    for (int j = 0; j < nnd; j++) {
+        const int o = off[j];
+        const int rs = o < 0 ? -o : 0, re = xlen - o < n ? xlen - o : n;
+        for (int r = rs; r < re; r++) y[r] += v[(size_t)j * ld + r] * x[r + o];
+    }
+    return 0;
+}
+int lisb200_spmv_jad(int n, int m, const int *jp, const int *perm, const int *i, const double *v, const double *x, double *y, void *s)
+{ (void)s; if (n > 0) orc_spmv_jad(n, m, jp, perm, i, v, x, y, 1); return 0; }
+int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *bp, const int *bi, const double *v, const double *x, double *y, void *s)
+{
+    /* like the kernels, never read x beyond the vector: entries of a padded last block column are
+     * structural zeros, but x[...] behind them does not exist */
+    (void)s;
+    const int bs = bnr * bnc;
+    for (int b = 0; b < nr; b++) {
+        double t[64];
+        for (int i = 0; i < bnr; i++) t[i] = 0.0;
+        for (int bc = bp[b]; bc < bp[b + 1]; bc++)
+            for (int j = 0; j < bnc; j++) {
+                const int c = bi[bc] * bnc + j;
+                const double xj = c < n ? x[c] : 0.0;
+                for (int i = 0; i < bnr; i++) t[i] += v[(size_t)bc * bs + (size_t)j * bnr + i] * xj;
+            }
+        for (int i = 0; i < bnr; i++) if (b * bnr + i < n) y[b * bnr + i] = t[i];
+    }
+    return 0;
+}
+
+int lisb200_copy(int n, const double *x, double *y, void *s) { (void)s; memmove(y, x, sizeof(double) * (size_t)(n > 0 ? n : 0)); return 0; }
+int lisb200_axpy(int n, double a, const double *x, double *y, void *s) { (void)s; orc_axpy(n, a, x, y); return 0; }
+int lisb200_axpy_dev(int n, const double *da, double sc, const double *x, double *y, void *s) { (void)s; orc_axpy(n, sc * *da, x, y); return 0; }
+int lisb200_xpay(int n, const double *x, double a, double *y, void *s) { (void)s; orc_xpay(n, x, a, y); return 0; }
+int lisb200_axpyz(int n, double a, const double *x, const double *y, double *z, void *s) { (void)s; orc_axpyz(n, a, x, y, z); return 0; }
+int lisb200_scale(int n, double a, double *x, void *s) { (void)s; orc_scale(n, a, x); return 0; }
+int lisb200_pmul(int n, const double *x, const double *y, double *z, void *s) { (void)s; orc_pmul(n, x, y, z); return 0; }
+int lisb200_pdiv(int n, const double *x, const double *y, double *z, void *s) { (void)s; orc_pdiv(n, x, y, z); return 0; }
+int lisb200_set_all(int n, double a, double *x, void *s) { (void)s; for (int i = 0; i < n; i++) x[i] = a; return 0; }
+int lisb200_abs(int n, double *x, void *s) { (void)s; orc_abs(n, x); return 0; }
+int lisb200_reciprocal(int n, double *x, void *s) { (void)s; orc_reciprocal(n, x); return 0; }
+int lisb200_shift(int n, double g, double *x, void *s) { (void)s; orc_shift(n, g, x); return 0; }
+int lisb200_swap(int n, double *x, double *y, void *s) { (void)s; for (int i = 0; i < n; i++) { double t = x[i]; x[i] = y[i]; y[i] = t; } return 0; }
+int lisb200_gather(int c, const int *idx, const double *x, double *out, void *s) { (void)s; for (int i = 0; i < c; i++) out[i] = x[idx[i]]; return 0; }
+
+int lisb200_reduce(int kind, int n, const double *x, const double *y, double *partial, unsigned int *counter, double *result, void *s)
+{
+    (void)partial; (void)counter; (void)s;
+    switch (kind) {
+    case 0: *result = orc_dot(n, x, y, 1); break;
+    case 1: *result = orc_dot(n, x, x, 1); break;
+    case 2: *result = orc_nrm1(n, x, 1); break;
+    case 3: *result = orc_nrmi(n, x); break;
+    case 4: *result = orc_sum(n, x, 1); break;
+    default: return 1;
+    }
+    return 0;
+}
+int lisb200_dot2(int n, const double *a, const double *b, double *partial, unsigned int *counter, double *r2, void *s)
+{ (void)partial; (void)counter; (void)s; r2[0] = orc_dot(n, a, b, 1); r2[1] = orc_dot(n, a, a, 1); return 0; }
+int lisb200_cg_update(int n, double alpha, const double *p, const double *q, double *x, double *r,
+                      double *partial, unsigned int *counter, double *rr, void *s)
+{ (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); *rr = orc_dot(n, r, r, 1); return 0; }
+int lisb200_jacobi_dot(int n, const double *r, const double *dinv, double *z, double *partial, unsigned int *counter, double *rho, void *s)
+{ (void)partial; (void)counter; (void)s; orc_pmul(n, r, dinv, z); *rho = orc_dot(n, r, z, 1); return 0; }
+int lisb200_csr_get_diagonal(int n, const int *p, const int *i, const double *v, double *d, void *s)
+{ (void)s; if (n > 0) orc_csr_get_diagonal(n, p, i, v, d); return 0; }
+
+int lisb200_ssor_forward_level(int nrows, const int *rows, const int *lp, const int *li, const double *lv,
+                               const double *wd, const int *bs, const double *b, double *x, void *s)
+{
+    (void)s;
+    for (int k = 0; k < nrows; k++) {
+        const int i = rows[k];
+        double t = b[i];
+        for (int j = lp[i]; j < lp[i + 1]; j++) { if (li[j] < bs[i]) continue; t -= lv[j] * x[li[j]]; }
+        x[i] = t * wd[i];
+    }
+    return 0;
+}
+int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const int *ui, const double *uv,
+                                const double *wd, const int *bs, const int *be, double *x, void *s)
+{
+    (void)s;
+    for (int k = 0; k < nrows; k++) {
+        const int i = rows[k];
+        double t = 0.0;
+        for (int j = up[i]; j < up[i + 1]; j++) { if (ui[j] < bs[i] || ui[j] >= be[i]) continue; t += uv[j] * x[ui[j]]; }
+        x[i] -= t * wd[i];
+    }
+    return 0;
+}
+/* slots are in dependency (level) order, so a sequential walk is a valid schedule */
+int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *order, const int *pp, const int *pi, const double *pv,
+                                const double *wd, const int *bs, const int *be, const double *in, double *out,
+                                unsigned int *ticket, void *s)
+{
+    (void)ticket; (void)s;
+    for (int i = 0; i < n; i++) out[i] = NAN;              /* a row read before it was written would poison the result */
+    for (int k = 0; k < nslots; k++) {
+        const int i = order[k];
+        if (i < 0) continue;
+        double t = forward ? in[i] : 0.0;
+        for (int j = pp[k]; j < pp[k + 1]; j++) {
+            const int jj = pi[j];
+            if (forward ? (jj < bs[i]) : (jj < bs[i] || jj >= be[i])) continue;
+            if (forward) t -= pv[j] * out[jj]; else t += pv[j] * out[jj];
+        }
+        out[i] = forward ? t * wd[i] : in[i] - t * wd[i];
+    }
+    return 0;
+}

@@ -5,7 +5,9 @@ gathering); the library's own process group does the work being tested.
 mode cpu : host-side logic only -- row partition, global->local numbering, halo lists,
            rank-ordered host allreduce.  No GPU needed.
 mode gpu : one GPU per rank -- row-partitioned SpMV (halo exchange over NCCL) and solvers,
-           compared by rank 0 with the single-process oracle."""
+           compared by rank 0 with the single-process oracle.
+mode hostcheck : the same flow on the mock-device build (tests/hostcheck), halo staged through
+           host memory: the whole multi-rank host logic on a CPU-only machine."""
 import ctypes as C
 import os
 import sys
@@ -29,10 +31,15 @@ def main():
     if rank == 0:
         tok[0] = int.from_bytes(os.urandom(7), "little")
     dist.broadcast(tok, 0)
-    lib = lis_b200.load_library()
+    hostcheck = os.environ.get("LIS_B200_HOSTCHECK_DIR")      # mock-device build (tests/hostcheck): CPU only
+    if hostcheck:
+        shim = lis_b200.Shim(os.path.join(hostcheck, "liblis_hostcheck_shim.so"))
+        lib = C.CDLL(os.path.join(hostcheck, "liblis_hostcheck.so"))
+    else:
+        lib = lis_b200.load_library()
+        shim = lis_b200.load_shim()
     lib.lis_b200_comm_attach.argtypes = [C.c_int, C.c_int, C.c_ulonglong]
     assert lib.lis_b200_comm_attach(rank, world, int(tok[0])) == 0
-    shim = lis_b200.load_shim()
     L = shim.lib
 
     l, m, n = 3 * world + 1, 5, 4                      # planes do not divide evenly among the ranks
@@ -95,7 +102,7 @@ def main():
     lib.lis_matrix_destroy(A)
 
     result = {"rank": rank, "mode": mode}
-    if mode == "gpu":
+    if mode in ("gpu", "hostcheck"):
         L.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int]
         L.shim_mv_set_x_local.argtypes = [C.c_int, f64p]; L.shim_mv_get_y_local.argtypes = [C.c_int, f64p]
         L.shim_mv_dot_xy.argtypes = [C.c_int, C.POINTER(C.c_double)]

@@ -1,0 +1,180 @@
+"""Host control flow on a CPU-only machine.  tests/hostcheck builds the product's host C sources
+(lis.h API, solvers, preconditioner setup, conversions, SSOR level schedule, process group)
+against a mock device whose "kernels" are the oracle's sequential loops.  That build must
+reproduce the SERIAL compiled reference bit for bit: iteration counts, full-precision residual
+histories, solutions.  (The real kernels are checked on the GPU by test_gpu_parity.py; this
+file is about everything around them.)"""
+import numpy as np
+import pytest
+
+import harness as H
+
+FORMATS = ["csr", "csc", "ell", "dia", "jad", "bsr"]
+
+
+@pytest.fixture(scope="module")
+def hc(built):
+    return H.hostcheck_shim()
+
+
+def systems():
+    ptr, idx, val = H.poisson3d_7pt(9, 8, 7)
+    yield "poisson7", (ptr, idx, val)
+    yield "unsym", H.random_csr(600, 6, 41, band=30)
+
+
+SOLVES = ["-i cg", "-i cg -p jacobi", "-i cg -p ssor", "-i cg -p ssor -ssor_omega 1.3", "-i bicgstab", "-i bicgstab -p jacobi",
+          "-i bicgstab -p ssor", "-i gmres -restart 7", "-i gmres -p jacobi", "-i gmres -restart 12 -p ssor",
+          "-i gmres -restart 3 -p jacobi -maxiter 40", "-i cg -p jacobi -conv_cond nrm2_b", "-i bicgstab -p jacobi -conv_cond nrm1_b",
+          "-i cg -p jacobi -tol 1e-6", "-i bicgstab -maxiter 5", "-i cg -initx_zeros false -p jacobi"]
+
+
+@pytest.mark.parametrize("opts", SOLVES)
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_solver_control_flow_bit_for_bit(hc, ref_serial, opts, fuse, monkeypatch):
+    monkeypatch.setenv("LIS_B200_FUSE", fuse)
+    for name, (ptr, idx, val) in systems():
+        if "-i cg" in opts and name == "unsym":
+            continue
+        n = len(ptr) - 1
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))
+        x0 = H.rand_vec(n, 7) if "initx_zeros false" in opts else None
+        g = hc.solve(ptr, idx, val, b, opts, x0=x0)
+        r = ref_serial.solve(ptr, idx, val, b, opts, x0=x0)
+        assert (g["err"], g["status"], g["iter"]) == (r["err"], r["status"], r["iter"]), (name, opts, g["iter"], r["iter"])
+        H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{name} {opts} residual history")
+        H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} solution")
+        assert np.float64(g["resid"]).view(np.uint64) == np.float64(r["resid"]).view(np.uint64)
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_solve_in_every_storage_format(hc, ref_serial, fmt):
+    """-storage converts the matrix in place before the solve (lis_matrix_convert_self); the matrix
+    may also arrive already converted (test3.c's matrix_type argument)"""
+    ptr, idx, val = H.poisson3d_7pt(8, 7, 6)
+    n = len(ptr) - 1
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))
+    for opts, kw in ((f"-i cg -p jacobi -storage {fmt}", {}), ("-i bicgstab -p jacobi", {"fmt": fmt})):
+        g = hc.solve(ptr, idx, val, b, opts, **kw)
+        r = ref_serial.solve(ptr, idx, val, b, opts, **kw)
+        assert (g["status"], g["iter"]) == (r["status"], r["iter"]), (fmt, opts)
+        H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{fmt} {opts}")
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_matvec_dispatch_and_layouts(hc, ref_serial, fmt):
+    for name, (ptr, idx, val) in systems():
+        if fmt == "dia" and name == "unsym":
+            continue
+        x = H.rand_vec(len(ptr) - 1, 3, "wide")
+        y, _ = hc.spmv(fmt, ptr, idx, val, x, bnr=3, bnc=2)
+        yr, _ = ref_serial.spmv(fmt, ptr, idx, val, x, bnr=3, bnc=2)
+        H.assert_bits_equal(y, yr, f"{fmt}/{name}")
+    ptr, idx, val = H.poisson3d_7pt(5, 6, 7)
+    x = H.rand_vec(len(ptr) - 1, 4)
+    H.assert_bits_equal(hc.spmv("csr", ptr, idx, val, x, split=True)[0], ref_serial.spmv("csr", ptr, idx, val, x, split=True)[0], "split")
+
+
+@pytest.mark.parametrize("mode", ["syncfree", "levels"])
+@pytest.mark.parametrize("blocks", [1, 2, 5, 16])
+def test_ssor_schedule(hc, oracle, mode, blocks, monkeypatch):
+    """the level schedule, its padded level-ordered permutation of L and U and the per-row block
+    bounds are host code: any slip shows up as a wrong sweep"""
+    monkeypatch.setenv("LIS_B200_SSOR", mode)
+    hc.set_threads(blocks)
+    try:
+        for name, (ptr, idx, val) in list(systems()) + [("poisson1d", H.poisson1d(77)), ("p27", H.poisson3d_27pt(5, 4, 6))]:
+            b = H.rand_vec(len(ptr) - 1, 9, "wide")
+            for omega in (1.0, 1.2):
+                H.assert_bits_equal(hc.psolve(ptr, idx, val, b, f"-p ssor -ssor_omega {omega}"),
+                                    oracle.psolve(ptr, idx, val, b, "ssor", omega=omega, nthreads=blocks), f"{name}/{mode}/T={blocks}")
+    finally:
+        hc.set_threads(1)
+
+
+def test_ssor_blocks_match_openmp_reference(hc, ref_omp):
+    """-omp_num_threads N / lis_b200_set_num_threads(N) == the OpenMP reference's block-SSOR (the dot
+    order of the mock stays serial, so only the preconditioner is compared)"""
+    ptr, idx, val = H.poisson3d_7pt(8, 8, 8)
+    b = H.rand_vec(len(ptr) - 1, 5)
+    for t in (2, 4):
+        hc.set_threads(t); ref_omp.set_threads(t)
+        try:
+            H.assert_bits_equal(hc.psolve(ptr, idx, val, b, "-p ssor"), ref_omp.psolve(ptr, idx, val, b, "-p ssor"), f"T={t}")
+        finally:
+            hc.set_threads(1)
+
+
+def test_repeated_solves_and_preconditioner_switch(hc, ref_serial):
+    """A is split in place by the SSOR setup and stays split (the next Jacobi solve takes its diagonal
+    from D and its products in D,L,U order), exactly like the reference"""
+    import ctypes as C
+    ptr, idx, val = H.poisson3d_7pt(7, 7, 7)
+    n = len(ptr) - 1
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))
+    for shim in (hc, ref_serial):
+        L = shim.lib
+        i32p = np.ctypeslib.ndpointer(np.int32, flags="C"); f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+        L.shim_mv_open.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int, C.c_int, C.c_int]
+        L.shim_mv_solve_b.argtypes = [C.c_int, C.c_char_p, f64p, f64p, i32p, f64p, f64p, C.c_int]
+    out = {}
+    for tag, shim in (("hc", hc), ("ref", ref_serial)):
+        h = shim.lib.shim_mv_open(1, n, ptr, idx, val, 0, 0, 0)
+        assert h >= 0
+        res = []
+        for opts in ("-i cg -p ssor", "-i cg -p jacobi", "-i bicgstab -p ssor -ssor_omega 1.2", "-i gmres -restart 5"):
+            x = np.zeros(n); oi = np.zeros(4, np.int32); od = np.zeros(4); rh = np.zeros(4000)
+            rc = shim.lib.shim_mv_solve_b(h, opts.encode(), b, x, oi, od, rh, 4000)
+            assert rc == 0 and oi[1] == 0, (tag, opts, rc, oi)
+            res.append((int(oi[0]), rh[:oi[3]].copy(), x.copy()))
+        shim.lib.shim_mv_close(h)
+        out[tag] = res
+    for (ia, ha, xa), (ib, hb, xb) in zip(out["hc"], out["ref"]):
+        assert ia == ib
+        H.assert_bits_equal(ha, hb, "history across repeated solves")
+        H.assert_bits_equal(xa, xb, "solution across repeated solves")
+
+
+def test_unsupported_requests_are_rejected(hc):
+    ptr, idx, val = H.poisson1d(30)
+    b = np.ones(30)
+    for opts, code in (("-i bicg", 5), ("-i cgs", 5), ("-i cg -p ilu", 5), ("-i cg -p jacobi -adds true", 5),
+                       ("-i cg -scale jacobi", 5), ("-i cg -f quad", 1), ("-i gmres -conv_cond nrm2_b", 1),
+                       ("-i gmres -restart -1", 1), ("-i cg -maxiter -3", 1)):
+        g = hc.solve(ptr, idx, val, b, opts)
+        assert g["err"] == code, (opts, g["err"])
+    with pytest.raises(RuntimeError):
+        hc.convert(3, ptr, idx, val)                   # MSR: no kernel, conversion refuses
+
+
+def test_registered_preconditioner_plugin(hc):
+    """lis_precon_register: the reference's plugin API (src/precon/lis_precon.c:410)"""
+    import ctypes as C
+    lib = C.CDLL(hc.path.replace("_shim", ""))
+    CREATE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+    PSOLVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+    calls = {"create": 0, "psolve": 0}
+    lib.lis_vector_copy.argtypes = [C.c_void_p, C.c_void_p]
+
+    def create(solver, precon):
+        calls["create"] += 1
+        return 0
+
+    def psolve(solver, b, x):                          # identity preconditioner written against lis.h
+        calls["psolve"] += 1
+        return lib.lis_vector_copy(b, x)
+
+    c_create, c_psolve = CREATE(create), PSOLVE(psolve)
+    lib.lis_precon_register.argtypes = [C.c_char_p, CREATE, PSOLVE, PSOLVE]
+    assert lib.lis_precon_register(b"myident", c_create, c_psolve, c_psolve) == 0
+    try:
+        ptr, idx, val = H.poisson3d_7pt(6, 6, 6)
+        n = len(ptr) - 1
+        b = np.ones(n)
+        g = hc.solve(ptr, idx, val, b, "-i cg -p myident")
+        plain = hc.solve(ptr, idx, val, b, "-i cg -p none")
+        assert g["err"] == 0 and g["status"] == 0 and calls["create"] == 1 and calls["psolve"] == g["iter"]
+        assert g["iter"] == plain["iter"]
+        H.assert_bits_equal(g["rhistory"], plain["rhistory"], "registered identity == none")
+    finally:
+        lib.lis_precon_register_free()

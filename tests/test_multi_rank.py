@@ -17,12 +17,13 @@ def free_port():
     return p
 
 
-def launch(world, mode, timeout=300):
+def launch(world, mode, timeout=300, extra_env=None):
     port = free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), GLOO_SOCKET_IFNAME="lo")
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mr_worker.py"), mode], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -43,6 +44,15 @@ def launch(world, mode, timeout=300):
 @pytest.mark.parametrize("world", [2, 3])
 def test_partition_and_halo_lists_cpu(built, world):
     launch(world, "cpu")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_partitioned_spmv_and_solvers_hostcheck(built, world):
+    """the complete multi-rank flow -- assemble, halo exchange (host-staged transport), SpMV in four
+    formats, CG / BiCGSTAB / GMRES / block-SSOR -- on the mock-device build, CPU only"""
+    import harness
+    d = harness.ensure_hostcheck()
+    launch(world, "hostcheck", timeout=600, extra_env={"LIS_B200_HOSTCHECK_DIR": d, "LIS_B200_TRANSPORT": "host"})
 
 
 @pytest.mark.gpu
