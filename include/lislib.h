@@ -67,6 +67,7 @@ LIS_INT lis_matrix_diag_destroy(LIS_MATRIX_DIAG D);
 LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon);
 LIS_INT lis_precon_destroy(LIS_PRECON precon);
 LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
+LIS_INT lis_psolveh(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
 LIS_INT lis_psolve_none(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
 LIS_INT lis_psolve_jacobi(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
 LIS_INT lis_psolve_ssor(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);

@@ -76,6 +76,9 @@ typedef struct lisd_matrix {
     double *diag;             /* D */
     double *wd;               /* WD (scaled + inverted diagonal), when present */
     void *sweep;              /* SSOR level schedule (lis_precon.c), built on first psolve */
+    /* transposed mirrors for lis_matvech (BiCG), built on first use */
+    int has_t;
+    lisd_csr csrT, LT, UT;
 } lisd_matrix;
 
 LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out);   /* build on first use */
@@ -92,6 +95,7 @@ LIS_INT lisd_set_all(LIS_SCALAR alpha, LIS_VECTOR x);
 LIS_INT lisd_pmul(LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR z);
 LIS_INT lisd_reduce(int kind, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *value);  /* syncs, allreduces */
 LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);                 /* async */
+LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);                /* y = A^H x, async */
 void    lisd_sweep_free(void *sweep);
 
 /* ---- fused steps of the Krylov loops: one launch, one host wait, scalar(s) returned ---- */

@@ -333,10 +333,66 @@ fail:
 #undef GCHK
 }
 
-/* BiCG needs the transposed product (lis_matvech), SURVEY.md section 8(f).1 */
+/* ================================================================== BiCG
+ * src/solver/lis_solver_bicg.c:137-290 -- the reference's DEFAULT solver (test1 testmat.mtx 0, the
+ * `make check` case).  First row of SURVEY.md section 8(f): same kernels plus the transposed product.
+ * q aliases z and qtld aliases ztld (work[2], work[3]) as in the reference. */
 LIS_INT lis_bicg(LIS_SOLVER solver)
 {
-    (void)solver;
-    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "BiCG (needs lis_matvech) is outside the B200 hot path\n");
-    return LIS_ERR_NOT_IMPLEMENTED;
+    LIS_MATRIX A = solver->A;
+    LIS_VECTOR x = solver->x;
+    LIS_VECTOR r = solver->work[0], rtld = solver->work[1], z = solver->work[2], ztld = solver->work[3];
+    LIS_VECTOR p = solver->work[4], ptld = solver->work[5], q = solver->work[2], qtld = solver->work[3];
+    const LIS_INT maxiter = solver->options[LIS_OPTIONS_MAXITER];
+    const LIS_INT output = solver->options[LIS_OPTIONS_OUTPUT];
+    LIS_SCALAR alpha, beta, rho, rho_old = 1.0, tmpdot1;
+    LIS_REAL bnrm2, nrm2 = 0.0, tol;
+    LIS_INT iter;
+    double time, ptime = 0.0;
+
+    {
+        LIS_INT e = lis_solver_get_initial_residual(solver, NULL, NULL, r, &bnrm2);
+        if (e == LIS_FAILS) return LIS_SUCCESS;
+        if (e) return e;
+    }
+    tol = solver->tol;
+    CHK(lis_host_solver_shadow_residual(solver, r, rtld));
+    CHK(lisd_set_all(0.0, p));
+    CHK(lisd_set_all(0.0, ptld));
+
+    for (iter = 1; iter <= maxiter; iter++) {
+        /* z = M^-1 r ; ztld = M^-H rtld */
+        time = lis_wtime();
+        CHK(lis_psolve(solver, r, z));
+        CHK(lis_psolveh(solver, rtld, ztld));
+        ptime += lis_wtime() - time;
+        CHK(lis_vector_dot(rtld, z, &rho));
+        if (rho == 0.0) {
+            solver->retcode = LIS_BREAKDOWN; solver->iter = iter; solver->resid = nrm2;
+            return LIS_BREAKDOWN;
+        }
+        beta = rho / rho_old;
+        CHK(lisd_xpay(z, beta, p));              /* p    = z    + beta*p    */
+        CHK(lisd_matvec(A, p, q));               /* q    = A p               */
+        CHK(lisd_xpay(ztld, beta, ptld));        /* ptld = ztld + beta*ptld */
+        CHK(lisd_matvech(A, ptld, qtld));        /* qtld = A^H ptld          */
+        CHK(lis_vector_dot(ptld, q, &tmpdot1));
+        if (tmpdot1 == 0.0) {
+            solver->retcode = LIS_BREAKDOWN; solver->iter = iter; solver->resid = nrm2;
+            return LIS_BREAKDOWN;
+        }
+        alpha = rho / tmpdot1;
+        CHK(lisd_axpy(alpha, p, x));
+        CHK(lisd_axpy(-alpha, q, r));
+        CHK(lis_host_solver_residual(solver, r, &nrm2));
+        record(solver, output, iter, nrm2);
+        if (tol >= nrm2) {
+            solver->retcode = LIS_SUCCESS; solver->iter = iter; solver->resid = nrm2; solver->ptime = ptime;
+            return LIS_SUCCESS;
+        }
+        CHK(lisd_axpy(-alpha, qtld, rtld));      /* rtld -= conj(alpha) qtld */
+        rho_old = rho;
+    }
+    solver->retcode = LIS_MAXITER; solver->iter = iter; solver->resid = nrm2;
+    return LIS_MAXITER;
 }

@@ -64,6 +64,7 @@ static void mirror_free(lisd_matrix *M)
 {
     if (M == NULL) return;
     csr_free(&M->csr); csr_free(&M->L); csr_free(&M->U);
+    csr_free(&M->csrT); csr_free(&M->LT); csr_free(&M->UT);
     lisd_free(M->idx); lisd_free(M->off); lisd_free(M->jptr); lisd_free(M->perm);
     lisd_free(M->bptr); lisd_free(M->bidx); lisd_free(M->val);
     lisd_free(M->diag); lisd_free(M->wd);
@@ -285,13 +286,79 @@ LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     return lisd_sync();
 }
 
-/* transposed product: only what BiCG needs, served by a transposed CSR mirror is future
- * work */
+/* ------------------------------------------------------------------ y = A^H x
+ * The reference's serial lis_matvech_csr (src/matvec/lis_matvec_csr.c:113-260) is a scatter,
+ * y[idx[j]] += val[j]*x[i] over rows i ascending: for every output entry the products arrive in
+ * ascending row order.  A counting transpose keeps exactly that order inside each row of A^T,
+ * so A^T in CSR through the ordinary (gather) CSR kernels adds the same products in the same
+ * order.  Split matrices: y = D x, then all of L's contributions, then all of U's (:170-199) ==
+ * the split kernel on (D, L^T, U^T).  CSC storage already is the CSR of A^T. */
+static LIS_INT transposed_upload(lisd_csr *dst, LIS_INT n, const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
+{
+    LIS_INT *tp, *ti;
+    LIS_SCALAR *tv;
+    LIS_INT err = lis_host_transpose(n, n, ptr, idx, val, &tp, &ti, &tv);
+    if (err) return err;
+    err = csr_upload(dst, (int)n, tp, ti, tv);
+    lis_free2(3, tp, ti, tv);
+    return err;
+}
+
+LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
+{
+    LIS_INT err = lisd_require("lis_matvech");
+    if (err) return err;
+    if (A->nprocs > 1) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech is single-process only (the reverse halo reduction is outside the hot path)\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    if (x == y || x->value == y->value) { LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvech: x and y must not alias\n"); return LIS_ERR_ILL_ARG; }
+    if (A->matrix_type != LIS_MATRIX_CSR && A->matrix_type != LIS_MATRIX_CSC) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech: CSR and CSC only (convert with -storage csr)\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    lisd_matrix *M;
+    err = lisd_matrix_get(A, &M);
+    if (err) return err;
+    const int n = A->n;
+    if (!M->has_t) {
+        if (M->splited) {
+            err = transposed_upload(&M->LT, n, A->L->ptr, A->L->index, A->L->value);
+            if (!err) err = transposed_upload(&M->UT, n, A->U->ptr, A->U->index, A->U->value);
+        } else if (A->matrix_type == LIS_MATRIX_CSR) {
+            err = transposed_upload(&M->csrT, n, A->ptr, A->index, A->value);
+        } else {
+            err = csr_upload(&M->csrT, n, A->ptr, A->index, A->value);       /* CSC arrays == CSR of A^T */
+        }
+        if (err) return err;
+        M->has_t = 1;
+    }
+    err = lisd_vec_device(x);
+    if (!err) err = lisd_vec_device(y);
+    if (err) return err;
+    void *st = lisd_stream();
+    int rc;
+    if (M->splited)
+        rc = lisb200_spmv_csr_split(n, M->diag, M->LT.ptr, M->LT.idx, M->LT.val, M->UT.ptr, M->UT.idx, M->UT.val, x->value, y->value, st);
+    else if (M->csrT.tma_rows)
+        rc = lisb200_spmv_csr_tma(n, M->csrT.tma_rows, M->csrT.tma_tile, M->csrT.tma_stages, M->csrT.ptr, M->csrT.idx, M->csrT.val, x->value, y->value, st);
+    else
+        rc = lisb200_spmv_csr(n, M->csrT.ptr, M->csrT.idx, M->csrT.val, x->value, y->value, st);
+    lisd_mark_busy();
+    return lisd_check(rc, "lis_matvech");
+}
+
 LIS_INT lis_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
 {
-    (void)A; (void)x; (void)y;
-    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech (transposed SpMV) is outside the B200 hot path\n");
-    return LIS_ERR_NOT_IMPLEMENTED;
+    LIS_INT err = lis_host_matrix_check_input(A);
+    if (err) return err;
+    if (A->n != x->n || A->n != y->n) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvech: sizes of A, x and y do not match\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    err = lisd_matvech(A, x, y);
+    if (err) return err;
+    return lisd_sync();
 }
 
 /* ---- per-format seam with raw pointers (include/lis_matvec.h:76-205 of the reference).

@@ -191,6 +191,23 @@ LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
     }
 }
 
+/* M^-H b for BiCG: none and Jacobi are self-adjoint for real scalars (lis_precon_jacobi.c
+ * lis_psolveh_jacobi: x = b*conj(d)); the transposed SSOR sweep (lis_matrix_solveh) is not part
+ * of the hot path */
+LIS_INT lis_psolveh(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    const LIS_INT type = solver->precon->precon_type;
+    switch (type) {
+    case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
+    case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
+    default:
+        if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg && g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh)
+            return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh(solver, b, x);
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "the transposed preconditioner solve (BiCG) is available for none and jacobi only\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+}
+
 /* ------------------------------------------------------------------ SSOR level schedule */
 typedef struct lisd_perm {        /* one direction of the one-launch sweep */
     int nslots;                   /* levels concatenated, each padded to a multiple of 32 */

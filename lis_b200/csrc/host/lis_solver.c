@@ -391,6 +391,7 @@ typedef LIS_INT (*lis_solver_fn)(LIS_SOLVER);
 
 static LIS_INT work_cg(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 4, 0); }
 static LIS_INT work_bicgstab(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 7, 0); }
+static LIS_INT work_bicg(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 6, 0); }
 /* work[0] of the reference is the (restart+1)-vector s of the least-squares problem; here
  * that short vector is a host array owned by lis_gmres, so slot 0 stays empty */
 static LIS_INT work_gmres(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 4 + s->options[LIS_OPTIONS_RESTART] + 1, 1); }
@@ -412,6 +413,7 @@ static lis_solver_entry solver_entry(LIS_INT nsolver)
     lis_solver_entry e = {NULL, NULL, NULL, 0};
     switch (nsolver) {
     case LIS_SOLVER_CG: e.check = check_none; e.work = work_cg; e.run = lis_cg; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_BICG: e.check = check_none; e.work = work_bicg; e.run = lis_bicg; e.conv_cond_ok = 1; break;
     case LIS_SOLVER_BICGSTAB: e.check = check_none; e.work = work_bicgstab; e.run = lis_bicgstab; e.conv_cond_ok = 1; break;
     case LIS_SOLVER_GMRES: e.check = check_gmres; e.work = work_gmres; e.run = lis_gmres; e.conv_cond_ok = 0; break;
     default: break;
@@ -469,7 +471,7 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     }
     lis_solver_entry entry = solver_entry(nsolver);
     if (entry.run == NULL) {
-        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "solver %s is outside the B200 hot path (cg, bicgstab and gmres are available)\n", k_solvername[nsolver]);
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "solver %s is outside the B200 hot path (cg, bicg, bicgstab and gmres are available)\n", k_solvername[nsolver]);
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (precon_type < 0 || precon_type >= lis_host_precon_type_end()) {

@@ -61,6 +61,22 @@ def main():
         print(tag, r["iter"], r["resid"])
     np.savez_compressed(os.path.join(HERE, "solve_unsym_1500.npz"), **out)
 
+    # BiCG (default solver): reference outputs for the GPU box
+    out = {}
+    for key, (ptr, idx, val) in {"p7": H.poisson3d_7pt(10, 9, 8), "unsym": H.random_csr(900, 6, 303, band=40)}.items():
+        n = len(ptr) - 1
+        b, _ = ref.spmv("csr", ptr, idx, val, np.ones(n))
+        out[f"ptr_{key}"], out[f"idx_{key}"], out[f"val_{key}"], out[f"b_{key}"] = ptr, idx, val, b
+        for pre in ("none", "jacobi"):
+            opts = f"-i bicg -p {pre}"
+            r = ref.solve(ptr, idx, val, b, opts)
+            assert r["status"] == 0
+            tag = f"{key}_{pre}"
+            out[f"iter_{tag}"] = np.array(r["iter"]); out[f"opts_{tag}"] = np.array(opts)
+            out[f"rhist_{tag}"] = r["rhistory"]; out[f"x_{tag}"] = r["x"]
+            print("bicg", tag, r["iter"], r["resid"])
+    np.savez_compressed(os.path.join(HERE, "solve_bicg.npz"), **out)
+
 
 if __name__ == "__main__":
     main()

@@ -186,6 +186,23 @@ EXPORT int shim_spmv(int fmt, int n, const int *ptr, const int *idx, const doubl
     return 0;
 }
 
+/* y = A^H x (lis_matvech), optionally on the split matrix */
+EXPORT int shim_matvech(int fmt, int n, const int *ptr, const int *idx, const double *val, int split, const double *x, double *y)
+{
+    LIS_MATRIX A0 = NULL, A = NULL;
+    LIS_VECTOR vx = NULL, vy = NULL;
+    LIS_INT err;
+    err = make_csr(n, ptr, idx, val, 0, &A0); if (err) return (int)err;
+    err = convert_to(A0, fmt, 0, 0, &A); if (err) return (int)err;
+    if (split) { err = lis_matrix_split(A); if (err) return (int)err; }
+    err = make_vec(A, x, &vx); if (err) return (int)err;
+    err = make_vec(A, NULL, &vy); if (err) return (int)err;
+    err = lis_matvech(A, vx, vy); if (err) return (int)err;
+    err = lis_vector_gather(vy, y); if (err) return (int)err;
+    lis_vector_destroy(vx); lis_vector_destroy(vy); lis_matrix_destroy(A); lis_matrix_destroy(A0);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ converted layouts */
 static LIS_MATRIX g_conv[16];
 static LIS_MATRIX g_conv0[16];
