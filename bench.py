@@ -318,6 +318,7 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
 # ----------------------------------------------------------------------------- lis_b200 arm
 def time_launches(torch, stream, fn, steps, warmup):
     """CUDA events on the launching stream around `steps` back-to-back launches."""
+    torch.cuda.synchronize()                 # inputs were produced by torch on its own stream
     with torch.cuda.stream(stream):
         for _ in range(warmup):
             fn()
