@@ -77,6 +77,27 @@ LIS_INT lis_cg(LIS_SOLVER solver);
 LIS_INT lis_bicg(LIS_SOLVER solver);
 LIS_INT lis_bicgstab(LIS_SOLVER solver);
 LIS_INT lis_gmres(LIS_SOLVER solver);
+LIS_INT lis_cgs(LIS_SOLVER solver);
+LIS_INT lis_crs(LIS_SOLVER solver);
+LIS_INT lis_cr(LIS_SOLVER solver);
+LIS_INT lis_cocg(LIS_SOLVER solver);
+LIS_INT lis_cocr(LIS_SOLVER solver);
+LIS_INT lis_bicr(LIS_SOLVER solver);
+LIS_INT lis_bicrstab(LIS_SOLVER solver);
+LIS_INT lis_idrs(LIS_SOLVER solver);
+LIS_INT lis_idr1(LIS_SOLVER solver);
+LIS_INT lis_jacobi(LIS_SOLVER solver);
+LIS_INT lis_gs(LIS_SOLVER solver);
+LIS_INT lis_sor(LIS_SOLVER solver);
+LIS_INT lis_bicgstabl(LIS_SOLVER solver);
+LIS_INT lis_orthomin(LIS_SOLVER solver);
+LIS_INT lis_minres(LIS_SOLVER solver);
+LIS_INT lis_fgmres(LIS_SOLVER solver);
+LIS_INT lis_tfqmr(LIS_SOLVER solver);
+LIS_INT lis_gpbicg(LIS_SOLVER solver);
+LIS_INT lis_gpbicr(LIS_SOLVER solver);
+LIS_INT lis_bicgsafe(LIS_SOLVER solver);
+LIS_INT lis_bicrsafe(LIS_SOLVER solver);
 LIS_INT lis_solver_get_initial_residual(LIS_SOLVER solver, LIS_PRECON M, LIS_VECTOR t, LIS_VECTOR r, LIS_REAL *bnrm2);
 LIS_INT lis_solver_work_destroy(LIS_SOLVER solver);
 LIS_INT lis_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);

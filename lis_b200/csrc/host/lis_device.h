@@ -76,6 +76,7 @@ typedef struct lisd_matrix {
     double *diag;             /* D */
     double *wd;               /* WD (scaled + inverted diagonal), when present */
     void *sweep;              /* SSOR level schedule (lis_precon.c), built on first psolve */
+    void *sweep_global;       /* one-block schedule for LIS_MATRIX_LOWER when `sweep` is blocked */
     /* transposed mirrors for lis_matvech (BiCG), built on first use */
     int has_t;
     lisd_csr csrT, LT, UT;

@@ -34,7 +34,10 @@ LIS_INT lis_host_precon_lookup(const char *name);
 void    lis_host_print_rhistory(LIS_INT iter, LIS_REAL resid);
 LIS_INT lis_host_solver_malloc_work(LIS_SOLVER solver, LIS_INT worklen, LIS_INT first);
 LIS_INT lis_host_solver_residual(LIS_SOLVER solver, LIS_VECTOR r, LIS_REAL *res);
+LIS_INT lis_host_fill_mt19937(LIS_INT s, LIS_INT n, LIS_VECTOR *P);
 LIS_INT lis_host_solver_shadow_residual(LIS_SOLVER solver, LIS_VECTOR r0, LIS_VECTOR rs0);
+
+LIS_INT lis_host_set_wd(LIS_MATRIX A, LIS_SCALAR scale, int do_scale, LIS_INT tag);
 
 /* vectors */
 LIS_INT lis_vector_check_same(LIS_VECTOR x, LIS_VECTOR y);

@@ -69,6 +69,7 @@ static void mirror_free(lisd_matrix *M)
     lisd_free(M->bptr); lisd_free(M->bidx); lisd_free(M->val);
     lisd_free(M->diag); lisd_free(M->wd);
     if (M->sweep) lisd_sweep_free(M->sweep);
+    if (M->sweep_global) lisd_sweep_free(M->sweep_global);
     free(M);
 }
 

@@ -72,6 +72,25 @@ LIS_INT lis_precon_register_free(void)
 
 LIS_INT lis_host_ssor_prepare(LIS_MATRIX A);
 
+/* WD = 1/(scale*D), remembered under `tag` (A->use_wd) like the reference does
+ * (lis_precon_ssor.c:79-90, lis_solver_gs.c, lis_solver_sor.c) */
+LIS_INT lis_host_set_wd(LIS_MATRIX A, LIS_SCALAR scale, int do_scale, LIS_INT tag)
+{
+    LIS_INT err;
+    if (A->use_wd == tag) return LIS_SUCCESS;
+    if (!A->WD) {
+        err = lis_host_diag_create(A, &A->WD);
+        if (err) return err;
+    }
+    for (LIS_INT i = 0; i < A->n; i++) {
+        LIS_SCALAR v = A->D->value[i];
+        if (do_scale) v = scale * v;
+        A->WD->value[i] = 1.0 / v;
+    }
+    A->use_wd = tag;
+    return lisd_matrix_refresh_wd(A);
+}
+
 /* ------------------------------------------------------------------ create / destroy */
 static LIS_INT create_none(LIS_SOLVER solver, LIS_PRECON precon) { (void)solver; (void)precon; return LIS_SUCCESS; }
 
@@ -95,20 +114,8 @@ static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
     if (err) return err;
     err = lis_matrix_split(A);
     if (err) return err;
-    if (A->use_wd != LIS_SOLVER_SOR) {
-        if (!A->WD) {
-            err = lis_host_diag_create(A, &A->WD);
-            if (err) return err;
-        }
-        for (LIS_INT i = 0; i < A->n; i++) {
-            LIS_SCALAR v = A->D->value[i];
-            v = w * v;
-            A->WD->value[i] = 1.0 / v;
-        }
-        A->use_wd = LIS_SOLVER_SOR;
-        err = lisd_matrix_refresh_wd(A);
-        if (err) return err;
-    }
+    err = lis_host_set_wd(A, w, 1, LIS_SOLVER_SOR);
+    if (err) return err;
     precon->A = A;
     precon->is_copy = LIS_FALSE;
     return lis_host_ssor_prepare(A);      /* upload D/L/U and build the level schedule now, not in the first sweep */
@@ -312,10 +319,9 @@ static int sweep_blocks(int n)
     return nb;
 }
 
-static LIS_INT sweep_build(LIS_MATRIX A, lisd_sweep **out)
+static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
 {
     const int n = A->n;
-    const int nb = sweep_blocks(n);
     lisd_sweep *S = (lisd_sweep *)calloc(1, sizeof(lisd_sweep));
     int *bs = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     int *be = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
@@ -395,11 +401,28 @@ static LIS_INT sweep_prepare(LIS_MATRIX A, lisd_matrix **Mout, lisd_sweep **Sout
     if (M->sweep == NULL || ((lisd_sweep *)M->sweep)->nblocks != sweep_blocks(A->n)) {
         lisd_sweep *S;
         if (M->sweep) { lisd_sweep_free(M->sweep); M->sweep = NULL; }
-        err = sweep_build(A, &S);
+        err = sweep_build(A, sweep_blocks(A->n), &S);
         if (err) return err;
         M->sweep = S;
     }
     *Mout = M; *Sout = (lisd_sweep *)M->sweep;
+    return LIS_SUCCESS;
+}
+
+/* the plain triangular solve (LIS_MATRIX_LOWER) is one global sweep whatever the thread count
+ * (src/matrix/lis_matrix_csr.c:1553-1562): its own single-block schedule when the SSOR one is blocked */
+static LIS_INT sweep_prepare_global(LIS_MATRIX A, lisd_matrix **Mout, lisd_sweep **Sout)
+{
+    LIS_INT err = sweep_prepare(A, Mout, Sout);
+    if (err || (*Sout)->nblocks == 1) return err;
+    lisd_matrix *M = *Mout;
+    if (M->sweep_global == NULL) {
+        lisd_sweep *S;
+        err = sweep_build(A, 1, &S);
+        if (err) return err;
+        M->sweep_global = S;
+    }
+    *Sout = (lisd_sweep *)M->sweep_global;
     return LIS_SUCCESS;
 }
 
@@ -415,8 +438,8 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
 {
     LIS_INT err = lisd_require("lis_matrix_solve");
     if (err) return err;
-    if (flag != LIS_MATRIX_SSOR) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_solve: only the SSOR sweep is part of the B200 hot path\n");
+    if (flag != LIS_MATRIX_SSOR && flag != LIS_MATRIX_LOWER) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_solve: the SSOR sweep and the lower triangular solve are available\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (!A->is_splited) { err = lis_matrix_split(A); if (err) return err; }
@@ -426,6 +449,19 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
     }
     lisd_matrix *M;
     lisd_sweep *S;
+    if (flag == LIS_MATRIX_LOWER) {
+        /* x[i] = (b[i] - sum_L L*x[jj]) * WD[i]: the forward sweep alone, written straight into x */
+        if (b == x || b->value == x->value) { LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matrix_solve: b and x must not alias\n"); return LIS_ERR_ILL_ARG; }
+        err = sweep_prepare_global(A, &M, &S);
+        if (err) return err;
+        err = lisd_vec_device(b);
+        if (!err) err = lisd_vec_device(x);
+        if (err) return err;
+        lisd_mark_busy();
+        return lisd_check(lisb200_ssor_sweep_syncfree(1, S->n, S->pf.nslots, S->pf.d_order, S->pf.d_pptr, S->pf.d_pidx, S->pf.d_pval,
+                                                      M->wd, S->d_blk_start, S->d_blk_end, b->value, x->value,
+                                                      S->d_ticket, lisd_stream()), "lower triangular solve");
+    }
     err = sweep_prepare(A, &M, &S);
     if (err) return err;
     err = lisd_vec_device(b);

@@ -328,10 +328,7 @@ LIS_INT lis_host_solver_residual(LIS_SOLVER solver, LIS_VECTOR r, LIS_REAL *res)
 /* rs0 = conj(r0) (default) or MT19937 uniforms: src/solver/lis_solver.c:1817-1875 */
 LIS_INT lis_host_solver_shadow_residual(LIS_SOLVER solver, LIS_VECTOR r0, LIS_VECTOR rs0)
 {
-    if (solver->options[LIS_OPTIONS_INIT_SHADOW_RESID] == LIS_RANDOM) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "random shadow residual is not part of the B200 hot path\n");
-        return LIS_ERR_NOT_IMPLEMENTED;
-    }
+    if (solver->options[LIS_OPTIONS_INIT_SHADOW_RESID] == LIS_RANDOM) return lis_host_fill_mt19937(1, solver->A->n, &rs0);
     return lisd_copy(r0, rs0);
 }
 
@@ -392,10 +389,43 @@ typedef LIS_INT (*lis_solver_fn)(LIS_SOLVER);
 static LIS_INT work_cg(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 4, 0); }
 static LIS_INT work_bicgstab(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 7, 0); }
 static LIS_INT work_bicg(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 6, 0); }
+static LIS_INT work_n(LIS_SOLVER s, LIS_INT n) { return lis_host_solver_malloc_work(s, n, 0); }
+static LIS_INT work_3(LIS_SOLVER s) { return work_n(s, 3); }
+static LIS_INT work_4(LIS_SOLVER s) { return work_n(s, 4); }
+static LIS_INT work_6(LIS_SOLVER s) { return work_n(s, 6); }
+static LIS_INT work_7(LIS_SOLVER s) { return work_n(s, 7); }
+static LIS_INT work_10(LIS_SOLVER s) { return work_n(s, 10); }
+static LIS_INT work_9(LIS_SOLVER s) { return work_n(s, 9); }
+static LIS_INT work_12(LIS_SOLVER s) { return work_n(s, 12); }
+static LIS_INT work_13(LIS_SOLVER s) { return work_n(s, 13); }
+static LIS_INT work_14(LIS_SOLVER s) { return work_n(s, 14); }
 /* work[0] of the reference is the (restart+1)-vector s of the least-squares problem; here
  * that short vector is a host array owned by lis_gmres, so slot 0 stays empty */
 static LIS_INT work_gmres(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 4 + s->options[LIS_OPTIONS_RESTART] + 1, 1); }
 
+static LIS_INT work_orthomin(LIS_SOLVER s) { return work_n(s, 3 + 3 * (s->options[LIS_OPTIONS_RESTART] + 1)); }
+/* FGMRES: slot 0 (the short vector s of the reference) stays empty, like GMRES */
+static LIS_INT work_fgmres(LIS_SOLVER s) { return lis_host_solver_malloc_work(s, 4 + 2 * s->options[LIS_OPTIONS_RESTART] + 1, 1); }
+static LIS_INT work_bicgstabl(LIS_SOLVER s) { return work_n(s, 4 + 2 * (s->options[LIS_OPTIONS_ELL] + 1)); }
+static LIS_INT check_bicgstabl(LIS_SOLVER s)
+{
+    const LIS_INT ell = s->options[LIS_OPTIONS_ELL];
+    if (ell < 1) {
+        LIS_SETERR1(LIS_ERR_ILL_ARG, "Parameter LIS_OPTIONS_ELL(=%D) is less than 1\n", ell);
+        return LIS_ERR_ILL_ARG;
+    }
+    return LIS_SUCCESS;
+}
+static LIS_INT work_idrs(LIS_SOLVER s) { return work_n(s, 4 + 3 * s->options[LIS_OPTIONS_IDRS_RESTART]); }
+static LIS_INT work_idr1(LIS_SOLVER s) { return work_n(s, 4 + 3 * (s->options[LIS_OPTIONS_IDRS_RESTART] > 1 ? s->options[LIS_OPTIONS_IDRS_RESTART] : 1)); }
+static LIS_INT check_idrs(LIS_SOLVER s)
+{
+    if (s->options[LIS_OPTIONS_IDRS_RESTART] < 1) {
+        LIS_SETERR1(LIS_ERR_ILL_ARG, "Parameter LIS_OPTIONS_IDRS_RESTART(=%D) is less than 1\n", s->options[LIS_OPTIONS_IDRS_RESTART]);
+        return LIS_ERR_ILL_ARG;
+    }
+    return LIS_SUCCESS;
+}
 static LIS_INT check_none(LIS_SOLVER s) { (void)s; return LIS_SUCCESS; }
 static LIS_INT check_gmres(LIS_SOLVER s)
 {
@@ -415,6 +445,27 @@ static lis_solver_entry solver_entry(LIS_INT nsolver)
     case LIS_SOLVER_CG: e.check = check_none; e.work = work_cg; e.run = lis_cg; e.conv_cond_ok = 1; break;
     case LIS_SOLVER_BICG: e.check = check_none; e.work = work_bicg; e.run = lis_bicg; e.conv_cond_ok = 1; break;
     case LIS_SOLVER_BICGSTAB: e.check = check_none; e.work = work_bicgstab; e.run = lis_bicgstab; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_CGS: e.check = check_none; e.work = work_7; e.run = lis_cgs; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_CRS: e.check = check_none; e.work = work_6; e.run = lis_crs; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_CR: e.check = check_none; e.work = work_6; e.run = lis_cr; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_COCR: e.check = check_none; e.work = work_6; e.run = lis_cocr; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_COCG: e.check = check_none; e.work = work_4; e.run = lis_cocg; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_BICR: e.check = check_none; e.work = work_10; e.run = lis_bicr; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_BICRSTAB: e.check = check_none; e.work = work_9; e.run = lis_bicrstab; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_TFQMR: e.check = check_none; e.work = work_9; e.run = lis_tfqmr; e.conv_cond_ok = 0; break;
+    case LIS_SOLVER_GPBICG: e.check = check_none; e.work = work_14; e.run = lis_gpbicg; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_GPBICR: e.check = check_none; e.work = work_14; e.run = lis_gpbicr; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_BICGSAFE: e.check = check_none; e.work = work_12; e.run = lis_bicgsafe; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_BICRSAFE: e.check = check_none; e.work = work_13; e.run = lis_bicrsafe; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_ORTHOMIN: e.check = check_gmres; e.work = work_orthomin; e.run = lis_orthomin; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_MINRES: e.check = check_none; e.work = work_7; e.run = lis_minres; e.conv_cond_ok = 0; break;
+    case LIS_SOLVER_FGMRES: e.check = check_gmres; e.work = work_fgmres; e.run = lis_fgmres; e.conv_cond_ok = 0; break;
+    case LIS_SOLVER_BICGSTABL: e.check = check_bicgstabl; e.work = work_bicgstabl; e.run = lis_bicgstabl; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_JACOBI: e.check = check_none; e.work = work_4; e.run = lis_jacobi; e.conv_cond_ok = 0; break;
+    case LIS_SOLVER_GS: e.check = check_none; e.work = work_3; e.run = lis_gs; e.conv_cond_ok = 0; break;
+    case LIS_SOLVER_SOR: e.check = check_none; e.work = work_3; e.run = lis_sor; e.conv_cond_ok = 0; break;
+    case LIS_SOLVER_IDRS: e.check = check_idrs; e.work = work_idrs; e.run = lis_idrs; e.conv_cond_ok = 1; break;
+    case LIS_SOLVER_IDR1: e.check = check_none; e.work = work_idr1; e.run = lis_idr1; e.conv_cond_ok = 1; break;
     case LIS_SOLVER_GMRES: e.check = check_gmres; e.work = work_gmres; e.run = lis_gmres; e.conv_cond_ok = 0; break;
     default: break;
     }
@@ -471,7 +522,7 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     }
     lis_solver_entry entry = solver_entry(nsolver);
     if (entry.run == NULL) {
-        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "solver %s is outside the B200 hot path (cg, bicg, bicgstab and gmres are available)\n", k_solvername[nsolver]);
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "solver %s has no driver in this library\n", k_solvername[nsolver]);
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (precon_type < 0 || precon_type >= lis_host_precon_type_end()) {
@@ -492,6 +543,10 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     }
     if (scale != LIS_SCALE_NONE || solver->options[LIS_OPTIONS_USE_AT]) {
         LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale and -use_at are outside the B200 hot path\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    if (nsolver >= LIS_SOLVER_JACOBI && nsolver <= LIS_SOLVER_SOR && precon_type != LIS_PRECON_TYPE_NONE) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "the stationary solvers (jacobi, gs, sor) run with -p none only (the reference rescales the system otherwise)\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     err = entry.check(solver);
@@ -515,7 +570,9 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     /* residual history */
     if (solver->rhistory) lis_free(solver->rhistory);
     solver->rhistory = NULL;
-    rhistory = (LIS_REAL *)lis_malloc(((size_t)maxiter + 2) * sizeof(LIS_REAL), "lis_solve::rhistory");
+    /* maxiter+2 entries like the reference, plus slack: BiCGSTAB(l) counts l steps per sweep and can
+     * record up to iteration maxiter+l (the reference writes past its array there) */
+    rhistory = (LIS_REAL *)lis_malloc(((size_t)maxiter + 2 + 64) * sizeof(LIS_REAL), "lis_solve::rhistory");
     if (rhistory == NULL) {
         LIS_SETERR_MEM((maxiter + 2) * sizeof(LIS_SCALAR));
         lis_vector_destroy(xx);

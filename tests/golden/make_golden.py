@@ -78,5 +78,48 @@ def main():
     np.savez_compressed(os.path.join(HERE, "solve_bicg.npz"), **out)
 
 
+EXT = ["cgs", "crs", "cr", "cocg", "cocr", "bicr", "bicrstab", "tfqmr", "gpbicg", "gpbicr", "bicgsafe", "bicrsafe", "orthomin",
+       "minres", "fgmres", "bicgstabl", "idrs", "idr1", "jacobi", "gs", "sor"]
+EXT_SYMMETRIC_ONLY = ("cr", "cocg", "cocr", "minres")
+EXT_STATIONARY = ("jacobi", "gs", "sor")
+
+
+def ext_solvers():
+    """solve_ext.npz: every further solver of the reference on two systems; per case the
+    iteration counts of the OpenMP reference at 1, 2, 4 and 8 threads (its own spread), and the
+    serial run's first residuals (its solution is the vector of ones to 1e-8, asserted here)."""
+    H.ensure_built()
+    ref, omp = H.ref_shim("serial"), H.ref_shim("omp")
+    out = {}
+    systems = {"p7": H.poisson3d_7pt(12, 11, 10), "unsym": H.random_csr(1500, 7, 404, band=50)}
+    for key, (ptr, idx, val) in systems.items():
+        n = len(ptr) - 1
+        b, _ = ref.spmv("csr", ptr, idx, val, np.ones(n))
+        out[f"ptr_{key}"], out[f"idx_{key}"], out[f"val_{key}"], out[f"b_{key}"] = ptr, idx, val, b
+        for sv in EXT:
+            if key == "unsym" and sv in EXT_SYMMETRIC_ONLY:
+                continue
+            for pre in ("none",) if sv in EXT_STATIONARY else ("none", "jacobi", "ssor"):
+                if (pre == "ssor" and sv == "bicr") or (key == "unsym" and sv == "sor"):
+                    continue                           # transposed SSOR: not provided; SOR(1.9) diverges on this matrix
+                opts = f"-i {sv} -p {pre}" + (" -maxiter 4000" if sv in EXT_STATIONARY else "")
+                r = ref.solve(ptr, idx, val, b, opts)
+                its = [r["iter"]]
+                if pre != "ssor":                      # block SSOR changes the preconditioner itself with the thread count
+                    for t in (2, 4, 8):
+                        omp.set_threads(t)
+                        its.append(omp.solve(ptr, idx, val, b, opts)["iter"])
+                tag = f"{key}_{sv}_{pre}"
+                out[f"opts_{tag}"] = np.array(opts); out[f"status_{tag}"] = np.array(r["status"]); out[f"iters_{tag}"] = np.array(its)
+                out[f"rhist_{tag}"] = r["rhistory"][:12]
+                assert r["status"] == 0 and np.abs(r["x"] - 1.0).max() < 1e-8, tag
+                print(tag, r["status"], its, r["resid"])
+    np.savez_compressed(os.path.join(HERE, "solve_ext.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ext":
+        ext_solvers()
+    else:
+        main()
+        ext_solvers()

@@ -1,0 +1,42 @@
+"""The further linear solvers of the reference (everything lis_solver_execute[] lists beyond
+CG/BiCG/BiCGSTAB/GMRES) on the B200, against outputs of the compiled reference committed in
+tests/golden/solve_ext.npz (made by tests/golden/make_golden.py ext).
+
+Their control flow is pinned bit-for-bit on the mock device (tests/test_hostcheck.py); on the GPU
+only the reduction order differs, exactly as it does between the reference's own thread counts.
+So the bar here is the reference's own envelope: the iteration count within the range the
+OpenMP reference shows at 1, 2, 4 and 8 threads (widened by that range, at least +-2), the first
+residuals equal to 1e-6, the solution equal to the reference's (the vector of ones) to 1e-7."""
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(H.GOLDEN, "solve_ext.npz")
+
+
+def _cases():
+    if not os.path.exists(GOLD):
+        return []
+    g = np.load(GOLD)
+    return sorted(k[5:] for k in g.files if k.startswith("opts_"))
+
+
+@pytest.mark.parametrize("tag", _cases())
+def test_further_solver_within_reference_envelope(b200, tag):
+    g = np.load(GOLD)
+    key = tag.split("_")[0]
+    opts = str(g[f"opts_{tag}"])
+    its = [int(v) for v in g[f"iters_{tag}"]]
+    r = b200.solve(g[f"ptr_{key}"], g[f"idx_{key}"], g[f"val_{key}"], g[f"b_{key}"], opts)
+    assert r["err"] == 0 and r["status"] == 0, (opts, r["err"], r["status"])
+    slack = max(2, max(its) - min(its))
+    assert min(its) - slack <= r["iter"] <= max(its) + slack, f"{opts}: {r['iter']} iterations, reference {its}"
+    ref_h = g[f"rhist_{tag}"]
+    k = min(5, len(ref_h), len(r["rhistory"]))
+    assert np.allclose(r["rhistory"][:k], ref_h[:k], rtol=1e-6, atol=0), (opts, r["rhistory"][:k], ref_h[:k])
+    assert np.abs(r["x"] - 1.0).max() < 1e-7, (opts, np.abs(r["x"] - 1.0).max())
