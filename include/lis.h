@@ -344,6 +344,7 @@ struct LIS_PRECON_STRUCT {
     LIS_INT worklen;
     LIS_INT is_copy;
     void *b200_sweep;        /* private: SSOR level schedule on the device */
+    void *b200_ilu;          /* private: ILU(k) factors (host) and their device schedules */
 };
 typedef struct LIS_PRECON_STRUCT *LIS_PRECON;
 

@@ -155,6 +155,19 @@ int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *d_ord
                                 const double *d_wd, const int *d_rowblk_start, const int *d_rowblk_end,
                                 const double *d_in, double *d_out, unsigned int *d_ticket, void *stream);
 
+/* One-launch triangular solve on a factor prepared the same way (strictly lower or strictly
+ * upper part, rows in dependency-level order, couplings that must be dropped already removed):
+ *   mode 0: out[i] = (in[i] - sum v*out[jj]) * wd[i]     ILU's U solve x = D(x - Ux)   src/precon/lis_precon_iluk.c:1040-1048
+ *                                                        and the second half of the transposed SSOR sweep
+ *   mode 1: out[i] =  in[i] - sum v*out[jj]              ILU's unit-diagonal L solve   src/precon/lis_precon_iluk.c:1030-1037
+ *   mode 2: out[i] =  in[i] - sum v*(out[jj]*wd[jj])     first half of the transposed SSOR sweep
+ *                                                        src/matrix/lis_matrix_csr.c:1838-1845
+ * Sums run in storage order, unfused.  d_wd may be NULL for mode 1.                             */
+int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *d_order,
+                            const int *d_pptr, const int *d_pidx, const double *d_pval,
+                            const double *d_wd, const double *d_in, double *d_out,
+                            unsigned int *d_ticket, void *stream);
+
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
 /* d_ws[i] = d_x[d_export_index[i]] */
 int lisb200_gather(int count, const int *d_index, const double *d_x, double *d_out, void *stream);

@@ -58,6 +58,7 @@ LIS_INT lis_matrix_split(LIS_MATRIX A);
 LIS_INT lis_matrix_merge(LIS_MATRIX A);
 LIS_INT lis_matrix_sort_csr(LIS_MATRIX A);
 LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag);
+LIS_INT lis_matrix_solveh(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag);   /* SSOR only */
 LIS_INT lis_matrix_convert_self(LIS_SOLVER solver);
 LIS_INT lis_matrix_storage_destroy(LIS_MATRIX A);
 LIS_INT lis_matrix_DLU_destroy(LIS_MATRIX A);

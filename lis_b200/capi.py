@@ -106,6 +106,7 @@ class Shim:
         L.shim_vec_op.argtypes = [C.c_int, C.c_int, C.c_double, _f64p, _f64p, _f64p, _f64p, C.POINTER(C.c_double)]
         L.shim_get_diagonal.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, C.c_int, C.c_int, _f64p]
         L.shim_psolve.argtypes = [C.c_int, _i32p, _i32p, _f64p, C.c_char_p, _f64p, _f64p]
+        L.shim_psolveh.argtypes = [C.c_int, _i32p, _i32p, _f64p, C.c_char_p, _f64p, _f64p]
         L.shim_solve.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_char_p,
                                  _i32p, _f64p, _f64p, C.c_int]
         err = L.shim_begin(init_args.encode())
@@ -255,11 +256,12 @@ class Shim:
             raise RuntimeError(f"shim_get_diagonal failed with Lis error {err}")
         return d
 
-    def psolve(self, ptr, idx, val, b, options):
+    def psolve(self, ptr, idx, val, b, options, transposed=False):
         ptr, idx, val = self._csr(ptr, idx, val)
         n = len(ptr) - 1
         x = np.empty(n, np.float64)
-        err = self.lib.shim_psolve(n, ptr, idx, val, options.encode(), np.ascontiguousarray(b, np.float64), x)
+        fn = self.lib.shim_psolveh if transposed else self.lib.shim_psolve
+        err = fn(n, ptr, idx, val, options.encode(), np.ascontiguousarray(b, np.float64), x)
         if err:
             raise RuntimeError(f"shim_psolve failed with Lis error {err}")
         return x

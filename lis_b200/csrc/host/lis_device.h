@@ -99,6 +99,29 @@ LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);                 /
 LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);                /* y = A^H x, async */
 void    lisd_sweep_free(void *sweep);
 
+/* ---- triangular factors prepared for the one-launch ("sync-free") solve kernels ---- */
+typedef struct lisd_perm {        /* rows in dependency-level order + the factor permuted to match */
+    int nslots;                   /* levels concatenated, each padded to a multiple of 32 */
+    int *d_order;                 /* slot -> row (or -1) */
+    int *d_pptr, *d_pidx;         /* the triangular part permuted into slot order */
+    double *d_pval;
+} lisd_perm;
+LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
+                        const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val);
+void    lisd_perm_free(lisd_perm *p);
+int    *lisd_order_by_level(int n, const int *lvl, int nlev, int *rows);   /* counting sort; returns level pointers */
+
+typedef struct lisd_tri {         /* one strictly triangular CSR factor (lower or upper), lis_sptrsv.c */
+    int n, nlev;
+    lisd_perm p;
+    unsigned int *d_ticket;
+} lisd_tri;
+/* ptr/idx/val: host CSR of the strict triangle, entries in the order the row sum must run */
+LIS_INT lisd_tri_build(int n, const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, lisd_tri **out);
+void    lisd_tri_free(lisd_tri *T);
+/* mode: 0 out=(in-sum)*wd, 1 out=in-sum, 2 out=in-sum over v*(out[jj]*wd[jj]); device pointers, async */
+LIS_INT lisd_tri_solve(const lisd_tri *T, int mode, const double *d_wd, const double *d_in, double *d_out, const char *what);
+
 /* ---- fused steps of the Krylov loops: one launch, one host wait, scalar(s) returned ---- */
 LIS_INT lisd_jacobi_dot(LIS_VECTOR r, LIS_VECTOR dinv, LIS_VECTOR z, LIS_SCALAR *rho);        /* z=r.*dinv; <r,z> */
 LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy);        /* y=Ax; <x,y> */

@@ -34,6 +34,10 @@ LIS_INT lis_host_precon_lookup(const char *name);
 void    lis_host_print_rhistory(LIS_INT iter, LIS_REAL resid);
 LIS_INT lis_host_solver_malloc_work(LIS_SOLVER solver, LIS_INT worklen, LIS_INT first);
 LIS_INT lis_host_solver_residual(LIS_SOLVER solver, LIS_VECTOR r, LIS_REAL *res);
+LIS_INT lis_host_ilu_create(LIS_SOLVER solver, LIS_PRECON precon);      /* lis_precon_ilu.c */
+void    lis_host_ilu_free(void *factors);
+LIS_INT lis_psolve_iluk(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
+LIS_INT lis_psolveh_iluk(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
 LIS_INT lis_host_fill_mt19937(LIS_INT s, LIS_INT n, LIS_VECTOR *P);
 LIS_INT lis_host_solver_shadow_residual(LIS_SOLVER solver, LIS_VECTOR r0, LIS_VECTOR rs0);
 

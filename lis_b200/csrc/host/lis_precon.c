@@ -124,7 +124,7 @@ static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
 static LIS_INT create_unsupported(LIS_SOLVER solver, LIS_PRECON precon)
 {
     (void)solver; (void)precon;
-    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is outside the B200 hot path (none, jacobi, ssor and registered ones are available)\n");
+    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is not available (none, jacobi, ssor, ilu and registered ones are)\n");
     return LIS_ERR_NOT_IMPLEMENTED;
 }
 
@@ -144,6 +144,7 @@ LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
     case LIS_PRECON_TYPE_NONE: err = create_none(solver, *precon); break;
     case LIS_PRECON_TYPE_JACOBI: err = create_jacobi(solver, *precon); break;
     case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
+    case LIS_PRECON_TYPE_ILU: err = lis_host_ilu_create(solver, *precon); break;
     default: err = create_unsupported(solver, *precon); break;
     }
     if (err) { lis_precon_destroy(*precon); *precon = NULL; return err; }
@@ -155,6 +156,7 @@ LIS_INT lis_precon_destroy(LIS_PRECON precon)
     if (precon) {
         if (precon->is_copy && precon->A) lis_matrix_destroy(precon->A);
         if (precon->D) lis_vector_destroy(precon->D);
+        if (precon->b200_ilu) lis_host_ilu_free(precon->b200_ilu);
         if (precon->work) {
             for (LIS_INT i = 0; i < precon->worklen; i++) lis_vector_destroy(precon->work[i]);
             lis_free(precon->work);
@@ -190,6 +192,7 @@ LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
     case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
     case LIS_PRECON_TYPE_SSOR: return lis_psolve_ssor(solver, b, x);
+    case LIS_PRECON_TYPE_ILU: return lis_psolve_iluk(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg)
             return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolve(solver, b, x);
@@ -198,31 +201,25 @@ LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
     }
 }
 
-/* M^-H b for BiCG: none and Jacobi are self-adjoint for real scalars (lis_precon_jacobi.c
- * lis_psolveh_jacobi: x = b*conj(d)); the transposed SSOR sweep (lis_matrix_solveh) is not part
- * of the hot path */
+/* M^-H b for BiCG / BiCR: none and Jacobi are self-adjoint for real scalars (lis_precon_jacobi.c
+ * lis_psolveh_jacobi: x = b*conj(d)); SSOR and ILU run their transposed sweeps */
 LIS_INT lis_psolveh(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
 {
     const LIS_INT type = solver->precon->precon_type;
     switch (type) {
     case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
+    case LIS_PRECON_TYPE_SSOR: return lis_matrix_solveh(solver->precon->A, b, x, LIS_MATRIX_SSOR);
+    case LIS_PRECON_TYPE_ILU: return lis_psolveh_iluk(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg && g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh)
             return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh(solver, b, x);
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "the transposed preconditioner solve (BiCG) is available for none and jacobi only\n");
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner has no transposed solve\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
 }
 
 /* ------------------------------------------------------------------ SSOR level schedule */
-typedef struct lisd_perm {        /* one direction of the one-launch sweep */
-    int nslots;                   /* levels concatenated, each padded to a multiple of 32 */
-    int *d_order;                 /* slot -> row (or -1) */
-    int *d_pptr, *d_pidx;         /* L or U permuted into slot order */
-    double *d_pval;
-} lisd_perm;
-
 typedef struct lisd_sweep {
     int n, nblocks;
     int nlev_f, nlev_b;
@@ -232,9 +229,10 @@ typedef struct lisd_sweep {
     lisd_perm pf, pb;              /* one-launch variant */
     double *d_w;                   /* forward-sweep result (input of the backward sweep) */
     unsigned int *d_ticket;
+    lisd_tri *tUT, *tLT;           /* transposed sweep (lis_matrix_solveh), built on first use */
 } lisd_sweep;
 
-static void perm_free(lisd_perm *p)
+void lisd_perm_free(lisd_perm *p)
 {
     lisd_free(p->d_order); lisd_free(p->d_pptr); lisd_free(p->d_pidx); lisd_free(p->d_pval);
     memset(p, 0, sizeof(*p));
@@ -242,8 +240,8 @@ static void perm_free(lisd_perm *p)
 
 /* rows[] is level-ordered, lptr[l] its level pointers; builds the padded order and the permuted
  * copy of the triangular part (ptr/idx/val, host) on the device */
-static LIS_INT perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
-                          const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
+LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
+                        const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
 {
     size_t nslots = 0;
     for (int l = 0; l < nlev; l++) nslots += (size_t)((lptr[l + 1] - lptr[l] + 31) & ~31);
@@ -290,13 +288,14 @@ void lisd_sweep_free(void *p)
     if (S == NULL) return;
     free(S->h_fptr); free(S->h_bptr);
     lisd_free(S->d_frows); lisd_free(S->d_brows); lisd_free(S->d_blk_start); lisd_free(S->d_blk_end);
-    perm_free(&S->pf); perm_free(&S->pb);
+    lisd_perm_free(&S->pf); lisd_perm_free(&S->pb);
     lisd_free(S->d_w); lisd_free(S->d_ticket);
+    lisd_tri_free(S->tUT); lisd_tri_free(S->tLT);
     free(S);
 }
 
 /* counting sort of rows by level; returns level pointers */
-static int *order_by_level(int n, const int *lvl, int nlev, int *rows)
+int *lisd_order_by_level(int n, const int *lvl, int nlev, int *rows)
 {
     int *ptr = (int *)calloc((size_t)nlev + 2, sizeof(int));
     if (!ptr) return NULL;
@@ -348,11 +347,11 @@ static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
         if (l + 1 > nlev) nlev = l + 1;
     }
     S->nlev_f = nlev;
-    S->h_fptr = order_by_level(n, lvl, nlev, rows);
+    S->h_fptr = lisd_order_by_level(n, lvl, nlev, rows);
     if (!S->h_fptr) goto fail;
     err = lisd_malloc((void **)&S->d_frows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_frows, rows, sizeof(int) * (size_t)n);
-    if (!err) err = perm_build(&S->pf, n, nlev, S->h_fptr, rows, A->L->ptr, A->L->index, A->L->value);
+    if (!err) err = lisd_perm_build(&S->pf, n, nlev, S->h_fptr, rows, A->L->ptr, A->L->index, A->L->value);
     if (err) goto fail;
     /* backward: row i waits for every U neighbour inside its block */
     nlev = 0;
@@ -367,12 +366,12 @@ static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
         if (l + 1 > nlev) nlev = l + 1;
     }
     S->nlev_b = nlev;
-    S->h_bptr = order_by_level(n, lvl, nlev, rows);
+    S->h_bptr = lisd_order_by_level(n, lvl, nlev, rows);
     err = LIS_OUT_OF_MEMORY;
     if (!S->h_bptr) goto fail;
     err = lisd_malloc((void **)&S->d_brows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_brows, rows, sizeof(int) * (size_t)n);
-    if (!err) err = perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value);
+    if (!err) err = lisd_perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value);
     if (!err) err = lisd_malloc((void **)&S->d_w, sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_malloc((void **)&S->d_ticket, 64);
     if (!err) err = lisd_malloc((void **)&S->d_blk_start, sizeof(int) * (size_t)(n > 0 ? n : 1));
@@ -495,4 +494,91 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
         if (err) return err;
     }
     return LIS_SUCCESS;
+}
+
+/* R^T restricted to couplings inside the owning block, as CSR; a row lists its entries by
+ * ascending (or descending) source row = the order the reference's column-oriented loops
+ * subtract them in */
+static LIS_INT core_transpose(LIS_INT n, LIS_MATRIX_CORE R, int nb, int descending, LIS_INT **optr, LIS_INT **oidx, LIS_SCALAR **oval)
+{
+    const size_t nnz = (size_t)R->ptr[n];
+    LIS_INT *ptr = (LIS_INT *)calloc((size_t)n + 1, sizeof(LIS_INT));
+    LIS_INT *idx = (LIS_INT *)malloc(sizeof(LIS_INT) * (nnz ? nnz : 1));
+    LIS_SCALAR *val = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (nnz ? nnz : 1));
+    LIS_INT *cur = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n > 0 ? n : 1));
+    LIS_INT *bs = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n > 0 ? n : 1));
+    LIS_INT *be = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n > 0 ? n : 1));
+    if (!ptr || !idx || !val || !cur || !bs || !be) {
+        free(ptr); free(idx); free(val); free(cur); free(bs); free(be);
+        LIS_SETERR_MEM(nnz * 12);
+        return LIS_OUT_OF_MEMORY;
+    }
+    for (int k = 0; k < nb; k++) {
+        LIS_INT is, ie;
+        LIS_GET_ISIE(k, nb, n, is, ie);
+        for (LIS_INT i = is; i < ie; i++) { bs[i] = is; be[i] = ie; }
+    }
+    for (LIS_INT i = 0; i < n; i++)
+        for (LIS_INT j = R->ptr[i]; j < R->ptr[i + 1]; j++) {
+            const LIS_INT c = R->index[j];
+            if (c >= bs[i] && c < be[i]) ptr[c + 1]++;
+        }
+    for (LIS_INT i = 0; i < n; i++) ptr[i + 1] += ptr[i];
+    for (LIS_INT i = 0; i < n; i++) cur[i] = ptr[i];
+    for (LIS_INT s = 0; s < n; s++) {
+        const LIS_INT i = descending ? n - 1 - s : s;
+        for (LIS_INT j = R->ptr[i]; j < R->ptr[i + 1]; j++) {
+            const LIS_INT c = R->index[j];
+            if (c < bs[i] || c >= be[i]) continue;
+            idx[cur[c]] = i; val[cur[c]++] = R->value[j];
+        }
+    }
+    free(cur); free(bs); free(be);
+    *optr = ptr; *oidx = idx; *oval = val;
+    return LIS_SUCCESS;
+}
+
+/* x = M^-T b for the SSOR splitting: src/matrix/lis_matrix_csr.c:1804-1855.  The reference runs
+ * two column-oriented loops,  t = x[i]*WD[i]; x[jj] -= U[i][jj]*t  (i ascending, x[i] itself left
+ * unscaled) and  x[i] = t = x[i]*WD[i]; x[jj] -= L[i][jj]*t  (i descending).  Row-wise these are
+ *   z[i] = b[i] - sum_k U^T[i][k] * (z[k]*WD[k])      k ascending
+ *   x[i] = (z[i] - sum_k L^T[i][k] * x[k]) * WD[i]    k descending
+ * i.e. two triangular solves on the transposed parts with the same products in the same order. */
+LIS_INT lis_matrix_solveh(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
+{
+    LIS_INT err = lisd_require("lis_matrix_solveh");
+    if (err) return err;
+    if (flag != LIS_MATRIX_SSOR) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_solveh: the transposed SSOR sweep is available\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    if (!A->is_splited) { err = lis_matrix_split(A); if (err) return err; }
+    if (A->WD == NULL) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matrix_solveh: the scaled diagonal WD is not set up\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    lisd_matrix *M;
+    lisd_sweep *S;
+    err = sweep_prepare(A, &M, &S);
+    if (err) return err;
+    if (S->tUT == NULL) {
+        LIS_INT *ptr, *idx;
+        LIS_SCALAR *val;
+        err = core_transpose(A->n, A->U, S->nblocks, 0, &ptr, &idx, &val);
+        if (err) return err;
+        err = lisd_tri_build(A->n, ptr, idx, val, &S->tUT);
+        free(ptr); free(idx); free(val);
+        if (err) return err;
+        err = core_transpose(A->n, A->L, S->nblocks, 1, &ptr, &idx, &val);
+        if (err) return err;
+        err = lisd_tri_build(A->n, ptr, idx, val, &S->tLT);
+        free(ptr); free(idx); free(val);
+        if (err) return err;
+    }
+    err = lisd_vec_device(b);
+    if (!err) err = lisd_vec_device(x);
+    if (err) return err;
+    err = lisd_tri_solve(S->tUT, 2, M->wd, b->value, S->d_w, "transposed SSOR sweep (U^T)");
+    if (err) return err;
+    return lisd_tri_solve(S->tLT, 0, M->wd, S->d_w, x->value, "transposed SSOR sweep (L^T)");
 }

@@ -89,7 +89,16 @@ fill_not_ready_kernel(int n, double *x)
         reinterpret_cast<unsigned long long *>(x)[i] = kNotReady;
 }
 
-template <bool kForward>
+// kMode selects the row formula (all sums in storage order, unfused):
+//   kSweepFwd   out[i] = (in[i] - sum v*out[jj]) * wd[i]        SSOR forward, (D/w+L)^-1, ILU's U solve
+//   kSweepBwd   out[i] = in[i] - (sum v*out[jj]) * wd[i]        SSOR backward
+//   kSweepPlain out[i] = in[i] - sum v*out[jj]                  unit-diagonal solve (ILU's L solve)
+//   kSweepReadScaled out[i] = in[i] - sum v*(out[jj]*wd[jj])    first half of the transposed SSOR sweep
+// kMasked: drop couplings outside the row's block (block-SSOR of the OpenMP reference); the
+// unmasked instantiations take a triangular factor that was already filtered on the host.
+enum { kSweepFwd = 0, kSweepBwd = 1, kSweepPlain = 2, kSweepReadScaled = 3 };
+
+template <int kMode, bool kMasked>
 __global__ void __launch_bounds__(128)
 ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
                      const int *__restrict__ pptr, const int *__restrict__ pidx, const double *__restrict__ pval,
@@ -103,7 +112,8 @@ ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
     if (k >= nslots) return;
     const int i = order[k];
     if (i < 0) return;
-    const int lo = blk_start[i], hi = blk_end[i];
+    constexpr bool kForward = kMode != kSweepBwd;
+    const int lo = kMasked ? blk_start[i] : 0, hi = kMasked ? blk_end[i] : 0x7fffffff;
     double t = kForward ? in[i] : 0.0;
     const int e = pptr[k + 1];
     constexpr int kBatch = 8;
@@ -116,7 +126,7 @@ ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
             const int j = min(j0 + q, e - 1);
             jj[q] = pidx[j];
             v[q] = pval[j];
-            const bool inblk = kForward ? (jj[q] >= lo) : (jj[q] >= lo && jj[q] < hi);   // else: coupling dropped
+            const bool inblk = !kMasked || (kForward ? (jj[q] >= lo) : (jj[q] >= lo && jj[q] < hi));   // else: coupling dropped
             if (j0 + q < e && inblk) used |= 1u << q;
             xv[q] = 0.0;
         }
@@ -131,9 +141,12 @@ ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
         }
 #pragma unroll
         for (int q = 0; q < kBatch; ++q)
-            if (used & (1u << q)) t = kForward ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
+            if (used & (1u << q)) {
+                if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
+                t = kForward ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
+            }
     }
-    st_publish(out + i, kForward ? mul(t, wd[i]) : sub(in[i], mul(t, wd[i])));
+    st_publish(out + i, kMode == kSweepFwd ? mul(t, wd[i]) : kMode == kSweepBwd ? sub(in[i], mul(t, wd[i])) : t);
 }
 
 }  // namespace lisb
@@ -154,11 +167,40 @@ extern "C" int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const
     fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
     const int grid = (nslots + 127) / 128;
     if (forward)
-        ssor_syncfree_kernel<true><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
+        ssor_syncfree_kernel<kSweepFwd, true><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
                                                         d_rowblk_end, d_in, d_out, d_ticket);
     else
-        ssor_syncfree_kernel<false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
+        ssor_syncfree_kernel<kSweepBwd, true><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
                                                          d_rowblk_end, d_in, d_out, d_ticket);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+/* One-launch triangular solve on a host-prepared factor (levels concatenated, padded to warps,
+ * entries permuted into slot order): mode 0 = scaled, 1 = plain, 2 = neighbours scaled on read. */
+extern "C" int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *d_order,
+                                       const int *d_pptr, const int *d_pidx, const double *d_pval,
+                                       const double *d_wd, const double *d_in, double *d_out,
+                                       unsigned int *d_ticket, void *stream)
+{
+    if (nslots <= 0 || n <= 0) return 0;
+    if (mode < 0 || mode > 2 || (mode != 1 && d_wd == nullptr)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    int fill_grid = (n + 255) / 256;
+    if (fill_grid > 148 * 8) fill_grid = 148 * 8;
+    fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
+    const int grid = (nslots + 127) / 128;
+    if (mode == 0)
+        ssor_syncfree_kernel<kSweepFwd, false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, nullptr,
+                                                                     nullptr, d_in, d_out, d_ticket);
+    else if (mode == 1)
+        ssor_syncfree_kernel<kSweepPlain, false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, nullptr, nullptr,
+                                                                       nullptr, d_in, d_out, d_ticket);
+    else
+        ssor_syncfree_kernel<kSweepReadScaled, false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, nullptr,
+                                                                            nullptr, d_in, d_out, d_ticket);
     LISB_CHECK_LAUNCH();
     return 0;
 }

@@ -82,6 +82,7 @@ EXT = ["cgs", "crs", "cr", "cocg", "cocr", "bicr", "bicrstab", "tfqmr", "gpbicg"
        "minres", "fgmres", "bicgstabl", "idrs", "idr1", "jacobi", "gs", "sor"]
 EXT_SYMMETRIC_ONLY = ("cr", "cocg", "cocr", "minres")
 EXT_STATIONARY = ("jacobi", "gs", "sor")
+BASE_WITH_NEW_PRECONS = ["cg", "bicg", "bicgstab", "gmres"]        # the north-star solvers with ILU / transposed SSOR
 
 
 def ext_solvers():
@@ -96,25 +97,46 @@ def ext_solvers():
         n = len(ptr) - 1
         b, _ = ref.spmv("csr", ptr, idx, val, np.ones(n))
         out[f"ptr_{key}"], out[f"idx_{key}"], out[f"val_{key}"], out[f"b_{key}"] = ptr, idx, val, b
-        for sv in EXT:
-            if key == "unsym" and sv in EXT_SYMMETRIC_ONLY:
+        for sv in EXT + BASE_WITH_NEW_PRECONS:
+            if key == "unsym" and (sv in EXT_SYMMETRIC_ONLY or sv == "cg"):
                 continue
-            for pre in ("none",) if sv in EXT_STATIONARY else ("none", "jacobi", "ssor"):
-                if (pre == "ssor" and sv == "bicr") or (key == "unsym" and sv == "sor"):
-                    continue                           # transposed SSOR: not provided; SOR(1.9) diverges on this matrix
+            if sv in BASE_WITH_NEW_PRECONS:
+                precs = ("ilu", "ilu -ilu_fill 1") + (("ssor",) if sv == "bicg" else ())
+            for pre in precs if sv in BASE_WITH_NEW_PRECONS else ("none",) if sv in EXT_STATIONARY else ("none", "jacobi", "ssor", "ilu"):
+                if key == "unsym" and sv == "sor":
+                    continue                           # SOR(1.9) diverges on this matrix
                 opts = f"-i {sv} -p {pre}" + (" -maxiter 4000" if sv in EXT_STATIONARY else "")
                 r = ref.solve(ptr, idx, val, b, opts)
                 its = [r["iter"]]
-                if pre != "ssor":                      # block SSOR changes the preconditioner itself with the thread count
+                if pre.split()[0] not in ("ssor", "ilu"):         # block SSOR / block ILU change the preconditioner itself with the thread count
                     for t in (2, 4, 8):
                         omp.set_threads(t)
                         its.append(omp.solve(ptr, idx, val, b, opts)["iter"])
-                tag = f"{key}_{sv}_{pre}"
+                tag = f"{key}_{sv}_{pre}".replace(" -ilu_fill ", "")
                 out[f"opts_{tag}"] = np.array(opts); out[f"status_{tag}"] = np.array(r["status"]); out[f"iters_{tag}"] = np.array(its)
                 out[f"rhist_{tag}"] = r["rhistory"][:12]
                 assert r["status"] == 0 and np.abs(r["x"] - 1.0).max() < 1e-8, tag
                 print(tag, r["status"], its, r["resid"])
     np.savez_compressed(os.path.join(HERE, "solve_ext.npz"), **out)
+
+    # one application of M^-1 and M^-H: bitwise fixtures (the triangular solves keep the reference's
+    # summation order, so the GPU must reproduce these exactly); serial and 4-thread block variants
+    out = {}
+    for key, (ptr, idx, val) in {"p7": H.poisson3d_7pt(9, 8, 7), "unsym": H.random_csr(600, 6, 41, band=30),
+                                 "p27": H.poisson3d_27pt(6, 5, 4)}.items():
+        n = len(ptr) - 1
+        b = H.rand_vec(n, 5)
+        out[f"ptr_{key}"], out[f"idx_{key}"], out[f"val_{key}"], out[f"b_{key}"] = ptr, idx, val, b
+        for pi, pre in enumerate(("ilu", "ilu -ilu_fill 1", "ilu -ilu_fill 3", "ssor", "ssor -ssor_omega 1.3")):
+            for t in (1, 4):
+                shim = ref if t == 1 else omp
+                shim.set_threads(t)
+                for tr in (0, 1):
+                    tag = f"{key}_{pi}_{t}_{tr}"
+                    out[f"opts_{tag}"] = np.array("-p " + pre)
+                    out[f"x_{tag}"] = shim.psolve(ptr, idx, val, b, "-p " + pre, transposed=bool(tr))
+    omp.set_threads(1)
+    np.savez_compressed(os.path.join(HERE, "psolve_ilu_ssor.npz"), **out)
 
 
 if __name__ == "__main__":

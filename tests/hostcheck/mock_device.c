@@ -165,6 +165,24 @@ int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const
     }
     return 0;
 }
+int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *order, const int *pp, const int *pi, const double *pv,
+                            const double *wd, const double *in, double *out, unsigned int *ticket, void *s)
+{
+    (void)ticket; (void)s;
+    for (int i = 0; i < n; i++) out[i] = NAN;
+    for (int k = 0; k < nslots; k++) {
+        const int i = order[k];
+        if (i < 0) continue;
+        double t = in[i];
+        for (int j = pp[k]; j < pp[k + 1]; j++) {
+            const int jj = pi[j];
+            const double xv = mode == 2 ? out[jj] * wd[jj] : out[jj];
+            t -= pv[j] * xv;
+        }
+        out[i] = mode == 0 ? t * wd[i] : t;
+    }
+    return 0;
+}
 /* slots are in dependency (level) order, so a sequential walk is a valid schedule */
 int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *order, const int *pp, const int *pi, const double *pv,
                                 const double *wd, const int *bs, const int *be, const double *in, double *out,

@@ -385,8 +385,21 @@ EXPORT int shim_get_diagonal(int fmt, int n, const int *ptr, const int *idx, con
 }
 
 /* x = M^-1 b with the preconditioner selected by `options` ("-p ssor -ssor_omega 1.2" ...) */
+static int psolve_any(int transposed, int n, const int *ptr, const int *idx, const double *val, const char *options,
+                      const double *b, double *x);
 EXPORT int shim_psolve(int n, const int *ptr, const int *idx, const double *val, const char *options,
                        const double *b, double *x)
+{
+    return psolve_any(0, n, ptr, idx, val, options, b, x);
+}
+/* x = M^-H b (what BiCG / BiCR call) */
+EXPORT int shim_psolveh(int n, const int *ptr, const int *idx, const double *val, const char *options,
+                        const double *b, double *x)
+{
+    return psolve_any(1, n, ptr, idx, val, options, b, x);
+}
+static int psolve_any(int transposed, int n, const int *ptr, const int *idx, const double *val, const char *options,
+                      const double *b, double *x)
 {
     LIS_MATRIX A;
     LIS_VECTOR vb, vx;
@@ -401,7 +414,7 @@ EXPORT int shim_psolve(int n, const int *ptr, const int *idx, const double *val,
     solver->A = A;
     err = lis_precon_create(solver, &precon); if (err) return (int)err;
     solver->precon = precon;
-    err = lis_psolve(solver, vb, vx); if (err) return (int)err;
+    err = transposed ? lis_psolveh(solver, vb, vx) : lis_psolve(solver, vb, vx); if (err) return (int)err;
     err = lis_vector_gather(vx, x); if (err) return (int)err;
     lis_precon_destroy(precon);
     solver->precon = NULL;

@@ -326,7 +326,7 @@ def test_solver_status_codes(b200):
     assert g["err"] == 0 and g["status"] == 4 and g["iter"] == 4        # LIS_MAXITER, iter = maxiter+1
     g = b200.solve(ptr, idx, val, np.zeros(n), "-i cg")
     assert g["status"] == 0 and g["iter"] == 1                            # already converged: iter = 1
-    g = b200.solve(ptr, idx, val, b, "-i cg -p ilu")
+    g = b200.solve(ptr, idx, val, b, "-i cg -p sainv")
     assert g["err"] == 5                                                  # LIS_ERR_NOT_IMPLEMENTED
 
 

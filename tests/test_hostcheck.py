@@ -27,7 +27,9 @@ SOLVES = ["-i cg", "-i cg -p jacobi", "-i cg -p ssor", "-i cg -p ssor -ssor_omeg
           "-i bicgstab -p ssor", "-i gmres -restart 7", "-i gmres -p jacobi", "-i gmres -restart 12 -p ssor",
           "-i gmres -restart 3 -p jacobi -maxiter 40", "-i cg -p jacobi -conv_cond nrm2_b", "-i bicgstab -p jacobi -conv_cond nrm1_b",
           "-i cg -p jacobi -tol 1e-6", "-i bicgstab -maxiter 5", "-i cg -initx_zeros false -p jacobi",
-          "", "-i bicg", "-i bicg -p jacobi", "-i bicg -p jacobi -conv_cond nrm2_b", "-i bicg -maxiter 4"]
+          "", "-i bicg", "-i bicg -p jacobi", "-i bicg -p jacobi -conv_cond nrm2_b", "-i bicg -maxiter 4",
+          "-i cg -p ilu", "-i cg -p ilu -ilu_fill 2", "-i bicgstab -p ilu -ilu_fill 1", "-i gmres -restart 9 -p ilu",
+          "-i bicg -p ssor", "-i bicg -p ilu", "-i bicg -p ilu -ilu_fill 3", "-i bicg -p ssor -ssor_omega 0.8"]
 
 
 @pytest.mark.parametrize("opts", SOLVES)
@@ -54,7 +56,6 @@ EXT_SOLVERS = ["cgs", "crs", "cr", "cocg", "cocr", "bicr", "bicrstab", "tfqmr", 
                "idrs", "idrs -irestart 4", "idrs -irestart 1", "idr1", "cgs -maxiter 6", "idrs -maxiter 9", "idr1 -maxiter 8",
                "tfqmr -conv_cond nrm2_b", "gpbicg -conv_cond nrm1_b", "bicgstabl -maxiter 7"]
 SYMMETRIC_ONLY = ("cr", "cocg", "cocr", "minres")
-TRANSPOSED = ("bicr",)                                 # call lis_psolveh: SSOR's transposed sweep has no kernel here
 
 
 @pytest.mark.parametrize("sv", EXT_SOLVERS)
@@ -62,12 +63,9 @@ def test_further_solvers_bit_for_bit(hc, ref_serial, sv):
     for name, (ptr, idx, val) in systems():
         n = len(ptr) - 1
         b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))
-        for pre in ("none", "jacobi", "ssor"):
+        for pre in ("none", "jacobi", "ssor", "ilu"):
             opts = f"-i {sv} -p {pre}"
             g = hc.solve(ptr, idx, val, b, opts)
-            if pre == "ssor" and sv.split()[0] in TRANSPOSED:
-                assert g["err"] == 5, opts
-                continue
             r = ref_serial.solve(ptr, idx, val, b, opts)
             assert (g["err"], g["status"], g["iter"]) == (r["err"], r["status"], r["iter"]), (name, opts, g["iter"], r["iter"])
             H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{name} {opts} residual history")
@@ -202,10 +200,29 @@ def test_matvech(hc, ref_serial):
             H.assert_bits_equal(res[("hc", fmt, split)], res[("ref", fmt, split)], f"matvech {name} fmt={fmt} split={split}")
 
 
+@pytest.mark.parametrize("threads", [1, 2, 3, 8])
+def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads):
+    """one application of M^-1 / M^-H for ILU(k) and SSOR against the reference: the serial build
+    at one block, the OpenMP build (per-thread diagonal blocks) at `threads` blocks
+    (src/precon/lis_precon_iluk.c:262-1287, src/matrix/lis_matrix_csr.c:1804-1855)"""
+    ref = ref_serial if threads == 1 else ref_omp
+    hc.set_threads(threads); ref.set_threads(threads)
+    try:
+        for name, (ptr, idx, val) in list(systems()) + [("p27", H.poisson3d_27pt(6, 5, 4))]:
+            b = H.rand_vec(len(ptr) - 1, 5)
+            for pre in ("ilu", "ilu -ilu_fill 1", "ilu -ilu_fill 3", "ssor", "ssor -ssor_omega 1.3"):
+                for tr in (False, True):
+                    g = hc.psolve(ptr, idx, val, b, "-p " + pre, transposed=tr)
+                    r = ref.psolve(ptr, idx, val, b, "-p " + pre, transposed=tr)
+                    H.assert_bits_equal(g, r, f"{name} -p {pre} transposed={tr} blocks={threads}")
+    finally:
+        hc.set_threads(1); ref.set_threads(1)
+
+
 def test_unsupported_requests_are_rejected(hc):
     ptr, idx, val = H.poisson1d(30)
     b = np.ones(30)
-    for opts, code in (("-i bicg -p ssor", 5), ("-i cg -p ilu", 5), ("-i cg -p jacobi -adds true", 5),
+    for opts, code in (("-i bicg -p sainv", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p jacobi -adds true", 5),
                        ("-i cg -scale jacobi", 5), ("-i cg -f quad", 1), ("-i gmres -conv_cond nrm2_b", 1), ("-i jacobi -conv_cond nrm2_b", 1),
                        ("-i gmres -restart -1", 1), ("-i cg -maxiter -3", 1)):
         g = hc.solve(ptr, idx, val, b, opts)

@@ -17,6 +17,7 @@ import harness as H
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(H.GOLDEN, "solve_ext.npz")
+GOLD_PSOLVE = os.path.join(H.GOLDEN, "psolve_ilu_ssor.npz")
 
 
 def _cases():
@@ -40,3 +41,21 @@ def test_further_solver_within_reference_envelope(b200, tag):
     k = min(5, len(ref_h), len(r["rhistory"]))
     assert np.allclose(r["rhistory"][:k], ref_h[:k], rtol=1e-6, atol=0), (opts, r["rhistory"][:k], ref_h[:k])
     assert np.abs(r["x"] - 1.0).max() < 1e-7, (opts, np.abs(r["x"] - 1.0).max())
+
+
+def test_ilu_and_transposed_sweeps_match_reference_bits(b200):
+    """M^-1 b and M^-H b for ILU(k) and SSOR, one block and four blocks: the triangular solve
+    kernels keep the reference's summation order, so these are bitwise comparisons against the
+    outputs of the compiled reference (serial / 4 OpenMP threads) in psolve_ilu_ssor.npz"""
+    g = np.load(GOLD_PSOLVE)
+    tags = sorted(k[5:] for k in g.files if k.startswith("opts_"))
+    assert tags
+    try:
+        for tag in tags:
+            key, _, t, tr = tag.split("_")
+            b200.set_threads(int(t))
+            x = b200.psolve(g[f"ptr_{key}"], g[f"idx_{key}"], g[f"val_{key}"], g[f"b_{key}"], str(g[f"opts_{tag}"]),
+                            transposed=bool(int(tr)))
+            H.assert_bits_equal(x, g[f"x_{tag}"], f"{key} {g[f'opts_{tag}']} blocks={t} transposed={tr}")
+    finally:
+        b200.set_threads(1)
