@@ -4,7 +4,11 @@
 // spelled with the round-to-nearest intrinsics (__dmul_rn/__dadd_rn/...), which the compiler
 // never contracts into FMA.  The translation units are additionally built with -fmad=false.
 #pragma once
+#ifdef LISB_EMU            // tests/cudaemu: kernel sources compiled for the host emulator (test infrastructure)
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #define LISB_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
@@ -17,6 +21,7 @@ __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, 
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
 
+#ifndef LISB_EMU           // the inline-PTX helpers; cuda_emu.h restates them for the host emulator
 // streaming (read-once) loads: bypass L1 allocation so the gathered x keeps the L1
 __device__ __forceinline__ double ld_stream(const double *p) {
     double v;
@@ -70,6 +75,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+#endif  // !LISB_EMU
 
 // ---- deterministic block reduction (sum or max) ------------------------------------------
 // Fixed shape: xor-shuffle tree inside each warp, then warp 0 combines the per-warp values

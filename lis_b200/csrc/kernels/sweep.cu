@@ -72,6 +72,7 @@ ssor_bwd_kernel(int nrows, const int *__restrict__ rows,
 //   backward: x[i] = w[i] - (sum_{U, in block} U*x[jj]) * wd[i]          (x pre-filled)
 constexpr unsigned long long kNotReady = 0x7ff4c0dedeadbeefull;     // sNaN payload: never a result
 
+#ifndef LISB_EMU
 __device__ __forceinline__ unsigned long long ld_poll(const double *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -80,6 +81,7 @@ __device__ __forceinline__ unsigned long long ld_poll(const double *p) {
 __device__ __forceinline__ void st_publish(double *p, double v) {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
+#endif
 
 __global__ void __launch_bounds__(256)
 fill_not_ready_kernel(int n, double *x)

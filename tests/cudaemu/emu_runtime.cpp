@@ -1,0 +1,313 @@
+/*
+ * emu_runtime.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_emu.h).  The fiber scheduler that runs
+ * one CTA at a time, plus host-memory stand-ins for the handful of CUDA runtime calls the
+ * product's host code and kernel launchers make.  "Device" allocations end flush against a
+ * PROT_NONE guard page, so a kernel that reads or writes past the end of a buffer (beyond the
+ * 16-byte granule) dies with SIGSEGV instead of passing silently.
+ */
+#include "cuda_emu.h"
+#include <stdio.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <unistd.h>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace emu {
+
+ThreadCtx *g_cur = nullptr;
+
+enum State { kRunnable, kAtBlockBarrier, kAtWarpBarrier, kDone };
+
+/* Context switch: on x86-64 a dozen instructions (callee-saved registers + stack pointer);
+ * swapcontext() elsewhere -- it makes a sigprocmask system call per switch, which dominated the
+ * run time of the emulated solver tests. */
+#if defined(__x86_64__)
+#define EMU_ASM_SWITCH 1
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#endif
+
+struct Fiber {
+    ucontext_t ctx;
+    void *sp = nullptr;
+    char *stack = nullptr;
+    ThreadCtx tc;
+    State state = kDone;
+    uint64_t shfl = 0;
+};
+
+static constexpr size_t kStackBytes = 256 * 1024;
+static std::vector<Fiber *> g_fibers;          /* pool, grown on demand */
+static ucontext_t g_sched;
+static void *g_sched_sp = nullptr;
+static Fiber *g_running = nullptr;
+static const std::function<void()> *g_body = nullptr;
+static std::vector<unsigned char> g_dyn_smem;
+static int g_nthreads = 0;
+static unsigned long long g_spins = 0;
+
+[[noreturn]] void fail(const char *what)
+{
+    fprintf(stderr, "cuda_emu: %s", what);
+    if (g_cur) fprintf(stderr, " (block %u, thread %u)", g_cur->bid.x, g_cur->tid.x);
+    fprintf(stderr, "\n");
+    abort();
+}
+
+static inline void switch_to_sched(Fiber *f)
+{
+#ifdef EMU_ASM_SWITCH
+    emu_switch(&f->sp, g_sched_sp);
+#else
+    swapcontext(&f->ctx, &g_sched);
+#endif
+}
+static inline void switch_to_fiber(Fiber *f)
+{
+#ifdef EMU_ASM_SWITCH
+    emu_switch(&g_sched_sp, f->sp);
+#else
+    swapcontext(&g_sched, &f->ctx);
+#endif
+}
+
+static void fiber_entry()
+{
+    (*g_body)();
+    g_running->state = kDone;
+    g_spins = 0;
+    switch_to_sched(g_running);
+    fail("a finished fiber was resumed");
+}
+
+static void to_scheduler()
+{
+    Fiber *f = g_running;
+    switch_to_sched(f);
+    g_cur = &f->tc;
+}
+
+void *dyn_smem() { return g_dyn_smem.data(); }
+
+void sync_block() { g_running->state = kAtBlockBarrier; to_scheduler(); }
+void sync_warp() { g_running->state = kAtWarpBarrier; to_scheduler(); }
+
+void spin_yield()
+{
+    if (++g_spins > 200000000ull) fail("deadlock: threads keep spinning and nothing completes");
+    to_scheduler();
+}
+
+uint64_t shfl_exchange(uint64_t mine, int src_lane)
+{
+    Fiber *f = g_running;
+    f->shfl = mine;
+    sync_warp();                                   /* everyone has published */
+    const int tid = (int)f->tc.tid.x;
+    const int base = tid & ~31;
+    uint64_t v = mine;
+    if (src_lane >= 0 && src_lane < 32 && base + src_lane < g_nthreads) v = g_fibers[base + src_lane]->shfl;
+    sync_warp();                                   /* everyone has read before the next publish */
+    return v;
+}
+
+static void run_block(dim3 grid, dim3 block, unsigned bx)
+{
+    const int nt = (int)(block.x * block.y * block.z);
+    g_nthreads = nt;
+    while ((int)g_fibers.size() < nt) {
+        Fiber *f = new Fiber;
+        f->stack = (char *)mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (f->stack == MAP_FAILED) fail("fiber stack allocation failed");
+        g_fibers.push_back(f);
+    }
+    for (int t = 0; t < nt; ++t) {
+        Fiber *f = g_fibers[t];
+        f->tc.tid = make_uint3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
+        f->tc.bid = make_uint3(bx, 0, 0);
+        f->tc.bdim = block; f->tc.gdim = grid;
+        f->state = kRunnable;
+#ifdef EMU_ASM_SWITCH
+        {
+            /* six callee-saved registers, the entry address `ret` jumps to, one pad slot so that
+             * the entry sees the stack alignment of a called function (rsp = 16k + 8) */
+            void **top = (void **)(((uintptr_t)f->stack + kStackBytes) & ~(uintptr_t)15);
+            void **sp = top - 8;
+            for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+            sp[6] = (void *)fiber_entry;
+            sp[7] = nullptr;
+            f->sp = sp;
+        }
+#else
+        getcontext(&f->ctx);
+        f->ctx.uc_stack.ss_sp = f->stack;
+        f->ctx.uc_stack.ss_size = kStackBytes;
+        f->ctx.uc_link = &g_sched;
+        makecontext(&f->ctx, fiber_entry, 0);
+#endif
+    }
+    for (;;) {
+        int live = 0;
+        for (int t = 0; t < nt; ++t) {
+            Fiber *f = g_fibers[t];
+            if (f->state != kRunnable) continue;
+            g_running = f; g_cur = &f->tc;
+            switch_to_fiber(f);
+        }
+        /* release barriers whose participants have all arrived (exited threads do not count) */
+        int at_block = 0;
+        for (int t = 0; t < nt; ++t) {
+            const State s = g_fibers[t]->state;
+            if (s != kDone) ++live;
+            if (s == kAtBlockBarrier) ++at_block;
+        }
+        if (live == 0) break;
+        bool released = false;
+        if (at_block == live) {
+            for (int t = 0; t < nt; ++t) if (g_fibers[t]->state == kAtBlockBarrier) g_fibers[t]->state = kRunnable;
+            released = true;
+        }
+        for (int w = 0; w < nt; w += 32) {
+            int wl = 0, ww = 0;
+            for (int t = w; t < w + 32 && t < nt; ++t) {
+                const State s = g_fibers[t]->state;
+                if (s != kDone) ++wl;
+                if (s == kAtWarpBarrier) ++ww;
+            }
+            if (wl > 0 && ww == wl) {
+                for (int t = w; t < w + 32 && t < nt; ++t) if (g_fibers[t]->state == kAtWarpBarrier) g_fibers[t]->state = kRunnable;
+                released = true;
+            }
+        }
+        if (released) { g_spins = 0; continue; }
+        bool any_runnable = false;
+        for (int t = 0; t < nt; ++t) if (g_fibers[t]->state == kRunnable) any_runnable = true;
+        if (!any_runnable) fail("deadlock: every live thread of the CTA waits at a barrier that cannot complete (divergent __syncthreads / __syncwarp?)");
+    }
+    g_cur = nullptr; g_running = nullptr;
+}
+
+static std::map<std::string, long> g_launches;      /* kernel expression as written at the launch site -> count */
+
+void launch(const char *name, dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &body)
+{
+    g_launches[name] += 1;
+    if (g_running) fail("nested kernel launch");
+    if (grid.y != 1 || grid.z != 1) fail("only 1-D grids are emulated");
+    const size_t nt = (size_t)block.x * block.y * block.z;
+    if (nt == 0 || nt > 1024) fail("invalid block size");
+    if (dyn_smem_bytes > 227 * 1024) fail("dynamic shared memory exceeds 227 KB");
+    g_dyn_smem.assign(dyn_smem_bytes + 128, 0xA5);
+    g_body = &body;
+    g_spins = 0;
+    for (unsigned b = 0; b < grid.x; ++b) run_block(grid, block, b);
+    g_body = nullptr;
+}
+
+/* ---- guarded "device" memory ---------------------------------------------------------------- */
+struct Alloc { void *base; size_t len; };
+static std::map<void *, Alloc> g_allocs;
+
+static void *guarded_alloc(size_t bytes)
+{
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t user = ((bytes ? bytes : 1) + 15) & ~(size_t)15;
+    const size_t body = (user + page - 1) / page * page;
+    char *base = (char *)mmap(nullptr, body + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return nullptr;
+    mprotect(base + body, page, PROT_NONE);
+    char *p = base + body - user;
+    memset(base, 0xCD, body);                      /* uninitialised device memory is not zero */
+    g_allocs[p] = Alloc{base, body + page};
+    return p;
+}
+
+static void guarded_free(void *p)
+{
+    if (!p) return;
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) { fprintf(stderr, "cuda_emu: cudaFree of an unknown pointer %p\n", p); abort(); }
+    munmap(it->second.base, it->second.len);
+    g_allocs.erase(it);
+}
+
+}  // namespace emu
+
+/* launch log for the tests: how many launches had `substr` in the kernel expression; NULL resets */
+extern "C" long emu_launch_count(const char *substr)
+{
+    if (substr == nullptr) { emu::g_launches.clear(); return 0; }
+    long n = 0;
+    for (auto &kv : emu::g_launches) if (kv.first.find(substr) != std::string::npos) n += kv.second;
+    return n;
+}
+
+/* ---- CUDA runtime stand-ins (host memory; streams and events are ordered by program order) ---- */
+extern "C" {
+
+/* SM count the launchers size their grids with: 148 (B200) by default, so that reduction trees
+ * and persistent grids are the ones the real device gets; LISB_EMU_SMS=2 makes small inputs
+ * exercise the persistent loops (several row blocks per CTA) */
+static int emu_sms()
+{
+    const char *e = getenv("LISB_EMU_SMS");
+    const int v = e ? atoi(e) : 148;
+    return v > 0 ? v : 148;
+}
+
+cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t) { return "emulated device error"; }
+cudaError_t cudaDeviceGetAttribute(int *v, enum cudaDeviceAttr a, int)
+{
+    *v = a == cudaDevAttrMultiProcessorCount ? emu_sms() : 0;
+    return cudaSuccess;
+}
+cudaError_t cudaFuncSetAttribute(const void *, enum cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int) { static int k = 0; *s = (cudaStream_t)(uintptr_t)(0x100 + 16 * ++k); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { static int k = 0; *e = (cudaEvent_t)(uintptr_t)(0x100000 + 16 * ++k); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = emu::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
+cudaError_t cudaFree(void *p) { emu::guarded_free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void *p) { emu::guarded_free(p); return cudaSuccess; }
+cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int) { *d = h; return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemPrefetchAsync(const void *, size_t, int, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
+
+}  // extern "C"

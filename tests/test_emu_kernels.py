@@ -1,0 +1,118 @@
+"""The product's CUDA kernel SOURCES executed on the host emulator (tests/cudaemu: every CUDA
+thread a fiber, inline PTX restated, device buffers ending at guard pages) underneath the
+product's unchanged host code, checked against the oracle with the very assertions of the GPU
+parity tests.
+
+This is not a parity claim for the GPU path and not a CPU fallback (the product library has
+none): it is what lets kernel logic -- indexing, tiling, TMA/mbarrier pipeline phases, alignment
+of 128-bit loads and bulk copies, out-of-bounds reads, the last-CTA fold, the dependency polling
+of the one-launch sweeps -- be checked in the `-m "not gpu"` suite."""
+import os
+import subprocess
+
+import pytest
+
+import harness as H
+import lis_b200
+import test_gpu_parity as G
+
+EMU_DIR = os.path.join(H.ROOT, "tests", "cudaemu")
+
+
+@pytest.fixture(scope="module")
+def b200(built):
+    r = subprocess.run(["make", "-C", EMU_DIR, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return lis_b200.Shim(os.path.join(EMU_DIR, "_build", "liblis_emu_shim.so"))
+
+
+test_spmv_bit_exact = G.test_spmv_bit_exact
+test_spmv_csr_both_kernels = G.test_spmv_csr_both_kernels
+test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
+test_spmv_csr_split_order = G.test_spmv_csr_split_order
+test_spmv_long_rows = G.test_spmv_long_rows
+test_blas1_elementwise_bit_exact = G.test_blas1_elementwise_bit_exact
+test_blas1_length_mismatch_is_ill_arg = G.test_blas1_length_mismatch_is_ill_arg
+test_reductions_bounded = G.test_reductions_bounded
+test_reductions_deterministic = G.test_reductions_deterministic
+test_empty_vector = G.test_empty_vector
+test_get_diagonal = G.test_get_diagonal
+test_psolve_ssor_bit_exact = G.test_psolve_ssor_bit_exact
+test_psolve_ssor_level_launch_path = G.test_psolve_ssor_level_launch_path
+test_psolve_ssor_repeated_sweeps = G.test_psolve_ssor_repeated_sweeps
+test_psolve_jacobi_bit_exact = G.test_psolve_jacobi_bit_exact
+test_bicg_default_solver = G.test_bicg_default_solver
+test_solvers_match_oracle_poisson = G.test_solvers_match_oracle_poisson
+test_solvers_match_oracle_unsymmetric = G.test_solvers_match_oracle_unsymmetric
+test_ssor_block_count_changes_iterations_like_openmp = G.test_ssor_block_count_changes_iterations_like_openmp
+test_solver_formats_give_same_iterations = G.test_solver_formats_give_same_iterations
+test_solver_status_codes = G.test_solver_status_codes
+test_golden_vectors = G.test_golden_vectors
+
+import test_solvers_ext_gpu as E  # noqa: E402
+
+test_further_solver_within_reference_envelope = E.test_further_solver_within_reference_envelope
+test_ilu_and_transposed_sweeps_match_reference_bits = E.test_ilu_and_transposed_sweeps_match_reference_bits
+
+
+# ---- the same SpMV checks with 2 emulated SMs: persistent grids (TMA row-block CSR kernel, BLAS-1
+# grid-stride loops, reductions) then give every CTA several row blocks / many elements
+@pytest.fixture()
+def two_sms(monkeypatch):
+    monkeypatch.setenv("LISB_EMU_SMS", "2")
+
+
+def test_persistent_grids_two_sms(b200, oracle, two_sms, monkeypatch):
+    G.test_spmv_csr_both_kernels(b200, oracle, monkeypatch)
+    G.test_spmv_bit_exact(b200, oracle, "csr")
+    G.test_reductions_bounded(b200, oracle, 100003)
+    G.test_blas1_elementwise_bit_exact(b200, oracle, "axpy", 100003)
+    for opts in ("-i cg -p jacobi", "-i bicgstab -p ssor"):
+        import numpy as np
+        ptr, idx, val = H.poisson3d_7pt(9, 8, 7)
+        b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        r = b200.solve(ptr, idx, val, b, opts)
+        assert r["status"] == 0 and abs(r["x"] - 1.0).max() < 1e-8
+
+
+# ---- the emulator must notice what it exists to notice
+_NEG = r"""
+import ctypes as C, numpy as np, sys
+lib = C.CDLL(sys.argv[1])
+what = sys.argv[2]
+vp = C.c_void_p
+def dev(a):
+    p = vp()
+    assert lib.cudaMalloc(C.byref(p), C.c_size_t(a.nbytes)) == 0
+    C.memmove(p, a.ctypes.data, a.nbytes)
+    return p
+n = 300
+ptr = np.arange(0, 3 * n + 1, 3, dtype=np.int32)
+idx = (np.arange(3 * n) % n).astype(np.int32)
+val = np.ones(3 * n)
+x = np.ones(n); y = np.zeros(n)
+d_ptr = dev(np.concatenate([ptr, np.zeros(4, np.int32)]))
+d_idx = dev(np.concatenate([idx, np.zeros(8, np.int32)])); d_val = dev(np.concatenate([val, np.zeros(8)]))
+d_x = dev(x); d_y = dev(y[:n - 8] if what == "short_y" else y)
+lib.lisb200_spmv_csr_tma.argtypes = [C.c_int] * 4 + [vp] * 6
+if what == "misaligned_ptr":
+    d_ptr = vp(d_ptr.value + 4)
+rc = lib.lisb200_spmv_csr_tma(n - (1 if what == "misaligned_ptr" else 0), 256, 1024, 2, d_ptr, d_idx, d_val, d_x, d_y, None)
+print("rc", rc)
+"""
+
+
+@pytest.mark.parametrize("what,expect", [("ok", 0), ("misaligned_ptr", "abort"), ("short_y", "segv")])
+def test_emulator_catches_misalignment_and_overrun(b200, what, expect):
+    """a TMA bulk copy from a 4-byte-aligned row-pointer slice aborts; an output vector
+    that is 8 entries short makes the kernel write into the guard page behind it"""
+    import signal
+    import sys
+    r = subprocess.run([sys.executable, "-c", _NEG, os.path.join(EMU_DIR, "_build", "liblis_emu.so"), what],
+                       capture_output=True, text=True)
+    if expect == 0:
+        assert r.returncode == 0 and "rc 0" in r.stdout, r.stderr
+    elif expect == "abort":
+        assert r.returncode == -signal.SIGABRT and "not 16-byte aligned" in r.stderr, (r.returncode, r.stderr)
+    else:
+        assert r.returncode == -signal.SIGSEGV, (r.returncode, r.stderr)
