@@ -488,6 +488,37 @@ def run_b200(args, grid):
     cg_it_s = done / od[2] if od[2] > 0 else None
     log(f"CG+Jacobi: {done} iterations in {od[2]:.3f}s solver time -> {cg_it_s:.1f} it/s (lis_solve wall {od[4]:.3f}s)")
 
+    # ---- e2e again through lis_b200_matvec_host: copy-in, product and copy-out overlapped chunk by
+    # chunk on three streams.  Runs last and is adopted only if it reproduces the bits of the
+    # three-call sequence, so a problem here can cost the overlap but never the bench line.
+    e2e_seq_s, e2e_what = e2e_s, "lis_vector_scatter(pinned host x) + lis_matvec + lis_vector_gather(pinned host y) per step"
+    try:
+        Ls.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        hy_seq = hy.clone()
+        hy.zero_()
+        for _ in range(max(args.warmup, 1)):
+            rc = Ls.shim_mv_step_e2e_pipelined(h, hx.data_ptr(), hy.data_ptr())
+            if rc != 0:
+                raise RuntimeError(f"lis_b200_matvec_host returned {rc}")
+        torch.cuda.synchronize()
+        if not torch.equal(hy.view(torch.int64), hy_seq.view(torch.int64)):
+            raise RuntimeError("overlapped product differs from the three-call sequence")
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rc = Ls.shim_mv_step_e2e_pipelined(h, hx.data_ptr(), hy.data_ptr())
+            if rc != 0:
+                raise RuntimeError(f"lis_b200_matvec_host returned {rc}")
+        torch.cuda.synchronize()
+        e2e_pipe_s = (time.perf_counter() - t0) / e2e_steps
+        log(f"e2e overlapped (lis_b200_matvec_host): {2.0 * nnz / e2e_pipe_s / 1e9:.1f} GFLOP/s "
+            f"({8.0 * n / e2e_pipe_s / 1e9:.1f} GB/s each way) vs {2.0 * nnz / e2e_seq_s / 1e9:.1f} sequential")
+        if e2e_pipe_s < e2e_s:
+            e2e_s = e2e_pipe_s
+            e2e_what = ("lis_b200_matvec_host(A, pinned host x, x, y, pinned host y): copy-in, product and copy-out "
+                        "overlapped chunk-wise on three streams; same bits as scatter + lis_matvec + gather (checked)")
+    except Exception as e:  # keep the sequential number
+        log(f"overlapped e2e path not used: {e!r}")
+
     out = None
     if rank == 0:
         gf = 2.0 * nnz / res["csr_s"] / 1e9
@@ -499,7 +530,7 @@ def run_b200(args, grid):
             "config": {"workload": f"spmvtest3 {grid}^3 7-pt Poisson, CSR, rows sorted (n={n}, nnz={nnz})",
                        "l2": "inputs (13.9 GB/step) exceed L2 by >100x, no flush between steps", "index": "int32"},
             "e2e": {"value": 2.0 * nnz / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                    "what": "lis_vector_scatter(pinned host x) + lis_matvec + lis_vector_gather(pinned host y) per step"},
+                    "what": e2e_what},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false>", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
                          "frac": ach / peak_gbs,
@@ -516,6 +547,7 @@ def run_b200(args, grid):
                 "csr_product_tile_kernel_gflops": 2.0 * nnz / res["csr_tile_s"] / 1e9,
                 "csr_product_tile_kernel_gbs": bytes_csr / res["csr_tile_s"] / 1e9,
                 "lis_matvec_api_gflops": 2.0 * nnz / api_s / 1e9,
+                "e2e_three_calls_gflops": 2.0 * nnz / e2e_seq_s / 1e9,
                 "cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": cg_iters,
                 "cg_unfused_formula_gbs": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9 if cg_it_s else None,
                 "nrm2_Ax": nrm.value,

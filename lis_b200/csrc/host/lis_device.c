@@ -17,6 +17,10 @@ typedef struct {
     unsigned int *counter;
     double *h_scalar, *d_scalar;
     double *dev_scalars, *h_fetch;     /* device-resident reduction results + pinned landing zone */
+    /* copy pipeline (lisd_pipe_*): one stream per PCIe direction + per-chunk events */
+    cudaStream_t s_in, s_out;
+    cudaEvent_t *ev; int nev;
+    cudaEvent_t ev_fork, ev_join;
 } lisd_ctx_t;
 
 static lisd_ctx_t g_ctx;
@@ -90,6 +94,9 @@ void lisd_shutdown(void)
     if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
     if (g_ctx.dev_scalars) cudaFree(g_ctx.dev_scalars);
     if (g_ctx.h_fetch) cudaFreeHost(g_ctx.h_fetch);
+    for (int i = 0; i < g_ctx.nev; i++) cudaEventDestroy(g_ctx.ev[i]);
+    free(g_ctx.ev);
+    if (g_ctx.s_in) { cudaEventDestroy(g_ctx.ev_fork); cudaEventDestroy(g_ctx.ev_join); cudaStreamDestroy(g_ctx.s_in); cudaStreamDestroy(g_ctx.s_out); }
     cudaStreamDestroy(g_ctx.stream);
     memset(&g_ctx, 0, sizeof(g_ctx));
 }
@@ -229,6 +236,67 @@ LIS_INT lisd_memset(void *dst, int byte, size_t bytes)
     if (bytes == 0) return LIS_SUCCESS;
     g_ctx.busy = 1;
     return lisd_check((int)cudaMemsetAsync(dst, byte, bytes, g_ctx.stream), "memset");
+}
+
+/* ---- copy pipeline ---------------------------------------------------------------------------
+ * Host -> device on one stream, kernels on the main stream, device -> host on a third, chained
+ * by events per chunk, so that both PCIe directions and the SMs work at the same time
+ * (lis_b200_matvec_host).  Chunk c uses events 2c (its input has landed) and 2c+1 (its kernel
+ * has finished). */
+LIS_INT lisd_pipe_begin(int nchunks)
+{
+    cudaError_t e = cudaSuccess;
+    if (g_ctx.s_in == NULL) {
+        e = cudaStreamCreateWithFlags(&g_ctx.s_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_ctx.s_out, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ctx.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ctx.ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) { g_ctx.s_in = NULL; return lisd_check((int)e, "copy pipeline setup"); }
+    }
+    if (2 * nchunks > g_ctx.nev) {
+        cudaEvent_t *nv = (cudaEvent_t *)realloc(g_ctx.ev, sizeof(cudaEvent_t) * (size_t)(2 * nchunks));
+        if (nv == NULL) { LIS_SETERR_MEM(2 * nchunks * sizeof(cudaEvent_t)); return LIS_OUT_OF_MEMORY; }
+        g_ctx.ev = nv;
+        while (g_ctx.nev < 2 * nchunks) {
+            e = cudaEventCreateWithFlags(&g_ctx.ev[g_ctx.nev], cudaEventDisableTiming);
+            if (e != cudaSuccess) return lisd_check((int)e, "copy pipeline setup");
+            g_ctx.nev++;
+        }
+    }
+    /* the incoming copies overwrite a vector that work already queued on the main stream may
+     * still read: the copy stream starts behind it */
+    e = cudaEventRecord(g_ctx.ev_fork, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.s_in, g_ctx.ev_fork, 0);
+    return lisd_check((int)e, "copy pipeline");
+}
+
+LIS_INT lisd_pipe_h2d(int c, void *dst, const void *src, size_t bytes)
+{
+    cudaError_t e = bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.s_in) : cudaSuccess;
+    if (e == cudaSuccess) e = cudaEventRecord(g_ctx.ev[2 * c], g_ctx.s_in);
+    return lisd_check((int)e, "host to device copy");
+}
+
+LIS_INT lisd_pipe_wait_in(int c)
+{
+    return lisd_check((int)cudaStreamWaitEvent(g_ctx.stream, g_ctx.ev[2 * c], 0), "copy pipeline");
+}
+
+LIS_INT lisd_pipe_d2h(int c, void *dst, const void *src, size_t bytes)
+{
+    cudaError_t e = cudaEventRecord(g_ctx.ev[2 * c + 1], g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.s_out, g_ctx.ev[2 * c + 1], 0);
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.s_out);
+    return lisd_check((int)e, "device to host copy");
+}
+
+/* the main stream continues behind the last outgoing copy; one lisd_sync() then covers all three */
+LIS_INT lisd_pipe_end(void)
+{
+    cudaError_t e = cudaEventRecord(g_ctx.ev_join, g_ctx.s_out);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.stream, g_ctx.ev_join, 0);
+    g_ctx.busy = 1;
+    return lisd_check((int)e, "copy pipeline");
 }
 
 /* ---- vector residency ---------------------------------------------------------------------

@@ -38,6 +38,13 @@ LIS_INT lisd_upload(void *dst, const void *src, size_t bytes);      /* H2D, sync
 LIS_INT lisd_download(void *dst, const void *src, size_t bytes);    /* D2H, synchronous */
 LIS_INT lisd_memset(void *dst, int byte, size_t bytes);
 
+/* ---- copy pipeline: H2D stream -> main stream -> D2H stream, chained per chunk by events ---- */
+LIS_INT lisd_pipe_begin(int nchunks);                                   /* copy-in stream starts behind the main stream */
+LIS_INT lisd_pipe_h2d(int c, void *dst, const void *src, size_t bytes); /* queue chunk c's input */
+LIS_INT lisd_pipe_wait_in(int c);                                       /* main stream waits for chunk c's input */
+LIS_INT lisd_pipe_d2h(int c, void *dst, const void *src, size_t bytes); /* after what the main stream holds now */
+LIS_INT lisd_pipe_end(void);                                            /* main stream joins the copy-out stream */
+
 /* ---- vectors: residency tracking of managed storage ---- */
 LIS_INT lisd_vec_device(LIS_VECTOR v);              /* make resident before a kernel touches it */
 void    lisd_vec_host(LIS_VECTOR v);                /* host is about to read/write v->value */
@@ -77,6 +84,10 @@ typedef struct lisd_matrix {
     double *wd;               /* WD (scaled + inverted diagonal), when present */
     void *sweep;              /* SSOR level schedule (lis_precon.c), built on first psolve */
     void *sweep_global;       /* one-block schedule for LIS_MATRIX_LOWER when `sweep` is blocked */
+    /* row chunks of the pipelined host-buffer product (lis_b200_matvec_host), built on first use:
+     * rows [pipe_row[c], pipe_row[c+1]) read no x entry beyond chunk pipe_need[c] */
+    int pipe_n;
+    int *pipe_row, *pipe_need;
     /* transposed mirrors for lis_matvech (BiCG), built on first use */
     int has_t;
     lisd_csr csrT, LT, UT;

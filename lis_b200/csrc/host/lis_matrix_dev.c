@@ -68,6 +68,7 @@ static void mirror_free(lisd_matrix *M)
     lisd_free(M->idx); lisd_free(M->off); lisd_free(M->jptr); lisd_free(M->perm);
     lisd_free(M->bptr); lisd_free(M->bidx); lisd_free(M->val);
     lisd_free(M->diag); lisd_free(M->wd);
+    free(M->pipe_row); free(M->pipe_need);
     if (M->sweep) lisd_sweep_free(M->sweep);
     if (M->sweep_global) lisd_sweep_free(M->sweep_global);
     free(M);
@@ -285,6 +286,115 @@ LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     err = lisd_matvec(A, x, y);
     if (err) return err;
     return lisd_sync();
+}
+
+/* ------------------------------------------------------------------ y = A x with HOST x and y
+ * What an application that keeps its vectors in host arrays pays per product is two PCIe
+ * transfers around a 2 ms kernel; done one after the other (lis_vector_scatter, lis_matvec,
+ * lis_vector_gather) the link is idle in one direction at any time.  Here the rows are cut into
+ * chunks, and chunk c's product starts as soon as the x entries its rows read have landed, its y
+ * slice leaving while later x chunks are still arriving: both directions of the link and the SMs
+ * overlap.  For a banded matrix (stencils: the band is one grid plane) a chunk needs x up to the
+ * next chunk only; a matrix whose rows read all of x degenerates to copy-in, then products
+ * overlapped with copy-out.  Every row is still summed by the same kernel in the same order:
+ * x, y, host_y hold the same bits as after the three separate calls.
+ * Unsplit CSR on one process; anything else takes the three calls. */
+#define LISD_PIPE_MIN_ROWS  (1 << 18)       /* 2 MiB of x per chunk at least */
+#define LISD_PIPE_MAX_CHUNKS 32
+
+static LIS_INT pipe_plan(LIS_MATRIX A, lisd_matrix *M)
+{
+    const int n = A->n;
+    int nch = n / LISD_PIPE_MIN_ROWS;
+    const char *force = getenv("LIS_B200_PIPE_CHUNKS");     /* tests: chunking at small n */
+    if (nch > LISD_PIPE_MAX_CHUNKS) nch = LISD_PIPE_MAX_CHUNKS;
+    if (force && atoi(force) > 0) nch = atoi(force);
+    if (nch > n / 4) nch = n / 4;
+    if (nch < 2) { M->pipe_n = -1; return LIS_SUCCESS; }       /* too small to be worth cutting */
+    /* chunk boundaries on multiples of 1024 rows: row-pointer slices stay 16-byte aligned for the
+     * bulk copies and a chunk's row blocks coincide with the whole-matrix ones the TMA plan was
+     * made for (forced small chunks in tests: multiples of the row-block size) */
+    const int align = (force && atoi(force) > 0) ? (M->csr.tma_rows ? M->csr.tma_rows : 4) : 1024;
+    int rows = ((n + nch - 1) / nch + align - 1) / align * align;
+    nch = (n + rows - 1) / rows;
+    if (nch < 2) { M->pipe_n = -1; return LIS_SUCCESS; }
+    M->pipe_row = (int *)malloc(sizeof(int) * (size_t)(nch + 1));
+    M->pipe_need = (int *)malloc(sizeof(int) * (size_t)nch);
+    if (!M->pipe_row || !M->pipe_need) { LIS_SETERR_MEM(nch * sizeof(int)); return LIS_OUT_OF_MEMORY; }
+    for (int c = 0; c <= nch; c++) M->pipe_row[c] = (long long)c * rows < n ? c * rows : n;
+    for (int c = 0; c < nch; c++) {
+        LIS_INT mx = 0;
+        const LIS_INT *idx = A->index;
+        for (LIS_INT j = A->ptr[M->pipe_row[c]]; j < A->ptr[M->pipe_row[c + 1]]; j++) if (idx[j] > mx) mx = idx[j];
+        M->pipe_need[c] = mx / rows < nch ? mx / rows : nch - 1;
+    }
+    M->pipe_n = nch;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_b200_matvec_host(LIS_MATRIX A, LIS_SCALAR host_x[], LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR host_y[])
+{
+    LIS_INT err = lis_host_matrix_check_input(A);
+    if (err) return err;
+    if (A->n != x->n || A->n != y->n) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_b200_matvec_host: sizes of A, x and y do not match\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    if (x == y || x->value == y->value) { LIS_SETERR(LIS_ERR_ILL_ARG, "lis_b200_matvec_host: x and y must not alias\n"); return LIS_ERR_ILL_ARG; }
+    err = lisd_require("lis_b200_matvec_host");
+    if (err) return err;
+    lisd_matrix *M;
+    err = lisd_matrix_get(A, &M);
+    if (err) return err;
+    int pipelined = A->matrix_type == LIS_MATRIX_CSR && !M->splited && A->nprocs == 1 && A->np == A->n &&
+                    x->b200_managed && y->b200_managed;
+    if (pipelined && M->pipe_n == 0) { err = pipe_plan(A, M); if (err) return err; }
+    if (!pipelined || M->pipe_n < 2) {
+        err = lis_vector_scatter(host_x, x);
+        if (!err) err = lis_matvec(A, x, y);
+        if (!err) err = lis_vector_gather(y, host_y);
+        return err;
+    }
+    err = lisd_vec_device(x);
+    if (!err) err = lisd_vec_device(y);
+    if (!err) err = lisd_pipe_begin(M->pipe_n);
+    if (err) return err;
+    const int *row = M->pipe_row;
+    for (int c = 0; c < M->pipe_n && !err; c++)
+        err = lisd_pipe_h2d(c, x->value + row[c], host_x + row[c], (size_t)(row[c + 1] - row[c]) * sizeof(LIS_SCALAR));
+    int landed = -1;                                  /* inputs the main stream already waits for */
+    void *st = lisd_stream();
+    for (int c = 0; c < M->pipe_n && !err; c++) {
+        const int nr = row[c + 1] - row[c];
+        int rc;
+        if (M->pipe_need[c] > landed) { landed = M->pipe_need[c]; err = lisd_pipe_wait_in(landed); if (err) break; }
+        if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(nr, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr + row[c], M->csr.idx, M->csr.val, x->value, y->value + row[c], st);
+        else rc = lisb200_spmv_csr(nr, M->csr.ptr + row[c], M->csr.idx, M->csr.val, x->value, y->value + row[c], st);
+        lisd_mark_busy();
+        err = lisd_check(rc, "lis_b200_matvec_host");
+        if (!err) err = lisd_pipe_d2h(c, host_y + row[c], y->value + row[c], (size_t)nr * sizeof(LIS_SCALAR));
+    }
+    /* x chunks nobody waited for (beyond every row's reach) still have to land before x is used again */
+    if (!err && landed < M->pipe_n - 1) err = lisd_pipe_wait_in(M->pipe_n - 1);
+    {
+        LIS_INT e2 = lisd_pipe_end();
+        if (!err) err = e2;
+    }
+    {
+        LIS_INT e2 = lisd_sync();
+        if (!err) err = e2;
+    }
+    return err;
+}
+
+/* the chunking lis_b200_matvec_host uses for A (tests): returns the chunk count (0: not chunked),
+ * fills up to cap+1 row bounds and cap `need` entries */
+LIS_INT lis_b200_matvec_host_plan(LIS_MATRIX A, LIS_INT cap, LIS_INT *rows, LIS_INT *need)
+{
+    lisd_matrix *M = (lisd_matrix *)A->b200_dev;
+    if (M == NULL || M->pipe_n < 2) return 0;
+    for (int c = 0; c < M->pipe_n && c < cap; c++) { rows[c] = M->pipe_row[c]; rows[c + 1] = M->pipe_row[c + 1]; need[c] = M->pipe_need[c]; }
+    return M->pipe_n;
 }
 
 /* ------------------------------------------------------------------ y = A^H x

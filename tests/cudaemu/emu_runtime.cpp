@@ -289,22 +289,76 @@ cudaError_t cudaDeviceGetAttribute(int *v, enum cudaDeviceAttr a, int)
     return cudaSuccess;
 }
 cudaError_t cudaFuncSetAttribute(const void *, enum cudaFuncAttribute, int) { return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int) { static int k = 0; *s = (cudaStream_t)(uintptr_t)(0x100 + 16 * ++k); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+/* Streams.  The first stream created (the library's main stream) and the kernels run eagerly, in
+ * program order.  Every OTHER stream is lazy: its copies are queued and carried out as late as
+ * the CUDA ordering rules allow -- when somebody waits on an event recorded behind them, or
+ * synchronises the stream.  A kernel that reads a buffer without waiting for the event of the
+ * copy that fills it therefore sees stale data here, and a kernel that overwrites a buffer whose
+ * outgoing copy is still queued corrupts that copy: missing cross-stream dependencies fail the
+ * tests instead of being hidden by a synchronous emulation. */
+struct EmuOp { void *dst; const void *src; size_t n; cudaEvent_t marker; };
+static cudaStream_t g_main_stream = nullptr;
+static std::map<cudaStream_t, std::vector<EmuOp>> g_lazy;     /* pending operations per lazy stream */
+static std::map<cudaEvent_t, cudaStream_t> g_event_on;        /* event -> lazy stream it is pending on */
+
+static void emu_flush(cudaStream_t s, cudaEvent_t upto)
+{
+    auto it = g_lazy.find(s);
+    if (it == g_lazy.end()) return;
+    std::vector<EmuOp> &q = it->second;
+    size_t k = 0;
+    for (; k < q.size(); ++k) {
+        if (q[k].marker) {
+            g_event_on.erase(q[k].marker);
+            if (q[k].marker == upto) { ++k; break; }
+        } else {
+            memmove(q[k].dst, q[k].src, q[k].n);
+        }
+    }
+    q.erase(q.begin(), q.begin() + (long)k);
+}
+static void emu_flush_all() { for (auto &kv : g_lazy) emu_flush(kv.first, nullptr); }
+static bool emu_is_lazy(cudaStream_t s) { return s != nullptr && s != g_main_stream; }
+
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int)
+{
+    static int k = 0;
+    *s = (cudaStream_t)(uintptr_t)(0x100 + 16 * ++k);
+    if (g_main_stream == nullptr) g_main_stream = *s;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { emu_flush(s, nullptr); return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { emu_flush_all(); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { emu_flush(s, nullptr); g_lazy.erase(s); if (s == g_main_stream) g_main_stream = nullptr; return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned int)
+{
+    auto it = g_event_on.find(e);
+    if (it != g_event_on.end()) emu_flush(it->second, e);
+    return cudaSuccess;
+}
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { static int k = 0; *e = (cudaEvent_t)(uintptr_t)(0x100000 + 16 * ++k); return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
+{
+    auto it = g_event_on.find(e);
+    if (it != g_event_on.end()) emu_flush(it->second, e);            /* re-recording: the old one is done with */
+    if (emu_is_lazy(s) && !g_lazy[s].empty()) { g_lazy[s].push_back(EmuOp{nullptr, nullptr, 0, e}); g_event_on[e] = s; }
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { return cudaStreamWaitEvent(nullptr, e, 0); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { cudaStreamWaitEvent(nullptr, e, 0); return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = emu::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
-cudaError_t cudaFree(void *p) { emu::guarded_free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p) { emu_flush_all(); emu::guarded_free(p); return cudaSuccess; }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
-cudaError_t cudaFreeHost(void *p) { emu::guarded_free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void *p) { emu_flush_all(); emu::guarded_free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int) { *d = h; return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t st)
+{
+    if (emu_is_lazy(st)) g_lazy[st].push_back(EmuOp{d, s, n, nullptr});
+    else memmove(d, s, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) { emu_flush_all(); memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemPrefetchAsync(const void *, size_t, int, cudaStream_t) { return cudaSuccess; }

@@ -28,6 +28,10 @@ cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int f) { (void)f; *s = (cudaStream_t)0x1; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void)s; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { (void)s; return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned int f) { (void)s; (void)e; (void)f; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int f) { (void)f; *e = (cudaEvent_t)0x2; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { (void)e; (void)s; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { (void)e; return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int f) { (void)f; return cudaMalloc(p, n); }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }

@@ -559,6 +559,32 @@ EXPORT int shim_mv_step_e2e(int h, double *host_x, double *host_y)
     return (int)lis_vector_gather(g_mv[h].y, host_y);
 }
 
+/* the same step through lis_b200's overlapped host-buffer product (lis_b200 builds only; the
+ * reference has one address space and nothing to overlap) */
+EXPORT int shim_mv_step_e2e_pipelined(int h, double *host_x, double *host_y)
+{
+#ifdef LIS_B200_LIS_H
+    return (int)lis_b200_matvec_host(g_mv[h].A, host_x, g_mv[h].x, g_mv[h].y, host_y);
+#else
+    return shim_mv_step_e2e(h, host_x, host_y);
+#endif
+}
+EXPORT int shim_mv_host_plan(int h, int cap, int *rows, int *need)
+{
+#ifdef LIS_B200_LIS_H
+    return (int)lis_b200_matvec_host_plan(g_mv[h].A, cap, rows, need);
+#else
+    (void)h; (void)cap; (void)rows; (void)need;
+    return 0;
+#endif
+}
+EXPORT int shim_mv_get_xy(int h, double *x_out, double *y_out)
+{
+    LIS_INT err = lis_vector_gather(g_mv[h].x, x_out);
+    if (!err) err = lis_vector_gather(g_mv[h].y, y_out);
+    return (int)err;
+}
+
 /* `iters` products with resident vectors, wall seconds by lis_wtime (the drivers' own timing) */
 EXPORT int shim_mv_run(int h, int iters, double *seconds, double *nrm2)
 {

@@ -116,3 +116,10 @@ def test_emulator_catches_misalignment_and_overrun(b200, what, expect):
         assert r.returncode == -signal.SIGABRT and "not 16-byte aligned" in r.stderr, (r.returncode, r.stderr)
     else:
         assert r.returncode == -signal.SIGSEGV, (r.returncode, r.stderr)
+
+
+# ---- the overlapped host-buffer product (lis_b200_matvec_host): three streams chained by events.
+# The emulator's secondary streams are lazy (copies happen as late as the events allow), so a row
+# chunk that starts before its x entries have landed reads the previous contents of x.
+test_matvec_host_pipelined = G.test_matvec_host_pipelined
+test_matvec_host_pipelined_default_chunks = G.test_matvec_host_pipelined_default_chunks

@@ -107,6 +107,91 @@ def test_blas1_elementwise_bit_exact(b200, oracle, op, n):
         H.assert_bits_equal(b_, ob, f"{op}(b) n={n}")
 
 
+@pytest.mark.parametrize("kernel", ["tma", "tile"])
+@pytest.mark.parametrize("case", ["banded", "stencil27", "full_reach", "ragged"])
+def test_matvec_host_pipelined(b200, oracle, monkeypatch, kernel, case):
+    """lis_b200_matvec_host (copy-in, product, copy-out overlapped chunk-wise on three streams) leaves
+    host_y, x and y with the bits of lis_vector_scatter + lis_matvec + lis_vector_gather, and its
+    chunk plan never lets a row start before the x entries it reads have landed"""
+    import ctypes as C
+    monkeypatch.setenv("LIS_B200_CSR_KERNEL", kernel)
+    monkeypatch.setenv("LIS_B200_PIPE_CHUNKS", "7")
+    if case == "banded":
+        ptr, idx, val = H.random_csr(5000, 5, 12, band=300, sorted_rows=True)
+    elif case == "stencil27":
+        ptr, idx, val = H.poisson3d_27pt(15, 14, 13)
+    elif case == "full_reach":
+        ptr, idx, val = H.random_csr(3000, 6, 5, values="wide")
+    else:
+        ptr, idx, val = H.random_csr(2600, 4, 13, empty_rows=True, diag_dominant=False)
+    n = len(ptr) - 1
+    L = b200.lib
+    vp = C.c_void_p
+    L.shim_mv_open.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.shim_mv_step_e2e.argtypes = [C.c_int, vp, vp]
+    L.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, vp, vp]
+    L.shim_mv_host_plan.argtypes = [C.c_int, C.c_int, vp, vp]
+    L.shim_mv_get_xy.argtypes = [C.c_int, vp, vp]
+    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
+    assert h >= 0
+    try:
+        for seed in (1, 2, 3):                      # x changes between calls: stale reads would show
+            hx = H.rand_vec(n, seed, "wide")
+            hy = np.full(n, np.nan)
+            assert L.shim_mv_step_e2e_pipelined(h, hx.ctypes.data, hy.ctypes.data) == 0
+            want = oracle.spmv("csr", ptr, idx, val, hx)
+            H.assert_bits_equal(hy, want, f"pipelined {case}/{kernel} seed {seed}")
+            xo = np.empty(n); yo = np.empty(n)
+            assert L.shim_mv_get_xy(h, xo.ctypes.data, yo.ctypes.data) == 0
+            H.assert_bits_equal(xo, hx, "x vector after the pipelined product")
+            H.assert_bits_equal(yo, want, "y vector after the pipelined product")
+            hy2 = np.full(n, np.nan)
+            assert L.shim_mv_step_e2e(h, hx.ctypes.data, hy2.ctypes.data) == 0
+            H.assert_bits_equal(hy2, want, "three separate calls")
+        rows = np.zeros(65, np.int32); need = np.zeros(64, np.int32)
+        nch = L.shim_mv_host_plan(h, 64, rows.ctypes.data, need.ctypes.data)
+        assert nch >= 2, nch
+        assert rows[0] == 0 and rows[nch] == n and np.all(np.diff(rows[:nch + 1]) > 0)
+        for c in range(nch):                         # no row of chunk c reads beyond x chunk need[c]
+            cols = idx[ptr[rows[c]]:ptr[rows[c + 1]]]
+            if len(cols):
+                assert cols.max() < rows[need[c] + 1], (c, cols.max(), rows[need[c] + 1])
+        if case in ("banded", "stencil27"):
+            assert np.all(need[:nch - 1] <= np.arange(nch - 1) + 1), need[:nch]   # band: next chunk at most
+    finally:
+        L.shim_mv_close(h)
+
+
+def test_matvec_host_pipelined_default_chunks(b200, oracle):
+    """the chunking the library picks by itself (>= 2^18 rows per chunk, boundaries on multiples of
+    1024 rows) on a 1.3 M-row stencil: same bits as the oracle and as the three-call sequence"""
+    import ctypes as C
+    ptr, idx, val = H.poisson3d_7pt(128, 128, 80, sort=True)
+    n = len(ptr) - 1
+    L = b200.lib
+    vp = C.c_void_p
+    L.shim_mv_open.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.shim_mv_step_e2e.argtypes = [C.c_int, vp, vp]
+    L.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, vp, vp]
+    L.shim_mv_host_plan.argtypes = [C.c_int, C.c_int, vp, vp]
+    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
+    assert h >= 0
+    try:
+        for seed in (5, 6):
+            hx = H.rand_vec(n, seed, "wide")
+            hy = np.full(n, np.nan); hy2 = np.full(n, np.nan)
+            assert L.shim_mv_step_e2e_pipelined(h, hx.ctypes.data, hy.ctypes.data) == 0
+            assert L.shim_mv_step_e2e(h, hx.ctypes.data, hy2.ctypes.data) == 0
+            H.assert_bits_equal(hy, hy2, "overlapped vs three calls")
+            H.assert_bits_equal(hy, oracle.spmv("csr", ptr, idx, val, hx), "overlapped vs oracle")
+        rows = np.zeros(65, np.int32); need = np.zeros(64, np.int32)
+        nch = L.shim_mv_host_plan(h, 64, rows.ctypes.data, need.ctypes.data)
+        assert nch == 5 and np.all(rows[1:nch] % 1024 == 0), (nch, rows[:nch + 1])
+        assert list(need[:nch]) == [1, 2, 3, 4, 4]           # a 7-point row reaches one grid plane ahead
+    finally:
+        L.shim_mv_close(h)
+
+
 def test_blas1_length_mismatch_is_ill_arg(b200):
     for op in ("axpy", "xpay", "copy", "dot"):
         assert b200.vec_mismatch(op) == 1          # LIS_ERR_ILL_ARG, lis_vector_opv.c:158-163
