@@ -120,6 +120,30 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unavailable: {e!r}"], "samples": 0}
 
 
+# ----------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa_node(torch, gpu_index):
+    """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off:
+    with 8 ranks on a two-socket host, buffers on the far socket put every copy on the
+    inter-socket link.  Best effort -- containers often hide the topology (numa_node = -1)."""
+    try:
+        pr = torch.cuda.get_device_properties(gpu_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- matrices
 def poisson7_host(l, m, n, k0=0, k1=None, ktot=None):
     """test/spmvtest3.c:142-157 rows (then sorted by column, :192-195) for planes [k0,k1) of an
@@ -290,6 +314,38 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     nnz_all = torch.tensor([nnz], device=dev, dtype=torch.int64)
     dist.all_reduce(nnz_all)
     nnz_g = int(nnz_all.item())
+    # e2e again through lis_b200_matvec_host (copy-in / product / copy-out overlapped); adopted only if
+    # every rank reproduces the bits of the three-call sequence.  Every rank takes the same branches:
+    # the call contains the halo exchange.
+    e2e_seq_s = e2e_s
+    e2e_what = "per rank: local x slice from pinned host + lis_matvec (halo exchange inside) + local y slice to pinned host"
+    Ls.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    hy_seq = hy.clone(); hy.zero_()
+    ok = 1
+    for _ in range(2):
+        if Ls.shim_mv_step_e2e_pipelined(h, hx.data_ptr(), hy.data_ptr()) != 0:
+            ok = 0
+    torch.cuda.synchronize()
+    if ok and not torch.equal(hy.view(torch.int64), hy_seq.view(torch.int64)):
+        ok = 0
+    t = torch.tensor([ok], device=dev, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 1:
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            Ls.shim_mv_step_e2e_pipelined(h, hx.data_ptr(), hy.data_ptr())
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_pipe_s = float(t.item()) / e2e_steps
+        log(f"[rank {rank}] e2e overlapped {2.0 * nnz_g / e2e_pipe_s / 1e9:.1f} GFLOP/s vs {2.0 * nnz_g / e2e_seq_s / 1e9:.1f} three calls")
+        if e2e_pipe_s < e2e_s:
+            e2e_s = e2e_pipe_s
+            e2e_what = ("per rank: lis_b200_matvec_host on the local slices -- copy-in, product (halo exchange inside) and "
+                        "copy-out overlapped chunk-wise on three streams; same bits as the three-call sequence (checked)")
+    else:
+        log(f"[rank {rank}] overlapped e2e path not used (ok={ok})")
     lib.lis_finalize()
     if rank != 0:
         return None
@@ -304,13 +360,13 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
                    "l2": "inputs (13.9 GB/step/GPU) exceed L2 by >100x, no flush between steps", "index": "int32 (local numbering + halo)",
                    "exchange": "2 boundary planes (2 MiB each) per product via grouped ncclSend/ncclRecv; dot partials via ncclAllGather"},
         "e2e": {"value": 2.0 * nnz_g / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                "what": "per rank: local x slice from pinned host + lis_matvec (halo exchange inside) + local y slice to pinned host"},
+                "what": e2e_what},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false> (+ halo pack, NCCL p2p)", "achieved": bytes_local / step_s / 1e9,
                      "peak": peak_gbs, "unit": "GB/s", "frac": bytes_local / step_s / 1e9 / peak_gbs, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "note": "per GPU, whole product incl. halo exchange"},
         "clocks": clocks,
-        "extra": {"cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": done,
+        "extra": {"cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": done, "e2e_three_calls_gflops": 2.0 * nnz_g / e2e_seq_s / 1e9,
                   "cg_unfused_formula_gbs_per_gpu": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9},
     }
 
@@ -343,6 +399,9 @@ def run_b200(args, grid):
         raise SystemExit("bench.py --impl lis_b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    node = bind_to_gpu_numa_node(torch, local)
+    if node is not None:
+        log(f"[rank {rank}] bound to NUMA node {node} of GPU {local} ({len(os.sched_getaffinity(0))} cpus)")
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -501,7 +501,8 @@ LIS_INT lis_b200_commtable_info(LIS_MATRIX A, LIS_INT *out, LIS_INT *import_ptr,
 /* y = A x for an application whose vectors live in host arrays: the same result as
  * lis_vector_scatter(host_x, x); lis_matvec(A, x, y); lis_vector_gather(y, host_y) -- x, y and
  * host_y end up with the same bits -- but copy-in, product and copy-out run chunk-wise
- * overlapped on three streams (pin host_x/host_y for the copies to be asynchronous) */
+ * overlapped on three streams (pin host_x/host_y for the copies to be asynchronous).  On a
+ * row-partitioned matrix host_x / host_y are the calling rank's n local entries. */
 LIS_INT lis_b200_matvec_host(LIS_MATRIX A, LIS_SCALAR host_x[], LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR host_y[]);
 LIS_INT lis_b200_matvec_host_plan(LIS_MATRIX A, LIS_INT cap, LIS_INT *rows, LIS_INT *need);
 /* the CUDA stream (cudaStream_t) all kernels of this process are enqueued on */

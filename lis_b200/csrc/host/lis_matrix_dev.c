@@ -298,7 +298,9 @@ LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
  * next chunk only; a matrix whose rows read all of x degenerates to copy-in, then products
  * overlapped with copy-out.  Every row is still summed by the same kernel in the same order:
  * x, y, host_y hold the same bits as after the three separate calls.
- * Unsplit CSR on one process; anything else takes the three calls. */
+ * Row-partitioned matrices: host_x / host_y are this rank's slices; the chunks that read halo
+ * entries run last, behind the halo exchange, which itself needs all of the local x.
+ * Unsplit CSR; anything else takes the three calls. */
 #define LISD_PIPE_MIN_ROWS  (1 << 18)       /* 2 MiB of x per chunk at least */
 #define LISD_PIPE_MAX_CHUNKS 32
 
@@ -326,7 +328,9 @@ static LIS_INT pipe_plan(LIS_MATRIX A, lisd_matrix *M)
         LIS_INT mx = 0;
         const LIS_INT *idx = A->index;
         for (LIS_INT j = A->ptr[M->pipe_row[c]]; j < A->ptr[M->pipe_row[c + 1]]; j++) if (idx[j] > mx) mx = idx[j];
-        M->pipe_need[c] = mx / rows < nch ? mx / rows : nch - 1;
+        /* a column beyond the owned range is a halo entry (row-partitioned matrix): such a chunk
+         * runs after the halo exchange, i.e. after all of x has landed */
+        M->pipe_need[c] = mx >= n ? nch : (mx / rows < nch ? mx / rows : nch - 1);
     }
     M->pipe_n = nch;
     return LIS_SUCCESS;
@@ -346,36 +350,48 @@ LIS_INT lis_b200_matvec_host(LIS_MATRIX A, LIS_SCALAR host_x[], LIS_VECTOR x, LI
     lisd_matrix *M;
     err = lisd_matrix_get(A, &M);
     if (err) return err;
-    int pipelined = A->matrix_type == LIS_MATRIX_CSR && !M->splited && A->nprocs == 1 && A->np == A->n &&
-                    x->b200_managed && y->b200_managed;
+    int pipelined = A->matrix_type == LIS_MATRIX_CSR && !M->splited && x->b200_managed && y->b200_managed;
     if (pipelined && M->pipe_n == 0) { err = pipe_plan(A, M); if (err) return err; }
     if (!pipelined || M->pipe_n < 2) {
-        err = lis_vector_scatter(host_x, x);
+        err = lis_vector_set_values2(LIS_INS_VALUE, x->is + x->origin, x->n, host_x, x);
         if (!err) err = lis_matvec(A, x, y);
-        if (!err) err = lis_vector_gather(y, host_y);
+        if (!err) err = lis_vector_get_values(y, y->is + y->origin, y->n, host_y);
         return err;
     }
+    if (A->np > A->n) { err = vec_reserve(x, (size_t)A->np + (size_t)A->pad_comm); if (err) return err; }
     err = lisd_vec_device(x);
     if (!err) err = lisd_vec_device(y);
     if (!err) err = lisd_pipe_begin(M->pipe_n);
     if (err) return err;
     const int *row = M->pipe_row;
+    const int nchunks = M->pipe_n;
     for (int c = 0; c < M->pipe_n && !err; c++)
         err = lisd_pipe_h2d(c, x->value + row[c], host_x + row[c], (size_t)(row[c + 1] - row[c]) * sizeof(LIS_SCALAR));
     int landed = -1;                                  /* inputs the main stream already waits for */
     void *st = lisd_stream();
-    for (int c = 0; c < M->pipe_n && !err; c++) {
-        const int nr = row[c + 1] - row[c];
-        int rc;
-        if (M->pipe_need[c] > landed) { landed = M->pipe_need[c]; err = lisd_pipe_wait_in(landed); if (err) break; }
-        if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(nr, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr + row[c], M->csr.idx, M->csr.val, x->value, y->value + row[c], st);
-        else rc = lisb200_spmv_csr(nr, M->csr.ptr + row[c], M->csr.idx, M->csr.val, x->value, y->value + row[c], st);
-        lisd_mark_busy();
-        err = lisd_check(rc, "lis_b200_matvec_host");
-        if (!err) err = lisd_pipe_d2h(c, host_y + row[c], y->value + row[c], (size_t)nr * sizeof(LIS_SCALAR));
+    /* pass 0: chunks whose rows read owned entries only, as their inputs land; pass 1 (row-partitioned
+     * matrices): the halo exchange once all of x is there, then the chunks that read halo entries */
+    for (int pass = 0; pass < 2 && !err; pass++) {
+        if (pass == 1) {
+            if (!(A->nprocs > 1 && A->commtable)) break;
+            if (landed < nchunks - 1) { landed = nchunks - 1; err = lisd_pipe_wait_in(landed); if (err) break; }
+            err = lisd_halo_exchange(A, x);
+            if (err) break;
+        }
+        for (int c = 0; c < nchunks && !err; c++) {
+            const int nr = row[c + 1] - row[c];
+            int rc;
+            if ((M->pipe_need[c] >= nchunks) != (pass == 1)) continue;
+            if (pass == 0 && M->pipe_need[c] > landed) { landed = M->pipe_need[c]; err = lisd_pipe_wait_in(landed); if (err) break; }
+            if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(nr, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr + row[c], M->csr.idx, M->csr.val, x->value, y->value + row[c], st);
+            else rc = lisb200_spmv_csr(nr, M->csr.ptr + row[c], M->csr.idx, M->csr.val, x->value, y->value + row[c], st);
+            lisd_mark_busy();
+            err = lisd_check(rc, "lis_b200_matvec_host");
+            if (!err) err = lisd_pipe_d2h(c, host_y + row[c], y->value + row[c], (size_t)nr * sizeof(LIS_SCALAR));
+        }
     }
     /* x chunks nobody waited for (beyond every row's reach) still have to land before x is used again */
-    if (!err && landed < M->pipe_n - 1) err = lisd_pipe_wait_in(M->pipe_n - 1);
+    if (!err && landed < nchunks - 1) err = lisd_pipe_wait_in(nchunks - 1);
     {
         LIS_INT e2 = lisd_pipe_end();
         if (!err) err = e2;

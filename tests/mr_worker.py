@@ -31,10 +31,12 @@ def main():
     if rank == 0:
         tok[0] = int.from_bytes(os.urandom(7), "little")
     dist.broadcast(tok, 0)
-    hostcheck = os.environ.get("LIS_B200_HOSTCHECK_DIR")      # mock-device build (tests/hostcheck): CPU only
+    # CPU-only builds of the host code: mock device (tests/hostcheck) or the kernel emulator (tests/cudaemu)
+    hostcheck = os.environ.get("LIS_B200_HOSTCHECK_DIR")
     if hostcheck:
-        shim = lis_b200.Shim(os.path.join(hostcheck, "liblis_hostcheck_shim.so"))
-        lib = C.CDLL(os.path.join(hostcheck, "liblis_hostcheck.so"))
+        name = os.environ.get("LIS_B200_HOSTCHECK_NAME", "hostcheck")
+        shim = lis_b200.Shim(os.path.join(hostcheck, f"liblis_{name}_shim.so"))
+        lib = C.CDLL(os.path.join(hostcheck, f"liblis_{name}.so"))
     else:
         lib = lis_b200.load_library()
         shim = lis_b200.load_shim()
@@ -103,6 +105,7 @@ def main():
 
     result = {"rank": rank, "mode": mode}
     if mode in ("gpu", "hostcheck"):
+        os.environ["LIS_B200_PIPE_CHUNKS"] = "3"
         L.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int]
         L.shim_mv_set_x_local.argtypes = [C.c_int, f64p]; L.shim_mv_get_y_local.argtypes = [C.c_int, f64p]
         L.shim_mv_dot_xy.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -126,6 +129,17 @@ def main():
                 assert np.allclose(yl, y_full[is_:ie], rtol=1e-13, atol=1e-13 * np.abs(y_full).max())
             else:
                 H.assert_bits_equal(yl, y_full[is_:ie], f"rank {rank} spmv {fmt}")
+            if fmt == "csr":
+                # the overlapped host-buffer product on local slices: chunks that read halo entries
+                # run behind the exchange, the others as their inputs land (LIS_B200_PIPE_CHUNKS=3 here)
+                L.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, f64p, f64p]
+                for seed in (8, 9):
+                    x2 = H.rand_vec(gn, seed, "wide")
+                    y2 = np.full(nl, np.nan)
+                    assert L.shim_mv_step_e2e_pipelined(h, np.ascontiguousarray(x2[is_:ie]), y2) == 0
+                    H.assert_bits_equal(y2, o.spmv("csr", ptr, idx, val, x2)[is_:ie], f"rank {rank} overlapped spmv")
+                assert L.shim_mv_set_x_local(h, np.ascontiguousarray(x[is_:ie])) == 0
+                assert L.shim_mv_matvec(h) == 0
             d = C.c_double()
             assert L.shim_mv_dot_xy(h, C.byref(d)) == 0
             assert abs(d.value - float(np.dot(x, y_full))) <= 1e-9 * abs(float(np.dot(np.abs(x), np.abs(y_full))))

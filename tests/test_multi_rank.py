@@ -55,6 +55,17 @@ def test_row_partitioned_spmv_and_solvers_hostcheck(built, world):
     launch(world, "hostcheck", timeout=600, extra_env={"LIS_B200_HOSTCHECK_DIR": d, "LIS_B200_TRANSPORT": "host"})
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_partitioned_spmv_and_solvers_emulated_kernels(built, world):
+    """the same flow with the product's kernel sources on the host emulator (tests/cudaemu) instead of
+    the mock: gather/pack, the SpMV kernels on local+halo numbering, reductions, block-SSOR sweeps"""
+    d = os.path.join(HERE, "cudaemu")
+    r = subprocess.run(["make", "-C", d, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    launch(world, "hostcheck", timeout=900, extra_env={"LIS_B200_HOSTCHECK_DIR": os.path.join(d, "_build"),
+                                                       "LIS_B200_HOSTCHECK_NAME": "emu", "LIS_B200_TRANSPORT": "host"})
+
+
 @pytest.mark.gpu
 def test_row_partitioned_spmv_and_solvers_2gpu(built):
     import torch
