@@ -127,6 +127,48 @@ int lisb200_jacobi_dot(int n, const double *d_r, const double *d_dinv, double *d
 int lisb200_csr_get_diagonal(int n, const int *d_ptr, const int *d_idx, const double *d_val,
                              double *d_d, void *stream);
 
+/* ---- storage-format conversion on the device: CSR -> ELL / DIA / JAD / BSR --------------------
+ * Same arrays as the reference's serial builders (and host/lis_convert.c) produce, entry for entry.
+ * Tables the host needs anyway (DIA offsets, JAD pointers, BSR block pointers) are prefix-summed on
+ * the host between the two launches of a conversion.                                            */
+/* *d_out = longest row (ELL maxnzr, JAD maxnzr)            src/matrix/lis_matrix_ell.c:1000-1012 */
+int lisb200_csr_max_row_len(int n, const int *d_ptr, int *d_out, void *stream);
+/* ELL: d_eval[j*ld+i], d_eidx[j*ld+i], unused slots (0.0, i)  src/matrix/lis_matrix_ell.c:1035-1052 */
+int lisb200_csr2ell(int n, int maxnzr, int ld, const int *d_ptr, const int *d_idx, const double *d_val,
+                    int *d_eidx, double *d_eval, void *stream);
+/* DIA (rows sorted by column).  mark: d_flags[col-row+n] (n+np bytes) and the number of distinct
+ * offsets per segment of 1024 flags in d_seg_count[lisb200_dia_segments(n,np)].  The host sums
+ * them (nnd) and passes the exclusive prefix as d_seg_base.  fill: ascending offsets into d_off,
+ * d_dval[k*ld+i] for every diagonal and row (0.0 where nothing is stored).
+ *                                                          src/matrix/lis_matrix_dia.c:1217-1300 */
+int lisb200_dia_segments(int n, int np);
+int lisb200_csr2dia_mark(int n, int np, const int *d_ptr, const int *d_idx,
+                         unsigned char *d_flags, int *d_seg_count, void *stream);
+int lisb200_csr2dia_fill(int n, int np, int nnd, int ld, const int *d_ptr, const int *d_idx, const double *d_val,
+                         const unsigned char *d_flags, const int *d_seg_base, const int *d_seg_count,
+                         int *d_off, double *d_dval, void *stream);
+/* JAD, maxnzr < lisb200_jad_bins().  hist: rows per bin (bin = maxnzr - length) for each of the
+ * lisb200_jad_ctas(n) CTAs, d_cta_bin[cta*bins + bin].  The host turns that into start positions
+ * d_cta_base (bins in ascending order = descending row length, CTAs in order inside a bin) and
+ * d_jptr[maxnzr+1].  fill: d_perm (rows by descending length, equal lengths in ascending row
+ * order) and the jagged diagonals d_jidx/d_jval[jptr[j] + p] = j-th entry of row perm[p].
+ *                                                          src/matrix/lis_matrix_jad.c:1682-1751 */
+int lisb200_jad_ctas(int n);
+int lisb200_jad_bins(void);
+int lisb200_csr2jad_hist(int n, int maxnzr, const int *d_ptr, int *d_cta_bin, void *stream);
+int lisb200_csr2jad_fill(int n, int maxnzr, const int *d_ptr, const int *d_idx, const double *d_val,
+                         const int *d_cta_base, const int *d_jptr, int *d_perm, int *d_jidx, double *d_jval,
+                         void *stream);
+/* BSR bnr x bnc.  count: distinct block columns per block row in d_count[nr]; *d_overflow = 1 when a
+ * block row holds more than lisb200_bsr_max_blocks() of them (convert on the host then).  The host
+ * prefix-sums d_count into d_bptr.  fill: d_bidx in first-seen order, blocks column-major
+ * d_bval[b*bnr*bnc + j*bnr + i], unset entries 0.0.       src/matrix/lis_matrix_bsr.c:411-540 */
+int lisb200_bsr_max_blocks(void);
+int lisb200_csr2bsr_count(int n, int nr, int bnr, int bnc, const int *d_ptr, const int *d_idx,
+                          int *d_count, int *d_overflow, void *stream);
+int lisb200_csr2bsr_fill(int n, int nr, int bnr, int bnc, const int *d_ptr, const int *d_idx, const double *d_val,
+                         const int *d_bptr, int *d_bidx, double *d_bval, void *stream);
+
 /* ---- SSOR sweep (level-scheduled, block-per-"thread" like the reference's OpenMP path) --- */
 /* forward:  x[i] = (b[i] - sum_{L, jj>=blk_start} L*x[jj]) * wd[i]
  * backward: x[i] -= (sum_{U, blk_start<=jj<blk_end} U*x[jj]) * wd[i]

@@ -399,6 +399,12 @@ static LIS_INT to_csr(LIS_MATRIX Ain, LIS_MATRIX Aout)
 static LIS_INT from_csr(LIS_MATRIX Acsr, LIS_MATRIX Aout)
 {
     inherit_partition(Acsr, Aout);
+    {
+        /* LIS_B200_CONVERT=device: rearranged in HBM by kernels/convert.cu (lis_convert_dev.c); same arrays */
+        int done = 0;
+        LIS_INT err = lisd_convert_from_csr(Acsr, Aout, &done);
+        if (err || done) return err;
+    }
     switch (Aout->matrix_type) {
     case LIS_MATRIX_CSR: return csr2csr(Acsr, Aout);
     case LIS_MATRIX_CSC: return csr2csc(Acsr, Aout);

@@ -96,6 +96,10 @@ typedef struct lisd_matrix {
 LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out);   /* build on first use */
 void    lisd_matrix_drop(LIS_MATRIX A);                     /* invalidate / free */
 LIS_INT lisd_matrix_refresh_wd(LIS_MATRIX A);               /* after WD changed on the host */
+void    lisd_mirror_free(lisd_matrix *M);                   /* a mirror that is not (yet) attached to a matrix */
+/* CSR -> ELL/DIA/JAD/BSR by kernels (lis_convert_dev.c); *done = 0: not handled, run the host builder */
+int     lisd_convert_on_device(void);
+LIS_INT lisd_convert_from_csr(LIS_MATRIX Acsr, LIS_MATRIX Aout, int *done);
 
 /* ---- internal async vector ops (no host sync; the public lis_vector_* wrap these) ---- */
 LIS_INT lisd_copy(LIS_VECTOR x, LIS_VECTOR y);

@@ -74,6 +74,8 @@ static void mirror_free(lisd_matrix *M)
     free(M);
 }
 
+void lisd_mirror_free(lisd_matrix *M) { mirror_free(M); }
+
 void lisd_matrix_drop(LIS_MATRIX A)
 {
     if (A->b200_dev) { mirror_free((lisd_matrix *)A->b200_dev); A->b200_dev = NULL; }

@@ -207,3 +207,107 @@ int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *order
     }
     return 0;
 }
+
+/* ---- device-side format conversion (kernels/convert.cu): plain sequential restatements ---- */
+int lisb200_csr_max_row_len(int n, const int *p, int *out, void *s)
+{ (void)s; int m = 0; for (int i = 0; i < n; i++) if (p[i + 1] - p[i] > m) m = p[i + 1] - p[i]; *out = m; return 0; }
+int lisb200_csr2ell(int n, int m, int ld, const int *p, const int *ix, const double *v, int *ei, double *ev, void *s)
+{
+    (void)s;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < m; j++) {
+            const size_t o = (size_t)j * ld + i;
+            if (j < p[i + 1] - p[i]) { ei[o] = ix[p[i] + j]; ev[o] = v[p[i] + j]; } else { ei[o] = i; ev[o] = 0.0; }
+        }
+    return 0;
+}
+int lisb200_dia_segments(int n, int np) { return (int)(((long long)n + np + 1023) / 1024); }
+int lisb200_csr2dia_mark(int n, int np, const int *p, const int *ix, unsigned char *f, int *sc, void *s)
+{
+    (void)s;
+    const long long span = (long long)n + np;
+    memset(f, 0, (size_t)span);
+    for (int i = 0; i < n; i++) for (int j = p[i]; j < p[i + 1]; j++) f[(long long)ix[j] - i + n] = 1;
+    for (int g = 0; g < lisb200_dia_segments(n, np); g++) {
+        int c = 0;
+        for (long long k = (long long)g * 1024; k < (long long)(g + 1) * 1024 && k < span; k++) c += f[k];
+        sc[g] = c;
+    }
+    return 0;
+}
+int lisb200_csr2dia_fill(int n, int np, int nnd, int ld, const int *p, const int *ix, const double *v, const unsigned char *f,
+                         const int *sb, const int *sc, int *off, double *dv, void *s)
+{
+    (void)s; (void)sb; (void)sc;
+    int k = 0;
+    for (long long q = 0; q < (long long)n + np; q++) if (f[q]) off[k++] = (int)(q - n);
+    for (int i = 0; i < n; i++) {
+        int q = p[i];
+        for (k = 0; k < nnd; k++) {
+            double t = 0.0;
+            while (q < p[i + 1] && ix[q] - i == off[k]) t = v[q++];
+            dv[(size_t)k * ld + i] = t;
+        }
+    }
+    return 0;
+}
+int lisb200_jad_ctas(int n) { return n > 0 ? (n + 4095) / 4096 : 0; }
+int lisb200_jad_bins(void) { return 256; }
+int lisb200_csr2jad_hist(int n, int m, const int *p, int *tab, void *s)
+{
+    (void)s;
+    memset(tab, 0, sizeof(int) * 256 * (size_t)lisb200_jad_ctas(n));
+    for (int i = 0; i < n; i++) tab[(size_t)(i / 4096) * 256 + (m - (p[i + 1] - p[i]))]++;
+    return 0;
+}
+int lisb200_csr2jad_fill(int n, int m, const int *p, const int *ix, const double *v, const int *base, const int *jp,
+                         int *perm, int *ji, double *jv, void *s)
+{
+    (void)s;
+    int *run = (int *)malloc(sizeof(int) * 256 * (size_t)(lisb200_jad_ctas(n) + 1));
+    memcpy(run, base, sizeof(int) * 256 * (size_t)lisb200_jad_ctas(n));
+    for (int i = 0; i < n; i++) perm[run[(size_t)(i / 4096) * 256 + (m - (p[i + 1] - p[i]))]++] = i;
+    free(run);
+    for (int q = 0; q < n; q++)
+        for (int j = 0; j < p[perm[q] + 1] - p[perm[q]]; j++) { ji[jp[j] + q] = ix[p[perm[q]] + j]; jv[jp[j] + q] = v[p[perm[q]] + j]; }
+    return 0;
+}
+int lisb200_bsr_max_blocks(void) { return 64; }
+static int mock_bsr_row(int n, int bi, int bnr, int bnc, const int *p, const int *ix, int *seen)
+{
+    int cnt = 0;
+    for (int ii = 0; ii < bnr && bi * bnr + ii < n; ii++)
+        for (int k = p[bi * bnr + ii]; k < p[bi * bnr + ii + 1]; k++) {
+            int q = 0;
+            while (q < cnt && seen[q] != ix[k] / bnc) q++;
+            if (q == cnt) { if (cnt == 64) return 65; seen[cnt++] = ix[k] / bnc; }
+        }
+    return cnt;
+}
+int lisb200_csr2bsr_count(int n, int nr, int bnr, int bnc, const int *p, const int *ix, int *count, int *over, void *s)
+{
+    (void)s;
+    int seen[64];
+    *over = 0;
+    for (int bi = 0; bi < nr; bi++) { count[bi] = mock_bsr_row(n, bi, bnr, bnc, p, ix, seen); if (count[bi] > 64) { count[bi] = 64; *over = 1; } }
+    return 0;
+}
+int lisb200_csr2bsr_fill(int n, int nr, int bnr, int bnc, const int *p, const int *ix, const double *v, const int *bp,
+                         int *bi_out, double *bv, void *s)
+{
+    (void)s;
+    const int bs = bnr * bnc;
+    for (int bi = 0; bi < nr; bi++) {
+        int seen[64], cnt = 0;
+        for (int ii = 0; ii < bnr && bi * bnr + ii < n; ii++)
+            for (int k = p[bi * bnr + ii]; k < p[bi * bnr + ii + 1]; k++) {
+                const int bj = ix[k] / bnc, j = ix[k] % bnc;
+                int q = 0;
+                while (q < cnt && seen[q] != bj) q++;
+                double *blk = bv + (size_t)(bp[bi] + q) * bs;
+                if (q == cnt) { seen[cnt++] = bj; bi_out[bp[bi] + q] = bj; for (int z = 0; z < bs; z++) blk[z] = 0.0; }
+                blk[j * bnr + ii] = v[k];
+            }
+    }
+    return 0;
+}

@@ -31,6 +31,8 @@ test_spmv_csr_both_kernels = G.test_spmv_csr_both_kernels
 test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
 test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
+test_device_conversion_same_arrays_as_host = G.test_device_conversion_same_arrays_as_host
+test_device_conversion_falls_back_to_host_builder = G.test_device_conversion_falls_back_to_host_builder
 test_blas1_elementwise_bit_exact = G.test_blas1_elementwise_bit_exact
 test_blas1_length_mismatch_is_ill_arg = G.test_blas1_length_mismatch_is_ill_arg
 test_reductions_bounded = G.test_reductions_bounded

@@ -192,6 +192,65 @@ def test_matvec_host_pipelined_default_chunks(b200, oracle):
         L.shim_mv_close(h)
 
 
+def _conv_cases():
+    yield "poisson3d_7pt_sorted", H.poisson3d_7pt(17, 13, 11, sort=True)
+    yield "poisson3d_7pt_unsorted", H.poisson3d_7pt(12, 9, 10)
+    yield "poisson3d_27pt", H.poisson3d_27pt(9, 8, 7)
+    yield "random_ragged", H.random_csr(2500, 7, 11, values="wide")
+    yield "random_banded_sorted", H.random_csr(9001, 5, 12, band=40, sorted_rows=True)
+    yield "random_empty_rows", H.random_csr(4200, 4, 13, empty_rows=True, diag_dominant=False)
+    yield "single_row", (np.array([0, 1], np.int32), np.array([0], np.int32), np.array([3.5]))
+    yield "poisson1d_5000", H.poisson1d(5000)
+
+
+@pytest.mark.parametrize("fmt,blk", [("ell", (0, 0)), ("dia", (0, 0)), ("jad", (0, 0)), ("bsr", (2, 2)), ("bsr", (3, 2)),
+                                     ("bsr", (1, 4)), ("bsr", (4, 4))])
+def test_device_conversion_same_arrays_as_host(b200, oracle, monkeypatch, fmt, blk):
+    """LIS_B200_CONVERT=device (kernels/convert.cu): lis_matrix_convert builds ELL / DIA / JAD / BSR in
+    HBM; every public array must equal the host builder's (which is pinned to the reference's
+    layouts in test_oracle_vs_reference.py), and the product on the converted matrix -- served by
+    the mirror the conversion left on the device -- must carry the oracle's bits"""
+    for name, (ptr, idx, val) in _conv_cases():
+        if fmt == "dia" and name == "random_ragged":
+            continue
+        monkeypatch.setenv("LIS_B200_CONVERT", "host")
+        want = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
+        monkeypatch.setenv("LIS_B200_CONVERT", "device")
+        got = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
+        assert set(got) == set(want)
+        for key in want:
+            if isinstance(want[key], np.ndarray):
+                assert got[key].dtype == want[key].dtype and got[key].shape == want[key].shape, (fmt, name, key)
+                if want[key].dtype == np.float64:
+                    H.assert_bits_equal(got[key], want[key], f"{fmt}/{name}/{key}")
+                else:
+                    assert np.array_equal(got[key], want[key]), (fmt, name, key)
+            else:
+                assert got[key] == want[key], (fmt, name, key, got[key], want[key])
+        x = H.rand_vec(len(ptr) - 1, 3, "wide")
+        y, _ = b200.spmv(fmt, ptr, idx, val, x, bnr=blk[0], bnc=blk[1])
+        H.assert_bits_equal(y, oracle.spmv(fmt, ptr, idx, val, x, bnr=blk[0] or 2, bnc=blk[1] or 2), f"spmv after device {fmt}/{name}")
+
+
+def test_device_conversion_falls_back_to_host_builder(b200, monkeypatch):
+    """rows longer than 255 entries (JAD) and block rows with more than 64 blocks (BSR) are outside
+    what the conversion kernels cover: the host builder takes over, same arrays"""
+    rng = np.random.default_rng(8)
+    n = 600
+    lens = rng.integers(1, 6, n); lens[17] = 300; lens[400] = 256
+    ptr = np.zeros(n + 1, np.int32); ptr[1:] = np.cumsum(lens)
+    idx = np.concatenate([rng.choice(n, l, replace=False) for l in lens]).astype(np.int32)
+    val = rng.standard_normal(ptr[-1])
+    for fmt, blk in (("jad", (0, 0)), ("bsr", (2, 2))):
+        monkeypatch.setenv("LIS_B200_CONVERT", "host")
+        want = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
+        monkeypatch.setenv("LIS_B200_CONVERT", "device")
+        got = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
+        for key in want:
+            if isinstance(want[key], np.ndarray):
+                assert np.array_equal(got[key], want[key]), (fmt, key)
+
+
 def test_blas1_length_mismatch_is_ill_arg(b200):
     for op in ("axpy", "xpay", "copy", "dot"):
         assert b200.vec_mismatch(op) == 1          # LIS_ERR_ILL_ARG, lis_vector_opv.c:158-163
