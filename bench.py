@@ -578,6 +578,41 @@ def run_b200(args, grid):
     except Exception as e:  # keep the sequential number
         log(f"overlapped e2e path not used: {e!r}")
 
+    # ---- the other storage formats through the public API: lis_matrix_convert (on the device with
+    # LIS_B200_CONVERT=device, kernels/convert.cu; ELL also by the host builder for comparison) and
+    # `steps` host-synchronous lis_matvec calls each.  Last and optional: failures land in `extra`.
+    fmt_extra = {}
+    if not args.no_format_extras:
+        Ls.shim_mv_convert.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        Ls.shim_mv_close.argtypes = [C.c_int]
+        for name, code, bnr, bnc, modes in (("ell", 5, 0, 0, ("device", "host")), ("dia", 4, 0, 0, ("device",)),
+                                            ("jad", 6, 0, 0, ("device",)), ("bsr", 7, 2, 2, ("device",))):
+            for mode in modes:
+                try:
+                    os.environ["LIS_B200_CONVERT"] = mode
+                    csec = C.c_double(0)
+                    h2 = Ls.shim_mv_convert(h, code, bnr, bnc, C.byref(csec))
+                    if h2 < 0:
+                        raise RuntimeError(f"lis_matrix_convert failed ({h2})")
+                    try:
+                        t2, n2 = C.c_double(0), C.c_double(0)
+                        rc = Ls.shim_mv_run(h2, 2, C.byref(t2), C.byref(n2))
+                        rc = rc or Ls.shim_mv_run(h2, args.steps, C.byref(t2), C.byref(n2))
+                        if rc:
+                            raise RuntimeError(f"lis_matvec failed ({rc})")
+                        fmt_extra[f"{name}_convert_{mode}_s"] = csec.value
+                        if mode == "device":
+                            fmt_extra[f"{name}_api_gflops"] = 2.0 * nnz * args.steps / t2.value / 1e9
+                            fmt_extra[f"{name}_api_ms"] = t2.value / args.steps * 1e3
+                            fmt_extra[f"{name}_nrm2_vs_csr_rel"] = abs(n2.value - nrm.value) / nrm.value
+                        log(f"{name}: lis_matrix_convert ({mode}) {csec.value:.2f}s, lis_matvec {2.0 * nnz * args.steps / t2.value / 1e9:.1f} GFLOP/s")
+                    finally:
+                        Ls.shim_mv_close(h2)
+                except Exception as e:
+                    fmt_extra[f"{name}_{mode}_error"] = repr(e)
+                    log(f"format extra {name}/{mode} skipped: {e!r}")
+        os.environ.pop("LIS_B200_CONVERT", None)
+
     out = None
     if rank == 0:
         gf = 2.0 * nnz / res["csr_s"] / 1e9
@@ -610,6 +645,7 @@ def run_b200(args, grid):
                 "cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": cg_iters,
                 "cg_unfused_formula_gbs": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9 if cg_it_s else None,
                 "nrm2_Ax": nrm.value,
+                **fmt_extra,
             },
         }
     return out
@@ -628,6 +664,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=256, help="edge of the bounded CPU sample")
     ap.add_argument("--cg-iters", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-format-extras", action="store_true", help="skip the ELL/DIA/JAD/BSR convert + lis_matvec extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -660,6 +660,23 @@ EXPORT int shim_mv_solve_b(int h, const char *options, const double *b_local, do
     return (int)err;
 }
 
+/* a new handle holding handle `src`'s matrix converted to storage format `fmt`
+ * (lis_matrix_convert, timed with lis_wtime); x is copied from the source handle */
+EXPORT int shim_mv_convert(int src, int fmt, int bnr, int bnc, double *seconds)
+{
+    int h;
+    LIS_MATRIX A = NULL;
+    for (h = 0; h < 8 && g_mv[h].A; h++) ;
+    if (h == 8) return -1;
+    const double t0 = lis_wtime();
+    if (convert_to(g_mv[src].A, fmt, bnr, bnc, &A)) return -3;
+    if (seconds) *seconds = lis_wtime() - t0;
+    if (make_vec(A, NULL, &g_mv[h].x) || make_vec(A, NULL, &g_mv[h].y)) return -4;
+    if (lis_vector_copy(g_mv[src].x, g_mv[h].x)) return -5;
+    g_mv[h].A = A;
+    return h;
+}
+
 EXPORT int shim_mv_close(int h)
 {
     lis_vector_destroy(g_mv[h].x); lis_vector_destroy(g_mv[h].y); lis_matrix_destroy(g_mv[h].A);
