@@ -514,6 +514,7 @@ LIS_INT lis_input_matrix(LIS_MATRIX A, char *filename);
 LIS_INT lis_input_vector(LIS_VECTOR v, char *filename);
 LIS_INT lis_output_vector(LIS_VECTOR v, LIS_INT format, char *filename);
 LIS_INT lis_output_matrix(LIS_MATRIX A, LIS_INT format, char *path);
+LIS_INT lis_output(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT format, char *path);
 LIS_INT lis_solver_output_rhistory(LIS_SOLVER solver, char *filename);
 
 #ifdef __cplusplus

@@ -2,7 +2,8 @@
  * lis_io.c -- the on-disk formats either side of the hot path that the reference drivers
  * touch: Matrix Market input (with Lis' extension that appends b and x to the file,
  * src/system/lis_input_mm.c:61-1069, used by test/test1.c), vector input, and the
- * solution / matrix writers (src/system/lis_output.c:200-440).  Host C, ASCII only.
+ * Harwell-Boeing (RUA) input (src/system/lis_input_hb.c), and the solution / matrix writers
+ * (src/system/lis_output.c:200-440).  Host C, ASCII only.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -45,14 +46,32 @@ static LIS_INT next_data_line(FILE *f, char *buf, size_t cap)
     return LIS_SUCCESS;
 }
 
-/* n lines "i value" (1-based) into the locally owned slice of v */
-static LIS_INT read_mm_vec_body(FILE *f, LIS_VECTOR v, LIS_INT gn)
+/* binary records of Lis' LIS_FMT_MMB extension (include/lis_io.h:104-115 of the reference): the
+ * size line carries a sixth field, 1 + (1 if the writer was little-endian) */
+typedef struct { LIS_INT i; LIS_SCALAR value; } mmb_vec_t;
+typedef struct { LIS_INT i; LIS_INT j; LIS_SCALAR value; } mmb_mat_t;
+
+static void bswap_bytes(void *p, size_t n)
+{
+    unsigned char *b = (unsigned char *)p;
+    for (size_t k = 0; k < n / 2; k++) { const unsigned char t = b[k]; b[k] = b[n - 1 - k]; b[n - 1 - k] = t; }
+}
+static int host_little_endian(void) { const int one = 1; return *(const char *)&one; }
+
+/* n lines "i value" (1-based), or n binary records, into the locally owned slice of v */
+static LIS_INT read_mm_vec_body(FILE *f, LIS_VECTOR v, LIS_INT gn, int isbin)
 {
     char buf[LINE_MAX_LEN];
+    const int swap = isbin && host_little_endian() != isbin - 1;
     lisd_vec_host(v);
     for (LIS_INT i = 0; i < gn; i++) {
         int idx; double val;
-        if (fgets(buf, sizeof(buf), f) == NULL || sscanf(buf, "%d %lg", &idx, &val) != 2) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
+        if (isbin) {
+            mmb_vec_t r;
+            if (fread(&r, sizeof(r), 1, f) != 1) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
+            if (swap) { bswap_bytes(&r.i, sizeof(r.i)); bswap_bytes(&r.value, sizeof(r.value)); }
+            idx = (int)r.i; val = (double)r.value;
+        } else if (fgets(buf, sizeof(buf), f) == NULL || sscanf(buf, "%d %lg", &idx, &val) != 2) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
         idx--;
         if (idx >= v->is && idx < v->ie) v->value[idx - v->is] = val;
     }
@@ -69,9 +88,12 @@ static LIS_INT input_mm(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, FILE *f)
     if (bn.is_vector || bn.is_array) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "only coordinate matrices are supported\n"); return LIS_ERR_NOT_IMPLEMENTED; }
     err = next_data_line(f, buf, sizeof(buf));
     if (err) return err;
-    int nr = 0, nc = 0, nnz = 0, isb = 0, isx = 0;
-    const int got = sscanf(buf, "%d %d %d %d %d", &nr, &nc, &nnz, &isb, &isx);
-    if (got != 3 && got != 5) { LIS_SETERR(LIS_ERR_FILE_IO, "matrix size line is not correct\n"); return LIS_ERR_FILE_IO; }
+    int nr = 0, nc = 0, nnz = 0, isb = 0, isx = 0, isbin = 0;
+    const int got = sscanf(buf, "%d %d %d %d %d %d", &nr, &nc, &nnz, &isb, &isx, &isbin);
+    if (got != 3 && got != 5 && got != 6) { LIS_SETERR(LIS_ERR_FILE_IO, "matrix size line is not correct\n"); return LIS_ERR_FILE_IO; }
+    if (got < 6) isbin = 0;
+    if (got < 5) { isb = 0; isx = 0; }
+    const int swap = isbin && host_little_endian() != isbin - 1;
     if (nr != nc) { LIS_SETERR(LIS_ERR_FILE_IO, "matrix is not square\n"); return LIS_ERR_FILE_IO; }
     err = lis_matrix_set_size(A, 0, nr);
     if (err) return err;
@@ -86,9 +108,16 @@ static LIS_INT input_mm(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, FILE *f)
     if (!ri || !ci || !va) { err = LIS_OUT_OF_MEMORY; LIS_SETERR_MEM(nnz); goto done; }
     for (int k = 0; k < nnz; k++) {
         double v = 1.0;
-        if (fgets(buf, sizeof(buf), f) == NULL) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; goto done; }
-        const int c = bn.is_pattern ? sscanf(buf, "%d %d", &ri[k], &ci[k]) + 1 : sscanf(buf, "%d %d %lg", &ri[k], &ci[k], &v);
-        if (c != 3) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; goto done; }
+        if (isbin) {
+            mmb_mat_t r;
+            if (fread(&r, sizeof(r), 1, f) != 1) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; goto done; }
+            if (swap) { bswap_bytes(&r.i, sizeof(r.i)); bswap_bytes(&r.j, sizeof(r.j)); bswap_bytes(&r.value, sizeof(r.value)); }
+            ri[k] = (int)r.i; ci[k] = (int)r.j; v = (double)r.value;
+        } else {
+            if (fgets(buf, sizeof(buf), f) == NULL) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; goto done; }
+            const int c = bn.is_pattern ? sscanf(buf, "%d %d", &ri[k], &ci[k]) + 1 : sscanf(buf, "%d %d %lg", &ri[k], &ci[k], &v);
+            if (c != 3) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; goto done; }
+        }
         ri[k]--; ci[k]--; va[k] = v;
         if (ri[k] < 0 || ri[k] >= nr || ci[k] < 0 || ci[k] >= nr) { LIS_SETERR(LIS_ERR_FILE_IO, "index out of range\n"); err = LIS_ERR_FILE_IO; goto done; }
     }
@@ -116,14 +145,15 @@ static LIS_INT input_mm(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, FILE *f)
     /* optional right-hand side and initial guess appended to the file */
     if (isb && b) {
         if (lis_vector_is_null(b)) { err = lis_vector_set_size(b, A->n, 0); if (err) goto done; }
-        err = read_mm_vec_body(f, b, nr);
+        err = read_mm_vec_body(f, b, nr, isbin);
         if (err) goto done;
     } else if (isb) {
-        for (int k = 0; k < nr; k++) if (fgets(buf, sizeof(buf), f) == NULL) break;
+        if (isbin) fseek(f, (long)sizeof(mmb_vec_t) * nr, SEEK_CUR);
+        else for (int k = 0; k < nr; k++) if (fgets(buf, sizeof(buf), f) == NULL) break;
     }
     if (isx && x) {
         if (lis_vector_is_null(x)) { err = lis_vector_set_size(x, A->n, 0); if (err) goto done; }
-        err = read_mm_vec_body(f, x, nr);
+        err = read_mm_vec_body(f, x, nr, isbin);
         if (err) goto done;
     }
     if (want_type != LIS_MATRIX_CSR) {
@@ -141,6 +171,129 @@ done:
     return err;
 }
 
+/* ------------------------------------------------------------------ Harwell-Boeing (RUA)
+ * What src/system/lis_input_hb.c:129-466 accepts: real, unsymmetric, assembled, square; the
+ * right-hand sides a file may carry are skipped (b and x are left to the caller, test/test1.c
+ * then builds b = A*1).  Fixed-width Fortran fields: "(10I8)" -> 10 per line, 8 wide; the count and
+ * width are taken the way the reference takes them (text before / after the edit letter through
+ * atoi), and every field goes through atoi / atof, so "1.5D+00" reads as 1.5 there and here.
+ * The file holds compressed columns: loaded as CSC, then converted to the requested storage. */
+static void hb_fmt(const char *field, int size, int *count, int *width)
+{
+    char tmp[64];
+    char *p, *s, *t;
+    if (size > 63) size = 63;
+    strncpy(tmp, field, (size_t)size); tmp[size] = '\0';
+    lower(tmp);
+    *count = 0; *width = 0;
+    p = strchr(tmp, '(');
+    if (p == NULL) return;
+    s = p + 1;
+    p = strchr(s, ')');
+    if (p) *p = '\0';
+    p = strchr(s, 'i');
+    if (p == NULL) {
+        p = strchr(s, 'e');
+        if (p == NULL) p = strchr(s, 'd');
+        if (p == NULL) return;
+        t = strchr(s, '.');
+        if (t) *t = '\0';
+    }
+    *p = '\0';
+    *count = atoi(s);
+    *width = atoi(p + 1);
+}
+
+static LIS_INT input_hb(LIS_MATRIX A, FILE *f)
+{
+    char buf[LINE_MAX_LEN], mtx[64] = "", dat[128];
+    int totcrd = 0, ptrcrd = 0, indcrd = 0, valcrd = 0, rhscrd = 0;
+    int nrow = 0, ncol = 0, nnzero = 0, neltvl = 0;
+    int iptr, iind, ival, irhs, wptr, wind, wval, wrhs;
+    const LIS_INT want_type = A->matrix_type;
+    LIS_INT *ptr = NULL, *index = NULL, err;
+    LIS_SCALAR *value = NULL;
+    if (A->nprocs > 1) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "Harwell-Boeing input is single-process only\n"); return LIS_ERR_NOT_IMPLEMENTED; }
+    if (fgets(buf, sizeof(buf), f) == NULL) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }                 /* line 1: title, key */
+    if (fgets(buf, sizeof(buf), f) == NULL ||
+        sscanf(buf, "%14d%14d%14d%14d%14d", &totcrd, &ptrcrd, &indcrd, &valcrd, &rhscrd) < 4) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
+    if (fgets(buf, sizeof(buf), f) == NULL ||
+        sscanf(buf, "%63s %d %d %d %d", mtx, &nrow, &ncol, &nnzero, &neltvl) != 5) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
+    lower(mtx);
+    if (mtx[0] != 'r') { LIS_SETERR(LIS_ERR_FILE_IO, "Not real\n"); return LIS_ERR_FILE_IO; }
+    if (mtx[1] != 'u') { LIS_SETERR(LIS_ERR_FILE_IO, "Not unsymmetric\n"); return LIS_ERR_FILE_IO; }
+    if (mtx[2] != 'a') { LIS_SETERR(LIS_ERR_FILE_IO, "Not assembled\n"); return LIS_ERR_FILE_IO; }
+    if (nrow != ncol) { LIS_SETERR(LIS_ERR_FILE_IO, "matrix is not square\n"); return LIS_ERR_FILE_IO; }
+    printf("matrix size = %d x %d (%d nonzero entries)\n\n", nrow, ncol, nnzero);
+    memset(buf, 0, sizeof(buf));
+    if (fgets(buf, sizeof(buf), f) == NULL) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }                 /* line 4: formats */
+    hb_fmt(buf, 16, &iptr, &wptr);
+    hb_fmt(buf + 16, 16, &iind, &wind);
+    hb_fmt(buf + 32, 20, &ival, &wval);
+    hb_fmt(buf + 52, 20, &irhs, &wrhs);
+    if (rhscrd != 0 && fgets(buf, sizeof(buf), f) == NULL) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; } /* line 5 */
+    if (wptr <= 0 || wind <= 0 || wval <= 0 || wptr > 127 || wind > 127 || wval > 127 || nnzero < 0) {
+        LIS_SETERR(LIS_ERR_FILE_IO, "Harwell-Boeing format line is not understood\n");
+        return LIS_ERR_FILE_IO;
+    }
+    err = lis_matrix_set_size(A, 0, nrow);
+    if (err) return err;
+    const LIS_INT n = A->n;
+    err = lis_matrix_malloc_csr(n, nnzero, &ptr, &index, &value);
+    if (err) return err;
+#define HB_READ(cards, per, width, limit, STORE)                                                  \
+    do {                                                                                           \
+        LIS_INT k = 0;                                                                             \
+        for (int c = 0; c < (cards); c++) {                                                        \
+            if (fgets(buf, sizeof(buf), f) == NULL) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; goto fail; } \
+            const size_t len = strlen(buf);                                                        \
+            const char *p = buf;                                                                   \
+            for (int j = 0; j < (per) && k < (limit); j++) {                                       \
+                if ((size_t)(p - buf) >= len) { dat[0] = '\0'; }                                   \
+                else { strncpy(dat, p, (size_t)(width)); dat[(width)] = '\0'; }                    \
+                STORE;                                                                             \
+                p += (width);                                                                      \
+                k++;                                                                               \
+            }                                                                                      \
+        }                                                                                          \
+    } while (0)
+    HB_READ(ptrcrd, iptr, wptr, n + 1, ptr[k] = atoi(dat) - 1);
+    HB_READ(indcrd, iind, wind, nnzero, index[k] = atoi(dat) - 1);
+    HB_READ(valcrd, ival, wval, nnzero, value[k] = atof(dat));
+#undef HB_READ
+    if (ptr[0] != 0 || ptr[n] != nnzero) { LIS_SETERR(LIS_ERR_FILE_IO, "Harwell-Boeing column pointers do not match the entry count\n"); err = LIS_ERR_FILE_IO; goto fail; }
+    for (LIS_INT k = 0; k < nnzero; k++)
+        if (index[k] < 0 || index[k] >= n) { LIS_SETERR(LIS_ERR_FILE_IO, "index out of range\n"); err = LIS_ERR_FILE_IO; goto fail; }
+    lis_matrix_set_type(A, LIS_MATRIX_CSC);
+    err = lis_matrix_set_csc(nnzero, ptr, index, value, A);
+    if (err) goto fail;
+    ptr = NULL; index = NULL; value = NULL;
+    err = lis_matrix_assemble(A);
+    if (err) return err;
+    if (want_type != LIS_MATRIX_CSC) {
+        /* through CSR, like lis_input_hb_csr + lis_input_hb (:391-407, :72-99) */
+        LIS_MATRIX B;
+        err = lis_matrix_duplicate(A, &B);
+        if (err) return err;
+        lis_matrix_set_type(B, LIS_MATRIX_CSR);
+        err = lis_matrix_convert(A, B);
+        if (err) { lis_matrix_destroy(B); return err; }
+        lis_host_matrix_adopt(A, B);
+        if (want_type != LIS_MATRIX_CSR) {
+            err = lis_matrix_duplicate(A, &B);
+            if (err) return err;
+            lis_matrix_set_type(B, want_type);
+            err = lis_matrix_convert(A, B);
+            if (err) { lis_matrix_destroy(B); return err; }
+            lis_host_matrix_adopt(A, B);
+        }
+    }
+    return LIS_SUCCESS;
+fail:
+    lis_free2(3, ptr, index, value);
+    return err;
+}
+
 LIS_INT lis_input(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, char *filename)
 {
     if (!lis_is_malloc(A)) { LIS_SETERR(LIS_ERR_ILL_ARG, "matrix A is undefined\n"); return LIS_ERR_ILL_ARG; }
@@ -155,7 +308,7 @@ LIS_INT lis_input(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, char *filename)
     rewind(f);
     LIS_INT err;
     if (strncmp(buf, "%%MatrixMarket", 14) == 0) err = input_mm(A, b, x, f);
-    else { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "only Matrix Market files are supported (Harwell-Boeing is outside the hot path)\n"); err = LIS_ERR_NOT_IMPLEMENTED; }
+    else err = input_hb(A, f);                     /* anything else is taken for Harwell-Boeing, src/system/lis_input.c:100-118 */
     fclose(f);
     return err;
 }
@@ -177,7 +330,7 @@ LIS_INT lis_input_vector(LIS_VECTOR v, char *filename)
         if (!err && sscanf(buf, "%d", &gn) != 1) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; }
         if (!err && lis_vector_is_null(v)) err = lis_vector_set_size(v, 0, gn);
         if (!err && v->gn != gn) { LIS_SETERR(LIS_ERR_FILE_IO, "vector size does not match\n"); err = LIS_ERR_FILE_IO; }
-        if (!err) err = read_mm_vec_body(f, v, gn);
+        if (!err) err = read_mm_vec_body(f, v, gn, 0);
     } else {
         /* PLAIN: count the lines first when the vector has no size yet */
         rewind(f);
@@ -234,30 +387,51 @@ LIS_INT lis_output_vector(LIS_VECTOR v, LIS_INT format, char *filename)
     return LIS_SUCCESS;
 }
 
-/* Matrix Market coordinate writer (single process) */
-LIS_INT lis_output_matrix(LIS_MATRIX A, LIS_INT format, char *path)
+/* Matrix Market coordinate writer (single process): the matrix, then b and x when they are set
+ * -- Lis' extension of the size line "n n nnz isb isx", which lis_input reads back
+ * (src/system/lis_output.c:62-143, lis_output_mm.c:404-466 header, :58-150 vectors, :560-720 CSR).
+ * LIS_FMT_MMB: same header with a sixth field (1 + little-endian), records in binary. */
+static void write_mm_vec(FILE *f, LIS_VECTOR v, LIS_INT format)
+{
+    lisd_vec_host(v);
+    for (LIS_INT i = 0; i < v->n; i++) {
+        if (format == LIS_FMT_MM) fprintf(f, "%d %28.20e\n", (int)(v->is + i + 1), (double)v->value[i]);
+        else { mmb_vec_t r; memset(&r, 0, sizeof(r)); r.i = v->is + i + 1; r.value = v->value[i]; fwrite(&r, sizeof(r), 1, f); }
+    }
+}
+
+LIS_INT lis_output(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT format, char *path)
 {
     LIS_INT err = lis_host_matrix_check_input(A);
     if (err) return err;
-    if (format != LIS_FMT_MM) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "only LIS_FMT_MM is supported\n"); return LIS_ERR_NOT_IMPLEMENTED; }
+    if (format != LIS_FMT_MM && format != LIS_FMT_MMB) return LIS_SUCCESS;      /* the reference writes nothing either */
     if (A->nprocs > 1) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "matrix output is single-process only\n"); return LIS_ERR_NOT_IMPLEMENTED; }
-    LIS_MATRIX C = A, T = NULL;
+    LIS_MATRIX Cm = A, T = NULL;
     if (A->matrix_type != LIS_MATRIX_CSR || A->is_splited) {
         err = lis_matrix_duplicate(A, &T);
         if (err) return err;
         lis_matrix_set_type(T, LIS_MATRIX_CSR);
         err = lis_matrix_convert(A, T);
         if (err) { lis_matrix_destroy(T); return err; }
-        C = T;
+        Cm = T;
     }
-    FILE *f = fopen(path, "w");
+    const int isb = b != NULL && !lis_vector_is_null(b), isx = x != NULL && !lis_vector_is_null(x);
+    FILE *f = fopen(path, format == LIS_FMT_MM ? "w" : "wb");
     if (f == NULL) { if (T) lis_matrix_destroy(T); LIS_SETERR1(LIS_ERR_FILE_IO, "cannot open file %s\n", path); return LIS_ERR_FILE_IO; }
     fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n");
-    fprintf(f, "%d %d %d 0 0\n", (int)C->gn, (int)C->gn, (int)C->ptr[C->n]);
-    for (LIS_INT i = 0; i < C->n; i++)
-        for (LIS_INT j = C->ptr[i]; j < C->ptr[i + 1]; j++)
-            fprintf(f, "%d %d %28.20e\n", (int)(i + 1), (int)(C->index[j] + 1), (double)C->value[j]);
+    if (format == LIS_FMT_MMB) fprintf(f, "%d %d %d %d %d %d\n", (int)Cm->gn, (int)Cm->gn, (int)Cm->nnz, isb, isx, host_little_endian() + 1);
+    else if (!isb && !isx) fprintf(f, "%d %d %d\n", (int)Cm->gn, (int)Cm->gn, (int)Cm->nnz);
+    else fprintf(f, "%d %d %d %d %d\n", (int)Cm->gn, (int)Cm->gn, (int)Cm->nnz, isb, isx);
+    for (LIS_INT i = 0; i < Cm->n; i++)
+        for (LIS_INT j = Cm->ptr[i]; j < Cm->ptr[i + 1]; j++) {
+            if (format == LIS_FMT_MM) fprintf(f, "%d %d %28.20e\n", (int)(i + 1), (int)(Cm->index[j] + 1), (double)Cm->value[j]);
+            else { mmb_mat_t r; memset(&r, 0, sizeof(r)); r.i = i + 1; r.j = Cm->index[j] + 1; r.value = Cm->value[j]; fwrite(&r, sizeof(r), 1, f); }
+        }
+    if (isb) write_mm_vec(f, b, format);
+    if (isx) write_mm_vec(f, x, format);
     fclose(f);
     if (T) lis_matrix_destroy(T);
     return LIS_SUCCESS;
 }
+
+LIS_INT lis_output_matrix(LIS_MATRIX A, LIS_INT format, char *path) { return lis_output(A, NULL, NULL, format, path); }

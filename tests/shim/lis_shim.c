@@ -186,6 +186,26 @@ EXPORT int shim_spmv(int fmt, int n, const int *ptr, const int *idx, const doubl
     return 0;
 }
 
+/* lis_output(A, b, x, format, path) for the matrix in storage format `fmt`; b / x may be NULL (then
+ * an unset vector is passed, like lis_output_matrix does); vformat > 0 also writes b with
+ * lis_output_vector(b, vformat, vpath) */
+EXPORT int shim_output(int fmt, int n, const int *ptr, const int *idx, const double *val, const double *b, const double *x,
+                       int format, const char *path, int vformat, const char *vpath)
+{
+    LIS_MATRIX A0 = NULL, A = NULL;
+    LIS_VECTOR vb = NULL, vx = NULL;
+    LIS_INT err;
+    err = make_csr(n, ptr, idx, val, 0, &A0); if (err) return (int)err;
+    err = convert_to(A0, fmt, 2, 2, &A); if (err) return (int)err;
+    if (b) { err = make_vec(A, b, &vb); } else { err = lis_vector_create(LIS_COMM_WORLD, &vb); } if (err) return (int)err;
+    if (x) { err = make_vec(A, x, &vx); } else { err = lis_vector_create(LIS_COMM_WORLD, &vx); } if (err) return (int)err;
+    err = lis_output(A, vb, vx, format, (char *)path); if (err) return (int)err;
+    if (vformat > 0 && b) { err = lis_output_vector(vb, vformat, (char *)vpath); if (err) return (int)err; }
+    lis_vector_destroy(vb); lis_vector_destroy(vx);
+    lis_matrix_destroy(A); lis_matrix_destroy(A0);
+    return 0;
+}
+
 /* y = A^H x (lis_matvech), optionally on the split matrix */
 EXPORT int shim_matvech(int fmt, int n, const int *ptr, const int *idx, const double *val, int split, const double *x, double *y)
 {

@@ -167,6 +167,132 @@ def test_matrix_market_input_matches_reference(b200, ref_serial, tmp_path):
                 H.assert_bits_equal(gb, rb, "rhs")
 
 
+def _write_hb(path, ptr, idx, val, ptrfmt=(8, 10), indfmt=(8, 10), valfmt=(3, 26, 18), rhs=False, exponent="E"):
+    """a Harwell-Boeing RUA file of the matrix given as CSR (written column by column)"""
+    import scipy.sparse as sp
+    n = len(ptr) - 1
+    csc = sp.csr_matrix((val, idx, ptr), shape=(n, n)).tocsc()
+    csc.sort_indices()
+
+    def cards(items, per, fmt):
+        lines = []
+        for k in range(0, len(items), per):
+            lines.append("".join(fmt(v) for v in items[k:k + per]))
+        return lines
+    pl = cards(list(csc.indptr + 1), ptrfmt[0], lambda v: f"{v:{ptrfmt[1]}d}")
+    il = cards(list(csc.indices + 1), indfmt[0], lambda v: f"{v:{indfmt[1]}d}")
+    vl = cards(list(csc.data), valfmt[0], lambda v: f"{v:{valfmt[1]}.{valfmt[2]}E}".replace("E", exponent))
+    rl = cards([1.0] * n, valfmt[0], lambda v: f"{v:{valfmt[1]}.{valfmt[2]}E}") if rhs else []
+    with open(path, "w") as f:
+        f.write(f"{'lis_b200 test matrix':<72}{'KEY':<8}\n")
+        f.write(f"{len(pl) + len(il) + len(vl) + len(rl):14d}{len(pl):14d}{len(il):14d}{len(vl):14d}{len(rl):14d}\n")
+        f.write(f"{'RUA':<14}{n:14d}{n:14d}{csc.nnz:14d}{0:14d}\n")
+        vf = f"({valfmt[0]}E{valfmt[1]}.{valfmt[2]})"
+        f.write(f"{f'({ptrfmt[0]}I{ptrfmt[1]})':<16}{f'({indfmt[0]}I{indfmt[1]})':<16}{vf:<20}{(vf if rhs else ''):<20}\n")
+        if rhs:
+            f.write(f"{'F':<14}{1:14d}{0:14d}\n")
+        f.write("\n".join(pl + il + vl + rl) + "\n")
+
+
+def test_harwell_boeing_input_matches_reference(b200, ref_serial, tmp_path):
+    """lis_input on Harwell-Boeing RUA files (src/system/lis_input_hb.c): same arrays as the compiled
+    reference in CSR, CSC and ELL; several field layouts, a right-hand-side block (skipped by both),
+    Fortran D exponents (both read the mantissa only: atof)"""
+    cases = [("p7", H.poisson3d_7pt(5, 4, 3), {}),
+             ("rand", H.random_csr(150, 6, 3, values="wide"), {"ptrfmt": (13, 6), "indfmt": (16, 5), "valfmt": (4, 20, 12)}),
+             ("rhs", H.random_csr(40, 4, 5), {"rhs": True}),
+             ("dexp", H.random_csr(30, 3, 6), {"exponent": "D", "valfmt": (3, 26, 17)})]
+    for name, (ptr, idx, val), kw in cases:
+        path = tmp_path / f"{name}.rua"
+        _write_hb(str(path), ptr, idx, val, **kw)
+        for fmt in ("csr", "csc", "ell"):
+            ga, gb, gx = b200.input_mm(str(path), fmt)
+            ra, rb, rx = ref_serial.input_mm(str(path), fmt)
+            assert ga["n"] == ra["n"] == len(ptr) - 1
+            for key in ("ptr", "index", "value"):
+                if key in ra:
+                    assert np.array_equal(np.asarray(ga[key]).view(np.uint8), np.asarray(ra[key]).view(np.uint8)), (name, fmt, key)
+            assert gb is None and rb is None and gx is None and rx is None
+        if name != "dexp":
+            ga, _, _ = b200.input_mm(str(path), "csr")
+            import scipy.sparse as sp
+            n = len(ptr) - 1
+            want = sp.csr_matrix((val, idx, ptr), shape=(n, n)); want.sort_indices()
+            got = sp.csr_matrix((ga["value"], ga["index"], ga["ptr"]), shape=(n, n)); got.sort_indices()
+            assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+            assert np.allclose(got.data, want.data, rtol=1e-11 if name == "rand" else 1e-15, atol=0)
+
+
+def test_harwell_boeing_rejects_what_the_reference_rejects(b200, ref_serial, tmp_path):
+    ptr, idx, val = H.poisson1d(6)
+    path = tmp_path / "sym.rsa"
+    _write_hb(str(path), ptr, idx, val)
+    text = path.read_text().replace("RUA", "RSA")
+    path.write_text(text)
+    for shim in (b200, ref_serial):
+        with pytest.raises(RuntimeError):
+            shim.input_mm(str(path), "csr")
+
+
+def test_lis_output_files_identical_to_reference(b200, ref_serial, tmp_path):
+    """lis_output (matrix [+ b, x] as Matrix Market, ASCII and Lis' binary variant) and lis_output_vector
+    write byte-identical files, and lis_input reads them back to the same arrays"""
+    import ctypes as C
+    ptr, idx, val = H.random_csr(60, 5, 17, values="wide")
+    n = len(ptr) - 1
+    bvec = H.rand_vec(n, 1, "wide"); xvec = H.rand_vec(n, 2, "wide")
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C"); f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    files = {}
+    for tag, shim in (("b200", b200), ("ref", ref_serial)):
+        shim.lib.shim_output.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p,
+                                         C.c_int, C.c_char_p]
+        for case, fmt, bb, xx, format in (("csr_mm", 1, bvec, xvec, 2), ("csr_mm_nob", 1, None, None, 2), ("ell_mm_b", 5, bvec, None, 2),
+                                          ("csr_mmb", 1, bvec, xvec, 8), ("bsr_mmb_nov", 7, None, None, 8)):
+            path = tmp_path / f"{tag}_{case}.mtx"
+            for vformat, vname in ((1, "plain"), (2, "mm"), (3, "lis")):
+                vpath = tmp_path / f"{tag}_{case}_{vname}.vec"
+                rc = shim.lib.shim_output(fmt, n, ptr, idx, val, bb.ctypes.data if bb is not None else None,
+                                          xx.ctypes.data if xx is not None else None, format, str(path).encode(),
+                                          vformat, str(vpath).encode())
+                assert rc == 0, (tag, case, rc)
+                if bb is not None:
+                    files[(tag, case, vname)] = vpath.read_bytes()
+            files[(tag, case)] = path.read_bytes()
+    for key, data in files.items():
+        if key[0] != "b200":
+            continue
+        ref = files[("ref",) + key[1:]]
+        if key[1:] == ("csr_mm",):
+            # the reference's serial ASCII writer prints b a second time where x belongs
+            # (src/system/lis_output_mm.c:303 reads b->value[i] in the x loop); lis_b200 writes x.
+            gl, rl = data.split(b"\n"), ref.split(b"\n")
+            assert len(gl) == len(rl) and gl[:-n - 1] == rl[:-n - 1], key
+            assert rl[-n - 1:-1] == rl[-2 * n - 1:-n - 1], "reference quirk gone?"
+            assert [float(t.split()[1]) for t in gl[-n - 1:-1]] == list(xvec)
+        elif key[1:] == ("csr_mmb",):
+            # binary vector records {int i; <4 bytes of padding>; double value}: the reference writes
+            # whatever its stack held into the padding, lis_b200 zeros
+            nv = 2 * n * 16
+            assert data[:-nv] == ref[:-nv], key
+            ga = np.frombuffer(data[-nv:], np.uint8).reshape(-1, 16); ra = np.frombuffer(ref[-nv:], np.uint8).reshape(-1, 16)
+            assert np.array_equal(ga[:, :4], ra[:, :4]) and np.array_equal(ga[:, 8:], ra[:, 8:]) and not ga[:, 4:8].any(), key
+        else:
+            assert data == ref, key
+    # read back (ASCII and binary) with both libraries
+    for case in ("csr_mm", "csr_mmb", "ell_mm_b"):
+        for tag, shim in (("b200", b200), ("ref", ref_serial)):
+            a, rb, rx = shim.input_mm(str(tmp_path / f"b200_{case}.mtx"), "csr")
+            assert np.array_equal(a["ptr"], ptr) and np.array_equal(a["index"], idx), (case, tag)
+            H.assert_bits_equal(a["value"], val, f"{case} {tag}")
+            H.assert_bits_equal(rb, bvec, f"{case} {tag} b")
+            if case != "ell_mm_b":
+                H.assert_bits_equal(rx, xvec, f"{case} {tag} x")
+    # and the reference's own ASCII file (x block = b, see above) reads back the same way in both
+    for tag, shim in (("b200", b200), ("ref", ref_serial)):
+        a, rb, rx = shim.input_mm(str(tmp_path / "ref_csr_mm.mtx"), "csr")
+        H.assert_bits_equal(rb, bvec, tag); H.assert_bits_equal(rx, bvec, tag)
+
+
 def test_reference_fixture_testmat(b200):
     """test/testmat.mtx of the reference, when its tree is present"""
     path = "/root/reference/test/testmat.mtx"
