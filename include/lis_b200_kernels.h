@@ -122,6 +122,14 @@ int lisb200_cg_update(int n, double alpha, const double *d_p, const double *d_q,
 int lisb200_jacobi_dot(int n, const double *d_r, const double *d_dinv, double *d_z,
                        double *d_partial, unsigned int *d_counter, double *d_rho, void *stream);
 
+/* One link of the modified Gram-Schmidt chain of GMRES, src/solver/lis_solver_gmres.c:225-236:
+ * w += (scale * *d_alpha) * v, then norm ? sum w*w : <w,u> into *d_result.  *d_alpha was written by
+ * an earlier reduction on the same stream.  Same bits as lisb200_axpy_dev followed by
+ * lisb200_reduce(0 or 1); all of v, w, u must be 16-byte aligned (else cudaErrorInvalidValue: launch
+ * the two separately).                                                                          */
+int lisb200_mgs_step(int norm, int n, const double *d_alpha, double scale, const double *d_v, double *d_w, const double *d_u,
+                     double *d_partial, unsigned int *d_counter, double *d_result, void *stream);
+
 /* ---- matrix helpers ---------------------------------------------------------------------- */
 /* d[i] = first stored entry with index==i, else 0         src/matrix/lis_matrix_csr.c:540-553 */
 int lisb200_csr_get_diagonal(int n, const int *d_ptr, const int *d_idx, const double *d_val,

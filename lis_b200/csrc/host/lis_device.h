@@ -60,6 +60,8 @@ double        lisd_fetched(int slot);
 /* <x,y> into device slot `slot` without waiting; y += (scale * slot) * x reading it back on the device */
 LIS_INT       lisd_dot_to_slot(LIS_VECTOR x, LIS_VECTOR y, int slot);
 LIS_INT       lisd_axpy_from_slot(int slot, double scale, LIS_VECTOR x, LIS_VECTOR y);
+/* both in one pass: y += (scale * slot_in) * x; then <y,u> -> slot_out, or (u == NULL) ||y||_2 -> *nrm2 (waits) */
+LIS_INT       lisd_mgs_step(int slot_in, double scale, LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR u, int slot_out, LIS_REAL *nrm2);
 
 /* ---- matrix device mirror ---- */
 typedef struct lisd_csr {

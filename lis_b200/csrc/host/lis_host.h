@@ -34,6 +34,7 @@ LIS_INT lis_host_precon_lookup(const char *name);
 void    lis_host_print_rhistory(LIS_INT iter, LIS_REAL resid);
 LIS_INT lis_host_solver_malloc_work(LIS_SOLVER solver, LIS_INT worklen, LIS_INT first);
 LIS_INT lis_host_solver_residual(LIS_SOLVER solver, LIS_VECTOR r, LIS_REAL *res);
+LIS_INT lis_host_mgs(LIS_VECTOR *v, LIS_INT i, LIS_SCALAR *hcol, LIS_REAL *nrm);       /* modified Gram-Schmidt of v[i], lis_krylov.c */
 LIS_INT lis_host_ilu_create(LIS_SOLVER solver, LIS_PRECON precon);      /* lis_precon_ilu.c */
 void    lis_host_ilu_free(void *factors);
 LIS_INT lis_psolve_iluk(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);

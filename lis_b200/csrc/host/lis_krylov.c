@@ -190,6 +190,46 @@ LIS_INT lis_bicgstab(LIS_SOLVER solver)
     return LIS_MAXITER;
 }
 
+/* ================================================================== modified Gram-Schmidt
+ * w = v[i] against v[0..i): hcol[k] = <w,v_k>; w -= hcol[k] v_k; *nrm = ||w||_2
+ * (src/solver/lis_solver_gmres.c:225-236, lis_solver_fgmres.c the same loop).
+ * The reference waits for every dot.  On one rank the whole chain stays on the device: each axpy
+ * reads its coefficient from the slot the dot before it wrote, and shares its pass over w with the
+ * next dot (or with the norm that ends the chain): i+1 passes over w and one host wait per Krylov
+ * step instead of 2i+1 passes and i+1 waits.  Same arithmetic in the same order: same bits
+ * (LIS_B200_MGS=chain keeps axpy and dot as separate launches, LIS_B200_FUSE=0 also the waits). */
+LIS_INT lis_host_mgs(LIS_VECTOR *v, LIS_INT i, LIS_SCALAR *hcol, LIS_REAL *nrm)
+{
+    const char *mode = getenv("LIS_B200_MGS");
+    const int on_device = fuse_enabled() && lisd_nranks() == 1 && i <= LISD_NSCALARS;
+    LIS_VECTOR w = v[i];
+    LIS_SCALAR t;
+    LIS_INT k;
+    if (on_device && !(mode && strcmp(mode, "chain") == 0)) {
+        CHK(lisd_dot_to_slot(w, v[0], 0));
+        for (k = 0; k + 1 < i; k++) CHK(lisd_mgs_step((int)k, -1.0, v[k], w, v[k + 1], (int)k + 1, NULL));
+        CHK(lisd_dev_scalars_fetch(0, (int)i));
+        CHK(lisd_mgs_step((int)i - 1, -1.0, v[i - 1], w, NULL, 0, nrm));          /* waits for the stream */
+        for (k = 0; k < i; k++) hcol[k] = lisd_fetched((int)k);
+    } else if (on_device) {
+        for (k = 0; k < i; k++) {
+            CHK(lisd_dot_to_slot(w, v[k], (int)k));
+            CHK(lisd_axpy_from_slot((int)k, -1.0, v[k], w));
+        }
+        CHK(lisd_dev_scalars_fetch(0, (int)i));
+        CHK(lis_vector_nrm2(w, nrm));                                              /* waits for the stream */
+        for (k = 0; k < i; k++) hcol[k] = lisd_fetched((int)k);
+    } else {
+        for (k = 0; k < i; k++) {
+            CHK(lis_vector_dot(w, v[k], &t));
+            hcol[k] = t;
+            CHK(lisd_axpy(-t, v[k], w));
+        }
+        CHK(lis_vector_nrm2(w, nrm));
+    }
+    return LIS_SUCCESS;
+}
+
 /* ================================================================== GMRES(m) */
 LIS_INT lis_gmres(LIS_SOLVER solver)
 {
@@ -206,7 +246,6 @@ LIS_INT lis_gmres(LIS_SOLVER solver)
     LIS_INT iter, i, j, k, ii = 0, i1 = 0, iih, jj;
     LIS_INT err = LIS_SUCCESS;
     double time, ptime = 0.0;
-    const int mgs_on_device = fuse_enabled() && lisd_nranks() == 1;
 
     LIS_SCALAR *h = (LIS_SCALAR *)lis_malloc(sizeof(LIS_SCALAR) * (size_t)(h_dim + 1) * (size_t)(h_dim + 2), "lis_gmres::h");
     LIS_SCALAR *s = (LIS_SCALAR *)lis_calloc(sizeof(LIS_SCALAR) * (size_t)(m + 2), "lis_gmres::s");
@@ -243,22 +282,7 @@ LIS_INT lis_gmres(LIS_SOLVER solver)
              * pairs are chained on the device (the axpy reads its coefficient from the slot the dot
              * wrote) and the host collects h[0..i) with the norm that follows: one wait per Krylov
              * step instead of i+1.  Same kernels, same bits. */
-            if (mgs_on_device && i <= LISD_NSCALARS) {
-                for (k = 0; k < i; k++) {
-                    GCHK(lisd_dot_to_slot(v[i1], v[k], (int)k));
-                    GCHK(lisd_axpy_from_slot((int)k, -1.0, v[k], v[i1]));
-                }
-                GCHK(lisd_dev_scalars_fetch(0, (int)i));
-                GCHK(lis_vector_nrm2(v[i1], &t));           /* waits for the stream */
-                for (k = 0; k < i; k++) h[k + iih] = lisd_fetched((int)k);
-            } else {
-                for (k = 0; k < i; k++) {
-                    GCHK(lis_vector_dot(v[i1], v[k], &t));
-                    h[k + iih] = t;
-                    GCHK(lisd_axpy(-t, v[k], v[i1]));
-                }
-                GCHK(lis_vector_nrm2(v[i1], &t));
-            }
+            GCHK(lis_host_mgs(v, i, h + iih, &t));
             h[i1 + iih] = t;
             GCHK(lisd_scale(1.0 / t, v[i1]));
             /* Givens rotations on the new Hessenberg column */

@@ -689,12 +689,7 @@ LIS_INT lis_fgmres(LIS_SOLVER solver)
             ii = i - 1; i1 = i; iih = (i - 1) * h_dim;
             { const double t0 = lis_wtime(); FCHK(lis_psolve(solver, v[ii], z[ii])); ptime += lis_wtime() - t0; }
             FCHK(lisd_matvec(A, z[ii], v[i1]));
-            for (k = 0; k < i; k++) {
-                FCHK(lis_vector_dot(v[i1], v[k], &t));
-                h[k + iih] = t;
-                FCHK(lisd_axpy(-t, v[k], v[i1]));
-            }
-            FCHK(lis_vector_nrm2(v[i1], &t));
+            FCHK(lis_host_mgs(v, i, h + iih, &t));
             h[i1 + iih] = t;
             FCHK(lisd_scale(1.0 / t, v[i1]));
             for (k = 1; k <= ii; k++) {

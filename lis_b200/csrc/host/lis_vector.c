@@ -411,6 +411,33 @@ LIS_INT lisd_axpy_from_slot(int slot, double scale, LIS_VECTOR x, LIS_VECTOR y)
     LISD_LAUNCH(lisb200_axpy_dev(x->n, lisd_dev_scalar(slot), scale, x->value, y->value, lisd_stream()), "lis_vector_axpy");
 }
 
+/* y += (scale * slot_in) * x, then <y,u> -> slot_out (u != NULL) or ||y||_2 -> *nrm2 (u == NULL, waits) */
+LIS_INT lisd_mgs_step(int slot_in, double scale, LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR u, int slot_out, LIS_REAL *nrm2)
+{
+    LISD_PREP2(x, y, "gram-schmidt step");
+    if (u) { LIS_INT e_ = lis_vector_check_same(x, u); if (e_) return e_; e_ = lisd_vec_device(u); if (e_) return e_; }
+    if ((((size_t)x->value | (size_t)y->value | (size_t)(u ? u->value : NULL)) & 15) != 0) {
+        /* storage handed out by this library is 256-byte aligned; anything else takes the two launches,
+         * whose packed / scalar paths the fused kernel could not both mirror */
+        LIS_INT e_ = lisd_axpy_from_slot(slot_in, scale, x, y);
+        if (e_) return e_;
+        if (u) return lisd_dot_to_slot(y, u, slot_out);
+        return lis_vector_nrm2(y, nrm2);
+    }
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    LIS_INT err = lisd_check(lisb200_mgs_step(u == NULL, x->n, lisd_dev_scalar(slot_in), scale, x->value, y->value, u ? u->value : NULL,
+                                              partial, lisd_counter(), u ? lisd_dev_scalar(slot_out) : lisd_scalar_dev(0), lisd_stream()),
+                             "gram-schmidt step");
+    if (err || u) return err;
+    double rr;
+    err = lisd_reduce_finish(&rr, 1, 0);
+    if (err) return err;
+    *nrm2 = sqrt(rr);
+    return LIS_SUCCESS;
+}
+
 /* reductions: kernel -> mapped host scalar; ranks combined in rank order on the host */
 LIS_INT lisd_reduce(int kind, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *value)
 {

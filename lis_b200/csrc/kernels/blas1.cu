@@ -287,6 +287,50 @@ cg_update_kernel(int n, double alpha, const double *__restrict__ p, const double
     grid_finish<false, kRedThreads, 1>(mine, partial, counter, result, red);
 }
 
+// One link of GMRES' modified Gram-Schmidt chain (src/solver/lis_solver_gmres.c:225-236) in one pass:
+//   w += (scale * *alpha) * v        alpha = the previous link's <w,v>, still on the device
+//   kNorm ? sum w*w : <w,u>          the next link's coefficient / the norm that ends the chain
+// Unfused this is axpy (read v,w; write w) + dot (read w,u): 40 B per element; here 32 (24 for the
+// norm).  Element -> thread map, accumulators and tree are those of reduce_kernel<0/1>, the update
+// is AxpyDevF's: w and the scalar carry the same bits as the two separate launches.
+template <bool kNorm>
+__global__ void __launch_bounds__(kRedThreads)
+mgs_step_kernel(int n, const double *__restrict__ alpha, double scale, const double *__restrict__ v,
+                double *__restrict__ w, const double *__restrict__ u, bool vec,
+                double *partial, unsigned int *counter, double *result)
+{
+    __shared__ double red[32];
+    const int stride = gridDim.x * blockDim.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double a = mul(scale, *alpha);
+    double a0 = 0.0, a1 = 0.0;
+    if (vec) {
+        const int n2 = n >> 1;
+#pragma unroll 4
+        for (int i = t; i < n2; i += stride) {
+            const double2 vv = reinterpret_cast<const double2 *>(v)[i];
+            double2 wv = reinterpret_cast<double2 *>(w)[i];
+            wv.x = add(wv.x, mul(a, vv.x)); wv.y = add(wv.y, mul(a, vv.y));
+            reinterpret_cast<double2 *>(w)[i] = wv;
+            double2 uv = wv;
+            if (!kNorm) uv = reinterpret_cast<const double2 *>(u)[i];
+            a0 = add(a0, mul(wv.x, uv.x)); a1 = add(a1, mul(wv.y, uv.y));
+        }
+        if (t == 0 && (n & 1)) {
+            const int i = n - 1;
+            const double wv = add(w[i], mul(a, v[i]));
+            w[i] = wv; a0 = add(a0, mul(wv, kNorm ? wv : u[i]));
+        }
+    } else {
+        for (int i = t; i < n; i += stride) {
+            const double wv = add(w[i], mul(a, v[i]));
+            w[i] = wv; a0 = add(a0, mul(wv, kNorm ? wv : u[i]));
+        }
+    }
+    double mine[1] = { block_reduce<false, kRedThreads>(add(a0, a1), red) };
+    grid_finish<false, kRedThreads, 1>(mine, partial, counter, result, red);
+}
+
 // z = r .* dinv ; rho = <r,z>
 __global__ void __launch_bounds__(kRedThreads)
 jacobi_dot_kernel(int n, const double *__restrict__ r, const double *__restrict__ dinv,
@@ -432,6 +476,20 @@ extern "C" int lisb200_jacobi_dot(int n, const double *r, const double *dinv, do
     if (n <= 0) return (int)cudaMemsetAsync(rho, 0, sizeof(double), st);
     const bool vec = aligned16(r) && aligned16(dinv) && aligned16(z);
     jacobi_dot_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, r, dinv, z, vec, partial, counter, rho);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_mgs_step(int norm, int n, const double *d_alpha, double scale, const double *v, double *w, const double *u,
+                                double *partial, unsigned int *counter, double *result, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return (int)cudaMemsetAsync(result, 0, sizeof(double), st);
+    /* the packed path only where the separate axpy and reduction would both take theirs */
+    const bool vec = aligned16(v) && aligned16(w) && (norm || aligned16(u));
+    if (!vec && (aligned16(w) && (norm || aligned16(u)))) return (int)cudaErrorInvalidValue;   /* mixed alignment: launch separately */
+    if (norm) mgs_step_kernel<true><<<red_grid(n), kRedThreads, 0, st>>>(n, d_alpha, scale, v, w, w, vec, partial, counter, result);
+    else mgs_step_kernel<false><<<red_grid(n), kRedThreads, 0, st>>>(n, d_alpha, scale, v, w, u, vec, partial, counter, result);
     LISB_CHECK_LAUNCH();
     return 0;
 }

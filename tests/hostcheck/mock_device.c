@@ -142,6 +142,9 @@ int lisb200_cg_update(int n, double alpha, const double *p, const double *q, dou
 { (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); *rr = orc_dot(n, r, r, 1); return 0; }
 int lisb200_jacobi_dot(int n, const double *r, const double *dinv, double *z, double *partial, unsigned int *counter, double *rho, void *s)
 { (void)partial; (void)counter; (void)s; orc_pmul(n, r, dinv, z); *rho = orc_dot(n, r, z, 1); return 0; }
+int lisb200_mgs_step(int norm, int n, const double *da, double sc, const double *v, double *w, const double *u,
+                     double *partial, unsigned int *counter, double *result, void *s)
+{ (void)partial; (void)counter; (void)s; orc_axpy(n, sc * *da, v, w); *result = orc_dot(n, w, norm ? w : u, 1); return 0; }
 int lisb200_csr_get_diagonal(int n, const int *p, const int *i, const double *v, double *d, void *s)
 { (void)s; if (n > 0) orc_csr_get_diagonal(n, p, i, v, d); return 0; }
 

@@ -31,6 +31,7 @@ test_spmv_csr_both_kernels = G.test_spmv_csr_both_kernels
 test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
 test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
+test_gram_schmidt_fused_chain_same_bits = G.test_gram_schmidt_fused_chain_same_bits
 test_device_conversion_same_arrays_as_host = G.test_device_conversion_same_arrays_as_host
 test_device_conversion_falls_back_to_host_builder = G.test_device_conversion_falls_back_to_host_builder
 test_blas1_elementwise_bit_exact = G.test_blas1_elementwise_bit_exact
@@ -125,3 +126,33 @@ def test_emulator_catches_misalignment_and_overrun(b200, what, expect):
 # chunk that starts before its x entries have landed reads the previous contents of x.
 test_matvec_host_pipelined = G.test_matvec_host_pipelined
 test_matvec_host_pipelined_default_chunks = G.test_matvec_host_pipelined_default_chunks
+
+
+# ---- the reference's own drivers (test/*.c, unchanged) linked against the emulator build: their
+# transcripts against the same sources linked with the compiled reference
+import test_reference_drivers as D  # noqa: E402
+
+
+@pytest.fixture()
+def emu_drivers(b200, monkeypatch):
+    monkeypatch.setattr(D, "OURS", os.path.join(EMU_DIR, "_build", "drivers"))
+
+
+@pytest.mark.parametrize("driver,args,analytic", [("spmvtest1", (20000, 3), "1.414214e+00"), ("spmvtest3", (24, 24, 24, 2), None),
+                                                  ("spmvtest3b", (9, 8, 7, 2), None)])
+def test_spmvtest_drivers_emulated(emu_drivers, driver, args, analytic):
+    D.test_spmvtest_drivers(driver, args, analytic)
+
+
+@pytest.mark.parametrize("driver", ["spmvtest4", "spmvtest5"])
+def test_spmvtest_file_drivers_emulated(emu_drivers, tmp_path, driver):
+    D.test_spmvtest_file_drivers(tmp_path, driver)
+
+
+@pytest.mark.parametrize("opts", ["-i cg -p jacobi", "-i bicgstab -p ssor", "-i gmres -restart 30 -p jacobi", "-i cg -p jacobi -storage ell"])
+def test_test3_driver_emulated(emu_drivers, tmp_path, opts):
+    D.test_test3_driver(tmp_path, opts)
+
+
+def test_test1_driver_emulated(emu_drivers, tmp_path):
+    D.test_test1_driver_matrix_market(tmp_path)

@@ -251,6 +251,26 @@ def test_device_conversion_falls_back_to_host_builder(b200, monkeypatch):
                 assert np.array_equal(got[key], want[key]), (fmt, key)
 
 
+@pytest.mark.parametrize("opts", ["-i gmres -restart 30 -p jacobi", "-i gmres -restart 7 -p none", "-i fgmres -restart 20 -p ssor"])
+def test_gram_schmidt_fused_chain_same_bits(b200, oracle, monkeypatch, opts):
+    """GMRES / FGMRES orthogonalisation: axpy fused with the following dot / norm (mgs_step_kernel),
+    axpy and dot as separate launches chained on the device, and the reference's call-for-call
+    sequence with a host wait per dot must give the same residual history and solution, bit for bit"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(12, 11, 10)), ("unsym", H.random_csr(1501, 6, 3)), ("odd", H.poisson1d(333))):
+        b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        runs = {}
+        for mode, env in (("fused", {}), ("chain", {"LIS_B200_MGS": "chain"}), ("waits", {"LIS_B200_FUSE": "0"})):
+            for key in ("LIS_B200_MGS", "LIS_B200_FUSE"):
+                monkeypatch.delenv(key, raising=False)
+            for key, v in env.items():
+                monkeypatch.setenv(key, v)
+            runs[mode] = b200.solve(ptr, idx, val, b, opts + " -maxiter 70")
+        for mode in ("chain", "waits"):
+            assert runs[mode]["iter"] == runs["fused"]["iter"] and runs[mode]["status"] == runs["fused"]["status"], (name, opts, mode)
+            H.assert_bits_equal(runs[mode]["rhistory"], runs["fused"]["rhistory"], f"{name} {opts} rhistory fused vs {mode}")
+            H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
+
+
 def test_blas1_length_mismatch_is_ill_arg(b200):
     for op in ("axpy", "xpay", "copy", "dot"):
         assert b200.vec_mismatch(op) == 1          # LIS_ERR_ILL_ARG, lis_vector_opv.c:158-163
