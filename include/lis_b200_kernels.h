@@ -126,9 +126,16 @@ int lisb200_jacobi_dot(int n, const double *d_r, const double *d_dinv, double *d
  * w += (scale * *d_alpha) * v, then norm ? sum w*w : <w,u> into *d_result.  *d_alpha was written by
  * an earlier reduction on the same stream.  Same bits as lisb200_axpy_dev followed by
  * lisb200_reduce(0 or 1); all of v, w, u must be 16-byte aligned (else cudaErrorInvalidValue: launch
- * the two separately).                                                                          */
+ * the two separately).  d_alpha == NULL: the coefficient is `scale` itself, i.e. axpy + norm / dot
+ * in one pass (BiCGSTAB's s = r - alpha v; ||s||, src/solver/lis_solver_bicgstab.c:233-236).   */
 int lisb200_mgs_step(int norm, int n, const double *d_alpha, double scale, const double *d_v, double *d_w, const double *d_u,
                      double *d_partial, unsigned int *d_counter, double *d_result, void *stream);
+
+/* BiCGSTAB: p = r + beta*(p - omega*v)    src/solver/lis_solver_bicgstab.c:212-213 (axpy then xpay) */
+int lisb200_bicgstab_p(int n, double omega, double beta, const double *d_v, const double *d_r, double *d_p, void *stream);
+/* BiCGSTAB: x += alpha*phat; x += omega*shat; r += (-omega)*t; rr = sum r*r     :272-279           */
+int lisb200_bicgstab_update(int n, double alpha, double omega, const double *d_phat, const double *d_shat, const double *d_t,
+                            double *d_x, double *d_r, double *d_partial, unsigned int *d_counter, double *d_rr, void *stream);
 
 /* ---- matrix helpers ---------------------------------------------------------------------- */
 /* d[i] = first stored entry with index==i, else 0         src/matrix/lis_matrix_csr.c:540-553 */

@@ -8,6 +8,8 @@
  * (lis_vector_dot / nrm2) is the one point per step where the host waits, because its scalar
  * feeds the next step.
  *
+ * BiCGSTAB fuses its vector updates with the norms that follow them (bit-identical to the separate
+ * calls: same element -> thread map and summation tree); GMRES fuses the Gram-Schmidt chain.
  * CG has a fused path (default) for CSR/ELL/... + none/Jacobi: psolve+dot, SpMV+dot and
  * axpy+axpy+nrm2 run as three kernels per iteration instead of eight.  The fused kernels
  * produce the same vector bits as the unfused sequence; dot values may differ in the last
@@ -118,6 +120,10 @@ LIS_INT lis_bicgstab(LIS_SOLVER solver)
     LIS_INT iter;
     double time, ptime = 0.0;
     const int fused = fuse_enabled();
+    /* vector updates fused with each other and with the norm that follows (LIS_B200_BICGSTAB=calls: one
+     * launch per reference call); the norm must be the 2-norm the fused kernels compute */
+    const int fusedv = fused && !(getenv("LIS_B200_BICGSTAB") && strcmp(getenv("LIS_B200_BICGSTAB"), "calls") == 0);
+    const int fusedn = fusedv && solver->options[LIS_OPTIONS_CONV_COND] != LIS_CONV_COND_NRM1_B;
 
     CHK(lisd_set_all(0.0, p));
     CHK(lisd_set_all(0.0, phat));
@@ -141,8 +147,11 @@ LIS_INT lis_bicgstab(LIS_SOLVER solver)
             CHK(lisd_copy(r, p));
         } else {
             beta = (rho / rho_old) * (alpha / omega);
-            CHK(lisd_axpy(-omega, v, p));       /* p = r + beta*(p - omega*v) */
-            CHK(lisd_xpay(r, beta, p));
+            if (fusedv) CHK(lisd_bicgstab_p(omega, beta, v, r, p));     /* p = r + beta*(p - omega*v), one pass */
+            else {
+                CHK(lisd_axpy(-omega, v, p));
+                CHK(lisd_xpay(r, beta, p));
+            }
         }
         time = lis_wtime();
         CHK(lis_psolve(solver, p, phat));
@@ -150,8 +159,13 @@ LIS_INT lis_bicgstab(LIS_SOLVER solver)
         CHK(lisd_matvec(A, phat, v));
         CHK(lis_vector_dot(rtld, v, &tmpdot1));
         alpha = rho / tmpdot1;
-        CHK(lisd_axpy(-alpha, v, r));           /* s = r - alpha*v */
-        CHK(lis_host_solver_residual(solver, s, &nrm2));
+        if (fusedn) {                           /* s = r - alpha*v ; ||s|| */
+            CHK(lisd_axpy_nrm2(-alpha, v, r, &nrm2));
+            nrm2 = nrm2 * solver->bnrm;
+        } else {
+            CHK(lisd_axpy(-alpha, v, r));
+            CHK(lis_host_solver_residual(solver, s, &nrm2));
+        }
         if (nrm2 <= tol) {
             record(solver, output, iter, nrm2);
             CHK(lisd_axpy(alpha, phat, x));
@@ -171,10 +185,15 @@ LIS_INT lis_bicgstab(LIS_SOLVER solver)
             CHK(lis_vector_dot(t, t, &tmpdot2));
         }
         omega = tmpdot1 / tmpdot2;
-        CHK(lisd_axpy(alpha, phat, x));
-        CHK(lisd_axpy(omega, shat, x));
-        CHK(lisd_axpy(-omega, t, r));
-        CHK(lis_host_solver_residual(solver, r, &nrm2));
+        if (fusedn) {                           /* x += alpha*phat + omega*shat ; r -= omega*t ; ||r|| */
+            CHK(lisd_bicgstab_update(alpha, omega, phat, shat, t, x, r, &nrm2));
+            nrm2 = nrm2 * solver->bnrm;
+        } else {
+            CHK(lisd_axpy(alpha, phat, x));
+            CHK(lisd_axpy(omega, shat, x));
+            CHK(lisd_axpy(-omega, t, r));
+            CHK(lis_host_solver_residual(solver, r, &nrm2));
+        }
         record(solver, output, iter, nrm2);
         if (tol >= nrm2) {
             solver->retcode = LIS_SUCCESS; solver->iter = iter; solver->resid = nrm2; solver->ptime = ptime;

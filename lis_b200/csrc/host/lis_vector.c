@@ -438,6 +438,71 @@ LIS_INT lisd_mgs_step(int slot_in, double scale, LIS_VECTOR x, LIS_VECTOR y, LIS
     return LIS_SUCCESS;
 }
 
+static int all_aligned16(const void *a, const void *b, const void *c, const void *d, const void *e)
+{
+    return ((((size_t)a) | ((size_t)b) | ((size_t)c) | ((size_t)d) | ((size_t)e)) & 15) == 0;
+}
+
+/* y += alpha*x ; *nrm2 = ||y||_2  (one pass; waits) */
+LIS_INT lisd_axpy_nrm2(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_REAL *nrm2)
+{
+    LISD_PREP2(x, y, "axpy+nrm2");
+    if (!all_aligned16(x->value, y->value, NULL, NULL, NULL)) {
+        LIS_INT e_ = lisd_axpy(alpha, x, y);
+        return e_ ? e_ : lis_vector_nrm2(y, nrm2);
+    }
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    LIS_INT err = lisd_check(lisb200_mgs_step(1, x->n, NULL, alpha, x->value, y->value, NULL, partial, lisd_counter(),
+                                              lisd_scalar_dev(0), lisd_stream()), "axpy+nrm2");
+    if (err) return err;
+    double rr;
+    err = lisd_reduce_finish(&rr, 1, 0);
+    if (err) return err;
+    *nrm2 = sqrt(rr);
+    return LIS_SUCCESS;
+}
+
+/* p = r + beta*(p - omega*v) */
+LIS_INT lisd_bicgstab_p(LIS_SCALAR omega, LIS_SCALAR beta, LIS_VECTOR v, LIS_VECTOR r, LIS_VECTOR p)
+{
+    LISD_PREP2(v, p, "bicgstab p update");
+    { LIS_INT e_ = lis_vector_check_same(v, r); if (e_) return e_; e_ = lisd_vec_device(r); if (e_) return e_; }
+    if (!all_aligned16(v->value, r->value, p->value, NULL, NULL)) {
+        LIS_INT e_ = lisd_axpy(-omega, v, p);
+        return e_ ? e_ : lisd_xpay(r, beta, p);
+    }
+    LISD_LAUNCH(lisb200_bicgstab_p(v->n, omega, beta, v->value, r->value, p->value, lisd_stream()), "bicgstab p update");
+}
+
+/* x += alpha*phat ; x += omega*shat ; r -= omega*t ; *nrm2 = ||r||_2  (one pass; waits) */
+LIS_INT lisd_bicgstab_update(LIS_SCALAR alpha, LIS_SCALAR omega, LIS_VECTOR phat, LIS_VECTOR shat, LIS_VECTOR t,
+                             LIS_VECTOR x, LIS_VECTOR r, LIS_REAL *nrm2)
+{
+    LISD_PREP2(phat, shat, "bicgstab update");
+    { LIS_INT e_ = lis_vector_check_same(phat, t); if (e_) return e_; e_ = lis_vector_check_same(phat, x); if (e_) return e_;
+      e_ = lis_vector_check_same(phat, r); if (e_) return e_;
+      e_ = lisd_vec_device(t); if (e_) return e_; e_ = lisd_vec_device(x); if (e_) return e_; e_ = lisd_vec_device(r); if (e_) return e_; }
+    if (!all_aligned16(phat->value, shat->value, t->value, x->value, r->value)) {
+        LIS_INT e_ = lisd_axpy(alpha, phat, x);
+        if (!e_) e_ = lisd_axpy(omega, shat, x);
+        if (!e_) e_ = lisd_axpy(-omega, t, r);
+        return e_ ? e_ : lis_vector_nrm2(r, nrm2);
+    }
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    LIS_INT err = lisd_check(lisb200_bicgstab_update(phat->n, alpha, omega, phat->value, shat->value, t->value, x->value, r->value,
+                                                     partial, lisd_counter(), lisd_scalar_dev(0), lisd_stream()), "bicgstab update");
+    if (err) return err;
+    double rr;
+    err = lisd_reduce_finish(&rr, 1, 0);
+    if (err) return err;
+    *nrm2 = sqrt(rr);
+    return LIS_SUCCESS;
+}
+
 /* reductions: kernel -> mapped host scalar; ranks combined in rank order on the host */
 LIS_INT lisd_reduce(int kind, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *value)
 {

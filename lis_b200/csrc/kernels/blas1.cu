@@ -169,6 +169,18 @@ struct SwapF {
         reinterpret_cast<double2 *>(x)[i] = b; reinterpret_cast<double2 *>(y)[i] = a;
     }
 };
+struct BicgstabPF {     // p = r + beta*(p + nomega*v): axpy(-omega,v,p) then xpay(r,beta,p), one pass
+    double nomega, beta; const double *v; const double *r; double *p;
+    __device__ void one(int i) const { p[i] = add(r[i], mul(beta, add(p[i], mul(nomega, v[i])))); }
+    __device__ void vec2(int i) const {
+        const double2 vv = reinterpret_cast<const double2 *>(v)[i];
+        const double2 rv = reinterpret_cast<const double2 *>(r)[i];
+        double2 pv = reinterpret_cast<double2 *>(p)[i];
+        pv.x = add(rv.x, mul(beta, add(pv.x, mul(nomega, vv.x))));
+        pv.y = add(rv.y, mul(beta, add(pv.y, mul(nomega, vv.y))));
+        reinterpret_cast<double2 *>(p)[i] = pv;
+    }
+};
 struct GatherF {
     const int *idx; const double *x; double *out;
     __device__ void one(int i) const { out[i] = x[idx[i]]; }
@@ -226,22 +238,36 @@ reduce_kernel(int n, const double *__restrict__ x, const double *__restrict__ y,
     grid_finish<kMax, kRedThreads, 1>(mine, partial, counter, result, red);
 }
 
-// r[0] = <a,b>, r[1] = <a,a>
+// r[0] = <a,b>, r[1] = <a,a>: one pass over a; element -> thread map, accumulators and tree of
+// reduce_kernel<0> / <1>, so both scalars carry the bits of the two separate reductions
 __global__ void __launch_bounds__(kRedThreads)
-dot2_kernel(int n, const double *__restrict__ a, const double *__restrict__ b,
+dot2_kernel(int n, const double *__restrict__ a, const double *__restrict__ b, bool vec,
             double *partial, unsigned int *counter, double *result)
 {
     __shared__ double red[32];
     const int stride = gridDim.x * blockDim.x;
-    double s0 = 0.0, s1 = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double av = a[i], bv = b[i];
-        s0 = add(s0, mul(av, bv));
-        s1 = add(s1, mul(av, av));
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+    if (vec) {
+        const int n2 = n >> 1;
+#pragma unroll 4
+        for (int i = t; i < n2; i += stride) {
+            const double2 av = reinterpret_cast<const double2 *>(a)[i];
+            const double2 bv = reinterpret_cast<const double2 *>(b)[i];
+            s0 = add(s0, mul(av.x, bv.x)); s1 = add(s1, mul(av.y, bv.y));
+            q0 = add(q0, mul(av.x, av.x)); q1 = add(q1, mul(av.y, av.y));
+        }
+        if (t == 0 && (n & 1)) { s0 = add(s0, mul(a[n - 1], b[n - 1])); q0 = add(q0, mul(a[n - 1], a[n - 1])); }
+    } else {
+        for (int i = t; i < n; i += stride) {
+            const double av = a[i], bv = b[i];
+            s0 = add(s0, mul(av, bv));
+            q0 = add(q0, mul(av, av));
+        }
     }
     double mine[2];
-    mine[0] = block_reduce<false, kRedThreads>(s0, red);
-    mine[1] = block_reduce<false, kRedThreads>(s1, red);
+    mine[0] = block_reduce<false, kRedThreads>(add(s0, s1), red);
+    mine[1] = block_reduce<false, kRedThreads>(add(q0, q1), red);
     grid_finish<false, kRedThreads, 2>(mine, partial, counter, result, red);
 }
 
@@ -302,7 +328,7 @@ mgs_step_kernel(int n, const double *__restrict__ alpha, double scale, const dou
     __shared__ double red[32];
     const int stride = gridDim.x * blockDim.x;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const double a = mul(scale, *alpha);
+    const double a = alpha ? mul(scale, *alpha) : scale;     // no device coefficient: `scale` is the coefficient (plain axpy)
     double a0 = 0.0, a1 = 0.0;
     if (vec) {
         const int n2 = n >> 1;
@@ -325,6 +351,53 @@ mgs_step_kernel(int n, const double *__restrict__ alpha, double scale, const dou
         for (int i = t; i < n; i += stride) {
             const double wv = add(w[i], mul(a, v[i]));
             w[i] = wv; a0 = add(a0, mul(wv, kNorm ? wv : u[i]));
+        }
+    }
+    double mine[1] = { block_reduce<false, kRedThreads>(add(a0, a1), red) };
+    grid_finish<false, kRedThreads, 1>(mine, partial, counter, result, red);
+}
+
+// BiCGSTAB's closing updates (src/solver/lis_solver_bicgstab.c:272-279) in one pass:
+//   x += alpha*phat ; x += omega*shat ; r += (-omega)*t ; rr = sum r*r
+// 56 B per element instead of 80 for three axpys and a norm; bits of x, r and rr unchanged
+// (the two x updates stay two rounded steps; thread map and tree of reduce_kernel<1>).
+__global__ void __launch_bounds__(kRedThreads)
+bicgstab_update_kernel(int n, double alpha, double omega, const double *__restrict__ phat, const double *__restrict__ shat,
+                       const double *__restrict__ tv, double *__restrict__ x, double *__restrict__ r, bool vec,
+                       double *partial, unsigned int *counter, double *result)
+{
+    __shared__ double red[32];
+    const int stride = gridDim.x * blockDim.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double no = -omega;
+    double a0 = 0.0, a1 = 0.0;
+    if (vec) {
+        const int n2 = n >> 1;
+#pragma unroll 2
+        for (int i = t; i < n2; i += stride) {
+            const double2 pv = reinterpret_cast<const double2 *>(phat)[i];
+            const double2 sv = reinterpret_cast<const double2 *>(shat)[i];
+            const double2 tt = reinterpret_cast<const double2 *>(tv)[i];
+            double2 xv = reinterpret_cast<double2 *>(x)[i];
+            double2 rv = reinterpret_cast<double2 *>(r)[i];
+            xv.x = add(add(xv.x, mul(alpha, pv.x)), mul(omega, sv.x));
+            xv.y = add(add(xv.y, mul(alpha, pv.y)), mul(omega, sv.y));
+            rv.x = add(rv.x, mul(no, tt.x)); rv.y = add(rv.y, mul(no, tt.y));
+            reinterpret_cast<double2 *>(x)[i] = xv;
+            reinterpret_cast<double2 *>(r)[i] = rv;
+            a0 = add(a0, mul(rv.x, rv.x)); a1 = add(a1, mul(rv.y, rv.y));
+        }
+        if (t == 0 && (n & 1)) {
+            const int i = n - 1;
+            x[i] = add(add(x[i], mul(alpha, phat[i])), mul(omega, shat[i]));
+            const double rv = add(r[i], mul(no, tv[i]));
+            r[i] = rv; a0 = add(a0, mul(rv, rv));
+        }
+    } else {
+        for (int i = t; i < n; i += stride) {
+            x[i] = add(add(x[i], mul(alpha, phat[i])), mul(omega, shat[i]));
+            const double rv = add(r[i], mul(no, tv[i]));
+            r[i] = rv; a0 = add(a0, mul(rv, rv));
         }
     }
     double mine[1] = { block_reduce<false, kRedThreads>(add(a0, a1), red) };
@@ -452,7 +525,7 @@ extern "C" int lisb200_dot2(int n, const double *a, const double *b, double *par
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= 0) return (int)cudaMemsetAsync(result2, 0, 2 * sizeof(double), st);
-    dot2_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, a, b, partial, counter, result2);
+    dot2_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, a, b, aligned16(a) && aligned16(b), partial, counter, result2);
     LISB_CHECK_LAUNCH();
     return 0;
 }
@@ -490,6 +563,20 @@ extern "C" int lisb200_mgs_step(int norm, int n, const double *d_alpha, double s
     if (!vec && (aligned16(w) && (norm || aligned16(u)))) return (int)cudaErrorInvalidValue;   /* mixed alignment: launch separately */
     if (norm) mgs_step_kernel<true><<<red_grid(n), kRedThreads, 0, st>>>(n, d_alpha, scale, v, w, w, vec, partial, counter, result);
     else mgs_step_kernel<false><<<red_grid(n), kRedThreads, 0, st>>>(n, d_alpha, scale, v, w, u, vec, partial, counter, result);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_bicgstab_p(int n, double omega, double beta, const double *v, const double *r, double *p, void *s)
+{ return launch_ew(n, BicgstabPF{-omega, beta, v, r, p}, aligned16(v) && aligned16(r) && aligned16(p), s); }
+
+extern "C" int lisb200_bicgstab_update(int n, double alpha, double omega, const double *phat, const double *shat, const double *t,
+                                       double *x, double *r, double *partial, unsigned int *counter, double *rr, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return (int)cudaMemsetAsync(rr, 0, sizeof(double), st);
+    const bool vec = aligned16(phat) && aligned16(shat) && aligned16(t) && aligned16(x) && aligned16(r);
+    bicgstab_update_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, alpha, omega, phat, shat, t, x, r, vec, partial, counter, rr);
     LISB_CHECK_LAUNCH();
     return 0;
 }

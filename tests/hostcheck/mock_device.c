@@ -144,7 +144,12 @@ int lisb200_jacobi_dot(int n, const double *r, const double *dinv, double *z, do
 { (void)partial; (void)counter; (void)s; orc_pmul(n, r, dinv, z); *rho = orc_dot(n, r, z, 1); return 0; }
 int lisb200_mgs_step(int norm, int n, const double *da, double sc, const double *v, double *w, const double *u,
                      double *partial, unsigned int *counter, double *result, void *s)
-{ (void)partial; (void)counter; (void)s; orc_axpy(n, sc * *da, v, w); *result = orc_dot(n, w, norm ? w : u, 1); return 0; }
+{ (void)partial; (void)counter; (void)s; orc_axpy(n, da ? sc * *da : sc, v, w); *result = orc_dot(n, w, norm ? w : u, 1); return 0; }
+int lisb200_bicgstab_p(int n, double omega, double beta, const double *v, const double *r, double *p, void *s)
+{ (void)s; orc_axpy(n, -omega, v, p); orc_xpay(n, r, beta, p); return 0; }
+int lisb200_bicgstab_update(int n, double alpha, double omega, const double *phat, const double *shat, const double *t,
+                            double *x, double *r, double *partial, unsigned int *counter, double *rr, void *s)
+{ (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, phat, x); orc_axpy(n, omega, shat, x); orc_axpy(n, -omega, t, r); *rr = orc_dot(n, r, r, 1); return 0; }
 int lisb200_csr_get_diagonal(int n, const int *p, const int *i, const double *v, double *d, void *s)
 { (void)s; if (n > 0) orc_csr_get_diagonal(n, p, i, v, d); return 0; }
 

@@ -31,6 +31,7 @@ test_spmv_csr_both_kernels = G.test_spmv_csr_both_kernels
 test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
 test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
+test_bicgstab_fused_updates_same_bits = G.test_bicgstab_fused_updates_same_bits
 test_gram_schmidt_fused_chain_same_bits = G.test_gram_schmidt_fused_chain_same_bits
 test_device_conversion_same_arrays_as_host = G.test_device_conversion_same_arrays_as_host
 test_device_conversion_falls_back_to_host_builder = G.test_device_conversion_falls_back_to_host_builder

@@ -271,6 +271,26 @@ def test_gram_schmidt_fused_chain_same_bits(b200, oracle, monkeypatch, opts):
             H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
 
 
+@pytest.mark.parametrize("opts", ["-i bicgstab -p jacobi", "-i bicgstab -p ssor", "-i bicgstab -p none -maxiter 60"])
+def test_bicgstab_fused_updates_same_bits(b200, oracle, monkeypatch, opts):
+    """BiCGSTAB with its vector updates fused (p update; s = r - alpha v with ||s||; x, r updates with
+    ||r||; <t,s> with <t,t>), with one launch per reference call for the updates, and with every
+    fusion off: same iteration count, residual history and solution, bit for bit"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(12, 11, 10)), ("unsym", H.random_csr(1501, 6, 3)), ("odd", H.poisson1d(333))):
+        b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        runs = {}
+        for mode, env in (("fused", {}), ("calls", {"LIS_B200_BICGSTAB": "calls"}), ("off", {"LIS_B200_FUSE": "0"})):
+            for key in ("LIS_B200_BICGSTAB", "LIS_B200_FUSE"):
+                monkeypatch.delenv(key, raising=False)
+            for key, v in env.items():
+                monkeypatch.setenv(key, v)
+            runs[mode] = b200.solve(ptr, idx, val, b, opts)
+        for mode in ("calls", "off"):
+            assert runs[mode]["iter"] == runs["fused"]["iter"] and runs[mode]["status"] == runs["fused"]["status"], (name, opts, mode)
+            H.assert_bits_equal(runs[mode]["rhistory"], runs["fused"]["rhistory"], f"{name} {opts} rhistory fused vs {mode}")
+            H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
+
+
 def test_blas1_length_mismatch_is_ill_arg(b200):
     for op in ("axpy", "xpay", "copy", "dot"):
         assert b200.vec_mismatch(op) == 1          # LIS_ERR_ILL_ARG, lis_vector_opv.c:158-163
