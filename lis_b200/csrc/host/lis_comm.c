@@ -630,6 +630,7 @@ static LIS_INT halo_exchange_raw(LIS_COMMTABLE t, LIS_INT n, double *x)
 }
 
 LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x) { return halo_exchange_raw(A->commtable, A->n, x->value); }
+LIS_INT lisd_halo_exchange_raw(LIS_MATRIX A, double *d_x) { return halo_exchange_raw(A->commtable, A->n, d_x); }
 
 /* public seam of the reference (src/matrix/lis_matrix_mpi.c:834): x has np entries, the
  * halo is received into x[n .. np).  Host-synchronous like every public entry point. */

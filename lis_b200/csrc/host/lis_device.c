@@ -21,6 +21,7 @@ typedef struct {
     cudaStream_t s_in, s_out;
     cudaEvent_t *ev; int nev;
     cudaEvent_t ev_fork, ev_join;
+    double *stage_x, *stage_y; size_t stage_xn, stage_yn;      /* plain device staging of the pipelined product */
 } lisd_ctx_t;
 
 static lisd_ctx_t g_ctx;
@@ -94,6 +95,8 @@ void lisd_shutdown(void)
     if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
     if (g_ctx.dev_scalars) cudaFree(g_ctx.dev_scalars);
     if (g_ctx.h_fetch) cudaFreeHost(g_ctx.h_fetch);
+    if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
+    if (g_ctx.stage_y) cudaFree(g_ctx.stage_y);
     for (int i = 0; i < g_ctx.nev; i++) cudaEventDestroy(g_ctx.ev[i]);
     free(g_ctx.ev);
     if (g_ctx.s_in) { cudaEventDestroy(g_ctx.ev_fork); cudaEventDestroy(g_ctx.ev_join); cudaStreamDestroy(g_ctx.s_in); cudaStreamDestroy(g_ctx.s_out); }
@@ -268,6 +271,36 @@ LIS_INT lisd_pipe_begin(int nchunks)
     e = cudaEventRecord(g_ctx.ev_fork, g_ctx.stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.s_in, g_ctx.ev_fork, 0);
     return lisd_check((int)e, "copy pipeline");
+}
+
+/* Staging vectors in plain device memory (cudaMalloc): copies between pinned host memory and such
+ * memory are asynchronous by specification, which vector storage (managed memory) does not
+ * promise.  Cached; grown on demand. */
+LIS_INT lisd_pipe_staging(size_t xcount, size_t ycount, double **xs, double **ys)
+{
+    if (xcount > g_ctx.stage_xn) {
+        lisd_sync();
+        if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
+        g_ctx.stage_x = NULL; g_ctx.stage_xn = 0;
+        if (cudaMalloc((void **)&g_ctx.stage_x, (xcount + 8) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(xcount * sizeof(double)); return LIS_ERR_OUT_OF_MEMORY; }
+        g_ctx.stage_xn = xcount;
+    }
+    if (ycount > g_ctx.stage_yn) {
+        lisd_sync();
+        if (g_ctx.stage_y) cudaFree(g_ctx.stage_y);
+        g_ctx.stage_y = NULL; g_ctx.stage_yn = 0;
+        if (cudaMalloc((void **)&g_ctx.stage_y, (ycount + 8) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(ycount * sizeof(double)); return LIS_ERR_OUT_OF_MEMORY; }
+        g_ctx.stage_yn = ycount;
+    }
+    *xs = g_ctx.stage_x; *ys = g_ctx.stage_y;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lisd_d2d(void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return LIS_SUCCESS;
+    g_ctx.busy = 1;
+    return lisd_check((int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream), "device copy");
 }
 
 LIS_INT lisd_pipe_h2d(int c, void *dst, const void *src, size_t bytes)

@@ -44,6 +44,8 @@ LIS_INT lisd_pipe_h2d(int c, void *dst, const void *src, size_t bytes); /* queue
 LIS_INT lisd_pipe_wait_in(int c);                                       /* main stream waits for chunk c's input */
 LIS_INT lisd_pipe_d2h(int c, void *dst, const void *src, size_t bytes); /* after what the main stream holds now */
 LIS_INT lisd_pipe_end(void);                                            /* main stream joins the copy-out stream */
+LIS_INT lisd_pipe_staging(size_t xcount, size_t ycount, double **xs, double **ys);   /* cached cudaMalloc'ed staging vectors */
+LIS_INT lisd_d2d(void *dst, const void *src, size_t bytes);             /* async on the main stream */
 
 /* ---- vectors: residency tracking of managed storage ---- */
 LIS_INT lisd_vec_device(LIS_VECTOR v);              /* make resident before a kernel touches it */
@@ -168,6 +170,7 @@ LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout);
 LIS_INT lisd_matrix_g2l(LIS_MATRIX A);              /* global -> local+halo column numbering */
 void    lisd_commtable_destroy(LIS_COMMTABLE t);
 LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x);   /* async on the stream */
+LIS_INT lisd_halo_exchange_raw(LIS_MATRIX A, double *d_x); /* same on a raw device array of np entries */
 
 #ifdef __cplusplus
 }
