@@ -22,6 +22,7 @@ typedef struct {
     cudaEvent_t *ev; int nev;
     cudaEvent_t ev_fork, ev_join;
     double *stage_x, *stage_y; size_t stage_xn, stage_yn;      /* plain device staging of the pipelined product */
+    cudaStream_t s_aux; cudaEvent_t ev_aux_fork, ev_aux_join;  /* second compute stream (interior rows during the halo exchange) */
 } lisd_ctx_t;
 
 static lisd_ctx_t g_ctx;
@@ -95,6 +96,7 @@ void lisd_shutdown(void)
     if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
     if (g_ctx.dev_scalars) cudaFree(g_ctx.dev_scalars);
     if (g_ctx.h_fetch) cudaFreeHost(g_ctx.h_fetch);
+    if (g_ctx.s_aux) { cudaEventDestroy(g_ctx.ev_aux_fork); cudaEventDestroy(g_ctx.ev_aux_join); cudaStreamDestroy(g_ctx.s_aux); }
     if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
     if (g_ctx.stage_y) cudaFree(g_ctx.stage_y);
     for (int i = 0; i < g_ctx.nev; i++) cudaEventDestroy(g_ctx.ev[i]);
@@ -280,7 +282,8 @@ LIS_INT lisd_pipe_staging(size_t xcount, size_t ycount, double **xs, double **ys
 {
     if (xcount > g_ctx.stage_xn) {
         lisd_sync();
-        if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
+        if (g_ctx.s_aux) { cudaEventDestroy(g_ctx.ev_aux_fork); cudaEventDestroy(g_ctx.ev_aux_join); cudaStreamDestroy(g_ctx.s_aux); }
+    if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
         g_ctx.stage_x = NULL; g_ctx.stage_xn = 0;
         if (cudaMalloc((void **)&g_ctx.stage_x, (xcount + 8) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(xcount * sizeof(double)); return LIS_ERR_OUT_OF_MEMORY; }
         g_ctx.stage_xn = xcount;
@@ -330,6 +333,32 @@ LIS_INT lisd_pipe_end(void)
     if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.stream, g_ctx.ev_join, 0);
     g_ctx.busy = 1;
     return lisd_check((int)e, "copy pipeline");
+}
+
+/* ---- second compute stream -----------------------------------------------------------------
+ * lisd_aux_fork: work enqueued on the returned stream from now on starts behind everything the main
+ * stream holds at this point; lisd_aux_join: the main stream continues behind it. */
+LIS_INT lisd_aux_fork(void **stream)
+{
+    cudaError_t e = cudaSuccess;
+    if (g_ctx.s_aux == NULL) {
+        e = cudaStreamCreateWithFlags(&g_ctx.s_aux, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ctx.ev_aux_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ctx.ev_aux_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) { g_ctx.s_aux = NULL; return lisd_check((int)e, "second stream setup"); }
+    }
+    e = cudaEventRecord(g_ctx.ev_aux_fork, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.s_aux, g_ctx.ev_aux_fork, 0);
+    *stream = (void *)g_ctx.s_aux;
+    return lisd_check((int)e, "second stream");
+}
+
+LIS_INT lisd_aux_join(void)
+{
+    cudaError_t e = cudaEventRecord(g_ctx.ev_aux_join, g_ctx.s_aux);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_ctx.stream, g_ctx.ev_aux_join, 0);
+    g_ctx.busy = 1;
+    return lisd_check((int)e, "second stream");
 }
 
 /* ---- vector residency ---------------------------------------------------------------------

@@ -47,6 +47,10 @@ LIS_INT lisd_pipe_end(void);                                            /* main 
 LIS_INT lisd_pipe_staging(size_t xcount, size_t ycount, double **xs, double **ys);   /* cached cudaMalloc'ed staging vectors */
 LIS_INT lisd_d2d(void *dst, const void *src, size_t bytes);             /* async on the main stream */
 
+/* ---- second compute stream: fork behind the main stream's current work, join back ---- */
+LIS_INT lisd_aux_fork(void **stream);
+LIS_INT lisd_aux_join(void);
+
 /* ---- vectors: residency tracking of managed storage ---- */
 LIS_INT lisd_vec_device(LIS_VECTOR v);              /* make resident before a kernel touches it */
 void    lisd_vec_host(LIS_VECTOR v);                /* host is about to read/write v->value */
@@ -88,6 +92,9 @@ typedef struct lisd_matrix {
     double *wd;               /* WD (scaled + inverted diagonal), when present */
     void *sweep;              /* SSOR level schedule (lis_precon.c), built on first psolve */
     void *sweep_global;       /* one-block schedule for LIS_MATRIX_LOWER when `sweep` is blocked */
+    /* row-partitioned CSR: rows [ov_lo, ov_hi) read no halo entry and run on a second stream while the
+     * halo exchange is in flight (ov_built: 0 not looked at yet, 1 usable, -1 not worth it) */
+    int ov_built, ov_lo, ov_hi;
     /* row chunks of the pipelined host-buffer product (lis_b200_matvec_host), built on first use:
      * rows [pipe_row[c], pipe_row[c+1]) read no x entry beyond chunk pipe_need[c] */
     int pipe_n;

@@ -198,6 +198,56 @@ static LIS_INT matvec_launch(LIS_MATRIX A, lisd_matrix *M, const double *x, doub
     return lisd_check(rc, "lis_matvec");
 }
 
+/* rows [r0, r1) of an unsplit CSR mirror on stream st (r0 a multiple of 1024: row-pointer slices stay
+ * aligned and the row blocks are those of the whole-matrix TMA plan) */
+static LIS_INT csr_rows_launch(lisd_matrix *M, int r0, int r1, const double *x, double *y, void *st, const char *what)
+{
+    int rc;
+    if (r1 <= r0) return LIS_SUCCESS;
+    if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(r1 - r0, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr + r0, M->csr.idx, M->csr.val, x, y + r0, st);
+    else rc = lisb200_spmv_csr(r1 - r0, M->csr.ptr + r0, M->csr.idx, M->csr.val, x, y + r0, st);
+    lisd_mark_busy();
+    return lisd_check(rc, what);
+}
+
+/* Row-partitioned CSR: the longest run of 1024-row blocks none of whose rows reads a halo entry
+ * (column >= n).  For a slab of a stencil grid that is everything but the first and last planes.
+ * Those rows do not need the exchange: they run on a second stream while it is in flight (the
+ * reference's LIS_MATVEC_SENDRECV, include/lis_matvec.h:31-44, finishes the exchange first). */
+static int g_overlap = -1;             /* -1: take LIS_B200_OVERLAP from the environment on first use */
+static int overlap_enabled(void)
+{
+    if (g_overlap < 0) { const char *e = getenv("LIS_B200_OVERLAP"); g_overlap = !(e && e[0] == '0'); }
+    return g_overlap;
+}
+LIS_INT lis_b200_set_overlap(LIS_INT on) { const int old = overlap_enabled(); g_overlap = on ? 1 : 0; return old; }
+
+static void overlap_plan(LIS_MATRIX A, lisd_matrix *M)
+{
+    const int n = A->n, blk = 1024;
+    const char *e = getenv("LIS_B200_OVERLAP");
+    int best_lo = 0, best_hi = 0, run_lo = -1;
+    M->ov_built = -1;
+    if (n < 4 * blk) return;
+    const int nb = n / blk;                              /* whole blocks only; the tail belongs to the boundary part */
+    for (int b = 0; b <= nb; b++) {
+        int touches = 1;
+        if (b < nb) {
+            touches = 0;
+            for (LIS_INT j = A->ptr[b * blk]; j < A->ptr[(b + 1) * blk]; j++) if (A->index[j] >= n) { touches = 1; break; }
+        }
+        if (!touches) { if (run_lo < 0) run_lo = b; }
+        else if (run_lo >= 0) {
+            if (b - run_lo > best_hi - best_lo) { best_lo = run_lo; best_hi = b; }
+            run_lo = -1;
+        }
+    }
+    if (best_hi <= best_lo) return;
+    if ((long long)(best_hi - best_lo) * blk * 2 < n && !(e && strcmp(e, "force") == 0)) return;   /* under half the rows: not worth a second launch */
+    M->ov_lo = best_lo * blk; M->ov_hi = best_hi * blk;
+    M->ov_built = 1;
+}
+
 /* grow x to np entries so the halo has somewhere to land (LIS_MATVEC_SENDRECV) */
 static LIS_INT vec_reserve(LIS_VECTOR x, size_t count)
 {
@@ -237,6 +287,19 @@ LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
     if (A->nprocs > 1 && A->commtable) {
+        if (M->type == LIS_MATRIX_CSR && !M->splited && M->ov_built == 0 && overlap_enabled()) overlap_plan(A, M);
+        if (M->type == LIS_MATRIX_CSR && !M->splited && M->ov_built == 1 && overlap_enabled()) {
+            /* exchange on the main stream (enqueued first, so its few CTAs are resident first), interior
+             * rows on the second stream meanwhile, then the rows that read halo entries */
+            void *aux;
+            err = lisd_aux_fork(&aux);
+            if (!err) err = lisd_halo_exchange(A, x);
+            if (!err) err = csr_rows_launch(M, M->ov_lo, M->ov_hi, x->value, y->value, aux, "lis_matvec (interior rows)");
+            if (!err) err = csr_rows_launch(M, 0, M->ov_lo, x->value, y->value, lisd_stream(), "lis_matvec (boundary rows)");
+            if (!err) err = csr_rows_launch(M, M->ov_hi, A->n, x->value, y->value, lisd_stream(), "lis_matvec (boundary rows)");
+            { LIS_INT e2 = lisd_aux_join(); if (!err) err = e2; }
+            return err;
+        }
         err = lisd_halo_exchange(A, x);
         if (err) return err;
     }

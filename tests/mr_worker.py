@@ -23,6 +23,56 @@ import harness as H  # noqa: E402
 import lis_b200  # noqa: E402
 
 
+def overlap_case(rank, world, shim, lib):
+    """rows that read no halo entry run on a second stream while the halo exchange is in flight
+    (LIS_B200_OVERLAP=force: even when they are a minority), the others behind it: same bits as the
+    one-process product; also through the overlapped host-buffer product"""
+    L = shim.lib
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C"); f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    l, m, n = 3 * world + 1, 48, 40
+    ptr, idx, val = H.poisson3d_7pt(l, m, n)
+    gn = l * m * n
+    q, r = divmod(gn, world)
+    sizes = [q + 1 if k < r else q for k in range(world)]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    is_, ie = int(starts[rank]), int(starts[rank + 1])
+    lp = (ptr[is_:ie + 1] - ptr[is_]).astype(np.int32)
+    li = np.ascontiguousarray(idx[ptr[is_]:ptr[ie]]); lv = np.ascontiguousarray(val[ptr[is_]:ptr[ie]])
+    nl = ie - is_
+    L.shim_mv_open_dist.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int]
+    L.shim_mv_set_x_local.argtypes = [C.c_int, f64p]; L.shim_mv_get_y_local.argtypes = [C.c_int, f64p]
+    L.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, f64p, f64p]
+    o = H.Oracle()
+    os.environ["LIS_B200_PIPE_CHUNKS"] = "5"
+    for kernel in ("tma", "tile"):
+        os.environ["LIS_B200_CSR_KERNEL"] = kernel
+        h = L.shim_mv_open_dist(1, nl, lp, li, lv, 0)
+        assert h >= 0
+        for seed in (3, 4):
+            x = H.rand_vec(gn, seed, "wide")
+            want = o.spmv("csr", ptr, idx, val, x)[is_:ie]
+            assert L.shim_mv_set_x_local(h, np.ascontiguousarray(x[is_:ie])) == 0
+            assert L.shim_mv_matvec(h) == 0
+            yl = np.zeros(nl)
+            assert L.shim_mv_get_y_local(h, yl) == 0
+            H.assert_bits_equal(yl, want, f"rank {rank} overlapped exchange ({kernel})")
+            y2 = np.full(nl, np.nan)
+            assert L.shim_mv_step_e2e_pipelined(h, np.ascontiguousarray(x[is_:ie]), y2) == 0
+            H.assert_bits_equal(y2, want, f"rank {rank} host-buffer product ({kernel})")
+        L.shim_mv_close(h)
+    try:
+        lib.emu_launch_count.restype = C.c_long; lib.emu_launch_count.argtypes = [C.c_char_p]
+        launches = int(lib.emu_launch_count(b""))
+    except AttributeError:
+        launches = -1
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {"rank": rank, "rows": nl, "launches": launches})
+    dist.barrier()
+    lib.lis_finalize()
+    if rank == 0:
+        print("MR_OK", gathered)
+
+
 def main():
     mode = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -44,6 +94,8 @@ def main():
     assert lib.lis_b200_comm_attach(rank, world, int(tok[0])) == 0
     L = shim.lib
 
+    if mode == "overlap":
+        return overlap_case(rank, world, shim, lib)
     l, m, n = 3 * world + 1, 5, 4                      # planes do not divide evenly among the ranks
     ptr, idx, val = H.poisson3d_7pt(l, m, n)
     gn = l * m * n

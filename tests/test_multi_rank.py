@@ -66,6 +66,17 @@ def test_row_partitioned_spmv_and_solvers_emulated_kernels(built, world):
                                                        "LIS_B200_HOSTCHECK_NAME": "emu", "LIS_B200_TRANSPORT": "host"})
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_interior_rows_overlap_the_halo_exchange_emulated(built, world):
+    """row-partitioned CSR product with the interior rows on a second stream during the exchange, on
+    the kernel emulator (19 k rows per rank at world 3, both CSR kernels), plus the host-buffer product"""
+    d = os.path.join(HERE, "cudaemu")
+    r = subprocess.run(["make", "-C", d, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    launch(world, "overlap", timeout=900, extra_env={"LIS_B200_HOSTCHECK_DIR": os.path.join(d, "_build"), "LIS_B200_HOSTCHECK_NAME": "emu",
+                                                     "LIS_B200_TRANSPORT": "host", "LIS_B200_OVERLAP": "force"})
+
+
 @pytest.mark.gpu
 def test_row_partitioned_spmv_and_solvers_2gpu(built):
     import torch
