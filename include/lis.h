@@ -371,6 +371,75 @@ struct LIS_SOLVER_STRUCT {
 };
 typedef struct LIS_SOLVER_STRUCT *LIS_SOLVER;
 
+/* eigensolver handle: the reference's public struct (include/lis.h:760-785 there) */
+#define LIS_EOPTIONS_LEN 13
+#define LIS_EOPTIONS_ESOLVER 0
+#define LIS_EOPTIONS_MAXITER 1
+#define LIS_EOPTIONS_SUBSPACE 2
+#define LIS_EOPTIONS_MODE 3
+#define LIS_EOPTIONS_OUTPUT 4
+#define LIS_EOPTIONS_INITGUESS_ONES 5
+#define LIS_EOPTIONS_INNER_ESOLVER 6
+#define LIS_EOPTIONS_INNER_GENERALIZED_ESOLVER 7
+#define LIS_EOPTIONS_STORAGE 8
+#define LIS_EOPTIONS_STORAGE_BLOCK 9
+#define LIS_EOPTIONS_PRECISION 10
+#define LIS_EOPTIONS_SWITCH_MAXITER 11
+#define LIS_EOPTIONS_RVAL 12
+#define LIS_EPARAMS_LEN 3
+#define LIS_EPARAMS_RESID (LIS_EOPTIONS_LEN + 0)
+#define LIS_EPARAMS_SHIFT (LIS_EOPTIONS_LEN + 1)
+#define LIS_EPARAMS_SHIFT_IM (LIS_EOPTIONS_LEN + 2)
+#define LIS_EPRINT_NONE 0
+#define LIS_EPRINT_MEM 1
+#define LIS_EPRINT_OUT 2
+#define LIS_EPRINT_ALL 3
+#define LIS_ESOLVER_LEN 16
+#define LIS_ESOLVER_PI 1
+#define LIS_ESOLVER_II 2
+#define LIS_ESOLVER_RQI 3
+#define LIS_ESOLVER_CG 4
+#define LIS_ESOLVER_CR 5
+#define LIS_ESOLVER_SI 6
+#define LIS_ESOLVER_LI 7
+#define LIS_ESOLVER_AI 8
+#define LIS_ESOLVER_GPI 9
+#define LIS_ESOLVER_GII 10
+#define LIS_ESOLVER_GRQI 11
+#define LIS_ESOLVER_GCG 12
+#define LIS_ESOLVER_GCR 13
+#define LIS_ESOLVER_GSI 14
+#define LIS_ESOLVER_GLI 15
+#define LIS_ESOLVER_GAI 16
+
+struct LIS_ESOLVER_STRUCT {
+    LIS_MATRIX A, B;
+    LIS_VECTOR x, xx, d;
+    LIS_SCALAR *evalue;
+    LIS_VECTOR *evector;
+    LIS_REAL *resid;
+    LIS_VECTOR *work;
+    LIS_REAL *rhistory;
+    LIS_INT worklen;
+    LIS_INT options[LIS_EOPTIONS_LEN];
+    LIS_SCALAR params[LIS_EPARAMS_LEN];
+    LIS_INT retcode;
+    LIS_INT *iter;
+    LIS_INT *iter2;
+    double time;
+    LIS_INT *nesol;
+    double itime;
+    double ptime;
+    double p_c_time;
+    double p_i_time;
+    LIS_INT eprecision;
+    LIS_SCALAR ishift;
+    LIS_REAL nrm2;
+    LIS_REAL tol;
+    LIS_INT nevector;        /* private to lis_b200: eigenvector handles owned by evector[] */
+};
+typedef struct LIS_ESOLVER_STRUCT *LIS_ESOLVER;
+
 typedef LIS_INT (*LIS_PRECON_CREATE_XXX)(LIS_SOLVER solver, LIS_PRECON precon);
 typedef LIS_INT (*LIS_PSOLVE_XXX)(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
 typedef LIS_INT (*LIS_PSOLVEH_XXX)(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
@@ -479,6 +548,35 @@ LIS_INT lis_solver_set_option(char *text, LIS_SOLVER solver);
 LIS_INT lis_solver_set_optionC(LIS_SOLVER solver);
 LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver);
 LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver, LIS_PRECON precon);
+LIS_INT lis_solve_setup(LIS_MATRIX A, LIS_SOLVER solver);
+LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma);
+
+/* ------------------------------------------------------------------ eigensolvers (standard problem:
+ * power, inverse, Rayleigh quotient, CG, CR, subspace, Lanczos) */
+LIS_INT lis_esolver_create(LIS_ESOLVER *esolver);
+LIS_INT lis_esolver_destroy(LIS_ESOLVER esolver);
+LIS_INT lis_esolver_work_destroy(LIS_ESOLVER esolver);
+LIS_INT lis_esolver_set_option(char *text, LIS_ESOLVER esolver);
+LIS_INT lis_esolver_set_optionC(LIS_ESOLVER esolver);
+LIS_INT lis_esolve(LIS_MATRIX A, LIS_VECTOR x, LIS_SCALAR *evalue0, LIS_ESOLVER esolver);
+LIS_INT lis_esolver_get_iter(LIS_ESOLVER esolver, LIS_INT *iter);
+LIS_INT lis_esolver_get_iterex(LIS_ESOLVER esolver, LIS_INT *iter, LIS_INT *iter_double, LIS_INT *iter_quad);
+LIS_INT lis_esolver_get_time(LIS_ESOLVER esolver, double *time);
+LIS_INT lis_esolver_get_timeex(LIS_ESOLVER esolver, double *time, double *itime, double *ptime, double *p_c_time, double *p_i_time);
+LIS_INT lis_esolver_get_residualnorm(LIS_ESOLVER esolver, LIS_REAL *residual);
+LIS_INT lis_esolver_get_status(LIS_ESOLVER esolver, LIS_INT *status);
+LIS_INT lis_esolver_get_rhistory(LIS_ESOLVER esolver, LIS_VECTOR v);
+LIS_INT lis_esolver_get_evalues(LIS_ESOLVER esolver, LIS_VECTOR v);
+LIS_INT lis_esolver_get_specific_evalue(LIS_ESOLVER esolver, LIS_INT mode, LIS_SCALAR *evalue);
+LIS_INT lis_esolver_get_evectors(LIS_ESOLVER esolver, LIS_MATRIX M);
+LIS_INT lis_esolver_get_specific_evector(LIS_ESOLVER esolver, LIS_INT mode, LIS_VECTOR x);
+LIS_INT lis_esolver_get_residualnorms(LIS_ESOLVER esolver, LIS_VECTOR v);
+LIS_INT lis_esolver_get_specific_residualnorm(LIS_ESOLVER esolver, LIS_INT mode, LIS_REAL *residual);
+LIS_INT lis_esolver_get_iters(LIS_ESOLVER esolver, LIS_VECTOR v);
+LIS_INT lis_esolver_get_specific_iter(LIS_ESOLVER esolver, LIS_INT mode, LIS_INT *iter);
+LIS_INT lis_esolver_get_esolver(LIS_ESOLVER esolver, LIS_INT *nesol);
+LIS_INT lis_esolver_get_esolvername(LIS_INT esolver, char *esolvername);
+LIS_INT lis_esolver_output_rhistory(LIS_ESOLVER esolver, char *filename);
 LIS_INT lis_solver_get_solvername(LIS_INT solver, char *solvername);
 LIS_INT lis_solver_get_preconname(LIS_INT precon_type, char *preconname);
 LIS_INT lis_precon_register(char *name, LIS_PRECON_CREATE_XXX pcreate, LIS_PSOLVE_XXX psolve, LIS_PSOLVEH_XXX psolveh);

@@ -638,6 +638,41 @@ LIS_INT lis_matrix_set_bsr(LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT *bptr
 }
 
 /* ------------------------------------------------------------------ CSR utilities */
+/* A <- A - sigma*I on the host arrays (src/matrix/lis_matrix_ops.c:780-830; per format
+ * lis_matrix_csr.c:565-603, lis_matrix_csc.c, lis_matrix_ell.c, lis_matrix_dia.c): the first stored
+ * diagonal entry of each row; a row without one is left alone.  The device mirror is dropped. */
+LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma)
+{
+    const LIS_INT n = A->n;
+    LIS_INT err = lis_host_matrix_check_input(A);
+    if (err) return err;
+    if (A->is_splited) {
+        if (A->matrix_type != LIS_MATRIX_CSR) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
+        for (LIS_INT i = 0; i < n; i++) A->D->value[i] -= sigma;
+    } else switch (A->matrix_type) {
+    case LIS_MATRIX_CSR:
+    case LIS_MATRIX_CSC:
+        for (LIS_INT i = 0; i < n; i++)
+            for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++)
+                if (A->index[j] == i) { A->value[j] -= sigma; break; }
+        break;
+    case LIS_MATRIX_ELL:
+        for (LIS_INT i = 0; i < n; i++)
+            for (LIS_INT j = 0; j < A->maxnzr; j++)
+                if (A->index[(size_t)j * n + i] == i) { A->value[(size_t)j * n + i] -= sigma; break; }
+        break;
+    case LIS_MATRIX_DIA:
+        for (LIS_INT j = 0; j < A->nnd; j++)
+            if (A->index[j] == 0) { for (LIS_INT i = 0; i < n; i++) A->value[(size_t)j * n + i] -= sigma; break; }
+        break;
+    default:
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_shift_diagonal: storage format %D (use CSR, CSC, ELL or DIA)\n", A->matrix_type);
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    lisd_matrix_drop(A);
+    return LIS_SUCCESS;
+}
+
 /* every row ascending by column: lis_matrix_sort_csr, src/matrix/lis_matrix_csr.c:1486-1521 */
 LIS_INT lis_matrix_sort_csr(LIS_MATRIX A)
 {

@@ -497,6 +497,24 @@ LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver)
     return LIS_SUCCESS;
 }
 
+/* run lis_solve up to, but not including, the solver loop: option checks, -storage conversion, work
+ * vectors -- what the CR eigensolver needs before it borrows the preconditioner
+ * (src/solver/lis_solver.c:408-437) */
+LIS_INT lis_solve_setup(LIS_MATRIX A, LIS_SOLVER solver)
+{
+    LIS_VECTOR b, x;
+    LIS_INT err = lis_vector_duplicate(A, &b);
+    if (err) return err;
+    err = lis_vector_duplicate(A, &x);
+    if (err) { lis_vector_destroy(b); return err; }
+    solver->setup = LIS_TRUE;
+    err = lis_solve(A, b, x, solver);
+    if (err) { lis_solver_work_destroy(solver); solver->retcode = err; }
+    lis_vector_destroy(b);
+    lis_vector_destroy(x);
+    return err;
+}
+
 LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver, LIS_PRECON precon)
 {
     const LIS_Comm comm = LIS_COMM_WORLD;

@@ -139,9 +139,43 @@ def ext_solvers():
     np.savez_compressed(os.path.join(HERE, "psolve_ilu_ssor.npz"), **out)
 
 
+ESOLVE_CASES = ["pi|-e pi -emaxiter 400", "ii|-e ii", "rqi|-e rqi", "cg|-e cg", "cr|-e cr", "crs|-e cr -shift 0.5",
+                "si|-e si -ss 3 -ie ii -emaxiter 60", "sipi|-e si -ss 2 -ie pi -emaxiter 300", "li|-e li -ss 3", "lirv|-e li -ss 4 -rval true"]
+ESOLVE_INITS = {"default": "", "cgjac": "-i cg -p jacobi"}
+
+
+def esolvers():
+    """esolve.npz: the compiled serial reference's eigensolvers (tests/esolve_worker.py drives
+    shim_esolve), one process per case -- the reference does not survive several lis_esolve calls of
+    different kinds in one process -- for the default inner linear solver and for "-i cg -p jacobi"
+    on the command line.  Keys: <init>_<case>_<matrix>_{rc,d,rh,x,ev,er,ei}."""
+    import subprocess
+    import tempfile
+    out = {}
+    ROOT = os.path.dirname(os.path.dirname(HERE))
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref_shim_serial.so")
+    worker = os.path.join(ROOT, "tests", "esolve_worker.py")
+    for iname, init in ESOLVE_INITS.items():
+        for case in ESOLVE_CASES:
+            if iname != "default" and case.split("|")[0] not in ("ii", "rqi", "cg", "cr", "li"):
+                continue
+            with tempfile.TemporaryDirectory() as d:
+                path = os.path.join(d, "o.npz")
+                r = subprocess.run([sys.executable, worker, ref, init, path, case], capture_output=True, text=True)
+                assert r.returncode == 0, (case, r.stderr[-2000:])
+                z = np.load(path)
+                for k in z.files:
+                    if case.startswith("lirv") and not (k.endswith("_ev") or k.endswith("_d")):
+                        continue            # -rval true: only the Ritz values are defined (the rest is uninitialised memory there)
+                    out[f"{iname}_{k}"] = z[k][:1] if (case.startswith("lirv") and k.endswith("_d")) else z[k]
+    np.savez_compressed(os.path.join(HERE, "esolve.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ext":
         ext_solvers()
+    elif len(sys.argv) > 1 and sys.argv[1] == "esolve":
+        esolvers()
     else:
         main()
         ext_solvers()

@@ -491,6 +491,61 @@ EXPORT int shim_solve(int fmt, int n, const int *ptr, const int *idx, const doub
     return (int)err;
 }
 
+/* ------------------------------------------------------------------ lis_esolve
+ * out_i: iter[0], status, lis_esolve return value, rhistory length, subspace size
+ * out_d: evalue0, resid[0]; x: initial vector in (used with -initx_ones false), eigenvector out;
+ * evals/eresid/eiter: per-mode arrays for the subspace / Lanczos solvers (ss entries), else untouched */
+EXPORT int shim_esolve(int fmt, int n, const int *ptr, const int *idx, const double *val, double *x, const char *options,
+                       int *out_i, double *out_d, double *rhistory, int rh_cap, double *evals, double *eresid, int *eiter, int ecap)
+{
+    LIS_MATRIX A0, A;
+    LIS_VECTOR vx, vh;
+    LIS_ESOLVER esolver;
+    LIS_INT err, iter = 0, status = 0, nesol = 0;
+    LIS_REAL resid = 0.0;
+    LIS_SCALAR evalue0 = 0.0;
+    err = make_csr(n, ptr, idx, val, 0, &A0); if (err) return (int)err;
+    err = convert_to(A0, fmt, 0, 0, &A); if (err) return (int)err;
+    lis_matrix_destroy(A0);
+    err = make_vec(A, x, &vx); if (err) return (int)err;
+    err = lis_esolver_create(&esolver); if (err) return (int)err;
+    err = lis_esolver_set_option((char *)"-eprint mem", esolver); if (err) return (int)err;
+    err = lis_esolver_set_option((char *)options, esolver); if (err) return (int)err;
+    { const int q = quiet_begin(); err = lis_esolve(A, vx, &evalue0, esolver); quiet_end(q); }
+    out_i[2] = (int)err; out_i[3] = 0;
+    if (!err) {
+        lis_esolver_get_iter(esolver, &iter);
+        lis_esolver_get_status(esolver, &status);
+        lis_esolver_get_residualnorm(esolver, &resid);
+        lis_esolver_get_esolver(esolver, &nesol);
+        out_i[0] = (int)iter; out_i[1] = (int)status; out_i[4] = (int)esolver->options[LIS_EOPTIONS_SUBSPACE];
+        out_d[0] = evalue0; out_d[1] = resid;
+        if (rhistory && rh_cap > 0) {
+            int len = (int)iter + 1;
+            if (status != LIS_SUCCESS) len--;
+            if (len > rh_cap) len = rh_cap;
+            if (len > 0 && make_vec_n(len, NULL, &vh) == 0) {
+                lis_esolver_get_rhistory(esolver, vh);
+                lis_vector_gather(vh, rhistory);
+                lis_vector_destroy(vh);
+                out_i[3] = len;
+            }
+        }
+        if (nesol == LIS_ESOLVER_SI || nesol == LIS_ESOLVER_LI || nesol == LIS_ESOLVER_AI)
+            for (int m = 0; m < out_i[4] && m < ecap; m++) {
+                LIS_SCALAR ev = 0.0; LIS_REAL er = 0.0; LIS_INT ei = 0;
+                lis_esolver_get_specific_evalue(esolver, m, &ev);
+                lis_esolver_get_specific_residualnorm(esolver, m, &er);
+                lis_esolver_get_specific_iter(esolver, m, &ei);
+                evals[m] = ev; eresid[m] = er; eiter[m] = (int)ei;
+            }
+        if (n > 0) lis_vector_gather(vx, x);
+    }
+    lis_esolver_destroy(esolver);
+    lis_vector_destroy(vx); lis_matrix_destroy(A);
+    return (int)err;
+}
+
 /* ------------------------------------------------------------------ bench handles
  * One matrix + x + y kept alive across steps (bench.py): open once, then time steps.
  * step_e2e is what a user with HOST buffers does per product: scatter x in, lis_matvec,

@@ -157,3 +157,12 @@ def test_test3_driver_emulated(emu_drivers, tmp_path, opts):
 
 def test_test1_driver_emulated(emu_drivers, tmp_path):
     D.test_test1_driver_matrix_market(tmp_path)
+
+
+@pytest.mark.parametrize("opts", ["", "-e ii -i cg -p jacobi", "-e rqi"])
+def test_etest1_driver_emulated(emu_drivers, tmp_path, opts):
+    D.test_etest1_driver(tmp_path, opts)
+
+
+def test_etest5_driver_emulated(emu_drivers, tmp_path):
+    D.test_etest5_driver_lanczos(tmp_path)

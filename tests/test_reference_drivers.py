@@ -28,12 +28,12 @@ def need(*names):
 
 
 def test_drivers_were_built_from_unmodified_reference_sources():
-    """15 reference drivers compile and link against lis_b200 (checked where the tree exists)"""
+    """22 reference drivers compile and link against lis_b200 (checked where the tree exists)"""
     if not os.path.isdir("/root/reference/test"):
         pytest.skip("reference tree not present")
     H.ensure_built()
     for n in ("spmvtest1", "spmvtest2", "spmvtest2b", "spmvtest3", "spmvtest3b", "spmvtest4", "spmvtest5", "test1", "test2", "test2b",
-              "test3", "test3b", "test3c", "test4", "test5"):
+              "test3", "test3b", "test3c", "test4", "test5", "etest1", "etest2", "etest3", "etest4", "etest5", "etest5b", "etest6"):
         assert os.path.exists(os.path.join(OURS, n)), n
 
 
@@ -100,6 +100,55 @@ def test_spmvtest_file_drivers(tmp_path, driver):
         # formats lis_b200 does not carry end the driver's cycle with LIS_ERR_NOT_IMPLEMENTED (exit code 5)
         assert r.returncode in (0, 5), (r.returncode, r.stderr[-800:])
         assert {int(t) for t, _ in got} >= ({1, 2} if fmt is None else {fmt}), got
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", ["", "-e ii -i cg -p jacobi", "-e rqi", "-e cg -i cg"])
+def test_etest1_driver(tmp_path, opts):
+    """etest1 (the reference's `make check` eigen case): eigenvalue of a Matrix Market matrix with the
+    default CR eigensolver and three others; printed eigenvalue equal to the reference-linked driver's
+    to the 7 digits it prints, iteration count within a few steps"""
+    need("etest1")
+    ptr, idx, val = H.poisson3d_7pt(6, 5, 4)
+    _write_mtx(tmp_path / "a.mtx", ptr, idx, val)
+
+    def go(binary, tag):
+        out = run(binary, tmp_path / "a.mtx", tmp_path / f"evec_{tag}.txt", tmp_path / f"rh_{tag}.txt", *opts.split())
+        ev = float(re.search(r"eigenvalue\s*=\s*(\S+)", out).group(1))
+        it = int(re.search(r"number of iterations\s*=\s*(\d+)", out).group(1))
+        return ev, it
+    ev, it = go(os.path.join(OURS, "etest1"), "ours")
+    vec = np.loadtxt(tmp_path / "evec_ours.txt", skiprows=2)[:, 1]
+    assert abs(np.linalg.norm(vec) - 1.0) < 1e-12
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, idx, ptr), shape=(len(ptr) - 1,) * 2)
+    assert np.linalg.norm(A @ vec - ev * vec) < 1e-6 * abs(ev)
+    if os.path.exists(os.path.join(REFS, "etest1")):
+        ev_r, it_r = go(os.path.join(REFS, "etest1"), "ref")
+        assert f"{ev:e}" == f"{ev_r:e}" and abs(it - it_r) <= max(2, it_r // 10), (opts, ev, ev_r, it, it_r)
+
+
+@pytest.mark.gpu
+def test_etest5_driver_lanczos(tmp_path):
+    """etest5: several eigenpairs (Lanczos, refined by inverse iteration), written with
+    lis_esolver_get_evalues / get_evectors / get_residualnorms / get_iters"""
+    need("etest5")
+    ptr, idx, val = H.poisson1d(40)
+    _write_mtx(tmp_path / "a.mtx", ptr, idx, val)
+
+    def go(binary, tag):
+        files = [tmp_path / f"{k}_{tag}.txt" for k in ("evalues", "evectors", "resid", "iters")]
+        run(binary, tmp_path / "a.mtx", *files, "-e", "li", "-ss", "3")
+        return np.loadtxt(files[0], skiprows=2)[:, 1], np.loadtxt(files[1], skiprows=2)
+    ev, vecs = go(os.path.join(OURS, "etest5"), "ours")
+    exact = 2.0 - 2.0 * np.cos(np.arange(1, 41) * np.pi / 41)
+    for e in ev:
+        assert np.abs(exact - e).min() < 1e-9, e
+    assert vecs.shape == (40 * 3, 3)
+    if os.path.exists(os.path.join(REFS, "etest5")):
+        ev_r, vecs_r = go(os.path.join(REFS, "etest5"), "ref")
+        assert np.allclose(ev, ev_r, rtol=1e-9)
+        assert np.array_equal(vecs[:, :2], vecs_r[:, :2])
 
 
 def solver_lines(out):
