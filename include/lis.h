@@ -552,7 +552,7 @@ LIS_INT lis_solve_setup(LIS_MATRIX A, LIS_SOLVER solver);
 LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma);
 
 /* ------------------------------------------------------------------ eigensolvers (standard problem:
- * power, inverse, Rayleigh quotient, CG, CR, subspace, Lanczos) */
+ * power, inverse, Rayleigh quotient, CG, CR, subspace, Lanczos, Arnoldi) */
 LIS_INT lis_esolver_create(LIS_ESOLVER *esolver);
 LIS_INT lis_esolver_destroy(LIS_ESOLVER esolver);
 LIS_INT lis_esolver_work_destroy(LIS_ESOLVER esolver);

@@ -3,13 +3,13 @@
  * lis_esolver_* / lis_esolve (src/esolver/lis_esolver.c:142-1385) and the standard eigensolvers
  *   power (lis_esolver_pi.c:127-225), inverse (lis_esolver_ii.c:127-300), Rayleigh quotient
  *   (lis_esolver_rqi.c:124-260), CG and CR (lis_esolver_cg.c, LOBPCG-style / Suetomi-Sekimoto),
- *   subspace (lis_esolver_si.c), Lanczos (lis_esolver_li.c).
+ *   subspace (lis_esolver_si.c), Lanczos (lis_esolver_li.c), Arnoldi (lis_esolver_ai.c).
  * They add no kernels: each is the reference's sequence of lis_matvec / lis_vector_* / lis_solve_kernel
  * calls with the same scalar arithmetic on the host, so on the mock device (tests/hostcheck) eigenvalue,
  * iteration count, residual history and eigenvector equal the serial reference bit for bit.  The small
  * dense helpers they use (3x3 Rayleigh-Ritz, QR iteration on the tridiagonal matrix) are restated from
  * src/array/lis_array.c in the operation order that file has.
- * Not carried: Arnoldi, the generalized (A x = lambda B x) variants, quad precision.
+ * Not carried: the generalized (A x = lambda B x) variants, quad precision.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -850,21 +850,67 @@ done:
 #undef SCHK
 }
 
+/* Lanczos / Arnoldi, second half: every Ritz value becomes the shift of one run of the inner
+ * eigensolver (lis_esolver_li.c:300-370, lis_esolver_ai.c:330-395); mode 0 also supplies the
+ * residual history and the times */
+static LIS_INT refine_ritz_pairs(LIS_ESOLVER esolver, const char *who)
+{
+    LIS_MATRIX A = esolver->A;
+    const LIS_INT ss = esolver->options[LIS_EOPTIONS_SUBSPACE], output = esolver->options[LIS_EOPTIONS_OUTPUT];
+    LIS_ESOLVER esolver2;
+    LIS_SCALAR evalue = 0.0;
+    LIS_INT err = LIS_SUCCESS;
+    if (output) lis_printf(LIS_COMM_WORLD, "computing refined eigenpairs using inner eigensolver:\n\n");
+    ECHK(lis_esolver_create(&esolver2));
+    esolver2->options[LIS_EOPTIONS_ESOLVER] = esolver->options[LIS_EOPTIONS_INNER_ESOLVER];
+    esolver2->options[LIS_EOPTIONS_SUBSPACE] = 1;
+    esolver2->options[LIS_EOPTIONS_MAXITER] = esolver->options[LIS_EOPTIONS_MAXITER];
+    esolver2->options[LIS_EOPTIONS_OUTPUT] = output;
+    esolver2->params[LIS_EPARAMS_RESID - LIS_EOPTIONS_LEN] = esolver->params[LIS_EPARAMS_RESID - LIS_EOPTIONS_LEN];
+    for (LIS_INT i = 0; i < ss && !err; i++) {
+        err = lis_vector_duplicate(A, &esolver->evector[i]);
+        if (err) break;
+        esolver2->ishift = esolver->evalue[i];
+        err = lis_esolve(A, esolver->evector[i], &evalue, esolver2);
+        if (err) break;
+        lis_esolver_work_destroy(esolver2);
+        esolver->evalue[i] = evalue;
+        esolver->iter[i] = esolver2->iter[0];
+        esolver->resid[i] = esolver2->resid[0];
+        if (i == 0) {
+            if (output & LIS_EPRINT_MEM) for (LIS_INT ic = 0; ic < esolver2->iter[0] + 1; ic++) esolver->rhistory[ic] = esolver2->rhistory[ic];
+            esolver->ptime += esolver2->ptime;
+            esolver->itime += esolver2->itime;
+            esolver->p_c_time += esolver2->p_c_time;
+            esolver->p_i_time += esolver2->p_i_time;
+        }
+        if (output) {
+            lis_printf(LIS_COMM_WORLD, "%s: mode number          = %D\n", who, i);
+            lis_printf(LIS_COMM_WORLD, "%s: eigenvalue           = %e\n", who, (double)esolver->evalue[i]);
+            lis_printf(LIS_COMM_WORLD, "%s: elapsed time         = %e sec.\n", who, esolver2->time);
+            lis_printf(LIS_COMM_WORLD, "%s: number of iterations = %D\n", who, esolver2->iter[0]);
+            lis_printf(LIS_COMM_WORLD, "%s: relative residual    = %e\n\n", who, (double)esolver2->resid[0]);
+        }
+    }
+    lis_esolver_destroy(esolver2);
+    if (!err) err = lis_vector_copy(esolver->evector[0], esolver->x);
+    return err;
+}
+
 /* ------------------------------------------------------------------ Lanczos, src/esolver/lis_esolver_li.c
  * work[0] = r, v = &work[1]; Ritz values of the ss x ss tridiagonal matrix by QR iteration, then each
  * refined by the inner eigensolver with the Ritz value as shift */
 static LIS_INT lis_eli(LIS_ESOLVER esolver)
 {
     LIS_MATRIX A = esolver->A;
-    const LIS_INT ss = esolver->options[LIS_EOPTIONS_SUBSPACE], emaxiter = esolver->options[LIS_EOPTIONS_MAXITER];
+    const LIS_INT ss = esolver->options[LIS_EOPTIONS_SUBSPACE];
     const LIS_INT output = esolver->options[LIS_EOPTIONS_OUTPUT], niesolver = esolver->options[LIS_EOPTIONS_INNER_ESOLVER];
     const LIS_INT rval = esolver->options[LIS_EOPTIONS_RVAL];
     const LIS_REAL tol = esolver->params[LIS_EPARAMS_RESID - LIS_EOPTIONS_LEN];
     LIS_VECTOR r = esolver->work[0], *v = &esolver->work[1];
-    LIS_SCALAR *t, *tq, *tr, dot, evalue = 0.0, evalue0 = 0.0;
-    LIS_REAL nrm2, resid0 = 0.0, qrerr, beta;
-    LIS_INT i, j, k, iter0 = 0, qriter, err = LIS_SUCCESS;
-    LIS_ESOLVER esolver2 = NULL;
+    LIS_SCALAR *t, *tq, *tr, dot;
+    LIS_REAL nrm2, qrerr, beta;
+    LIS_INT i, j, k, qriter, err = LIS_SUCCESS;
     char esolvername[128];
     if (niesolver < LIS_ESOLVER_PI || niesolver > LIS_ESOLVER_CR) {
         LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "inner eigensolver %D is not available for Lanczos in lis_b200\n", niesolver);
@@ -925,48 +971,109 @@ static LIS_INT lis_eli(LIS_ESOLVER esolver)
         }
     }
     if (rval) goto done;
-    if (output) lis_printf(LIS_COMM_WORLD, "computing refined eigenpairs using inner eigensolver:\n\n");
-    LCHK(lis_esolver_create(&esolver2));
-    esolver2->options[LIS_EOPTIONS_ESOLVER] = niesolver;
-    esolver2->options[LIS_EOPTIONS_SUBSPACE] = 1;
-    esolver2->options[LIS_EOPTIONS_MAXITER] = emaxiter;
-    esolver2->options[LIS_EOPTIONS_OUTPUT] = esolver->options[LIS_EOPTIONS_OUTPUT];
-    esolver2->params[LIS_EPARAMS_RESID - LIS_EOPTIONS_LEN] = tol;
-    for (i = 0; i < ss; i++) {
-        LCHK(lis_vector_duplicate(A, &esolver->evector[i]));
-        esolver2->ishift = esolver->evalue[i];
-        LCHK(lis_esolve(A, esolver->evector[i], &evalue, esolver2));
-        lis_esolver_work_destroy(esolver2);
-        esolver->evalue[i] = evalue;
-        esolver->iter[i] = esolver2->iter[0];
-        esolver->resid[i] = esolver2->resid[0];
-        if (i == 0) {
-            evalue0 = esolver->evalue[0];
-            iter0 = esolver2->iter[0];
-            resid0 = esolver2->resid[0];
-            if (output & LIS_EPRINT_MEM) for (LIS_INT ic = 0; ic < iter0 + 1; ic++) esolver->rhistory[ic] = esolver2->rhistory[ic];
-            esolver->ptime += esolver2->ptime;
-            esolver->itime += esolver2->itime;
-            esolver->p_c_time += esolver2->p_c_time;
-            esolver->p_i_time += esolver2->p_i_time;
-        }
-        if (output) {
-            lis_printf(LIS_COMM_WORLD, "Lanczos: mode number          = %D\n", i);
-            lis_printf(LIS_COMM_WORLD, "Lanczos: eigenvalue           = %e\n", (double)esolver->evalue[i]);
-            lis_printf(LIS_COMM_WORLD, "Lanczos: elapsed time         = %e sec.\n", esolver2->time);
-            lis_printf(LIS_COMM_WORLD, "Lanczos: number of iterations = %D\n", esolver2->iter[0]);
-            lis_printf(LIS_COMM_WORLD, "Lanczos: relative residual    = %e\n\n", (double)esolver2->resid[0]);
-        }
-    }
-    esolver->evalue[0] = evalue0;
-    esolver->iter[0] = iter0;
-    esolver->resid[0] = resid0;
-    LCHK(lis_vector_copy(esolver->evector[0], esolver->x));
+    LCHK(refine_ritz_pairs(esolver, "Lanczos"));
 done:
-    if (esolver2) lis_esolver_destroy(esolver2);
     lis_free2(3, t, tq, tr);
     return err;
 #undef LCHK
+}
+
+/* ------------------------------------------------------------------ Arnoldi, src/esolver/lis_esolver_ai.c
+ * work[0] = w, v = &work[1]; Ritz values from the ss x ss Hessenberg matrix by QR iteration (1x1 and 2x2
+ * diagonal blocks; a complex pair contributes its real part), then refined like Lanczos' */
+static LIS_INT lis_eai(LIS_ESOLVER esolver)
+{
+    LIS_MATRIX A = esolver->A;
+    const LIS_INT ss = esolver->options[LIS_EOPTIONS_SUBSPACE];
+    const LIS_INT output = esolver->options[LIS_EOPTIONS_OUTPUT], niesolver = esolver->options[LIS_EOPTIONS_INNER_ESOLVER];
+    const LIS_INT rval = esolver->options[LIS_EOPTIONS_RVAL];
+    const LIS_REAL tol = esolver->params[LIS_EPARAMS_RESID - LIS_EOPTIONS_LEN];
+    LIS_VECTOR w = esolver->work[0], *v = &esolver->work[1];
+    LIS_SCALAR *h, *hq, *hr;
+    LIS_REAL hqrerr, D, nrm;
+    LIS_INT i, j, hqriter, err = LIS_SUCCESS;
+    char esolvername[128];
+    if (niesolver < LIS_ESOLVER_PI || niesolver > LIS_ESOLVER_CR) {
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "inner eigensolver %D is not available for Arnoldi in lis_b200\n", niesolver);
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    /* one spare entry: the reference's last h(j+1,j) lands one past its ss*ss array */
+    h = (LIS_SCALAR *)lis_malloc(((size_t)ss * ss + 1) * sizeof(LIS_SCALAR), "lis_eai::h");
+    hq = (LIS_SCALAR *)lis_malloc((size_t)ss * ss * sizeof(LIS_SCALAR), "lis_eai::hq");
+    hr = (LIS_SCALAR *)lis_malloc((size_t)ss * ss * sizeof(LIS_SCALAR), "lis_eai::hr");
+    if (!h || !hq || !hr) { lis_free2(3, h, hq, hr); LIS_SETERR_MEM(ss * ss * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
+#define ACHK(e) do { err = (e); if (err) goto done; } while (0)
+    ACHK(lis_vector_set_all(1.0, v[0]));
+    ACHK(normalize(v[0]));
+    {
+        LIS_SOLVER solver;
+        lis_esolver_get_esolvername(niesolver, esolvername);
+        if (output) lis_printf(LIS_COMM_WORLD, "inner eigensolver     : %s\n", esolvername);
+        ACHK(inner_solver(esolver, "-i bicg -p none", &solver));
+        lis_solver_destroy(solver);
+    }
+    for (i = 0; i < ss * ss; i++) h[i] = 0.0;
+    j = -1;
+    while (j < ss - 1) {
+        j = j + 1;
+        ACHK(lis_matvec(A, v[j], w));
+        for (i = 0; i <= j; i++) {
+            ACHK(lis_vector_dot(v[i], w, &h[i + j * ss]));
+            ACHK(lis_vector_axpy(-h[i + j * ss], v[i], w));
+        }
+        ACHK(lis_vector_nrm2(w, &nrm));
+        h[j + 1 + j * ss] = nrm;
+        if (fabs(h[j + 1 + j * ss]) < tol) break;
+        ACHK(lis_vector_scale(1 / h[j + 1 + j * ss], w));
+        ACHK(lis_vector_copy(w, v[j + 1]));
+    }
+    {
+        const double time0 = lis_wtime();
+        arr_qr(ss, h, hq, hr, &hqriter, &hqrerr);
+        const double time = lis_wtime() - time0;
+        if (output) {
+            lis_printf(LIS_COMM_WORLD, "size of subspace      : %D\n\n", ss);
+            lis_printf(LIS_COMM_WORLD, "Ritz values:\n\n");
+        }
+        i = 0;
+        while (i < ss) {
+            i = i + 1;
+            if (ss == i || fabs(h[i + (i - 1) * ss]) < tol) {
+                if (output) {
+                    lis_printf(LIS_COMM_WORLD, "Arnoldi: mode number          = %D\n", i - 1);
+                    lis_printf(LIS_COMM_WORLD, "Arnoldi: Ritz value           = %e\n", (double)(h[i - 1 + (i - 1) * ss]));
+                }
+                esolver->evalue[i - 1] = h[i - 1 + (i - 1) * ss];
+            } else {
+                D = (h[i - 1 + (i - 1) * ss] + h[i + i * ss]) * (h[i - 1 + (i - 1) * ss] + h[i + i * ss])
+                  - 4 * (h[i - 1 + (i - 1) * ss] * h[i + i * ss] - h[i - 1 + i * ss] * h[i + (i - 1) * ss]);
+                if (D < 0) {
+                    if (output) {
+                        lis_printf(LIS_COMM_WORLD, "Arnoldi: mode number          = %D\n", i - 1);
+                        lis_printf(LIS_COMM_WORLD, "Arnoldi: Ritz value           = (%e, %e)\n", (double)((h[i - 1 + (i - 1) * ss] + h[i + i * ss]) / 2), (double)sqrt(-D) / 2);
+                        lis_printf(LIS_COMM_WORLD, "Arnoldi: mode number          = %D\n", i);
+                        lis_printf(LIS_COMM_WORLD, "Arnoldi: Ritz value           = (%e, %e)\n", (double)((h[i - 1 + (i - 1) * ss] + h[i + i * ss]) / 2), (double)-sqrt(-D) / 2);
+                    }
+                    esolver->evalue[i - 1] = (h[i - 1 + (i - 1) * ss] + h[i + i * ss]) / 2;
+                    esolver->evalue[i] = (h[i - 1 + (i - 1) * ss] + h[i + i * ss]) / 2;
+                    i = i + 1;
+                } else {
+                    if (output) {
+                        lis_printf(LIS_COMM_WORLD, "Arnoldi: mode number          = %D\n", i - 1);
+                        lis_printf(LIS_COMM_WORLD, "Arnoldi: Ritz value           = %e\n", (double)(h[i - 1 + (i - 1) * ss]));
+                    }
+                    esolver->evalue[i - 1] = h[i - 1 + (i - 1) * ss];
+                }
+            }
+        }
+        lis_printf(LIS_COMM_WORLD, "Arnoldi: elapsed time         = %e sec.\n\n", time);     /* unconditional there too */
+    }
+    if (rval) goto done;
+    ACHK(refine_ritz_pairs(esolver, "Arnoldi"));
+done:
+    lis_free2(3, h, hq, hr);
+    return err;
+#undef ACHK
 }
 
 /* ------------------------------------------------------------------ lis_esolve (lis_gesolve with B = NULL,
@@ -977,7 +1084,7 @@ static const esolver_entry_t k_esolvers[LIS_ESOLVER_LEN + 1] = {
     {lis_epi, 2, 0}, {lis_eii, 2, 0}, {lis_erqi, 2, 0}, {lis_ecg, 6, 0}, {lis_ecr, 6, 0},
     {lis_esi, 4, 1},           /* lis_esi_malloc_work: 4 + ss */
     {lis_eli, 2, 1},           /* lis_eli_malloc_work: 2 + ss */
-    {NULL, 0, 0},
+    {lis_eai, 2, 1},           /* lis_eai_malloc_work: 2 + ss */
     {NULL, 0, 0}, {NULL, 0, 0}, {NULL, 0, 0}, {NULL, 0, 0}, {NULL, 0, 0}, {NULL, 0, 0}, {NULL, 0, 0}, {NULL, 0, 0},
 };
 
@@ -999,7 +1106,7 @@ LIS_INT lis_esolve(LIS_MATRIX A, LIS_VECTOR x, LIS_SCALAR *evalue0, LIS_ESOLVER 
         return LIS_ERR_ILL_ARG;
     }
     if (k_esolvers[nesolver].run == NULL) {
-        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "eigensolver %s is not part of lis_b200 (Arnoldi and the generalized eigensolvers are not carried)\n", k_esolvername[nesolver]);
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "eigensolver %s is not part of lis_b200 (the generalized eigensolvers are not carried)\n", k_esolvername[nesolver]);
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (eprecision != LIS_PRECISION_DOUBLE) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "quad precision is not part of lis_b200\n"); return LIS_ERR_NOT_IMPLEMENTED; }

@@ -140,7 +140,8 @@ def ext_solvers():
 
 
 ESOLVE_CASES = ["pi|-e pi -emaxiter 400", "ii|-e ii", "rqi|-e rqi", "cg|-e cg", "cr|-e cr", "crs|-e cr -shift 0.5",
-                "si|-e si -ss 3 -ie ii -emaxiter 60", "sipi|-e si -ss 2 -ie pi -emaxiter 300", "li|-e li -ss 3", "lirv|-e li -ss 4 -rval true"]
+                "si|-e si -ss 3 -ie ii -emaxiter 60", "sipi|-e si -ss 2 -ie pi -emaxiter 300", "li|-e li -ss 3", "lirv|-e li -ss 4 -rval true",
+                "ai|-e ai -ss 3", "aicr|-e ai -ss 2 -ie cr"]
 ESOLVE_INITS = {"default": "", "cgjac": "-i cg -p jacobi"}
 
 
@@ -157,7 +158,7 @@ def esolvers():
     worker = os.path.join(ROOT, "tests", "esolve_worker.py")
     for iname, init in ESOLVE_INITS.items():
         for case in ESOLVE_CASES:
-            if iname != "default" and case.split("|")[0] not in ("ii", "rqi", "cg", "cr", "li"):
+            if iname != "default" and case.split("|")[0] not in ("ii", "rqi", "cg", "cr", "li", "ai"):
                 continue
             with tempfile.TemporaryDirectory() as d:
                 path = os.path.join(d, "o.npz")

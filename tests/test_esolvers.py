@@ -37,7 +37,7 @@ def run_worker(lib, init, cases, matrices=None):
 
 
 def cases_for(iname):
-    return [c for c in ESOLVE_CASES if iname == "default" or c.split("|")[0] in ("ii", "rqi", "cg", "cr", "li")]
+    return [c for c in ESOLVE_CASES if iname == "default" or c.split("|")[0] in ("ii", "rqi", "cg", "cr", "li", "ai")]
 
 
 @pytest.mark.parametrize("iname", list(ESOLVE_INITS))
@@ -76,7 +76,7 @@ def check_close(gold, got, iname, matrices, cases=None):
                 # eigenvector up to sign
                 x, rx = got[key + "_x"], gold[f"{iname}_{key}_x"]
                 assert min(np.abs(x - rx).max(), np.abs(x + rx).max()) < 1e-6, key
-            if name in ("si", "sipi", "li"):
+            if name in ("si", "sipi", "li", "ai", "aicr"):
                 assert np.allclose(got[key + "_ev"], gold[f"{iname}_{key}_ev"], rtol=1e-8, atol=1e-12), key
 
 
@@ -85,7 +85,7 @@ def test_eigensolvers_on_kernel_emulator(built, iname):
     d = os.path.join(H.ROOT, "tests", "cudaemu")
     r = subprocess.run(["make", "-C", d, "-j8"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    light = [c for c in cases_for(iname) if c.split("|")[0] in ("rqi", "cg", "cr", "li", "lirv")]     # seconds, not minutes
+    light = [c for c in cases_for(iname) if c.split("|")[0] in ("rqi", "cg", "cr", "li", "lirv", "aicr")]     # seconds, not minutes
     got = run_worker(os.path.join(d, "_build", "liblis_emu_shim.so"), ESOLVE_INITS[iname], light, matrices=("p7",))
     check_close(np.load(GOLD), got, iname, ("p7",), light)
 
