@@ -184,6 +184,10 @@ int lisb200_csr2bsr_count(int n, int nr, int bnr, int bnc, const int *d_ptr, con
 int lisb200_csr2bsr_fill(int n, int nr, int bnr, int bnc, const int *d_ptr, const int *d_idx, const double *d_val,
                          const int *d_bptr, int *d_bidx, double *d_bval, void *stream);
 
+/* A <- A - sigma*I on a CSR mirror: the first stored diagonal entry of every row
+ *                                                         src/matrix/lis_matrix_csr.c:565-603 */
+int lisb200_csr_shift_diagonal(int n, const int *d_ptr, const int *d_idx, double *d_val, double sigma, void *stream);
+
 /* ---- SSOR sweep (level-scheduled, block-per-"thread" like the reference's OpenMP path) --- */
 /* forward:  x[i] = (b[i] - sum_{L, jj>=blk_start} L*x[jj]) * wd[i]
  * backward: x[i] -= (sum_{U, blk_start<=jj<blk_end} U*x[jj]) * wd[i]

@@ -107,6 +107,7 @@ typedef struct lisd_matrix {
 LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out);   /* build on first use */
 void    lisd_matrix_drop(LIS_MATRIX A);                     /* invalidate / free */
 LIS_INT lisd_matrix_refresh_wd(LIS_MATRIX A);               /* after WD changed on the host */
+LIS_INT lisd_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma);  /* same edit on the mirror (or drops it) */
 void    lisd_mirror_free(lisd_matrix *M);                   /* a mirror that is not (yet) attached to a matrix */
 /* CSR -> ELL/DIA/JAD/BSR by kernels (lis_convert_dev.c); *done = 0: not handled, run the host builder */
 int     lisd_convert_on_device(void);

@@ -640,7 +640,8 @@ LIS_INT lis_matrix_set_bsr(LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT *bptr
 /* ------------------------------------------------------------------ CSR utilities */
 /* A <- A - sigma*I on the host arrays (src/matrix/lis_matrix_ops.c:780-830; per format
  * lis_matrix_csr.c:565-603, lis_matrix_csc.c, lis_matrix_ell.c, lis_matrix_dia.c): the first stored
- * diagonal entry of each row; a row without one is left alone.  The device mirror is dropped. */
+ * diagonal entry of each row; a row without one is left alone.  A CSR / split device mirror gets the
+ * same edit by a kernel, other mirrors are dropped. */
 LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma)
 {
     const LIS_INT n = A->n;
@@ -669,8 +670,7 @@ LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma)
         LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_shift_diagonal: storage format %D (use CSR, CSC, ELL or DIA)\n", A->matrix_type);
         return LIS_ERR_NOT_IMPLEMENTED;
     }
-    lisd_matrix_drop(A);
-    return LIS_SUCCESS;
+    return lisd_matrix_shift_diagonal(A, sigma);
 }
 
 /* every row ascending by column: lis_matrix_sort_csr, src/matrix/lis_matrix_csr.c:1486-1521 */

@@ -88,6 +88,23 @@ LIS_INT lis_matrix_b200_invalidate(LIS_MATRIX A)
     return LIS_SUCCESS;
 }
 
+/* lis_matrix_shift_diagonal changed the host arrays: make the same edit in HBM where the mirror is an
+ * unsplit CSR or a split matrix (one small kernel instead of re-uploading the matrix -- Rayleigh
+ * quotient iteration shifts twice per step), drop the mirror otherwise.  Transposed mirrors and
+ * sweep schedules are rebuilt on demand: their "first diagonal entry" may be another stored one. */
+LIS_INT lisd_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma)
+{
+    lisd_matrix *M = (lisd_matrix *)A->b200_dev;
+    if (M == NULL) return LIS_SUCCESS;
+    const int usable = M->type == A->matrix_type && M->splited == A->is_splited && M->n == A->n &&
+                       (M->splited || M->type == LIS_MATRIX_CSR) && M->sweep == NULL && M->sweep_global == NULL;
+    if (!usable) { lisd_matrix_drop(A); return LIS_SUCCESS; }
+    if (M->has_t) { csr_free(&M->csrT); csr_free(&M->LT); csr_free(&M->UT); M->has_t = 0; }
+    lisd_mark_busy();
+    if (M->splited) return lisd_check(lisb200_shift(A->n, sigma, M->diag, lisd_stream()), "lis_matrix_shift_diagonal");
+    return lisd_check(lisb200_csr_shift_diagonal(A->n, M->csr.ptr, M->csr.idx, M->csr.val, sigma, lisd_stream()), "lis_matrix_shift_diagonal");
+}
+
 LIS_INT lisd_matrix_refresh_wd(LIS_MATRIX A)
 {
     lisd_matrix *M = (lisd_matrix *)A->b200_dev;

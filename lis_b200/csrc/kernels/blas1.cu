@@ -461,6 +461,18 @@ csr_diag_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx,
     d[i] = v;
 }
 
+// first stored entry of row i whose column is i: value -= sigma   (A <- A - sigma I,
+// src/matrix/lis_matrix_csr.c:565-603); rows without a stored diagonal are left alone
+__global__ void __launch_bounds__(256)
+csr_shift_diag_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx, double *__restrict__ val, double sigma)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = ptr[i + 1];
+    for (int j = ptr[i]; j < e; ++j)
+        if (idx[j] == i) { val[j] = sub(val[j], sigma); break; }
+}
+
 }  // namespace lisb
 
 using namespace lisb;
@@ -577,6 +589,14 @@ extern "C" int lisb200_bicgstab_update(int n, double alpha, double omega, const 
     if (n <= 0) return (int)cudaMemsetAsync(rr, 0, sizeof(double), st);
     const bool vec = aligned16(phat) && aligned16(shat) && aligned16(t) && aligned16(x) && aligned16(r);
     bicgstab_update_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, alpha, omega, phat, shat, t, x, r, vec, partial, counter, rr);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int lisb200_csr_shift_diagonal(int n, const int *ptr, const int *idx, double *val, double sigma, void *stream)
+{
+    if (n <= 0) return 0;
+    csr_shift_diag_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, ptr, idx, val, sigma);
     LISB_CHECK_LAUNCH();
     return 0;
 }

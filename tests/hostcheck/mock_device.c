@@ -150,6 +150,13 @@ int lisb200_bicgstab_p(int n, double omega, double beta, const double *v, const 
 int lisb200_bicgstab_update(int n, double alpha, double omega, const double *phat, const double *shat, const double *t,
                             double *x, double *r, double *partial, unsigned int *counter, double *rr, void *s)
 { (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, phat, x); orc_axpy(n, omega, shat, x); orc_axpy(n, -omega, t, r); *rr = orc_dot(n, r, r, 1); return 0; }
+int lisb200_csr_shift_diagonal(int n, const int *p, const int *ix, double *v, double sigma, void *s)
+{
+    (void)s;
+    for (int i = 0; i < n; i++)
+        for (int j = p[i]; j < p[i + 1]; j++) if (ix[j] == i) { v[j] -= sigma; break; }
+    return 0;
+}
 int lisb200_csr_get_diagonal(int n, const int *p, const int *i, const double *v, double *d, void *s)
 { (void)s; if (n > 0) orc_csr_get_diagonal(n, p, i, v, d); return 0; }
 
