@@ -138,14 +138,32 @@ LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
     if (type >= LIS_PRECON_TYPE_USERDEF) {
         if (type >= g_reg_type || g_reg == NULL) err = create_unsupported(solver, *precon);
         else err = g_reg[type - LIS_PRECON_TYPE_USERDEF].pcreate(solver, *precon);
-    } else if (type && solver->options[LIS_OPTIONS_ADDS]) {
-        err = create_unsupported(solver, *precon);          /* additive Schwarz: out of scope */
-    } else switch (type) {
-    case LIS_PRECON_TYPE_NONE: err = create_none(solver, *precon); break;
-    case LIS_PRECON_TYPE_JACOBI: err = create_jacobi(solver, *precon); break;
-    case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
-    case LIS_PRECON_TYPE_ILU: err = lis_host_ilu_create(solver, *precon); break;
-    default: err = create_unsupported(solver, *precon); break;
+    } else {
+        switch (type) {
+        case LIS_PRECON_TYPE_NONE: err = create_none(solver, *precon); break;
+        case LIS_PRECON_TYPE_JACOBI: err = create_jacobi(solver, *precon); break;
+        case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
+        case LIS_PRECON_TYPE_ILU: err = lis_host_ilu_create(solver, *precon); break;
+        default: err = create_unsupported(solver, *precon); break;
+        }
+        if (!err && type && solver->options[LIS_OPTIONS_ADDS]) {
+            /* -adds true: the preconditioner becomes the inner solve of an additive Schwarz /
+             * Richardson loop (src/precon/lis_precon.c:142-146, lis_precon_ads.c:52-100): two work
+             * vectors, the matrix the solver iterates on */
+            LIS_VECTOR *work = (LIS_VECTOR *)lis_calloc(2 * sizeof(LIS_VECTOR), "lis_precon_create_adds::work");
+            if (work == NULL) { LIS_SETERR_MEM(2 * sizeof(LIS_VECTOR)); err = LIS_OUT_OF_MEMORY; }
+            else if ((*precon)->work) { lis_free(work); LIS_SETERR_IMP; err = LIS_ERR_NOT_IMPLEMENTED; }
+            else {
+                (*precon)->work = work;
+                for (LIS_INT i = 0; i < 2 && !err; i++) { err = lis_vector_duplicate(solver->A, &work[i]); if (!err) (*precon)->worklen = i + 1; }
+                if (!err) {
+                    if ((*precon)->is_copy && (*precon)->A && (*precon)->A != solver->A) lis_matrix_destroy((*precon)->A);
+                    (*precon)->A = solver->A;
+                    (*precon)->is_copy = LIS_FALSE;
+                    (*precon)->precon_type = LIS_PRECON_TYPE_ADDS;
+                }
+            }
+        }
     }
     if (err) { lis_precon_destroy(*precon); *precon = NULL; return err; }
     return LIS_SUCCESS;
@@ -184,10 +202,42 @@ LIS_INT lis_psolve_ssor(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
     return lis_matrix_solve(solver->precon->A, b, x, LIS_MATRIX_SSOR);
 }
 
+static LIS_INT psolve_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
+static LIS_INT psolveh_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x);
+
+/* additive Schwarz wrapper, src/precon/lis_precon_ads.c:104-150 (transposed: :196-245):
+ *   x = 0; r = b; repeat adds_iter+1 times: w = M^-1 r; x += w; (not after the last) r = b - A x
+ * On one process this is adds_iter steps of preconditioned Richardson.  "x += w" and "r = b - r" are
+ * axpy(1.0) and xpay(-1.0): multiplications by +-1 are exact, the bits are those of the reference's loops.
+ * The reference also zeroes the halo part of r before each inner solve; the inner solves here never
+ * read beyond the owned rows. */
+static LIS_INT psolve_adds(LIS_SOLVER solver, LIS_VECTOR B, LIS_VECTOR X, int transposed)
+{
+    LIS_PRECON precon = solver->precon;
+    LIS_VECTOR W = precon->work[0], R = precon->work[1];
+    const LIS_INT iter = solver->options[LIS_OPTIONS_ADDS_ITER], ptype = solver->options[LIS_OPTIONS_PRECON];
+    LIS_INT err = lisd_set_all(0.0, X);
+    if (!err) err = lisd_copy(B, R);
+    for (LIS_INT k = 0; k < iter + 1 && !err; k++) {
+        err = transposed ? psolveh_type(ptype, solver, R, W) : psolve_type(ptype, solver, R, W);
+        if (!err) err = lisd_axpy(1.0, W, X);
+        if (!err && k != iter) {
+            err = transposed ? lisd_matvech(precon->A, X, R) : lisd_matvec(precon->A, X, R);
+            if (!err) err = lisd_xpay(B, -1.0, R);
+        }
+    }
+    return err;
+}
+
 /* the lis_psolve macro of the reference (include/lis_precon.h:32) as a function; async */
 LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
 {
-    const LIS_INT type = solver->precon->precon_type;
+    if (solver->precon->precon_type == LIS_PRECON_TYPE_ADDS) return psolve_adds(solver, b, x, 0);
+    return psolve_type(solver->precon->precon_type, solver, b, x);
+}
+
+static LIS_INT psolve_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
     switch (type) {
     case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
@@ -205,7 +255,12 @@ LIS_INT lis_psolve(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
  * lis_psolveh_jacobi: x = b*conj(d)); SSOR and ILU run their transposed sweeps */
 LIS_INT lis_psolveh(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
 {
-    const LIS_INT type = solver->precon->precon_type;
+    if (solver->precon->precon_type == LIS_PRECON_TYPE_ADDS) return psolve_adds(solver, b, x, 1);
+    return psolveh_type(solver->precon->precon_type, solver, b, x);
+}
+
+static LIS_INT psolveh_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
     switch (type) {
     case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);

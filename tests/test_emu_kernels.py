@@ -166,3 +166,7 @@ def test_etest1_driver_emulated(emu_drivers, tmp_path, opts):
 
 def test_etest5_driver_emulated(emu_drivers, tmp_path):
     D.test_etest5_driver_lanczos(tmp_path)
+
+
+def test_test3b_driver_hpcg_kernel_emulated(emu_drivers, tmp_path):
+    D.test_test3b_driver_hpcg_kernel(tmp_path)

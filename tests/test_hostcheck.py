@@ -88,6 +88,24 @@ def test_stationary_solvers_bit_for_bit(hc, ref_serial, opts):
     assert g["err"] == 5                               # the reference rescales the system there; not provided
 
 
+@pytest.mark.parametrize("opts", ["-i cg -p ssor -adds true", "-i cg -p jacobi -adds true -adds_iter 3", "-i bicgstab -p ilu -adds true",
+                                  "-i bicg -p ssor -adds true -adds_iter 2", "-i gmres -restart 12 -p ssor -adds true",
+                                  "-i cg -p none -adds true"])
+def test_additive_schwarz_wrapper_bit_for_bit(hc, ref_serial, opts):
+    """-adds true (src/precon/lis_precon_ads.c): the preconditioner as the inner solve of adds_iter
+    Richardson steps; what test/test3b.c (hpcg_kernel) hard-wires.  With -p none the option is ignored."""
+    for name, (ptr, idx, val) in systems():
+        if ("-i cg" in opts or "-i bicg " in opts) and name == "unsym" and "-i cg" in opts:
+            continue
+        n = len(ptr) - 1
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))
+        g = hc.solve(ptr, idx, val, b, opts)
+        r = ref_serial.solve(ptr, idx, val, b, opts)
+        assert (g["err"], g["status"], g["iter"]) == (r["err"], r["status"], r["iter"]), (name, opts, g["iter"], r["iter"])
+        H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{name} {opts} residual history")
+        H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} solution")
+
+
 @pytest.mark.parametrize("fmt", FORMATS)
 def test_solve_in_every_storage_format(hc, ref_serial, fmt):
     """-storage converts the matrix in place before the solve (lis_matrix_convert_self); the matrix
@@ -222,7 +240,7 @@ def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads)
 def test_unsupported_requests_are_rejected(hc):
     ptr, idx, val = H.poisson1d(30)
     b = np.ones(30)
-    for opts, code in (("-i bicg -p sainv", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p jacobi -adds true", 5),
+    for opts, code in (("-i bicg -p sainv", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p saamg -adds true", 5),
                        ("-i cg -scale jacobi", 5), ("-i cg -f quad", 1), ("-i gmres -conv_cond nrm2_b", 1), ("-i jacobi -conv_cond nrm2_b", 1),
                        ("-i gmres -restart -1", 1), ("-i cg -maxiter -3", 1)):
         g = hc.solve(ptr, idx, val, b, opts)

@@ -215,9 +215,15 @@ def test_test1_driver_matrix_market(tmp_path):
 
 @pytest.mark.gpu
 def test_test3b_driver_hpcg_kernel(tmp_path):
-    """test3b hard-wires -i cg -p ssor -adds true (additive Schwarz); lis_b200 rejects ADDS, so
-    the driver is run with -adds false appended (later options win, as in the reference)"""
+    """test3b (installed as hpcg_kernel) hard-wires -i cg -p ssor -adds true: CG with the additive Schwarz
+    wrapper around SSOR, on its own 27-point matrix; same iteration count as the reference-linked binary"""
     need("test3b")
-    args = (12, 12, 12, 1, tmp_path / "sol.txt", tmp_path / "rh.txt", "-adds", "false")
+    args = (12, 12, 12, 1, tmp_path / "sol.txt", tmp_path / "rh.txt")
     it, res = solver_lines(run(os.path.join(OURS, "test3b"), *args))
     assert res < 1e-12 and it > 0
+    sol = np.loadtxt(tmp_path / "sol.txt", skiprows=2)[:, 1]
+    assert np.abs(sol - 1.0).max() < 1e-8
+    if os.path.exists(os.path.join(REFS, "test3b")):
+        args_r = (12, 12, 12, 1, tmp_path / "sol_r.txt", tmp_path / "rh_r.txt")
+        it_r, _ = solver_lines(run(os.path.join(REFS, "test3b"), *args_r))
+        assert it == it_r, (it, it_r)
