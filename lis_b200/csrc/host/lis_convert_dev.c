@@ -10,7 +10,7 @@
  * Selected with LIS_B200_CONVERT=device (default this round: host); any case the
  * kernels do not cover (more than 255 entries in a row for JAD, more than 64 blocks in a block row
  * for BSR, row-partitioned BSR) reports *done = 0 and the host builder runs.  Output arrays are
- * identical to the host builder's, entry for entry (tests/test_gpu_parity.py, tests/test_emu_kernels.py).
+ * identical to the host builder's, entry for entry (tests/test_z1_gpu_parity2.py, tests/test_emu_kernels.py).
  */
 #include <stdio.h>
 #include <stdlib.h>

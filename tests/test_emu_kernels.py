@@ -15,6 +15,7 @@ import pytest
 import harness as H
 import lis_b200
 import test_gpu_parity as G
+import test_z1_gpu_parity2 as G2
 
 EMU_DIR = os.path.join(H.ROOT, "tests", "cudaemu")
 
@@ -31,10 +32,10 @@ test_spmv_csr_both_kernels = G.test_spmv_csr_both_kernels
 test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
 test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
-test_bicgstab_fused_updates_same_bits = G.test_bicgstab_fused_updates_same_bits
-test_gram_schmidt_fused_chain_same_bits = G.test_gram_schmidt_fused_chain_same_bits
-test_device_conversion_same_arrays_as_host = G.test_device_conversion_same_arrays_as_host
-test_device_conversion_falls_back_to_host_builder = G.test_device_conversion_falls_back_to_host_builder
+test_bicgstab_fused_updates_same_bits = G2.test_bicgstab_fused_updates_same_bits
+test_gram_schmidt_fused_chain_same_bits = G2.test_gram_schmidt_fused_chain_same_bits
+test_device_conversion_same_arrays_as_host = G2.test_device_conversion_same_arrays_as_host
+test_device_conversion_falls_back_to_host_builder = G2.test_device_conversion_falls_back_to_host_builder
 test_blas1_elementwise_bit_exact = G.test_blas1_elementwise_bit_exact
 test_blas1_length_mismatch_is_ill_arg = G.test_blas1_length_mismatch_is_ill_arg
 test_reductions_bounded = G.test_reductions_bounded
@@ -125,13 +126,14 @@ def test_emulator_catches_misalignment_and_overrun(b200, what, expect):
 # ---- the overlapped host-buffer product (lis_b200_matvec_host): three streams chained by events.
 # The emulator's secondary streams are lazy (copies happen as late as the events allow), so a row
 # chunk that starts before its x entries have landed reads the previous contents of x.
-test_matvec_host_pipelined = G.test_matvec_host_pipelined
-test_matvec_host_pipelined_default_chunks = G.test_matvec_host_pipelined_default_chunks
+test_matvec_host_pipelined = G2.test_matvec_host_pipelined
+test_matvec_host_pipelined_default_chunks = G2.test_matvec_host_pipelined_default_chunks
 
 
 # ---- the reference's own drivers (test/*.c, unchanged) linked against the emulator build: their
 # transcripts against the same sources linked with the compiled reference
 import test_reference_drivers as D  # noqa: E402
+import test_z2_reference_drivers2 as D2  # noqa: E402
 
 
 @pytest.fixture()
@@ -147,7 +149,7 @@ def test_spmvtest_drivers_emulated(emu_drivers, driver, args, analytic):
 
 @pytest.mark.parametrize("driver", ["spmvtest4", "spmvtest5"])
 def test_spmvtest_file_drivers_emulated(emu_drivers, tmp_path, driver):
-    D.test_spmvtest_file_drivers(tmp_path, driver)
+    D2.test_spmvtest_file_drivers(tmp_path, driver)
 
 
 @pytest.mark.parametrize("opts", ["-i cg -p jacobi", "-i bicgstab -p ssor", "-i gmres -restart 30 -p jacobi", "-i cg -p jacobi -storage ell"])
@@ -161,11 +163,11 @@ def test_test1_driver_emulated(emu_drivers, tmp_path):
 
 @pytest.mark.parametrize("opts", ["", "-e ii -i cg -p jacobi", "-e rqi"])
 def test_etest1_driver_emulated(emu_drivers, tmp_path, opts):
-    D.test_etest1_driver(tmp_path, opts)
+    D2.test_etest1_driver(tmp_path, opts)
 
 
 def test_etest5_driver_emulated(emu_drivers, tmp_path):
-    D.test_etest5_driver_lanczos(tmp_path)
+    D2.test_etest5_driver_lanczos(tmp_path)
 
 
 def test_test3b_driver_hpcg_kernel_emulated(emu_drivers, tmp_path):

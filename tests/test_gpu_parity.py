@@ -107,190 +107,6 @@ def test_blas1_elementwise_bit_exact(b200, oracle, op, n):
         H.assert_bits_equal(b_, ob, f"{op}(b) n={n}")
 
 
-@pytest.mark.parametrize("kernel", ["tma", "tile"])
-@pytest.mark.parametrize("case", ["banded", "stencil27", "full_reach", "ragged"])
-def test_matvec_host_pipelined(b200, oracle, monkeypatch, kernel, case):
-    """lis_b200_matvec_host (copy-in, product, copy-out overlapped chunk-wise on three streams) leaves
-    host_y, x and y with the bits of lis_vector_scatter + lis_matvec + lis_vector_gather, and its
-    chunk plan never lets a row start before the x entries it reads have landed"""
-    import ctypes as C
-    monkeypatch.setenv("LIS_B200_CSR_KERNEL", kernel)
-    monkeypatch.setenv("LIS_B200_PIPE_CHUNKS", "7")
-    if case == "banded":
-        ptr, idx, val = H.random_csr(5000, 5, 12, band=300, sorted_rows=True)
-    elif case == "stencil27":
-        ptr, idx, val = H.poisson3d_27pt(15, 14, 13)
-    elif case == "full_reach":
-        ptr, idx, val = H.random_csr(3000, 6, 5, values="wide")
-    else:
-        ptr, idx, val = H.random_csr(2600, 4, 13, empty_rows=True, diag_dominant=False)
-    n = len(ptr) - 1
-    L = b200.lib
-    vp = C.c_void_p
-    L.shim_mv_open.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
-    L.shim_mv_step_e2e.argtypes = [C.c_int, vp, vp]
-    L.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, vp, vp]
-    L.shim_mv_host_plan.argtypes = [C.c_int, C.c_int, vp, vp]
-    L.shim_mv_get_xy.argtypes = [C.c_int, vp, vp]
-    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
-    assert h >= 0
-    try:
-        for seed in (1, 2, 3):                      # x changes between calls: stale reads would show
-            hx = H.rand_vec(n, seed, "wide")
-            hy = np.full(n, np.nan)
-            assert L.shim_mv_step_e2e_pipelined(h, hx.ctypes.data, hy.ctypes.data) == 0
-            want = oracle.spmv("csr", ptr, idx, val, hx)
-            H.assert_bits_equal(hy, want, f"pipelined {case}/{kernel} seed {seed}")
-            xo = np.empty(n); yo = np.empty(n)
-            assert L.shim_mv_get_xy(h, xo.ctypes.data, yo.ctypes.data) == 0
-            H.assert_bits_equal(xo, hx, "x vector after the pipelined product")
-            H.assert_bits_equal(yo, want, "y vector after the pipelined product")
-            hy2 = np.full(n, np.nan)
-            assert L.shim_mv_step_e2e(h, hx.ctypes.data, hy2.ctypes.data) == 0
-            H.assert_bits_equal(hy2, want, "three separate calls")
-        rows = np.zeros(65, np.int32); need = np.zeros(64, np.int32)
-        nch = L.shim_mv_host_plan(h, 64, rows.ctypes.data, need.ctypes.data)
-        assert nch >= 2, nch
-        assert rows[0] == 0 and rows[nch] == n and np.all(np.diff(rows[:nch + 1]) > 0)
-        for c in range(nch):                         # no row of chunk c reads beyond x chunk need[c]
-            cols = idx[ptr[rows[c]]:ptr[rows[c + 1]]]
-            if len(cols):
-                assert cols.max() < rows[need[c] + 1], (c, cols.max(), rows[need[c] + 1])
-        if case in ("banded", "stencil27"):
-            assert np.all(need[:nch - 1] <= np.arange(nch - 1) + 1), need[:nch]   # band: next chunk at most
-    finally:
-        L.shim_mv_close(h)
-
-
-def test_matvec_host_pipelined_default_chunks(b200, oracle):
-    """the chunking the library picks by itself (>= 2^18 rows per chunk, boundaries on multiples of
-    1024 rows) on a 1.3 M-row stencil: same bits as the oracle and as the three-call sequence"""
-    import ctypes as C
-    ptr, idx, val = H.poisson3d_7pt(128, 128, 80, sort=True)
-    n = len(ptr) - 1
-    L = b200.lib
-    vp = C.c_void_p
-    L.shim_mv_open.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
-    L.shim_mv_step_e2e.argtypes = [C.c_int, vp, vp]
-    L.shim_mv_step_e2e_pipelined.argtypes = [C.c_int, vp, vp]
-    L.shim_mv_host_plan.argtypes = [C.c_int, C.c_int, vp, vp]
-    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
-    assert h >= 0
-    try:
-        for seed in (5, 6):
-            hx = H.rand_vec(n, seed, "wide")
-            hy = np.full(n, np.nan); hy2 = np.full(n, np.nan)
-            assert L.shim_mv_step_e2e_pipelined(h, hx.ctypes.data, hy.ctypes.data) == 0
-            assert L.shim_mv_step_e2e(h, hx.ctypes.data, hy2.ctypes.data) == 0
-            H.assert_bits_equal(hy, hy2, "overlapped vs three calls")
-            H.assert_bits_equal(hy, oracle.spmv("csr", ptr, idx, val, hx), "overlapped vs oracle")
-        rows = np.zeros(65, np.int32); need = np.zeros(64, np.int32)
-        nch = L.shim_mv_host_plan(h, 64, rows.ctypes.data, need.ctypes.data)
-        assert nch == 5 and np.all(rows[1:nch] % 1024 == 0), (nch, rows[:nch + 1])
-        assert list(need[:nch]) == [1, 2, 3, 4, 4]           # a 7-point row reaches one grid plane ahead
-    finally:
-        L.shim_mv_close(h)
-
-
-def _conv_cases():
-    yield "poisson3d_7pt_sorted", H.poisson3d_7pt(17, 13, 11, sort=True)
-    yield "poisson3d_7pt_unsorted", H.poisson3d_7pt(12, 9, 10)
-    yield "poisson3d_27pt", H.poisson3d_27pt(9, 8, 7)
-    yield "random_ragged", H.random_csr(2500, 7, 11, values="wide")
-    yield "random_banded_sorted", H.random_csr(9001, 5, 12, band=40, sorted_rows=True)
-    yield "random_empty_rows", H.random_csr(4200, 4, 13, empty_rows=True, diag_dominant=False)
-    yield "single_row", (np.array([0, 1], np.int32), np.array([0], np.int32), np.array([3.5]))
-    yield "poisson1d_5000", H.poisson1d(5000)
-
-
-@pytest.mark.parametrize("fmt,blk", [("ell", (0, 0)), ("dia", (0, 0)), ("jad", (0, 0)), ("bsr", (2, 2)), ("bsr", (3, 2)),
-                                     ("bsr", (1, 4)), ("bsr", (4, 4))])
-def test_device_conversion_same_arrays_as_host(b200, oracle, monkeypatch, fmt, blk):
-    """LIS_B200_CONVERT=device (kernels/convert.cu): lis_matrix_convert builds ELL / DIA / JAD / BSR in
-    HBM; every public array must equal the host builder's (which is pinned to the reference's
-    layouts in test_oracle_vs_reference.py), and the product on the converted matrix -- served by
-    the mirror the conversion left on the device -- must carry the oracle's bits"""
-    for name, (ptr, idx, val) in _conv_cases():
-        if fmt == "dia" and name == "random_ragged":
-            continue
-        monkeypatch.setenv("LIS_B200_CONVERT", "host")
-        want = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
-        monkeypatch.setenv("LIS_B200_CONVERT", "device")
-        got = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
-        assert set(got) == set(want)
-        for key in want:
-            if isinstance(want[key], np.ndarray):
-                assert got[key].dtype == want[key].dtype and got[key].shape == want[key].shape, (fmt, name, key)
-                if want[key].dtype == np.float64:
-                    H.assert_bits_equal(got[key], want[key], f"{fmt}/{name}/{key}")
-                else:
-                    assert np.array_equal(got[key], want[key]), (fmt, name, key)
-            else:
-                assert got[key] == want[key], (fmt, name, key, got[key], want[key])
-        x = H.rand_vec(len(ptr) - 1, 3, "wide")
-        y, _ = b200.spmv(fmt, ptr, idx, val, x, bnr=blk[0], bnc=blk[1])
-        H.assert_bits_equal(y, oracle.spmv(fmt, ptr, idx, val, x, bnr=blk[0] or 2, bnc=blk[1] or 2), f"spmv after device {fmt}/{name}")
-
-
-def test_device_conversion_falls_back_to_host_builder(b200, monkeypatch):
-    """rows longer than 255 entries (JAD) and block rows with more than 64 blocks (BSR) are outside
-    what the conversion kernels cover: the host builder takes over, same arrays"""
-    rng = np.random.default_rng(8)
-    n = 600
-    lens = rng.integers(1, 6, n); lens[17] = 300; lens[400] = 256
-    ptr = np.zeros(n + 1, np.int32); ptr[1:] = np.cumsum(lens)
-    idx = np.concatenate([rng.choice(n, l, replace=False) for l in lens]).astype(np.int32)
-    val = rng.standard_normal(ptr[-1])
-    for fmt, blk in (("jad", (0, 0)), ("bsr", (2, 2))):
-        monkeypatch.setenv("LIS_B200_CONVERT", "host")
-        want = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
-        monkeypatch.setenv("LIS_B200_CONVERT", "device")
-        got = b200.convert(fmt, ptr, idx, val, bnr=blk[0], bnc=blk[1])
-        for key in want:
-            if isinstance(want[key], np.ndarray):
-                assert np.array_equal(got[key], want[key]), (fmt, key)
-
-
-@pytest.mark.parametrize("opts", ["-i gmres -restart 30 -p jacobi", "-i gmres -restart 7 -p none", "-i fgmres -restart 20 -p ssor"])
-def test_gram_schmidt_fused_chain_same_bits(b200, oracle, monkeypatch, opts):
-    """GMRES / FGMRES orthogonalisation: axpy fused with the following dot / norm (mgs_step_kernel),
-    axpy and dot as separate launches chained on the device, and the reference's call-for-call
-    sequence with a host wait per dot must give the same residual history and solution, bit for bit"""
-    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(12, 11, 10)), ("unsym", H.random_csr(1501, 6, 3)), ("odd", H.poisson1d(333))):
-        b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
-        runs = {}
-        for mode, env in (("fused", {}), ("chain", {"LIS_B200_MGS": "chain"}), ("waits", {"LIS_B200_FUSE": "0"})):
-            for key in ("LIS_B200_MGS", "LIS_B200_FUSE"):
-                monkeypatch.delenv(key, raising=False)
-            for key, v in env.items():
-                monkeypatch.setenv(key, v)
-            runs[mode] = b200.solve(ptr, idx, val, b, opts + " -maxiter 70")
-        for mode in ("chain", "waits"):
-            assert runs[mode]["iter"] == runs["fused"]["iter"] and runs[mode]["status"] == runs["fused"]["status"], (name, opts, mode)
-            H.assert_bits_equal(runs[mode]["rhistory"], runs["fused"]["rhistory"], f"{name} {opts} rhistory fused vs {mode}")
-            H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
-
-
-@pytest.mark.parametrize("opts", ["-i bicgstab -p jacobi", "-i bicgstab -p ssor", "-i bicgstab -p none -maxiter 60"])
-def test_bicgstab_fused_updates_same_bits(b200, oracle, monkeypatch, opts):
-    """BiCGSTAB with its vector updates fused (p update; s = r - alpha v with ||s||; x, r updates with
-    ||r||; <t,s> with <t,t>), with one launch per reference call for the updates, and with every
-    fusion off: same iteration count, residual history and solution, bit for bit"""
-    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(12, 11, 10)), ("unsym", H.random_csr(1501, 6, 3)), ("odd", H.poisson1d(333))):
-        b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
-        runs = {}
-        for mode, env in (("fused", {}), ("calls", {"LIS_B200_BICGSTAB": "calls"}), ("off", {"LIS_B200_FUSE": "0"})):
-            for key in ("LIS_B200_BICGSTAB", "LIS_B200_FUSE"):
-                monkeypatch.delenv(key, raising=False)
-            for key, v in env.items():
-                monkeypatch.setenv(key, v)
-            runs[mode] = b200.solve(ptr, idx, val, b, opts)
-        for mode in ("calls", "off"):
-            assert runs[mode]["iter"] == runs["fused"]["iter"] and runs[mode]["status"] == runs["fused"]["status"], (name, opts, mode)
-            H.assert_bits_equal(runs[mode]["rhistory"], runs["fused"]["rhistory"], f"{name} {opts} rhistory fused vs {mode}")
-            H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
-
-
 def test_blas1_length_mismatch_is_ill_arg(b200):
     for op in ("axpy", "xpay", "copy", "dot"):
         assert b200.vec_mismatch(op) == 1          # LIS_ERR_ILL_ARG, lis_vector_opv.c:158-163
