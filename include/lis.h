@@ -550,6 +550,7 @@ LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver);
 LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver, LIS_PRECON precon);
 LIS_INT lis_solve_setup(LIS_MATRIX A, LIS_SOLVER solver);
 LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma);
+LIS_INT lis_matrix_scale(LIS_MATRIX A, LIS_VECTOR B, LIS_VECTOR D, LIS_INT action);
 
 /* ------------------------------------------------------------------ eigensolvers (standard problem:
  * power, inverse, Rayleigh quotient, CG, CR, subspace, Lanczos, Arnoldi) */

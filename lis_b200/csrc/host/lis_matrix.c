@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "lis_device.h"
 #include "lis_host.h"
 #include "lis_b200_kernels.h"
@@ -638,6 +639,61 @@ LIS_INT lis_matrix_set_bsr(LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT *bptr
 }
 
 /* ------------------------------------------------------------------ CSR utilities */
+/* -scale: A <- D^-1 A, b <- D^-1 b (LIS_SCALE_JACOBI) or A <- D^-1/2 A D^-1/2, b <- D^-1/2 b
+ * (LIS_SCALE_SYMM_DIAG), D = diag(A); the scaling vector stays in Dv (src/matrix/lis_matrix_ops.c:579-712,
+ * CSR loops src/matrix/lis_matrix_csr.c:607-693).  Once per solve, on the host arrays the caller sees
+ * (they stay scaled, A->is_scaled, like in the reference); the device mirror is dropped.  CSR, one process. */
+LIS_INT lis_matrix_scale(LIS_MATRIX A, LIS_VECTOR B, LIS_VECTOR Dv, LIS_INT action)
+{
+    const LIS_INT n = A->n;
+    LIS_INT err = lis_host_matrix_check_input(A);
+    if (err) return err;
+    if (A->matrix_type != LIS_MATRIX_CSR || A->nprocs > 1) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale needs a CSR matrix on one process (scaling runs before -storage converts)\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    if (action != LIS_SCALE_JACOBI && action != LIS_SCALE_SYMM_DIAG) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
+    err = lis_matrix_get_diagonal(A, Dv);
+    if (err) return err;
+    LIS_SCALAR *d = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(n > 0 ? n : 1));
+    if (d == NULL) { LIS_SETERR_MEM(n * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
+    err = n > 0 ? lis_vector_get_values(Dv, Dv->is + Dv->origin, n, d) : LIS_SUCCESS;
+    if (err) { free(d); return err; }
+    if (action == LIS_SCALE_SYMM_DIAG) {
+        for (LIS_INT i = 0; i < n; i++) d[i] = 1.0 / sqrt(fabs(d[i]));
+        if (A->is_splited) {
+            for (LIS_INT i = 0; i < n; i++) {
+                A->D->value[i] = 1.0;
+                for (LIS_INT j = A->L->ptr[i]; j < A->L->ptr[i + 1]; j++) A->L->value[j] = A->L->value[j] * d[i] * d[A->L->index[j]];
+                for (LIS_INT j = A->U->ptr[i]; j < A->U->ptr[i + 1]; j++) A->U->value[j] = A->U->value[j] * d[i] * d[A->U->index[j]];
+            }
+        } else {
+            for (LIS_INT i = 0; i < n; i++)
+                for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) A->value[j] = A->value[j] * d[i] * d[A->index[j]];
+        }
+    } else {
+        for (LIS_INT i = 0; i < n; i++) d[i] = 1.0 / d[i];
+        if (A->is_splited) {
+            for (LIS_INT i = 0; i < n; i++) {
+                A->D->value[i] = 1.0;
+                for (LIS_INT j = A->L->ptr[i]; j < A->L->ptr[i + 1]; j++) A->L->value[j] *= d[i];
+                for (LIS_INT j = A->U->ptr[i]; j < A->U->ptr[i + 1]; j++) A->U->value[j] *= d[i];
+            }
+        } else {
+            for (LIS_INT i = 0; i < n; i++)
+                for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) A->value[j] *= d[i];
+        }
+    }
+    lisd_matrix_drop(A);
+    if (n > 0) err = lis_vector_set_values2(LIS_INS_VALUE, Dv->is + Dv->origin, n, d, Dv);
+    free(d);
+    if (!err) err = lis_vector_pmul(B, Dv, B);                 /* b[i] = b[i]*d[i] */
+    if (err) return err;
+    A->is_scaled = LIS_TRUE;
+    B->is_scaled = LIS_TRUE;
+    return LIS_SUCCESS;
+}
+
 /* A <- A - sigma*I on the host arrays (src/matrix/lis_matrix_ops.c:780-830; per format
  * lis_matrix_csr.c:565-603, lis_matrix_csc.c, lis_matrix_ell.c, lis_matrix_dia.c): the first stored
  * diagonal entry of each row; a row without one is left alone.  A CSR / split device mirror gets the

@@ -8,7 +8,7 @@
  *   :1792-1813, shadow residual :1817-1875, getters :1640-1790.
  * Every vector/matrix operation inside is a CUDA kernel launch; scalars stay on the host.
  * Not carried over (outside the hot path, rejected with an error instead of ignored):
- * -scale, quad/switch precision, -use_at, I+S and additive-Schwarz preconditioning.
+ * quad/switch precision, -use_at, I+S preconditioning.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -522,7 +522,7 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     const LIS_INT precon_type = solver->options[LIS_OPTIONS_PRECON];
     const LIS_INT maxiter = solver->options[LIS_OPTIONS_MAXITER];
     const LIS_INT output = solver->options[LIS_OPTIONS_OUTPUT];
-    const LIS_INT scale = solver->options[LIS_OPTIONS_SCALE];
+    LIS_INT scale = solver->options[LIS_OPTIONS_SCALE];
     const LIS_INT precision = solver->options[LIS_OPTIONS_PRECISION];
     const LIS_INT conv_cond = solver->options[LIS_OPTIONS_CONV_COND];
     const LIS_REAL tol = solver->params[LIS_PARAMS_RESID - LIS_OPTIONS_LEN];
@@ -559,12 +559,12 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
         LIS_SETERR(LIS_ERR_ILL_ARG, "Quad precision is not enabled\n");
         return LIS_ERR_ILL_ARG;
     }
-    if (scale != LIS_SCALE_NONE || solver->options[LIS_OPTIONS_USE_AT]) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale and -use_at are outside the B200 hot path\n");
+    if (solver->options[LIS_OPTIONS_USE_AT]) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-use_at is outside the B200 hot path\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
-    if (nsolver >= LIS_SOLVER_JACOBI && nsolver <= LIS_SOLVER_SOR && precon_type != LIS_PRECON_TYPE_NONE) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "the stationary solvers (jacobi, gs, sor) run with -p none only (the reference rescales the system otherwise)\n");
+    if (scale != LIS_SCALE_NONE && solver->options[LIS_OPTIONS_STORAGE] == LIS_MATRIX_BSR && scale == LIS_SCALE_JACOBI) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "block Jacobi scaling of BSR matrices is outside the B200 hot path\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     err = entry.check(solver);
@@ -601,6 +601,20 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
 
     p_c_time = 0.0;
     itime = lis_wtime();
+
+    /* system scaling (src/solver/lis_solver.c:636-721): the stationary solvers with a preconditioner
+     * always work on D^-1 A; -scale jacobi|symm_diag on request (CG turns jacobi into symm_diag to keep
+     * the matrix symmetric).  A and b stay scaled afterwards, exactly as there. */
+    if (nsolver >= LIS_SOLVER_JACOBI && nsolver <= LIS_SOLVER_SOR && precon_type != LIS_PRECON_TYPE_NONE) {
+        if (solver->d == NULL) err = lis_vector_duplicate(A, &solver->d);
+        if (!err && !A->is_scaled) err = lis_matrix_scale(A, b, solver->d, LIS_SCALE_JACOBI);
+    } else if (scale) {
+        if (solver->d == NULL) err = lis_vector_duplicate(A, &solver->d);
+        if (scale == LIS_SCALE_JACOBI && nsolver == LIS_SOLVER_CG) scale = LIS_SCALE_SYMM_DIAG;
+        if (!err && !A->is_scaled) err = lis_matrix_scale(A, b, solver->d, scale);
+        else if (!err && !b->is_scaled) err = lis_vector_pmul(b, solver->d, b);
+    }
+    if (err) { lis_vector_destroy(xx); lis_free(rhistory); solver->retcode = err; return err; }
 
     /* -storage: converts A in place */
     err = lis_matrix_convert_self(solver);
@@ -656,7 +670,8 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
         }
     }
     {
-        LIS_INT e2 = lisd_copy(xx, x);
+        /* symmetric scaling solved for D^1/2 x: x = xx .* d (:877-886) */
+        LIS_INT e2 = (scale == LIS_SCALE_SYMM_DIAG && solver->d) ? lisd_pmul(xx, solver->d, x) : lisd_copy(xx, x);
         if (!e2) e2 = lisd_sync();
         if (e2) { lis_solver_work_destroy(solver); lis_vector_destroy(xx); return e2; }
     }

@@ -32,6 +32,7 @@ test_spmv_csr_both_kernels = G.test_spmv_csr_both_kernels
 test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
 test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
+test_scaling_and_additive_schwarz_follow_the_reference = G2.test_scaling_and_additive_schwarz_follow_the_reference
 test_bicgstab_fused_updates_same_bits = G2.test_bicgstab_fused_updates_same_bits
 test_gram_schmidt_fused_chain_same_bits = G2.test_gram_schmidt_fused_chain_same_bits
 test_device_conversion_same_arrays_as_host = G2.test_device_conversion_same_arrays_as_host

@@ -193,3 +193,19 @@ def test_bicgstab_fused_updates_same_bits(b200, oracle, monkeypatch, opts):
             assert runs[mode]["iter"] == runs["fused"]["iter"] and runs[mode]["status"] == runs["fused"]["status"], (name, opts, mode)
             H.assert_bits_equal(runs[mode]["rhistory"], runs["fused"]["rhistory"], f"{name} {opts} rhistory fused vs {mode}")
             H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
+
+
+@pytest.mark.parametrize("opts", ["-i cg -scale jacobi", "-i bicgstab -scale symm_diag -p jacobi", "-i sor -p jacobi -omega 1.5 -maxiter 400",
+                                  "-i cg -p ssor -adds true"])
+def test_scaling_and_additive_schwarz_follow_the_reference(b200, ref_serial, opts):
+    """-scale (A and b scaled in place before the loop), the stationary solvers with a preconditioner
+    and the additive Schwarz wrapper against the compiled serial reference: same status, iteration
+    count within one step (the reductions differ), same solution"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(10, 9, 8)), ("p1d", H.poisson1d(150))):
+        n = len(ptr) - 1
+        b = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))[0]
+        g = b200.solve(ptr, idx, val, b, opts)
+        r = ref_serial.solve(ptr, idx, val, b, opts)
+        assert g["err"] == r["err"] == 0 and g["status"] == r["status"], (name, opts, g["err"], g["status"], r["status"])
+        assert abs(g["iter"] - r["iter"]) <= max(1, r["iter"] // 100), (name, opts, g["iter"], r["iter"])
+        assert np.abs(g["x"] - r["x"]).max() < 1e-8 * max(1.0, np.abs(r["x"]).max()), (name, opts)
