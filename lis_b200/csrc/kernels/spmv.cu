@@ -403,7 +403,8 @@ bsr_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ 
         const double *v = val + (size_t)bc * (R * C);
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            const double xj = __ldg(x + bj + j);
+            // a padded last block column holds structural zeros; x behind them does not exist
+            const double xj = bj + j < n ? __ldg(x + bj + j) : 0.0;
 #pragma unroll
             for (int i = 0; i < R; ++i) t[i] = add(t[i], mul(__ldg(v + j * R + i), xj));
         }
@@ -411,6 +412,32 @@ bsr_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ 
 #pragma unroll
     for (int i = 0; i < R; ++i)
         if (bi * R + i < n) y[bi * R + i] = t[i];
+}
+
+// 2x2 blocks (the reference's default block size, src/matrix/lis_matrix.c:83-84): a block is two
+// 128-bit loads, its two x entries one (x and val 16-byte aligned: block columns start at even
+// positions).  Same products in the same order as bsr_kernel<2,2>:
+//   t0 += a0*x0; t1 += a1*x0; t0 += a2*x1; t1 += a3*x1          (lis_matvec_bsr.c:338-343)
+__global__ void __launch_bounds__(128)
+bsr22_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
+             const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nr) return;
+    double t0 = 0.0, t1 = 0.0;
+    const int s = __ldg(bptr + bi), e = __ldg(bptr + bi + 1);
+    for (int bc = s; bc < e; ++bc) {
+        const int c = __ldg(bidx + bc) * 2;
+        const double2 a01 = ld_stream2(reinterpret_cast<const double2 *>(val + (size_t)bc * 4));
+        const double2 a23 = ld_stream2(reinterpret_cast<const double2 *>(val + (size_t)bc * 4 + 2));
+        double x0, x1;
+        if (c + 1 < n) { const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + c)); x0 = xv.x; x1 = xv.y; }
+        else { x0 = __ldg(x + c); x1 = 0.0; }
+        t0 = add(t0, mul(a01.x, x0)); t1 = add(t1, mul(a01.y, x0));
+        t0 = add(t0, mul(a23.x, x1)); t1 = add(t1, mul(a23.y, x1));
+    }
+    if (2 * bi + 1 < n) *reinterpret_cast<double2 *>(y + 2 * bi) = make_double2(t0, t1);
+    else y[2 * bi] = t0;
 }
 
 // generic block size (bnr or bnc > 4): one thread per scalar row, same per-row order
@@ -428,7 +455,7 @@ bsr_generic_kernel(int n, int nr, int bnr, int bnc, const int *__restrict__ bptr
     for (int bc = s; bc < e; ++bc) {
         const int bj = __ldg(bidx + bc) * bnc;
         const double *v = val + (size_t)bc * bs + i;
-        for (int j = 0; j < bnc; ++j) t = add(t, mul(__ldg(v + (size_t)j * bnr), __ldg(x + bj + j)));
+        for (int j = 0; j < bnc; ++j) t = add(t, mul(__ldg(v + (size_t)j * bnr), bj + j < n ? __ldg(x + bj + j) : 0.0));
     }
     y[row] = t;
 }
@@ -657,6 +684,11 @@ extern "C" int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bp
     if (n <= 0 || nr <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = -1;
+    if (bnr == 2 && bnc == 2 && (((uintptr_t)d_val | (uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0) {
+        bsr22_kernel<<<(nr + 127) / 128, 128, 0, st>>>(n, nr, d_bptr, d_bidx, d_val, d_x, d_y);
+        LISB_CHECK_LAUNCH();
+        return 0;
+    }
     if (bnc >= 1 && bnc <= 4) {
         switch (bnr) {
         case 1: rc = launch_bsr_c<1>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
