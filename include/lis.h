@@ -531,6 +531,7 @@ LIS_INT lis_matrix_set_dia(LIS_INT nnd, LIS_INT *index, LIS_SCALAR *value, LIS_M
 
 /* ------------------------------------------------------------------ matrix-vector product */
 LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);
+LIS_INT lis_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);
 
 /* ------------------------------------------------------------------ linear solvers */
 LIS_INT lis_solver_create(LIS_SOLVER *solver);
@@ -549,6 +550,8 @@ LIS_INT lis_solver_set_optionC(LIS_SOLVER solver);
 LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver);
 LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver, LIS_PRECON precon);
 LIS_INT lis_solve_setup(LIS_MATRIX A, LIS_SOLVER solver);
+LIS_INT lis_solver_set_matrix(LIS_MATRIX A, LIS_SOLVER solver);
+LIS_INT lis_matrix_set_values(LIS_INT flag, LIS_INT n, LIS_SCALAR value[], LIS_MATRIX A);
 LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma);
 LIS_INT lis_matrix_scale(LIS_MATRIX A, LIS_VECTOR B, LIS_VECTOR D, LIS_INT action);
 

@@ -639,6 +639,15 @@ LIS_INT lis_matrix_set_bsr(LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT *bptr
 }
 
 /* ------------------------------------------------------------------ CSR utilities */
+/* a dense n x n block given row by row, entry by entry through lis_matrix_set_value
+ * (src/matrix/lis_matrix.c:859-875) */
+LIS_INT lis_matrix_set_values(LIS_INT flag, LIS_INT n, LIS_SCALAR value[], LIS_MATRIX A)
+{
+    for (LIS_INT i = 0; i < n; i++)
+        for (LIS_INT j = 0; j < n; j++) lis_matrix_set_value(flag, i, j, value[(size_t)i * n + j], A);
+    return LIS_SUCCESS;
+}
+
 /* -scale: A <- D^-1 A, b <- D^-1 b (LIS_SCALE_JACOBI) or A <- D^-1/2 A D^-1/2, b <- D^-1/2 b
  * (LIS_SCALE_SYMM_DIAG), D = diag(A); the scaling vector stays in Dv (src/matrix/lis_matrix_ops.c:579-712,
  * CSR loops src/matrix/lis_matrix_csr.c:607-693).  Once per solve, on the host arrays the caller sees

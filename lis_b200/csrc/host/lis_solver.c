@@ -497,6 +497,8 @@ LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver)
     return LIS_SUCCESS;
 }
 
+LIS_INT lis_solver_set_matrix(LIS_MATRIX A, LIS_SOLVER solver) { solver->A = A; return LIS_SUCCESS; }
+
 /* run lis_solve up to, but not including, the solver loop: option checks, -storage conversion, work
  * vectors -- what the CR eigensolver needs before it borrows the preconditioner
  * (src/solver/lis_solver.c:408-437) */
