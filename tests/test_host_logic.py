@@ -293,6 +293,75 @@ def test_lis_output_files_identical_to_reference(b200, ref_serial, tmp_path):
         H.assert_bits_equal(rb, bvec, tag); H.assert_bits_equal(rx, bvec, tag)
 
 
+def test_lis_array_matches_reference(built):
+    """lis_array_* (the public dense helpers, src/array/lis_array.c): every function, n = 1..6 and the
+    three `op` modes, bit for bit against the compiled reference -- incl. the written-out small cases"""
+    import ctypes as C
+    ref_path = os.path.join(H.ROOT, "oracle", "_ref", "libref_shim_serial.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ref = C.CDLL(ref_path); our = lis_b200.load_library()
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    rng = np.random.default_rng(12)
+
+    def both(name, argtypes, make_args, outs):
+        res = []
+        args0 = make_args()
+        for lib in (ref, our):
+            fn = getattr(lib, name); fn.argtypes = argtypes; fn.restype = C.c_int
+            args = [a.copy() if isinstance(a, np.ndarray) else a for a in args0]
+            rc = fn(*[a if not isinstance(a, np.ndarray) else a for a in args])
+            res.append((rc, [args[k].copy() for k in outs]))
+        assert res[0][0] == res[1][0], name
+        for a, b in zip(res[0][1], res[1][1]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (name, a, b)
+
+    ci, cd = C.c_int, C.c_double
+    for n in (1, 2, 3, 4, 6):
+        v = lambda k=n: rng.standard_normal(k) * 10.0 ** rng.integers(-3, 3, k)
+        m = lambda k=n: (rng.standard_normal((k, k)) + 3 * np.eye(k)).ravel()
+        for name in ("lis_array_swap", "lis_array_copy"):
+            both(name, [ci, f64p, f64p], lambda: [n, v(), v()], (1, 2))
+        both("lis_array_axpy", [ci, cd, f64p, f64p], lambda: [n, 0.37, v(), v()], (3,))
+        both("lis_array_xpay", [ci, f64p, cd, f64p], lambda: [n, v(), -1.7, v()], (3,))
+        both("lis_array_axpyz", [ci, cd, f64p, f64p, f64p], lambda: [n, 2.5, v(), v(), v()], (4,))
+        both("lis_array_scale", [ci, cd, f64p], lambda: [n, -0.3, v()], (2,))
+        for name in ("lis_array_pmul", "lis_array_pdiv"):
+            both(name, [ci, f64p, f64p, f64p], lambda: [n, v(), v(), v()], (3,))
+        both("lis_array_set_all", [ci, cd, f64p], lambda: [n, 4.25, v()], (2,))
+        for name in ("lis_array_abs", "lis_array_reciprocal", "lis_array_conjugate"):
+            both(name, [ci, f64p], lambda: [n, v()], (1,))
+        both("lis_array_shift", [ci, cd, f64p], lambda: [n, 0.125, v()], (2,))
+        for name in ("lis_array_dot", "lis_array_nhdot"):
+            both(name, [ci, f64p, f64p, f64p], lambda: [n, v(), v(), np.zeros(1)], (3,))
+        for name in ("lis_array_nrm1", "lis_array_nrm2", "lis_array_nrmi", "lis_array_sum"):
+            both(name, [ci, f64p, f64p], lambda: [n, v(), np.zeros(1)], (2,))
+        for op in (0, 1, 2):                       # LIS_INS_VALUE, LIS_ADD_VALUE, LIS_SUB_VALUE
+            for name in ("lis_array_matvec", "lis_array_matvech"):
+                both(name, [ci, f64p, f64p, f64p, ci], lambda: [n, m(), v(), v(), op], (3,))
+            both("lis_array_matvec_ns", [ci, ci, f64p, ci, f64p, f64p, ci], lambda: [n, n, m(n + 1)[:(n + 1) * n], n + 1, v(), v(), op], (5,))
+            both("lis_array_matmat", [ci, f64p, f64p, f64p, ci], lambda: [n, m(), m(), m(), op], (3,))
+            both("lis_array_matmat_ns", [ci, ci, ci, f64p, ci, f64p, ci, f64p, ci, ci],
+                 lambda: [n, n, n, m(), n, m(), n, m(), n, op], (7,))
+        both("lis_array_ge", [ci, f64p], lambda: [n, m()], (1,))
+        both("lis_array_solve", [ci, f64p, f64p, f64p, f64p], lambda: [n, m(), v(), v(), m()], (3, 4))
+        for name in ("lis_array_cgs", "lis_array_mgs"):
+            both(name, [ci, f64p, f64p, f64p], lambda: [n, m(), m(), m()], (1, 2, 3))
+    # QR iteration on a symmetric tridiagonal matrix (what Lanczos hands it)
+    n = 5
+    t = np.zeros((n, n)); t[np.arange(n), np.arange(n)] = [4, 3, 5, 2, 6]; t[np.arange(n - 1), np.arange(1, n)] = 1; t += np.triu(t, 1).T
+    for lib_out in ([], []):
+        pass
+    outs = []
+    for lib in (ref, our):
+        a = t.ravel().copy(); q = np.zeros(n * n); r = np.zeros(n * n); it = C.c_int(0); er = C.c_double(0)
+        lib.lis_array_qr.argtypes = [ci, f64p, f64p, f64p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        assert lib.lis_array_qr(n, a, q, r, C.byref(it), C.byref(er)) == 0
+        outs.append((a, it.value, er.value))
+    assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2] and np.array_equal(outs[0][0].view(np.uint8), outs[1][0].view(np.uint8))
+    assert np.allclose(np.sort(np.diag(outs[1][0].reshape(n, n))), np.linalg.eigvalsh(t))
+
+
 def test_reference_fixture_testmat(b200):
     """test/testmat.mtx of the reference, when its tree is present"""
     path = "/root/reference/test/testmat.mtx"

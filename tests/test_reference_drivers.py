@@ -28,13 +28,25 @@ def need(*names):
 
 
 def test_drivers_were_built_from_unmodified_reference_sources():
-    """22 reference drivers compile and link against lis_b200 (checked where the tree exists)"""
+    """24 reference drivers compile and link against lis_b200 (checked where the tree exists)"""
     if not os.path.isdir("/root/reference/test"):
         pytest.skip("reference tree not present")
     H.ensure_built()
     for n in ("spmvtest1", "spmvtest2", "spmvtest2b", "spmvtest3", "spmvtest3b", "spmvtest4", "spmvtest5", "test1", "test2", "test2b",
-              "test3", "test3b", "test3c", "test4", "test5", "etest1", "etest2", "etest3", "etest4", "etest5", "etest5b", "etest6"):
+              "test3", "test3b", "test3c", "test4", "test5", "etest1", "etest2", "etest3", "etest4", "etest5", "etest5b", "etest6", "etest7", "test6"):
         assert os.path.exists(os.path.join(OURS, n)), n
+
+
+def test_dense_helper_drivers_print_what_the_reference_prints():
+    """test6 (dense Gaussian elimination / matvec through lis_array_*) and etest7 (QR iteration on a
+    dense matrix): host-only drivers, so they run here; transcripts equal to the reference-linked binaries"""
+    need("test6", "etest7")
+    for d in ("test6", "etest7"):
+        if not os.path.exists(os.path.join(REFS, d)):
+            pytest.skip("oracle/_ref drivers not built (reference tree absent)")
+        for args in ((3, 2), (4, 4), (6, 5)):
+            keep = lambda s: [ln for ln in s.splitlines() if "sec" not in ln and "time" not in ln]
+            assert keep(run(os.path.join(OURS, d), *args)) == keep(run(os.path.join(REFS, d), *args)), (d, args)
 
 
 def norms(out):
