@@ -1,0 +1,68 @@
+"""bench.py's control flow, end to end, without a GPU: tests/bench_on_emulator.py fakes torch's CUDA
+surface on the CPU and loads the kernel-emulator build instead of the product library, so the whole
+single-GPU and torchrun (2 ranks, gloo standing in for NCCL) paths execute -- kernel asserts, JSON
+assembly, the overlapped e2e leg, the format extras, the watchdog.  The numbers are meaningless; the
+shape of the line and the absence of Python errors are what is checked."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import harness as H
+
+RUNNER = os.path.join(H.ROOT, "tests", "bench_on_emulator.py")
+EMU_DIR = os.path.join(H.ROOT, "tests", "cudaemu")
+KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+        "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"}
+
+
+def build_emu():
+    r = subprocess.run(["make", "-C", EMU_DIR, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def line_of(r):
+    assert r.returncode == 0, r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines                      # ONE JSON line on stdout
+    return json.loads(lines[0])
+
+
+def test_single_gpu_flow(built):
+    build_emu()
+    env = dict(os.environ, LIS_B200_PIPE_CHUNKS="4")
+    r = subprocess.run([sys.executable, RUNNER, "--grid", "12", "--cpu-grid", "12", "--steps", "3", "--warmup", "3", "--cg-iters", "5"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    d = line_of(r)
+    assert KEYS <= set(d) and "cpu_baseline" in d and "watchdog" not in d
+    assert d["n_gpus"] == 1 and d["metric"] == "spmv_csr_gflops" and d["config"]["workload"].startswith("spmvtest3 12^3")
+    # the overlapped leg ran and passed its bit check (it is adopted only when faster: a coin flip on the emulator)
+    assert "e2e overlapped (lis_b200_matvec_host)" in r.stderr and "overlapped e2e path not used" not in r.stderr, r.stderr[-2000:]
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 * 12 ** 3
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    for k in ("ell", "dia", "jad", "bsr"):
+        assert d["extra"][f"{k}_nrm2_vs_csr_rel"] == 0.0 and f"{k}_convert_device_s" in d["extra"], k
+    assert "ell_convert_host_s" in d["extra"] and d["cpu_baseline"]["kind"] == "reference"
+
+
+def test_watchdog_prints_the_line_without_the_optional_legs(built):
+    build_emu()
+    r = subprocess.run([sys.executable, RUNNER, "--grid", "12", "--cpu-grid", "12", "--steps", "3", "--warmup", "3", "--cg-iters", "5",
+                        "--watchdog", "0.0001"], capture_output=True, text=True, timeout=600)
+    d = line_of(r)
+    assert KEYS <= set(d) and "watchdog" in d and "cpu_baseline" in d
+    assert d["e2e"]["what"].startswith("lis_vector_scatter")
+
+
+def test_two_rank_flow(built):
+    build_emu()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, LIS_B200_PIPE_CHUNKS="4", LIS_B200_OVERLAP="force")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), RUNNER, "--gpus", "2", "--grid", "24", "--steps", "3", "--warmup", "3", "--cg-iters", "5"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    d = line_of(r)
+    assert KEYS <= set(d) and d["n_gpus"] == 2 and d["scaling"] == "weak"
+    assert d["config"]["overlap"].startswith("interior rows on a second stream"), d["config"]["overlap"]
+    assert d["gpu_launches"] == 4 * 3 and d["extra"]["cg_jacobi_iters_per_s"] > 0
