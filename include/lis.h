@@ -608,7 +608,9 @@ LIS_INT lis_b200_commtable_info(LIS_MATRIX A, LIS_INT *out, LIS_INT *import_ptr,
 LIS_INT lis_b200_matvec_host(LIS_MATRIX A, LIS_SCALAR host_x[], LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR host_y[]);
 LIS_INT lis_b200_matvec_host_plan(LIS_MATRIX A, LIS_INT cap, LIS_INT *rows, LIS_INT *need);
 /* row-partitioned CSR products run the rows that read no halo entry on a second stream while the halo
- * exchange is in flight (default on; LIS_B200_OVERLAP=0 or this call turn it off).  Returns the old setting. */
+ * exchange is in flight; so does CG's fused q = A p, <p,q> step (the dot is then the sum of the range
+ * shares).  on = 1 both (default), 2 products only (LIS_B200_OVERLAP=spmv), 0 neither (LIS_B200_OVERLAP=0).
+ * Returns the old setting. */
 LIS_INT lis_b200_set_overlap(LIS_INT on);
 /* the CUDA stream (cudaStream_t) all kernels of this process are enqueued on */
 void *lis_b200_stream(void);

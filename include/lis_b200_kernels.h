@@ -49,6 +49,13 @@ int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, int stages, const 
 int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                              const double *d_val, const double *d_x, double *d_y, double *d_partial,
                              unsigned int *d_counter, double *d_result, void *stream);
+/* ... on a row range (row-partitioned CG: interior rows during the halo exchange, boundary rows behind it):
+ * d_ptr, d_y and d_dotx point at the first row of the range (d_dotx = d_x + first row), d_x at the whole
+ * vector; the range's share of <x,y> lands in *d_result.  Concurrent launches need their own
+ * d_partial / d_counter.                                                                      */
+int lisb200_spmv_csr_tma_dot_rows(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
+                                  const double *d_val, const double *d_x, double *d_y, const double *d_dotx,
+                                  double *d_partial, unsigned int *d_counter, double *d_result, void *stream);
 /* CSR, split order  t = D[i]*x[i]; t += L...; t += U...  src/matvec/lis_matvec_csr.c:64-87 */
 int lisb200_spmv_csr_split(int n, const double *d_diag,
                            const int *d_lptr, const int *d_lidx, const double *d_lval,

@@ -231,13 +231,18 @@ static LIS_INT csr_rows_launch(lisd_matrix *M, int r0, int r1, const double *x, 
  * (column >= n).  For a slab of a stencil grid that is everything but the first and last planes.
  * Those rows do not need the exchange: they run on a second stream while it is in flight (the
  * reference's LIS_MATVEC_SENDRECV, include/lis_matvec.h:31-44, finishes the exchange first). */
-static int g_overlap = -1;             /* -1: take LIS_B200_OVERLAP from the environment on first use */
+static int g_overlap = -1;             /* -1: take LIS_B200_OVERLAP from the environment on first use; 0 off; 1 products and the
+                                        * fused CG step; 2 products only */
 static int overlap_enabled(void)
 {
-    if (g_overlap < 0) { const char *e = getenv("LIS_B200_OVERLAP"); g_overlap = !(e && e[0] == '0'); }
-    return g_overlap;
+    if (g_overlap < 0) {
+        const char *e = getenv("LIS_B200_OVERLAP");
+        g_overlap = (e && e[0] == '0') ? 0 : (e && strcmp(e, "spmv") == 0) ? 2 : 1;
+    }
+    return g_overlap != 0;
 }
-LIS_INT lis_b200_set_overlap(LIS_INT on) { const int old = overlap_enabled(); g_overlap = on ? 1 : 0; return old; }
+static int overlap_dot_enabled(void) { return overlap_enabled() && g_overlap == 1; }
+LIS_INT lis_b200_set_overlap(LIS_INT on) { overlap_enabled(); const int old = g_overlap; g_overlap = on == 2 ? 2 : on ? 1 : 0; return old; }
 
 static void overlap_plan(LIS_MATRIX A, lisd_matrix *M)
 {
@@ -323,6 +328,43 @@ LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     return matvec_launch(A, M, x->value, y->value);
 }
 
+/* the fused SpMV+dot on rows [r0, r1): its share of <x,y> goes to mapped scalar `slot`; `lane` picks
+ * the partial-sum scratch and ticket counter, one per stream that may be running such a launch */
+static LIS_INT csr_rows_dot_launch(lisd_matrix *M, int r0, int r1, const double *x, double *y, double *partial, int lane, int slot, void *st,
+                                   const char *what)
+{
+    const int rc = lisb200_spmv_csr_tma_dot_rows(r1 - r0, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr + r0, M->csr.idx,
+                                                 M->csr.val, x, y + r0, x + r0, partial + (size_t)lane * (size_t)lisb200_reduce_slots(),
+                                                 lisd_counter() + lane, lisd_scalar_dev(slot), st);
+    lisd_mark_busy();
+    return lisd_check(rc, what);
+}
+
+/* row-partitioned CG step q = A p, <p,q>: interior rows (fused with their share of the dot) on the
+ * second stream while the halo exchange is in flight, the rows that read halo entries behind it.
+ * The dot is the sum of the (up to three) range shares in row order: a fixed order, the same on every
+ * run, but not the single tree of the one-launch path -- like any change of the rank count it moves
+ * the last bits of <p,q>, not the result class (tests/test_multi_rank.py checks CG against the oracle). */
+static LIS_INT matvec_dot_overlapped(LIS_MATRIX A, lisd_matrix *M, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy)
+{
+    double vals[3] = {0.0, 0.0, 0.0};
+    void *aux;
+    double *partial = lisd_partial(2 * (size_t)lisb200_reduce_slots());
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    LIS_INT err = lisd_aux_fork(&aux);
+    if (!err) err = lisd_halo_exchange(A, x);
+    /* every rank fills all three slots (an empty range stores 0): the cross-rank sum is slot by slot */
+    if (!err) err = csr_rows_dot_launch(M, 0, M->ov_lo, x->value, y->value, partial, 0, 0, lisd_stream(), "lis_matvec+dot (boundary rows)");
+    if (!err) err = csr_rows_dot_launch(M, M->ov_lo, M->ov_hi, x->value, y->value, partial, 1, 1, aux, "lis_matvec+dot (interior rows)");
+    if (!err) err = csr_rows_dot_launch(M, M->ov_hi, A->n, x->value, y->value, partial, 0, 2, lisd_stream(), "lis_matvec+dot (boundary rows)");
+    { LIS_INT e2 = lisd_aux_join(); if (!err) err = e2; }
+    if (err) return err;
+    err = lisd_reduce_finish(vals, 3, 0);
+    if (err) return err;
+    *dot_xy = (vals[0] + vals[1]) + vals[2];
+    return LIS_SUCCESS;
+}
+
 /* y = A x and <x,y> in one pass where a fused kernel exists (unsplit CSR / CSC mirror) */
 LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy)
 {
@@ -342,7 +384,13 @@ LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *do
     err = lisd_vec_device(x);
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
-    if (A->nprocs > 1 && A->commtable) { err = lisd_halo_exchange(A, x); if (err) return err; }
+    if (A->nprocs > 1 && A->commtable) {
+        if (M->type == LIS_MATRIX_CSR && M->csr.tma_rows && M->ov_built == 0 && overlap_dot_enabled()) overlap_plan(A, M);
+        if (M->type == LIS_MATRIX_CSR && M->csr.tma_rows && M->ov_built == 1 && overlap_dot_enabled())
+            return matvec_dot_overlapped(A, M, x, y, dot_xy);
+        err = lisd_halo_exchange(A, x);
+        if (err) return err;
+    }
     double *partial = lisd_partial(M->csr.tma_rows ? 0 : (size_t)lisb200_spmv_csr_dot_slots(A->n));
     if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
     lisd_mark_busy();

@@ -141,6 +141,7 @@ template <int kRows, int kStages, bool kDot>
 __global__ void __launch_bounds__(kRows + 32, 1152 / (kRows + 32))
 csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const int *__restrict__ idx,
                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+               const double *__restrict__ dotx /* kDot: row r pairs with dotx[r] (x itself, or x + first row of a row range) */,
                double *partial, unsigned int *counter, double *result)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -224,7 +225,7 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
                         if (j + k < e) acc = add(acc, mul(v[k], xv[k]));
                 }
                 y[r] = acc;
-                if (kDot) dsum = add(dsum, mul(__ldg(x + r), acc));
+                if (kDot) dsum = add(dsum, mul(__ldg(dotx + r), acc));
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
@@ -494,7 +495,7 @@ static int sm_count_spmv() {
 
 template <int kRows, int kStages, bool kDot>
 static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
-                            double *partial, unsigned int *counter, double *result, cudaStream_t st)
+                            const double *dotx, double *partial, unsigned int *counter, double *result, cudaStream_t st)
 {
     const size_t smem = kStages * CsrTmaSmem<kRows>::stage_bytes(tile);
     auto kern = csr_tma_kernel<kRows, kStages, kDot>;
@@ -511,21 +512,21 @@ static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, con
     const int nblocks = (n + kRows - 1) / kRows;
     int grid = sm_count_spmv() * per_sm;
     if (grid > nblocks) grid = nblocks;
-    kern<<<grid, kRows + 32, smem, st>>>(n, nblocks, tile, ptr, idx, val, x, y, partial, counter, result);
+    kern<<<grid, kRows + 32, smem, st>>>(n, nblocks, tile, ptr, idx, val, x, y, dotx, partial, counter, result);
     LISB_CHECK_LAUNCH();
     return 0;
 }
 
 template <int kRows, bool kDot>
 static int launch_csr_tma(int n, int tile, int stages, const int *ptr, const int *idx, const double *val, const double *x, double *y,
-                          double *partial, unsigned int *counter, double *result, cudaStream_t st)
+                          const double *dotx, double *partial, unsigned int *counter, double *result, cudaStream_t st)
 {
     switch (stages) {
-    case 3: return launch_csr_tma_s<kRows, 3, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
-    case 4: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
-    case 6: return launch_csr_tma_s<kRows, 6, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
-    case 8: return launch_csr_tma_s<kRows, 8, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
-    case 2: return launch_csr_tma_s<kRows, 2, kDot>(n, tile, ptr, idx, val, x, y, partial, counter, result, st);
+    case 3: return launch_csr_tma_s<kRows, 3, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
+    case 4: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
+    case 6: return launch_csr_tma_s<kRows, 6, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
+    case 8: return launch_csr_tma_s<kRows, 8, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
+    case 2: return launch_csr_tma_s<kRows, 2, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
     default: return (int)cudaErrorInvalidValue;
     }
 }
@@ -541,23 +542,36 @@ extern "C" int lisb200_spmv_csr_tma(int n, int rows_per_block, int tile, int sta
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (rows_per_block) {
-    case 256: return launch_csr_tma<256, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
-    case 128: return launch_csr_tma<128, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
-    case 64:  return launch_csr_tma<64, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, st);
+    case 256: return launch_csr_tma<256, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, nullptr, st);
+    case 128: return launch_csr_tma<128, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, nullptr, st);
+    case 64:  return launch_csr_tma<64, false>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, nullptr, st);
     default:  return (int)cudaErrorInvalidValue;
     }
 }
+
+extern "C" int lisb200_spmv_csr_tma_dot_rows(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
+                                             const double *d_val, const double *d_x, double *d_y, const double *d_dotx,
+                                             double *d_partial, unsigned int *d_counter, double *d_result, void *stream);
 
 extern "C" int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                                         const double *d_val, const double *d_x, double *d_y, double *d_partial,
                                         unsigned int *d_counter, double *d_result, void *stream)
 {
-    if (n <= 0) return 0;
+    return lisb200_spmv_csr_tma_dot_rows(n, rows_per_block, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_x, d_partial, d_counter, d_result, stream);
+}
+
+/* the same on a row range: d_ptr / d_y / d_dotx point at the range's first row (d_dotx = x + first row), d_x at the
+ * whole vector; the range's share of <x,y> goes to *d_result (empty range: 0) */
+extern "C" int lisb200_spmv_csr_tma_dot_rows(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
+                                             const double *d_val, const double *d_x, double *d_y, const double *d_dotx,
+                                             double *d_partial, unsigned int *d_counter, double *d_result, void *stream)
+{
+    if (n <= 0) return (int)cudaMemsetAsync(d_result, 0, sizeof(double), (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     switch (rows_per_block) {
-    case 256: return launch_csr_tma<256, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
-    case 128: return launch_csr_tma<128, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
-    case 64:  return launch_csr_tma<64, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_partial, d_counter, d_result, st);
+    case 256: return launch_csr_tma<256, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_dotx, d_partial, d_counter, d_result, st);
+    case 128: return launch_csr_tma<128, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_dotx, d_partial, d_counter, d_result, st);
+    case 64:  return launch_csr_tma<64, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_dotx, d_partial, d_counter, d_result, st);
     default:  return (int)cudaErrorInvalidValue;
     }
 }

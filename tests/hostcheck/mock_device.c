@@ -66,6 +66,9 @@ int lisb200_spmv_csr_dot(int n, const int *p, const int *i, const double *v, con
 int lisb200_spmv_csr_tma_dot(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y,
                              double *partial, unsigned int *counter, double *result, void *s)
 { (void)r; (void)t; (void)st; return lisb200_spmv_csr_dot(n, p, i, v, x, y, partial, counter, result, s); }
+int lisb200_spmv_csr_tma_dot_rows(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y,
+                                  const double *dotx, double *partial, unsigned int *counter, double *result, void *s)
+{ (void)r; (void)t; (void)st; (void)partial; (void)counter; lisb200_spmv_csr(n, p, i, v, x, y, s); *result = n > 0 ? orc_dot(n, dotx, y, 1) : 0.0; return 0; }
 int lisb200_spmv_ell(int n, int m, int ld, const int *i, const double *v, const double *x, double *y, void *s)
 {
     (void)s;

@@ -62,9 +62,35 @@ def overlap_case(rank, world, shim, lib):
         L.shim_mv_close(h)
     try:
         lib.emu_launch_count.restype = C.c_long; lib.emu_launch_count.argtypes = [C.c_char_p]
-        launches = int(lib.emu_launch_count(b""))
+        count = lambda: int(lib.emu_launch_count(b""))
     except AttributeError:
-        launches = -1
+        count = lambda: -1
+    # CG on the same partition: q = A p with <p,q> fused, interior rows on the second stream during the
+    # exchange, the dot assembled from the range shares.  Same iteration count as the oracle's
+    # one-process CG and as the run without overlap; the overlapped run launches more kernels.
+    os.environ["LIS_B200_CSR_KERNEL"] = "tma"
+    L.shim_mv_solve_b.argtypes = [C.c_int, C.c_char_p, f64p, f64p, i32p, f64p, f64p, C.c_int]
+    bvec = o.spmv("csr", ptr, idx, val, np.ones(gn))
+    ref = o.solve("cg", ptr, idx, val, bvec, precon="jacobi")
+    h = L.shim_mv_open_dist(1, nl, lp, li, lv, 0)
+    assert h >= 0
+    runs = {}
+    for on in (1, 0):
+        lib.lis_b200_set_overlap(on)
+        xl = np.zeros(nl); oi = np.zeros(4, np.int32); od = np.zeros(4); rh = np.zeros(5000)
+        c0 = count()
+        rc = L.shim_mv_solve_b(h, b"-i cg -p jacobi", np.ascontiguousarray(bvec[is_:ie]), xl, oi, od, rh, 5000)
+        assert rc == 0 and oi[1] == 0, (on, rc, oi)
+        assert np.abs(xl - 1.0).max() < 1e-8, on
+        assert int(oi[0]) == ref["iter"], (on, int(oi[0]), ref["iter"])
+        n_it = int(oi[0])
+        assert np.allclose(rh[:n_it + 1], ref["rhistory"][:n_it + 1], rtol=1e-6, atol=0), on
+        runs[on] = (count() - c0, n_it)
+    lib.lis_b200_set_overlap(1)
+    if runs[1][0] >= 0:
+        assert runs[1][0] >= runs[0][0] + runs[1][1], ("overlapped CG did not split its products", runs)
+    L.shim_mv_close(h)
+    launches = count()
     gathered = [None] * world
     dist.all_gather_object(gathered, {"rank": rank, "rows": nl, "launches": launches})
     dist.barrier()

@@ -66,3 +66,6 @@ def test_two_rank_flow(built):
     assert KEYS <= set(d) and d["n_gpus"] == 2 and d["scaling"] == "weak"
     assert d["config"]["overlap"].startswith("interior rows on a second stream"), d["config"]["overlap"]
     assert d["gpu_launches"] == 4 * 3 and d["extra"]["cg_jacobi_iters_per_s"] > 0
+    # CG ran both ways (one fused launch behind the exchange / split around it) and agreed on the residual
+    assert "with the split fused step" in r.stderr and "split fused CG step off" not in r.stderr, r.stderr[-2000:]
+    assert d["extra"]["cg_matvec_dot"]
