@@ -125,6 +125,13 @@ int lisb200_dot2(int n, const double *d_a, const double *d_b,
 int lisb200_cg_update(int n, double alpha, const double *d_p, const double *d_q,
                       double *d_x, double *d_r,
                       double *d_partial, unsigned int *d_counter, double *d_rr, void *stream);
+/* the same plus the Jacobi psolve and <r,z> of the NEXT iteration (src/solver/lis_solver_cg.c:171-177):
+ * z = r*dinv ; d_rr_rho[0] = sum r*r ; d_rr_rho[1] = <r,z>.  Bits equal lisb200_cg_update followed by
+ * lisb200_jacobi_dot.  Returns cudaErrorInvalidValue without launching when the 16-byte alignment of the
+ * pointers is mixed (call the two separately then). */
+int lisb200_cg_update_jacobi(int n, double alpha, const double *d_p, const double *d_q, double *d_x, double *d_r,
+                             const double *d_dinv, double *d_z, double *d_partial, unsigned int *d_counter,
+                             double *d_rr_rho, void *stream);
 /* z = r .* dinv ; rho = <r,z>     src/solver/lis_solver_cg.c:173-177 with Jacobi psolve      */
 int lisb200_jacobi_dot(int n, const double *d_r, const double *d_dinv, double *d_z,
                        double *d_partial, unsigned int *d_counter, double *d_rho, void *stream);

@@ -64,10 +64,19 @@ LIS_INT lis_cg(LIS_SOLVER solver)
     tol = solver->tol;
     CHK(lisd_set_all(0.0, p));
 
+    /* Jacobi: the update that ends iteration k also forms z = M^-1 r and <r,z> for iteration k+1 in the
+     * same pass over r (LIS_B200_CG=split: separate launches, same bits) */
+    const int carry = fused && ptype == LIS_PRECON_TYPE_JACOBI && !(getenv("LIS_B200_CG") && strcmp(getenv("LIS_B200_CG"), "split") == 0);
+    int have_rho = 0;
+    LIS_SCALAR rho_next = 0.0;
+
     for (iter = 1; iter <= maxiter; iter++) {
         /* z = M^-1 r ; rho = <r,z> */
         time = lis_wtime();
-        if (fused && ptype == LIS_PRECON_TYPE_JACOBI) {
+        if (have_rho) {
+            rho = rho_next;
+            have_rho = 0;
+        } else if (fused && ptype == LIS_PRECON_TYPE_JACOBI) {
             CHK(lisd_jacobi_dot(r, solver->precon->D, z, &rho));
             ptime += lis_wtime() - time;
         } else {
@@ -87,7 +96,11 @@ LIS_INT lis_cg(LIS_SOLVER solver)
         }
         alpha = rho / dot_pq;
         /* x += alpha*p ; r -= alpha*q ; nrm2 = ||r|| * bnrm */
-        if (fused) {
+        if (carry) {
+            CHK(lisd_cg_update_jacobi(alpha, p, q, x, r, solver->precon->D, z, &nrm2, &rho_next, &have_rho));
+            if (!have_rho) CHK(lisd_cg_update(alpha, p, q, x, r, &nrm2));
+            nrm2 = nrm2 * solver->bnrm;
+        } else if (fused) {
             CHK(lisd_cg_update(alpha, p, q, x, r, &nrm2));
             nrm2 = nrm2 * solver->bnrm;
         } else {

@@ -10,6 +10,7 @@
  * checks, partition, zero initialisation, duplicate-from-matrix).
  */
 #include <stdio.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -363,6 +364,34 @@ LIS_INT lisd_jacobi_dot(LIS_VECTOR r, LIS_VECTOR dinv, LIS_VECTOR z, LIS_SCALAR 
                                                 lisd_scalar_dev(0), lisd_stream()), "jacobi+dot");
     if (err) return err;
     return lisd_reduce_finish(rho, 1, 0);
+}
+
+/* cg update + the next iteration's Jacobi psolve and <r,z>; *fused_out = 0 (nothing done) when the
+ * pointers' alignment is mixed and the caller has to take the two separate steps */
+LIS_INT lisd_cg_update_jacobi(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_VECTOR x, LIS_VECTOR r, LIS_VECTOR dinv, LIS_VECTOR z,
+                              LIS_REAL *nrm2_r, LIS_SCALAR *rho, int *fused_out)
+{
+    LISD_PREP2(p, q, "cg update");
+    { LIS_INT e_ = lis_vector_check_same(p, x); if (e_) return e_; e_ = lis_vector_check_same(p, r); if (e_) return e_;
+      e_ = lis_vector_check_same(p, dinv); if (e_) return e_; e_ = lis_vector_check_same(p, z); if (e_) return e_;
+      e_ = lisd_vec_device(x); if (e_) return e_; e_ = lisd_vec_device(r); if (e_) return e_;
+      e_ = lisd_vec_device(dinv); if (e_) return e_; e_ = lisd_vec_device(z); if (e_) return e_; }
+    *fused_out = 0;
+    if ((((uintptr_t)p->value | (uintptr_t)q->value | (uintptr_t)x->value | (uintptr_t)r->value | (uintptr_t)dinv->value | (uintptr_t)z->value) & 15) != 0)
+        return LIS_SUCCESS;
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    LIS_INT err = lisd_check(lisb200_cg_update_jacobi(p->n, alpha, p->value, q->value, x->value, r->value, dinv->value, z->value, partial,
+                                                      lisd_counter(), lisd_scalar_dev(0), lisd_stream()), "cg update + jacobi");
+    if (err) return err;
+    double v[2];
+    err = lisd_reduce_finish(v, 2, 0);
+    if (err) return err;
+    *nrm2_r = sqrt(v[0]);
+    *rho = v[1];
+    *fused_out = 1;
+    return LIS_SUCCESS;
 }
 
 LIS_INT lisd_cg_update(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_VECTOR x, LIS_VECTOR r, LIS_REAL *nrm2_r)

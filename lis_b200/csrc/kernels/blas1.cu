@@ -313,6 +313,63 @@ cg_update_kernel(int n, double alpha, const double *__restrict__ p, const double
     grid_finish<false, kRedThreads, 1>(mine, partial, counter, result, red);
 }
 
+// cg_update_kernel and the jacobi_dot_kernel of the NEXT iteration in one pass over r:
+//   x += alpha*p ; r += (-alpha)*q ; z = r*dinv ; result[0] = sum r*r ; result[1] = <r,z>
+// (src/solver/lis_solver_cg.c:205-211, then :171-177 of the following iteration; lis_psolve_jacobi is
+// a multiply, src/precon/lis_precon_jacobi.c:88-147).  Separately the two launches move 48 + 24 B per
+// element, here 64, and the host waits once instead of twice.  Element -> thread map, accumulator
+// pairs and trees are those of the two kernels: x, r, z and both scalars carry the same bits.
+__global__ void __launch_bounds__(kRedThreads)
+cg_update_jacobi_kernel(int n, double alpha, const double *__restrict__ p, const double *__restrict__ q,
+                        double *__restrict__ x, double *__restrict__ r, const double *__restrict__ dinv,
+                        double *__restrict__ z, bool vec, double *partial, unsigned int *counter, double *result)
+{
+    __shared__ double red[32];
+    const int stride = gridDim.x * blockDim.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double na = -alpha;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    if (vec) {
+        const int n2 = n >> 1;
+#pragma unroll 2
+        for (int i = t; i < n2; i += stride) {
+            const double2 pv = reinterpret_cast<const double2 *>(p)[i];
+            const double2 qv = reinterpret_cast<const double2 *>(q)[i];
+            const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+            double2 xv = reinterpret_cast<double2 *>(x)[i];
+            double2 rv = reinterpret_cast<double2 *>(r)[i];
+            xv.x = add(xv.x, mul(alpha, pv.x)); xv.y = add(xv.y, mul(alpha, pv.y));
+            rv.x = add(rv.x, mul(na, qv.x));    rv.y = add(rv.y, mul(na, qv.y));
+            double2 zv; zv.x = mul(rv.x, dv.x); zv.y = mul(rv.y, dv.y);
+            reinterpret_cast<double2 *>(x)[i] = xv;
+            reinterpret_cast<double2 *>(r)[i] = rv;
+            reinterpret_cast<double2 *>(z)[i] = zv;
+            a0 = add(a0, mul(rv.x, rv.x)); a1 = add(a1, mul(rv.y, rv.y));
+            b0 = add(b0, mul(rv.x, zv.x)); b1 = add(b1, mul(rv.y, zv.y));
+        }
+        if (t == 0 && (n & 1)) {
+            const int i = n - 1;
+            x[i] = add(x[i], mul(alpha, p[i]));
+            const double rv = add(r[i], mul(na, q[i]));
+            const double zv = mul(rv, dinv[i]);
+            r[i] = rv; z[i] = zv;
+            a0 = add(a0, mul(rv, rv)); b0 = add(b0, mul(rv, zv));
+        }
+    } else {
+        for (int i = t; i < n; i += stride) {
+            x[i] = add(x[i], mul(alpha, p[i]));
+            const double rv = add(r[i], mul(na, q[i]));
+            const double zv = mul(rv, dinv[i]);
+            r[i] = rv; z[i] = zv;
+            a0 = add(a0, mul(rv, rv)); b0 = add(b0, mul(rv, zv));
+        }
+    }
+    double mine[2];
+    mine[0] = block_reduce<false, kRedThreads>(add(a0, a1), red);
+    mine[1] = block_reduce<false, kRedThreads>(add(b0, b1), red);
+    grid_finish<false, kRedThreads, 2>(mine, partial, counter, result, red);
+}
+
 // One link of GMRES' modified Gram-Schmidt chain (src/solver/lis_solver_gmres.c:225-236) in one pass:
 //   w += (scale * *alpha) * v        alpha = the previous link's <w,v>, still on the device
 //   kNorm ? sum w*w : <w,u>          the next link's coefficient / the norm that ends the chain
@@ -550,6 +607,22 @@ extern "C" int lisb200_cg_update(int n, double alpha, const double *p, const dou
     if (n <= 0) return (int)cudaMemsetAsync(rr, 0, sizeof(double), st);
     const bool vec = aligned16(p) && aligned16(q) && aligned16(x) && aligned16(r);
     cg_update_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, alpha, p, q, x, r, vec, partial, counter, rr);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+/* returns cudaErrorInvalidValue (nothing launched) when the pointers' 16-byte alignment is mixed: the two
+ * separate kernels would then pick different accumulator layouts and the bits would differ */
+extern "C" int lisb200_cg_update_jacobi(int n, double alpha, const double *p, const double *q, double *x, double *r,
+                                        const double *dinv, double *z, double *partial, unsigned int *counter,
+                                        double *rr_rho, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return (int)cudaMemsetAsync(rr_rho, 0, 2 * sizeof(double), st);
+    const bool v1 = aligned16(p) && aligned16(q) && aligned16(x) && aligned16(r);      /* cg_update_kernel's choice */
+    const bool v2 = aligned16(r) && aligned16(dinv) && aligned16(z);                   /* jacobi_dot_kernel's */
+    if (v1 != v2) return (int)cudaErrorInvalidValue;
+    cg_update_jacobi_kernel<<<red_grid(n), kRedThreads, 0, st>>>(n, alpha, p, q, x, r, dinv, z, v1, partial, counter, rr_rho);
     LISB_CHECK_LAUNCH();
     return 0;
 }

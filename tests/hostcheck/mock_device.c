@@ -143,6 +143,14 @@ int lisb200_dot2(int n, const double *a, const double *b, double *partial, unsig
 int lisb200_cg_update(int n, double alpha, const double *p, const double *q, double *x, double *r,
                       double *partial, unsigned int *counter, double *rr, void *s)
 { (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); *rr = orc_dot(n, r, r, 1); return 0; }
+int lisb200_cg_update_jacobi(int n, double alpha, const double *p, const double *q, double *x, double *r, const double *dinv, double *z,
+                             double *partial, unsigned int *counter, double *rr_rho, void *s)
+{
+    (void)partial; (void)counter; (void)s;
+    orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); rr_rho[0] = orc_dot(n, r, r, 1);
+    orc_pmul(n, r, dinv, z); rr_rho[1] = orc_dot(n, r, z, 1);
+    return 0;
+}
 int lisb200_jacobi_dot(int n, const double *r, const double *dinv, double *z, double *partial, unsigned int *counter, double *rho, void *s)
 { (void)partial; (void)counter; (void)s; orc_pmul(n, r, dinv, z); *rho = orc_dot(n, r, z, 1); return 0; }
 int lisb200_mgs_step(int norm, int n, const double *da, double sc, const double *v, double *w, const double *u,

@@ -34,6 +34,7 @@ test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
 test_scaling_and_additive_schwarz_follow_the_reference = G2.test_scaling_and_additive_schwarz_follow_the_reference
 test_bicgstab_fused_updates_same_bits = G2.test_bicgstab_fused_updates_same_bits
+test_cg_carried_jacobi_step_same_bits = G2.test_cg_carried_jacobi_step_same_bits
 test_gram_schmidt_fused_chain_same_bits = G2.test_gram_schmidt_fused_chain_same_bits
 test_device_conversion_same_arrays_as_host = G2.test_device_conversion_same_arrays_as_host
 test_device_conversion_falls_back_to_host_builder = G2.test_device_conversion_falls_back_to_host_builder
@@ -79,6 +80,23 @@ def test_persistent_grids_two_sms(b200, oracle, two_sms, monkeypatch):
         b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
         r = b200.solve(ptr, idx, val, b, opts)
         assert r["status"] == 0 and abs(r["x"] - 1.0).max() < 1e-8
+
+
+def test_cg_launch_pattern(b200, oracle):
+    """CG + Jacobi launches per iteration: xpay, fused SpMV+dot, update carrying the next Jacobi step --
+    jacobi_dot_kernel only once, before the first iteration"""
+    import ctypes as C
+    import numpy as np
+    lib = C.CDLL(os.path.join(EMU_DIR, "_build", "liblis_emu.so"))
+    lib.emu_launch_count.restype = C.c_long; lib.emu_launch_count.argtypes = [C.c_char_p]
+    names = (b"cg_update_jacobi_kernel", b"jacobi_dot_kernel", b"cg_update_kernel", b"csr_tma_kernel", b"")
+    ptr, idx, val = H.poisson3d_7pt(12, 11, 10)
+    b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+    before = {k: lib.emu_launch_count(k) for k in names}
+    r = b200.solve(ptr, idx, val, b, "-i cg -p jacobi")
+    d = {k: lib.emu_launch_count(k) - before[k] for k in names}
+    assert r["status"] == 0
+    assert d[b"cg_update_jacobi_kernel"] == r["iter"] and d[b"jacobi_dot_kernel"] == 1 and d[b"cg_update_kernel"] == 0, (d, r["iter"])
 
 
 # ---- the emulator must notice what it exists to notice

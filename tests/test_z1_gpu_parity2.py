@@ -195,6 +195,28 @@ def test_bicgstab_fused_updates_same_bits(b200, oracle, monkeypatch, opts):
             H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
 
 
+@pytest.mark.parametrize("opts", ["-i cg -p jacobi", "-i cg -p jacobi -maxiter 7", "-i cg -p jacobi -initx_zeros false"])
+def test_cg_carried_jacobi_step_same_bits(b200, oracle, monkeypatch, opts):
+    """CG + Jacobi with the update that ends an iteration also forming z = M^-1 r and <r,z> of the next one
+    (one launch, one host wait less per iteration) and with the two as separate launches (LIS_B200_CG=split):
+    same iteration count, residual history and solution, bit for bit.  (LIS_B200_FUSE=0 is not in this list:
+    it also replaces the fused SpMV+dot, whose <p,q> is summed per row block -- envelope parity, not bits.)"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(12, 11, 10)), ("odd", H.poisson1d(333)), ("big", H.poisson3d_7pt(40, 30, 20))):
+        b = oracle.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        runs = {}
+        for mode, env in (("carried", {}), ("split", {"LIS_B200_CG": "split"})):
+            for key in ("LIS_B200_CG", "LIS_B200_FUSE"):
+                monkeypatch.delenv(key, raising=False)
+            for key, v in env.items():
+                monkeypatch.setenv(key, v)
+            runs[mode] = b200.solve(ptr, idx, val, b, opts)
+        assert runs["carried"]["iter"] > 5
+        for mode in ("split",):
+            assert runs[mode]["iter"] == runs["carried"]["iter"] and runs[mode]["status"] == runs["carried"]["status"], (name, opts, mode)
+            H.assert_bits_equal(runs[mode]["rhistory"], runs["carried"]["rhistory"], f"{name} {opts} rhistory carried vs {mode}")
+            H.assert_bits_equal(runs[mode]["x"], runs["carried"]["x"], f"{name} {opts} x carried vs {mode}")
+
+
 @pytest.mark.parametrize("opts", ["-i cg -scale jacobi", "-i bicgstab -scale symm_diag -p jacobi", "-i sor -p jacobi -omega 1.5 -maxiter 400",
                                   "-i cg -p ssor -adds true"])
 def test_scaling_and_additive_schwarz_follow_the_reference(b200, ref_serial, opts):
