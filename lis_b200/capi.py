@@ -11,7 +11,7 @@ REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_DIR = os.path.join(REPO_ROOT, "lis_b200", "_lib")
 
 # LIS_MATRIX_* storage-format codes (include/lis.h)
-FMT = {"csr": 1, "csc": 2, "dia": 4, "ell": 5, "jad": 6, "bsr": 7}
+FMT = {"csr": 1, "csc": 2, "msr": 3, "dia": 4, "ell": 5, "jad": 6, "bsr": 7, "bsc": 8, "vbr": 9, "coo": 10, "dns": 11}
 
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -190,9 +190,9 @@ class Shim:
 
     def _grab_handle(self, h, fmt):
         n_unused = 0
-        dims = np.zeros(9, np.int32)
+        dims = np.zeros(11, np.int32)
         self.lib.shim_convert_dims(h, dims)
-        d = dict(zip(["n", "nnz", "maxnzr", "nnd", "nr", "bnr", "bnc", "bnnz", "type"], map(int, dims)))
+        d = dict(zip(["n", "nnz", "maxnzr", "nnd", "nr", "bnr", "bnc", "bnnz", "type", "nc", "ndz"], map(int, dims)))
         n = d["n"]
 
         def grab(which, count, dtype):
@@ -224,6 +224,26 @@ class Shim:
             out["bptr"] = grab(4, d["nr"] + 1, np.int32)
             out["bindex"] = grab(5, d["bnnz"], np.int32)
             out["value"] = grab(2, d["bnnz"] * d["bnr"] * d["bnc"], np.float64)
+        elif fmt == "msr":
+            out["index"] = grab(1, d["nnz"] + d["ndz"] + 1, np.int32)
+            out["value"] = grab(2, d["nnz"] + d["ndz"] + 1, np.float64)
+        elif fmt == "coo":
+            out["row"] = grab(3, d["nnz"], np.int32)
+            out["col"] = grab(6, d["nnz"], np.int32)
+            out["value"] = grab(2, d["nnz"], np.float64)
+        elif fmt == "bsc":
+            out["bptr"] = grab(4, d["nc"] + 1, np.int32)
+            out["bindex"] = grab(5, d["bnnz"], np.int32)
+            out["value"] = grab(2, d["bnnz"] * d["bnr"] * d["bnc"], np.float64)
+        elif fmt == "vbr":
+            out["row"] = grab(3, d["nr"] + 1, np.int32)
+            out["col"] = grab(6, d["nc"] + 1, np.int32)
+            out["ptr"] = grab(0, d["bnnz"] + 1, np.int32)
+            out["bptr"] = grab(4, d["nr"] + 1, np.int32)
+            out["bindex"] = grab(5, d["bnnz"], np.int32)
+            out["value"] = grab(2, d["nnz"], np.float64)
+        elif fmt == "dns":
+            out["value"] = grab(2, n * n, np.float64)
         self.lib.shim_convert_close(h)
         return out
 

@@ -390,9 +390,13 @@ static LIS_INT to_csr(LIS_MATRIX Ain, LIS_MATRIX Aout)
     case LIS_MATRIX_DIA: return dia2csr(Ain, Aout);
     case LIS_MATRIX_JAD: return jad2csr(Ain, Aout);
     case LIS_MATRIX_BSR: return bsr2csr(Ain, Aout);
-    default:
-        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "conversion from storage format %D is not part of the B200 hot path\n", Ain->matrix_type);
+    default: {
+        int handled = 0;                                   /* MSR, COO, BSC, VBR, DNS: lis_formats_ext.c */
+        LIS_INT err = lis_host_ext_to_csr(Ain, Aout, &handled);
+        if (handled) return err;
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "conversion from storage format %D is not available\n", Ain->matrix_type);
         return LIS_ERR_NOT_IMPLEMENTED;
+    }
     }
 }
 
@@ -412,9 +416,13 @@ static LIS_INT from_csr(LIS_MATRIX Acsr, LIS_MATRIX Aout)
     case LIS_MATRIX_DIA: return csr2dia(Acsr, Aout);
     case LIS_MATRIX_JAD: return csr2jad(Acsr, Aout);
     case LIS_MATRIX_BSR: return csr2bsr(Acsr, Aout);
-    default:
-        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "conversion to storage format %D is not part of the B200 hot path\n", Aout->matrix_type);
+    default: {
+        int handled = 0;
+        LIS_INT err = lis_host_ext_from_csr(Acsr, Aout, &handled);
+        if (handled) return err;
+        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "conversion to storage format %D is not available\n", Aout->matrix_type);
         return LIS_ERR_NOT_IMPLEMENTED;
+    }
     }
 }
 
@@ -431,7 +439,7 @@ LIS_INT lis_matrix_copy(LIS_MATRIX Ain, LIS_MATRIX Aout)
     err = to_csr(Ain, T);
     if (err) { lis_matrix_destroy(T); return err; }
     Aout->matrix_type = type;
-    if (type == LIS_MATRIX_BSR) { Aout->conv_bnr = Ain->bnr; Aout->conv_bnc = Ain->bnc; }
+    if (type == LIS_MATRIX_BSR || type == LIS_MATRIX_BSC) { Aout->conv_bnr = Ain->bnr; Aout->conv_bnc = Ain->bnc; }
     err = from_csr(T, Aout);
     lis_matrix_destroy(T);
     return err;

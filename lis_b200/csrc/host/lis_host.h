@@ -19,6 +19,12 @@ void lis_host_header_copy(const void *src, void *dst);
 LIS_INT lis_host_csr_from(LIS_MATRIX A, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value, LIS_INT *owned);
 
 LIS_INT lis_host_matrix_check_input(LIS_MATRIX A);
+LIS_INT lis_host_matrix_check_set(LIS_MATRIX A);
+/* MSR / COO / BSC / VBR / DNS (lis_formats_ext.c) */
+LIS_INT lis_host_ext_from_csr(LIS_MATRIX Acsr, LIS_MATRIX Aout, int *handled);
+LIS_INT lis_host_ext_to_csr(LIS_MATRIX Ain, LIS_MATRIX Aout, int *handled);
+LIS_INT lis_host_ext_get_diagonal(LIS_MATRIX A, LIS_SCALAR *d, int *handled);
+LIS_INT lis_host_ordered_rows(LIS_MATRIX A, int keep_zeros, LIS_INT *nnz, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);
 void    lis_host_matrix_adopt(LIS_MATRIX dst, LIS_MATRIX src);
 LIS_INT lis_host_diag_create(LIS_MATRIX A, LIS_MATRIX_DIAG *Dout);
 LIS_INT lis_host_transpose(LIS_INT n, LIS_INT ncols, const LIS_INT *ptr, const LIS_INT *index, const LIS_SCALAR *value,

@@ -80,6 +80,7 @@ static LIS_INT matrix_check(LIS_MATRIX A, int level)
 }
 
 LIS_INT lis_host_matrix_check_input(LIS_MATRIX A) { return matrix_check(A, CHECK_ALL); }
+LIS_INT lis_host_matrix_check_set(LIS_MATRIX A) { return matrix_check(A, CHECK_SET); }
 
 /* ------------------------------------------------------------------ lifetime */
 LIS_INT lis_matrix_create(LIS_Comm comm, LIS_MATRIX *Amat)
@@ -915,9 +916,13 @@ LIS_INT lis_matrix_get_diagonal(LIS_MATRIX A, LIS_VECTOR d)
             }
         break;
     }
-    default:
+    default: {
+        int handled = 0;                                   /* MSR, COO, BSC, VBR, DNS */
+        LIS_INT err = lis_host_ext_get_diagonal(A, v, &handled);
+        if (handled) return err;
         LIS_SETERR_IMP;
         return LIS_ERR_NOT_IMPLEMENTED;
+    }
     }
     return LIS_SUCCESS;
 }

@@ -180,8 +180,31 @@ LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out)
             if (!err) err = up((void **)&M->val, A->value, cnt * sizeof(double), 16);
             break;
         }
+        case LIS_MATRIX_MSR: {
+            /* t = value[i]*x[i]; t += off-diagonals (src/matvec/lis_matvec_msr.c:91-102) is the split-order
+             * product with D = value[0..n), L = the off-diagonal rows, U = nothing */
+            LIS_INT *rp = (LIS_INT *)malloc(((size_t)n + 1) * sizeof(LIS_INT));
+            LIS_INT *zp = (LIS_INT *)calloc((size_t)n + 1, sizeof(LIS_INT));
+            LIS_INT zi = 0; LIS_SCALAR zv = 0.0;
+            if (!rp || !zp) { free(rp); free(zp); err = LIS_OUT_OF_MEMORY; LIS_SETERR_MEM(n); break; }
+            for (int i = 0; i <= n; i++) rp[i] = A->index[i] - (n + 1);
+            err = csr_upload(&M->L, n, rp, A->index + n + 1, A->value + n + 1);
+            if (!err) err = csr_upload(&M->U, n, zp, &zi, &zv);
+            if (!err) err = up((void **)&M->diag, A->value, (size_t)n * sizeof(double), 16);
+            free(rp); free(zp);
+            break;
+        }
+        case LIS_MATRIX_COO: case LIS_MATRIX_BSC: case LIS_MATRIX_VBR: case LIS_MATRIX_DNS: {
+            /* rows rebuilt in the order the reference's serial product adds into y[i] (explicit zeros of
+             * the dense blocks included), run through the CSR kernels: host/lis_formats_ext.c */
+            LIS_INT nnz, *tp, *ti;
+            LIS_SCALAR *tv;
+            err = lis_host_ordered_rows(A, 1, &nnz, &tp, &ti, &tv);
+            if (!err) { err = csr_upload(&M->csr, n, tp, ti, tv); lis_free2(3, tp, ti, tv); }
+            break;
+        }
         default:
-            LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "storage format %D has no B200 kernel (CSR, CSC, ELL, DIA, JAD, BSR do)\n", A->matrix_type);
+            LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "storage format %D has no B200 kernel\n", A->matrix_type);
             err = LIS_ERR_NOT_IMPLEMENTED;
         }
     }
@@ -197,11 +220,12 @@ static LIS_INT matvec_launch(LIS_MATRIX A, lisd_matrix *M, const double *x, doub
     void *st = lisd_stream();
     const int n = A->n;
     int rc;
-    if (M->splited)
+    if (M->splited || M->type == LIS_MATRIX_MSR)
         rc = lisb200_spmv_csr_split(n, M->diag, M->L.ptr, M->L.idx, M->L.val, M->U.ptr, M->U.idx, M->U.val, x, y, st);
     else switch (M->type) {
     case LIS_MATRIX_CSR:
     case LIS_MATRIX_CSC:
+    case LIS_MATRIX_COO: case LIS_MATRIX_BSC: case LIS_MATRIX_VBR: case LIS_MATRIX_DNS:      /* ordered-row mirrors */
         if (M->csr.tma_rows) rc = lisb200_spmv_csr_tma(n, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
         else rc = lisb200_spmv_csr(n, M->csr.ptr, M->csr.idx, M->csr.val, x, y, st);
         break;
@@ -373,7 +397,8 @@ LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *do
     if (err) return err;
     err = lisd_matrix_get(A, &M);
     if (err) return err;
-    const int fusable = !M->splited && (M->type == LIS_MATRIX_CSR || M->type == LIS_MATRIX_CSC);
+    const int fusable = !M->splited && (M->type == LIS_MATRIX_CSR || M->type == LIS_MATRIX_CSC || M->type == LIS_MATRIX_COO ||
+                                        M->type == LIS_MATRIX_BSC || M->type == LIS_MATRIX_VBR || M->type == LIS_MATRIX_DNS);
     if (!fusable) {
         err = lisd_matvec(A, x, y);
         if (err) return err;
@@ -641,3 +666,8 @@ void lis_matvec_ell(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A
 void lis_matvec_dia(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_DIA, x, y); }
 void lis_matvec_jad(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_JAD, x, y); }
 void lis_matvec_bsr(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_BSR, x, y); }
+void lis_matvec_msr(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_MSR, x, y); }
+void lis_matvec_coo(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_COO, x, y); }
+void lis_matvec_bsc(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_BSC, x, y); }
+void lis_matvec_vbr(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_VBR, x, y); }
+void lis_matvec_dns(LIS_MATRIX A, LIS_SCALAR x[], LIS_SCALAR y[]) { raw_matvec(A, LIS_MATRIX_DNS, x, y); }

@@ -132,7 +132,7 @@ static LIS_INT convert_to(LIS_MATRIX A0, int fmt, int bnr, int bnc, LIS_MATRIX *
     LIS_MATRIX A;
     LIS_INT err = lis_matrix_duplicate(A0, &A); if (err) return err;
     err = lis_matrix_set_type(A, fmt); if (err) return err;
-    if (fmt == LIS_MATRIX_BSR && bnr > 0) { err = lis_matrix_set_blocksize(A, bnr, bnc, NULL, NULL); if (err) return err; }
+    if ((fmt == LIS_MATRIX_BSR || fmt == LIS_MATRIX_BSC) && bnr > 0) { err = lis_matrix_set_blocksize(A, bnr, bnc, NULL, NULL); if (err) return err; }
     err = lis_matrix_convert(A0, A); if (err) return err;
     *out = A;
     return LIS_SUCCESS;
@@ -237,6 +237,21 @@ EXPORT int shim_convert_open(int fmt, int n, const int *ptr, const int *idx, con
     return h;
 }
 
+/* CSR -> fmt -> CSR; the handle holds the final CSR matrix */
+EXPORT int shim_roundtrip_open(int fmt, int n, const int *ptr, const int *idx, const double *val, int bnr, int bnc)
+{
+    int h;
+    LIS_MATRIX A0, A1;
+    for (h = 0; h < 16 && g_conv[h]; h++) ;
+    if (h == 16) return -1;
+    if (make_csr(n, ptr, idx, val, 0, &A0)) return -2;
+    if (convert_to(A0, fmt, bnr, bnc, &A1)) return -3;
+    if (convert_to(A1, LIS_MATRIX_CSR, bnr, bnc, &g_conv[h])) return -4;
+    lis_matrix_destroy(A1);
+    g_conv0[h] = A0;
+    return h;
+}
+
 /* lis_input (Matrix Market) into a handle; b/x presence flags returned in has[0..1] and the
  * vectors copied to bx (2*n doubles) when present */
 EXPORT int shim_input_open(const char *path, int fmt, int *has, double *bx, int bx_cap)
@@ -293,16 +308,17 @@ EXPORT int shim_parse_options(const char *text, int *o, double *d)
     return (int)err;
 }
 
-/* dims: n, nnz, maxnzr, nnd, nr, bnr, bnc, bnnz, matrix_type */
+/* dims: n, nnz, maxnzr, nnd, nr, bnr, bnc, bnnz, matrix_type, nc, ndz */
 EXPORT int shim_convert_dims(int h, int *dims)
 {
     LIS_MATRIX A = g_conv[h];
     dims[0] = A->n; dims[1] = A->nnz; dims[2] = A->maxnzr; dims[3] = A->nnd; dims[4] = A->nr;
     dims[5] = A->bnr; dims[6] = A->bnc; dims[7] = A->bnnz; dims[8] = A->matrix_type;
+    dims[9] = A->nc; dims[10] = A->ndz;
     return 0;
 }
 
-/* which: 0 ptr, 1 index, 2 value, 3 row(perm), 4 bptr, 5 bindex; count elements copied */
+/* which: 0 ptr, 1 index, 2 value, 3 row(perm), 4 bptr, 5 bindex, 6 col; count elements copied */
 EXPORT int shim_convert_copy(int h, int which, void *dst, int count)
 {
     LIS_MATRIX A = g_conv[h];
@@ -315,6 +331,7 @@ EXPORT int shim_convert_copy(int h, int which, void *dst, int count)
     case 3: src = A->row; break;
     case 4: src = A->bptr; break;
     case 5: src = A->bindex; break;
+    case 6: src = A->col; break;
     default: return -1;
     }
     if (src == NULL) return -2;

@@ -35,6 +35,7 @@ test_spmv_long_rows = G.test_spmv_long_rows
 test_scaling_and_additive_schwarz_follow_the_reference = G2.test_scaling_and_additive_schwarz_follow_the_reference
 test_bicgstab_fused_updates_same_bits = G2.test_bicgstab_fused_updates_same_bits
 test_cg_carried_jacobi_step_same_bits = G2.test_cg_carried_jacobi_step_same_bits
+test_other_formats_spmv_bits = G2.test_other_formats_spmv_bits
 test_gram_schmidt_fused_chain_same_bits = G2.test_gram_schmidt_fused_chain_same_bits
 test_device_conversion_same_arrays_as_host = G2.test_device_conversion_same_arrays_as_host
 test_device_conversion_falls_back_to_host_builder = G2.test_device_conversion_falls_back_to_host_builder
@@ -164,6 +165,11 @@ def emu_drivers(b200, monkeypatch):
                                                   ("spmvtest3b", (9, 8, 7, 2), None)])
 def test_spmvtest_drivers_emulated(emu_drivers, driver, args, analytic):
     D.test_spmvtest_drivers(driver, args, analytic)
+
+
+@pytest.mark.parametrize("driver,args", [("spmvtest1", (3000, 2)), ("spmvtest3", (9, 8, 7, 2))])
+def test_spmvtest_drivers_walk_all_formats_emulated(emu_drivers, driver, args):
+    D.test_spmvtest_drivers_walk_all_formats(driver, args)
 
 
 @pytest.mark.parametrize("driver", ["spmvtest4", "spmvtest5"])

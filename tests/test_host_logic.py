@@ -127,6 +127,59 @@ def test_conversion_layouts_match_reference(b200, ref_serial, fmt):
             assert list(lens[got["row"]]) == sorted(lens, reverse=True)
 
 
+@pytest.mark.parametrize("fmt", ["msr", "coo", "bsc", "vbr", "dns"])
+def test_other_format_layouts_match_reference(b200, ref_serial, fmt):
+    """the five formats outside the named path (host/lis_formats_ext.c): same arrays as the reference's
+    serial builders, byte for byte (BSC goes CSR -> CSC -> BSC there; VBR derives its own partition)"""
+    for name, mk in MATS.items():
+        ptr, idx, val = mk()
+        if fmt == "dns" and len(ptr) - 1 > 1500:
+            continue
+        got = b200.convert(fmt, ptr, idx, val, bnr=2, bnc=2)
+        ref = ref_serial.convert(fmt, ptr, idx, val, bnr=2, bnc=2)
+        for key in ("nnz", "ndz", "bnnz", "nr", "nc") + (("bnr", "bnc") if fmt == "bsc" else ()):
+            assert got[key] == ref[key], f"{fmt}/{name}/{key}: {got[key]} vs {ref[key]}"
+        for key in ("row", "col", "ptr", "bptr", "bindex", "index", "value"):
+            if key not in ref:
+                continue
+            a, b = np.asarray(got[key]).copy(), np.asarray(ref[key]).copy()
+            if fmt == "msr":
+                n = got["n"]
+                a[n] = b[n] = 0                      # value[n] is never written by the reference (malloc'ed), index[n] compared through nnz
+                if key == "value" and got["ndz"]:
+                    continue                          # ... nor the diagonal slot of a row that stores none
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"{fmt}/{name}/{key}"
+
+
+def test_other_formats_convert_back_to_csr(b200, ref_serial):
+    """<fmt> -> CSR: explicit zeros of the dense blocks dropped, MSR diagonal first; same arrays as the
+    reference except COO, whose rows keep the order of k (the reference's unstable quicksort does not)"""
+    import ctypes as C
+    for name, mk in MATS.items():
+        ptr, idx, val = mk()
+        n = len(ptr) - 1
+        x = H.rand_vec(n, 12, "wide")
+        for fmt in ("msr", "coo", "bsc", "vbr") + (("dns",) if n <= 1500 else ()):
+            if fmt == "msr" and name == "random_empty":
+                continue                  # rows without a diagonal entry: the reference's MSR round trip corrupts its heap (glibc abort)
+            for shim in (b200, ref_serial):
+                L = shim.lib
+                L.shim_roundtrip_open.argtypes = [C.c_int, C.c_int, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32),
+                                                  np.ctypeslib.ndpointer(np.float64), C.c_int, C.c_int]
+            hs = [s.lib.shim_roundtrip_open(lis_b200.FMT[fmt], n, ptr, idx, val, 2, 2) for s in (b200, ref_serial)]
+            assert min(hs) >= 0, (fmt, name, hs)
+            got, ref = b200._grab_handle(hs[0], "csr"), ref_serial._grab_handle(hs[1], "csr")
+            assert np.array_equal(got["ptr"], ref["ptr"]), f"{fmt}/{name}"
+            if fmt == "coo":
+                for i in range(n):
+                    a = sorted(zip(got["index"][got["ptr"][i]:got["ptr"][i + 1]], got["value"][got["ptr"][i]:got["ptr"][i + 1]]))
+                    b = sorted(zip(ref["index"][ref["ptr"][i]:ref["ptr"][i + 1]], ref["value"][ref["ptr"][i]:ref["ptr"][i + 1]]))
+                    assert a == b, f"coo/{name}/row {i}"
+                assert np.array_equal(got["index"], idx) and np.array_equal(got["value"], val)        # k order kept
+            else:
+                assert np.array_equal(got["index"], ref["index"]) and np.array_equal(got["value"].view(np.uint8), ref["value"].view(np.uint8)), f"{fmt}/{name}"
+
+
 def test_set_value_assembly_matches_reference(b200, ref_serial):
     rng = np.random.default_rng(5)
     n = 60

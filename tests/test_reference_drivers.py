@@ -75,6 +75,21 @@ def test_spmvtest_drivers(driver, args, analytic):
         assert abs(got[7] - np.sqrt(6 * (N - 2) ** 2 + 48 * (N - 2) + 72)) < 1e-3
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("driver,args", [("spmvtest1", (30000, 5)), ("spmvtest2", (40, 30, 5)), ("spmvtest3", (12, 11, 10, 5))])
+def test_spmvtest_drivers_walk_all_formats(driver, args):
+    """without a format argument the drivers convert to and multiply in formats 1..10 (CSR, CSC, MSR, DIA,
+    ELL, JAD, BSR, BSC, VBR, COO; test/spmvtest1.c:188-204): every one answers, with the reference's norm"""
+    need(driver)
+    got = norms(run(os.path.join(OURS, driver), *args))
+    assert sorted(got) == list(range(1, 11)), got
+    if driver == "spmvtest1":
+        assert all(f"{v:e}" == "1.414214e+00" for v in got.values()), got
+    if os.path.exists(os.path.join(REFS, driver)):
+        ref = norms(run(os.path.join(REFS, driver), *args))
+        assert {k: f"{v:e}" for k, v in got.items()} == {k: f"{v:e}" for k, v in ref.items()}
+
+
 def solver_lines(out):
     it = re.search(r"number of iterations\s*=\s*(\d+)", out)
     rs = re.search(r"relative residual\s*=\s*(\S+)", out)

@@ -195,6 +195,29 @@ def test_bicgstab_fused_updates_same_bits(b200, oracle, monkeypatch, opts):
             H.assert_bits_equal(runs[mode]["x"], runs["fused"]["x"], f"{name} {opts} x fused vs {mode}")
 
 
+@pytest.mark.parametrize("fmt", ["msr", "coo", "bsc", "vbr", "dns"])
+def test_other_formats_spmv_bits(b200, ref_serial, fmt):
+    """MSR / COO / BSC / VBR / DNS through their row-ordered device mirrors (host/lis_formats_ext.c): the CSR
+    kernels add the products in the order of the reference's serial lis_matvec_<fmt> -- same bits; a solve
+    with -storage <fmt> ends on the reference's iteration count"""
+    mats = [("p7", H.poisson3d_7pt(9, 8, 7)), ("unsym", H.random_csr(600, 6, 41, band=30)), ("p1d", H.poisson1d(333))]
+    if fmt != "dns":
+        mats.append(("p7_big", H.poisson3d_7pt(40, 30, 20)))               # row-block (TMA) kernel territory
+    for name, (ptr, idx, val) in mats:
+        n = len(ptr) - 1
+        for seed, kind in ((3, "wide"), (5, "uniform")):
+            x = H.rand_vec(n, seed, kind)
+            y, _ = b200.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2)
+            yr, _ = ref_serial.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2)
+            H.assert_bits_equal(y, yr, f"{fmt}/{name}")
+    ptr, idx, val = H.poisson3d_7pt(9, 8, 7)
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+    opts = f"-i cg -p jacobi -storage {fmt} -storage_block 2"
+    g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
+    assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and g["iter"] == r["iter"], (fmt, g["iter"], r["iter"])
+    assert np.abs(g["x"] - 1.0).max() < 1e-8
+
+
 @pytest.mark.parametrize("opts", ["-i cg -p jacobi", "-i cg -p jacobi -maxiter 7", "-i cg -p jacobi -initx_zeros false"])
 def test_cg_carried_jacobi_step_same_bits(b200, oracle, monkeypatch, opts):
     """CG + Jacobi with the update that ends an iteration also forming z = M^-1 r and <r,z> of the next one
