@@ -30,6 +30,10 @@ extern "C" {
 /* ------------------------------------------------------------------ scalar & index types */
 typedef double LIS_SCALAR;
 typedef double LIS_REAL;
+#ifdef HAVE_COMPLEX_H                      /* set by lis_config.h for the drivers (test/test7.c uses _Complex_I, creal through lis.h) */
+#include <complex.h>
+#endif
+typedef double _Complex LIS_COMPLEX;      /* include/lis.h:418 of the reference; only test/test7.c names it (real build: LIS_SCALAR stays double) */
 typedef int LIS_INT;
 typedef unsigned int LIS_UNSIGNED_INT;
 typedef LIS_INT LIS_Comm;            /* no MPI: ranks are processes bootstrapped from the env */

@@ -28,12 +28,13 @@ def need(*names):
 
 
 def test_drivers_were_built_from_unmodified_reference_sources():
-    """24 reference drivers compile and link against lis_b200 (checked where the tree exists)"""
+    """25 of the reference's 28 C drivers compile and link against lis_b200 (checked where the tree exists); the
+    other three are the generalized-eigenproblem drivers getest1/5/5b"""
     if not os.path.isdir("/root/reference/test"):
         pytest.skip("reference tree not present")
     H.ensure_built()
     for n in ("spmvtest1", "spmvtest2", "spmvtest2b", "spmvtest3", "spmvtest3b", "spmvtest4", "spmvtest5", "test1", "test2", "test2b",
-              "test3", "test3b", "test3c", "test4", "test5", "etest1", "etest2", "etest3", "etest4", "etest5", "etest5b", "etest6", "etest7", "test6"):
+              "test3", "test3b", "test3c", "test4", "test5", "etest1", "etest2", "etest3", "etest4", "etest5", "etest5b", "etest6", "etest7", "test6", "test7"):
         assert os.path.exists(os.path.join(OURS, n)), n
 
 
@@ -47,6 +48,8 @@ def test_dense_helper_drivers_print_what_the_reference_prints():
         for args in ((3, 2), (4, 4), (6, 5)):
             keep = lambda s: [ln for ln in s.splitlines() if "sec" not in ln and "time" not in ln]
             assert keep(run(os.path.join(OURS, d), *args)) == keep(run(os.path.join(REFS, d), *args)), (d, args)
+    if os.path.exists(os.path.join(OURS, "test7")) and os.path.exists(os.path.join(REFS, "test7")):
+        assert run(os.path.join(OURS, "test7")) == run(os.path.join(REFS, "test7"))         # the complex-number smoke driver (real build)
 
 
 def norms(out):
