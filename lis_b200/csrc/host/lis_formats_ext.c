@@ -411,13 +411,43 @@ typedef struct { LIS_INT r, c; LIS_SCALAR v; } slot_t;
 /* walks every stored slot of A in accumulation order; visit() gets (row, column, value) */
 typedef void (*visit_fn)(void *ctx, LIS_INT r, LIS_INT c, LIS_SCALAR v);
 
+static int g_walk_msr_offdiag_only = 0;
+
 static void walk(LIS_MATRIX A, visit_fn visit, void *ctx)
 {
     const LIS_INT n = A->n;
     switch (A->matrix_type) {
+    /* the four hot-path formats below are walked only for the transposed mirror (lis_matvech): storage
+     * order, padding slots included -- the reference's serial lis_matvech_<fmt> scatters in exactly this
+     * order (lis_matvec_ell.c:230-245, lis_matvec_dia.c:320-345, lis_matvec_jad.c:330-350, lis_matvec_bsr.c:985-1005) */
+    case LIS_MATRIX_ELL:
+        for (LIS_INT j = 0; j < A->maxnzr; j++)
+            for (LIS_INT i = 0; i < n; i++) visit(ctx, i, A->index[(size_t)j * n + i], A->value[(size_t)j * n + i]);
+        break;
+    case LIS_MATRIX_DIA:
+        for (LIS_INT j = 0; j < A->nnd; j++) {
+            const LIS_INT off = A->index[j], js = off < 0 ? -off : 0, je = n - off < n ? n - off : n;
+            for (LIS_INT i = js; i < je; i++) visit(ctx, i, i + off, A->value[(size_t)j * n + i]);
+        }
+        break;
+    case LIS_MATRIX_JAD:
+        for (LIS_INT j = 0; j < A->maxnzr; j++)
+            for (LIS_INT p = A->ptr[j], k = 0; p < A->ptr[j + 1]; p++, k++) visit(ctx, A->row[k], A->index[p], A->value[p]);
+        break;
+    case LIS_MATRIX_BSR: {
+        const LIS_INT bnr = A->bnr, bnc = A->bnc, bs = bnr * bnc;
+        for (LIS_INT bi = 0; bi < A->nr; bi++)
+            for (LIS_INT bc = A->bptr[bi]; bc < A->bptr[bi + 1]; bc++)
+                for (LIS_INT j = 0; j < bnc; j++)
+                    for (LIS_INT i = 0; i < bnr; i++) {
+                        const LIS_INT r = bi * bnr + i, c = A->bindex[bc] * bnc + j;
+                        if (r < n && c < n) visit(ctx, r, c, A->value[(size_t)bc * bs + (size_t)j * bnr + i]);
+                    }
+        break;
+    }
     case LIS_MATRIX_MSR:
         for (LIS_INT i = 0; i < n; i++) {
-            visit(ctx, i, i, A->value[i]);
+            if (!g_walk_msr_offdiag_only) visit(ctx, i, i, A->value[i]);
             for (LIS_INT j = A->index[i]; j < A->index[i + 1]; j++) visit(ctx, i, A->index[j], A->value[j]);
         }
         break;
@@ -503,6 +533,49 @@ LIS_INT lis_host_ordered_rows(LIS_MATRIX A, int keep_zeros, LIS_INT *nnz_out, LI
     }
     free(f.fill);
     *nnz_out = nnz; *ptr_out = f.ptr; *index_out = f.index; *value_out = f.value;
+    return LIS_SUCCESS;
+}
+
+/* The mirror lis_matvech runs on: A^T as CSR arrays, each row of A^T (= column c of A) listing its entries in
+ * the order in which the reference's serial lis_matvech_<fmt> adds them into y[c] -- every one of those
+ * routines zeroes y and scatters y[col] += v * x[row] while walking the storage once, front to back, so
+ * the order is "storage order, filed by column" (a stable counting sort).  MSR sets y[i] = d[i]*x[i] first
+ * (lis_matvec_msr.c:215-232): its mirror holds the off-diagonals only and runs on the split-order kernel
+ * behind the diagonal.  Explicit zeros and padding slots stay in (they are added there too). */
+typedef struct { LIS_INT *ptr, *fill, *index; LIS_SCALAR *value; } tr_ctx;
+static void tr_count(void *ctx, LIS_INT r, LIS_INT c, LIS_SCALAR v) { (void)r; (void)v; ((tr_ctx *)ctx)->ptr[c + 1]++; }
+static void tr_fill(void *ctx, LIS_INT r, LIS_INT c, LIS_SCALAR v)
+{
+    tr_ctx *t = (tr_ctx *)ctx;
+    t->index[t->fill[c]] = r; t->value[t->fill[c]] = v; t->fill[c]++;
+}
+
+LIS_INT lis_host_transposed_rows(LIS_MATRIX A, LIS_INT **ptr_out, LIS_INT **index_out, LIS_SCALAR **value_out)
+{
+    const LIS_INT n = A->n;
+    tr_ctx t;
+    memset(&t, 0, sizeof(t));
+    switch (A->matrix_type) {
+    case LIS_MATRIX_ELL: case LIS_MATRIX_DIA: case LIS_MATRIX_JAD: case LIS_MATRIX_BSR:
+    case LIS_MATRIX_MSR: case LIS_MATRIX_COO: case LIS_MATRIX_BSC: case LIS_MATRIX_VBR: case LIS_MATRIX_DNS: break;
+    default: LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    t.ptr = (LIS_INT *)tracked((size_t)n + 1, sizeof(LIS_INT), "lis_host_transposed_rows::ptr");
+    if (t.ptr == NULL) { LIS_SETERR_MEM(n); return LIS_OUT_OF_MEMORY; }
+    memset(t.ptr, 0, ((size_t)n + 1) * sizeof(LIS_INT));
+    g_walk_msr_offdiag_only = 1;
+    walk(A, tr_count, &t);
+    for (LIS_INT i = 0; i < n; i++) t.ptr[i + 1] += t.ptr[i];
+    const LIS_INT nnz = t.ptr[n];
+    t.index = (LIS_INT *)tracked((size_t)nnz, sizeof(LIS_INT), "lis_host_transposed_rows::index");
+    t.value = (LIS_SCALAR *)tracked((size_t)nnz, sizeof(LIS_SCALAR), "lis_host_transposed_rows::value");
+    t.fill = (LIS_INT *)malloc(((size_t)n + 1) * sizeof(LIS_INT));
+    if (!t.index || !t.value || !t.fill) { g_walk_msr_offdiag_only = 0; lis_free2(3, t.ptr, t.index, t.value); free(t.fill); LIS_SETERR_MEM(nnz); return LIS_OUT_OF_MEMORY; }
+    memcpy(t.fill, t.ptr, ((size_t)n + 1) * sizeof(LIS_INT));
+    walk(A, tr_fill, &t);
+    g_walk_msr_offdiag_only = 0;
+    free(t.fill);
+    *ptr_out = t.ptr; *index_out = t.index; *value_out = t.value;
     return LIS_SUCCESS;
 }
 

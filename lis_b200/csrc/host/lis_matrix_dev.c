@@ -602,10 +602,7 @@ LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (x == y || x->value == y->value) { LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvech: x and y must not alias\n"); return LIS_ERR_ILL_ARG; }
-    if (A->matrix_type != LIS_MATRIX_CSR && A->matrix_type != LIS_MATRIX_CSC) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech: CSR and CSC only (convert with -storage csr)\n");
-        return LIS_ERR_NOT_IMPLEMENTED;
-    }
+    if (A->is_splited && A->matrix_type != LIS_MATRIX_CSR) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
     lisd_matrix *M;
     err = lisd_matrix_get(A, &M);
     if (err) return err;
@@ -616,12 +613,23 @@ LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
             if (!err) err = transposed_upload(&M->UT, n, A->U->ptr, A->U->index, A->U->value);
         } else if (A->matrix_type == LIS_MATRIX_CSR) {
             err = transposed_upload(&M->csrT, n, A->ptr, A->index, A->value);
-        } else {
+        } else if (A->matrix_type == LIS_MATRIX_CSC) {
             err = csr_upload(&M->csrT, n, A->ptr, A->index, A->value);       /* CSC arrays == CSR of A^T */
+        } else {
+            /* every other format: A^T with each row in the order the reference's serial lis_matvech_<fmt>
+             * scatters into it (host/lis_formats_ext.c); MSR keeps its diagonal apart */
+            LIS_INT *tp, *ti;
+            LIS_SCALAR *tv;
+            err = lis_host_transposed_rows(A, &tp, &ti, &tv);
+            if (!err) {
+                err = csr_upload(A->matrix_type == LIS_MATRIX_MSR ? &M->LT : &M->csrT, n, tp, ti, tv);
+                lis_free2(3, tp, ti, tv);
+            }
         }
         if (err) return err;
         M->has_t = 1;
     }
+    const int msr = !M->splited && M->type == LIS_MATRIX_MSR;
     err = lisd_vec_device(x);
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
@@ -629,6 +637,8 @@ LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     int rc;
     if (M->splited)
         rc = lisb200_spmv_csr_split(n, M->diag, M->LT.ptr, M->LT.idx, M->LT.val, M->UT.ptr, M->UT.idx, M->UT.val, x->value, y->value, st);
+    else if (msr)                   /* y = d*x first, then the scattered off-diagonals; U (the forward mirror's empty part) adds nothing */
+        rc = lisb200_spmv_csr_split(n, M->diag, M->LT.ptr, M->LT.idx, M->LT.val, M->U.ptr, M->U.idx, M->U.val, x->value, y->value, st);
     else if (M->csrT.tma_rows)
         rc = lisb200_spmv_csr_tma(n, M->csrT.tma_rows, M->csrT.tma_tile, M->csrT.tma_stages, M->csrT.ptr, M->csrT.idx, M->csrT.val, x->value, y->value, st);
     else

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import harness as H
+import lis_b200
 
 pytestmark = pytest.mark.gpu
 
@@ -215,6 +216,37 @@ def test_other_formats_spmv_bits(b200, ref_serial, fmt):
     opts = f"-i cg -p jacobi -storage {fmt} -storage_block 2"
     g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
     assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and g["iter"] == r["iter"], (fmt, g["iter"], r["iter"])
+    assert np.abs(g["x"] - 1.0).max() < 1e-8
+
+
+@pytest.mark.parametrize("fmt", ["csc", "msr", "dia", "ell", "jad", "bsr", "bsc", "vbr", "coo", "dns"])
+def test_matvech_and_bicg_in_every_format(b200, ref_serial, fmt):
+    """lis_matvech through the transposed mirror of each storage format: the bits of the reference's serial scatter
+    loop (JAD within rounding: equal-length rows sit in a different order in the reference's layout); BiCG -- the
+    reference's default solver -- with -storage <fmt> ends on its iteration count"""
+    import ctypes as C
+    i32p, f64p = np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.float64)
+    mats = [("p7", H.poisson3d_7pt(9, 8, 7))] + ([("unsym", H.random_csr(600, 6, 41, band=30))] if fmt != "dia" else [])
+    if fmt not in ("dns", "dia"):
+        mats.append(("p7_big", H.poisson3d_7pt(40, 30, 20)))
+    for name, (ptr, idx, val) in mats:
+        n = len(ptr) - 1
+        x = H.rand_vec(n, 12, "wide")
+        ys = []
+        for shim in (b200, ref_serial):
+            shim.lib.shim_matvech.argtypes = [C.c_int, C.c_int, i32p, i32p, f64p, C.c_int, f64p, f64p]
+            y = np.zeros(n)
+            assert shim.lib.shim_matvech(lis_b200.FMT[fmt], n, ptr, idx, val, 0, x, y) == 0, (fmt, name)
+            ys.append(y)
+        if fmt == "jad":
+            assert np.abs(ys[0] - ys[1]).max() <= 1e-13 * np.abs(ys[1]).max()
+        else:
+            H.assert_bits_equal(ys[0], ys[1], f"matvech {fmt}/{name}")
+    ptr, idx, val = H.poisson3d_7pt(9, 8, 7)
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+    opts = f"-i bicg -p jacobi -storage {fmt} -storage_block 2"
+    g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
+    assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and abs(g["iter"] - r["iter"]) <= 1, (fmt, g["iter"], r["iter"])
     assert np.abs(g["x"] - 1.0).max() < 1e-8
 
 
