@@ -847,7 +847,7 @@ LIS_INT lis_bicgstabl(LIS_SOLVER solver)
  * x directly, use the raw -tol against ||b - A M^-1 x|| / ||b||, and finish with x = M^-1 x.
  * (With a preconditioner the reference first rescales the system, lis_solver.c:676-690; that
  * path is not carried over, so lis_solve accepts these three with -p none only.) */
-static LIS_INT stationary(LIS_SOLVER solver, int kind)
+static LIS_INT stationary_run(LIS_SOLVER solver, int kind, LIS_MATRIX S)
 {
     LIS_MATRIX A = solver->A;
     LIS_VECTOR b = solver->b, x = solver->x, r = W(0), t = W(1), s = W(2);
@@ -862,9 +862,9 @@ static LIS_INT stationary(LIS_SOLVER solver, int kind)
         CHK(lis_matrix_get_diagonal(A, W(3)));
         CHK(lis_vector_reciprocal(W(3)));
     } else {
-        CHK(lis_matrix_split(A));
-        if (kind == 1) CHK(lis_host_set_wd(A, 1.0, 0, LIS_SOLVER_GS));                                            /* WD = 1/D     */
-        else CHK(lis_host_set_wd(A, 1.0 / solver->params[LIS_PARAMS_OMEGA - LIS_OPTIONS_LEN], 1, LIS_SOLVER_SOR));  /* WD = 1/(D/w) */
+        CHK(lis_matrix_split(S));
+        if (kind == 1) CHK(lis_host_set_wd(S, 1.0, 0, LIS_SOLVER_GS));                                            /* WD = 1/D     */
+        else CHK(lis_host_set_wd(S, 1.0 / solver->params[LIS_PARAMS_OMEGA - LIS_OPTIONS_LEN], 1, LIS_SOLVER_SOR));  /* WD = 1/(D/w) */
     }
     for (iter = 1; iter <= maxiter; iter++) {
         PSOLVE(x, s);
@@ -875,7 +875,7 @@ static LIS_INT stationary(LIS_SOLVER solver, int kind)
             CHK(lisd_pmul(r, W(3), r));
             CHK(lisd_axpy(1.0, r, x));
         } else {
-            CHK(lis_matrix_solve(A, r, t, LIS_MATRIX_LOWER));
+            CHK(lis_matrix_solve(S, r, t, LIS_MATRIX_LOWER));
             CHK(lisd_axpy(1.0, t, x));
         }
         nrm2 = nrm2 * bnrm2;
@@ -887,6 +887,29 @@ static LIS_INT stationary(LIS_SOLVER solver, int kind)
     solver->iter = iter; solver->resid = nrm2; solver->ptime = ptime;
     solver->retcode = iter <= maxiter ? LIS_SUCCESS : LIS_MAXITER;
     return solver->retcode;
+}
+
+/* Gauss-Seidel / SOR sweep on the (D + L) part: in CSR storage the solver's own matrix is split in place like
+ * the reference does; in the other scalar formats the sweep runs on a private CSR copy (same D and L) while the
+ * products stay in the chosen format.  The block formats sweep block-wise in the reference: not offered. */
+static LIS_INT stationary(LIS_SOLVER solver, int kind)
+{
+    LIS_MATRIX A = solver->A, S = A;
+    LIS_INT err;
+    if (kind != 0 && A->matrix_type != LIS_MATRIX_CSR) {
+        if (A->matrix_type == LIS_MATRIX_BSR || A->matrix_type == LIS_MATRIX_BSC || A->matrix_type == LIS_MATRIX_VBR) {
+            LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "Gauss-Seidel / SOR on block storage (BSR/BSC/VBR) is not available; use a scalar format\n");
+            return LIS_ERR_NOT_IMPLEMENTED;
+        }
+        err = lis_matrix_duplicate(A, &S);
+        if (err) return err;
+        err = lis_matrix_set_type(S, LIS_MATRIX_CSR);
+        if (!err) err = lis_matrix_convert(A, S);
+        if (err) { lis_matrix_destroy(S); return err; }
+    }
+    err = stationary_run(solver, kind, S);
+    if (S != A) lis_matrix_destroy(S);
+    return err;
 }
 
 LIS_INT lis_jacobi(LIS_SOLVER solver) { return stationary(solver, 0); }

@@ -112,6 +112,30 @@ static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
     const LIS_SCALAR w = solver->params[LIS_PARAMS_SSOR_OMEGA - LIS_OPTIONS_LEN];
     LIS_INT err = lis_matrix_convert_self(solver);
     if (err) return err;
+    A = solver->A;
+    if (A->matrix_type != LIS_MATRIX_CSR) {
+        /* The reference splits and sweeps in the storage format itself (lis_matrix_split_<fmt>, lis_matrix_solve_<fmt>).
+         * For the scalar formats that is the same D, L, U and the same sweep as on the CSR form of the matrix, so the
+         * sweeps run on a private CSR copy while the products stay in the chosen format (unsplit order: the
+         * reference's products switch to the D + L + U order once split -- envelope parity, not bits).  The block
+         * formats are a different preconditioner there (block SSOR on the dense diagonal blocks): not offered. */
+        LIS_MATRIX C;
+        if (A->matrix_type == LIS_MATRIX_BSR || A->matrix_type == LIS_MATRIX_BSC || A->matrix_type == LIS_MATRIX_VBR) {
+            LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "SSOR on block storage (BSR/BSC/VBR) is block SSOR in Lis and is not available; use a scalar format\n");
+            return LIS_ERR_NOT_IMPLEMENTED;
+        }
+        err = lis_matrix_duplicate(A, &C);
+        if (err) return err;
+        err = lis_matrix_set_type(C, LIS_MATRIX_CSR);
+        if (!err) err = lis_matrix_convert(A, C);
+        if (!err) err = lis_matrix_split(C);
+        if (!err) err = lis_host_set_wd(C, w, 1, LIS_SOLVER_SOR);
+        if (!err) err = lis_host_ssor_prepare(C);
+        if (err) { lis_matrix_destroy(C); return err; }
+        precon->A = C;
+        precon->is_copy = LIS_TRUE;
+        return LIS_SUCCESS;
+    }
     err = lis_matrix_split(A);
     if (err) return err;
     err = lis_host_set_wd(A, w, 1, LIS_SOLVER_SOR);
@@ -157,9 +181,12 @@ LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
                 (*precon)->work = work;
                 for (LIS_INT i = 0; i < 2 && !err; i++) { err = lis_vector_duplicate(solver->A, &work[i]); if (!err) (*precon)->worklen = i + 1; }
                 if (!err) {
-                    if ((*precon)->is_copy && (*precon)->A && (*precon)->A != solver->A) lis_matrix_destroy((*precon)->A);
-                    (*precon)->A = solver->A;
-                    (*precon)->is_copy = LIS_FALSE;
+                    /* the Richardson loop multiplies by solver->A; an SSOR inner solve keeps its (possibly private) split matrix */
+                    if ((*precon)->precon_type != LIS_PRECON_TYPE_SSOR) {
+                        if ((*precon)->is_copy && (*precon)->A && (*precon)->A != solver->A) lis_matrix_destroy((*precon)->A);
+                        (*precon)->A = solver->A;
+                        (*precon)->is_copy = LIS_FALSE;
+                    }
                     (*precon)->precon_type = LIS_PRECON_TYPE_ADDS;
                 }
             }
@@ -222,7 +249,7 @@ static LIS_INT psolve_adds(LIS_SOLVER solver, LIS_VECTOR B, LIS_VECTOR X, int tr
         err = transposed ? psolveh_type(ptype, solver, R, W) : psolve_type(ptype, solver, R, W);
         if (!err) err = lisd_axpy(1.0, W, X);
         if (!err && k != iter) {
-            err = transposed ? lisd_matvech(precon->A, X, R) : lisd_matvec(precon->A, X, R);
+            err = transposed ? lisd_matvech(solver->A, X, R) : lisd_matvec(solver->A, X, R);
             if (!err) err = lisd_xpay(B, -1.0, R);
         }
     }

@@ -250,6 +250,18 @@ def test_matvech_and_bicg_in_every_format(b200, ref_serial, fmt):
     assert np.abs(g["x"] - 1.0).max() < 1e-8
 
 
+@pytest.mark.parametrize("fmt", ["ell", "dia", "msr", "jad"])
+def test_ssor_and_stationary_sweeps_in_scalar_formats(b200, ref_serial, fmt):
+    """SSOR / Gauss-Seidel / SOR with -storage <fmt>: sweeps on a private CSR copy, products in the format"""
+    ptr, idx, val = H.poisson3d_7pt(9, 8, 7)
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+    for o in ("-i cg -p ssor", "-i bicg -p ssor", "-i bicgstab -p ssor -adds true", "-i sor -omega 1.3"):
+        opts = f"{o} -storage {fmt} -maxiter 3000"
+        g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
+        assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and abs(g["iter"] - r["iter"]) <= 1, (opts, g["err"], g["iter"], r["iter"])
+        assert np.abs(g["x"] - 1.0).max() < 1e-8
+
+
 @pytest.mark.parametrize("opts", ["-i cg -p jacobi", "-i cg -p jacobi -maxiter 7", "-i cg -p jacobi -initx_zeros false"])
 def test_cg_carried_jacobi_step_same_bits(b200, oracle, monkeypatch, opts):
     """CG + Jacobi with the update that ends an iteration also forming z = M^-1 r and <r,z> of the next one
