@@ -39,6 +39,7 @@ void lis_host_set_num_threads(int n);
 LIS_INT lis_host_precon_type_end(void);
 LIS_INT lis_host_precon_lookup(const char *name);
 void    lis_host_print_rhistory(LIS_INT iter, LIS_REAL resid);
+LIS_INT lis_host_solver_entry(LIS_INT nsolver, LIS_INT (**work)(LIS_SOLVER), LIS_INT (**run)(LIS_SOLVER));
 LIS_INT lis_host_solver_malloc_work(LIS_SOLVER solver, LIS_INT worklen, LIS_INT first);
 LIS_INT lis_host_solver_residual(LIS_SOLVER solver, LIS_VECTOR r, LIS_REAL *res);
 LIS_INT lis_host_mgs(LIS_VECTOR *v, LIS_INT i, LIS_SCALAR *hcol, LIS_REAL *nrm);       /* modified Gram-Schmidt of v[i], lis_krylov.c */

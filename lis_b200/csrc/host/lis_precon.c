@@ -145,10 +145,64 @@ static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
     return lis_host_ssor_prepare(A);      /* upload D/L/U and build the level schedule now, not in the first sweep */
 }
 
+/* -p hybrid: M^-1 b = a few steps of another solver on the same matrix (src/precon/lis_precon_hybrid.c:54-135).
+ * The inner solver takes -hybrid_i / _maxiter / _tol / _omega / _ell / _restart / _p, runs its loop directly
+ * (no lis_solve front end: no scaling, no initial-vector copy beyond the one below) and keeps its work vectors,
+ * iterate and preconditioner for the lifetime of the outer preconditioner. */
+static LIS_INT create_hybrid(LIS_SOLVER solver, LIS_PRECON precon)
+{
+    LIS_SOLVER ps;
+    LIS_PRECON pp = NULL;
+    LIS_VECTOR xx = NULL;
+    LIS_INT (*work)(LIS_SOLVER), (*run)(LIS_SOLVER);
+    LIS_INT err = lis_solver_create(&ps);
+    if (err) return err;
+    ps->params[LIS_PARAMS_RESID - LIS_OPTIONS_LEN] = solver->params[LIS_PARAMS_PRESID - LIS_OPTIONS_LEN];
+    ps->params[LIS_PARAMS_SSOR_OMEGA - LIS_OPTIONS_LEN] = solver->params[LIS_PARAMS_POMEGA - LIS_OPTIONS_LEN];
+    ps->options[LIS_OPTIONS_MAXITER] = solver->options[LIS_OPTIONS_PMAXITER];
+    ps->options[LIS_OPTIONS_ELL] = solver->options[LIS_OPTIONS_PELL];
+    ps->options[LIS_OPTIONS_RESTART] = solver->options[LIS_OPTIONS_PRESTART];
+    ps->options[LIS_OPTIONS_OUTPUT] = 0;
+    ps->options[LIS_OPTIONS_SOLVER] = solver->options[LIS_OPTIONS_PSOLVER];
+    ps->options[LIS_OPTIONS_PRECON] = solver->options[LIS_OPTIONS_PPRECON];
+    ps->options[LIS_OPTIONS_INITGUESS_ZEROS] = solver->options[LIS_OPTIONS_INITGUESS_ZEROS];
+    ps->options[LIS_OPTIONS_PRECISION] = solver->options[LIS_OPTIONS_PRECISION];
+    ps->A = solver->A; ps->Ah = solver->Ah; ps->precision = solver->precision;
+    err = lis_host_solver_entry(ps->options[LIS_OPTIONS_SOLVER], &work, &run);
+    if (!err && ps->options[LIS_OPTIONS_PRECON] == LIS_PRECON_TYPE_HYBRID) { LIS_SETERR_IMP; err = LIS_ERR_NOT_IMPLEMENTED; }
+    if (!err) err = lis_vector_duplicate(solver->A, &xx);
+    if (!err) {
+        ps->rhistory = (LIS_REAL *)lis_malloc(((size_t)ps->options[LIS_OPTIONS_MAXITER] + 2 + 64) * sizeof(LIS_REAL), "lis_precon_create_hybrid::rhistory");
+        if (ps->rhistory == NULL) { LIS_SETERR_MEM(ps->options[LIS_OPTIONS_MAXITER]); err = LIS_OUT_OF_MEMORY; }
+    }
+    if (!err) err = lis_precon_create(ps, &pp);
+    if (!err) err = work(ps);
+    if (err) { if (pp) lis_precon_destroy(pp); if (xx) lis_vector_destroy(xx); lis_solver_destroy(ps); return err; }
+    ps->x = xx;
+    ps->precon = pp;
+    precon->solver = ps;
+    return LIS_SUCCESS;
+}
+
+/* src/precon/lis_precon_hybrid.c:138-200 */
+LIS_INT lis_psolve_hybrid(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    LIS_SOLVER ps = solver->precon->solver;
+    LIS_INT (*work)(LIS_SOLVER), (*run)(LIS_SOLVER);
+    LIS_INT err = lis_host_solver_entry(ps->options[LIS_OPTIONS_SOLVER], &work, &run);
+    if (err) return err;
+    ps->b = b;
+    err = ps->options[LIS_OPTIONS_INITGUESS_ZEROS] ? lisd_set_all(0.0, ps->x) : lisd_copy(b, ps->x);
+    if (err) return err;
+    err = run(ps);                                      /* MAXITER after -hybrid_maxiter steps is the normal way out */
+    if (err == LIS_ERR_DEVICE || err == LIS_ERR_OUT_OF_MEMORY || err == LIS_ERR_NOT_IMPLEMENTED || err == LIS_ERR_ILL_ARG) return err;
+    return lisd_copy(ps->x, x);
+}
+
 static LIS_INT create_unsupported(LIS_SOLVER solver, LIS_PRECON precon)
 {
     (void)solver; (void)precon;
-    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is not available (none, jacobi, ssor, ilu and registered ones are)\n");
+    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is not available (none, jacobi, ssor, ilu, hybrid and registered ones are)\n");
     return LIS_ERR_NOT_IMPLEMENTED;
 }
 
@@ -168,6 +222,7 @@ LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
         case LIS_PRECON_TYPE_JACOBI: err = create_jacobi(solver, *precon); break;
         case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
         case LIS_PRECON_TYPE_ILU: err = lis_host_ilu_create(solver, *precon); break;
+        case LIS_PRECON_TYPE_HYBRID: err = create_hybrid(solver, *precon); break;
         default: err = create_unsupported(solver, *precon); break;
         }
         if (!err && type && solver->options[LIS_OPTIONS_ADDS]) {
@@ -200,6 +255,11 @@ LIS_INT lis_precon_destroy(LIS_PRECON precon)
 {
     if (precon) {
         if (precon->is_copy && precon->A) lis_matrix_destroy(precon->A);
+        if (precon->solver) {                           /* hybrid: the inner solver with its iterate and preconditioner */
+            if (precon->solver->x) lis_vector_destroy(precon->solver->x);
+            lis_precon_destroy(precon->solver->precon);
+            lis_solver_destroy(precon->solver);
+        }
         if (precon->D) lis_vector_destroy(precon->D);
         if (precon->b200_ilu) lis_host_ilu_free(precon->b200_ilu);
         if (precon->work) {
@@ -270,6 +330,7 @@ static LIS_INT psolve_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VE
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
     case LIS_PRECON_TYPE_SSOR: return lis_psolve_ssor(solver, b, x);
     case LIS_PRECON_TYPE_ILU: return lis_psolve_iluk(solver, b, x);
+    case LIS_PRECON_TYPE_HYBRID: return lis_psolve_hybrid(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg)
             return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolve(solver, b, x);

@@ -472,6 +472,16 @@ static lis_solver_entry solver_entry(LIS_INT nsolver)
     return e;
 }
 
+/* work-vector allocator and iteration loop of solver `nsolver` (the reference's lis_solver_malloc_work[] /
+ * lis_solver_execute[] tables, which its hybrid preconditioner indexes directly) */
+LIS_INT lis_host_solver_entry(LIS_INT nsolver, LIS_INT (**work)(LIS_SOLVER), LIS_INT (**run)(LIS_SOLVER))
+{
+    const lis_solver_entry e = solver_entry(nsolver);
+    if (e.run == NULL) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
+    *work = e.work; *run = e.run;
+    return LIS_SUCCESS;
+}
+
 LIS_INT lis_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER solver)
 {
     LIS_INT err;

@@ -306,6 +306,25 @@ def test_ssor_and_stationary_sweeps_in_scalar_formats(hc, ref_serial, fmt):
         assert hc.solve(ptr, idx, val, b, f"-i cg -p ssor -storage {blk}")["err"] == 5         # block SSOR there: not offered
 
 
+HYBRID = ["-i cg -p hybrid", "-i bicgstab -p hybrid -hybrid_i gs -hybrid_maxiter 3", "-i gmres -p hybrid -hybrid_i cg -hybrid_maxiter 5 -hybrid_tol 1e-2",
+          "-i fgmres -p hybrid -hybrid_i bicgstab -hybrid_maxiter 4 -hybrid_p jacobi", "-i bicgstab -p hybrid -hybrid_i gmres -hybrid_restart 3 -hybrid_maxiter 6",
+          "-i cgs -p hybrid -hybrid_i sor -hybrid_omega 1.2 -hybrid_maxiter 2", "-i bicgstab -p hybrid -hybrid_i bicgstabl -hybrid_ell 3 -hybrid_maxiter 3 -hybrid_p ilu",
+          "-i gpbicg -p hybrid -hybrid_i jacobi -hybrid_maxiter 4 -storage ell", "-i bicgstab -p hybrid -initx_zeros false"]
+
+
+@pytest.mark.parametrize("opts", HYBRID)
+def test_hybrid_preconditioner_bit_for_bit(hc, ref_serial, opts):
+    """-p hybrid (an inner solver as the preconditioner, src/precon/lis_precon_hybrid.c): status, iteration count and
+    residual history of the serial reference, bit for bit, for inner stationary and Krylov solvers with their own
+    preconditioner -- including the runs the reference itself does not converge"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(7, 6, 5)), ("unsym", H.random_csr(400, 6, 17, band=25))):
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        g, r = hc.solve(ptr, idx, val, b, opts + " -maxiter 400"), ref_serial.solve(ptr, idx, val, b, opts + " -maxiter 400")
+        assert g["err"] == r["err"] == 0 and (g["status"], g["iter"]) == (r["status"], r["iter"]), (name, opts, g["err"], g["iter"], r["iter"])
+        H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{name} {opts}")
+        H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} x")
+
+
 @pytest.mark.parametrize("threads", [1, 2, 3, 8])
 def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads):
     """one application of M^-1 / M^-H for ILU(k) and SSOR against the reference: the serial build
@@ -328,7 +347,7 @@ def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads)
 def test_unsupported_requests_are_rejected(hc):
     ptr, idx, val = H.poisson1d(30)
     b = np.ones(30)
-    for opts, code in (("-i bicg -p sainv", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p saamg -adds true", 5),
+    for opts, code in (("-i bicg -p sainv", 5), ("-i bicg -p hybrid", 5), ("-i cg -p hybrid -hybrid_p hybrid", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p saamg -adds true", 5),
                        ("-i cg -scale jacobi -storage bsr", 5), ("-i cg -f quad", 1), ("-i gmres -conv_cond nrm2_b", 1), ("-i jacobi -conv_cond nrm2_b", 1),
                        ("-i gmres -restart -1", 1), ("-i cg -maxiter -3", 1)):
         g = hc.solve(ptr, idx, val, b, opts)

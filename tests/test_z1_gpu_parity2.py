@@ -250,6 +250,19 @@ def test_matvech_and_bicg_in_every_format(b200, ref_serial, fmt):
     assert np.abs(g["x"] - 1.0).max() < 1e-8
 
 
+@pytest.mark.parametrize("opts", ["-i bicgstab -p hybrid -hybrid_i gs -hybrid_maxiter 3", "-i fgmres -p hybrid -hybrid_i bicgstab -hybrid_maxiter 4 -hybrid_p jacobi",
+                                  "-i gmres -p hybrid -hybrid_i sor -hybrid_maxiter 3 -hybrid_tol 1e-30"])
+def test_hybrid_preconditioner(b200, ref_serial, opts):
+    """-p hybrid on the device kernels: converges like the serial reference (iteration count within its rounding spread).
+    (GMRES needs a FIXED preconditioner: a fixed number of stationary inner steps.  With an inner Krylov solver stopped
+    by -hybrid_tol it returns a wrong x in the reference as well -- the mock-device test reproduces even that bit for bit.)"""
+    ptr, idx, val = H.poisson3d_7pt(10, 9, 8)
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+    g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
+    assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and abs(g["iter"] - r["iter"]) <= max(1, r["iter"] // 10), (opts, g["iter"], r["iter"])
+    assert np.abs(g["x"] - 1.0).max() < 1e-8
+
+
 @pytest.mark.parametrize("fmt", ["ell", "dia", "msr", "jad"])
 def test_ssor_and_stationary_sweeps_in_scalar_formats(b200, ref_serial, fmt):
     """SSOR / Gauss-Seidel / SOR with -storage <fmt>: sweeps on a private CSR copy, products in the format"""
