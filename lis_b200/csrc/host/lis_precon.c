@@ -221,7 +221,7 @@ LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
         case LIS_PRECON_TYPE_NONE: err = create_none(solver, *precon); break;
         case LIS_PRECON_TYPE_JACOBI: err = create_jacobi(solver, *precon); break;
         case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
-        case LIS_PRECON_TYPE_ILU: err = lis_host_ilu_create(solver, *precon); break;
+        case LIS_PRECON_TYPE_ILU: case LIS_PRECON_TYPE_ILUT: err = lis_host_ilu_create(solver, *precon); break;
         case LIS_PRECON_TYPE_HYBRID: err = create_hybrid(solver, *precon); break;
         default: err = create_unsupported(solver, *precon); break;
         }
@@ -329,7 +329,7 @@ static LIS_INT psolve_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VE
     case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
     case LIS_PRECON_TYPE_SSOR: return lis_psolve_ssor(solver, b, x);
-    case LIS_PRECON_TYPE_ILU: return lis_psolve_iluk(solver, b, x);
+    case LIS_PRECON_TYPE_ILU: case LIS_PRECON_TYPE_ILUT: return lis_psolve_iluk(solver, b, x);
     case LIS_PRECON_TYPE_HYBRID: return lis_psolve_hybrid(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg)
@@ -353,7 +353,7 @@ static LIS_INT psolveh_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_V
     case LIS_PRECON_TYPE_NONE: return lis_psolve_none(solver, b, x);
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
     case LIS_PRECON_TYPE_SSOR: return lis_matrix_solveh(solver->precon->A, b, x, LIS_MATRIX_SSOR);
-    case LIS_PRECON_TYPE_ILU: return lis_psolveh_iluk(solver, b, x);
+    case LIS_PRECON_TYPE_ILU: case LIS_PRECON_TYPE_ILUT: return lis_psolveh_iluk(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg && g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh)
             return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh(solver, b, x);

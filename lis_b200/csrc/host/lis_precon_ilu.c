@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "lis_device.h"
 #include "lis_host.h"
 
@@ -183,6 +184,135 @@ static LIS_INT ilu_numeric(LIS_MATRIX A, int nb, lisd_ilu *F, LIS_SCALAR *d)
     return LIS_SUCCESS;
 }
 
+/* ILUT (`-p ilut [-iluc_drop tol] [-iluc_rate m]`), the serial factorization of
+ * src/precon/lis_precon_ilut.c:364-620 into the same L / U / D containers as ILU(k), so that the apply
+ * (lis_precon_ilut.c:623-830 and :832-1030: the loops of the ILU(k) apply) runs on the same sweeps.
+ * Row i: the entries left of the diagonal are eliminated in ascending column order (fill-ins join the
+ * queue), l = w * d[k], every update lxu = -l * u_kj is dropped when it would create a new entry and
+ * |lxu| < tol * mean|a_i*|; d[i] = 1/w_ii.  Then each part keeps at most lfil = int(nnz/(2n) * m) entries:
+ * the reference sorts |w| ASCENDING and keeps the first lfil, i.e. the smallest (lis_sort_di, :556-560) --
+ * followed here, with its quicksort scheme, which decides among equal magnitudes at the cut.  What is kept stays in position order: L ascending by column, U in A's order then fill-ins in
+ * discovery order (the summation order of the U solve). */
+typedef struct { LIS_SCALAR mag; LIS_INT pos; } ilut_key;
+/* Which of several equal magnitudes survive the cut is decided by the reference's sort, so this is that
+ * sort's scheme (src/system/lis_sort.c:431-470, lis_sort_di): quicksort on the magnitudes, pivot = the
+ * middle element parked at the right end, both scans with strict comparisons, halves [lo, j] and [i, hi]. */
+static void ilut_sort(ilut_key *k, LIS_INT lo, LIS_INT hi)
+{
+    while (lo < hi) {
+        const LIS_INT mid = (lo + hi) / 2;
+        const LIS_SCALAR pivot = k[mid].mag;
+        ilut_key t = k[mid]; k[mid] = k[hi]; k[hi] = t;
+        LIS_INT i = lo, j = hi;
+        while (i <= j) {
+            while (k[i].mag < pivot) i++;
+            while (k[j].mag > pivot) j--;
+            if (i <= j) { t = k[i]; k[i] = k[j]; k[j] = t; i++; j--; }
+        }
+        ilut_sort(k, lo, j);
+        lo = i;                                            /* right half in place of the second recursive call */
+    }
+}
+static int ilut_pos_cmp(const void *a, const void *b) { return (*(const LIS_INT *)a > *(const LIS_INT *)b) - (*(const LIS_INT *)a < *(const LIS_INT *)b); }
+
+static LIS_INT ilut_keep(ilu_rows *R, LIS_INT count, LIS_INT lfil, const LIS_INT *cols, const LIS_SCALAR *vals, ilut_key *keys, LIS_INT *sel)
+{
+    const LIS_INT len = lfil < count ? lfil : count;
+    if (rows_reserve(R, (size_t)(len > 0 ? len : 0), 0)) return LIS_OUT_OF_MEMORY;
+    {
+        LIS_SCALAR *nv = (LIS_SCALAR *)realloc(R->val, sizeof(LIS_SCALAR) * (R->cap ? R->cap : 1));
+        if (!nv) return LIS_OUT_OF_MEMORY;
+        R->val = nv;
+    }
+    if (len == count) {
+        for (LIS_INT j = 0; j < count; j++) sel[j] = j;
+    } else {
+        for (LIS_INT j = 0; j < count; j++) { keys[j].mag = fabs(vals[j]); keys[j].pos = j; }
+        ilut_sort(keys, 0, count - 1);
+        for (LIS_INT j = 0; j < len; j++) sel[j] = keys[j].pos;
+        qsort(sel, (size_t)len, sizeof(LIS_INT), ilut_pos_cmp);
+    }
+    for (LIS_INT j = 0; j < len; j++) { R->idx[R->nnz] = cols[sel[j]]; R->val[R->nnz] = vals[sel[j]]; R->nnz++; }
+    return LIS_SUCCESS;
+}
+
+static LIS_INT ilut_factor(LIS_MATRIX A, LIS_SCALAR tol, LIS_SCALAR rate, lisd_ilu *F, LIS_SCALAR *d)
+{
+    const LIS_INT n = A->n;
+    const LIS_INT lfil = n > 0 ? (LIS_INT)(((double)A->ptr[n] / (2.0 * n)) * rate) : 0;
+    LIS_INT err = LIS_OUT_OF_MEMORY;
+    LIS_INT *where = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1));       /* column -> slot (lower: 0.., diagonal: -2, upper: n + k), -1 absent */
+    LIS_INT *lcol = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1)), *ucol = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1));
+    LIS_INT *sel = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1));
+    LIS_SCALAR *lval = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(n + 1)), *uval = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(n + 1));
+    ilut_key *keys = (ilut_key *)malloc(sizeof(ilut_key) * (size_t)(n + 1));
+    char *done = (char *)calloc((size_t)(n + 1), 1);
+    F->L.ptr = (LIS_INT *)calloc((size_t)n + 1, sizeof(LIS_INT));
+    F->U.ptr = (LIS_INT *)calloc((size_t)n + 1, sizeof(LIS_INT));
+    if (!where || !lcol || !ucol || !sel || !lval || !uval || !keys || !done || !F->L.ptr || !F->U.ptr) { LIS_SETERR_MEM(n); goto out; }
+    for (LIS_INT i = 0; i < n; i++) where[i] = -1;
+    for (LIS_INT i = 0; i < n; i++) {
+        LIS_REAL tnorm = 0;
+        LIS_INT nl = 0, nu = 0;
+        LIS_SCALAR wd = 0;
+        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) tnorm += fabs(A->value[j]);
+        tnorm = tnorm / (double)(A->ptr[i + 1] - A->ptr[i]);
+        const LIS_REAL tolnorm = tol * tnorm;
+        where[i] = -2;
+        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
+            const LIS_INT c = A->index[j];
+            if (c >= n) continue;
+            /* a column stored twice overwrites the slot map like the reference's iw[] does: both copies stay in the list */
+            if (c < i) { lcol[nl] = c; lval[nl] = A->value[j]; where[c] = nl; done[nl] = 0; nl++; }
+            else if (c == i) wd = A->value[j];
+            else { ucol[nu] = c; uval[nu] = A->value[j]; where[c] = n + nu; nu++; }
+        }
+        for (LIS_INT step = 0; step < nl; step++) {
+            LIS_INT q = -1;                                       /* next pivot: the smallest column not yet eliminated */
+            for (LIS_INT k = 0; k < nl; k++) if (!done[k] && (q < 0 || lcol[k] < lcol[q])) q = k;
+            done[q] = 1;
+            const LIS_INT k = lcol[q];
+            const LIS_SCALAR fact = lval[q] * d[k];
+            lval[q] = fact;
+            where[k] = -1;
+            for (LIS_INT p = F->U.ptr[k]; p < F->U.ptr[k + 1]; p++) {
+                const LIS_INT c = F->U.idx[p];
+                const LIS_INT slot = where[c];
+                const LIS_SCALAR lxu = -fact * F->U.val[p];
+                if (fabs(lxu) < tolnorm && slot == -1) continue;
+                if (c >= i) {
+                    if (slot == -1) { ucol[nu] = c; uval[nu] = lxu; where[c] = n + nu; nu++; }
+                    else if (slot == -2) wd += lxu;
+                    else uval[slot - n] += lxu;
+                } else {
+                    if (slot == -1) { lcol[nl] = c; lval[nl] = lxu; where[c] = nl; done[nl] = 0; nl++; }
+                    else lval[slot] += lxu;
+                }
+            }
+        }
+        where[i] = -1;
+        for (LIS_INT k = 0; k < nu; k++) where[ucol[k]] = -1;
+        for (LIS_INT k = 0; k < nl; k++) where[lcol[k]] = -1;
+        d[i] = 1.0 / wd;
+        /* L in ascending column order = the order the reference's selection loop leaves behind */
+        for (LIS_INT a = 1; a < nl; a++) {
+            const LIS_INT c = lcol[a]; const LIS_SCALAR v = lval[a];
+            LIS_INT b = a - 1;
+            while (b >= 0 && lcol[b] > c) { lcol[b + 1] = lcol[b]; lval[b + 1] = lval[b]; b--; }
+            lcol[b + 1] = c; lval[b + 1] = v;
+        }
+        if (ilut_keep(&F->L, nl, lfil, lcol, lval, keys, sel) || ilut_keep(&F->U, nu, lfil, ucol, uval, keys, sel)) { LIS_SETERR_MEM(nl + nu); goto out; }
+        F->L.ptr[i + 1] = (LIS_INT)F->L.nnz;
+        F->U.ptr[i + 1] = (LIS_INT)F->U.nnz;
+    }
+    if (F->L.idx == NULL) { F->L.idx = (LIS_INT *)calloc(1, sizeof(LIS_INT)); F->L.val = (LIS_SCALAR *)calloc(1, sizeof(LIS_SCALAR)); }
+    if (F->U.idx == NULL) { F->U.idx = (LIS_INT *)calloc(1, sizeof(LIS_INT)); F->U.val = (LIS_SCALAR *)calloc(1, sizeof(LIS_SCALAR)); }
+    err = LIS_SUCCESS;
+out:
+    free(where); free(lcol); free(ucol); free(sel); free(lval); free(uval); free(keys); free(done);
+    return err;
+}
+
 /* T = R^T as CSR; a row of T lists its entries by ascending (or descending) source row: the
  * order in which the reference's column-oriented loops subtract them */
 static LIS_INT rows_transpose(LIS_INT n, const ilu_rows *R, int descending, ilu_rows *T)
@@ -235,8 +365,13 @@ LIS_INT lis_host_ilu_create(LIS_SOLVER solver, LIS_PRECON precon)
     err = lis_vector_duplicate(solver->A, &precon->D);
     LIS_SCALAR *d = NULL;
     if (!err) { d = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(A->n > 0 ? A->n : 1)); if (!d) { LIS_SETERR_MEM(A->n * 8); err = LIS_OUT_OF_MEMORY; } }
-    if (!err) err = ilu_symbolic(A, solver->options[LIS_OPTIONS_FILL], nb, F);
-    if (!err) err = ilu_numeric(A, nb, F, d);
+    if (!err && solver->options[LIS_OPTIONS_PRECON] == LIS_PRECON_TYPE_ILUT) {
+        if (nb > 1) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "ILUT: the per-thread block variant (-omp_num_threads > 1) is not available\n"); err = LIS_ERR_NOT_IMPLEMENTED; }
+        else err = ilut_factor(A, solver->params[LIS_PARAMS_DROP - LIS_OPTIONS_LEN], solver->params[LIS_PARAMS_RATE - LIS_OPTIONS_LEN], F, d);
+    } else {
+        if (!err) err = ilu_symbolic(A, solver->options[LIS_OPTIONS_FILL], nb, F);
+        if (!err) err = ilu_numeric(A, nb, F, d);
+    }
     if (!err && A->n > 0) err = lis_vector_set_values2(LIS_INS_VALUE, precon->D->is + precon->D->origin, A->n, d, precon->D);
     free(d);
     if (B) lis_matrix_destroy(B);

@@ -325,6 +325,24 @@ def test_hybrid_preconditioner_bit_for_bit(hc, ref_serial, opts):
         H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} x")
 
 
+ILUT = ["-i cg -p ilut", "-i bicgstab -p ilut -iluc_drop 0.001", "-i gmres -p ilut -iluc_drop 0 -iluc_rate 1", "-i bicgstab -p ilut -iluc_rate 0.5",
+        "-i bicg -p ilut", "-i bicgstab -p ilut -storage ell", "-i bicgstab -p ilut -iluc_drop 0.2 -iluc_rate 10"]
+
+
+@pytest.mark.parametrize("opts", ILUT)
+def test_ilut_preconditioner_bit_for_bit(hc, ref_serial, opts):
+    """-p ilut: the threshold factorization of src/precon/lis_precon_ilut.c (drop rule, fill cap that keeps the
+    SMALLEST magnitudes, the reference's tie order at the cut) into the ILU(k) containers, applied by the same
+    sweeps (also transposed, for BiCG): status, iteration count, residual history and solution of the serial reference"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(7, 6, 5)), ("unsym", H.random_csr(400, 6, 17, band=25)), ("p27", H.poisson3d_27pt(5, 5, 4)),
+                                  ("wide", H.random_csr(300, 12, 5, band=60))):
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        g, r = hc.solve(ptr, idx, val, b, opts + " -maxiter 400"), ref_serial.solve(ptr, idx, val, b, opts + " -maxiter 400")
+        assert g["err"] == r["err"] == 0 and (g["status"], g["iter"]) == (r["status"], r["iter"]), (name, opts, g["err"], g["iter"], r["iter"])
+        H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{name} {opts}")
+        H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} x")
+
+
 @pytest.mark.parametrize("threads", [1, 2, 3, 8])
 def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads):
     """one application of M^-1 / M^-H for ILU(k) and SSOR against the reference: the serial build

@@ -263,6 +263,17 @@ def test_hybrid_preconditioner(b200, ref_serial, opts):
     assert np.abs(g["x"] - 1.0).max() < 1e-8
 
 
+@pytest.mark.parametrize("opts", ["-i bicgstab -p ilut", "-i bicg -p ilut -iluc_drop 0.001", "-i gmres -p ilut -iluc_rate 0.5"])
+def test_ilut_preconditioner(b200, ref_serial, opts):
+    """-p ilut: host factorization (bit-equal to the reference's, tests/test_hostcheck.py), the two triangular solves on the
+    one-launch sweep kernel -- converges like the serial reference"""
+    for ptr, idx, val in (H.poisson3d_7pt(10, 9, 8), H.random_csr(1500, 7, 404, band=50)):
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
+        assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and abs(g["iter"] - r["iter"]) <= max(1, r["iter"] // 10), (opts, g["iter"], r["iter"])
+        assert np.abs(g["x"] - 1.0).max() < 1e-8
+
+
 @pytest.mark.parametrize("fmt", ["ell", "dia", "msr", "jad"])
 def test_ssor_and_stationary_sweeps_in_scalar_formats(b200, ref_serial, fmt):
     """SSOR / Gauss-Seidel / SOR with -storage <fmt>: sweeps on a private CSR copy, products in the format"""
