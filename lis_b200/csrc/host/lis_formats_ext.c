@@ -620,3 +620,48 @@ LIS_INT lis_host_ext_get_diagonal(LIS_MATRIX A, LIS_SCALAR *d, int *handled)
     free(q.seen);
     return LIS_SUCCESS;
 }
+
+/* A <- A - sigma*I on the stored diagonal slots (src/matrix/lis_matrix_<fmt>.c, lis_matrix_shift_diagonal_<fmt>:
+ * MSR value[i]; COO every k with row == col; JAD / BSR / BSC / VBR / DNS the slot of (i, i)) */
+LIS_INT lis_host_ext_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma, int *handled)
+{
+    const LIS_INT n = A->n;
+    *handled = 1;
+    switch (A->matrix_type) {
+    case LIS_MATRIX_MSR:
+        for (LIS_INT i = 0; i < n; i++) A->value[i] -= sigma;
+        break;
+    case LIS_MATRIX_COO:
+        for (LIS_INT k = 0; k < A->nnz; k++) if (A->row[k] == A->col[k]) A->value[k] -= sigma;
+        break;
+    case LIS_MATRIX_DNS:
+        for (LIS_INT i = 0; i < n; i++) A->value[(size_t)i * n + i] -= sigma;
+        break;
+    case LIS_MATRIX_JAD:
+        for (LIS_INT j = 0; j < A->maxnzr; j++)
+            for (LIS_INT p = A->ptr[j], k = 0; p < A->ptr[j + 1]; p++, k++) if (A->row[k] == A->index[p]) A->value[p] -= sigma;
+        break;
+    case LIS_MATRIX_BSR: case LIS_MATRIX_BSC: {
+        const LIS_INT bnr = A->bnr, bnc = A->bnc, bs = bnr * bnc, outer = A->matrix_type == LIS_MATRIX_BSR ? A->nr : A->nc;
+        for (LIS_INT bo = 0; bo < outer; bo++)
+            for (LIS_INT bc = A->bptr[bo]; bc < A->bptr[bo + 1]; bc++)
+                for (LIS_INT j = 0; j < bnc; j++)
+                    for (LIS_INT i = 0; i < bnr; i++) {
+                        const LIS_INT r = (A->matrix_type == LIS_MATRIX_BSR ? bo : A->bindex[bc]) * bnr + i;
+                        const LIS_INT c = (A->matrix_type == LIS_MATRIX_BSR ? A->bindex[bc] : bo) * bnc + j;
+                        if (r == c && r < n) A->value[(size_t)bc * bs + (size_t)j * bnr + i] -= sigma;
+                    }
+        break;
+    }
+    case LIS_MATRIX_VBR:
+        for (LIS_INT bi = 0; bi < A->nr; bi++)
+            for (LIS_INT bc = A->bptr[bi]; bc < A->bptr[bi + 1]; bc++) {
+                const LIS_INT bj = A->bindex[bc], h = A->row[bi + 1] - A->row[bi];
+                for (LIS_INT j = A->col[bj]; j < A->col[bj + 1]; j++)
+                    if (j >= A->row[bi] && j < A->row[bi + 1]) A->value[(size_t)A->ptr[bc] + (size_t)(j - A->col[bj]) * h + (j - A->row[bi])] -= sigma;
+            }
+        break;
+    default: *handled = 0; break;
+    }
+    return LIS_SUCCESS;
+}

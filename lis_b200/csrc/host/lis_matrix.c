@@ -732,9 +732,14 @@ LIS_INT lis_matrix_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma)
         for (LIS_INT j = 0; j < A->nnd; j++)
             if (A->index[j] == 0) { for (LIS_INT i = 0; i < n; i++) A->value[(size_t)j * n + i] -= sigma; break; }
         break;
-    default:
-        LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_shift_diagonal: storage format %D (use CSR, CSC, ELL or DIA)\n", A->matrix_type);
-        return LIS_ERR_NOT_IMPLEMENTED;
+    default: {
+        int handled = 0;                                   /* MSR, JAD, BSR, BSC, VBR, COO, DNS: lis_formats_ext.c */
+        lis_host_ext_shift_diagonal(A, sigma, &handled);
+        if (!handled) {
+            LIS_SETERR1(LIS_ERR_NOT_IMPLEMENTED, "lis_matrix_shift_diagonal: storage format %D\n", A->matrix_type);
+            return LIS_ERR_NOT_IMPLEMENTED;
+        }
+    }
     }
     return lisd_matrix_shift_diagonal(A, sigma);
 }
