@@ -530,6 +530,14 @@ LIS_INT lis_matrix_malloc_ell(LIS_INT n, LIS_INT maxnzr, LIS_INT **index, LIS_SC
 LIS_INT lis_matrix_set_ell(LIS_INT maxnzr, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
 LIS_INT lis_matrix_malloc_jad(LIS_INT n, LIS_INT nnz, LIS_INT maxnzr, LIS_INT **perm, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);
 LIS_INT lis_matrix_set_jad(LIS_INT nnz, LIS_INT maxnzr, LIS_INT *perm, LIS_INT *ptr, LIS_INT *index, LIS_SCALAR *value, LIS_MATRIX A);
+/* in-place update of a stored entry of an assembled CSR matrix, and friends (include/lis.h:827-892, :1032-1037 of the reference) */
+LIS_INT lis_matrix_psd_set_value(LIS_INT flag, LIS_INT i, LIS_INT j, LIS_SCALAR value, LIS_MATRIX A);
+LIS_INT lis_matrix_psd_set_value_csr(LIS_INT flag, LIS_INT i, LIS_INT j, LIS_SCALAR value, LIS_MATRIX A);
+LIS_INT lis_matrix_psd_reset_scale(LIS_MATRIX A);
+LIS_INT lis_vector_psd_reset_scale(LIS_VECTOR vec);
+LIS_INT lis_matrix_get_vbr_rowcol(LIS_MATRIX Ain, LIS_INT *nr, LIS_INT *nc, LIS_INT **row, LIS_INT **col);
+void    lis_do_not_handle_mpi(void);
+LIS_INT lis_debug_trace_func(LIS_INT flag, char *func);
 /* the formats outside the named hot path (MSR, COO, BSC, VBR, DNS; /root/reference include/lis.h:898-914): conversion
  * from and to CSR, lis_matvec through a row-ordered device mirror with the reference's accumulation order */
 LIS_INT lis_matrix_malloc_msr(LIS_INT n, LIS_INT nnz, LIS_INT ndz, LIS_INT **index, LIS_SCALAR **value);

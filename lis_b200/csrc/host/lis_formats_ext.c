@@ -286,6 +286,8 @@ out:
 /* the partition the reference derives when the caller gave none (lis_matrix_vbr.c:262-337): a boundary
  * wherever a run of consecutive column numbers starts or ends in any (sorted) row; the same list cuts
  * rows and columns */
+static LIS_INT vbr_partition(LIS_MATRIX Ain, LIS_INT *nblk, LIS_INT **row, LIS_INT **col);
+LIS_INT lis_host_vbr_partition(LIS_MATRIX Ain, LIS_INT *nblk, LIS_INT **row, LIS_INT **col) { return vbr_partition(Ain, nblk, row, col); }
 static LIS_INT vbr_partition(LIS_MATRIX Ain, LIS_INT *nblk, LIS_INT **row, LIS_INT **col)
 {
     const LIS_INT n = Ain->n;

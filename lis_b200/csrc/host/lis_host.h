@@ -24,6 +24,7 @@ LIS_INT lis_host_matrix_check_set(LIS_MATRIX A);
 LIS_INT lis_host_ext_from_csr(LIS_MATRIX Acsr, LIS_MATRIX Aout, int *handled);
 LIS_INT lis_host_ext_to_csr(LIS_MATRIX Ain, LIS_MATRIX Aout, int *handled);
 LIS_INT lis_host_ext_shift_diagonal(LIS_MATRIX A, LIS_SCALAR sigma, int *handled);
+LIS_INT lis_host_vbr_partition(LIS_MATRIX Ain, LIS_INT *nblk, LIS_INT **row, LIS_INT **col);
 LIS_INT lis_host_ext_get_diagonal(LIS_MATRIX A, LIS_SCALAR *d, int *handled);
 LIS_INT lis_host_transposed_rows(LIS_MATRIX A, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);
 LIS_INT lis_host_ordered_rows(LIS_MATRIX A, int keep_zeros, LIS_INT *nnz, LIS_INT **ptr, LIS_INT **index, LIS_SCALAR **value);

@@ -639,6 +639,60 @@ LIS_INT lis_matrix_set_bsr(LIS_INT bnr, LIS_INT bnc, LIS_INT bnnz, LIS_INT *bptr
     return LIS_SUCCESS;
 }
 
+/* In-place update of one stored entry of an ASSEMBLED matrix (the reference's "psd" calls, for time-stepping codes
+ * that keep the pattern and rewrite the numbers: src/matrix/lis_matrix.c:806-860, lis_matrix_csr.c:205-268): CSR
+ * only, the first stored (i, j) of the row; an (i, j) that is not stored is silently left alone, as there.  The
+ * device mirror is dropped and re-uploaded by the next product. */
+LIS_INT lis_matrix_psd_set_value_csr(LIS_INT flag, LIS_INT i, LIS_INT j, LIS_SCALAR value, LIS_MATRIX A)
+{
+    const LIS_INT n = A->n, gn = A->gn, is = A->is, ie = A->ie;
+    if (A->origin) { i--; j--; }
+    if (i < 0 || j < 0) {
+        LIS_SETERR3(LIS_ERR_ILL_ARG, "i(=%D) or j(=%D) are less than %D\n", i + A->origin, j + A->origin, A->origin);
+        return LIS_ERR_ILL_ARG;
+    }
+    if (i >= gn || j >= gn) {
+        LIS_SETERR3(LIS_ERR_ILL_ARG, "i(=%D) or j(=%D) are larger than global n=(%D)\n", i + A->origin, j + A->origin, gn);
+        return LIS_ERR_ILL_ARG;
+    }
+    if (i < is || i >= ie) {
+        LIS_SETERR3(LIS_ERR_ILL_ARG, "row i(=%D) is outside the local range [%D,%D)\n", i + A->origin, is, ie);
+        return LIS_ERR_ILL_ARG;
+    }
+    for (LIS_INT k = A->ptr[i - is]; k < A->ptr[i - is + 1]; k++) {
+        const LIS_INT c = A->index[k];
+        const LIS_INT jg = c < n ? c + is : (A->l2g_map ? A->l2g_map[c - n] : c);
+        if (jg == j) {
+            if (flag == LIS_INS_VALUE) A->value[k] = value; else A->value[k] += value;
+            lisd_matrix_drop(A);
+            break;
+        }
+    }
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_matrix_psd_set_value(LIS_INT flag, LIS_INT i, LIS_INT j, LIS_SCALAR value, LIS_MATRIX A)
+{
+    LIS_INT err = matrix_check(A, CHECK_SIZE);
+    if (err) return err;
+    if (A->status == LIS_MATRIX_CSR && !A->is_splited) return lis_matrix_psd_set_value_csr(flag, i, j, value, A);
+    if (A->status > 0) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }             /* assembled, another format */
+    return lis_matrix_set_value(flag, i, j, value, A);                                   /* not assembled yet: the ordinary path */
+}
+
+LIS_INT lis_matrix_psd_reset_scale(LIS_MATRIX A) { A->is_scaled = LIS_FALSE; return LIS_SUCCESS; }
+
+/* the block partition lis_matrix_convert derives for VBR when the caller gave none */
+LIS_INT lis_matrix_get_vbr_rowcol(LIS_MATRIX Ain, LIS_INT *nr, LIS_INT *nc, LIS_INT **row, LIS_INT **col)
+{
+    LIS_INT err = lis_host_matrix_check_input(Ain);
+    if (err) return err;
+    if (Ain->matrix_type != LIS_MATRIX_CSR) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
+    err = lis_host_vbr_partition(Ain, nr, row, col);
+    if (!err) *nc = *nr;
+    return err;
+}
+
 /* ------------------------------------------------------------------ CSR utilities */
 /* a dense n x n block given row by row, entry by entry through lis_matrix_set_value
  * (src/matrix/lis_matrix.c:859-875) */

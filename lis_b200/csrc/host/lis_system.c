@@ -167,6 +167,18 @@ LIS_INT lis_printf(LIS_Comm comm, const char *mess, ...)
     return LIS_SUCCESS;
 }
 
+/* call-depth trace behind the reference's LIS_DEBUG_FUNC_IN / _OUT macros (src/system/lis_error.c:67-95) */
+LIS_INT lis_debug_trace_func(LIS_INT flag, char *func)
+{
+    static int depth = 0;
+    if (flag) { lis_printf(LIS_COMM_WORLD, "%*s : %s\n", depth + 3, "IN ", func); depth++; }
+    else { depth--; lis_printf(LIS_COMM_WORLD, "%*s : %s\n", depth + 3, "OUT", func); }
+    return LIS_SUCCESS;
+}
+
+/* the reference's "the application owns MPI_Init/Finalize" switch (src/system/lis_init.c:99): nothing to own here */
+void lis_do_not_handle_mpi(void) {}
+
 void CHKERR(LIS_INT err)
 {
     if (err) {

@@ -136,6 +136,8 @@ LIS_INT lis_vector_get_range(LIS_VECTOR v, LIS_INT *is, LIS_INT *ie)
     return LIS_SUCCESS;
 }
 
+LIS_INT lis_vector_psd_reset_scale(LIS_VECTOR vec) { vec->is_scaled = LIS_FALSE; return LIS_SUCCESS; }
+
 LIS_INT lis_vector_is_null(LIS_VECTOR v)
 {
     return (v == NULL || !lis_is_malloc(v) || v->status == LIS_VECTOR_NULL) ? LIS_TRUE : LIS_FALSE;
