@@ -246,6 +246,10 @@ int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *d_order,
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
 /* d_ws[i] = d_x[d_export_index[i]] */
 int lisb200_gather(int count, const int *d_index, const double *d_x, double *d_out, void *stream);
+/* the reverse step behind lis_matvech on a row-partitioned matrix (lis_reduce, src/matrix/lis_matrix_mpi.c:958-996):
+ * d_y[d_index[i]] += d_src[i] for one neighbour's segment of the export list (no index twice inside a segment);
+ * segments are applied one launch after the other in rank order, so the sums have a fixed order */
+int lisb200_scatter_add(int count, const int *d_index, const double *d_src, double *d_y, void *stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ extern LIS_MATVEC_FUNC LIS_MATVEC;
 
 /* halo exchange before a row-partitioned SpMV (reference: src/matrix/lis_matrix_mpi.c:834) */
 LIS_INT lis_send_recv(LIS_COMMTABLE commtable, LIS_SCALAR x[]);
+LIS_INT lis_reduce(LIS_COMMTABLE commtable, LIS_SCALAR x[]);      /* the reverse step: x[n..np) back to the owners, added (lis_matrix_mpi.c:958) */
 
 /* ---- matrix internals the solver layer uses ---- */
 LIS_INT lis_matrix_split(LIS_MATRIX A);

@@ -629,6 +629,99 @@ static LIS_INT halo_exchange_raw(LIS_COMMTABLE t, LIS_INT n, double *x)
     return err;
 }
 
+/* ------------------------------------------------------------------ reverse halo reduction (lis_reduce,
+ * src/matrix/lis_matrix_mpi.c:958-996): after y = A_loc^T x the entries y[n .. np) belong to rows other ranks
+ * own.  Each goes back to its owner, which adds what it receives to y[export_index[..]], neighbour after
+ * neighbour in rank order.  The segment rank k returns to me is its import segment for owner me: as long as my
+ * export segment for k and in the same order. */
+static int peer_import_offset(LIS_COMMTABLE t, int k, int owner)          /* import_ptr[owner] of rank k, from the export tables */
+{
+    const int np_ = t->nranks;
+    int off = 0;
+    for (int j = 0; j < owner; j++) off += t->peer_export_ptr[j * (np_ + 1) + k + 1] - t->peer_export_ptr[j * (np_ + 1) + k];
+    return off;
+}
+
+static LIS_INT halo_reduce_apply(LIS_COMMTABLE t, double *y)
+{
+    cudaStream_t st = (cudaStream_t)lisd_stream();
+    for (int k = 0; k < t->nranks; k++) {
+        const int ne = t->export_ptr[k + 1] - t->export_ptr[k];
+        if (k == t->rank || ne == 0) continue;
+        lisd_mark_busy();
+        LIS_INT err = lisd_check(lisb200_scatter_add(ne, t->d_export_index + t->export_ptr[k], t->d_ws + t->export_ptr[k], y, st), "halo reduce");
+        if (err) return err;
+    }
+    return LIS_SUCCESS;
+}
+
+static LIS_INT halo_reduce_staged(LIS_COMMTABLE t, LIS_INT n, double *y)
+{
+    const int np_ = t->nranks, me = t->rank;
+    size_t lens[LISC_MAXR], offs[LISC_MAXR], total = 0;
+    for (int k = 0; k < np_; k++) { lens[k] = sizeof(double) * (size_t)peer_import_offset(t, k, np_); offs[k] = total; total += lens[k]; }
+    const size_t need = total + sizeof(double) * ((size_t)t->n_export + (size_t)t->n_import + 2);
+    if (need > t->h_stage_len) {
+        free(t->h_stage);
+        t->h_stage = (double *)malloc(need);
+        t->h_stage_len = t->h_stage ? need : 0;
+        if (!t->h_stage) { LIS_SETERR_MEM(need); return LIS_OUT_OF_MEMORY; }
+    }
+    double *all = t->h_stage, *mine = (double *)((char *)t->h_stage + total), *back = mine + t->n_import + 1;
+    LIS_INT err = t->n_import ? lisd_download(mine, y + n, sizeof(double) * (size_t)t->n_import) : lisd_sync();
+    if (err) return err;
+    err = shm_allgatherv(mine, all, lens, offs);
+    if (err) return err;
+    for (int k = 0; k < np_; k++) {
+        const int ne = t->export_ptr[k + 1] - t->export_ptr[k];
+        if (k == me || ne == 0) continue;
+        memcpy(back + t->export_ptr[k], (const double *)((const char *)all + offs[k]) + peer_import_offset(t, k, me), sizeof(double) * (size_t)ne);
+    }
+    if (t->n_export) { err = lisd_upload(t->d_ws, back, sizeof(double) * (size_t)t->n_export); if (err) return err; }
+    return halo_reduce_apply(t, y);
+}
+
+LIS_INT lisd_halo_reduce_raw(LIS_MATRIX A, double *d_y)
+{
+    LIS_COMMTABLE t = A->commtable;
+    const LIS_INT n = A->n;
+    if (t == NULL || g.nranks == 1) return LIS_SUCCESS;
+    if (!g.nccl_ok) return halo_reduce_staged(t, n, d_y);
+    cudaStream_t st = (cudaStream_t)lisd_stream();
+    LIS_INT err = LIS_SUCCESS;
+    /* the halo part of y is contiguous and already grouped by owner; it goes through the plain device buffer
+     * (vector storage is managed memory, which NCCL never sees) */
+    if (t->n_import) {
+        lisd_mark_busy();
+        err = lisd_check((int)cudaMemcpyAsync(t->d_wr, d_y + n, sizeof(double) * (size_t)t->n_import, cudaMemcpyDeviceToDevice, st), "halo reduce pack");
+        if (err) return err;
+    }
+    err = nccl_check(g.GroupStart(), "ncclGroupStart");
+    if (err) return err;
+    for (int k = 0; k < t->nranks; k++) {
+        if (k == t->rank) continue;
+        const int ne = t->export_ptr[k + 1] - t->export_ptr[k], ni = t->import_ptr[k + 1] - t->import_ptr[k];
+        if (ni) { err = nccl_check(g.Send(t->d_wr + t->import_ptr[k], (size_t)ni, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclSend"); if (err) { g.GroupEnd(); return err; } }
+        if (ne) { err = nccl_check(g.Recv(t->d_ws + t->export_ptr[k], (size_t)ne, LISC_NCCL_DOUBLE, k, g.comm, st), "ncclRecv"); if (err) { g.GroupEnd(); return err; } }
+    }
+    lisd_mark_busy();
+    err = nccl_check(g.GroupEnd(), "ncclGroupEnd");
+    if (err) return err;
+    return halo_reduce_apply(t, d_y);
+}
+
+/* public seam of the reference (src/matrix/lis_matrix_mpi.c:958): x has np entries */
+LIS_INT lis_reduce(LIS_COMMTABLE commtable, LIS_SCALAR x[])
+{
+    if (commtable == NULL || g.nranks == 1) return LIS_SUCCESS;
+    struct LIS_MATRIX_STRUCT fake;
+    memset(&fake, 0, sizeof(fake));
+    fake.commtable = commtable; fake.n = commtable->n;
+    LIS_INT err = lisd_halo_reduce_raw(&fake, x);
+    if (err) return err;
+    return lisd_sync();
+}
+
 LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x) { return halo_exchange_raw(A->commtable, A->n, x->value); }
 LIS_INT lisd_halo_exchange_raw(LIS_MATRIX A, double *d_x) { return halo_exchange_raw(A->commtable, A->n, d_x); }
 

@@ -582,6 +582,19 @@ LIS_INT lis_b200_matvec_host_plan(LIS_MATRIX A, LIS_INT cap, LIS_INT *rows, LIS_
  * so A^T in CSR through the ordinary (gather) CSR kernels adds the same products in the same
  * order.  Split matrices: y = D x, then all of L's contributions, then all of U's (:170-199) ==
  * the split kernel on (D, L^T, U^T).  CSC storage already is the CSR of A^T. */
+/* n rows, ncols columns (ncols = np on a row-partitioned matrix: the halo columns become rows n..np of the
+ * transpose, whose sums go back to their owners afterwards) */
+static LIS_INT transposed_upload_cols(lisd_csr *dst, LIS_INT n, LIS_INT ncols, const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
+{
+    LIS_INT *tp, *ti;
+    LIS_SCALAR *tv;
+    LIS_INT err = lis_host_transpose(n, ncols, ptr, idx, val, &tp, &ti, &tv);
+    if (err) return err;
+    err = csr_upload(dst, (int)ncols, tp, ti, tv);
+    lis_free2(3, tp, ti, tv);
+    return err;
+}
+
 static LIS_INT transposed_upload(lisd_csr *dst, LIS_INT n, const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
 {
     LIS_INT *tp, *ti;
@@ -597,11 +610,36 @@ LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
 {
     LIS_INT err = lisd_require("lis_matvech");
     if (err) return err;
-    if (A->nprocs > 1) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech is single-process only (the reverse halo reduction is outside the hot path)\n");
-        return LIS_ERR_NOT_IMPLEMENTED;
-    }
     if (x == y || x->value == y->value) { LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvech: x and y must not alias\n"); return LIS_ERR_ILL_ARG; }
+    if (A->nprocs > 1 && A->commtable) {
+        /* row-partitioned: y[0..np) = A_loc^T x with the halo columns as extra rows, then lis_reduce sends those
+         * sums to their owners (src/matvec/lis_matvec.c:199-205 + lis_matrix_mpi.c:958).  CSR, unsplit. */
+        if (A->matrix_type != LIS_MATRIX_CSR || A->is_splited) {
+            LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "lis_matvech on a row-partitioned matrix: unsplit CSR only\n");
+            return LIS_ERR_NOT_IMPLEMENTED;
+        }
+        lisd_matrix *Mp;
+        err = lisd_matrix_get(A, &Mp);
+        if (err) return err;
+        if (!Mp->has_t) {
+            err = transposed_upload_cols(&Mp->csrT, A->n, A->np, A->ptr, A->index, A->value);
+            if (err) return err;
+            Mp->has_t = 1;
+        }
+        err = vec_reserve(y, (size_t)A->np + (size_t)A->pad_comm);
+        if (!err) err = lisd_vec_device(x);
+        if (!err) err = lisd_vec_device(y);
+        if (err) return err;
+        int rc;
+        if (Mp->csrT.tma_rows)
+            rc = lisb200_spmv_csr_tma(A->np, Mp->csrT.tma_rows, Mp->csrT.tma_tile, Mp->csrT.tma_stages, Mp->csrT.ptr, Mp->csrT.idx, Mp->csrT.val, x->value, y->value, lisd_stream());
+        else
+            rc = lisb200_spmv_csr(A->np, Mp->csrT.ptr, Mp->csrT.idx, Mp->csrT.val, x->value, y->value, lisd_stream());
+        lisd_mark_busy();
+        err = lisd_check(rc, "lis_matvech");
+        if (err) return err;
+        return lisd_halo_reduce_raw(A, y->value);
+    }
     if (A->is_splited && A->matrix_type != LIS_MATRIX_CSR) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
     lisd_matrix *M;
     err = lisd_matrix_get(A, &M);

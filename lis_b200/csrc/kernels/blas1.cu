@@ -181,6 +181,11 @@ struct BicgstabPF {     // p = r + beta*(p + nomega*v): axpy(-omega,v,p) then xp
         reinterpret_cast<double2 *>(p)[i] = pv;
     }
 };
+struct ScatterAddF {        // y[idx[i]] += src[i]; idx holds no value twice (one neighbour's export list)
+    const int *idx; const double *src; double *y;
+    __device__ void one(int i) const { const int k = idx[i]; y[k] = add(y[k], src[i]); }
+    __device__ void vec2(int i) const { one(2 * i); one(2 * i + 1); }
+};
 struct GatherF {
     const int *idx; const double *x; double *out;
     __device__ void one(int i) const { out[i] = x[idx[i]]; }
@@ -566,6 +571,8 @@ extern "C" int lisb200_swap(int n, double *x, double *y, void *s)
 { return launch_ew(n, SwapF{x, y}, aligned16(x) && aligned16(y), s); }
 extern "C" int lisb200_gather(int count, const int *idx, const double *x, double *out, void *s)
 { return launch_ew(count, GatherF{idx, x, out}, false, s); }
+extern "C" int lisb200_scatter_add(int count, const int *idx, const double *src, double *y, void *s)
+{ return launch_ew(count, ScatterAddF{idx, src, y}, false, s); }
 
 extern "C" int lisb200_reduce(int kind, int n, const double *x, const double *y,
                               double *partial, unsigned int *counter, double *result, void *stream)

@@ -124,6 +124,7 @@ int lisb200_reciprocal(int n, double *x, void *s) { (void)s; orc_reciprocal(n, x
 int lisb200_shift(int n, double g, double *x, void *s) { (void)s; orc_shift(n, g, x); return 0; }
 int lisb200_swap(int n, double *x, double *y, void *s) { (void)s; for (int i = 0; i < n; i++) { double t = x[i]; x[i] = y[i]; y[i] = t; } return 0; }
 int lisb200_gather(int c, const int *idx, const double *x, double *out, void *s) { (void)s; for (int i = 0; i < c; i++) out[i] = x[idx[i]]; return 0; }
+int lisb200_scatter_add(int c, const int *idx, const double *src, double *y, void *s) { (void)s; for (int i = 0; i < c; i++) y[idx[i]] += src[i]; return 0; }
 
 int lisb200_reduce(int kind, int n, const double *x, const double *y, double *partial, unsigned int *counter, double *result, void *s)
 {

@@ -222,6 +222,22 @@ def main():
             assert L.shim_mv_dot_xy(h, C.byref(d)) == 0
             assert abs(d.value - float(np.dot(x, y_full))) <= 1e-9 * abs(float(np.dot(np.abs(x), np.abs(y_full))))
             if fmt == "csr":
+                # y = A^T x: local transposed product with the halo columns as extra rows, their sums sent back to the
+                # owners and added in rank order (lis_reduce) -- against the one-process product of the transposed matrix
+                import scipy.sparse as sp
+                AT = sp.csr_matrix((val, idx, ptr), shape=(gn, gn)).T.tocsr()
+                yt_full = AT @ x
+                scale_t = np.abs(AT) @ np.abs(x)
+                for rep in range(2):
+                    assert L.shim_mv_matvech(h) == 0
+                ytl = np.zeros(nl)
+                assert L.shim_mv_get_y_local(h, ytl) == 0
+                assert np.all(np.abs(ytl - yt_full[is_:ie]) <= 1e-14 * scale_t[is_:ie] + 1e-300), f"rank {rank} matvech"
+                assert L.shim_mv_matvec(h) == 0                      # y back to A x for the dot check below
+                xl = np.zeros(nl); oi = np.zeros(4, np.int32); od = np.zeros(4); rh = np.zeros(5000)
+                rc = L.shim_mv_solve_b(h, b"-i bicg -p jacobi", np.ascontiguousarray(bvec[is_:ie]), xl, oi, od, rh, 5000)
+                assert rc == 0 and oi[1] == 0 and np.abs(xl - 1.0).max() < 1e-8, ("bicg", rc, oi)
+                result["bicg"] = int(oi[0])
                 for opts, solver, pre in (("-i cg -p jacobi", "cg", "jacobi"), ("-i bicgstab -p jacobi", "bicgstab", "jacobi"),
                                           ("-i gmres -restart 20 -p none", "gmres", "none"), ("-i cg -p ssor", "cg", "ssor")):
                     xl = np.zeros(nl); oi = np.zeros(4, np.int32); od = np.zeros(4); rh = np.zeros(5000)

@@ -642,6 +642,7 @@ EXPORT int shim_mv_get_y_local(int h, double *y_local)
     return (int)lis_vector_get_values(y, y->is, y->n, y_local);
 }
 EXPORT int shim_mv_matvec(int h) { return (int)lis_matvec(g_mv[h].A, g_mv[h].x, g_mv[h].y); }
+EXPORT int shim_mv_matvech(int h) { return (int)lis_matvech(g_mv[h].A, g_mv[h].x, g_mv[h].y); }
 EXPORT int shim_mv_dot_xy(int h, double *out) { LIS_SCALAR s = 0; LIS_INT e = lis_vector_dot(g_mv[h].x, g_mv[h].y, &s); *out = s; return (int)e; }
 
 EXPORT int shim_mv_step_e2e(int h, double *host_x, double *host_y)
