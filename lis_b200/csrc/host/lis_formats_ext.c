@@ -413,9 +413,8 @@ typedef struct { LIS_INT r, c; LIS_SCALAR v; } slot_t;
 /* walks every stored slot of A in accumulation order; visit() gets (row, column, value) */
 typedef void (*visit_fn)(void *ctx, LIS_INT r, LIS_INT c, LIS_SCALAR v);
 
-static int g_walk_msr_offdiag_only = 0;
-
-static void walk(LIS_MATRIX A, visit_fn visit, void *ctx)
+/* msr_offdiag_only: leave MSR's diagonal slots out (the transposed mirror keeps them apart) */
+static void walk_ex(LIS_MATRIX A, visit_fn visit, void *ctx, int msr_offdiag_only)
 {
     const LIS_INT n = A->n;
     switch (A->matrix_type) {
@@ -449,7 +448,7 @@ static void walk(LIS_MATRIX A, visit_fn visit, void *ctx)
     }
     case LIS_MATRIX_MSR:
         for (LIS_INT i = 0; i < n; i++) {
-            if (!g_walk_msr_offdiag_only) visit(ctx, i, i, A->value[i]);
+            if (!msr_offdiag_only) visit(ctx, i, i, A->value[i]);
             for (LIS_INT j = A->index[i]; j < A->index[i + 1]; j++) visit(ctx, i, A->index[j], A->value[j]);
         }
         break;
@@ -483,6 +482,8 @@ static void walk(LIS_MATRIX A, visit_fn visit, void *ctx)
     default: break;
     }
 }
+
+static void walk(LIS_MATRIX A, visit_fn visit, void *ctx) { walk_ex(A, visit, ctx, 0); }
 
 typedef struct { LIS_INT *ptr, *fill, *index; LIS_SCALAR *value; int keep_zeros, msr; } fill_ctx;
 
@@ -565,17 +566,15 @@ LIS_INT lis_host_transposed_rows(LIS_MATRIX A, LIS_INT **ptr_out, LIS_INT **inde
     t.ptr = (LIS_INT *)tracked((size_t)n + 1, sizeof(LIS_INT), "lis_host_transposed_rows::ptr");
     if (t.ptr == NULL) { LIS_SETERR_MEM(n); return LIS_OUT_OF_MEMORY; }
     memset(t.ptr, 0, ((size_t)n + 1) * sizeof(LIS_INT));
-    g_walk_msr_offdiag_only = 1;
-    walk(A, tr_count, &t);
+    walk_ex(A, tr_count, &t, 1);
     for (LIS_INT i = 0; i < n; i++) t.ptr[i + 1] += t.ptr[i];
     const LIS_INT nnz = t.ptr[n];
     t.index = (LIS_INT *)tracked((size_t)nnz, sizeof(LIS_INT), "lis_host_transposed_rows::index");
     t.value = (LIS_SCALAR *)tracked((size_t)nnz, sizeof(LIS_SCALAR), "lis_host_transposed_rows::value");
     t.fill = (LIS_INT *)malloc(((size_t)n + 1) * sizeof(LIS_INT));
-    if (!t.index || !t.value || !t.fill) { g_walk_msr_offdiag_only = 0; lis_free2(3, t.ptr, t.index, t.value); free(t.fill); LIS_SETERR_MEM(nnz); return LIS_OUT_OF_MEMORY; }
+    if (!t.index || !t.value || !t.fill) { lis_free2(3, t.ptr, t.index, t.value); free(t.fill); LIS_SETERR_MEM(nnz); return LIS_OUT_OF_MEMORY; }
     memcpy(t.fill, t.ptr, ((size_t)n + 1) * sizeof(LIS_INT));
-    walk(A, tr_fill, &t);
-    g_walk_msr_offdiag_only = 0;
+    walk_ex(A, tr_fill, &t, 1);
     free(t.fill);
     *ptr_out = t.ptr; *index_out = t.index; *value_out = t.value;
     return LIS_SUCCESS;
