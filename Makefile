@@ -18,7 +18,7 @@ HOBJ     := $(patsubst lis_b200/csrc/host/%.c,$(OBJ)/h_%.o,$(HSRC))
 # against include/ + liblis_b200.so (drop-in check).  Only where the reference tree exists; the
 # binaries travel to the GPU box with the snapshot.
 REF      ?= /root/reference
-DRIVERS  := spmvtest1 spmvtest2 spmvtest2b spmvtest3 spmvtest3b spmvtest4 spmvtest5 test1 test2 test2b test3 test3b test3c test4 test5 etest1 etest2 etest3 etest4 etest5 etest5b etest6 etest7 test6 test7
+DRIVERS  := spmvtest1 spmvtest2 spmvtest2b spmvtest3 spmvtest3b spmvtest4 spmvtest5 test1 test2 test2b test3 test3b test3c test4 test5 etest1 etest2 etest3 etest4 etest5 etest5b etest6 etest7 test6 test7 getest1 getest5 getest5b
 DRVBIN   := $(patsubst %,$(OUT)/drivers/%,$(DRIVERS))
 
 .PHONY: all clean drivers

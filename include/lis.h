@@ -589,6 +589,7 @@ LIS_INT lis_esolver_work_destroy(LIS_ESOLVER esolver);
 LIS_INT lis_esolver_set_option(char *text, LIS_ESOLVER esolver);
 LIS_INT lis_esolver_set_optionC(LIS_ESOLVER esolver);
 LIS_INT lis_esolve(LIS_MATRIX A, LIS_VECTOR x, LIS_SCALAR *evalue0, LIS_ESOLVER esolver);
+LIS_INT lis_gesolve(LIS_MATRIX A, LIS_MATRIX B, LIS_VECTOR x, LIS_SCALAR *evalue0, LIS_ESOLVER esolver);   /* B must be NULL: standard problems only */
 LIS_INT lis_esolver_get_iter(LIS_ESOLVER esolver, LIS_INT *iter);
 LIS_INT lis_esolver_get_iterex(LIS_ESOLVER esolver, LIS_INT *iter, LIS_INT *iter_double, LIS_INT *iter_quad);
 LIS_INT lis_esolver_get_time(LIS_ESOLVER esolver, double *time);

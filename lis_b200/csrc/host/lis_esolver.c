@@ -1200,3 +1200,14 @@ LIS_INT lis_esolve(LIS_MATRIX A, LIS_VECTOR x, LIS_SCALAR *evalue0, LIS_ESOLVER 
     esolver->x = NULL;
     return LIS_SUCCESS;
 }
+
+/* The reference's lis_esolve is lis_gesolve(A, NULL, ...) (src/esolver/lis_esolver.c:263-282).  The generalized
+ * problem A x = lambda B x (its eight g-solvers) is not carried over: B must be NULL. */
+LIS_INT lis_gesolve(LIS_MATRIX A, LIS_MATRIX B, LIS_VECTOR x, LIS_SCALAR *evalue0, LIS_ESOLVER esolver)
+{
+    if (B != NULL) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "generalized eigenproblems (A x = lambda B x) are not available; pass B = NULL for the standard problem\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    return lis_esolve(A, x, evalue0, esolver);
+}
