@@ -42,7 +42,9 @@ def test_single_gpu_flow(built):
     assert d["e2e"]["h2d_bytes_per_step"] == 8 * 12 ** 3
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     for k in ("ell", "dia", "jad", "bsr"):
-        assert d["extra"][f"{k}_nrm2_vs_csr_rel"] == 0.0 and f"{k}_convert_device_s" in d["extra"], k
+        # BSR adds a row's products block by block in first-seen block order, not in CSR order: with the random x of
+        # this leg ||y|| may differ from the CSR run in the last bit (seen once in ~15 runs); the others follow CSR order
+        assert d["extra"][f"{k}_nrm2_vs_csr_rel"] <= (1e-14 if k == "bsr" else 0.0) and f"{k}_convert_device_s" in d["extra"], k
     assert "ell_convert_host_s" in d["extra"] and d["cpu_baseline"]["kind"] == "reference"
 
 
