@@ -236,10 +236,14 @@ static LIS_INT ilut_keep(ilu_rows *R, LIS_INT count, LIS_INT lfil, const LIS_INT
     return LIS_SUCCESS;
 }
 
-static LIS_INT ilut_factor(LIS_MATRIX A, LIS_SCALAR tol, LIS_SCALAR rate, lisd_ilu *F, LIS_SCALAR *d)
+/* nb > 1: the OpenMP build's variant (lis_precon_ilut.c:105-362) -- every thread factors its own diagonal block
+ * (couplings that leave it are skipped, the row norm is taken over the block's entries only) and the fill cap
+ * is int(nnz/(2n)) * rate, truncated BEFORE the multiplication there. */
+static LIS_INT ilut_factor(LIS_MATRIX A, LIS_SCALAR tol, LIS_SCALAR rate, int nb, lisd_ilu *F, LIS_SCALAR *d)
 {
     const LIS_INT n = A->n;
-    const LIS_INT lfil = n > 0 ? (LIS_INT)(((double)A->ptr[n] / (2.0 * n)) * rate) : 0;
+    const LIS_INT lfil = n <= 0 ? 0 : nb > 1 ? (LIS_INT)((double)(LIS_INT)((double)A->ptr[n] / (2.0 * n)) * rate)
+                                             : (LIS_INT)(((double)A->ptr[n] / (2.0 * n)) * rate);
     LIS_INT err = LIS_OUT_OF_MEMORY;
     LIS_INT *where = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1));       /* column -> slot (lower: 0.., diagonal: -2, upper: n + k), -1 absent */
     LIS_INT *lcol = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1)), *ucol = (LIS_INT *)malloc(sizeof(LIS_INT) * (size_t)(n + 1));
@@ -251,17 +255,24 @@ static LIS_INT ilut_factor(LIS_MATRIX A, LIS_SCALAR tol, LIS_SCALAR rate, lisd_i
     F->U.ptr = (LIS_INT *)calloc((size_t)n + 1, sizeof(LIS_INT));
     if (!where || !lcol || !ucol || !sel || !lval || !uval || !keys || !done || !F->L.ptr || !F->U.ptr) { LIS_SETERR_MEM(n); goto out; }
     for (LIS_INT i = 0; i < n; i++) where[i] = -1;
-    for (LIS_INT i = 0; i < n; i++) {
+    for (int blk = 0; blk < nb; blk++) {
+    LIS_INT is, ie;
+    LIS_GET_ISIE(blk, nb, n, is, ie);
+    for (LIS_INT i = is; i < ie; i++) {
         LIS_REAL tnorm = 0;
-        LIS_INT nl = 0, nu = 0;
+        LIS_INT nl = 0, nu = 0, cnt = 0;
         LIS_SCALAR wd = 0;
-        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) tnorm += fabs(A->value[j]);
-        tnorm = tnorm / (double)(A->ptr[i + 1] - A->ptr[i]);
+        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
+            if (A->index[j] < is || A->index[j] >= ie) continue;
+            tnorm += fabs(A->value[j]);
+            cnt++;
+        }
+        tnorm = tnorm / (double)(nb > 1 ? cnt : A->ptr[i + 1] - A->ptr[i]);
         const LIS_REAL tolnorm = tol * tnorm;
         where[i] = -2;
         for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
             const LIS_INT c = A->index[j];
-            if (c >= n) continue;
+            if (c < is || c >= ie) continue;
             /* a column stored twice overwrites the slot map like the reference's iw[] does: both copies stay in the list */
             if (c < i) { lcol[nl] = c; lval[nl] = A->value[j]; where[c] = nl; done[nl] = 0; nl++; }
             else if (c == i) wd = A->value[j];
@@ -304,6 +315,7 @@ static LIS_INT ilut_factor(LIS_MATRIX A, LIS_SCALAR tol, LIS_SCALAR rate, lisd_i
         if (ilut_keep(&F->L, nl, lfil, lcol, lval, keys, sel) || ilut_keep(&F->U, nu, lfil, ucol, uval, keys, sel)) { LIS_SETERR_MEM(nl + nu); goto out; }
         F->L.ptr[i + 1] = (LIS_INT)F->L.nnz;
         F->U.ptr[i + 1] = (LIS_INT)F->U.nnz;
+    }
     }
     if (F->L.idx == NULL) { F->L.idx = (LIS_INT *)calloc(1, sizeof(LIS_INT)); F->L.val = (LIS_SCALAR *)calloc(1, sizeof(LIS_SCALAR)); }
     if (F->U.idx == NULL) { F->U.idx = (LIS_INT *)calloc(1, sizeof(LIS_INT)); F->U.val = (LIS_SCALAR *)calloc(1, sizeof(LIS_SCALAR)); }
@@ -366,8 +378,7 @@ LIS_INT lis_host_ilu_create(LIS_SOLVER solver, LIS_PRECON precon)
     LIS_SCALAR *d = NULL;
     if (!err) { d = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(A->n > 0 ? A->n : 1)); if (!d) { LIS_SETERR_MEM(A->n * 8); err = LIS_OUT_OF_MEMORY; } }
     if (!err && solver->options[LIS_OPTIONS_PRECON] == LIS_PRECON_TYPE_ILUT) {
-        if (nb > 1) { LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "ILUT: the per-thread block variant (-omp_num_threads > 1) is not available\n"); err = LIS_ERR_NOT_IMPLEMENTED; }
-        else err = ilut_factor(A, solver->params[LIS_PARAMS_DROP - LIS_OPTIONS_LEN], solver->params[LIS_PARAMS_RATE - LIS_OPTIONS_LEN], F, d);
+        err = ilut_factor(A, solver->params[LIS_PARAMS_DROP - LIS_OPTIONS_LEN], solver->params[LIS_PARAMS_RATE - LIS_OPTIONS_LEN], nb, F, d);
     } else {
         if (!err) err = ilu_symbolic(A, solver->options[LIS_OPTIONS_FILL], nb, F);
         if (!err) err = ilu_numeric(A, nb, F, d);

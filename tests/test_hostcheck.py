@@ -353,7 +353,7 @@ def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads)
     try:
         for name, (ptr, idx, val) in list(systems()) + [("p27", H.poisson3d_27pt(6, 5, 4))]:
             b = H.rand_vec(len(ptr) - 1, 5)
-            for pre in ("ilu", "ilu -ilu_fill 1", "ilu -ilu_fill 3", "ssor", "ssor -ssor_omega 1.3"):
+            for pre in ("ilu", "ilu -ilu_fill 1", "ilu -ilu_fill 3", "ssor", "ssor -ssor_omega 1.3", "ilut", "ilut -iluc_drop 0.001 -iluc_rate 0.7"):
                 for tr in (False, True):
                     g = hc.psolve(ptr, idx, val, b, "-p " + pre, transposed=tr)
                     r = ref.psolve(ptr, idx, val, b, "-p " + pre, transposed=tr)
