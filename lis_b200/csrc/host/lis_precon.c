@@ -199,10 +199,96 @@ LIS_INT lis_psolve_hybrid(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
     return lisd_copy(ps->x, x);
 }
 
+/* -p is (I+S, src/precon/lis_precon_is.c:54-100 and :417-460) at its default level with a non-stationary solver:
+ * M^-1 = I - alpha*S, S = the first (is_m + 1) stored entries of every row of the strict upper part.  The matrix is
+ * brought to CSR and split like there (so the products switch to the D + L + U order); S is kept as a small CSR
+ * matrix of its own, so the apply is one product on the CSR kernel and one axpyz:
+ *   y = x - alpha * (S x)     ->  t = S x ;  y = (-alpha)*t + x      (same bits: the sign change is exact)
+ * The transposed apply uses S^T through lis_matvech.  Level 0 (which rewrites the system as (I+S)A) and the
+ * stationary solvers are not carried over. */
+static LIS_INT create_is(LIS_SOLVER solver, LIS_PRECON precon)
+{
+    LIS_MATRIX A = solver->A;
+    const LIS_INT nsol = solver->options[LIS_OPTIONS_SOLVER];
+    LIS_INT err;
+    const LIS_INT st = solver->options[LIS_OPTIONS_STORAGE];
+    if (solver->options[LIS_OPTIONS_ISLEVEL] == 0 || (nsol >= LIS_SOLVER_JACOBI && nsol <= LIS_SOLVER_SOR) || A->nprocs > 1 ||
+        (st > 0 && st != LIS_MATRIX_CSR)) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-p is: only -is_level != 0 with a Krylov solver, CSR storage and one process is available\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    if (A->matrix_type != LIS_MATRIX_CSR) {            /* the reference converts the solver's matrix to CSR in place here */
+        LIS_MATRIX B;
+        err = lis_matrix_duplicate(A, &B);
+        if (err) return err;
+        lis_matrix_set_type(B, LIS_MATRIX_CSR);
+        err = lis_matrix_convert(A, B);
+        if (err) { lis_matrix_destroy(B); return err; }
+        lis_host_matrix_adopt(A, B);
+    }
+    err = lis_matrix_split(A);
+    if (err) return err;
+    precon->work = (LIS_VECTOR *)lis_calloc(sizeof(LIS_VECTOR), "lis_precon_create_is::work");
+    if (precon->work == NULL) { LIS_SETERR_MEM(sizeof(LIS_VECTOR)); return LIS_OUT_OF_MEMORY; }
+    err = lis_vector_duplicate(A, &precon->work[0]);
+    if (!err) precon->worklen = 1;
+    return err;
+}
+
+/* S is cut out of the split matrix at the first apply: lis_solve scales the system to a unit diagonal AFTER the
+ * preconditioner is created (src/solver/lis_solver.c:613-641), and the reference's apply reads A->U as it is then */
+static LIS_INT is_build(LIS_SOLVER solver, LIS_PRECON precon)
+{
+    LIS_MATRIX A = solver->A, S = NULL;
+    LIS_INT err;
+    if (A->matrix_type != LIS_MATRIX_CSR || !A->is_splited || A->U == NULL) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-p is needs the solver's matrix in (split) CSR storage: do not combine it with -storage\n");
+        return LIS_ERR_NOT_IMPLEMENTED;
+    }
+    const LIS_INT n = A->n, m = solver->options[LIS_OPTIONS_M] + 1;
+    LIS_INT nnz = 0, *ptr, *index;
+    LIS_SCALAR *value;
+    for (LIS_INT i = 0; i < n; i++) { const LIS_INT len = A->U->ptr[i + 1] - A->U->ptr[i]; nnz += len < m ? len : m; }
+    err = lis_matrix_malloc_csr(n, nnz, &ptr, &index, &value);
+    if (err) return err;
+    ptr[0] = 0;
+    for (LIS_INT i = 0, k = 0; i < n; i++) {
+        const LIS_INT len = A->U->ptr[i + 1] - A->U->ptr[i], take = len < m ? len : m;
+        for (LIS_INT j = 0; j < take; j++, k++) { index[k] = A->U->index[A->U->ptr[i] + j]; value[k] = A->U->value[A->U->ptr[i] + j]; }
+        ptr[i + 1] = k;
+    }
+    err = lis_matrix_create(A->comm, &S);
+    if (!err) err = lis_matrix_set_size(S, n, 0);
+    if (!err) err = lis_matrix_set_csr(nnz, ptr, index, value, S);
+    if (err) { lis_free2(3, ptr, index, value); if (S) lis_matrix_destroy(S); return err; }
+    err = lis_matrix_assemble(S);
+    if (err) { lis_matrix_destroy(S); return err; }
+    precon->Ah = S;
+    return LIS_SUCCESS;
+}
+
+LIS_INT lis_psolve_is(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    LIS_PRECON precon = solver->precon;
+    LIS_INT err = precon->Ah ? LIS_SUCCESS : is_build(solver, precon);
+    if (!err) err = lisd_matvec(precon->Ah, b, precon->work[0]);
+    if (err) return err;
+    return lisd_axpyz(-solver->params[LIS_PARAMS_ALPHA - LIS_OPTIONS_LEN], precon->work[0], b, x);
+}
+
+LIS_INT lis_psolveh_is(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
+{
+    LIS_PRECON precon = solver->precon;
+    LIS_INT err = precon->Ah ? LIS_SUCCESS : is_build(solver, precon);
+    if (!err) err = lisd_matvech(precon->Ah, b, precon->work[0]);
+    if (err) return err;
+    return lisd_axpyz(-solver->params[LIS_PARAMS_ALPHA - LIS_OPTIONS_LEN], precon->work[0], b, x);
+}
+
 static LIS_INT create_unsupported(LIS_SOLVER solver, LIS_PRECON precon)
 {
     (void)solver; (void)precon;
-    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is not available (none, jacobi, ssor, ilu, hybrid and registered ones are)\n");
+    LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "this preconditioner is not available (none, jacobi, ssor, ilu, ilut, hybrid, is and registered ones are)\n");
     return LIS_ERR_NOT_IMPLEMENTED;
 }
 
@@ -223,6 +309,7 @@ LIS_INT lis_precon_create(LIS_SOLVER solver, LIS_PRECON *precon)
         case LIS_PRECON_TYPE_SSOR: err = create_ssor(solver, *precon); break;
         case LIS_PRECON_TYPE_ILU: case LIS_PRECON_TYPE_ILUT: err = lis_host_ilu_create(solver, *precon); break;
         case LIS_PRECON_TYPE_HYBRID: err = create_hybrid(solver, *precon); break;
+        case LIS_PRECON_TYPE_IS: err = create_is(solver, *precon); break;
         default: err = create_unsupported(solver, *precon); break;
         }
         if (!err && type && solver->options[LIS_OPTIONS_ADDS]) {
@@ -255,6 +342,7 @@ LIS_INT lis_precon_destroy(LIS_PRECON precon)
 {
     if (precon) {
         if (precon->is_copy && precon->A) lis_matrix_destroy(precon->A);
+        if (precon->Ah) lis_matrix_destroy(precon->Ah);  /* I+S: the truncated strict upper part */
         if (precon->solver) {                           /* hybrid: the inner solver with its iterate and preconditioner */
             if (precon->solver->x) lis_vector_destroy(precon->solver->x);
             lis_precon_destroy(precon->solver->precon);
@@ -331,6 +419,7 @@ static LIS_INT psolve_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_VE
     case LIS_PRECON_TYPE_SSOR: return lis_psolve_ssor(solver, b, x);
     case LIS_PRECON_TYPE_ILU: case LIS_PRECON_TYPE_ILUT: return lis_psolve_iluk(solver, b, x);
     case LIS_PRECON_TYPE_HYBRID: return lis_psolve_hybrid(solver, b, x);
+    case LIS_PRECON_TYPE_IS: return lis_psolve_is(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg)
             return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolve(solver, b, x);
@@ -354,6 +443,7 @@ static LIS_INT psolveh_type(LIS_INT type, LIS_SOLVER solver, LIS_VECTOR b, LIS_V
     case LIS_PRECON_TYPE_JACOBI: return lis_psolve_jacobi(solver, b, x);
     case LIS_PRECON_TYPE_SSOR: return lis_matrix_solveh(solver->precon->A, b, x, LIS_MATRIX_SSOR);
     case LIS_PRECON_TYPE_ILU: case LIS_PRECON_TYPE_ILUT: return lis_psolveh_iluk(solver, b, x);
+    case LIS_PRECON_TYPE_IS: return lis_psolveh_is(solver, b, x);
     default:
         if (type >= LIS_PRECON_TYPE_USERDEF && type < g_reg_type && g_reg && g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh)
             return g_reg[type - LIS_PRECON_TYPE_USERDEF].psolveh(solver, b, x);

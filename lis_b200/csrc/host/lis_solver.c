@@ -617,7 +617,12 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     /* system scaling (src/solver/lis_solver.c:636-721): the stationary solvers with a preconditioner
      * always work on D^-1 A; -scale jacobi|symm_diag on request (CG turns jacobi into symm_diag to keep
      * the matrix symmetric).  A and b stay scaled afterwards, exactly as there. */
-    if (nsolver >= LIS_SOLVER_JACOBI && nsolver <= LIS_SOLVER_SOR && precon_type != LIS_PRECON_TYPE_NONE) {
+    if (precon_type == LIS_PRECON_TYPE_IS) {
+        /* I+S works on the unit-diagonal system D^-1 A (:613-641) */
+        if (solver->d == NULL) err = lis_vector_duplicate(A, &solver->d);
+        if (!err && !A->is_scaled) err = lis_matrix_scale(A, b, solver->d, LIS_SCALE_JACOBI);
+        else if (!err && !b->is_scaled) err = lis_vector_pmul(b, solver->d, b);
+    } else if (nsolver >= LIS_SOLVER_JACOBI && nsolver <= LIS_SOLVER_SOR && precon_type != LIS_PRECON_TYPE_NONE) {
         if (solver->d == NULL) err = lis_vector_duplicate(A, &solver->d);
         if (!err && !A->is_scaled) err = lis_matrix_scale(A, b, solver->d, LIS_SCALE_JACOBI);
     } else if (scale) {

@@ -343,6 +343,22 @@ def test_ilut_preconditioner_bit_for_bit(hc, ref_serial, opts):
         H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} x")
 
 
+@pytest.mark.parametrize("opts", ["-i cg -p is", "-i bicgstab -p is", "-i gmres -p is -is_alpha 0.5", "-i bicgstab -p is -is_m 1",
+                                  "-i bicgstab -p is -is_m 10 -is_alpha 0.3", "-i bicg -p is"])
+def test_is_preconditioner(hc, ref_serial, opts):
+    """-p is (I+S at its default level, src/precon/lis_precon_is.c): the system is scaled to a unit diagonal, split, and
+    M^-1 = I - alpha*S with S the first is_m+1 strict-upper entries of each row -- one CSR product and one axpyz.
+    Status, iteration count, residual history and solution of the serial reference bit for bit (the transposed apply
+    of BiCG: same iteration count)"""
+    for name, (ptr, idx, val) in (("p7", H.poisson3d_7pt(7, 6, 5)), ("unsym", H.random_csr(400, 6, 17, band=25))):
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        g, r = hc.solve(ptr, idx, val, b, opts + " -maxiter 600"), ref_serial.solve(ptr, idx, val, b, opts + " -maxiter 600")
+        assert g["err"] == r["err"] == 0 and (g["status"], g["iter"]) == (r["status"], r["iter"]), (name, opts, g["err"], g["iter"], r["iter"])
+        if "bicg " not in opts:
+            H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{name} {opts}")
+            H.assert_bits_equal(g["x"], r["x"], f"{name} {opts} x")
+
+
 @pytest.mark.parametrize("threads", [1, 2, 3, 8])
 def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads):
     """one application of M^-1 / M^-H for ILU(k) and SSOR against the reference: the serial build
@@ -365,7 +381,7 @@ def test_ilu_and_transposed_sweeps_bit_for_bit(hc, ref_serial, ref_omp, threads)
 def test_unsupported_requests_are_rejected(hc):
     ptr, idx, val = H.poisson1d(30)
     b = np.ones(30)
-    for opts, code in (("-i bicg -p sainv", 5), ("-i bicg -p hybrid", 5), ("-i cg -p hybrid -hybrid_p hybrid", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p saamg -adds true", 5),
+    for opts, code in (("-i bicg -p sainv", 5), ("-i bicg -p hybrid", 5), ("-i cg -p is -storage ell", 5), ("-i cg -p is -is_level 0", 5), ("-i sor -p is", 5), ("-i cg -p hybrid -hybrid_p hybrid", 5), ("-i cg -p iluc", 5), ("-i cg -p ilu -storage bsr", 5), ("-i cg -p saamg -adds true", 5),
                        ("-i cg -scale jacobi -storage bsr", 5), ("-i cg -f quad", 1), ("-i gmres -conv_cond nrm2_b", 1), ("-i jacobi -conv_cond nrm2_b", 1),
                        ("-i gmres -restart -1", 1), ("-i cg -maxiter -3", 1)):
         g = hc.solve(ptr, idx, val, b, opts)
