@@ -40,6 +40,7 @@ test_matvech_and_bicg_in_every_format = G2.test_matvech_and_bicg_in_every_format
 test_ssor_and_stationary_sweeps_in_scalar_formats = G2.test_ssor_and_stationary_sweeps_in_scalar_formats
 test_hybrid_preconditioner = G2.test_hybrid_preconditioner
 test_ilut_preconditioner = G2.test_ilut_preconditioner
+test_is_preconditioner = G2.test_is_preconditioner
 test_gram_schmidt_fused_chain_same_bits = G2.test_gram_schmidt_fused_chain_same_bits
 test_device_conversion_same_arrays_as_host = G2.test_device_conversion_same_arrays_as_host
 test_device_conversion_falls_back_to_host_builder = G2.test_device_conversion_falls_back_to_host_builder

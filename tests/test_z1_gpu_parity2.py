@@ -274,6 +274,17 @@ def test_ilut_preconditioner(b200, ref_serial, opts):
         assert np.abs(g["x"] - 1.0).max() < 1e-8
 
 
+@pytest.mark.parametrize("opts", ["-i bicgstab -p is", "-i gmres -p is -is_alpha 0.5", "-i bicg -p is -is_m 1"])
+def test_is_preconditioner(b200, ref_serial, opts):
+    """-p is on the device kernels (one CSR product with the truncated upper part + axpyz per apply): converges like the
+    serial reference"""
+    for ptr, idx, val in (H.poisson3d_7pt(10, 9, 8), H.random_csr(1500, 7, 404, band=50)):
+        b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(len(ptr) - 1))
+        g, r = b200.solve(ptr, idx, val, b, opts), ref_serial.solve(ptr, idx, val, b, opts)
+        assert g["err"] == r["err"] == 0 and g["status"] == r["status"] == 0 and abs(g["iter"] - r["iter"]) <= max(1, r["iter"] // 10), (opts, g["iter"], r["iter"])
+        assert np.abs(g["x"] - 1.0).max() < 1e-8
+
+
 @pytest.mark.parametrize("fmt", ["ell", "dia", "msr", "jad"])
 def test_ssor_and_stationary_sweeps_in_scalar_formats(b200, ref_serial, fmt):
     """SSOR / Gauss-Seidel / SOR with -storage <fmt>: sweeps on a private CSR copy, products in the format"""
