@@ -96,12 +96,21 @@ void lisd_shutdown(void)
     if (g_ctx.h_scalar) cudaFreeHost(g_ctx.h_scalar);
     if (g_ctx.dev_scalars) cudaFree(g_ctx.dev_scalars);
     if (g_ctx.h_fetch) cudaFreeHost(g_ctx.h_fetch);
-    if (g_ctx.s_aux) { cudaEventDestroy(g_ctx.ev_aux_fork); cudaEventDestroy(g_ctx.ev_aux_join); cudaStreamDestroy(g_ctx.s_aux); }
+    if (g_ctx.s_aux) {
+        cudaStreamSynchronize(g_ctx.s_aux);
+        cudaEventDestroy(g_ctx.ev_aux_fork); cudaEventDestroy(g_ctx.ev_aux_join); cudaStreamDestroy(g_ctx.s_aux);
+        g_ctx.s_aux = NULL; g_ctx.ev_aux_fork = NULL; g_ctx.ev_aux_join = NULL;
+    }
     if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
     if (g_ctx.stage_y) cudaFree(g_ctx.stage_y);
+    g_ctx.stage_x = g_ctx.stage_y = NULL; g_ctx.stage_xn = g_ctx.stage_yn = 0;
     for (int i = 0; i < g_ctx.nev; i++) cudaEventDestroy(g_ctx.ev[i]);
     free(g_ctx.ev);
-    if (g_ctx.s_in) { cudaEventDestroy(g_ctx.ev_fork); cudaEventDestroy(g_ctx.ev_join); cudaStreamDestroy(g_ctx.s_in); cudaStreamDestroy(g_ctx.s_out); }
+    g_ctx.ev = NULL; g_ctx.nev = 0;
+    if (g_ctx.s_in) {
+        cudaEventDestroy(g_ctx.ev_fork); cudaEventDestroy(g_ctx.ev_join); cudaStreamDestroy(g_ctx.s_in); cudaStreamDestroy(g_ctx.s_out);
+        g_ctx.s_in = g_ctx.s_out = NULL;
+    }
     cudaStreamDestroy(g_ctx.stream);
     memset(&g_ctx, 0, sizeof(g_ctx));
 }
@@ -282,8 +291,7 @@ LIS_INT lisd_pipe_staging(size_t xcount, size_t ycount, double **xs, double **ys
 {
     if (xcount > g_ctx.stage_xn) {
         lisd_sync();
-        if (g_ctx.s_aux) { cudaEventDestroy(g_ctx.ev_aux_fork); cudaEventDestroy(g_ctx.ev_aux_join); cudaStreamDestroy(g_ctx.s_aux); }
-    if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
+        if (g_ctx.stage_x) cudaFree(g_ctx.stage_x);
         g_ctx.stage_x = NULL; g_ctx.stage_xn = 0;
         if (cudaMalloc((void **)&g_ctx.stage_x, (xcount + 8) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(xcount * sizeof(double)); return LIS_ERR_OUT_OF_MEMORY; }
         g_ctx.stage_xn = xcount;

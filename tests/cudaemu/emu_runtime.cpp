@@ -11,6 +11,7 @@
 #include <ucontext.h>
 #include <unistd.h>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -301,6 +302,19 @@ static cudaStream_t g_main_stream = nullptr;
 static std::map<cudaStream_t, std::vector<EmuOp>> g_lazy;     /* pending operations per lazy stream */
 static std::map<cudaEvent_t, cudaStream_t> g_event_on;        /* event -> lazy stream it is pending on */
 
+/* Live handles.  Real CUDA has undefined behaviour (in practice: a crash) on a stream or event that
+ * was already destroyed; here every use or second destroy of a dead handle aborts the test. */
+static std::set<cudaStream_t> g_live_streams;
+static std::set<cudaEvent_t> g_live_events;
+static void emu_need_stream(cudaStream_t s, const char *what)
+{
+    if (s != nullptr && !g_live_streams.count(s)) { fprintf(stderr, "cuda_emu: %s on a stream that was destroyed or never created (%p)\n", what, (void *)s); abort(); }
+}
+static void emu_need_event(cudaEvent_t e, const char *what)
+{
+    if (!g_live_events.count(e)) { fprintf(stderr, "cuda_emu: %s on an event that was destroyed or never created (%p)\n", what, (void *)e); abort(); }
+}
+
 static void emu_flush(cudaStream_t s, cudaEvent_t upto)
 {
     auto it = g_lazy.find(s);
@@ -325,27 +339,43 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int)
     static int k = 0;
     *s = (cudaStream_t)(uintptr_t)(0x100 + 16 * ++k);
     if (g_main_stream == nullptr) g_main_stream = *s;
+    g_live_streams.insert(*s);
     return cudaSuccess;
 }
-cudaError_t cudaStreamSynchronize(cudaStream_t s) { emu_flush(s, nullptr); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { emu_need_stream(s, "cudaStreamSynchronize"); emu_flush(s, nullptr); return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { emu_flush_all(); return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { emu_flush(s, nullptr); g_lazy.erase(s); if (s == g_main_stream) g_main_stream = nullptr; return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned int)
+cudaError_t cudaStreamDestroy(cudaStream_t s)
+{
+    if (s == nullptr) { fprintf(stderr, "cuda_emu: cudaStreamDestroy(NULL)\n"); abort(); }
+    emu_need_stream(s, "cudaStreamDestroy");
+    emu_flush(s, nullptr); g_lazy.erase(s); g_live_streams.erase(s);
+    if (s == g_main_stream) g_main_stream = nullptr;
+    return cudaSuccess;
+}
+static cudaError_t emu_wait_event(cudaEvent_t e)
 {
     auto it = g_event_on.find(e);
     if (it != g_event_on.end()) emu_flush(it->second, e);
     return cudaSuccess;
 }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { static int k = 0; *e = (cudaEvent_t)(uintptr_t)(0x100000 + 16 * ++k); return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned int)
+{
+    emu_need_stream(s, "cudaStreamWaitEvent"); emu_need_event(e, "cudaStreamWaitEvent");
+    auto it = g_event_on.find(e);
+    if (it != g_event_on.end()) emu_flush(it->second, e);
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { static int k = 0; *e = (cudaEvent_t)(uintptr_t)(0x100000 + 16 * ++k); g_live_events.insert(*e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
 {
+    emu_need_stream(s, "cudaEventRecord"); emu_need_event(e, "cudaEventRecord");
     auto it = g_event_on.find(e);
     if (it != g_event_on.end()) emu_flush(it->second, e);            /* re-recording: the old one is done with */
     if (emu_is_lazy(s) && !g_lazy[s].empty()) { g_lazy[s].push_back(EmuOp{nullptr, nullptr, 0, e}); g_event_on[e] = s; }
     return cudaSuccess;
 }
-cudaError_t cudaEventSynchronize(cudaEvent_t e) { return cudaStreamWaitEvent(nullptr, e, 0); }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { cudaStreamWaitEvent(nullptr, e, 0); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { emu_need_event(e, "cudaEventSynchronize"); return emu_wait_event(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { emu_need_event(e, "cudaEventDestroy"); emu_wait_event(e); g_live_events.erase(e); return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = emu::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
 cudaError_t cudaFree(void *p) { emu_flush_all(); emu::guarded_free(p); return cudaSuccess; }
@@ -354,14 +384,15 @@ cudaError_t cudaFreeHost(void *p) { emu_flush_all(); emu::guarded_free(p); retur
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int) { *d = h; return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t st)
 {
+    emu_need_stream(st, "cudaMemcpyAsync");
     if (emu_is_lazy(st)) g_lazy[st].push_back(EmuOp{d, s, n, nullptr});
     else memmove(d, s, n);
     return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) { emu_flush_all(); memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { emu_need_stream(st, "cudaMemsetAsync"); memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemPrefetchAsync(const void *, size_t, int, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaMemPrefetchAsync(const void *, size_t, int, cudaStream_t st) { emu_need_stream(st, "cudaMemPrefetchAsync"); return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
 
 }  // extern "C"

@@ -25,13 +25,34 @@
 cudaError_t cudaGetDeviceCount(int *c) { *c = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int d) { (void)d; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int f) { (void)f; *s = (cudaStream_t)0x1; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void)s; return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { (void)s; return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned int f) { (void)s; (void)e; (void)f; return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int f) { (void)f; *e = (cudaEvent_t)0x2; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { (void)e; (void)s; return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { (void)e; return cudaSuccess; }
+/* Streams and events are tracked: using or destroying a handle that is not alive aborts (on a real
+ * device that is undefined behaviour -- a double cudaStreamDestroy took down every rank once). */
+#include <stdio.h>
+#define MOCK_MAXH 4096
+static unsigned char g_stream_live[MOCK_MAXH], g_event_live[MOCK_MAXH];
+static int g_nstream = 0, g_nevent = 0;
+static void mock_need_stream(cudaStream_t s, const char *what)
+{
+    size_t k = (size_t)s;
+    if (s == NULL) return;
+    if (k >= MOCK_MAXH || !g_stream_live[k]) { fprintf(stderr, "mock_device: %s on a dead stream %p\n", what, (void *)s); abort(); }
+}
+static void mock_need_event(cudaEvent_t e, const char *what)
+{
+    size_t k = (size_t)e;
+    if (k >= MOCK_MAXH || !g_event_live[k]) { fprintf(stderr, "mock_device: %s on a dead event %p\n", what, (void *)e); abort(); }
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int f)
+{ (void)f; if (++g_nstream >= MOCK_MAXH) abort(); g_stream_live[g_nstream] = 1; *s = (cudaStream_t)(size_t)g_nstream; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { mock_need_stream(s, "cudaStreamSynchronize"); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s)
+{ if (s == NULL) { fprintf(stderr, "mock_device: cudaStreamDestroy(NULL)\n"); abort(); } mock_need_stream(s, "cudaStreamDestroy"); g_stream_live[(size_t)s] = 0; return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned int f)
+{ (void)f; mock_need_stream(s, "cudaStreamWaitEvent"); mock_need_event(e, "cudaStreamWaitEvent"); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int f)
+{ (void)f; if (++g_nevent >= MOCK_MAXH) abort(); g_event_live[g_nevent] = 1; *e = (cudaEvent_t)(size_t)g_nevent; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { mock_need_event(e, "cudaEventRecord"); mock_need_stream(s, "cudaEventRecord"); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { mock_need_event(e, "cudaEventDestroy"); g_event_live[(size_t)e] = 0; return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int f) { (void)f; return cudaMalloc(p, n); }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
@@ -39,8 +60,8 @@ cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int f) { (void)f; return 
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int f) { (void)f; *d = h; return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind k, cudaStream_t st)
-{ (void)k; (void)st; memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { (void)st; memset(d, v, n); return cudaSuccess; }
+{ (void)k; mock_need_stream(st, "cudaMemcpyAsync"); memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { mock_need_stream(st, "cudaMemsetAsync"); memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemPrefetchAsync(const void *p, size_t n, int dev, cudaStream_t st) { (void)p; (void)n; (void)dev; (void)st; return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
