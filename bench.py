@@ -145,14 +145,6 @@ def bind_to_gpu_numa_node(torch, gpu_index):
 
 
 # ----------------------------------------------------------------------------- matrices
-def poisson7_host(l, m, n, k0=0, k1=None, ktot=None):
-    """test/spmvtest3.c:142-157 rows (then sorted by column, :192-195) for planes [k0,k1) of an
-    l x m x ktot grid... used for the CPU sample; numpy, a few seconds at 256^3."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import harness
-    return harness.poisson3d_7pt(l, m, n, sort=True)
-
-
 def poisson7_device(torch, L, M, N, i0, i1, dev):
     """Rows of planes i in [i0, i1) of the L x M x N grid (global size L*M*N, lexicographic
     ii = i*M*N + j*N + k), sorted by column, global column indices, built with torch on `dev`.
@@ -198,38 +190,131 @@ def host_malloc_array(count, dtype):
     return np.frombuffer(buf, dtype=dtype, count=int(count)), p
 
 
+# ----------------------------------------------------------------------------- workload naming
+def workload_config(grid, world):
+    """The `config` object, identical for the lis_b200 arm and the reference arm at the same N."""
+    n = grid ** 3
+    nnz = 7 * n - 6 * grid * grid
+    if world == 1:
+        return {"workload": f"spmvtest3 {grid}^3 7-pt Poisson, CSR, rows sorted (n={n}, nnz={nnz})",
+                "l2": "inputs (13.9 GB/step) exceed L2 by >100x, no flush between steps", "index": "int32"}
+    L = grid * world
+    nnz_g = 7 * n * world - 2 * (grid * grid + 2 * L * grid)
+    return {"workload": f"spmvtest3 {L}x{grid}x{grid} 7-pt Poisson, CSR, {world} row slabs of {grid}^3 (n={n * world}, nnz={nnz_g})",
+            "l2": "inputs (13.9 GB/step/GPU) exceed L2 by >100x, no flush between steps", "index": "int32 (local numbering + halo)"}
+
+
+_AFFINITY0 = os.sched_getaffinity(0)
+
+
+def host_poisson7(L, grid_l, grid_m, grid_n, i0, i1, sorted_rows):
+    """malloc'ed CSR arrays of planes [i0, i1) from the shim's C generator (rows as spmvtest3.c leaves
+    them when sorted_rows, in test3.c's order otherwise).  Returns (n, nnz, p_ptr, p_idx, p_val)."""
+    L.shim_poisson7.restype = C.c_longlong
+    L.shim_poisson7.argtypes = [C.c_int] * 6 + [C.c_void_p] * 3
+    n = (i1 - i0) * grid_m * grid_n
+    nnz = L.shim_poisson7(grid_l, grid_m, grid_n, i0, i1, int(sorted_rows), None, None, None)
+    p_ptr, p_idx, p_val = _libc.malloc(4 * (n + 1)), _libc.malloc(4 * nnz), _libc.malloc(8 * nnz)
+    if not (p_ptr and p_idx and p_val):
+        raise MemoryError(12 * nnz)
+    assert L.shim_poisson7(grid_l, grid_m, grid_n, i0, i1, int(sorted_rows), p_ptr, p_idx, p_val) == nnz
+    return n, nnz, p_ptr, p_idx, p_val
+
+
+# ----------------------------------------------------------------------------- CG to convergence
+def cg_to_convergence(Ls, grid, tol="1e-12"):
+    """BASELINE.json config 3: test/test3.c's system on a grid^3 cube (rows in test3.c's order, diagonal
+    last; b = A*1; x0 = 0) solved with `-i cg -p jacobi -tol 1e-12` through lis_solve, compared with the
+    compiled reference's run of the same system stored in tests/golden/cg_poisson_<grid>.npz
+    (tests/golden/make_cg_fullsize.py; the reference itself cannot run on the GPU box's clock budget)."""
+    t0 = time.time()
+    n, nnz, p_ptr, p_idx, p_val = host_poisson7(Ls, grid, grid, grid, 0, grid, False)
+    h = Ls.shim_mv_open(1, n, p_ptr, p_idx, p_val, 0, 0, 1)
+    assert h >= 0, h
+    try:
+        g = np.arange(grid)
+        edge = (g > 0).astype(np.float64) + (g < grid - 1)
+        b = (6.0 - (edge[:, None, None] + edge[None, :, None] + edge[None, None, :])).reshape(-1)   # = A*1 exactly
+        x = np.zeros(n); rh = np.zeros(16384)
+        oi = np.zeros(4, np.int32); od = np.zeros(4, np.float64)
+        Ls.shim_mv_solve_b.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        opts = f"-i cg -p jacobi -tol {tol} -maxiter 6000".encode()
+        setup_s = time.time() - t0
+        rc = Ls.shim_mv_solve_b(h, opts, b.ctypes.data, x.ctypes.data, oi.ctypes.data, od.ctypes.data, rh.ctypes.data, len(rh))
+        if rc != 0 or oi[1] != 0:
+            raise RuntimeError(f"lis_solve: rc={rc} status={oi[1]} iter={oi[0]}")
+        it = int(oi[0]); hist = rh[:int(oi[3])].copy()
+        out = {"cg_iters_to_1e-12": it, "cg_converge_solver_s": float(od[2] + od[3]), "cg_converge_iters_per_s": it / float(od[2] + od[3]),
+               "cg_converge_gflops": (2.0 * nnz + 13.0 * n) * it / float(od[2] + od[3]) / 1e9,
+               "cg_final_relres": float(od[0]), "cg_max_abs_x_minus_1": float(np.abs(x - 1.0).max()),
+               "cg_system": f"test3.c {grid}^3 7-pt Poisson (rows in test3.c order), b=A*1, x0=0, -i cg -p jacobi -tol {tol}; setup {setup_s:.1f}s"}
+        gp = os.path.join(ROOT, "tests", "golden", f"cg_poisson_{grid}.npz")
+        if os.path.exists(gp):
+            gd = np.load(gp)
+            ref = gd["rhistory"]; m = min(len(ref), len(hist))
+            rel = np.abs(hist[:m] - ref[:m]) / ref[:m]
+            out.update({"reference_iters": int(gd["iters"]), "reference_threads": int(gd["threads"]),
+                        "reference_final_relres": float(gd["resid"]), "iteration_count_identical": bool(int(gd["iters"]) == it),
+                        "history_gap": float(rel.max()), "history_gap_first_half": float(rel[: m // 2].max()),
+                        "history_gap_first_three_quarters": float(rel[: 3 * m // 4].max()),
+                        "reference_source": f"tests/golden/cg_poisson_{grid}.npz (compiled reference, OpenMP, {int(gd['threads'])} threads, {float(gd['wall_s']):.0f}s of CPU wall)"})
+        else:
+            out["reference_iters"] = None
+            out["reference_source"] = f"no golden file for {grid}^3 (tests/golden/make_cg_fullsize.py {grid})"
+        return out
+    finally:
+        Ls.shim_mv_close.argtypes = [C.c_int]
+        Ls.shim_mv_close(h)
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, grid):
-    """The reference's own CPU lis_matvec (OpenMP build, all host threads) on a bounded sample."""
+    """The reference's own CPU lis_matvec (OpenMP build compiled from the reference sources, every
+    host core) on ONE 512^3 slab of the workload -- the whole workload at N=1.  torchrun exports
+    OMP_NUM_THREADS=1; the thread count is therefore set explicitly through the reference's own
+    -omp_num_threads initialisation option (src/system/lis_init.c:163-172)."""
     import lis_b200
     path = os.path.join(ROOT, "oracle", "_ref", "libref_shim_omp.so")
-    kind = "reference"
     if not os.path.exists(path):
         return {"impl": "reference", "unavailable": "oracle/_ref/libref_shim_omp.so missing (build with make -C oracle ref where /root/reference exists)"}
-    shim = lis_b200.Shim(path)
-    g = min(grid, args.cpu_grid)
-    ptr, idx, val = poisson7_host(g, g, g)
-    n, nnz = len(ptr) - 1, int(ptr[-1])
+    try:
+        os.sched_setaffinity(0, _AFFINITY0)        # the lis_b200 arm may have bound this process to one NUMA node
+    except Exception:
+        pass
+    cores = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    shim = lis_b200.Shim(path, f"-omp_num_threads {cores}")
     L = shim.lib
+    shim.set_threads(cores)
+    g = args.cpu_grid if args.cpu_grid > 0 else grid
+    world = max(args.gpus, 1)
+    n, nnz, p_ptr, p_idx, p_val = host_poisson7(L, g, g, g, 0, g, True)
     L.shim_mv_open.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
-    L.shim_mv_step_e2e.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     L.shim_mv_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.shim_mv_set_x.argtypes = [C.c_int, C.c_void_p]
-    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
+    h = L.shim_mv_open(1, n, p_ptr, p_idx, p_val, 0, 0, 1)
     assert h >= 0, h
-    x = np.ones(n)
+    x = np.random.default_rng(1).uniform(-1, 1, n)
     L.shim_mv_set_x(h, x.ctypes.data)
     sec, nrm = C.c_double(0), C.c_double(0)
     L.shim_mv_run(h, max(args.warmup, 1), C.byref(sec), C.byref(nrm))
     L.shim_mv_run(h, args.steps, C.byref(sec), C.byref(nrm))
+    used = shim.max_threads()
+    L.shim_mv_close.argtypes = [C.c_int]
+    L.shim_mv_close(h)
     gf = 2.0 * nnz * args.steps / sec.value / 1e9
-    cores = shim.max_threads()
-    sample = f"{g}^3 7-pt CSR (n={n}, nnz={nnz}), {args.steps} lis_matvec calls, OMP threads={cores}"
+    sample = (f"{g}^3 7-pt CSR (n={n}, nnz={nnz}), {args.steps} lis_matvec calls of the reference's OpenMP build, "
+              f"threads={used} of {os.cpu_count()} host cpus")
+    if world > 1:
+        sample += f"; one of the {world} slabs (the CPU rate is per-host, not per-GPU: it does not grow with N)"
+    if g != grid:
+        sample += f"; REDUCED sample ({g}^3 instead of {grid}^3)"
     return {"impl": "reference", "metric": "spmv_csr_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec.value / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"spmvtest3 {grid}^3 7-pt Poisson CSR (reference timed on a {g}^3 sample)"},
-            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": workload_config(grid, world),
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": used, "kind": "reference", "sample": sample},
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "nrm2": nrm.value}
 
@@ -290,24 +375,43 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
         lib.lis_b200_set_overlap(0)
         overlap_note = f"off: {e!r}"
     log(f"[rank {rank}] halo overlap: {overlap_note}")
-    for _ in range(args.warmup):
-        assert Ls.shim_mv_matvec(h) == 0
-    sampler = ClockSampler(local) if rank == 0 else None
-    dist.barrier(); torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    evs[0].record(stream)
-    for k in range(args.steps):
-        assert Ls.shim_mv_matvec(h) == 0
-        evs[k + 1].record(stream)
-    stream.synchronize()
-    clocks = sampler.stop() if sampler else None
-    per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps))
-    log(f"[rank {rank}] per-product ms: min {per[0]:.3f} median {per[len(per) // 2]:.3f} max {per[-1]:.3f}")
-    t = torch.tensor([evs[0].elapsed_time(evs[-1]) * 1e-3], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_s = float(t.item()) / args.steps
+    def time_products(use_sampler):
+        for _ in range(args.warmup):
+            assert Ls.shim_mv_matvec(h) == 0
+        sampler = ClockSampler(local) if (rank == 0 and use_sampler) else None
+        dist.barrier(); torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        evs[0].record(stream)
+        for k in range(args.steps):
+            assert Ls.shim_mv_matvec(h) == 0
+            evs[k + 1].record(stream)
+        stream.synchronize()
+        ck = sampler.stop() if sampler else None
+        per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps))
+        t = torch.tensor([evs[0].elapsed_time(evs[-1]) * 1e-3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, per, ck
+
+    # exchange-then-product (what the reference's LIS_MATVEC_SENDRECV does) and, where it reproduces the
+    # bits, the overlapped order: both timed, the faster one is the library setting for the rest
+    overlap_ok = overlap_note.startswith("interior")
+    lib.lis_b200_set_overlap(0)
+    step_s, per, clocks = time_products(True)
+    log(f"[rank {rank}] exchange then product: {step_s * 1e3:.3f} ms/product (max over ranks); this rank min {per[0]:.3f} median {per[len(per) // 2]:.3f} max {per[-1]:.3f}")
+    step_modes = {"exchange_then_product_ms": step_s * 1e3}
+    if overlap_ok:
+        lib.lis_b200_set_overlap(1)
+        s2, per2, ck2 = time_products(True)
+        log(f"[rank {rank}] interior rows during the exchange: {s2 * 1e3:.3f} ms/product; this rank min {per2[0]:.3f} median {per2[len(per2) // 2]:.3f} max {per2[-1]:.3f}")
+        step_modes["overlapped_ms"] = s2 * 1e3
+        if s2 <= step_s:
+            step_s, per, clocks = s2, per2, ck2
+        else:
+            overlap_ok = False
+            overlap_note = f"off: exchange-then-product is faster here ({step_s * 1e3:.3f} vs {s2 * 1e3:.3f} ms); the overlapped order reproduced the bits"
+            lib.lis_b200_set_overlap(0)
     # e2e: local slice of x in from pinned host memory, product, local slice of y out
     dist.barrier(); torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, 10))
@@ -337,7 +441,7 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     # then a sum of range shares (last bits move, like between rank counts).  Keep that only if the run
     # ends on the same residual to 1e-6 and is not slower; otherwise products-only overlap.
     cg_note = "one fused launch behind the exchange"
-    if lib.lis_b200_set_overlap(2) != 0:
+    if overlap_ok and lib.lis_b200_set_overlap(2) != 0:
         done, cg_it_s, res_plain = timed_cg()
         try:
             lib.lis_b200_set_overlap(1)
@@ -356,6 +460,24 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     else:
         lib.lis_b200_set_overlap(0)
         done, cg_it_s, _ = timed_cg()
+    # dot / nrm2 partials across ranks: host control plane (default) against ncclAllGather over NVLink
+    reduce_note = "host control plane (reduction kernel writes a mapped host scalar; shm allgather; folded in rank order)"
+    cg_reduce = {"cg_it_s_reduce_host": cg_it_s}
+    try:
+        lib.lis_b200_set_reduce(1)
+        d3, cg3, _ = timed_cg()
+        cg_reduce["cg_it_s_reduce_nccl"] = cg3
+        log(f"[rank {rank}] CG with ncclAllGather reductions {cg3:.1f} it/s vs {cg_it_s:.1f} through the host control plane")
+        fl = torch.tensor([int(d3 == done and cg3 > cg_it_s)], device=dev)
+        dist.all_reduce(fl, op=dist.ReduceOp.MIN)
+        if int(fl.item()):
+            cg_it_s = cg3
+            reduce_note = "ncclAllGather of the per-rank partials over NVLink + one pinned read-back; folded in rank order"
+        else:
+            lib.lis_b200_set_reduce(0)
+    except Exception as e:
+        lib.lis_b200_set_reduce(0)
+        log(f"[rank {rank}] NCCL reduction leg failed: {e!r}")
     nnz_all = torch.tensor([nnz], device=dev, dtype=torch.int64)
     dist.all_reduce(nnz_all)
     nnz_g = int(nnz_all.item())
@@ -401,19 +523,19 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
         "metric": "spmv_csr_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"spmvtest3 {grid * world}x{grid}x{grid} 7-pt Poisson, CSR, {world} row slabs of {grid}^3 (n={n * world}, nnz={nnz_g})",
-                   "l2": "inputs (13.9 GB/step/GPU) exceed L2 by >100x, no flush between steps", "index": "int32 (local numbering + halo)",
-                   "exchange": "2 boundary planes (2 MiB each) per product via grouped ncclSend/ncclRecv; dot partials via ncclAllGather",
-                   "overlap": overlap_note},
+        "config": workload_config(grid, world),
         "e2e": {"value": 2.0 * nnz_g / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                 "what": e2e_what},
-        "gpu_launches": (4 if overlap_note.startswith("interior") else 2) * args.steps,
+        "gpu_launches": (4 if overlap_ok else 2) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false> (+ halo pack, NCCL p2p)", "achieved": bytes_local / step_s / 1e9,
                      "peak": peak_gbs, "unit": "GB/s", "frac": bytes_local / step_s / 1e9 / peak_gbs, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "note": "per GPU, whole product incl. halo exchange"},
         "clocks": clocks,
         "extra": {"cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": done, "cg_matvec_dot": cg_note, "e2e_three_calls_gflops": 2.0 * nnz_g / e2e_seq_s / 1e9,
-                  "cg_unfused_formula_gbs_per_gpu": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9},
+                  "exchange": "2 boundary planes (2 MiB each) per product via grouped ncclSend/ncclRecv; dot partials: " + reduce_note,
+                  "overlap": overlap_note, **step_modes, **cg_reduce,
+                  "cg_roofline": {"bytes_per_iteration_per_gpu": 12.0 * nnz + 108.0 * n, "what": "fused traffic: 12 nnz + 20 n (q=Ap,<p,q>) + 64 n (update + next Jacobi step) + 24 n (xpay)",
+                                  "achieved_gbs_per_gpu": (12.0 * nnz + 108.0 * n) * cg_it_s / 1e9, "frac": (12.0 * nnz + 108.0 * n) * cg_it_s / 1e9 / peak_gbs}},
     }
 
 
@@ -613,6 +735,24 @@ def run_b200(args, grid):
     finally:
         os.environ.pop("LIS_B200_CG", None)
 
+    cg_bytes = 12.0 * nnz + (108.0 if cg_step.startswith("update carries") else 116.0) * n
+    cg_conv = {}
+    if not args.no_cg_converge:
+        try:
+            cg_conv = cg_to_convergence(Ls, grid)
+            log("CG+Jacobi to 1e-12: " + json.dumps(cg_conv))
+        except Exception as e:
+            cg_conv = {"cg_converge_error": repr(e)}
+            log(f"CG convergence leg failed: {e!r}")
+    traffic, traffic_src = None, "no ncu capture of this kernel at this size under profiles/ncu_traffic.json"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tj.get(f"csr_tma_kernel<256,4,false>@{grid}^3")
+        if ent:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+    except Exception:
+        pass
+
     def assemble(e2e_now, what_now, fmt_now, baseline_now):
         gf = 2.0 * nnz / res["csr_s"] / 1e9
         ach = bytes_csr / res["csr_s"] / 1e9
@@ -620,15 +760,13 @@ def run_b200(args, grid):
             "metric": "spmv_csr_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["csr_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"spmvtest3 {grid}^3 7-pt Poisson, CSR, rows sorted (n={n}, nnz={nnz})",
-                       "l2": "inputs (13.9 GB/step) exceed L2 by >100x, no flush between steps", "index": "int32"},
+            "config": workload_config(grid, 1),
             "e2e": {"value": 2.0 * nnz / e2e_now / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                     "what": what_now},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false>", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
                          "frac": ach / peak_gbs,
-                         "traffic": 14092449000 if grid == 512 else None,
-                         "traffic_source": "dram__bytes_read+write of one launch, ncu --set full (profiles/r01_ncu_summary.txt)",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_csr},
             "clocks": clocks,
@@ -642,7 +780,10 @@ def run_b200(args, grid):
                 "lis_matvec_api_gflops": 2.0 * nnz / api_s / 1e9,
                 "e2e_three_calls_gflops": 2.0 * nnz / e2e_seq_s / 1e9,
                 "cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": cg_iters, "cg_step": cg_step, "cg_other_variant_iters_per_s": cg_split_it_s,
-                "cg_unfused_formula_gbs": (12.0 * nnz + 156.0 * n) * cg_it_s / 1e9 if cg_it_s else None,
+                "cg_roofline": None if not cg_it_s else {
+                    "bytes_per_iteration": cg_bytes, "what": "fused traffic: 12 nnz + 20 n (q=Ap,<p,q>) + 64 n (update + next Jacobi step) + 24 n (xpay); 12 nnz + 116 n with separate update / Jacobi launches",
+                    "achieved_gbs": cg_bytes * cg_it_s / 1e9, "frac": cg_bytes * cg_it_s / 1e9 / peak_gbs},
+                **cg_conv,
                 "nrm2_Ax": nrm.value,
                 **fmt_now,
             },
@@ -754,9 +895,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lis_b200", choices=["lis_b200", "reference"])
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--cpu-grid", type=int, default=256, help="edge of the bounded CPU sample")
+    ap.add_argument("--cpu-grid", type=int, default=0, help="edge of the CPU sample (0 = the workload's own grid)")
     ap.add_argument("--cg-iters", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cg-converge", action="store_true", help="skip the CG-to-1e-12 solve of BASELINE config 3")
     ap.add_argument("--no-format-extras", action="store_true", help="skip the ELL/DIA/JAD/BSR convert + lis_matvec extras")
     ap.add_argument("--watchdog", type=float, default=420.0, help="seconds the optional legs may take before the line is emitted without them")
     args = ap.parse_args()

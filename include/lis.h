@@ -639,6 +639,8 @@ LIS_INT lis_b200_matvec_host_plan(LIS_MATRIX A, LIS_INT cap, LIS_INT *rows, LIS_
  * shares).  on = 1 both (default), 2 products only (LIS_B200_OVERLAP=spmv), 0 neither (LIS_B200_OVERLAP=0).
  * Returns the old setting. */
 LIS_INT lis_b200_set_overlap(LIS_INT on);
+/* partial scalars of dot/nrm2 across ranks: 0 = host control plane (default), 1 = ncclAllGather over NVLink */
+LIS_INT lis_b200_set_reduce(LIS_INT nccl);
 /* the CUDA stream (cudaStream_t) all kernels of this process are enqueued on */
 void *lis_b200_stream(void);
 

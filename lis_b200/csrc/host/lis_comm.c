@@ -332,11 +332,20 @@ LIS_INT lis_b200_allreduce_sum(double *vals, LIS_INT count) { return allreduce_h
  * host, the host folds it in rank order (same bits on every rank) */
 /* Default: the scalars go through the host control plane (mapped scalar -> shm exchange, ~2 us,
  * no NCCL collective involved); LIS_B200_REDUCE=nccl selects the ncclAllGather route. */
+static int g_reduce_mode = -1;
 int lisd_reduce_uses_nccl(void)
 {
-    static int mode = -1;
-    if (mode < 0) { const char *e = getenv("LIS_B200_REDUCE"); mode = (e && strcmp(e, "nccl") == 0) ? 1 : 0; }
-    return mode == 1 && g.nranks > 1 && g.nccl_ok;
+    if (g_reduce_mode < 0) { const char *e = getenv("LIS_B200_REDUCE"); g_reduce_mode = (e && strcmp(e, "nccl") == 0) ? 1 : 0; }
+    return g_reduce_mode == 1 && g.nranks > 1 && g.nccl_ok;
+}
+/* 0: host control plane (default), 1: ncclAllGather.  Call on every rank at the same point, with
+ * no reduction in flight.  Returns the previous mode. */
+LIS_INT lis_b200_set_reduce(LIS_INT nccl)
+{
+    lisd_sync();
+    const int old = g_reduce_mode == 1;
+    g_reduce_mode = nccl ? 1 : 0;
+    return old;
 }
 double *lisd_reduce_dev_buffer(void) { return g.d_red; }
 

@@ -563,6 +563,44 @@ EXPORT int shim_esolve(int fmt, int n, const int *ptr, const int *idx, const dou
     return (int)err;
 }
 
+/* ------------------------------------------------------------------ synthetic matrices for bench.py
+ * Rows [i0*m*n, i1*m*n) of the 7-point Poisson matrix of an l x m x n grid, lexicographic
+ * ii = i*m*n + j*n + k (test/spmvtest3.c:142-157 values: 6 on the diagonal, -1 off it), global
+ * column indices.  sorted != 0: ascending columns (what spmvtest3.c:192-195 leaves after
+ * lis_sort_id); sorted == 0: test/test3.c:116-126 order (-mn, +mn, -n, +n, -1, +1, diagonal last).
+ * pass ptr == NULL to get the entry count only.  Returns nnz. */
+EXPORT long long shim_poisson7(int l, int m, int n, int i0, int i1, int sorted, int *ptr, int *idx, double *val)
+{
+    const long long mn = (long long)m * n;
+    long long k = 0, row = 0;
+    for (int i = i0; i < i1; i++)
+        for (int j = 0; j < m; j++)
+            for (int q = 0; q < n; q++, row++) {
+                const long long ii = (long long)i * mn + (long long)j * n + q;
+                if (ptr) ptr[row] = (int)k;
+                if (!ptr) { k += 1 + (i > 0) + (i < l - 1) + (j > 0) + (j < m - 1) + (q > 0) + (q < n - 1); continue; }
+                if (sorted) {
+                    if (i > 0)     { idx[k] = (int)(ii - mn); val[k++] = -1.0; }
+                    if (j > 0)     { idx[k] = (int)(ii - n);  val[k++] = -1.0; }
+                    if (q > 0)     { idx[k] = (int)(ii - 1);  val[k++] = -1.0; }
+                    idx[k] = (int)ii; val[k++] = 6.0;
+                    if (q < n - 1) { idx[k] = (int)(ii + 1);  val[k++] = -1.0; }
+                    if (j < m - 1) { idx[k] = (int)(ii + n);  val[k++] = -1.0; }
+                    if (i < l - 1) { idx[k] = (int)(ii + mn); val[k++] = -1.0; }
+                } else {
+                    if (i > 0)     { idx[k] = (int)(ii - mn); val[k++] = -1.0; }
+                    if (i < l - 1) { idx[k] = (int)(ii + mn); val[k++] = -1.0; }
+                    if (j > 0)     { idx[k] = (int)(ii - n);  val[k++] = -1.0; }
+                    if (j < m - 1) { idx[k] = (int)(ii + n);  val[k++] = -1.0; }
+                    if (q > 0)     { idx[k] = (int)(ii - 1);  val[k++] = -1.0; }
+                    if (q < n - 1) { idx[k] = (int)(ii + 1);  val[k++] = -1.0; }
+                    idx[k] = (int)ii; val[k++] = 6.0;
+                }
+            }
+    if (ptr) ptr[row] = (int)k;
+    return k;
+}
+
 /* ------------------------------------------------------------------ bench handles
  * One matrix + x + y kept alive across steps (bench.py): open once, then time steps.
  * step_e2e is what a user with HOST buffers does per product: scatter x in, lis_matvec,
@@ -743,6 +781,9 @@ EXPORT int shim_mv_solve_b(int h, const char *options, const double *b_local, do
     lis_solver_get_status(solver, &status);
     lis_solver_get_residualnorm(solver, &resid);
     out_i[0] = (int)iter; out_i[1] = (int)status; out_d[0] = resid;
+    { double time = 0, itime = 0, ptime = 0, pc = 0, pi = 0;          /* out_d needs 4 slots */
+      lis_solver_get_timeex(solver, &time, &itime, &ptime, &pc, &pi);
+      out_d[1] = time; out_d[2] = itime; out_d[3] = ptime; }
     int len = (int)iter + 1 - (status != LIS_SUCCESS ? 1 : 0);
     if (len > rh_cap) len = rh_cap;
     out_i[3] = 0;

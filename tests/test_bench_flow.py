@@ -46,6 +46,26 @@ def test_single_gpu_flow(built):
         # this leg ||y|| may differ from the CSR run in the last bit (seen once in ~15 runs); the others follow CSR order
         assert d["extra"][f"{k}_nrm2_vs_csr_rel"] <= (1e-14 if k == "bsr" else 0.0) and f"{k}_convert_device_s" in d["extra"], k
     assert "ell_convert_host_s" in d["extra"] and d["cpu_baseline"]["kind"] == "reference"
+    # BASELINE config 3 leg: CG + Jacobi to 1e-12 on test3.c's system (12^3: no golden file, count only)
+    assert d["extra"]["cg_iters_to_1e-12"] > 5 and d["extra"]["cg_final_relres"] < 1e-12 and d["extra"]["cg_max_abs_x_minus_1"] < 1e-9
+    assert set(d["config"]) == {"workload", "l2", "index"}
+
+
+def test_reference_arm_same_config_and_all_threads(built):
+    """--impl reference under torchrun's OMP_NUM_THREADS=1: the thread count is set explicitly, the config object is
+    the lis_b200 arm's"""
+    import bench
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--grid", "24", "--steps", "3", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    d = line_of(r)
+    assert d["impl"] == "reference" and d["config"] == bench.workload_config(24, 1)
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["cpu_baseline"]["kind"] == "reference"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--gpus", "4", "--grid", "16", "--steps", "3"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    d = line_of(r)
+    assert d["config"] == bench.workload_config(16, 4) and d["n_gpus"] == 4 and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 def test_watchdog_prints_the_line_without_the_optional_legs(built):
@@ -66,7 +86,9 @@ def test_two_rank_flow(built):
                        capture_output=True, text=True, timeout=900, env=env)
     d = line_of(r)
     assert KEYS <= set(d) and d["n_gpus"] == 2 and d["scaling"] == "weak"
-    assert d["config"]["overlap"].startswith("interior rows on a second stream"), d["config"]["overlap"]
+    assert d["extra"]["overlap"].startswith("interior rows on a second stream"), d["extra"]["overlap"]
+    assert {"exchange_then_product_ms", "overlapped_ms", "cg_it_s_reduce_host"} <= set(d["extra"])
+    assert set(d["config"]) == {"workload", "l2", "index"}
     assert d["gpu_launches"] == 4 * 3 and d["extra"]["cg_jacobi_iters_per_s"] > 0
     # CG ran both ways (one fused launch behind the exchange / split around it) and agreed on the residual
     assert "with the split fused step" in r.stderr and "split fused CG step off" not in r.stderr, r.stderr[-2000:]
