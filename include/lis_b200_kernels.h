@@ -218,30 +218,26 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
                                 const double *d_wd, const int *d_rowblk_start,
                                 const int *d_rowblk_end, double *d_x, void *stream);
 
-/* The same sweeps in ONE launch each ("sync-free"): d_order lists the rows level by level, every
- * level padded to a multiple of 32 slots with -1; d_pptr/d_pidx/d_pval are L (forward) or U
- * (backward) permuted into that slot order (nslots+1 pointers); d_ticket one unsigned int of
- * scratch.  forward:  d_out = w,  d_in = b:  w[i] = (b[i] - sum L*w[jj]) * wd[i]
- *           backward: d_out = x,  d_in = w:  x[i] = w[i] - (sum U*x[jj]) * wd[i]
- * d_out (n entries, must not alias d_in) is overwritten with a not-ready pattern first and
- * doubles as the dependency signal.  Same result bits as the level-launched kernels.          */
-int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *d_order,
-                                const int *d_pptr, const int *d_pidx, const double *d_pval,
-                                const double *d_wd, const int *d_rowblk_start, const int *d_rowblk_end,
-                                const double *d_in, double *d_out, unsigned int *d_ticket, void *stream);
-
-/* One-launch triangular solve on a factor prepared the same way (strictly lower or strictly
- * upper part, rows in dependency-level order, couplings that must be dropped already removed):
- *   mode 0: out[i] = (in[i] - sum v*out[jj]) * wd[i]     ILU's U solve x = D(x - Ux)   src/precon/lis_precon_iluk.c:1040-1048
- *                                                        and the second half of the transposed SSOR sweep
- *   mode 1: out[i] =  in[i] - sum v*out[jj]              ILU's unit-diagonal L solve   src/precon/lis_precon_iluk.c:1030-1037
- *   mode 2: out[i] =  in[i] - sum v*(out[jj]*wd[jj])     first half of the transposed SSOR sweep
- *                                                        src/matrix/lis_matrix_csr.c:1838-1845
- * Sums run in storage order, unfused.  d_wd may be NULL for mode 1.                             */
-int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *d_order,
-                            const int *d_pptr, const int *d_pidx, const double *d_pval,
-                            const double *d_wd, const double *d_in, double *d_out,
-                            unsigned int *d_ticket, void *stream);
+/* One-launch ("sync-free") triangular sweep on a factor the host prepared once (host/lis_precon.c
+ * lisd_perm_build): the rows of the strictly lower or strictly upper part listed level by level,
+ * every level padded to a multiple of 32 slots with -1 (d_order, nslots entries); per warp of 32
+ * slots a SELL slice -- entry q of lane l at d_wptr[w] + 32*q + l of d_sidx/d_sval, d_plen[slot]
+ * entries per row, in the order the row sum must run, couplings that must be dropped already
+ * removed -- and d_wdep[w], the neighbour (row index) of the warp's rows that sits latest in slot
+ * order (-1: none).  d_ticket: one unsigned int of scratch.  d_out (n entries, must not alias
+ * d_in) is overwritten with a not-ready pattern first and doubles as the dependency signal.
+ *   mode 0: out[i] = (in[i] - sum v*out[jj]) * wd[i]     SSOR forward w = (D/w+L)^-1 b   src/matrix/lis_matrix_csr.c:1578-1592, 1610-1617
+ *                                                        ILU's U solve                   src/precon/lis_precon_iluk.c:1040-1048
+ *   mode 1: out[i] =  in[i] - sum v*out[jj]              ILU's unit-diagonal L solve     src/precon/lis_precon_iluk.c:1030-1037
+ *   mode 2: out[i] =  in[i] - sum v*(out[jj]*wd[jj])     first half of the transposed SSOR sweep   src/matrix/lis_matrix_csr.c:1838-1845
+ *   mode 3: out[i] =  in[i] - (sum v*out[jj]) * wd[i]    SSOR backward                   src/matrix/lis_matrix_csr.c:1593-1605, 1618-1628
+ * Sums run in storage order, unfused: same result bits as the level-launched kernels and the
+ * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm (1..8, else 8) bounds the persistent
+ * grid, i.e. the number of rows waiting at any time. */
+int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
+                       const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,
+                       const double *d_wd, const double *d_in, double *d_out,
+                       unsigned int *d_ticket, int ctas_per_sm, void *stream);
 
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
 /* d_ws[i] = d_x[d_export_index[i]] */

@@ -127,14 +127,18 @@ LIS_INT lisd_matvech(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);                /
 void    lisd_sweep_free(void *sweep);
 
 /* ---- triangular factors prepared for the one-launch ("sync-free") solve kernels ---- */
-typedef struct lisd_perm {        /* rows in dependency-level order + the factor permuted to match */
+typedef struct lisd_perm {        /* rows in dependency-level order + the factor as SELL-32 slices in that order */
     int nslots;                   /* levels concatenated, each padded to a multiple of 32 */
     int *d_order;                 /* slot -> row (or -1) */
-    int *d_pptr, *d_pidx;         /* the triangular part permuted into slot order */
-    double *d_pval;
+    int *d_wptr;                  /* per warp of 32 slots: start of its slice (nslots/32 + 1 entries) */
+    int *d_plen;                  /* per slot: kept entries of the row */
+    int *d_wdep;                  /* per warp: the neighbour row latest in slot order (-1: none) */
+    int *d_sidx;                  /* slices: entry q of lane l at wptr[w] + 32*q + l */
+    double *d_sval;
 } lisd_perm;
 LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
-                        const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val);
+                        const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, const int *blk_lo, const int *blk_hi);
+int     lisd_perm_sweep(const lisd_perm *P, int mode, int n, const double *d_wd, const double *d_in, double *d_out, unsigned int *d_ticket);
 void    lisd_perm_free(lisd_perm *p);
 int    *lisd_order_by_level(int n, const int *lvl, int nlev, int *rows);   /* counting sort; returns level pointers */
 

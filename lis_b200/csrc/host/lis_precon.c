@@ -467,52 +467,126 @@ typedef struct lisd_sweep {
 
 void lisd_perm_free(lisd_perm *p)
 {
-    lisd_free(p->d_order); lisd_free(p->d_pptr); lisd_free(p->d_pidx); lisd_free(p->d_pval);
+    lisd_free(p->d_order); lisd_free(p->d_wptr); lisd_free(p->d_plen); lisd_free(p->d_wdep); lisd_free(p->d_sidx); lisd_free(p->d_sval);
     memset(p, 0, sizeof(*p));
 }
 
-/* rows[] is level-ordered, lptr[l] its level pointers; builds the padded order and the permuted
- * copy of the triangular part (ptr/idx/val, host) on the device */
+/* rows[] is level-ordered, lptr[l] its level pointers.  Builds, on the device, what the one-launch sweep
+ * kernel reads (kernels/sweep.cu): the padded slot order, and the triangular part (ptr/idx/val, host)
+ * as SELL-32 slices in that order -- per warp of 32 slots, entry q of lane l at wptr[w] + 32*q + l,
+ * each row's entries in their storage order.  blk_lo/blk_hi (or NULL): per row, the range of columns
+ * the row keeps; couplings outside are the ones the block sweep drops (src/matrix/lis_matrix_csr.c:1590,
+ * 1601) and are left out here.  wdep[w]: of all neighbours the warp's rows read, the one latest in slot order. */
 LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
-                        const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val)
+                        const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, const int *blk_lo, const int *blk_hi)
 {
     size_t nslots = 0;
     for (int l = 0; l < nlev; l++) nslots += (size_t)((lptr[l + 1] - lptr[l] + 31) & ~31);
-    if (nslots > 0x7fffff00u) { LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "SSOR schedule too large\n"); return LIS_ERR_OUT_OF_MEMORY; }
+    if (nslots > 0x7fffff00u) { LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "sweep schedule too large\n"); return LIS_ERR_OUT_OF_MEMORY; }
+    const size_t nw = nslots / 32;
     int *order = (int *)malloc(sizeof(int) * (nslots ? nslots : 1));
-    int *pptr = (int *)malloc(sizeof(int) * (nslots + 1));
-    const size_t nnz = (size_t)ptr[n];
-    int *pidx = (int *)malloc(sizeof(int) * (nnz ? nnz : 1));
-    double *pval = (double *)malloc(sizeof(double) * (nnz ? nnz : 1));
+    int *plen = (int *)malloc(sizeof(int) * (nslots ? nslots : 1));
+    int *slot_of = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    int *wptr = (int *)malloc(sizeof(int) * (nw + 1));
+    int *wdep = (int *)malloc(sizeof(int) * (nw ? nw : 1));
+    int *sidx = NULL;
+    double *sval = NULL;
     LIS_INT err = LIS_OUT_OF_MEMORY;
-    if (!order || !pptr || !pidx || !pval) { LIS_SETERR_MEM(nnz * 12); goto done; }
+    if (!order || !plen || !slot_of || !wptr || !wdep) { LIS_SETERR_MEM(nslots * 12); goto done; }
     {
-        size_t k = 0, q = 0;
-        pptr[0] = 0;
+        size_t k = 0;
         for (int l = 0; l < nlev; l++) {
             const int cnt = lptr[l + 1] - lptr[l], padded = (cnt + 31) & ~31;
             for (int r = 0; r < padded; r++, k++) {
-                if (r < cnt) {
-                    const int i = rows[lptr[l] + r];
-                    order[k] = i;
-                    for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++, q++) { pidx[q] = idx[j]; pval[q] = val[j]; }
-                } else order[k] = -1;
-                pptr[k + 1] = (int)q;
+                order[k] = r < cnt ? rows[lptr[l] + r] : -1;
+                if (r < cnt) slot_of[order[k]] = (int)k;
+            }
+        }
+    }
+    /* pass 1: kept entries per row, slice widths, the warp's latest neighbour */
+    {
+        size_t total = 0;
+        for (size_t w = 0; w < nw; w++) {
+            int width = 0, latest = -1, latest_row = -1;
+            for (int lane = 0; lane < 32; lane++) {
+                const size_t k = w * 32 + (size_t)lane;
+                const int i = order[k];
+                int cnt = 0;
+                if (i >= 0)
+                    for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++) {
+                        const int jj = idx[j];
+                        if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
+                        cnt++;
+                        if (slot_of[jj] > latest) { latest = slot_of[jj]; latest_row = jj; }
+                    }
+                plen[k] = cnt;
+                if (cnt > width) width = cnt;
+            }
+            wptr[w] = (int)total;
+            wdep[w] = latest_row;
+            total += (size_t)32 * (size_t)width;
+            if (total > 0x7fffff00u) { LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "sweep schedule too large\n"); err = LIS_ERR_OUT_OF_MEMORY; goto done; }
+        }
+        wptr[nw] = (int)total;
+        sidx = (int *)malloc(sizeof(int) * (total ? total : 1));
+        sval = (double *)malloc(sizeof(double) * (total ? total : 1));
+        if (!sidx || !sval) { LIS_SETERR_MEM(total * 12); goto done; }
+    }
+    /* pass 2: fill the slices; unused positions point at the row itself with a zero (never read) */
+    for (size_t w = 0; w < nw; w++) {
+        const int width = (wptr[w + 1] - wptr[w]) / 32;
+        for (int lane = 0; lane < 32; lane++) {
+            const int i = order[w * 32 + (size_t)lane];
+            int q = 0;
+            if (i >= 0)
+                for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++) {
+                    const int jj = idx[j];
+                    if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
+                    sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = jj;
+                    sval[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = val[j];
+                    q++;
+                }
+            for (; q < width; q++) {
+                sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = i >= 0 ? i : 0;
+                sval[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = 0.0;
             }
         }
     }
     P->nslots = (int)nslots;
-    err = lisd_malloc((void **)&P->d_order, sizeof(int) * (nslots ? nslots : 1));
-    if (!err) err = lisd_upload(P->d_order, order, sizeof(int) * nslots);
-    if (!err) err = lisd_malloc((void **)&P->d_pptr, sizeof(int) * (nslots + 1));
-    if (!err) err = lisd_upload(P->d_pptr, pptr, sizeof(int) * (nslots + 1));
-    if (!err) err = lisd_malloc((void **)&P->d_pidx, sizeof(int) * (nnz ? nnz : 1));
-    if (!err) err = lisd_upload(P->d_pidx, pidx, sizeof(int) * nnz);
-    if (!err) err = lisd_malloc((void **)&P->d_pval, sizeof(double) * (nnz ? nnz : 1));
-    if (!err) err = lisd_upload(P->d_pval, pval, sizeof(double) * nnz);
+    {
+        const size_t total = (size_t)wptr[nw];
+        err = lisd_malloc((void **)&P->d_order, sizeof(int) * (nslots ? nslots : 1));
+        if (!err) err = lisd_upload(P->d_order, order, sizeof(int) * nslots);
+        if (!err) err = lisd_malloc((void **)&P->d_plen, sizeof(int) * (nslots ? nslots : 1));
+        if (!err) err = lisd_upload(P->d_plen, plen, sizeof(int) * nslots);
+        if (!err) err = lisd_malloc((void **)&P->d_wptr, sizeof(int) * (nw + 1));
+        if (!err) err = lisd_upload(P->d_wptr, wptr, sizeof(int) * (nw + 1));
+        if (!err) err = lisd_malloc((void **)&P->d_wdep, sizeof(int) * (nw ? nw : 1));
+        if (!err) err = lisd_upload(P->d_wdep, wdep, sizeof(int) * nw);
+        if (!err) err = lisd_malloc((void **)&P->d_sidx, sizeof(int) * (total ? total : 1));
+        if (!err) err = lisd_upload(P->d_sidx, sidx, sizeof(int) * total);
+        if (!err) err = lisd_malloc((void **)&P->d_sval, sizeof(double) * (total ? total : 1));
+        if (!err) err = lisd_upload(P->d_sval, sval, sizeof(double) * total);
+    }
 done:
-    free(order); free(pptr); free(pidx); free(pval);
+    free(order); free(plen); free(slot_of); free(wptr); free(wdep); free(sidx); free(sval);
     return err;
+}
+
+int lisd_sweep_ctas(void);
+/* one sweep on a prepared factor; mode as in lisb200_sweep_sell; async on the library stream */
+int lisd_perm_sweep(const lisd_perm *P, int mode, int n, const double *d_wd, const double *d_in, double *d_out, unsigned int *d_ticket)
+{
+    return lisb200_sweep_sell(mode, n, P->nslots, P->d_order, P->d_wptr, P->d_plen, P->d_wdep, P->d_sidx, P->d_sval,
+                              d_wd, d_in, d_out, d_ticket, lisd_sweep_ctas(), lisd_stream());
+}
+
+/* how many CTAs per SM the persistent sweep grid gets (LIS_B200_SWEEP_CTAS=1..8; default 8) */
+int lisd_sweep_ctas(void)
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LIS_B200_SWEEP_CTAS"); v = e ? atoi(e) : 0; if (v < 1 || v > 8) v = 8; }
+    return v;
 }
 
 void lisd_sweep_free(void *p)
@@ -584,7 +658,7 @@ static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
     if (!S->h_fptr) goto fail;
     err = lisd_malloc((void **)&S->d_frows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_frows, rows, sizeof(int) * (size_t)n);
-    if (!err) err = lisd_perm_build(&S->pf, n, nlev, S->h_fptr, rows, A->L->ptr, A->L->index, A->L->value);
+    if (!err) err = lisd_perm_build(&S->pf, n, nlev, S->h_fptr, rows, A->L->ptr, A->L->index, A->L->value, bs, be);
     if (err) goto fail;
     /* backward: row i waits for every U neighbour inside its block */
     nlev = 0;
@@ -604,7 +678,7 @@ static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
     if (!S->h_bptr) goto fail;
     err = lisd_malloc((void **)&S->d_brows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_brows, rows, sizeof(int) * (size_t)n);
-    if (!err) err = lisd_perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value);
+    if (!err) err = lisd_perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value, bs, be);
     if (!err) err = lisd_malloc((void **)&S->d_w, sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_malloc((void **)&S->d_ticket, 64);
     if (!err) err = lisd_malloc((void **)&S->d_blk_start, sizeof(int) * (size_t)(n > 0 ? n : 1));
@@ -690,9 +764,7 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
         if (!err) err = lisd_vec_device(x);
         if (err) return err;
         lisd_mark_busy();
-        return lisd_check(lisb200_ssor_sweep_syncfree(1, S->n, S->pf.nslots, S->pf.d_order, S->pf.d_pptr, S->pf.d_pidx, S->pf.d_pval,
-                                                      M->wd, S->d_blk_start, S->d_blk_end, b->value, x->value,
-                                                      S->d_ticket, lisd_stream()), "lower triangular solve");
+        return lisd_check(lisd_perm_sweep(&S->pf, 0, S->n, M->wd, b->value, x->value, S->d_ticket), "lower triangular solve");
     }
     err = sweep_prepare(A, &M, &S);
     if (err) return err;
@@ -705,13 +777,9 @@ LIS_INT lis_matrix_solve(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT flag)
         /* default: one launch per direction; LIS_B200_SSOR=levels keeps the launch-per-level path */
         const char *e = getenv("LIS_B200_SSOR");
         if (!(e && strcmp(e, "levels") == 0)) {
-            err = lisd_check(lisb200_ssor_sweep_syncfree(1, S->n, S->pf.nslots, S->pf.d_order, S->pf.d_pptr, S->pf.d_pidx, S->pf.d_pval,
-                                                         M->wd, S->d_blk_start, S->d_blk_end, b->value, S->d_w,
-                                                         S->d_ticket, st), "SSOR forward sweep");
+            err = lisd_check(lisd_perm_sweep(&S->pf, 0, S->n, M->wd, b->value, S->d_w, S->d_ticket), "SSOR forward sweep");
             if (err) return err;
-            return lisd_check(lisb200_ssor_sweep_syncfree(0, S->n, S->pb.nslots, S->pb.d_order, S->pb.d_pptr, S->pb.d_pidx, S->pb.d_pval,
-                                                          M->wd, S->d_blk_start, S->d_blk_end, S->d_w, x->value,
-                                                          S->d_ticket, st), "SSOR backward sweep");
+            return lisd_check(lisd_perm_sweep(&S->pb, 3, S->n, M->wd, S->d_w, x->value, S->d_ticket), "SSOR backward sweep");
         }
     }
     for (int l = 0; l < S->nlev_f; l++) {

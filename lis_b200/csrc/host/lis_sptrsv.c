@@ -1,6 +1,6 @@
 /*
  * lis_sptrsv.c -- a strictly triangular CSR factor prepared for the one-launch solve kernel
- * (lisb200_sptrsv_syncfree): rows grouped by dependency level on the host, once per factor, the
+ * (lisb200_sweep_sell): rows grouped by dependency level on the host, once per factor, the
  * factor uploaded permuted into that order.  Users: the ILU(k) apply (lis_precon_ilu.c) and the
  * transposed SSOR sweep (lis_precon.c).  The row sums run in the storage order of the CSR given
  * here, which is how the callers pin the reference's summation order.
@@ -49,7 +49,7 @@ LIS_INT lisd_tri_build(int n, const LIS_INT *ptr, const LIS_INT *idx, const LIS_
     lptr = lisd_order_by_level(n, lvl, nlev, rows);
     if (!lptr) { LIS_SETERR_MEM(nlev * sizeof(int)); goto fail; }
     T->n = n; T->nlev = nlev;
-    err = lisd_perm_build(&T->p, n, nlev, lptr, rows, ptr, idx, val);
+    err = lisd_perm_build(&T->p, n, nlev, lptr, rows, ptr, idx, val, NULL, NULL);
     if (!err) err = lisd_malloc((void **)&T->d_ticket, 64);
     if (err) goto fail;
     free(lvl); free(rows); free(lptr);
@@ -64,6 +64,5 @@ fail:
 LIS_INT lisd_tri_solve(const lisd_tri *T, int mode, const double *d_wd, const double *d_in, double *d_out, const char *what)
 {
     lisd_mark_busy();
-    return lisd_check(lisb200_sptrsv_syncfree(mode, T->n, T->p.nslots, T->p.d_order, T->p.d_pptr, T->p.d_pidx, T->p.d_pval,
-                                              d_wd, d_in, d_out, T->d_ticket, lisd_stream()), what);
+    return lisd_check(lisd_perm_sweep(&T->p, mode, T->n, d_wd, d_in, d_out, T->d_ticket), what);
 }

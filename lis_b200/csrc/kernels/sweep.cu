@@ -58,18 +58,29 @@ ssor_bwd_kernel(int nrows, const int *__restrict__ rows,
 
 // ---- one-launch ("sync-free") sweeps ---------------------------------------------------------
 // Level-by-level launches pay a launch + drain per level (1534 levels for a 512^3 7-point grid,
-// thousands for a random band).  Here a whole sweep is ONE kernel: slot k of `order` holds a
-// row (levels concatenated, each padded to a multiple of 32 with -1 so that no warp straddles
-// two levels => lanes of a warp never wait on each other), L/U are stored permuted in that order
-// (coalesced), and the output vector itself carries the "done" signal: it is pre-filled with a
-// signalling-NaN pattern that no IEEE operation can produce, and a row polls each neighbour it
-// reads until the pattern is gone (one L2 round trip per dependency hop, 8 neighbours polled
-// at a time).  CTAs take a ticket at start and process slots in ticket order, so a waiting
-// row's dependencies are always in CTAs that are already running or finished: no deadlock.
+// thousands for a random band).  Here a whole sweep is ONE kernel.  The host lists the rows level
+// by level ("slots"; each level padded to a multiple of 32 with -1 so that no warp straddles two
+// levels => lanes of a warp never wait on each other) and stores the triangular factor in that
+// order as SELL-32: the 32 rows of a warp form a slice, entry q of lane l sits at
+// slice_start + 32*q + l, so every load of the factor is coalesced.  Couplings the block sweep
+// drops (OpenMP block-SSOR) are removed on the host.  The output vector itself carries the "done"
+// signal: it is pre-filled with a signalling-NaN pattern that no IEEE operation can produce, and a
+// row reads a neighbour by polling until the pattern is gone.
+//
+// What bounds a sweep is the dependency depth times the time of one hop (publish -> L2 -> poll).
+// Round 1's kernel let every waiting thread poll all of its neighbours: at 256^3, 22 GB of L2
+// traffic for 1.3 GB of DRAM traffic, L2 at 71 % of peak and 3 us per hop
+// (profiles/r02_ncu_ssor_v1.txt).  Now
+//   * a warp first polls ONE address -- the neighbour of its 32 rows that sits latest in slot
+//     order (found by the host) -- all lanes the same sector, and only then collects its own
+//     neighbours (normally all there on the first try);
+//   * everything that does not depend on a neighbour (slot -> row, row length, first batch of
+//     the factor, in[i], wd[i]) is loaded before the first poll;
+//   * the grid is persistent (CTAs take tickets of 128 slots in slot order), which bounds the
+//     number of waiting warps; a waiting row's dependencies are always in CTAs that hold an
+//     earlier ticket, i.e. are running or finished: no deadlock.
 // Each row still subtracts its products in storage order => same bits as the level-launched
 // sweep and as the reference loop (src/matrix/lis_matrix_csr.c:1578-1628).
-//   forward : w[i] = (b[i] - sum_{L, in block} L*w[jj]) * wd[i]          (w pre-filled)
-//   backward: x[i] = w[i] - (sum_{U, in block} U*x[jj]) * wd[i]          (x pre-filled)
 constexpr unsigned long long kNotReady = 0x7ff4c0dedeadbeefull;     // sNaN payload: never a result
 
 #ifndef LISB_EMU
@@ -93,116 +104,120 @@ fill_not_ready_kernel(int n, double *x)
 
 // kMode selects the row formula (all sums in storage order, unfused):
 //   kSweepFwd   out[i] = (in[i] - sum v*out[jj]) * wd[i]        SSOR forward, (D/w+L)^-1, ILU's U solve
-//   kSweepBwd   out[i] = in[i] - (sum v*out[jj]) * wd[i]        SSOR backward
 //   kSweepPlain out[i] = in[i] - sum v*out[jj]                  unit-diagonal solve (ILU's L solve)
 //   kSweepReadScaled out[i] = in[i] - sum v*(out[jj]*wd[jj])    first half of the transposed SSOR sweep
-// kMasked: drop couplings outside the row's block (block-SSOR of the OpenMP reference); the
-// unmasked instantiations take a triangular factor that was already filtered on the host.
-enum { kSweepFwd = 0, kSweepBwd = 1, kSweepPlain = 2, kSweepReadScaled = 3 };
+//   kSweepBwd   out[i] = in[i] - (sum v*out[jj]) * wd[i]        SSOR backward
+enum { kSweepFwd = 0, kSweepPlain = 1, kSweepReadScaled = 2, kSweepBwd = 3 };
+constexpr int kSweepThreads = 128;
 
-template <int kMode, bool kMasked>
-__global__ void __launch_bounds__(128)
-ssor_syncfree_kernel(int nslots, const int *__restrict__ order,
-                     const int *__restrict__ pptr, const int *__restrict__ pidx, const double *__restrict__ pval,
-                     const double *__restrict__ wd, const int *__restrict__ blk_start, const int *__restrict__ blk_end,
-                     const double *__restrict__ in /* b (forward) or w (backward) */, double *out, unsigned int *ticket)
+template <int kMode>
+__global__ void __launch_bounds__(kSweepThreads, 8)
+sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restrict__ wptr,
+                  const int *__restrict__ plen, const int *__restrict__ wdep,
+                  const int *__restrict__ sidx, const double *__restrict__ sval,
+                  const double *__restrict__ wd, const double *__restrict__ in, double *out, unsigned int *ticket)
 {
-    __shared__ unsigned int vblock;
-    if (threadIdx.x == 0) vblock = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int k = (int)vblock * blockDim.x + threadIdx.x;
-    if (k >= nslots) return;
-    const int i = order[k];
-    if (i < 0) return;
-    constexpr bool kForward = kMode != kSweepBwd;
-    const int lo = kMasked ? blk_start[i] : 0, hi = kMasked ? blk_end[i] : 0x7fffffff;
-    double t = kForward ? in[i] : 0.0;
-    const int e = pptr[k + 1];
+    __shared__ unsigned int vblock[2];
+    constexpr bool kSub = kMode != kSweepBwd;       // running value starts at in[i] and products are subtracted
     constexpr int kBatch = 8;
-    for (int j0 = pptr[k]; j0 < e; j0 += kBatch) {
+    if (threadIdx.x == 0) vblock[0] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    for (int round = 0;; round ^= 1) {
+        const long long k0 = (long long)vblock[round] * kSweepThreads;
+        if (k0 >= nslots) break;
+        // the next ticket is on its way while this block's rows are worked on
+        unsigned int next_ticket = 0;
+        if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
+        const int k = (int)k0 + threadIdx.x;
+        const int i = k < nslots ? order[k] : -1;    // nslots is a multiple of 32: whole warps; -1: padding lane
+        if (i >= 0) {
+        const int w = k >> 5, lane = k & 31;
+        const int len = plen[k];
+        const int dep = wdep[w];
+        const int *ci = sidx + (size_t)wptr[w] + lane;
+        const double *cv = sval + (size_t)wptr[w] + lane;
+        const double inv = in[i];
+        const double wdv = (kMode == kSweepFwd || kMode == kSweepBwd) ? wd[i] : 0.0;
         int jj[kBatch];
-        double v[kBatch], xv[kBatch];
-        unsigned int pending = 0, used = 0;
+        double v[kBatch];
 #pragma unroll
         for (int q = 0; q < kBatch; ++q) {
-            const int j = min(j0 + q, e - 1);
-            jj[q] = pidx[j];
-            v[q] = pval[j];
-            const bool inblk = !kMasked || (kForward ? (jj[q] >= lo) : (jj[q] >= lo && jj[q] < hi));   // else: coupling dropped
-            if (j0 + q < e && inblk) used |= 1u << q;
-            xv[q] = 0.0;
+            const int qq = q < len ? q : 0;
+            jj[q] = len > 0 ? ci[32 * qq] : 0;
+            v[q] = len > 0 ? cv[32 * qq] : 0.0;
         }
-        pending = used;
-        while (pending) {
+        // the warp's latest neighbour: one sector per poll for the whole warp
+        if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+        double t = kSub ? inv : 0.0;
+        for (int q0 = 0; q0 < len; q0 += kBatch) {
+            double xv[kBatch];
+            unsigned int used = 0;
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
+            unsigned int pending = used;
+            while (pending) {
+#pragma unroll
+                for (int q = 0; q < kBatch; ++q)
+                    if (pending & (1u << q)) {
+                        const unsigned long long bits = ld_poll(out + jj[q]);
+                        if (bits != kNotReady) { xv[q] = __longlong_as_double((long long)bits); pending &= ~(1u << q); }
+                    }
+            }
 #pragma unroll
             for (int q = 0; q < kBatch; ++q)
-                if (pending & (1u << q)) {
-                    const unsigned long long bits = ld_poll(out + jj[q]);
-                    if (bits != kNotReady) { xv[q] = __longlong_as_double((long long)bits); pending &= ~(1u << q); }
+                if (used & (1u << q)) {
+                    if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
+                    t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
                 }
-        }
+            if (q0 + kBatch < len) {
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q)
-            if (used & (1u << q)) {
-                if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
-                t = kForward ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
+                for (int q = 0; q < kBatch; ++q) {
+                    const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
+                    jj[q] = ci[32 * (size_t)qq];
+                    v[q] = cv[32 * (size_t)qq];
+                }
             }
+        }
+        st_publish(out + i, kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t);
+        }
+        if (threadIdx.x == 0) vblock[round ^ 1] = next_ticket;
+        __syncthreads();
     }
-    st_publish(out + i, kMode == kSweepFwd ? mul(t, wd[i]) : kMode == kSweepBwd ? sub(in[i], mul(t, wd[i])) : t);
 }
 
 }  // namespace lisb
 
 using namespace lisb;
 
-extern "C" int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *d_order,
-                                           const int *d_pptr, const int *d_pidx, const double *d_pval,
-                                           const double *d_wd, const int *d_rowblk_start, const int *d_rowblk_end,
-                                           const double *d_in, double *d_out, unsigned int *d_ticket, void *stream)
+/* One-launch triangular sweep on a host-prepared factor (rows in dependency-level order, SELL-32
+ * slices, dropped couplings already removed); see include/lis_b200_kernels.h. */
+extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
+                                  const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,
+                                  const double *d_wd, const double *d_in, double *d_out,
+                                  unsigned int *d_ticket, int ctas_per_sm, void *stream)
 {
     if (nslots <= 0 || n <= 0) return 0;
+    if (mode < 0 || mode > 3 || (mode != kSweepPlain && d_wd == nullptr) || (nslots & 31)) return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
     int fill_grid = (n + 255) / 256;
-    if (fill_grid > 148 * 8) fill_grid = 148 * 8;
+    if (fill_grid > sms * 8) fill_grid = sms * 8;
     fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
-    const int grid = (nslots + 127) / 128;
-    if (forward)
-        ssor_syncfree_kernel<kSweepFwd, true><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
-                                                        d_rowblk_end, d_in, d_out, d_ticket);
-    else
-        ssor_syncfree_kernel<kSweepBwd, true><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, d_rowblk_start,
-                                                         d_rowblk_end, d_in, d_out, d_ticket);
-    LISB_CHECK_LAUNCH();
-    return 0;
-}
-
-/* One-launch triangular solve on a host-prepared factor (levels concatenated, padded to warps,
- * entries permuted into slot order): mode 0 = scaled, 1 = plain, 2 = neighbours scaled on read. */
-extern "C" int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *d_order,
-                                       const int *d_pptr, const int *d_pidx, const double *d_pval,
-                                       const double *d_wd, const double *d_in, double *d_out,
-                                       unsigned int *d_ticket, void *stream)
-{
-    if (nslots <= 0 || n <= 0) return 0;
-    if (mode < 0 || mode > 2 || (mode != 1 && d_wd == nullptr)) return (int)cudaErrorInvalidValue;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return (int)e;
-    int fill_grid = (n + 255) / 256;
-    if (fill_grid > 148 * 8) fill_grid = 148 * 8;
-    fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
-    const int grid = (nslots + 127) / 128;
-    if (mode == 0)
-        ssor_syncfree_kernel<kSweepFwd, false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, nullptr,
-                                                                     nullptr, d_in, d_out, d_ticket);
-    else if (mode == 1)
-        ssor_syncfree_kernel<kSweepPlain, false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, nullptr, nullptr,
-                                                                       nullptr, d_in, d_out, d_ticket);
-    else
-        ssor_syncfree_kernel<kSweepReadScaled, false><<<grid, 128, 0, st>>>(nslots, d_order, d_pptr, d_pidx, d_pval, d_wd, nullptr,
-                                                                            nullptr, d_in, d_out, d_ticket);
+    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
+    int grid = (nslots + kSweepThreads - 1) / kSweepThreads;
+    if (grid > sms * ctas_per_sm) grid = sms * ctas_per_sm;
+    switch (mode) {
+    case kSweepFwd: sweep_sell_kernel<kSweepFwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
+    case kSweepPlain: sweep_sell_kernel<kSweepPlain><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
+    case kSweepReadScaled: sweep_sell_kernel<kSweepReadScaled><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
+    default: sweep_sell_kernel<kSweepBwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
+    }
     LISB_CHECK_LAUNCH();
     return 0;
 }

@@ -217,41 +217,25 @@ int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const
     }
     return 0;
 }
-int lisb200_sptrsv_syncfree(int mode, int n, int nslots, const int *order, const int *pp, const int *pi, const double *pv,
-                            const double *wd, const double *in, double *out, unsigned int *ticket, void *s)
-{
-    (void)ticket; (void)s;
-    for (int i = 0; i < n; i++) out[i] = NAN;
-    for (int k = 0; k < nslots; k++) {
-        const int i = order[k];
-        if (i < 0) continue;
-        double t = in[i];
-        for (int j = pp[k]; j < pp[k + 1]; j++) {
-            const int jj = pi[j];
-            const double xv = mode == 2 ? out[jj] * wd[jj] : out[jj];
-            t -= pv[j] * xv;
-        }
-        out[i] = mode == 0 ? t * wd[i] : t;
-    }
-    return 0;
-}
 /* slots are in dependency (level) order, so a sequential walk is a valid schedule */
-int lisb200_ssor_sweep_syncfree(int forward, int n, int nslots, const int *order, const int *pp, const int *pi, const double *pv,
-                                const double *wd, const int *bs, const int *be, const double *in, double *out,
-                                unsigned int *ticket, void *s)
+int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int *wptr, const int *plen, const int *wdep,
+                       const int *sidx, const double *sval, const double *wd, const double *in, double *out,
+                       unsigned int *ticket, int ctas, void *s)
 {
-    (void)ticket; (void)s;
+    (void)ticket; (void)s; (void)ctas; (void)wdep;
     for (int i = 0; i < n; i++) out[i] = NAN;              /* a row read before it was written would poison the result */
     for (int k = 0; k < nslots; k++) {
         const int i = order[k];
         if (i < 0) continue;
-        double t = forward ? in[i] : 0.0;
-        for (int j = pp[k]; j < pp[k + 1]; j++) {
-            const int jj = pi[j];
-            if (forward ? (jj < bs[i]) : (jj < bs[i] || jj >= be[i])) continue;
-            if (forward) t -= pv[j] * out[jj]; else t += pv[j] * out[jj];
+        const size_t base = (size_t)wptr[k >> 5] + (size_t)(k & 31);
+        double t = mode == 3 ? 0.0 : in[i];
+        for (int q = 0; q < plen[k]; q++) {
+            const int jj = sidx[base + 32 * (size_t)q];
+            const double v = sval[base + 32 * (size_t)q];
+            const double xv = mode == 2 ? out[jj] * wd[jj] : out[jj];
+            if (mode == 3) t += v * xv; else t -= v * xv;
         }
-        out[i] = forward ? t * wd[i] : in[i] - t * wd[i];
+        out[i] = mode == 0 ? t * wd[i] : mode == 3 ? in[i] - t * wd[i] : t;
     }
     return 0;
 }
