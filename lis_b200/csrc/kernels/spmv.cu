@@ -359,6 +359,9 @@ dia_kernel(int n, int xlen, int nnd, int ld, const int *__restrict__ off,
 // ---- JAD -------------------------------------------------------------------------------
 // w[i] = sum_j value[jptr[j]+i]*x[index[jptr[j]+i]] for all j with i < jptr[j+1]-jptr[j];
 // y[perm[i]] = w[i]                                                (lis_matvec_jad.c:171-196)
+// A row sits in the first `cnt` jagged diagonals (their lengths never increase), so the trip count
+// is known up front: four diagonals' index/value loads and x gathers are in flight before the first
+// add (round 1 walked one diagonal at a time behind a data-dependent break: 0.72 of the HBM peak).
 __global__ void __launch_bounds__(256)
 jad_kernel(int n, int maxnzr, const int *__restrict__ jptr, const int *__restrict__ perm,
            const int *__restrict__ idx, const double *__restrict__ val,
@@ -373,72 +376,116 @@ jad_kernel(int n, int maxnzr, const int *__restrict__ jptr, const int *__restric
     const int *jp = cached ? sjp : jptr;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double t = 0.0;
-    // jagged diagonals have non-increasing length, so row i is in diagonals 0..k-1
-    for (int j = 0; j < maxnzr; ++j) {
-        const int s = jp[j];
-        if (i >= jp[j + 1] - s) break;
-        const size_t o = (size_t)s + i;
-        t = add(t, mul(ld_stream(val + o), __ldg(x + ld_stream(idx + o))));
+    const int out = __ldg(perm + i);
+    // cnt = number of diagonals longer than i (binary search over the non-increasing lengths)
+    int lo = 0, hi = maxnzr;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (jp[mid + 1] - jp[mid] > i) lo = mid + 1; else hi = mid;
     }
-    y[perm[i]] = t;
+    const int cnt = lo;
+    double t = 0.0;
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+        const size_t o0 = (size_t)jp[j] + i, o1 = (size_t)jp[j + 1] + i, o2 = (size_t)jp[j + 2] + i, o3 = (size_t)jp[j + 3] + i;
+        const int c0 = ld_stream(idx + o0), c1 = ld_stream(idx + o1), c2 = ld_stream(idx + o2), c3 = ld_stream(idx + o3);
+        const double v0 = ld_stream(val + o0), v1 = ld_stream(val + o1), v2 = ld_stream(val + o2), v3 = ld_stream(val + o3);
+        const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+        t = add(t, mul(v0, x0)); t = add(t, mul(v1, x1)); t = add(t, mul(v2, x2)); t = add(t, mul(v3, x3));
+    }
+    if (j < cnt) {                           // 1..3 left: same loads, the missing ones clamped to the last valid diagonal
+        const int r = cnt - j;
+        const size_t o0 = (size_t)jp[j] + i, o1 = (size_t)jp[j + (r > 1 ? 1 : 0)] + i, o2 = (size_t)jp[j + (r > 2 ? 2 : 0)] + i;
+        const int c0 = ld_stream(idx + o0), c1 = ld_stream(idx + o1), c2 = ld_stream(idx + o2);
+        const double v0 = ld_stream(val + o0), v1 = ld_stream(val + o1), v2 = ld_stream(val + o2);
+        const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2);
+        t = add(t, mul(v0, x0));
+        if (r > 1) t = add(t, mul(v1, x1));
+        if (r > 2) t = add(t, mul(v2, x2));
+    }
+    y[out] = t;
 }
 
 // ---- BSR -------------------------------------------------------------------------------
 // per block row bi: t[0..bnr) = 0; for each block bc (storage order): for j<bnc, for i<bnr:
 //   t[i] += value[bc*bs + j*bnr + i] * x[bindex[bc]*bnc + j]       (lis_matvec_bsr.c:134-146)
 // The unrolled RxC kernels of the reference accumulate each t[i] in exactly this order.
+// Block-row tile kernel for the 4x4 table of block shapes (2x2 is the reference's default).
+// Round 1 ran a thread per block row: every thread walked its own 36-byte-strided run of blocks and
+// DRAM moved 3.4x the algorithmic bytes (profiles/r02_ncu_bsr_v1.txt, 0.25 of the HBM peak at 512^3).
+// Here a CTA owns kBsrRows consecutive block rows, i.e. ONE contiguous slice of value[]: phase 1
+// streams that slice with coalesced loads (element e of the slice belongs to block e / (R*C),
+// column (e % (R*C)) / R), multiplies by the matching x entry and parks the rounded product in
+// shared memory; phase 2 lets thread r add the products of block row r in the reference's order --
+// block by block, inside a block column by column, t[i] += a[j*R+i]*x[j] (lis_matvec_bsr.c:134-146,
+// 338-343) -- so the bits are the reference's.
+constexpr int kBsrRows = 256;             // block rows per CTA == threads per CTA
+constexpr int kBsrTileDoubles = 4096;     // products per shared-memory window (32 KB)
+
 template <int R, int C>
-__global__ void __launch_bounds__(128)
-bsr_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
-           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+__global__ void __launch_bounds__(kBsrRows)
+bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
+                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
 {
-    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi >= nr) return;
+    constexpr int BS = R * C;
+    constexpr bool kVec = (BS % 2) == 0;                       // a slice then starts 16-byte aligned
+    constexpr int W = (kBsrTileDoubles / (2 * BS)) * (2 * BS); // whole blocks, even element count
+    __shared__ __align__(16) double prod[W];
+    const int tid = threadIdx.x;
+    const int br0 = blockIdx.x * kBsrRows;
+    const int brend = min(br0 + kBsrRows, nr);
+    const int bi = br0 + tid;
+    const bool ok = bi < nr;
+    const long long e0 = (long long)__ldg(bptr + br0) * BS, e1 = (long long)__ldg(bptr + brend) * BS;
+    long long ps = e1, pe = e1;
+    if (ok) { ps = (long long)__ldg(bptr + bi) * BS; pe = (long long)__ldg(bptr + bi + 1) * BS; }
     double t[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) t[i] = 0.0;
-    const int s = __ldg(bptr + bi), e = __ldg(bptr + bi + 1);
-    for (int bc = s; bc < e; ++bc) {
-        const int bj = __ldg(bidx + bc) * C;
-        const double *v = val + (size_t)bc * (R * C);
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            // a padded last block column holds structural zeros; x behind them does not exist
-            const double xj = bj + j < n ? __ldg(x + bj + j) : 0.0;
-#pragma unroll
-            for (int i = 0; i < R; ++i) t[i] = add(t[i], mul(__ldg(v + j * R + i), xj));
+    for (long long w = e0; w < e1; w += W) {
+        const long long wend = w + W < e1 ? w + W : e1;
+        // ---- phase 1: products of elements [w, wend)
+        if (kVec) {
+            for (long long e = w + 2 * tid; e < wend; e += 2 * kBsrRows) {
+                const double2 a = ld_stream2(reinterpret_cast<const double2 *>(val + e));
+                const long long b = e / BS;
+                const int rem = (int)(e - b * BS);             // even; rem and rem+1 share the column when R is even
+                const int col0 = __ldg(bidx + b) * C + rem / R;
+                const int col1 = __ldg(bidx + b) * C + (rem + 1) / R;
+                // a padded last block column holds structural zeros; x behind them does not exist
+                const double x0 = col0 < n ? __ldg(x + col0) : 0.0;
+                const double x1 = col1 < n ? __ldg(x + col1) : 0.0;
+                *reinterpret_cast<double2 *>(prod + (e - w)) = make_double2(mul(a.x, x0), mul(a.y, x1));
+            }
+        } else {
+            for (long long e = w + tid; e < wend; e += kBsrRows) {
+                const double a = ld_stream(val + e);
+                const long long b = e / BS;
+                const int rem = (int)(e - b * BS);
+                const int col = __ldg(bidx + b) * C + rem / R;
+                prod[e - w] = mul(a, col < n ? __ldg(x + col) : 0.0);
+            }
         }
-    }
+        __syncthreads();
+        // ---- phase 2: ordered sums of this thread's block row inside the window (window and row
+        // bounds are whole blocks)
+        {
+            const long long s = ps > w ? ps : w, e = pe < wend ? pe : wend;
+            for (long long k = s; k < e; k += BS) {
+                const double *p = prod + (k - w);
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-        if (bi * R + i < n) y[bi * R + i] = t[i];
-}
-
-// 2x2 blocks (the reference's default block size, src/matrix/lis_matrix.c:83-84): a block is two
-// 128-bit loads, its two x entries one (x and val 16-byte aligned: block columns start at even
-// positions).  Same products in the same order as bsr_kernel<2,2>:
-//   t0 += a0*x0; t1 += a1*x0; t0 += a2*x1; t1 += a3*x1          (lis_matvec_bsr.c:338-343)
-__global__ void __launch_bounds__(128)
-bsr22_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
-             const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
-{
-    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi >= nr) return;
-    double t0 = 0.0, t1 = 0.0;
-    const int s = __ldg(bptr + bi), e = __ldg(bptr + bi + 1);
-    for (int bc = s; bc < e; ++bc) {
-        const int c = __ldg(bidx + bc) * 2;
-        const double2 a01 = ld_stream2(reinterpret_cast<const double2 *>(val + (size_t)bc * 4));
-        const double2 a23 = ld_stream2(reinterpret_cast<const double2 *>(val + (size_t)bc * 4 + 2));
-        double x0, x1;
-        if (c + 1 < n) { const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + c)); x0 = xv.x; x1 = xv.y; }
-        else { x0 = __ldg(x + c); x1 = 0.0; }
-        t0 = add(t0, mul(a01.x, x0)); t1 = add(t1, mul(a01.y, x0));
-        t0 = add(t0, mul(a23.x, x1)); t1 = add(t1, mul(a23.y, x1));
+                for (int j = 0; j < C; ++j)
+#pragma unroll
+                    for (int i = 0; i < R; ++i) t[i] = add(t[i], p[j * R + i]);
+            }
+        }
+        __syncthreads();
     }
-    if (2 * bi + 1 < n) *reinterpret_cast<double2 *>(y + 2 * bi) = make_double2(t0, t1);
-    else y[2 * bi] = t0;
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            if (bi * R + i < n) y[bi * R + i] = t[i];
+    }
 }
 
 // generic block size (bnr or bnc > 4): one thread per scalar row, same per-row order
@@ -465,12 +512,12 @@ template <int R>
 static int launch_bsr_c(int n, int nr, int bnc, const int *bptr, const int *bidx, const double *val,
                         const double *x, double *y, cudaStream_t st)
 {
-    const int grid = (nr + 127) / 128;
+    const int grid = (nr + kBsrRows - 1) / kBsrRows;
     switch (bnc) {
-    case 1: bsr_kernel<R, 1><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
-    case 2: bsr_kernel<R, 2><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
-    case 3: bsr_kernel<R, 3><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
-    case 4: bsr_kernel<R, 4><<<grid, 128, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 1: bsr_tile_kernel<R, 1><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 2: bsr_tile_kernel<R, 2><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 3: bsr_tile_kernel<R, 3><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 4: bsr_tile_kernel<R, 4><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
     default: return -1;
     }
     return 0;
@@ -698,12 +745,7 @@ extern "C" int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bp
     if (n <= 0 || nr <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = -1;
-    if (bnr == 2 && bnc == 2 && (((uintptr_t)d_val | (uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0) {
-        bsr22_kernel<<<(nr + 127) / 128, 128, 0, st>>>(n, nr, d_bptr, d_bidx, d_val, d_x, d_y);
-        LISB_CHECK_LAUNCH();
-        return 0;
-    }
-    if (bnc >= 1 && bnc <= 4) {
+    if (bnc >= 1 && bnc <= 4 && ((uintptr_t)d_val & 15) == 0) {
         switch (bnr) {
         case 1: rc = launch_bsr_c<1>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
         case 2: rc = launch_bsr_c<2>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;

@@ -65,12 +65,16 @@ def test_spmv_csr_both_kernels(b200, oracle, monkeypatch):
     H.assert_bits_equal(y, oracle.spmv("csr", ptr, idx, val, x), "tma/27pt")
 
 
-@pytest.mark.parametrize("bnr,bnc", [(1, 1), (1, 3), (2, 2), (3, 2), (4, 4), (3, 4), (5, 2), (2, 6)])
+@pytest.mark.parametrize("bnr,bnc", [(r, c) for r in (1, 2, 3, 4) for c in (1, 2, 3, 4)] + [(5, 2), (2, 6)])
 def test_spmv_bsr_block_shapes(b200, oracle, bnr, bnc):
-    ptr, idx, val = H.random_csr(1003, 6, 21)
-    x = H.rand_vec(1003, 6, "wide")
-    y, _ = b200.spmv("bsr", ptr, idx, val, x, bnr=bnr, bnc=bnc)
-    H.assert_bits_equal(y, oracle.spmv("bsr", ptr, idx, val, x, bnr=bnr, bnc=bnc), f"bsr {bnr}x{bnc}")
+    """the block-row tile kernel for the 4x4 table (every shape its own instantiation; 1003 rows: the last block row
+    and block column are padded) and the generic kernel beyond it; a second matrix with long rows makes one block
+    row span several shared-memory windows"""
+    for n, per_row, seed in ((1003, 6, 21), (700, 90, 22)):
+        ptr, idx, val = H.random_csr(n, per_row, seed)
+        x = H.rand_vec(n, 6, "wide")
+        y, _ = b200.spmv("bsr", ptr, idx, val, x, bnr=bnr, bnc=bnc)
+        H.assert_bits_equal(y, oracle.spmv("bsr", ptr, idx, val, x, bnr=bnr, bnc=bnc), f"bsr {bnr}x{bnc} n={n}")
 
 
 def test_spmv_csr_split_order(b200, oracle):
