@@ -111,7 +111,7 @@ enum { kSweepFwd = 0, kSweepPlain = 1, kSweepReadScaled = 2, kSweepBwd = 3 };
 constexpr int kSweepThreads = 128;
 
 template <int kMode>
-__global__ void __launch_bounds__(kSweepThreads, 8)
+__global__ void __launch_bounds__(kSweepThreads, 6)
 sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restrict__ wptr,
                   const int *__restrict__ plen, const int *__restrict__ wdep,
                   const int *__restrict__ sidx, const double *__restrict__ sval,
@@ -129,56 +129,63 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
         unsigned int next_ticket = 0;
         if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
         const int k = (int)k0 + threadIdx.x;
-        const int i = k < nslots ? order[k] : -1;    // nslots is a multiple of 32: whole warps; -1: padding lane
-        if (i >= 0) {
-        const int w = k >> 5, lane = k & 31;
-        const int len = plen[k];
-        const int dep = wdep[w];
-        const int *ci = sidx + (size_t)wptr[w] + lane;
-        const double *cv = sval + (size_t)wptr[w] + lane;
-        const double inv = in[i];
-        const double wdv = (kMode == kSweepFwd || kMode == kSweepBwd) ? wd[i] : 0.0;
-        int jj[kBatch];
-        double v[kBatch];
-#pragma unroll
-        for (int q = 0; q < kBatch; ++q) {
-            const int qq = q < len ? q : 0;
-            jj[q] = len > 0 ? ci[32 * qq] : 0;
-            v[q] = len > 0 ? cv[32 * qq] : 0.0;
-        }
-        // the warp's latest neighbour: one sector per poll for the whole warp
-        if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
-        double t = kSub ? inv : 0.0;
-        for (int q0 = 0; q0 < len; q0 += kBatch) {
-            double xv[kBatch];
-            unsigned int used = 0;
-#pragma unroll
-            for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
-            unsigned int pending = used;
-            while (pending) {
-#pragma unroll
-                for (int q = 0; q < kBatch; ++q)
-                    if (pending & (1u << q)) {
-                        const unsigned long long bits = ld_poll(out + jj[q]);
-                        if (bits != kNotReady) { xv[q] = __longlong_as_double((long long)bits); pending &= ~(1u << q); }
-                    }
-            }
-#pragma unroll
-            for (int q = 0; q < kBatch; ++q)
-                if (used & (1u << q)) {
-                    if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
-                    t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
-                }
-            if (q0 + kBatch < len) {
+        if (k < nslots) {                            // nslots is a multiple of 32: whole warps
+            // first wave: nothing here depends on another load
+            const int w = k >> 5, lane = k & 31;
+            const int i = order[k];                  // -1: padding lane
+            const int len = plen[k];
+            const int dep = wdep[w];
+            const size_t base = (size_t)wptr[w] + lane;
+            if (i >= 0) {
+                // second wave: the row's operands and its first batch of the factor
+                const int *ci = sidx + base;
+                const double *cv = sval + base;
+                const double inv = in[i];
+                const double wdv = (kMode == kSweepFwd || kMode == kSweepBwd) ? wd[i] : 0.0;
+                int jj[kBatch];
+                double v[kBatch];
 #pragma unroll
                 for (int q = 0; q < kBatch; ++q) {
-                    const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
-                    jj[q] = ci[32 * (size_t)qq];
-                    v[q] = cv[32 * (size_t)qq];
+                    const int qq = q < len ? q : 0;
+                    jj[q] = len > 0 ? ci[32 * qq] : 0;
+                    v[q] = len > 0 ? cv[32 * qq] : 0.0;
                 }
+                // the warp's latest neighbour: one sector per poll for the whole warp
+                if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+                double t = kSub ? inv : 0.0;
+                for (int q0 = 0; q0 < len; q0 += kBatch) {
+                    double xv[kBatch];
+                    unsigned int used = 0;
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
+                    unsigned int pending = used;
+                    while (pending) {
+                        // all polls of the batch are issued before the first answer is looked at: one
+                        // round trip per batch, not one per neighbour
+                        unsigned long long bits[kBatch];
+#pragma unroll
+                        for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(out + jj[q]) : kNotReady;
+#pragma unroll
+                        for (int q = 0; q < kBatch; ++q)
+                            if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q)
+                        if (used & (1u << q)) {
+                            if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
+                            t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
+                        }
+                    if (q0 + kBatch < len) {
+#pragma unroll
+                        for (int q = 0; q < kBatch; ++q) {
+                            const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
+                            jj[q] = ci[32 * (size_t)qq];
+                            v[q] = cv[32 * (size_t)qq];
+                        }
+                    }
+                }
+                st_publish(out + i, kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t);
             }
-        }
-        st_publish(out + i, kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t);
         }
         if (threadIdx.x == 0) vblock[round ^ 1] = next_ticket;
         __syncthreads();
@@ -209,7 +216,7 @@ extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_orde
     int fill_grid = (n + 255) / 256;
     if (fill_grid > sms * 8) fill_grid = sms * 8;
     fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
-    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm < 1 || ctas_per_sm > 6) ctas_per_sm = 6;
     int grid = (nslots + kSweepThreads - 1) / kSweepThreads;
     if (grid > sms * ctas_per_sm) grid = sms * ctas_per_sm;
     switch (mode) {
