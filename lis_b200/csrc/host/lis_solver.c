@@ -687,8 +687,10 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
         }
     }
     {
-        /* symmetric scaling solved for D^1/2 x: x = xx .* d (:877-886) */
-        LIS_INT e2 = (scale == LIS_SCALE_SYMM_DIAG && solver->d) ? lisd_pmul(xx, solver->d, x) : lisd_copy(xx, x);
+        /* symmetric scaling solved for D^1/2 x: x = xx .* d -- not under I+S, whose unit-diagonal scaling is a left
+         * scaling only, whatever -scale says (src/solver/lis_solver.c:877-886) */
+        LIS_INT e2 = (scale == LIS_SCALE_SYMM_DIAG && precon_type != LIS_PRECON_TYPE_IS && solver->d) ? lisd_pmul(xx, solver->d, x)
+                                                                                                       : lisd_copy(xx, x);
         if (!e2) e2 = lisd_sync();
         if (e2) { lis_solver_work_destroy(solver); lis_vector_destroy(xx); return e2; }
     }

@@ -119,3 +119,21 @@ def test_symmetry_and_linearity(big):
     spmv_tma(big, z, az)
     err = (az - (a * ax + b_ * ay)).abs().max().item()
     assert err <= 256 * np.finfo(float).eps * 12.0, err       # |row sum| <= 12 * max|z|, a few roundings each side
+
+
+@pytest.mark.parametrize("grid", [256, 512])
+def test_cg_jacobi_to_1e12_iteration_count_equals_reference(b200, grid):
+    """BASELINE.json config 3 at its stated size: test/test3.c's system (7-pt Poisson, rows in test3.c order, b = A*1,
+    x0 = 0), `-i cg -p jacobi -tol 1e-12` through lis_solve on the GPU against the compiled reference's run of the same
+    system (tests/golden/cg_poisson_<grid>.npz, made by tests/golden/make_cg_fullsize.py with the OpenMP build):
+    identical iteration count (764 at 256^3, 1504 at 512^3); residual history within the reference's own
+    thread-count envelope (~1e-12..1e-9 relative over the first three quarters, growing
+    towards convergence where conditioning takes over); solution error of the same size as the reference's."""
+    import bench
+    out = bench.cg_to_convergence(b200.lib, grid)
+    assert out["reference_iters"] is not None, out["reference_source"]
+    assert out["cg_iters_to_1e-12"] == out["reference_iters"], out
+    assert out["cg_final_relres"] < 1e-12
+    assert out["history_gap_first_three_quarters"] < 1e-8, out
+    assert out["history_gap"] < 5e-2, out
+    assert out["cg_max_abs_x_minus_1"] < 1e-9

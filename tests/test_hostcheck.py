@@ -344,7 +344,8 @@ def test_ilut_preconditioner_bit_for_bit(hc, ref_serial, opts):
 
 
 @pytest.mark.parametrize("opts", ["-i cg -p is", "-i bicgstab -p is", "-i gmres -p is -is_alpha 0.5", "-i bicgstab -p is -is_m 1",
-                                  "-i bicgstab -p is -is_m 10 -is_alpha 0.3", "-i bicg -p is"])
+                                  "-i bicgstab -p is -is_m 10 -is_alpha 0.3", "-i bicg -p is",
+                                  "-i bicgstab -p is -scale symm_diag", "-i cg -p is -scale symm_diag", "-i gmres -p is -scale jacobi"])
 def test_is_preconditioner(hc, ref_serial, opts):
     """-p is (I+S at its default level, src/precon/lis_precon_is.c): the system is scaled to a unit diagonal, split, and
     M^-1 = I - alpha*S with S the first is_m+1 strict-upper entries of each row -- one CSR product and one axpyz.
