@@ -422,6 +422,11 @@ jad_kernel(int n, int maxnzr, const int *__restrict__ jptr, const int *__restric
 constexpr int kBsrRows = 256;             // block rows per CTA == threads per CTA
 constexpr int kBsrTileDoubles = 4096;     // products per shared-memory window (32 KB)
 
+// Shared-memory layout of a window: component-major -- product (block b, element c of the block)
+// at prod[c * WB + b] -- so that in phase 2 the lanes of a warp (consecutive block rows, i.e. block
+// offsets a row length apart) read 8-byte words a row length apart: conflict-free for the odd and
+// 2-way for the even row lengths of stencils, where the block-major layout of the first version was
+// 8-way (32-byte blocks 7 blocks apart; profiles/r02_ncu_bsr_v2.txt).
 template <int R, int C>
 __global__ void __launch_bounds__(kBsrRows)
 bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
@@ -429,54 +434,76 @@ bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restri
 {
     constexpr int BS = R * C;
     constexpr bool kVec = (BS % 2) == 0;                       // a slice then starts 16-byte aligned
-    constexpr int W = (kBsrTileDoubles / (2 * BS)) * (2 * BS); // whole blocks, even element count
+    constexpr int WB = kBsrTileDoubles / BS;                   // blocks per window
+    constexpr int W = WB * BS;                                 // elements per window
+    constexpr int kPer = kVec ? 2 : 1;                         // elements per thread per step
+    constexpr int kSteps = (W + kPer * kBsrRows - 1) / (kPer * kBsrRows);
+    constexpr int kUnroll = 4;                                 // steps whose loads are in flight together
     __shared__ __align__(16) double prod[W];
     const int tid = threadIdx.x;
     const int br0 = blockIdx.x * kBsrRows;
     const int brend = min(br0 + kBsrRows, nr);
     const int bi = br0 + tid;
     const bool ok = bi < nr;
-    const long long e0 = (long long)__ldg(bptr + br0) * BS, e1 = (long long)__ldg(bptr + brend) * BS;
-    long long ps = e1, pe = e1;
-    if (ok) { ps = (long long)__ldg(bptr + bi) * BS; pe = (long long)__ldg(bptr + bi + 1) * BS; }
+    const long long b0 = __ldg(bptr + br0), b1 = __ldg(bptr + brend);       // block range of the CTA
+    long long ps = b1, pe = b1;                                            // block range of this thread's block row
+    if (ok) { ps = __ldg(bptr + bi); pe = __ldg(bptr + bi + 1); }
     double t[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) t[i] = 0.0;
-    for (long long w = e0; w < e1; w += W) {
-        const long long wend = w + W < e1 ? w + W : e1;
-        // ---- phase 1: products of elements [w, wend)
-        if (kVec) {
-            for (long long e = w + 2 * tid; e < wend; e += 2 * kBsrRows) {
-                const double2 a = ld_stream2(reinterpret_cast<const double2 *>(val + e));
-                const long long b = e / BS;
-                const int rem = (int)(e - b * BS);             // even; rem and rem+1 share the column when R is even
-                const int col0 = __ldg(bidx + b) * C + rem / R;
-                const int col1 = __ldg(bidx + b) * C + (rem + 1) / R;
-                // a padded last block column holds structural zeros; x behind them does not exist
-                const double x0 = col0 < n ? __ldg(x + col0) : 0.0;
-                const double x1 = col1 < n ? __ldg(x + col1) : 0.0;
-                *reinterpret_cast<double2 *>(prod + (e - w)) = make_double2(mul(a.x, x0), mul(a.y, x1));
+    for (long long wb = b0; wb < b1; wb += WB) {
+        const long long wbend = wb + WB < b1 ? wb + WB : b1;
+        const long long e0 = wb * BS;
+        const int cnt = (int)(wbend - wb) * BS;                // elements in this window
+        // ---- phase 1: products of the window's elements, kUnroll steps of loads in flight together
+        for (int s0 = 0; s0 < kSteps; s0 += kUnroll) {
+            double a0[kUnroll], a1[kUnroll];
+            int bcol[kUnroll], off[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                off[u] = kPer * (tid + (s0 + u) * kBsrRows);
+                const bool in = s0 + u < kSteps && off[u] < cnt;
+                a0[u] = 0.0; a1[u] = 0.0; bcol[u] = 0;
+                if (in) {
+                    if (kVec) {
+                        const double2 a = ld_stream2(reinterpret_cast<const double2 *>(val + e0 + off[u]));
+                        a0[u] = a.x; a1[u] = a.y;
+                    } else {
+                        a0[u] = ld_stream(val + e0 + off[u]);
+                    }
+                    bcol[u] = __ldg(bidx + wb + off[u] / BS) * C;
+                } else off[u] = -1;
             }
-        } else {
-            for (long long e = w + tid; e < wend; e += kBsrRows) {
-                const double a = ld_stream(val + e);
-                const long long b = e / BS;
-                const int rem = (int)(e - b * BS);
-                const int col = __ldg(bidx + b) * C + rem / R;
-                prod[e - w] = mul(a, col < n ? __ldg(x + col) : 0.0);
+            double x0[kUnroll], x1[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                x0[u] = 0.0; x1[u] = 0.0;
+                if (off[u] >= 0) {
+                    const int rem = off[u] % BS;
+                    // a padded last block column holds structural zeros; x behind them does not exist
+                    const int c0 = bcol[u] + rem / R;
+                    x0[u] = c0 < n ? __ldg(x + c0) : 0.0;
+                    if (kVec) { const int c1 = bcol[u] + (rem + 1) / R; x1[u] = c1 < n ? __ldg(x + c1) : 0.0; }
+                }
             }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (off[u] >= 0) {
+                    const int bl = off[u] / BS, rem = off[u] % BS;
+                    prod[rem * WB + bl] = mul(a0[u], x0[u]);
+                    if (kVec) prod[(rem + 1) * WB + bl] = mul(a1[u], x1[u]);      // rem even, BS even: same block
+                }
         }
         __syncthreads();
-        // ---- phase 2: ordered sums of this thread's block row inside the window (window and row
-        // bounds are whole blocks)
+        // ---- phase 2: ordered sums of this thread's block row inside the window
         {
-            const long long s = ps > w ? ps : w, e = pe < wend ? pe : wend;
-            for (long long k = s; k < e; k += BS) {
-                const double *p = prod + (k - w);
+            const long long s = ps > wb ? ps : wb, e = pe < wbend ? pe : wbend;
+            for (long long kb = s; kb < e; ++kb) {
+                const double *p = prod + (kb - wb);
 #pragma unroll
                 for (int j = 0; j < C; ++j)
 #pragma unroll
-                    for (int i = 0; i < R; ++i) t[i] = add(t[i], p[j * R + i]);
+                    for (int i = 0; i < R; ++i) t[i] = add(t[i], p[(j * R + i) * WB]);
             }
         }
         __syncthreads();

@@ -71,9 +71,10 @@ ssor_bwd_kernel(int nrows, const int *__restrict__ rows,
 // Round 1's kernel let every waiting thread poll all of its neighbours: at 256^3, 22 GB of L2
 // traffic for 1.3 GB of DRAM traffic, L2 at 71 % of peak and 3 us per hop
 // (profiles/r02_ncu_ssor_v1.txt).  Now
-//   * a warp first polls ONE address -- the neighbour of its 32 rows that sits latest in slot
-//     order (found by the host) -- all lanes the same sector, and only then collects its own
-//     neighbours (normally all there on the first try);
+//   * a row polls its own neighbours once (all polls of a batch in flight together; this also pulls
+//     their sectors into L2 while the row is still levels ahead of the sweep front), then the warp
+//     waits on ONE address -- the neighbour of its 32 rows that sits latest in slot order (found
+//     by the host), all lanes the same sector -- and only then collects what was missing;
 //   * everything that does not depend on a neighbour (slot -> row, row length, first batch of
 //     the factor, in[i], wd[i]) is loaded before the first poll;
 //   * the grid is persistent (CTAs take tickets of 128 slots in slot order), which bounds the
@@ -150,9 +151,10 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
                     jj[q] = len > 0 ? ci[32 * qq] : 0;
                     v[q] = len > 0 ? cv[32 * qq] : 0.0;
                 }
-                // the warp's latest neighbour: one sector per poll for the whole warp
-                if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+                // long rows: touch the neighbours behind the first batch too (sectors into L2, values unused)
+                for (int q = kBatch; q < len; ++q) (void)ld_poll(out + ci[32 * (size_t)q]);
                 double t = kSub ? inv : 0.0;
+                bool waited = false;
                 for (int q0 = 0; q0 < len; q0 += kBatch) {
                     double xv[kBatch];
                     unsigned int used = 0;
@@ -161,13 +163,22 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
                     unsigned int pending = used;
                     while (pending) {
                         // all polls of the batch are issued before the first answer is looked at: one
-                        // round trip per batch, not one per neighbour
+                        // round trip per batch, not one per neighbour.  The first round also brings the
+                        // neighbours' sectors into L2 long before their values are published (this row
+                        // is several levels ahead of the sweep front), so the round after the wait
+                        // below is an L2 hit and not a DRAM fill.
                         unsigned long long bits[kBatch];
 #pragma unroll
                         for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(out + jj[q]) : kNotReady;
 #pragma unroll
                         for (int q = 0; q < kBatch; ++q)
                             if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
+                        if (pending && !waited) {
+                            // wait on ONE address for the whole warp -- the neighbour of its 32 rows that
+                            // sits latest in slot order -- instead of every lane polling all of its own
+                            waited = true;
+                            if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < kBatch; ++q)

@@ -601,6 +601,79 @@ EXPORT long long shim_poisson7(int l, int m, int n, int i0, int i1, int sorted, 
     return k;
 }
 
+/* Rows [i0*m*n, i1*m*n) of the 27-point stencil of test/spmvtest3b.c:148-163 / test/test3b.c:113-135
+ * on an l x m x n grid (26 on the diagonal, -1 elsewhere, the driver's loop order = ascending
+ * columns), global column indices.  ptr == NULL: entry count only. */
+EXPORT long long shim_poisson27(int l, int m, int n, int i0, int i1, int *ptr, int *idx, double *val)
+{
+    const long long mn = (long long)m * n;
+    long long ctr = 0, row = 0;
+    for (int i = i0; i < i1; i++)
+        for (int j = 0; j < m; j++)
+            for (int k = 0; k < n; k++, row++) {
+                const long long ii = (long long)i * mn + (long long)j * n + k;
+                if (ptr) ptr[row] = (int)ctr;
+                for (int si = -1; si <= 1; si++) {
+                    if (i + si < 0 || i + si >= l) continue;
+                    for (int sj = -1; sj <= 1; sj++) {
+                        if (j + sj < 0 || j + sj >= m) continue;
+                        for (int sk = -1; sk <= 1; sk++) {
+                            if (k + sk < 0 || k + sk >= n) continue;
+                            if (ptr) {
+                                const long long jj = ii + si * mn + (long long)sj * n + sk;
+                                idx[ctr] = (int)jj;
+                                val[ctr] = jj == ii ? 26.0 : -1.0;
+                            }
+                            ctr++;
+                        }
+                    }
+                }
+            }
+    if (ptr) ptr[row] = (int)ctr;
+    return ctr;
+}
+
+/* BASELINE.json config 4: rows [i0, i1) of a seeded unsymmetric banded
+ * matrix with `per_row` stored entries per row -- the diagonal at a random position of the row and
+ * per_row-1 off-diagonals in random storage order, columns within |i-j| <= band (reflected at the
+ * ends), values uniform(-1,1), diagonal = dshift + dom * sum|off-diagonals| (dom = 1, dshift = 1:
+ * strictly dominant; smaller dom: harder).  Every row is generated from its own counter-based
+ * stream (splitmix64 of seed and row number), so any row partition yields the same matrix. */
+static unsigned long long shim_sm64(unsigned long long *s)
+{
+    unsigned long long z = (*s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+EXPORT long long shim_banded_rows(int n, int i0, int i1, int per_row, int band, double dom, double dshift,
+                                  unsigned long long seed, int *ptr, int *idx, double *val)
+{
+    long long ctr = 0;
+    if (band > n - 1) band = n - 1;
+    for (int i = i0; i < i1; i++) {
+        unsigned long long s = seed ^ ((unsigned long long)(i + 1) * 0xD1B54A32D192ED03ull);
+        const int pos = (int)(shim_sm64(&s) % (unsigned long long)per_row);
+        double sumabs = 0.0;
+        ptr[i - i0] = (int)ctr;
+        for (int q = 0; q < per_row; q++, ctr++) {
+            if (q == pos) { idx[ctr] = i; val[ctr] = 0.0; continue; }
+            const long long off = 1 + (long long)(shim_sm64(&s) % (unsigned long long)(band > 0 ? band : 1));
+            long long col = (shim_sm64(&s) & 1) ? i + off : i - off;
+            if (col < 0 || col >= n) col = 2LL * i - col;             /* reflect at the ends */
+            if (col < 0) col = 0;
+            if (col >= n) col = n - 1;
+            if (col == i) col = (i + 1) % n;
+            const double v = (double)(shim_sm64(&s) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+            idx[ctr] = (int)col; val[ctr] = v;
+            sumabs += v < 0 ? -v : v;
+        }
+        val[ptr[i - i0] + pos] = dshift + dom * sumabs;
+    }
+    ptr[i1 - i0] = (int)ctr;
+    return ctr;
+}
+
 /* ------------------------------------------------------------------ bench handles
  * One matrix + x + y kept alive across steps (bench.py): open once, then time steps.
  * step_e2e is what a user with HOST buffers does per product: scatter x in, lis_matvec,
@@ -756,6 +829,43 @@ EXPORT int shim_mv_solve(int h, const char *options, int *out_i, double *out_d, 
     lis_solver_get_timeex(solver, &time, &itime, &ptime, &pc, &pi);
     out_i[0] = (int)iter; out_i[1] = (int)status;
     out_d[0] = resid; out_d[1] = time; out_d[2] = itime; out_d[3] = ptime;
+    lis_solver_destroy(solver);
+    lis_vector_destroy(u); lis_vector_destroy(b); lis_vector_destroy(x);
+    return (int)err;
+}
+
+/* lis_solve on the handle's matrix with b = A*1, x0 = 0 (test/test3.c:150-151); residual history and the
+ * times of lis_solver_get_timeex returned; out_d: resid, time, itime, ptime, wall, max|x-1| over the local rows */
+EXPORT int shim_mv_solve_ones(int h, const char *options, int *out_i, double *out_d, double *rhistory, int rh_cap)
+{
+    LIS_MATRIX A = g_mv[h].A;
+    LIS_VECTOR u, b, x;
+    LIS_SOLVER solver;
+    LIS_INT err, iter = 0, status = 0;
+    LIS_REAL resid = 0.0, dev = 0.0;
+    double time = 0, itime = 0, ptime = 0, pc = 0, pi = 0;
+    if (make_vec(A, NULL, &u) || make_vec(A, NULL, &b) || make_vec(A, NULL, &x)) return -1;
+    err = lis_vector_set_all(1.0, u); if (err) return (int)err;
+    err = lis_matvec(A, u, b); if (err) return (int)err;
+    err = lis_solver_create(&solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)"-print mem", solver); if (err) return (int)err;
+    err = lis_solver_set_option((char *)options, solver); if (err) return (int)err;
+    const double t0 = lis_wtime();
+    { const int q = quiet_begin(); err = lis_solve(A, b, x, solver); quiet_end(q); }
+    out_d[4] = lis_wtime() - t0;
+    out_i[2] = (int)err;
+    lis_solver_get_iter(solver, &iter);
+    lis_solver_get_status(solver, &status);
+    lis_solver_get_residualnorm(solver, &resid);
+    lis_solver_get_timeex(solver, &time, &itime, &ptime, &pc, &pi);
+    out_i[0] = (int)iter; out_i[1] = (int)status;
+    out_d[0] = resid; out_d[1] = time; out_d[2] = itime; out_d[3] = ptime;
+    int len = (int)iter + 1 - (status != LIS_SUCCESS ? 1 : 0);
+    if (len > rh_cap) len = rh_cap;
+    out_i[3] = 0;
+    if (!err && rhistory && len > 0 && solver->rhistory) { memcpy(rhistory, solver->rhistory, sizeof(double) * (size_t)len); out_i[3] = len; }
+    if (!err) { err = lis_vector_axpy(-1.0, x, u); if (!err) err = lis_vector_nrmi(u, &dev); }      /* u = 1 - x */
+    out_d[5] = dev;
     lis_solver_destroy(solver);
     lis_vector_destroy(u); lis_vector_destroy(b); lis_vector_destroy(x);
     return (int)err;
