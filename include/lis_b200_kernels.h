@@ -232,7 +232,7 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
  *   mode 2: out[i] =  in[i] - sum v*(out[jj]*wd[jj])     first half of the transposed SSOR sweep   src/matrix/lis_matrix_csr.c:1838-1845
  *   mode 3: out[i] =  in[i] - (sum v*out[jj]) * wd[i]    SSOR backward                   src/matrix/lis_matrix_csr.c:1593-1605, 1618-1628
  * Sums run in storage order, unfused: same result bits as the level-launched kernels and the
- * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm (1..6, else 6) bounds the persistent
+ * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm (1..8, else 8) bounds the persistent
  * grid, i.e. the number of rows waiting at any time. */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
                        const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,

@@ -215,6 +215,44 @@ void lisd_free_vector(LIS_SCALAR *value, LIS_INT managed)
     else free(value);
 }
 
+/* ---- arrays that are the public host arrays of a matrix AND its device mirror ------------------
+ * lis_matrix_convert on the device writes its result into managed memory: Aout->index / Aout->value
+ * point at it (the host may read it; pages migrate on demand), the mirror points at the same bytes,
+ * nothing is downloaded or uploaded.  lis_free() recognises such blocks through lisd_shared_release. */
+#define LISD_SHARED_MAX 1024
+static void *g_shared[LISD_SHARED_MAX];
+static int g_nshared = 0;
+
+void *lisd_shared_alloc(size_t bytes)
+{
+    if (!lisd_available() || g_nshared >= LISD_SHARED_MAX) return NULL;
+    void *p = NULL;
+    if (bytes == 0) bytes = 16;
+    if (cudaMallocManaged(&p, bytes, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    if (cudaMemPrefetchAsync(p, bytes, g_ctx.device, g_ctx.stream) != cudaSuccess) cudaGetLastError();
+    g_ctx.busy = 1;
+    g_shared[g_nshared++] = p;
+    return p;
+}
+
+int lisd_is_shared(const void *p)
+{
+    for (int i = 0; i < g_nshared; i++) if (g_shared[i] == p) return 1;
+    return 0;
+}
+
+int lisd_shared_release(void *p)
+{
+    if (p == NULL) return 0;
+    for (int i = 0; i < g_nshared; i++)
+        if (g_shared[i] == p) {
+            g_shared[i] = g_shared[--g_nshared];
+            if (g_ctx.available) { lisd_sync(); cudaFree(p); }
+            return 1;
+        }
+    return 0;
+}
+
 LIS_INT lisd_malloc(void **p, size_t bytes)
 {
     *p = NULL;

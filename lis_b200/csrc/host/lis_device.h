@@ -70,6 +70,14 @@ LIS_INT       lisd_axpy_from_slot(int slot, double scale, LIS_VECTOR x, LIS_VECT
 LIS_INT       lisd_mgs_step(int slot_in, double scale, LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR u, int slot_out, LIS_REAL *nrm2);
 
 /* ---- matrix device mirror ---- */
+#define LISD_SH_IDX 1u
+#define LISD_SH_VAL 2u
+#define LISD_SH_PERM 4u
+#define LISD_SH_BIDX 8u
+void *lisd_shared_alloc(size_t bytes);       /* managed block, resident on the device; NULL when unavailable */
+int   lisd_is_shared(const void *p);
+int   lisd_shared_release(void *p);          /* 1: p was such a block and has been freed */
+
 typedef struct lisd_csr {
     int n, nnz;
     int *ptr, *idx;
@@ -100,6 +108,7 @@ typedef struct lisd_matrix {
     int pipe_n;
     int *pipe_row, *pipe_need;
     /* transposed mirrors for lis_matvech (BiCG), built on first use */
+    unsigned shared;          /* LISD_SH_*: pointers below that are the matrix's public (managed) arrays, not the mirror's own */
     int has_t;
     lisd_csr csrT, LT, UT;
 } lisd_matrix;

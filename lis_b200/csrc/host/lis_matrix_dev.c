@@ -65,8 +65,11 @@ static void mirror_free(lisd_matrix *M)
     if (M == NULL) return;
     csr_free(&M->csr); csr_free(&M->L); csr_free(&M->U);
     csr_free(&M->csrT); csr_free(&M->LT); csr_free(&M->UT);
-    lisd_free(M->idx); lisd_free(M->off); lisd_free(M->jptr); lisd_free(M->perm);
-    lisd_free(M->bptr); lisd_free(M->bidx); lisd_free(M->val);
+    if (!(M->shared & LISD_SH_IDX)) lisd_free(M->idx);
+    if (!(M->shared & LISD_SH_PERM)) lisd_free(M->perm);
+    if (!(M->shared & LISD_SH_BIDX)) lisd_free(M->bidx);
+    if (!(M->shared & LISD_SH_VAL)) lisd_free(M->val);
+    lisd_free(M->off); lisd_free(M->jptr); lisd_free(M->bptr);
     lisd_free(M->diag); lisd_free(M->wd);
     free(M->pipe_row); free(M->pipe_need);
     if (M->sweep) lisd_sweep_free(M->sweep);

@@ -100,6 +100,7 @@ void lis_free(void *p)
 {
     size_t slot;
     if (p == NULL) return;
+    if (lisd_shared_release(p)) return;           /* a converted matrix's arrays living in managed memory */
     if (set_find(p, &slot)) { g_set[slot] = TOMB; g_set_used--; g_set_tomb++; }
     free(p);
 }

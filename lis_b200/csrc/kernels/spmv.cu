@@ -483,7 +483,10 @@ bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restri
                     // a padded last block column holds structural zeros; x behind them does not exist
                     const int c0 = bcol[u] + rem / R;
                     x0[u] = c0 < n ? __ldg(x + c0) : 0.0;
-                    if (kVec) { const int c1 = bcol[u] + (rem + 1) / R; x1[u] = c1 < n ? __ldg(x + c1) : 0.0; }
+                    if (kVec) {
+                        if (R % 2 == 0) x1[u] = x0[u];                 // rem is even: both elements sit in the same block column
+                        else { const int c1 = bcol[u] + (rem + 1) / R; x1[u] = c1 < n ? __ldg(x + c1) : 0.0; }
+                    }
                 }
             }
 #pragma unroll
