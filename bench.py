@@ -35,7 +35,12 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
 # one process per GPU: show each rank only its own device (managed vector storage would otherwise
 # be mapped into every visible peer; with 8 ranks x 8 visible GPUs cudaMallocManaged was seen to fail)
-if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "LOCAL_RANK" in os.environ and "CUDA_VISIBLE_DEVICES" not in os.environ:
+# LIS_B200_NARROW=1: show each rank only its own device (round 1's workaround for cudaMallocManaged failing with 8
+# ranks x 8 visible GPUs).  Default now: every GPU visible to every rank -- what peer access / CUDA IPC need, i.e. the
+# in-kernel halo exchange and NCCL's own NVLink P2P transport; vector storage falls back to device-only memory if
+# managed memory is refused.
+if (os.environ.get("LIS_B200_NARROW") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1 and "LOCAL_RANK" in os.environ
+        and "CUDA_VISIBLE_DEVICES" not in os.environ):
     os.environ["CUDA_VISIBLE_DEVICES"] = os.environ["LOCAL_RANK"]
     os.environ["LIS_B200_PHYSICAL_GPU"] = os.environ["LOCAL_RANK"]
 
@@ -229,6 +234,7 @@ def cg_to_convergence(Ls, grid, tol="1e-12"):
     (tests/golden/make_cg_fullsize.py; the reference itself cannot run on the GPU box's clock budget)."""
     t0 = time.time()
     n, nnz, p_ptr, p_idx, p_val = host_poisson7(Ls, grid, grid, grid, 0, grid, False)
+    Ls.shim_mv_open.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     h = Ls.shim_mv_open(1, n, p_ptr, p_idx, p_val, 0, 0, 1)
     assert h >= 0, h
     try:
@@ -412,6 +418,42 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
             overlap_ok = False
             overlap_note = f"off: exchange-then-product is faster here ({step_s * 1e3:.3f} vs {s2 * 1e3:.3f} ms); the overlapped order reproduced the bits"
             lib.lis_b200_set_overlap(0)
+    # the halo exchange inside the SpMV kernel over peer memory (CUDA IPC + NVLink; the library's default where every
+    # rank can map its neighbours): must reproduce the bits of the NCCL path on every rank, then both are timed
+    p2p_note = "not available (a GPU hidden from a rank, no peer access, or LIS_B200_P2P=0): NCCL send/recv"
+    try:
+        lib.lis_b200_set_p2p(0)
+        y_ref = torch.empty(n, dtype=torch.float64); y_p2p = torch.empty(n, dtype=torch.float64)
+        assert Ls.shim_mv_matvec(h) == 0 and Ls.shim_mv_get_y_local(h, y_ref.data_ptr()) == 0
+        lib.lis_b200_set_p2p(1)
+        for _ in range(3):                                   # both inbox buffers, and the epoch after
+            assert Ls.shim_mv_matvec(h) == 0
+        assert Ls.shim_mv_get_y_local(h, y_p2p.data_ptr()) == 0
+        lib.lis_b200_p2p_products.restype = C.c_ulonglong
+        used = torch.tensor([int(lib.lis_b200_p2p_products() > 0)], device=dev)
+        dist.all_reduce(used, op=dist.ReduceOp.MIN)
+        same = torch.tensor([int(torch.equal(y_ref.view(torch.int64), y_p2p.view(torch.int64)))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        del y_ref, y_p2p
+        if int(used.item()) and int(same.item()):
+            s3, per3, ck3 = time_products(True)
+            log(f"[rank {rank}] halo exchange inside the kernel (peer memory): {s3 * 1e3:.3f} ms/product; this rank min {per3[0]:.3f} median {per3[len(per3) // 2]:.3f} max {per3[-1]:.3f}")
+            step_modes["in_kernel_exchange_ms"] = s3 * 1e3
+            if s3 <= step_s:
+                step_s, per, clocks = s3, per3, ck3
+                p2p_note = "on: pushes into the neighbours' inboxes, flags, interior rows first, halo columns from the inbox -- one launch per product; same bits as the NCCL path (checked)"
+            else:
+                lib.lis_b200_set_p2p(0)
+                p2p_note = f"off: slower here ({s3 * 1e3:.3f} ms vs {step_s * 1e3:.3f} ms); bits equal"
+        else:
+            lib.lis_b200_set_p2p(0)
+            if int(used.item()):
+                p2p_note = "off: the in-kernel exchange did not reproduce the bits"
+    except Exception as e:
+        lib.lis_b200_set_p2p(0)
+        p2p_note = f"off: {e!r}"
+    p2p_on = p2p_note.startswith("on")
+    log(f"[rank {rank}] in-kernel halo exchange: {p2p_note}")
     # e2e: local slice of x in from pinned host memory, product, local slice of y out
     dist.barrier(); torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, 10))
@@ -526,14 +568,14 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
         "config": workload_config(grid, world),
         "e2e": {"value": 2.0 * nnz_g / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                 "what": e2e_what},
-        "gpu_launches": (4 if overlap_ok else 2) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false> (+ halo pack, NCCL p2p)", "achieved": bytes_local / step_s / 1e9,
+        "gpu_launches": (1 if p2p_on else 4 if overlap_ok else 2) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "lisb::csr_tma_kernel<256,4,false,true> (halo exchange inside)" if p2p_on else "lisb::csr_tma_kernel<256,4,false,false> (+ halo pack, NCCL send/recv)", "achieved": bytes_local / step_s / 1e9,
                      "peak": peak_gbs, "unit": "GB/s", "frac": bytes_local / step_s / 1e9 / peak_gbs, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_local, "note": "per GPU, whole product incl. halo exchange"},
         "clocks": clocks,
         "extra": {"cg_jacobi_iters_per_s": cg_it_s, "cg_iters_timed": done, "cg_matvec_dot": cg_note, "e2e_three_calls_gflops": 2.0 * nnz_g / e2e_seq_s / 1e9,
                   "exchange": "2 boundary planes (2 MiB each) per product via grouped ncclSend/ncclRecv; dot partials: " + reduce_note,
-                  "overlap": overlap_note, **step_modes, **cg_reduce,
+                  "overlap": overlap_note, "in_kernel_exchange": p2p_note, **step_modes, **cg_reduce,
                   "cg_roofline": {"bytes_per_iteration_per_gpu": 12.0 * nnz + 108.0 * n, "what": "fused traffic: 12 nnz + 20 n (q=Ap,<p,q>) + 64 n (update + next Jacobi step) + 24 n (xpay)",
                                   "achieved_gbs_per_gpu": (12.0 * nnz + 108.0 * n) * cg_it_s / 1e9, "frac": (12.0 * nnz + 108.0 * n) * cg_it_s / 1e9 / peak_gbs}},
     }

@@ -641,6 +641,11 @@ LIS_INT lis_b200_matvec_host_plan(LIS_MATRIX A, LIS_INT cap, LIS_INT *rows, LIS_
 LIS_INT lis_b200_set_overlap(LIS_INT on);
 /* partial scalars of dot/nrm2 across ranks: 0 = host control plane (default), 1 = ncclAllGather over NVLink */
 LIS_INT lis_b200_set_reduce(LIS_INT nccl);
+/* row-partitioned CSR products exchange their halo inside the SpMV kernel over peer memory (CUDA IPC + NVLink)
+ * where every rank can map its neighbours' GPUs: 1 (default) use it, 0 always the NCCL send/recv exchange.
+ * Returns the old setting; call on every rank alike. */
+LIS_INT lis_b200_set_p2p(LIS_INT on);
+unsigned long long lis_b200_p2p_products(void);   /* products so far that took that path (diagnostics) */
 /* the CUDA stream (cudaStream_t) all kernels of this process are enqueued on */
 void *lis_b200_stream(void);
 

@@ -56,6 +56,38 @@ int lisb200_spmv_csr_tma_dot(int n, int rows_per_block, int tile, int stages, co
 int lisb200_spmv_csr_tma_dot_rows(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
                                   const double *d_val, const double *d_x, double *d_y, const double *d_dotx,
                                   double *d_partial, unsigned int *d_counter, double *d_result, void *stream);
+/* Row-partitioned CSR product with the halo exchange INSIDE the kernel -- what replaces the reference's
+ * LIS_MATVEC_SENDRECV (include/lis_matvec.h:31-44: lis_send_recv, src/matrix/lis_matrix_mpi.c:834-954, then the
+ * local product) when every rank's GPU can map its neighbours' memory (one process per GPU, CUDA IPC, NVLink).
+ * The table lives in DEVICE memory and is filled once per communication table by the host (host/lis_comm.c):
+ * where each neighbour's segment of my export list lands in that neighbour's inbox, where my own inbox is, and
+ * the arrival flags.  Per product: all CTAs push x[export_index[..]] into the neighbours' inboxes (buffer
+ * epoch & 1), the last one to finish writes `epoch` into my flag in every neighbour; row blocks
+ * [interior_lo, interior_hi) (multiples of rows_per_block; they read no column >= n) run first; before its first
+ * other block a CTA waits until every neighbour's flag holds `epoch`; columns c >= n are read from
+ * inbox[c - n].  epoch must grow by one per product on this table, starting at 1, on every rank alike.
+ * Same products in the same order as lisb200_spmv_csr_tma: y has the same bits.  with_dot: also <x,y> as in
+ * lisb200_spmv_csr_tma_dot (blocks are visited interior first, so its last bits differ from that call's). */
+#define LISB200_P2P_MAX 16
+typedef struct lisb200_p2p {
+    int n_nbr;                                   /* neighbours (ranks I export to == ranks I import from) */
+    int n_export;
+    const int *export_index;                     /* device: local rows to send, neighbour segments back to back */
+    int exp_start[LISB200_P2P_MAX + 1];          /* segment of neighbour s in export_index */
+    int nbr_rank[LISB200_P2P_MAX];               /* rank of neighbour s */
+    double *peer_inbox[LISB200_P2P_MAX];         /* mapped: where segment s starts in neighbour s's inbox, buffer 0 */
+    long long peer_stride[LISB200_P2P_MAX];      /* doubles from buffer 0 to buffer 1 in that neighbour's inbox */
+    unsigned long long *peer_flag[LISB200_P2P_MAX];   /* mapped: my arrival flag in neighbour s ([parity * LISB200_P2P_MAX]) */
+    const double *inbox;                         /* my inbox, buffer 0: halo slot k at inbox[k] */
+    long long inbox_stride;
+    const unsigned long long *my_flag;           /* my flags: [parity * LISB200_P2P_MAX + sender rank] */
+    unsigned int *push_count;                    /* device scratch, zero between products */
+    int *error;                                  /* mapped host int: set to 1 if a neighbour's flag never arrived */
+} lisb200_p2p;
+int lisb200_spmv_csr_tma_p2p(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
+                             const double *d_val, const double *d_x, double *d_y, int with_dot, double *d_partial,
+                             unsigned int *d_counter, double *d_result, const lisb200_p2p *d_table,
+                             unsigned long long epoch, int interior_lo, int interior_hi, void *stream);
 /* CSR, split order  t = D[i]*x[i]; t += L...; t += U...  src/matvec/lis_matvec_csr.c:64-87 */
 int lisb200_spmv_csr_split(int n, const double *d_diag,
                            const int *d_lptr, const int *d_lidx, const double *d_lval,
@@ -232,7 +264,7 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
  *   mode 2: out[i] =  in[i] - sum v*(out[jj]*wd[jj])     first half of the transposed SSOR sweep   src/matrix/lis_matrix_csr.c:1838-1845
  *   mode 3: out[i] =  in[i] - (sum v*out[jj]) * wd[i]    SSOR backward                   src/matrix/lis_matrix_csr.c:1593-1605, 1618-1628
  * Sums run in storage order, unfused: same result bits as the level-launched kernels and the
- * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm (1..8, else 8) bounds the persistent
+ * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm (1..6, else 6) bounds the persistent
  * grid, i.e. the number of rows waiting at any time. */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
                        const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,

@@ -450,6 +450,13 @@ struct LIS_COMMTABLE_STRUCT {
     double *h_stage;                          /* host staging for the transport without NCCL */
     size_t h_stage_len;
     int neibpetot;                            /* number of ranks exchanged with (information) */
+    /* in-kernel halo exchange over peer memory (p2p_prepare): 0 not looked at yet, 1 ready, -1 not available */
+    int p2p;
+    unsigned long long p2p_epoch;             /* products done through the table */
+    double *p2p_inbox;                        /* [2][stride] doubles + [2][LISB200_P2P_MAX] flags, exported through CUDA IPC */
+    void *p2p_peer_base[LISC_MAXR];           /* neighbours' inboxes mapped into this process */
+    unsigned int *p2p_push_count;
+    lisb200_p2p *d_p2p;                       /* the kernel's table, device */
 };
 
 void lisd_commtable_destroy(LIS_COMMTABLE t)
@@ -460,6 +467,12 @@ void lisd_commtable_destroy(LIS_COMMTABLE t)
     lisd_free(t->d_ws);
     lisd_free(t->d_wr);
     free(t->peer_export_ptr); free(t->peer_n_export); free(t->h_stage);
+    if (t->p2p == 1) {
+        lisd_sync();
+        for (int k = 0; k < LISC_MAXR; k++) if (t->p2p_peer_base[k]) cudaIpcCloseMemHandle(t->p2p_peer_base[k]);
+        cudaFree(t->p2p_inbox); cudaFree(t->p2p_push_count); cudaFree(t->d_p2p);
+        cudaGetLastError();
+    }
     free(t);
 }
 
@@ -540,6 +553,8 @@ LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout)
     memcpy(t, s, sizeof(*t));
     t->d_export_index = NULL; t->d_ws = NULL; t->d_wr = NULL;
     t->h_stage = NULL; t->h_stage_len = 0;
+    t->p2p = 0; t->p2p_epoch = 0; t->p2p_inbox = NULL; t->p2p_push_count = NULL; t->d_p2p = NULL;
+    memset(t->p2p_peer_base, 0, sizeof(t->p2p_peer_base));
     t->peer_export_ptr = (int *)malloc(sizeof(int) * (size_t)s->nranks * (size_t)(s->nranks + 1));
     t->peer_n_export = (int *)malloc(sizeof(int) * (size_t)s->nranks);
     if (!t->peer_export_ptr || !t->peer_n_export) { free(t->peer_export_ptr); free(t->peer_n_export); free(t); LIS_SETERR_MEM(s->nranks); return LIS_OUT_OF_MEMORY; }
@@ -729,6 +744,145 @@ LIS_INT lis_reduce(LIS_COMMTABLE commtable, LIS_SCALAR x[])
     LIS_INT err = lisd_halo_reduce_raw(&fake, x);
     if (err) return err;
     return lisd_sync();
+}
+
+/* ------------------------------------------------------------------ halo exchange inside the SpMV kernel
+ * One process per GPU; where every rank's GPU can map its neighbours' memory (all GPUs visible to every process,
+ * peer access over NVLink, CUDA IPC) the row-partitioned CSR product needs no pack kernel, no NCCL group and no
+ * unpack copy: kernels/spmv.cu (csr_tma_kernel<.., kHalo>) stores the exported x entries straight into the
+ * neighbours' inboxes, raises a flag there, runs the rows that read no halo entry, waits for the neighbours'
+ * flags and reads the halo columns from its own inbox.  This file sets up what the kernel needs, once per
+ * communication table: inbox + flags (one cudaMalloc block, exported with cudaIpcGetMemHandle, the handles
+ * travel through the shm control plane), the neighbours' blocks mapped with cudaIpcOpenMemHandle, and the
+ * table of addresses in device memory.  Anything missing -- a GPU hidden by CUDA_VISIBLE_DEVICES, no peer
+ * access, an unsymmetric neighbour relation, LIS_B200_P2P=0 -- leaves the NCCL exchange in place. */
+static struct { int probed, ok, enabled; int *h_error, *d_error; } gp = { .enabled = 1 };
+
+/* 1: use the in-kernel exchange where it is available (default), 0: NCCL send/recv.  Returns the old setting.
+ * Call on every rank alike. */
+LIS_INT lis_b200_set_p2p(LIS_INT on) { const int old = gp.enabled; gp.enabled = on ? 1 : 0; return old; }
+
+static int all_agree(int mine)
+{
+    int all[LISC_MAXR];
+    if (lisd_allgather_int(&mine, 1, all)) return 0;
+    for (int k = 0; k < g.nranks; k++) if (!all[k]) return 0;
+    return 1;
+}
+
+static void p2p_probe(void)              /* collective */
+{
+    gp.probed = 1; gp.ok = 0;
+    const char *e = getenv("LIS_B200_P2P");
+    int want = g.nccl_ok && lisd_available() && !(e && e[0] == '0');
+    char bus[32], all[LISC_MAXR][32];
+    memset(bus, 0, sizeof(bus));
+    if (want && cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), lisd_device_id()) != cudaSuccess) { cudaGetLastError(); want = 0; }
+    if (shm_allgather(bus, sizeof(bus), all)) return;
+    int ok = want;
+    for (int k = 0; k < g.nranks && ok; k++) {
+        int dev = -1, can = 0;
+        if (k == g.rank) continue;
+        if (all[k][0] == 0 || cudaDeviceGetByPCIBusId(&dev, all[k]) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        if (dev == lisd_device_id()) { ok = 0; break; }                       /* two ranks on one GPU */
+        if (cudaDeviceCanAccessPeer(&can, lisd_device_id(), dev) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(dev, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+        cudaGetLastError();
+    }
+    if (ok && (cudaHostAlloc((void **)&gp.h_error, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+               cudaHostGetDevicePointer((void **)&gp.d_error, gp.h_error, 0) != cudaSuccess)) { cudaGetLastError(); ok = 0; }
+    if (ok) *gp.h_error = 0;
+    gp.ok = all_agree(ok);
+    if (g.rank == 0 && getenv("LIS_B200_VERBOSE"))
+        fprintf(stderr, "lis_b200: in-kernel halo exchange over peer memory %s\n", gp.ok ? "available" : "not available (NCCL send/recv)");
+}
+
+int lisd_p2p_error(void) { return gp.h_error && *(volatile int *)gp.h_error; }
+
+typedef struct { cudaIpcMemHandle_t handle; long long stride; int ok; } p2p_msg;
+
+static void p2p_prepare(LIS_COMMTABLE t)  /* collective: every rank comes here at its first product on the table */
+{
+    const int me = t->rank, np_ = t->nranks;
+    t->p2p = -1;
+    if (!gp.probed) p2p_probe();
+    int ok = gp.ok, nn = 0;
+    for (int k = 0; k < np_; k++) {
+        const int ne = t->export_ptr[k + 1] - t->export_ptr[k], ni = t->import_ptr[k + 1] - t->import_ptr[k];
+        if (k == me) continue;
+        if ((ne > 0) != (ni > 0)) ok = 0;                     /* the double-buffer argument needs mutual neighbours */
+        if (ne > 0) nn++;
+    }
+    if (nn == 0 || nn > LISB200_P2P_MAX) ok = 0;
+    p2p_msg mine, all[LISC_MAXR];
+    memset(&mine, 0, sizeof(mine));
+    const long long stride = ((long long)t->n_import + 15) & ~15LL;
+    const size_t bytes = sizeof(double) * (size_t)(2 * stride) + sizeof(unsigned long long) * 2 * LISB200_P2P_MAX + 64;
+    if (ok) {
+        if (cudaMalloc((void **)&t->p2p_inbox, bytes) != cudaSuccess || cudaMemset(t->p2p_inbox, 0, bytes) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine.handle, t->p2p_inbox) != cudaSuccess) {
+            cudaGetLastError(); ok = 0;
+        }
+    }
+    mine.stride = stride; mine.ok = ok;
+    if (shm_allgather(&mine, sizeof(mine), all)) ok = 0;
+    for (int k = 0; k < np_; k++) if (!all[k].ok) ok = 0;
+    if (ok)
+        for (int k = 0; k < np_; k++) {
+            if (k == me || t->export_ptr[k + 1] == t->export_ptr[k]) continue;
+            if (cudaIpcOpenMemHandle(&t->p2p_peer_base[k], all[k].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError(); t->p2p_peer_base[k] = NULL; ok = 0; break;
+            }
+        }
+    lisb200_p2p tb;
+    memset(&tb, 0, sizeof(tb));
+    if (ok) {
+        int s = 0;
+        for (int k = 0; k < np_; k++) {
+            if (k == me || t->export_ptr[k + 1] == t->export_ptr[k]) continue;
+            tb.exp_start[s] = t->export_ptr[k];
+            tb.nbr_rank[s] = k;
+            tb.peer_inbox[s] = (double *)t->p2p_peer_base[k] + peer_import_offset(t, k, me);
+            tb.peer_stride[s] = all[k].stride;
+            tb.peer_flag[s] = (unsigned long long *)((double *)t->p2p_peer_base[k] + 2 * all[k].stride) + me;
+            s++;
+        }
+        tb.exp_start[s] = t->n_export;
+        tb.n_nbr = s; tb.n_export = t->n_export; tb.export_index = t->d_export_index;
+        tb.inbox = t->p2p_inbox; tb.inbox_stride = stride;
+        tb.my_flag = (const unsigned long long *)(t->p2p_inbox + 2 * stride);
+        tb.error = gp.d_error;
+        if (cudaMalloc((void **)&t->p2p_push_count, 64) != cudaSuccess || cudaMemset(t->p2p_push_count, 0, 64) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_p2p, sizeof(tb)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        else {
+            tb.push_count = t->p2p_push_count;
+            if (cudaMemcpy(t->d_p2p, &tb, sizeof(tb), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
+    }
+    if (all_agree(ok)) { t->p2p = 1; t->p2p_epoch = 0; return; }
+    for (int k = 0; k < np_; k++) if (t->p2p_peer_base[k]) { cudaIpcCloseMemHandle(t->p2p_peer_base[k]); t->p2p_peer_base[k] = NULL; }
+    if (t->p2p_inbox) cudaFree(t->p2p_inbox);
+    if (t->p2p_push_count) cudaFree(t->p2p_push_count);
+    if (t->d_p2p) cudaFree(t->d_p2p);
+    t->p2p_inbox = NULL; t->p2p_push_count = NULL; t->d_p2p = NULL;
+    cudaGetLastError();
+}
+
+static unsigned long long g_p2p_products = 0;
+/* products of this process that exchanged their halo inside the kernel (diagnostics, bench.py) */
+unsigned long long lis_b200_p2p_products(void) { return g_p2p_products; }
+
+/* the table for the fused product on A (device pointer) and the epoch of this product, or NULL: use lisd_halo_exchange */
+const lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, unsigned long long *epoch)
+{
+    LIS_COMMTABLE t = A->commtable;
+    if (t == NULL || g.nranks == 1 || !gp.enabled) return NULL;
+    if (t->p2p == 0) p2p_prepare(t);
+    if (t->p2p != 1) return NULL;
+    *epoch = ++t->p2p_epoch;
+    g_p2p_products++;
+    return t->d_p2p;
 }
 
 LIS_INT lisd_halo_exchange(LIS_MATRIX A, LIS_VECTOR x) { return halo_exchange_raw(A->commtable, A->n, x->value); }

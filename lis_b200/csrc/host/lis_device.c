@@ -83,7 +83,12 @@ LIS_INT lisd_sync(void)
 {
     if (!g_ctx.available || !g_ctx.busy) return LIS_SUCCESS;
     g_ctx.busy = 0;
-    return lisd_check((int)cudaStreamSynchronize(g_ctx.stream), "stream synchronize");
+    LIS_INT err = lisd_check((int)cudaStreamSynchronize(g_ctx.stream), "stream synchronize");
+    if (!err && lisd_p2p_error()) {
+        LIS_SETERR(LIS_ERR_DEVICE, "row-partitioned product: a neighbour's halo never arrived (ranks out of step?)\n");
+        return LIS_ERR_DEVICE;
+    }
+    return err;
 }
 
 void lisd_shutdown(void)

@@ -336,6 +336,19 @@ LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
     if (A->nprocs > 1 && A->commtable) {
+        if (M->type == LIS_MATRIX_CSR && !M->splited && M->csr.tma_rows) {
+            /* halo exchange inside the kernel over peer memory, where every rank can map its neighbours */
+            unsigned long long epoch = 0;
+            const struct lisb200_p2p *tb = lisd_p2p_begin(A, &epoch);
+            if (tb) {
+                if (M->ov_built == 0) overlap_plan(A, M);
+                const int lo = M->ov_built == 1 ? M->ov_lo : 0, hi = M->ov_built == 1 ? M->ov_hi : 0;
+                lisd_mark_busy();
+                return lisd_check(lisb200_spmv_csr_tma_p2p(A->n, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr, M->csr.idx,
+                                                           M->csr.val, x->value, y->value, 0, NULL, NULL, NULL, tb, epoch, lo, hi,
+                                                           lisd_stream()), "lis_matvec (halo exchange in the kernel)");
+            }
+        }
         if (M->type == LIS_MATRIX_CSR && !M->splited && M->ov_built == 0 && overlap_enabled()) overlap_plan(A, M);
         if (M->type == LIS_MATRIX_CSR && !M->splited && M->ov_built == 1 && overlap_enabled()) {
             /* exchange on the main stream (enqueued first, so its few CTAs are resident first), interior
@@ -413,6 +426,22 @@ LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *do
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
     if (A->nprocs > 1 && A->commtable) {
+        if (M->type == LIS_MATRIX_CSR && M->csr.tma_rows) {
+            unsigned long long epoch = 0;
+            const struct lisb200_p2p *tb = lisd_p2p_begin(A, &epoch);
+            if (tb) {
+                if (M->ov_built == 0) overlap_plan(A, M);
+                const int lo = M->ov_built == 1 ? M->ov_lo : 0, hi = M->ov_built == 1 ? M->ov_hi : 0;
+                double *partial = lisd_partial(0);
+                if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+                lisd_mark_busy();
+                err = lisd_check(lisb200_spmv_csr_tma_p2p(A->n, M->csr.tma_rows, M->csr.tma_tile, M->csr.tma_stages, M->csr.ptr, M->csr.idx,
+                                                          M->csr.val, x->value, y->value, 1, partial, lisd_counter(), lisd_scalar_dev(0), tb,
+                                                          epoch, lo, hi, lisd_stream()), "lis_matvec+dot (halo exchange in the kernel)");
+                if (err) return err;
+                return lisd_reduce_finish(dot_xy, 1, 0);
+            }
+        }
         if (M->type == LIS_MATRIX_CSR && M->csr.tma_rows && M->ov_built == 0 && overlap_dot_enabled()) overlap_plan(A, M);
         if (M->type == LIS_MATRIX_CSR && M->csr.tma_rows && M->ov_built == 1 && overlap_dot_enabled())
             return matvec_dot_overlapped(A, M, x, y, dot_xy);

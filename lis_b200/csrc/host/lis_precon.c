@@ -581,11 +581,11 @@ int lisd_perm_sweep(const lisd_perm *P, int mode, int n, const double *d_wd, con
                               d_wd, d_in, d_out, d_ticket, lisd_sweep_ctas(), lisd_stream());
 }
 
-/* how many CTAs per SM the persistent sweep grid gets (LIS_B200_SWEEP_CTAS=1..8; default 8) */
+/* how many CTAs per SM the persistent sweep grid gets (LIS_B200_SWEEP_CTAS=1..6; default 6) */
 int lisd_sweep_ctas(void)
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("LIS_B200_SWEEP_CTAS"); v = e ? atoi(e) : 0; if (v < 1 || v > 8) v = 8; }
+    if (v < 0) { const char *e = getenv("LIS_B200_SWEEP_CTAS"); v = e ? atoi(e) : 0; if (v < 1 || v > 6) v = 6; }
     return v;
 }
 

@@ -137,12 +137,47 @@ struct CsrTmaSmem {
     static __host__ __device__ size_t stage_bytes(int tile) { return (size_t)tile * 12 + kPtrInts * 4; }
 };
 
-template <int kRows, int kStages, bool kDot>
+// kHalo: the row-partitioned product with the halo exchange INSIDE the kernel (one process per GPU,
+// peers' memory mapped through CUDA IPC, NVLink loads/stores; host/lis_comm.c sets the table up):
+//   1. all CTAs copy this rank's exported x entries straight into the neighbours' inboxes (P2P
+//      stores), fence, and the last CTA to finish raises this rank's flag in every neighbour;
+//   2. the row blocks that read no halo entry -- [int_lo, int_hi), found by the host -- run first;
+//   3. before its first other block a CTA waits for the neighbours' flags of this epoch, and those
+//      blocks read columns >= n from the inbox instead of x[n..).
+// No pack kernel, no NCCL group, no unpack copy, no second stream: the transfer overlaps the
+// interior rows by construction.  Inboxes are double-buffered by epoch parity: a neighbour can only
+// be one product ahead (it needs this rank's push of the current epoch to finish its own).
+#ifndef LISB_EMU
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+__device__ __forceinline__ int halo_block_of(int v, int int_lo, int int_hi)
+{
+    const int ni = int_hi - int_lo;                  // interior blocks first, then the others in row order
+    if (v < ni) return int_lo + v;
+    v -= ni;
+    return v < int_lo ? v : v + ni;
+}
+
+template <int kRows, int kStages, bool kDot, bool kHalo>
 __global__ void __launch_bounds__(kRows + 32, 1152 / (kRows + 32))
 csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const int *__restrict__ idx,
                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                const double *__restrict__ dotx /* kDot: row r pairs with dotx[r] (x itself, or x + first row of a row range) */,
-               double *partial, unsigned int *counter, double *result)
+               double *partial, unsigned int *counter, double *result,
+               const lisb200_p2p *__restrict__ pd, unsigned long long epoch, int int_lo, int int_hi)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
@@ -154,25 +189,52 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kRows / 32); }
         mbar_fence_init();
     }
+    const int par = kHalo ? (int)(epoch & 1ull) : 0;
+    if (kHalo) {
+        // ---- push: exported entries into the neighbours' inboxes of this epoch's parity
+        const int tot = pd->n_export;
+        for (int q = blockIdx.x * (kRows + 32) + tid; q < tot; q += gridDim.x * (kRows + 32)) {
+            int s = 0;
+            while (q >= pd->exp_start[s + 1]) ++s;
+            pd->peer_inbox[s][(long long)par * pd->peer_stride[s] + (q - pd->exp_start[s])] = x[__ldg(pd->export_index + q)];
+        }
+        __threadfence_system();
+    }
     __syncthreads();
+    if (kHalo && tid == 0) {
+        const unsigned int arrived = atomicAdd(pd->push_count, 1u);
+        if (arrived == gridDim.x - 1) {
+            *pd->push_count = 0u;                    // every CTA has arrived: ready for the next product
+            __threadfence_system();
+            for (int s = 0; s < pd->n_nbr; ++s) st_release_sys(pd->peer_flag[s] + par * LISB200_P2P_MAX, epoch);
+        }
+    }
+    const double *inbox = kHalo ? pd->inbox + (long long)par * pd->inbox_stride - n : nullptr;   // column c >= n -> inbox[c]
+    const int n_first = kHalo ? int_hi - int_lo : 0;
 
     double dsum = 0.0;
     if (tid >= kRows) {
         // ---------------- producer warp: one lane drives the TMA ----------------
         if (tid == kRows) {
             int it = 0;
-            int b = blockIdx.x;
+            int vb = blockIdx.x;                     // position in the visiting order; b: the row block
             // slice bounds of the block after this one are fetched one iteration ahead, so the
             // producer never sits on a DRAM round trip between "stage free" and "TMA issued"
             int a0 = 0, a1 = 0;
-            if (b < nblocks) { a0 = __ldg(ptr + b * kRows); a1 = __ldg(ptr + min(b * kRows + kRows, n)); }
-            for (; b < nblocks; b += gridDim.x, ++it) {
+            if (vb < nblocks) {
+                const int b = kHalo ? halo_block_of(vb, int_lo, int_hi) : vb;
+                a0 = __ldg(ptr + b * kRows); a1 = __ldg(ptr + min(b * kRows + kRows, n));
+            }
+            for (; vb < nblocks; vb += gridDim.x, ++it) {
+                const int b = kHalo ? halo_block_of(vb, int_lo, int_hi) : vb;
                 const int s = it % kStages;
                 const int r0 = b * kRows;
                 const int rend = min(r0 + kRows, n);
-                const int bn = b + gridDim.x;
                 int na0 = 0, na1 = 0;
-                if (bn < nblocks) { na0 = __ldg(ptr + bn * kRows); na1 = __ldg(ptr + min(bn * kRows + kRows, n)); }
+                if (vb + (int)gridDim.x < nblocks) {
+                    const int bn = kHalo ? halo_block_of(vb + gridDim.x, int_lo, int_hi) : vb + gridDim.x;
+                    na0 = __ldg(ptr + bn * kRows); na1 = __ldg(ptr + min(bn * kRows + kRows, n));
+                }
                 if (it >= kStages) mbar_wait(&empty_bar[s], ((it / kStages) - 1) & 1);
                 unsigned char *st = smem_raw + (size_t)s * stage_bytes;
                 double *sval = reinterpret_cast<double *>(st);
@@ -193,7 +255,20 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
     } else {
         // ---------------- consumers: thread r walks row r ----------------
         int it = 0;
-        for (int b = blockIdx.x; b < nblocks; b += gridDim.x, ++it) {
+        bool have_halo = false;
+        for (int vb = blockIdx.x; vb < nblocks; vb += gridDim.x, ++it) {
+            const int b = kHalo ? halo_block_of(vb, int_lo, int_hi) : vb;
+            if (kHalo && !have_halo && vb >= n_first) {
+                // first block that may read halo entries: the neighbours' pushes of this epoch must have landed
+                have_halo = true;
+                const unsigned long long t0 = global_timer_ns();
+                for (int q = 0; q < pd->n_nbr; ++q) {
+                    const unsigned long long *f = pd->my_flag + par * LISB200_P2P_MAX + pd->nbr_rank[q];
+                    while (ld_acquire_sys(f) != epoch) {
+                        if (global_timer_ns() - t0 > 20000000000ull) { *pd->error = 1; break; }   // 20 s: a neighbour never pushed
+                    }
+                }
+            }
             const int s = it % kStages;
             unsigned char *st = smem_raw + (size_t)s * stage_bytes;
             const double *sval = reinterpret_cast<const double *>(st);
@@ -219,7 +294,7 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
                         v[k] = sval[jj];
                     }
 #pragma unroll
-                    for (int k = 0; k < kGather; ++k) xv[k] = __ldg(x + c[k]);
+                    for (int k = 0; k < kGather; ++k) xv[k] = (!kHalo || c[k] < n) ? __ldg(x + c[k]) : __ldcg(inbox + c[k]);
 #pragma unroll
                     for (int k = 0; k < kGather; ++k)
                         if (j + k < e) acc = add(acc, mul(v[k], xv[k]));
@@ -570,12 +645,14 @@ static int sm_count_spmv() {
     return g_sm_count;
 }
 
-template <int kRows, int kStages, bool kDot>
+struct HaloArgs { const lisb200_p2p *pd; unsigned long long epoch; int int_lo, int_hi; };
+
+template <int kRows, int kStages, bool kDot, bool kHalo>
 static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, const double *val, const double *x, double *y,
-                            const double *dotx, double *partial, unsigned int *counter, double *result, cudaStream_t st)
+                            const double *dotx, double *partial, unsigned int *counter, double *result, HaloArgs h, cudaStream_t st)
 {
     const size_t smem = kStages * CsrTmaSmem<kRows>::stage_bytes(tile);
-    auto kern = csr_tma_kernel<kRows, kStages, kDot>;
+    auto kern = csr_tma_kernel<kRows, kStages, kDot, kHalo>;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -589,27 +666,57 @@ static int launch_csr_tma_s(int n, int tile, const int *ptr, const int *idx, con
     const int nblocks = (n + kRows - 1) / kRows;
     int grid = sm_count_spmv() * per_sm;
     if (grid > nblocks) grid = nblocks;
-    kern<<<grid, kRows + 32, smem, st>>>(n, nblocks, tile, ptr, idx, val, x, y, dotx, partial, counter, result);
+    kern<<<grid, kRows + 32, smem, st>>>(n, nblocks, tile, ptr, idx, val, x, y, dotx, partial, counter, result,
+                                         h.pd, h.epoch, h.int_lo / kRows, h.int_hi / kRows);
     LISB_CHECK_LAUNCH();
     return 0;
 }
 
-template <int kRows, bool kDot>
+template <int kRows, bool kDot, bool kHalo = false>
 static int launch_csr_tma(int n, int tile, int stages, const int *ptr, const int *idx, const double *val, const double *x, double *y,
-                          const double *dotx, double *partial, unsigned int *counter, double *result, cudaStream_t st)
+                          const double *dotx, double *partial, unsigned int *counter, double *result, cudaStream_t st,
+                          HaloArgs h = HaloArgs{nullptr, 0ull, 0, 0})
 {
     switch (stages) {
-    case 3: return launch_csr_tma_s<kRows, 3, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
-    case 4: return launch_csr_tma_s<kRows, 4, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
-    case 6: return launch_csr_tma_s<kRows, 6, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
-    case 8: return launch_csr_tma_s<kRows, 8, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
-    case 2: return launch_csr_tma_s<kRows, 2, kDot>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, st);
+    case 3: return launch_csr_tma_s<kRows, 3, kDot, kHalo>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, h, st);
+    case 4: return launch_csr_tma_s<kRows, 4, kDot, kHalo>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, h, st);
+    case 2: return launch_csr_tma_s<kRows, 2, kDot, kHalo>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, h, st);
+    default: break;
+    }
+    if (kHalo) return (int)cudaErrorInvalidValue;        // the plan only yields depths 2..4
+    switch (stages) {
+    case 6: return launch_csr_tma_s<kRows, 6, kDot, false>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, h, st);
+    case 8: return launch_csr_tma_s<kRows, 8, kDot, false>(n, tile, ptr, idx, val, x, y, dotx, partial, counter, result, h, st);
     default: return (int)cudaErrorInvalidValue;
     }
 }
 }  // namespace lisb
 
-
+/* row-partitioned product with the halo exchange inside the kernel; see include/lis_b200_kernels.h */
+extern "C" int lisb200_spmv_csr_tma_p2p(int n, int rows_per_block, int tile, int stages, const int *d_ptr, const int *d_idx,
+                                        const double *d_val, const double *d_x, double *d_y, int with_dot, double *d_partial,
+                                        unsigned int *d_counter, double *d_result, const lisb200_p2p *d_table,
+                                        unsigned long long epoch, int interior_lo, int interior_hi, void *stream)
+{
+    if (n <= 0 || d_table == nullptr || epoch == 0) return (int)cudaErrorInvalidValue;
+    if (interior_lo % rows_per_block || interior_hi % rows_per_block || interior_lo > interior_hi || interior_hi > n) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    const HaloArgs h{d_table, epoch, interior_lo, interior_hi};
+    if (with_dot) {
+        switch (rows_per_block) {
+        case 256: return launch_csr_tma<256, true, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_x, d_partial, d_counter, d_result, st, h);
+        case 128: return launch_csr_tma<128, true, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_x, d_partial, d_counter, d_result, st, h);
+        case 64:  return launch_csr_tma<64, true, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, d_x, d_partial, d_counter, d_result, st, h);
+        default:  return (int)cudaErrorInvalidValue;
+        }
+    }
+    switch (rows_per_block) {
+    case 256: return launch_csr_tma<256, false, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, nullptr, st, h);
+    case 128: return launch_csr_tma<128, false, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, nullptr, st, h);
+    case 64:  return launch_csr_tma<64, false, true>(n, tile, stages, d_ptr, d_idx, d_val, d_x, d_y, nullptr, nullptr, nullptr, nullptr, st, h);
+    default:  return (int)cudaErrorInvalidValue;
+    }
+}
 
 // rows_per_block in {256,128,64}; tile = entries staged per row block (multiple of 4);
 // stages in {2,3,4,6,8} with stages * (12*tile + 4*(rows+4)) <= ~224 KB

@@ -77,8 +77,8 @@ ssor_bwd_kernel(int nrows, const int *__restrict__ rows,
 //     by the host), all lanes the same sector -- and only then collects what was missing;
 //   * everything that does not depend on a neighbour (slot -> row, row length, first batch of
 //     the factor, in[i], wd[i]) is loaded before the first poll;
-//   * the grid is persistent (every warp takes tickets of 32 slots in slot order), which bounds the
-//     number of waiting warps; a waiting row's dependencies are always in warps that hold an
+//   * the grid is persistent (CTAs take tickets of 128 slots in slot order), which bounds the
+//     number of waiting warps; a waiting row's dependencies are always in CTAs that hold an
 //     earlier ticket, i.e. are running or finished: no deadlock.
 // Each row still subtracts its products in storage order => same bits as the level-launched
 // sweep and as the reference loop (src/matrix/lis_matrix_csr.c:1578-1628).
@@ -112,97 +112,94 @@ enum { kSweepFwd = 0, kSweepPlain = 1, kSweepReadScaled = 2, kSweepBwd = 3 };
 constexpr int kSweepThreads = 128;
 
 template <int kMode>
-__global__ void __launch_bounds__(kSweepThreads, 8)
+__global__ void __launch_bounds__(kSweepThreads, 6)
 sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restrict__ wptr,
                   const int *__restrict__ plen, const int *__restrict__ wdep,
                   const int *__restrict__ sidx, const double *__restrict__ sval,
                   const double *__restrict__ wd, const double *__restrict__ in, double *out, unsigned int *ticket)
 {
+    __shared__ unsigned int vblock[2];
     constexpr bool kSub = kMode != kSweepBwd;       // running value starts at in[i] and products are subtracted
-    constexpr int kBatch = 4;
-    const int lane = threadIdx.x & 31;
-    const unsigned int nwarps = (unsigned int)nslots >> 5;      // nslots is a multiple of 32
-    // Every WARP takes its own tickets (one per 32 slots, in slot order): no block barrier, the warps of
-    // a CTA never wait for each other.  Tickets are drawn two rounds ahead and the first wave of loads
-    // of the next round (slot -> row, row length, the warp's latest neighbour, slice start) is in
-    // flight while this round waits for its neighbours.
-    unsigned int t0 = 0, t1 = 0;
-    if (lane == 0) { t0 = atomicAdd(ticket, 1u); t1 = atomicAdd(ticket, 1u); }
-    t0 = __shfl_sync(0xffffffffu, t0, 0);
-    t1 = __shfl_sync(0xffffffffu, t1, 0);
-    int i = -1, len = 0, dep = -1, base = 0;
-    if (t0 < nwarps) { i = order[t0 * 32 + lane]; len = plen[t0 * 32 + lane]; dep = wdep[t0]; base = wptr[t0]; }
-    while (t0 < nwarps) {
-        unsigned int t2 = 0;
-        if (lane == 0) t2 = atomicAdd(ticket, 1u);
-        // second wave of this round: the row's operands and its first batch of the factor
-        const int *ci = sidx + (size_t)base + lane;
-        const double *cv = sval + (size_t)base + lane;
-        double inv = 0.0, wdv = 0.0;
-        int jj[kBatch];
-        double v[kBatch];
-        if (i >= 0) {
-            inv = in[i];
-            if (kMode == kSweepFwd || kMode == kSweepBwd) wdv = wd[i];
+    constexpr int kBatch = 8;
+    if (threadIdx.x == 0) vblock[0] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    for (int round = 0;; round ^= 1) {
+        const long long k0 = (long long)vblock[round] * kSweepThreads;
+        if (k0 >= nslots) break;
+        // the next ticket is on its way while this block's rows are worked on
+        unsigned int next_ticket = 0;
+        if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
+        const int k = (int)k0 + threadIdx.x;
+        if (k < nslots) {                            // nslots is a multiple of 32: whole warps
+            // first wave: nothing here depends on another load
+            const int w = k >> 5, lane = k & 31;
+            const int i = order[k];                  // -1: padding lane
+            const int len = plen[k];
+            const int dep = wdep[w];
+            const size_t base = (size_t)wptr[w] + lane;
+            if (i >= 0) {
+                // second wave: the row's operands and its first batch of the factor
+                const int *ci = sidx + base;
+                const double *cv = sval + base;
+                const double inv = in[i];
+                const double wdv = (kMode == kSweepFwd || kMode == kSweepBwd) ? wd[i] : 0.0;
+                int jj[kBatch];
+                double v[kBatch];
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
-                const int qq = q < len ? q : 0;
-                jj[q] = len > 0 ? ci[32 * qq] : 0;
-                v[q] = len > 0 ? cv[32 * qq] : 0.0;
-            }
-        }
-        // first wave of the NEXT round
-        int ni = -1, nlen = 0, ndep = -1, nbase = 0;
-        if (t1 < nwarps) { ni = order[t1 * 32 + lane]; nlen = plen[t1 * 32 + lane]; ndep = wdep[t1]; nbase = wptr[t1]; }
-        if (i >= 0) {                                // -1: padding lane
-            // long rows: touch the neighbours behind the first batch too (sectors into L2, values unused)
-            for (int q = kBatch; q < len; ++q) (void)ld_poll(out + ci[32 * (size_t)q]);
-            double t = kSub ? inv : 0.0;
-            bool waited = false;
-            for (int q0 = 0; q0 < len; q0 += kBatch) {
-                double xv[kBatch];
-                unsigned int used = 0;
+                for (int q = 0; q < kBatch; ++q) {
+                    const int qq = q < len ? q : 0;
+                    jj[q] = len > 0 ? ci[32 * qq] : 0;
+                    v[q] = len > 0 ? cv[32 * qq] : 0.0;
+                }
+                // long rows: touch the neighbours behind the first batch too (sectors into L2, values unused)
+                for (int q = kBatch; q < len; ++q) (void)ld_poll(out + ci[32 * (size_t)q]);
+                double t = kSub ? inv : 0.0;
+                bool waited = false;
+                for (int q0 = 0; q0 < len; q0 += kBatch) {
+                    double xv[kBatch];
+                    unsigned int used = 0;
 #pragma unroll
-                for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
-                unsigned int pending = used;
-                while (pending) {
-                    // all polls of the batch are issued before the first answer is looked at: one
-                    // round trip per batch, not one per neighbour.  The first round also brings the
-                    // neighbours' sectors into L2 long before their values are published (this row
-                    // is several levels ahead of the sweep front).
-                    unsigned long long bits[kBatch];
+                    for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
+                    unsigned int pending = used;
+                    while (pending) {
+                        // all polls of the batch are issued before the first answer is looked at: one
+                        // round trip per batch, not one per neighbour.  The first round also brings the
+                        // neighbours' sectors into L2 long before their values are published (this row
+                        // is several levels ahead of the sweep front), so the round after the wait
+                        // below is an L2 hit and not a DRAM fill.
+                        unsigned long long bits[kBatch];
 #pragma unroll
-                    for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(out + jj[q]) : kNotReady;
+                        for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(out + jj[q]) : kNotReady;
+#pragma unroll
+                        for (int q = 0; q < kBatch; ++q)
+                            if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
+                        if (pending && !waited) {
+                            // wait on ONE address for the whole warp -- the neighbour of its 32 rows that
+                            // sits latest in slot order -- instead of every lane polling all of its own
+                            waited = true;
+                            if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < kBatch; ++q)
-                        if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
-                    if (pending && !waited) {
-                        // wait on ONE address for the whole warp -- the neighbour of its 32 rows that
-                        // sits latest in slot order -- instead of every lane polling all of its own
-                        waited = true;
-                        if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+                        if (used & (1u << q)) {
+                            if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
+                            t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
+                        }
+                    if (q0 + kBatch < len) {
+#pragma unroll
+                        for (int q = 0; q < kBatch; ++q) {
+                            const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
+                            jj[q] = ci[32 * (size_t)qq];
+                            v[q] = cv[32 * (size_t)qq];
+                        }
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < kBatch; ++q)
-                    if (used & (1u << q)) {
-                        if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
-                        t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
-                    }
-                if (q0 + kBatch < len) {
-#pragma unroll
-                    for (int q = 0; q < kBatch; ++q) {
-                        const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
-                        jj[q] = ci[32 * (size_t)qq];
-                        v[q] = cv[32 * (size_t)qq];
-                    }
-                }
+                st_publish(out + i, kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t);
             }
-            st_publish(out + i, kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t);
         }
-        __syncwarp();
-        t0 = t1; i = ni; len = nlen; dep = ndep; base = nbase;
-        t1 = __shfl_sync(0xffffffffu, t2, 0);
+        if (threadIdx.x == 0) vblock[round ^ 1] = next_ticket;
+        __syncthreads();
     }
 }
 
@@ -230,7 +227,7 @@ extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_orde
     int fill_grid = (n + 255) / 256;
     if (fill_grid > sms * 8) fill_grid = sms * 8;
     fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
-    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm < 1 || ctas_per_sm > 6) ctas_per_sm = 6;
     int grid = (nslots + kSweepThreads - 1) / kSweepThreads;
     if (grid > sms * ctas_per_sm) grid = sms * ctas_per_sm;
     switch (mode) {

@@ -79,6 +79,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcg(const T *p) { return *p; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 static inline void __syncthreads() { emu::sync_block(); }
@@ -180,5 +181,9 @@ __forceinline__ unsigned long long ld_poll(const double *p) {
     unsigned long long v; memcpy(&v, p, 8); return v;
 }
 __forceinline__ void st_publish(double *p, double v) { *p = v; }
+/* flags of the in-kernel halo exchange (spmv.cu, kHalo) */
+__forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { emu::spin_yield(); return *(const volatile unsigned long long *)p; }
+__forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
+__forceinline__ unsigned long long global_timer_ns() { return 0ull; }
 
 }  // namespace lisb

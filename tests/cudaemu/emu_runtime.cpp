@@ -394,5 +394,14 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { emu_nee
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemPrefetchAsync(const void *, size_t, int, cudaStream_t st) { emu_need_stream(st, "cudaMemPrefetchAsync"); return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
+/* peer memory / IPC: not available here, so the in-kernel halo exchange stays off and the staged transport runs */
+cudaError_t cudaDeviceGetPCIBusId(char *b, int len, int dev) { (void)dev; if (len > 0) b[0] = 0; return cudaErrorNotSupported; }
+cudaError_t cudaDeviceGetByPCIBusId(int *dev, const char *b) { (void)b; *dev = -1; return cudaErrorNotSupported; }
+cudaError_t cudaDeviceCanAccessPeer(int *can, int a, int b) { (void)a; (void)b; *can = 0; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int dev, unsigned int f) { (void)dev; (void)f; return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { (void)h; (void)p; return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned int f) { (void)h; (void)f; *p = 0; return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *p) { (void)p; return cudaErrorNotSupported; }
+
 
 }  // extern "C"

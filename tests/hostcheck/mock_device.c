@@ -65,6 +65,16 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { mock_ne
 cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemPrefetchAsync(const void *p, size_t n, int dev, cudaStream_t st) { (void)p; (void)n; (void)dev; (void)st; return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+/* peer memory / IPC: not available here, so the in-kernel halo exchange stays off and the staged transport runs */
+cudaError_t cudaDeviceGetPCIBusId(char *b, int len, int dev) { (void)dev; if (len > 0) b[0] = 0; return cudaErrorNotSupported; }
+cudaError_t cudaDeviceGetByPCIBusId(int *dev, const char *b) { (void)b; *dev = -1; return cudaErrorNotSupported; }
+cudaError_t cudaDeviceCanAccessPeer(int *can, int a, int b) { (void)a; (void)b; *can = 0; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int dev, unsigned int f) { (void)dev; (void)f; return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { (void)h; (void)p; return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned int f) { (void)h; (void)f; *p = 0; return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *p) { (void)p; return cudaErrorNotSupported; }
+
 
 /* ------------------------------------------------------------------ kernel C-ABI on the oracle */
 int lisb200_sm_count(void) { return 1; }
@@ -239,6 +249,11 @@ int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int 
     }
     return 0;
 }
+
+int lisb200_spmv_csr_tma_p2p(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y, int dot,
+                             double *part, unsigned int *cnt, double *res, const lisb200_p2p *tb, unsigned long long ep, int lo, int hi, void *s)
+{ (void)n; (void)r; (void)t; (void)st; (void)p; (void)i; (void)v; (void)x; (void)y; (void)dot; (void)part; (void)cnt; (void)res; (void)tb; (void)ep; (void)lo; (void)hi; (void)s;
+  return 1; }                     /* never reached: the mock runtime offers no peer memory */
 
 /* ---- device-side format conversion (kernels/convert.cu): plain sequential restatements ---- */
 int lisb200_csr_max_row_len(int n, const int *p, int *out, void *s)

@@ -202,3 +202,89 @@ def test_etest5_driver_emulated(emu_drivers, tmp_path):
 
 def test_test3b_driver_hpcg_kernel_emulated(emu_drivers, tmp_path):
     D.test_test3b_driver_hpcg_kernel(tmp_path)
+
+
+# ---- halo exchange inside the SpMV kernel (csr_tma_kernel<.., kHalo>): the kernel logic on the emulator
+class _P2PTable(__import__("ctypes").Structure):
+    import ctypes as _C
+    _MAX = 16
+    _fields_ = [("n_nbr", _C.c_int), ("n_export", _C.c_int), ("export_index", _C.c_void_p), ("exp_start", _C.c_int * (_MAX + 1)),
+                ("nbr_rank", _C.c_int * _MAX), ("peer_inbox", _C.c_void_p * _MAX), ("peer_stride", _C.c_longlong * _MAX),
+                ("peer_flag", _C.c_void_p * _MAX), ("inbox", _C.c_void_p), ("inbox_stride", _C.c_longlong), ("my_flag", _C.c_void_p),
+                ("push_count", _C.c_void_p), ("error", _C.c_void_p)]
+
+
+@pytest.mark.parametrize("with_dot", [0, 1])
+@pytest.mark.parametrize("sms", ["148", "2"])
+def test_in_kernel_halo_exchange_two_slabs(oracle, with_dot, sms):
+    """Two row slabs of a 7-point cube, each multiplied by the kHalo kernel with the other slab's inbox as its push target
+    (one address space stands in for CUDA IPC).  The emulator runs one kernel at a time, so the neighbour's arrival flag is
+    raised by hand before a launch; what is checked is everything else the kernel does: the values and positions it
+    pushes and the flag it raises, interior blocks first, halo columns read from the inbox of the epoch's parity, y with
+    the bits of the one-process product, and the fused <x,y>.  Two epochs: both buffers."""
+    import ctypes as C
+    import numpy as np
+    env_old = os.environ.get("LISB_EMU_SMS")
+    os.environ["LISB_EMU_SMS"] = sms
+    try:
+        r = subprocess.run(["make", "-C", EMU_DIR, "-j8"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        lib = C.CDLL(os.path.join(EMU_DIR, "_build", "liblis_emu.so"))
+        vp = C.c_void_p
+        lib.lisb200_spmv_csr_tma_p2p.argtypes = [C.c_int] * 4 + [vp] * 5 + [C.c_int] + [vp] * 4 + [C.c_ulonglong, C.c_int, C.c_int, vp]
+        lib.lisb200_reduce_slots.restype = C.c_int
+        L, M, N = 24, 16, 16                       # 2 slabs of 12 planes, 256 rows per plane: row blocks align with planes
+        ptr, idx, val = H.poisson3d_7pt(L, M, N, sort=True)
+        nloc = L // 2 * M * N; plane = M * N
+        keep = []                                  # buffers must outlive the launches
+        slabs = []
+        for rk in (0, 1):
+            r0 = rk * nloc
+            p = ptr[r0:r0 + nloc + 1].astype(np.int64)
+            cols = idx[p[0]:p[-1]].astype(np.int64); vals = val[p[0]:p[-1]].copy()
+            halo = np.unique(cols[(cols < r0) | (cols >= r0 + nloc)])
+            loc = np.where((cols >= r0) & (cols < r0 + nloc), cols - r0, nloc + np.searchsorted(halo, cols))
+            slabs.append(dict(ptr=(p - p[0]).astype(np.int32), idx=loc.astype(np.int32), val=vals, halo=halo, r0=r0))
+        rng = np.random.default_rng(5)
+        for epoch in (1, 2):
+            xg = rng.uniform(-1, 1, L * M * N)
+            yref = oracle.spmv("csr", ptr, idx, val, xg)
+            stride = 256
+            inbox = [np.zeros(2 * stride + 2 * 16 + 8) for _ in (0, 1)]         # doubles; flags live behind the two buffers
+            flags = [ib[2 * stride:2 * stride + 32].view(np.uint64) for ib in inbox]
+            for rk in (0, 1):
+                s = slabs[rk]; other = 1 - rk
+                x = xg[s["r0"]:s["r0"] + nloc].copy(); y = np.zeros(nloc)
+                export = (slabs[other]["halo"] - s["r0"]).astype(np.int32)      # my rows the neighbour reads, its halo order
+                par = epoch & 1
+                # the neighbour's push, by hand: my inbox + its flag
+                inbox[rk][par * stride:par * stride + len(s["halo"])] = xg[s["halo"]]
+                flags[rk][par * 16 + other] = epoch
+                tb = _P2PTable()
+                tb.n_nbr = 1; tb.n_export = len(export); tb.export_index = export.ctypes.data
+                tb.exp_start[0] = 0; tb.exp_start[1] = len(export); tb.nbr_rank[0] = other
+                tb.peer_inbox[0] = inbox[other].ctypes.data; tb.peer_stride[0] = stride
+                tb.peer_flag[0] = flags[other].ctypes.data + 8 * rk
+                tb.inbox = inbox[rk].ctypes.data; tb.inbox_stride = stride; tb.my_flag = flags[rk].ctypes.data
+                cnt = np.zeros(16, np.uint32); err = np.zeros(4, np.int32)
+                tb.push_count = cnt.ctypes.data; tb.error = err.ctypes.data
+                pp = np.concatenate([s["ptr"], np.zeros(4, np.int32)]); ii = np.concatenate([s["idx"], np.zeros(8, np.int32)])
+                vv = np.concatenate([s["val"], np.zeros(8)])
+                part = np.zeros(lib.lisb200_reduce_slots() + 8); counter = np.zeros(16, np.uint32); res = np.zeros(4)
+                lo, hi = plane, nloc - plane                                    # all but the first and last plane
+                keep += [x, y, export, pp, ii, vv, part, counter, res, cnt, err]
+                rc = lib.lisb200_spmv_csr_tma_p2p(nloc, 256, 2048, 2, pp.ctypes.data, ii.ctypes.data, vv.ctypes.data, x.ctypes.data, y.ctypes.data,
+                                                  with_dot, part.ctypes.data, counter.ctypes.data, res.ctypes.data, C.addressof(tb), epoch, lo, hi, None)
+                assert rc == 0 and err[0] == 0
+                H.assert_bits_equal(y, yref[s["r0"]:s["r0"] + nloc], f"slab {rk} epoch {epoch}")
+                # what it pushed: the neighbour's halo values at the neighbour's halo positions, flag = epoch, counter reset
+                np.testing.assert_array_equal(inbox[other][par * stride:par * stride + len(export)], xg[slabs[other]["halo"]])
+                assert flags[other][par * 16 + rk] == epoch and cnt[0] == 0
+                if with_dot:
+                    exact = float(np.dot(x, y))
+                    assert abs(res[0] - exact) <= 1e-12 * np.abs(x * y).sum()
+    finally:
+        if env_old is None:
+            os.environ.pop("LISB_EMU_SMS", None)
+        else:
+            os.environ["LISB_EMU_SMS"] = env_old
