@@ -255,9 +255,11 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
  * every level padded to a multiple of 32 slots with -1 (d_order, nslots entries); per warp of 32
  * slots a SELL slice -- entry q of lane l at d_wptr[w] + 32*q + l of d_sidx/d_sval, d_plen[slot]
  * entries per row, in the order the row sum must run, couplings that must be dropped already
- * removed -- and d_wdep[w], the neighbour (row index) of the warp's rows that sits latest in slot
- * order (-1: none).  d_ticket: one unsigned int of scratch.  d_out (n entries, must not alias
- * d_in) is overwritten with a not-ready pattern first and doubles as the dependency signal.
+ * removed, and the column of an entry given as the SLOT of that row -- and d_wdep[w], the slot
+ * latest in slot order among everything the warp's rows read (-1: none).  d_slot_scratch: 2*nslots
+ * doubles (results in slot order -- overwritten with a not-ready pattern first, this is what waiting
+ * rows poll -- and, for mode 2, wd in slot order); d_ticket: one unsigned int.  d_out (n entries,
+ * row order) must not alias d_in.
  *   mode 0: out[i] = (in[i] - sum v*out[jj]) * wd[i]     SSOR forward w = (D/w+L)^-1 b   src/matrix/lis_matrix_csr.c:1578-1592, 1610-1617
  *                                                        ILU's U solve                   src/precon/lis_precon_iluk.c:1040-1048
  *   mode 1: out[i] =  in[i] - sum v*out[jj]              ILU's unit-diagonal L solve     src/precon/lis_precon_iluk.c:1030-1037
@@ -268,7 +270,7 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
  * grid, i.e. the number of rows waiting at any time. */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
                        const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,
-                       const double *d_wd, const double *d_in, double *d_out,
+                       const double *d_wd, const double *d_in, double *d_out, double *d_slot_scratch,
                        unsigned int *d_ticket, int ctas_per_sm, void *stream);
 
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */

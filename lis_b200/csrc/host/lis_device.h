@@ -141,9 +141,10 @@ typedef struct lisd_perm {        /* rows in dependency-level order + the factor
     int *d_order;                 /* slot -> row (or -1) */
     int *d_wptr;                  /* per warp of 32 slots: start of its slice (nslots/32 + 1 entries) */
     int *d_plen;                  /* per slot: kept entries of the row */
-    int *d_wdep;                  /* per warp: the neighbour row latest in slot order (-1: none) */
-    int *d_sidx;                  /* slices: entry q of lane l at wptr[w] + 32*q + l */
+    int *d_wdep;                  /* per warp: the neighbour SLOT latest in slot order (-1: none) */
+    int *d_sidx;                  /* slices: entry q of lane l at wptr[w] + 32*q + l; columns are slot numbers */
     double *d_sval;
+    double *d_slots;              /* 2 * nslots doubles of scratch: slot-ordered results (the dependency signal) and wd */
 } lisd_perm;
 LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
                         const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, const int *blk_lo, const int *blk_hi);

@@ -468,15 +468,17 @@ typedef struct lisd_sweep {
 void lisd_perm_free(lisd_perm *p)
 {
     lisd_free(p->d_order); lisd_free(p->d_wptr); lisd_free(p->d_plen); lisd_free(p->d_wdep); lisd_free(p->d_sidx); lisd_free(p->d_sval);
+    lisd_free(p->d_slots);
     memset(p, 0, sizeof(*p));
 }
 
 /* rows[] is level-ordered, lptr[l] its level pointers.  Builds, on the device, what the one-launch sweep
  * kernel reads (kernels/sweep.cu): the padded slot order, and the triangular part (ptr/idx/val, host)
  * as SELL-32 slices in that order -- per warp of 32 slots, entry q of lane l at wptr[w] + 32*q + l,
- * each row's entries in their storage order.  blk_lo/blk_hi (or NULL): per row, the range of columns
+ * each row's entries in their storage order, the column of an entry replaced by the SLOT of that row (the
+ * kernel publishes and polls in slot order).  blk_lo/blk_hi (or NULL): per row, the range of columns
  * the row keeps; couplings outside are the ones the block sweep drops (src/matrix/lis_matrix_csr.c:1590,
- * 1601) and are left out here.  wdep[w]: of all neighbours the warp's rows read, the one latest in slot order. */
+ * 1601) and are left out here.  wdep[w]: of all neighbours the warp's rows read, the slot latest in slot order. */
 LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
                         const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, const int *blk_lo, const int *blk_hi)
 {
@@ -507,7 +509,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
     {
         size_t total = 0;
         for (size_t w = 0; w < nw; w++) {
-            int width = 0, latest = -1, latest_row = -1;
+            int width = 0, latest = -1;
             for (int lane = 0; lane < 32; lane++) {
                 const size_t k = w * 32 + (size_t)lane;
                 const int i = order[k];
@@ -517,13 +519,13 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
                         const int jj = idx[j];
                         if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
                         cnt++;
-                        if (slot_of[jj] > latest) { latest = slot_of[jj]; latest_row = jj; }
+                        if (slot_of[jj] > latest) latest = slot_of[jj];
                     }
                 plen[k] = cnt;
                 if (cnt > width) width = cnt;
             }
             wptr[w] = (int)total;
-            wdep[w] = latest_row;
+            wdep[w] = latest;
             total += (size_t)32 * (size_t)width;
             if (total > 0x7fffff00u) { LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "sweep schedule too large\n"); err = LIS_ERR_OUT_OF_MEMORY; goto done; }
         }
@@ -542,12 +544,12 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
                 for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++) {
                     const int jj = idx[j];
                     if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
-                    sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = jj;
+                    sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = slot_of[jj];
                     sval[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = val[j];
                     q++;
                 }
             for (; q < width; q++) {
-                sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = i >= 0 ? i : 0;
+                sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = (int)(w * 32 + (size_t)lane);
                 sval[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = 0.0;
             }
         }
@@ -567,6 +569,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         if (!err) err = lisd_upload(P->d_sidx, sidx, sizeof(int) * total);
         if (!err) err = lisd_malloc((void **)&P->d_sval, sizeof(double) * (total ? total : 1));
         if (!err) err = lisd_upload(P->d_sval, sval, sizeof(double) * total);
+        if (!err) err = lisd_malloc((void **)&P->d_slots, sizeof(double) * 2 * (nslots ? nslots : 1));     /* slot-ordered results + wd */
     }
 done:
     free(order); free(plen); free(slot_of); free(wptr); free(wdep); free(sidx); free(sval);
@@ -578,7 +581,7 @@ int lisd_sweep_ctas(void);
 int lisd_perm_sweep(const lisd_perm *P, int mode, int n, const double *d_wd, const double *d_in, double *d_out, unsigned int *d_ticket)
 {
     return lisb200_sweep_sell(mode, n, P->nslots, P->d_order, P->d_wptr, P->d_plen, P->d_wdep, P->d_sidx, P->d_sval,
-                              d_wd, d_in, d_out, d_ticket, lisd_sweep_ctas(), lisd_stream());
+                              d_wd, d_in, d_out, P->d_slots, d_ticket, lisd_sweep_ctas(), lisd_stream());
 }
 
 /* how many CTAs per SM the persistent sweep grid gets (LIS_B200_SWEEP_CTAS=1..6; default 6) */

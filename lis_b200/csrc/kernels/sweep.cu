@@ -63,9 +63,15 @@ ssor_bwd_kernel(int nrows, const int *__restrict__ rows,
 // levels => lanes of a warp never wait on each other) and stores the triangular factor in that
 // order as SELL-32: the 32 rows of a warp form a slice, entry q of lane l sits at
 // slice_start + 32*q + l, so every load of the factor is coalesced.  Couplings the block sweep
-// drops (OpenMP block-SSOR) are removed on the host.  The output vector itself carries the "done"
-// signal: it is pre-filled with a signalling-NaN pattern that no IEEE operation can produce, and a
-// row reads a neighbour by polling until the pattern is gone.
+// drops (OpenMP block-SSOR) are removed on the host.  Results are published twice: in row order
+// (the output vector) and in SLOT order into a scratch vector that also carries the "done" signal --
+// it is pre-filled with a signalling-NaN pattern that no IEEE operation can produce, and a row reads
+// a neighbour (the factor's column indices are slot numbers) by polling until the pattern is gone.
+// In slot order the rows a warp waits for sit next to each other (for a stencil the neighbours of 32
+// consecutive rows of a level are 32 consecutive rows of the level before): a poll of the warp is
+// 8 sectors instead of 32, and the part of the vector that is live -- a few levels -- is a compact
+// window that stays in L2, where the row-ordered vector of the earlier versions was scattered over
+// the whole array and every first touch went to DRAM.
 //
 // What bounds a sweep is the dependency depth times the time of one hop (publish -> L2 -> poll).
 // Round 1's kernel let every waiting thread poll all of its neighbours: at 256^3, 22 GB of L2
@@ -116,7 +122,8 @@ __global__ void __launch_bounds__(kSweepThreads, 6)
 sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restrict__ wptr,
                   const int *__restrict__ plen, const int *__restrict__ wdep,
                   const int *__restrict__ sidx, const double *__restrict__ sval,
-                  const double *__restrict__ wd, const double *__restrict__ in, double *out, unsigned int *ticket)
+                  const double *__restrict__ wd, const double *__restrict__ wds /* kSweepReadScaled: wd in slot order */,
+                  const double *__restrict__ in, double *__restrict__ out, double *pout, unsigned int *ticket)
 {
     __shared__ unsigned int vblock[2];
     constexpr bool kSub = kMode != kSweepBwd;       // running value starts at in[i] and products are subtracted
@@ -152,7 +159,7 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
                     v[q] = len > 0 ? cv[32 * qq] : 0.0;
                 }
                 // long rows: touch the neighbours behind the first batch too (sectors into L2, values unused)
-                for (int q = kBatch; q < len; ++q) (void)ld_poll(out + ci[32 * (size_t)q]);
+                for (int q = kBatch; q < len; ++q) (void)ld_poll(pout + ci[32 * (size_t)q]);
                 double t = kSub ? inv : 0.0;
                 bool waited = false;
                 for (int q0 = 0; q0 < len; q0 += kBatch) {
@@ -169,7 +176,7 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
                         // below is an L2 hit and not a DRAM fill.
                         unsigned long long bits[kBatch];
 #pragma unroll
-                        for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(out + jj[q]) : kNotReady;
+                        for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(pout + jj[q]) : kNotReady;
 #pragma unroll
                         for (int q = 0; q < kBatch; ++q)
                             if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
@@ -177,13 +184,13 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
                             // wait on ONE address for the whole warp -- the neighbour of its 32 rows that
                             // sits latest in slot order -- instead of every lane polling all of its own
                             waited = true;
-                            if (dep >= 0) while (ld_poll(out + dep) == kNotReady) { }
+                            if (dep >= 0) while (ld_poll(pout + dep) == kNotReady) { }
                         }
                     }
 #pragma unroll
                     for (int q = 0; q < kBatch; ++q)
                         if (used & (1u << q)) {
-                            if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wd[jj[q]]);
+                            if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wds[jj[q]]);
                             t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
                         }
                     if (q0 + kBatch < len) {
@@ -195,7 +202,9 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
                         }
                     }
                 }
-                st_publish(out + i, kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t);
+                const double r = kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t;
+                st_publish(pout + k, r);             // slot order: what the waiting rows poll (contiguous per warp)
+                out[i] = r;                          // row order: the result
             }
         }
         if (threadIdx.x == 0) vblock[round ^ 1] = next_ticket;
@@ -203,19 +212,24 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
     }
 }
 
-}  // namespace lisb
+/* slot-ordered copy of a row-ordered vector (wd for the read-scaled mode) */
+__global__ void __launch_bounds__(256)
+gather_slots_kernel(int nslots, const int *__restrict__ order, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nslots) { const int i = order[k]; dst[k] = i >= 0 ? src[i] : 0.0; }
+}
 
+}  // namespace lisb
 using namespace lisb;
 
-/* One-launch triangular sweep on a host-prepared factor (rows in dependency-level order, SELL-32
- * slices, dropped couplings already removed); see include/lis_b200_kernels.h. */
 extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
                                   const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,
-                                  const double *d_wd, const double *d_in, double *d_out,
+                                  const double *d_wd, const double *d_in, double *d_out, double *d_slot_scratch,
                                   unsigned int *d_ticket, int ctas_per_sm, void *stream)
 {
     if (nslots <= 0 || n <= 0) return 0;
-    if (mode < 0 || mode > 3 || (mode != kSweepPlain && d_wd == nullptr) || (nslots & 31)) return (int)cudaErrorInvalidValue;
+    if (mode < 0 || mode > 3 || (mode != kSweepPlain && d_wd == nullptr) || (nslots & 31) || d_slot_scratch == nullptr) return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
@@ -224,17 +238,19 @@ extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_orde
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
-    int fill_grid = (n + 255) / 256;
+    double *pout = d_slot_scratch, *wds = d_slot_scratch + nslots;      // scratch: 2 * nslots doubles
+    int fill_grid = (nslots + 255) / 256;
     if (fill_grid > sms * 8) fill_grid = sms * 8;
-    fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(n, d_out);
+    fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(nslots, pout);
+    if (mode == kSweepReadScaled) gather_slots_kernel<<<(nslots + 255) / 256, 256, 0, st>>>(nslots, d_order, d_wd, wds);
     if (ctas_per_sm < 1 || ctas_per_sm > 6) ctas_per_sm = 6;
     int grid = (nslots + kSweepThreads - 1) / kSweepThreads;
     if (grid > sms * ctas_per_sm) grid = sms * ctas_per_sm;
     switch (mode) {
-    case kSweepFwd: sweep_sell_kernel<kSweepFwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
-    case kSweepPlain: sweep_sell_kernel<kSweepPlain><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
-    case kSweepReadScaled: sweep_sell_kernel<kSweepReadScaled><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
-    default: sweep_sell_kernel<kSweepBwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, d_in, d_out, d_ticket); break;
+    case kSweepFwd: sweep_sell_kernel<kSweepFwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    case kSweepPlain: sweep_sell_kernel<kSweepPlain><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    case kSweepReadScaled: sweep_sell_kernel<kSweepReadScaled><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    default: sweep_sell_kernel<kSweepBwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
     }
     LISB_CHECK_LAUNCH();
     return 0;

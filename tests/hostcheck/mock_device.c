@@ -229,23 +229,25 @@ int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const
 }
 /* slots are in dependency (level) order, so a sequential walk is a valid schedule */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int *wptr, const int *plen, const int *wdep,
-                       const int *sidx, const double *sval, const double *wd, const double *in, double *out,
+                       const int *sidx, const double *sval, const double *wd, const double *in, double *out, double *scratch,
                        unsigned int *ticket, int ctas, void *s)
 {
     (void)ticket; (void)s; (void)ctas; (void)wdep;
-    for (int i = 0; i < n; i++) out[i] = NAN;              /* a row read before it was written would poison the result */
+    double *pout = scratch;
+    for (int i = 0; i < n; i++) out[i] = NAN;
+    for (int k = 0; k < nslots; k++) pout[k] = NAN;        /* a row read before it was written would poison the result */
     for (int k = 0; k < nslots; k++) {
         const int i = order[k];
         if (i < 0) continue;
         const size_t base = (size_t)wptr[k >> 5] + (size_t)(k & 31);
         double t = mode == 3 ? 0.0 : in[i];
         for (int q = 0; q < plen[k]; q++) {
-            const int jj = sidx[base + 32 * (size_t)q];
+            const int ks = sidx[base + 32 * (size_t)q];      /* the neighbour's slot */
             const double v = sval[base + 32 * (size_t)q];
-            const double xv = mode == 2 ? out[jj] * wd[jj] : out[jj];
+            const double xv = mode == 2 ? pout[ks] * wd[order[ks]] : pout[ks];
             if (mode == 3) t += v * xv; else t -= v * xv;
         }
-        out[i] = mode == 0 ? t * wd[i] : mode == 3 ? in[i] - t * wd[i] : t;
+        pout[k] = out[i] = mode == 0 ? t * wd[i] : mode == 3 ? in[i] - t * wd[i] : t;
     }
     return 0;
 }
