@@ -148,6 +148,14 @@ LIS_INT lisd_alloc_vector(size_t count, LIS_SCALAR **value, LIS_INT *managed)
         void *p = NULL;
         for (int i = 0; i < LISD_POOL_SLOTS && !p; i++)
             if (g_pool[i].p && g_pool[i].bytes == bytes) { p = g_pool[i].p; g_pool[i].p = NULL; g_pool_bytes -= bytes; }
+        static int force_device = -1;
+        if (force_device < 0) { const char *fv = getenv("LIS_B200_VECTORS"); force_device = (fv && strcmp(fv, "device") == 0) ? 1 : 0; }
+        if (p == NULL && force_device) {
+            /* LIS_B200_VECTORS=device: plain device memory (experiments; v->value is then reachable through the API only) */
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); LIS_SETERR_MEM(bytes); return LIS_ERR_OUT_OF_MEMORY; }
+            *value = (LIS_SCALAR *)p; *managed = 2;
+            return LIS_SUCCESS;
+        }
         if (p == NULL) {
             cudaError_t e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
             if (e != cudaSuccess) {
