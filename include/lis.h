@@ -646,6 +646,9 @@ LIS_INT lis_b200_set_reduce(LIS_INT nccl);
  * Returns the old setting; call on every rank alike. */
 LIS_INT lis_b200_set_p2p(LIS_INT on);
 unsigned long long lis_b200_p2p_products(void);   /* products so far that took that path (diagnostics) */
+/* lis_matvec enqueued on the library stream without waiting for it; lis_b200_sync (or any host-synchronous call) waits */
+LIS_INT lis_b200_matvec_async(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);
+LIS_INT lis_b200_sync(void);
 /* the CUDA stream (cudaStream_t) all kernels of this process are enqueued on */
 void *lis_b200_stream(void);
 

@@ -475,6 +475,21 @@ LIS_INT lis_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     return lisd_sync();
 }
 
+/* lis_matvec without the closing stream synchronisation: the product is enqueued on the library stream
+ * (lis_b200_stream) and the call returns; lis_b200_sync() -- or any host-synchronous lis.h call -- waits for
+ * it.  For callers that keep the queue full (bench.py's device-timed leg). */
+LIS_INT lis_b200_matvec_async(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
+{
+    LIS_INT err = lis_host_matrix_check_input(A);
+    if (err) return err;
+    if (A->n != x->n || A->n != y->n) {
+        LIS_SETERR(LIS_ERR_ILL_ARG, "lis_matvec: sizes of A, x and y do not match\n");
+        return LIS_ERR_ILL_ARG;
+    }
+    return lisd_matvec(A, x, y);
+}
+LIS_INT lis_b200_sync(void) { return lisd_sync(); }
+
 /* ------------------------------------------------------------------ y = A x with HOST x and y
  * What an application that keeps its vectors in host arrays pays per product is two PCIe
  * transfers around a 2 ms kernel; done one after the other (lis_vector_scatter, lis_matvec,

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--impl", default="lis_b200", choices=["lis_b200", "reference"])
     ap.add_argument("--opts", default="")
     ap.add_argument("--dom", type=float, default=0.17)
+    ap.add_argument("--slab", type=int, default=0, help="gm27/cg7: planes per rank of an (slab*N) x size x size box instead of size^3 per rank")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     ref = a.impl == "reference"
@@ -62,23 +63,25 @@ def main():
     t0 = time.time()
     if a.config == "cg7":
         g = a.size or 256
+        sl = a.slab or g
         L.shim_poisson7.restype = C.c_longlong; L.shim_poisson7.argtypes = [C.c_int] * 6 + [C.c_void_p] * 3
-        n = g ** 3
-        nnz = L.shim_poisson7(g * world, g, g, rank * g, (rank + 1) * g, 0, None, None, None)
+        n = sl * g * g
+        nnz = L.shim_poisson7(sl * world, g, g, rank * sl, (rank + 1) * sl, 0, None, None, None)
         pp, pi, pv = libc.malloc(4 * (n + 1)), libc.malloc(4 * nnz), libc.malloc(8 * nnz)
-        L.shim_poisson7(g * world, g, g, rank * g, (rank + 1) * g, 0, pp, pi, pv)
+        L.shim_poisson7(sl * world, g, g, rank * sl, (rank + 1) * sl, 0, pp, pi, pv)
         opts = "-i cg -p jacobi -tol 1e-12 -maxiter 20000 " + a.opts
-        what = f"test3.c 7-pt Poisson {g * world}x{g}x{g}"
+        what = f"test3.c 7-pt Poisson {sl * world}x{g}x{g}"
         flops_it = lambda nnz_g, n_g: 2.0 * nnz_g + 13.0 * n_g
     elif a.config == "gm27":
         g = a.size or 128
+        sl = a.slab or g
         L.shim_poisson27.restype = C.c_longlong; L.shim_poisson27.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
-        n = g ** 3
-        nnz = L.shim_poisson27(g * world, g, g, rank * g, (rank + 1) * g, None, None, None)
+        n = sl * g * g
+        nnz = L.shim_poisson27(sl * world, g, g, rank * sl, (rank + 1) * sl, None, None, None)
         pp, pi, pv = libc.malloc(4 * (n + 1)), libc.malloc(4 * nnz), libc.malloc(8 * nnz)
-        L.shim_poisson27(g * world, g, g, rank * g, (rank + 1) * g, pp, pi, pv)
+        L.shim_poisson27(sl * world, g, g, rank * sl, (rank + 1) * sl, pp, pi, pv)
         opts = "-i gmres -restart 30 -p jacobi -tol 1e-12 -maxiter 20000 " + a.opts
-        what = f"spmvtest3b.c 27-pt stencil {g * world}x{g}x{g}"
+        what = f"spmvtest3b.c 27-pt stencil {sl * world}x{g}x{g}"
         flops_it = lambda nnz_g, n_g: 2.0 * nnz_g + 65.0 * n_g          # (2m+5) n with m = 30
     else:
         gn = a.size or 1000000
@@ -105,7 +108,7 @@ def main():
     oi = np.zeros(4, np.int32); od = np.zeros(6, np.float64); rh = np.zeros(32768)
     L.shim_mv_solve_ones.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     rc = L.shim_mv_solve_ones(h, opts.encode(), oi.ctypes.data, od.ctypes.data, rh.ctypes.data, len(rh))
-    assert rc == 0, (rc, oi)
+    assert rc == 0 or oi[1] == 4, (rc, oi)      # a -maxiter cap (status 4) is a valid rate measurement
     mine = np.array([od[2], od[3], od[4], od[5], float(nnz), float(n)])
     if world > 1:
         lib = lis_b200.load_library()

@@ -753,6 +753,18 @@ EXPORT int shim_mv_get_y_local(int h, double *y_local)
     return (int)lis_vector_get_values(y, y->is, y->n, y_local);
 }
 EXPORT int shim_mv_matvec(int h) { return (int)lis_matvec(g_mv[h].A, g_mv[h].x, g_mv[h].y); }
+/* `iters` products enqueued back to back, one synchronisation at the end (lis_b200 only; the reference is synchronous anyway) */
+EXPORT int shim_mv_matvec_queue(int h, int iters)
+{
+    LIS_INT err = 0;
+#ifdef LIS_B200_LIS_H
+    for (int k = 0; k < iters && !err; k++) err = lis_b200_matvec_async(g_mv[h].A, g_mv[h].x, g_mv[h].y);
+    if (!err) err = lis_b200_sync();
+#else
+    for (int k = 0; k < iters && !err; k++) err = lis_matvec(g_mv[h].A, g_mv[h].x, g_mv[h].y);
+#endif
+    return (int)err;
+}
 EXPORT int shim_mv_matvech(int h) { return (int)lis_matvech(g_mv[h].A, g_mv[h].x, g_mv[h].y); }
 EXPORT int shim_mv_dot_xy(int h, double *out) { LIS_SCALAR s = 0; LIS_INT e = lis_vector_dot(g_mv[h].x, g_mv[h].y, &s); *out = s; return (int)e; }
 
