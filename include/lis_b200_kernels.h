@@ -119,6 +119,9 @@ int lisb200_spmv_jad(int n, int maxnzr, const int *d_jptr, const int *d_perm,
  *                                      src/matvec/lis_matvec_bsr.c:57-150 and :152-858     */
 int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bptr, const int *d_bidx,
                      const double *d_val, const double *d_x, double *d_y, void *stream);
+/* ... for a row-partitioned matrix: x has ncols = n + halo entries, block columns cover [0, ncols) */
+int lisb200_spmv_bsr_cols(int n, int ncols, int nr, int bnr, int bnc, const int *d_bptr,
+                          const int *d_bidx, const double *d_val, const double *d_x, double *d_y, void *stream);
 
 /* ---- BLAS-1 elementwise (bit-exact) -------------------- src/vector/lis_vector_opv.c ---- */
 int lisb200_copy   (int n, const double *d_x, double *d_y, void *stream);               /* :136 */
@@ -266,8 +269,9 @@ int lisb200_ssor_backward_level(int nrows, const int *d_rows,
  *   mode 2: out[i] =  in[i] - sum v*(out[jj]*wd[jj])     first half of the transposed SSOR sweep   src/matrix/lis_matrix_csr.c:1838-1845
  *   mode 3: out[i] =  in[i] - (sum v*out[jj]) * wd[i]    SSOR backward                   src/matrix/lis_matrix_csr.c:1593-1605, 1618-1628
  * Sums run in storage order, unfused: same result bits as the level-launched kernels and the
- * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm (1..6, else 6) bounds the persistent
- * grid, i.e. the number of rows waiting at any time. */
+ * reference loops.  d_wd may be NULL for mode 1.  ctas_per_sm: low byte 1..9 bounds the persistent
+ * grid (the number of rows waiting at any time; 0 = as many as fit); bit 8 set = no row has more than 4
+ * entries: the narrow-batch instantiation (9 instead of 6 CTAs per SM). */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const int *d_wptr,
                        const int *d_plen, const int *d_wdep, const int *d_sidx, const double *d_sval,
                        const double *d_wd, const double *d_in, double *d_out, double *d_slot_scratch,

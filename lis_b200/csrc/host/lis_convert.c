@@ -147,11 +147,8 @@ static LIS_INT csr2bsr(LIS_MATRIX Ain, LIS_MATRIX Aout)
 {
     const LIS_INT n = Ain->n, np = Ain->np;
     const LIS_INT bnr = Aout->conv_bnr, bnc = Aout->conv_bnc, bs = bnr * bnc;
-    if (np != n) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "BSR is not available for row-partitioned (multi-GPU) matrices\n");
-        return LIS_ERR_NOT_IMPLEMENTED;
-    }
-    const LIS_INT nr = 1 + (n - 1) / bnr, nc = 1 + (n - 1) / bnc;
+    /* row-partitioned: n local rows, np = n + halo columns (src/matrix/lis_matrix_bsr.c:371-375 under USE_MPI) */
+    const LIS_INT nr = 1 + (n - 1) / bnr, nc = 1 + (np - 1) / bnc;
     LIS_INT *bptr = NULL, *bindex = NULL, err;
     LIS_SCALAR *value = NULL;
     LIS_INT *pos = (LIS_INT *)calloc((size_t)nc, sizeof(LIS_INT));       /* 1 + block slot, 0 = unseen */
@@ -231,13 +228,11 @@ LIS_INT lis_host_transpose(LIS_INT n, LIS_INT ncols, const LIS_INT *ptr, const L
 
 static LIS_INT csr2csc(LIS_MATRIX Ain, LIS_MATRIX Aout)
 {
-    if (Ain->np != Ain->n) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "CSC is not available for row-partitioned (multi-GPU) matrices\n");
-        return LIS_ERR_NOT_IMPLEMENTED;
-    }
+    /* row-partitioned: np = n + halo columns, each with its own (possibly empty) column list
+     * (src/matrix/lis_matrix_csc.c: ptr has np+1 entries under USE_MPI) */
     LIS_INT *ptr, *index;
     LIS_SCALAR *value;
-    LIS_INT err = transpose(Ain->n, Ain->n, Ain->ptr, Ain->index, Ain->value, &ptr, &index, &value);
+    LIS_INT err = transpose(Ain->n, Ain->np, Ain->ptr, Ain->index, Ain->value, &ptr, &index, &value);
     if (err) return err;
     err = lis_matrix_set_csc(Ain->ptr[Ain->n], ptr, index, value, Aout);
     if (err) { lis_free2(3, ptr, index, value); return err; }
@@ -256,7 +251,7 @@ static LIS_INT csc2csr(LIS_MATRIX Ain, LIS_MATRIX Aout)
 {
     LIS_INT *ptr, *index;
     LIS_SCALAR *value;
-    LIS_INT err = transpose(Ain->n, Ain->n, Ain->ptr, Ain->index, Ain->value, &ptr, &index, &value);
+    LIS_INT err = transpose(Ain->np, Ain->n, Ain->ptr, Ain->index, Ain->value, &ptr, &index, &value);       /* np columns back into n rows */
     if (err) return err;
     return install_csr(Aout, Ain->ptr[Ain->n], ptr, index, value);
 }

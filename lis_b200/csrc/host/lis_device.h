@@ -138,6 +138,7 @@ void    lisd_sweep_free(void *sweep);
 /* ---- triangular factors prepared for the one-launch ("sync-free") solve kernels ---- */
 typedef struct lisd_perm {        /* rows in dependency-level order + the factor as SELL-32 slices in that order */
     int nslots;                   /* levels concatenated, each padded to a multiple of 32 */
+    int short_rows;               /* no row keeps more than 4 entries: the narrow-batch kernel instantiation */
     int *d_order;                 /* slot -> row (or -1) */
     int *d_wptr;                  /* per warp of 32 slots: start of its slice (nslots/32 + 1 entries) */
     int *d_plen;                  /* per slot: kept entries of the row */

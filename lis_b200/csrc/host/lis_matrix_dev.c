@@ -148,7 +148,7 @@ LIS_INT lisd_matrix_get(LIS_MATRIX A, lisd_matrix **out)
              * arrays, run through the CSR kernel, adds the same products in the same order */
             LIS_INT *tp, *ti;
             LIS_SCALAR *tv;
-            err = lis_host_transpose(n, n, A->ptr, A->index, A->value, &tp, &ti, &tv);
+            err = lis_host_transpose(A->np, n, A->ptr, A->index, A->value, &tp, &ti, &tv);     /* np columns (halo included) -> n rows */
             if (!err) { err = csr_upload(&M->csr, n, tp, ti, tv); lis_free2(3, tp, ti, tv); }
             break;
         }
@@ -235,7 +235,7 @@ static LIS_INT matvec_launch(LIS_MATRIX A, lisd_matrix *M, const double *x, doub
     case LIS_MATRIX_ELL: rc = lisb200_spmv_ell(n, M->maxnzr, M->ld, M->idx, M->val, x, y, st); break;
     case LIS_MATRIX_DIA: rc = lisb200_spmv_dia(n, M->np, M->nnd, M->ld, M->off, M->val, x, y, st); break;
     case LIS_MATRIX_JAD: rc = lisb200_spmv_jad(n, M->maxnzr, M->jptr, M->perm, M->idx, M->val, x, y, st); break;
-    case LIS_MATRIX_BSR: rc = lisb200_spmv_bsr(n, M->nr, M->bnr, M->bnc, M->bptr, M->bidx, M->val, x, y, st); break;
+    case LIS_MATRIX_BSR: rc = lisb200_spmv_bsr_cols(n, M->np > n ? M->np : n, M->nr, M->bnr, M->bnc, M->bptr, M->bidx, M->val, x, y, st); break;
     default: LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED;
     }
     lisd_mark_busy();

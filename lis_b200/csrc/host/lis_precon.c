@@ -506,6 +506,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         }
     }
     /* pass 1: kept entries per row, slice widths, the warp's latest neighbour */
+    int maxlen = 0;
     {
         size_t total = 0;
         for (size_t w = 0; w < nw; w++) {
@@ -523,6 +524,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
                     }
                 plen[k] = cnt;
                 if (cnt > width) width = cnt;
+                if (cnt > maxlen) maxlen = cnt;
             }
             wptr[w] = (int)total;
             wdep[w] = latest;
@@ -555,6 +557,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         }
     }
     P->nslots = (int)nslots;
+    P->short_rows = maxlen <= 4;
     {
         const size_t total = (size_t)wptr[nw];
         err = lisd_malloc((void **)&P->d_order, sizeof(int) * (nslots ? nslots : 1));
@@ -581,14 +584,14 @@ int lisd_sweep_ctas(void);
 int lisd_perm_sweep(const lisd_perm *P, int mode, int n, const double *d_wd, const double *d_in, double *d_out, unsigned int *d_ticket)
 {
     return lisb200_sweep_sell(mode, n, P->nslots, P->d_order, P->d_wptr, P->d_plen, P->d_wdep, P->d_sidx, P->d_sval,
-                              d_wd, d_in, d_out, P->d_slots, d_ticket, lisd_sweep_ctas(), lisd_stream());
+                              d_wd, d_in, d_out, P->d_slots, d_ticket, lisd_sweep_ctas() | (P->short_rows ? 0x100 : 0), lisd_stream());
 }
 
-/* how many CTAs per SM the persistent sweep grid gets (LIS_B200_SWEEP_CTAS=1..6; default 6) */
+/* how many CTAs per SM the persistent sweep grid gets (LIS_B200_SWEEP_CTAS=1..9; default: as many as fit, 9 for short-row factors, 6 otherwise) */
 int lisd_sweep_ctas(void)
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("LIS_B200_SWEEP_CTAS"); v = e ? atoi(e) : 0; if (v < 1 || v > 6) v = 6; }
+    if (v < 0) { const char *e = getenv("LIS_B200_SWEEP_CTAS"); v = e ? atoi(e) : 0; if (v < 1 || v > 9) v = 0; }
     return v;
 }
 

@@ -504,7 +504,7 @@ constexpr int kBsrTileDoubles = 4096;     // products per shared-memory window (
 // 8-way (32-byte blocks 7 blocks apart; profiles/r02_ncu_bsr_v2.txt).
 template <int R, int C>
 __global__ void __launch_bounds__(kBsrRows)
-bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
+bsr_tile_kernel(int n, int ncols, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
                 const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
 {
     constexpr int BS = R * C;
@@ -557,10 +557,10 @@ bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restri
                     const int rem = off[u] % BS;
                     // a padded last block column holds structural zeros; x behind them does not exist
                     const int c0 = bcol[u] + rem / R;
-                    x0[u] = c0 < n ? __ldg(x + c0) : 0.0;
+                    x0[u] = c0 < ncols ? __ldg(x + c0) : 0.0;
                     if (kVec) {
                         if (R % 2 == 0) x1[u] = x0[u];                 // rem is even: both elements sit in the same block column
-                        else { const int c1 = bcol[u] + (rem + 1) / R; x1[u] = c1 < n ? __ldg(x + c1) : 0.0; }
+                        else { const int c1 = bcol[u] + (rem + 1) / R; x1[u] = c1 < ncols ? __ldg(x + c1) : 0.0; }
                     }
                 }
             }
@@ -595,7 +595,7 @@ bsr_tile_kernel(int n, int nr, const int *__restrict__ bptr, const int *__restri
 
 // generic block size (bnr or bnc > 4): one thread per scalar row, same per-row order
 __global__ void __launch_bounds__(256)
-bsr_generic_kernel(int n, int nr, int bnr, int bnc, const int *__restrict__ bptr,
+bsr_generic_kernel(int n, int ncols, int nr, int bnr, int bnc, const int *__restrict__ bptr,
                    const int *__restrict__ bidx, const double *__restrict__ val,
                    const double *__restrict__ x, double *__restrict__ y)
 {
@@ -608,21 +608,21 @@ bsr_generic_kernel(int n, int nr, int bnr, int bnc, const int *__restrict__ bptr
     for (int bc = s; bc < e; ++bc) {
         const int bj = __ldg(bidx + bc) * bnc;
         const double *v = val + (size_t)bc * bs + i;
-        for (int j = 0; j < bnc; ++j) t = add(t, mul(__ldg(v + (size_t)j * bnr), bj + j < n ? __ldg(x + bj + j) : 0.0));
+        for (int j = 0; j < bnc; ++j) t = add(t, mul(__ldg(v + (size_t)j * bnr), bj + j < ncols ? __ldg(x + bj + j) : 0.0));
     }
     y[row] = t;
 }
 
 template <int R>
-static int launch_bsr_c(int n, int nr, int bnc, const int *bptr, const int *bidx, const double *val,
+static int launch_bsr_c(int n, int ncols, int nr, int bnc, const int *bptr, const int *bidx, const double *val,
                         const double *x, double *y, cudaStream_t st)
 {
     const int grid = (nr + kBsrRows - 1) / kBsrRows;
     switch (bnc) {
-    case 1: bsr_tile_kernel<R, 1><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
-    case 2: bsr_tile_kernel<R, 2><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
-    case 3: bsr_tile_kernel<R, 3><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
-    case 4: bsr_tile_kernel<R, 4><<<grid, kBsrRows, 0, st>>>(n, nr, bptr, bidx, val, x, y); break;
+    case 1: bsr_tile_kernel<R, 1><<<grid, kBsrRows, 0, st>>>(n, ncols, nr, bptr, bidx, val, x, y); break;
+    case 2: bsr_tile_kernel<R, 2><<<grid, kBsrRows, 0, st>>>(n, ncols, nr, bptr, bidx, val, x, y); break;
+    case 3: bsr_tile_kernel<R, 3><<<grid, kBsrRows, 0, st>>>(n, ncols, nr, bptr, bidx, val, x, y); break;
+    case 4: bsr_tile_kernel<R, 4><<<grid, kBsrRows, 0, st>>>(n, ncols, nr, bptr, bidx, val, x, y); break;
     default: return -1;
     }
     return 0;
@@ -875,24 +875,32 @@ extern "C" int lisb200_spmv_jad(int n, int maxnzr, const int *d_jptr, const int 
     return 0;
 }
 
-extern "C" int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bptr,
-                                const int *d_bidx, const double *d_val,
-                                const double *d_x, double *d_y, void *stream)
+/* ncols: entries of x (n for a square matrix, n + halo columns for a row-partitioned one) */
+extern "C" int lisb200_spmv_bsr_cols(int n, int ncols, int nr, int bnr, int bnc, const int *d_bptr,
+                                     const int *d_bidx, const double *d_val,
+                                     const double *d_x, double *d_y, void *stream)
 {
     if (n <= 0 || nr <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = -1;
     if (bnc >= 1 && bnc <= 4 && ((uintptr_t)d_val & 15) == 0) {
         switch (bnr) {
-        case 1: rc = launch_bsr_c<1>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
-        case 2: rc = launch_bsr_c<2>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
-        case 3: rc = launch_bsr_c<3>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
-        case 4: rc = launch_bsr_c<4>(n, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 1: rc = launch_bsr_c<1>(n, ncols, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 2: rc = launch_bsr_c<2>(n, ncols, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 3: rc = launch_bsr_c<3>(n, ncols, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
+        case 4: rc = launch_bsr_c<4>(n, ncols, nr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, st); break;
         default: break;
         }
     }
     if (rc != 0)
-        bsr_generic_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, nr, bnr, bnc, d_bptr, d_bidx, d_val, d_x, d_y);
+        bsr_generic_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, ncols, nr, bnr, bnc, d_bptr, d_bidx, d_val, d_x, d_y);
     LISB_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *d_bptr,
+                                const int *d_bidx, const double *d_val,
+                                const double *d_x, double *d_y, void *stream)
+{
+    return lisb200_spmv_bsr_cols(n, n, nr, bnr, bnc, d_bptr, d_bidx, d_val, d_x, d_y, stream);
 }

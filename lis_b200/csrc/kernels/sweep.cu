@@ -117,97 +117,106 @@ fill_not_ready_kernel(int n, double *x)
 enum { kSweepFwd = 0, kSweepPlain = 1, kSweepReadScaled = 2, kSweepBwd = 3 };
 constexpr int kSweepThreads = 128;
 
-template <int kMode>
-__global__ void __launch_bounds__(kSweepThreads, 6)
+// kBatch: neighbours polled together (registers: 8 -> 80, 4 -> ~56; the host picks 4 for factors whose
+// rows are short -- stencils -- where the extra resident CTAs matter more than the batch width).
+template <int kMode, int kBatch>
+__global__ void __launch_bounds__(kSweepThreads, kBatch == 4 ? 9 : 6)
 sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restrict__ wptr,
                   const int *__restrict__ plen, const int *__restrict__ wdep,
                   const int *__restrict__ sidx, const double *__restrict__ sval,
                   const double *__restrict__ wd, const double *__restrict__ wds /* kSweepReadScaled: wd in slot order */,
                   const double *__restrict__ in, double *__restrict__ out, double *pout, unsigned int *ticket)
 {
-    __shared__ unsigned int vblock[2];
+    // Tickets (128 slots each, in slot order) are drawn two rounds ahead, so that every thread knows the
+    // NEXT block at the start of a round and its first wave of loads (slot -> row, row length, the warp's
+    // latest neighbour, slice start) is in flight while this round waits for its neighbours.
+    __shared__ unsigned int vblock[3];
     constexpr bool kSub = kMode != kSweepBwd;       // running value starts at in[i] and products are subtracted
-    constexpr int kBatch = 8;
-    if (threadIdx.x == 0) vblock[0] = atomicAdd(ticket, 1u);
+    if (threadIdx.x == 0) { vblock[0] = atomicAdd(ticket, 1u); vblock[1] = atomicAdd(ticket, 1u); }
     __syncthreads();
-    for (int round = 0;; round ^= 1) {
-        const long long k0 = (long long)vblock[round] * kSweepThreads;
-        if (k0 >= nslots) break;
-        // the next ticket is on its way while this block's rows are worked on
-        unsigned int next_ticket = 0;
-        if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
-        const int k = (int)k0 + threadIdx.x;
-        if (k < nslots) {                            // nslots is a multiple of 32: whole warps
-            // first wave: nothing here depends on another load
-            const int w = k >> 5, lane = k & 31;
-            const int i = order[k];                  // -1: padding lane
-            const int len = plen[k];
-            const int dep = wdep[w];
-            const size_t base = (size_t)wptr[w] + lane;
-            if (i >= 0) {
-                // second wave: the row's operands and its first batch of the factor
-                const int *ci = sidx + base;
-                const double *cv = sval + base;
-                const double inv = in[i];
-                const double wdv = (kMode == kSweepFwd || kMode == kSweepBwd) ? wd[i] : 0.0;
-                int jj[kBatch];
-                double v[kBatch];
+    const int lane = threadIdx.x & 31;
+    int i = -1, len = 0, dep = -1, base = 0, k = 0;
+    {
+        const long long k0 = (long long)vblock[0] * kSweepThreads + threadIdx.x;
+        if (k0 < nslots) { k = (int)k0; i = order[k]; len = plen[k]; dep = wdep[k >> 5]; base = wptr[k >> 5]; }
+    }
+    for (int round = 0;; round = round == 2 ? 0 : round + 1) {
+        if ((long long)vblock[round] * kSweepThreads >= nslots) break;
+        const int rnext = round == 2 ? 0 : round + 1, rnext2 = rnext == 2 ? 0 : rnext + 1;
+        unsigned int ticket2 = 0;
+        if (threadIdx.x == 0) ticket2 = atomicAdd(ticket, 1u);          // for the round after the next
+        // second wave of this round: the row's operands and its first batch of the factor
+        const int *ci = sidx + (size_t)base + lane;
+        const double *cv = sval + (size_t)base + lane;
+        double inv = 0.0, wdv = 0.0;
+        int jj[kBatch];
+        double v[kBatch];
+        if (i >= 0) {
+            inv = in[i];
+            if (kMode == kSweepFwd || kMode == kSweepBwd) wdv = wd[i];
 #pragma unroll
-                for (int q = 0; q < kBatch; ++q) {
-                    const int qq = q < len ? q : 0;
-                    jj[q] = len > 0 ? ci[32 * qq] : 0;
-                    v[q] = len > 0 ? cv[32 * qq] : 0.0;
-                }
-                // long rows: touch the neighbours behind the first batch too (sectors into L2, values unused)
-                for (int q = kBatch; q < len; ++q) (void)ld_poll(pout + ci[32 * (size_t)q]);
-                double t = kSub ? inv : 0.0;
-                bool waited = false;
-                for (int q0 = 0; q0 < len; q0 += kBatch) {
-                    double xv[kBatch];
-                    unsigned int used = 0;
-#pragma unroll
-                    for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
-                    unsigned int pending = used;
-                    while (pending) {
-                        // all polls of the batch are issued before the first answer is looked at: one
-                        // round trip per batch, not one per neighbour.  The first round also brings the
-                        // neighbours' sectors into L2 long before their values are published (this row
-                        // is several levels ahead of the sweep front), so the round after the wait
-                        // below is an L2 hit and not a DRAM fill.
-                        unsigned long long bits[kBatch];
-#pragma unroll
-                        for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(pout + jj[q]) : kNotReady;
-#pragma unroll
-                        for (int q = 0; q < kBatch; ++q)
-                            if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
-                        if (pending && !waited) {
-                            // wait on ONE address for the whole warp -- the neighbour of its 32 rows that
-                            // sits latest in slot order -- instead of every lane polling all of its own
-                            waited = true;
-                            if (dep >= 0) while (ld_poll(pout + dep) == kNotReady) { }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < kBatch; ++q)
-                        if (used & (1u << q)) {
-                            if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wds[jj[q]]);
-                            t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
-                        }
-                    if (q0 + kBatch < len) {
-#pragma unroll
-                        for (int q = 0; q < kBatch; ++q) {
-                            const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
-                            jj[q] = ci[32 * (size_t)qq];
-                            v[q] = cv[32 * (size_t)qq];
-                        }
-                    }
-                }
-                const double r = kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t;
-                st_publish(pout + k, r);             // slot order: what the waiting rows poll (contiguous per warp)
-                out[i] = r;                          // row order: the result
+            for (int q = 0; q < kBatch; ++q) {
+                const int qq = q < len ? q : 0;
+                jj[q] = len > 0 ? ci[32 * qq] : 0;
+                v[q] = len > 0 ? cv[32 * qq] : 0.0;
             }
         }
-        if (threadIdx.x == 0) vblock[round ^ 1] = next_ticket;
+        // first wave of the NEXT round
+        int ni = -1, nlen = 0, ndep = -1, nbase = 0, nk = 0;
+        {
+            const long long k0 = (long long)vblock[rnext] * kSweepThreads + threadIdx.x;
+            if (k0 < nslots) { nk = (int)k0; ni = order[nk]; nlen = plen[nk]; ndep = wdep[nk >> 5]; nbase = wptr[nk >> 5]; }
+        }
+        if (i >= 0) {                                // -1: padding lane (or past the end)
+            // long rows: touch the neighbours behind the first batch too (sectors into L2, values unused)
+            for (int q = kBatch; q < len; ++q) (void)ld_poll(pout + ci[32 * (size_t)q]);
+            double t = kSub ? inv : 0.0;
+            bool waited = false;
+            for (int q0 = 0; q0 < len; q0 += kBatch) {
+                double xv[kBatch];
+                unsigned int used = 0;
+#pragma unroll
+                for (int q = 0; q < kBatch; ++q) { if (q0 + q < len) used |= 1u << q; xv[q] = 0.0; }
+                unsigned int pending = used;
+                while (pending) {
+                    // all polls of the batch are issued before the first answer is looked at: one
+                    // round trip per batch, not one per neighbour.  The first round also brings the
+                    // neighbours' sectors into L2 long before their values are published (this row
+                    // is several levels ahead of the sweep front).
+                    unsigned long long bits[kBatch];
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) bits[q] = (pending & (1u << q)) ? ld_poll(pout + jj[q]) : kNotReady;
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q)
+                        if ((pending & (1u << q)) && bits[q] != kNotReady) { xv[q] = __longlong_as_double((long long)bits[q]); pending &= ~(1u << q); }
+                    if (pending && !waited) {
+                        // wait on ONE address for the whole warp -- the slot latest in slot order among
+                        // everything its 32 rows read -- instead of every lane polling all of its own
+                        waited = true;
+                        if (dep >= 0) while (ld_poll(pout + dep) == kNotReady) { }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kBatch; ++q)
+                    if (used & (1u << q)) {
+                        if (kMode == kSweepReadScaled) xv[q] = mul(xv[q], wds[jj[q]]);
+                        t = kSub ? sub(t, mul(v[q], xv[q])) : add(t, mul(v[q], xv[q]));
+                    }
+                if (q0 + kBatch < len) {
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) {
+                        const int qq = q0 + kBatch + q < len ? q0 + kBatch + q : q0 + kBatch;
+                        jj[q] = ci[32 * (size_t)qq];
+                        v[q] = cv[32 * (size_t)qq];
+                    }
+                }
+            }
+            const double r = kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t;
+            st_publish(pout + k, r);                 // slot order: what the waiting rows poll (contiguous per warp)
+            out[i] = r;                              // row order: the result
+        }
+        if (threadIdx.x == 0) vblock[rnext2] = ticket2;
+        i = ni; len = nlen; dep = ndep; base = nbase; k = nk;
         __syncthreads();
     }
 }
@@ -243,15 +252,31 @@ extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_orde
     if (fill_grid > sms * 8) fill_grid = sms * 8;
     fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(nslots, pout);
     if (mode == kSweepReadScaled) gather_slots_kernel<<<(nslots + 255) / 256, 256, 0, st>>>(nslots, d_order, d_wd, wds);
-    if (ctas_per_sm < 1 || ctas_per_sm > 6) ctas_per_sm = 6;
+    // ctas_per_sm: bit 8 set = the factor's rows are short (<= 4 kept entries): the narrow-batch instantiation,
+    // which fits 9 CTAs per SM instead of 6
+    const bool short_rows = (ctas_per_sm & 0x100) != 0;
+    ctas_per_sm &= 0xff;
+    const int cap = short_rows ? 9 : 6;
+    if (ctas_per_sm < 1 || ctas_per_sm > cap) ctas_per_sm = cap;
     int grid = (nslots + kSweepThreads - 1) / kSweepThreads;
     if (grid > sms * ctas_per_sm) grid = sms * ctas_per_sm;
-    switch (mode) {
-    case kSweepFwd: sweep_sell_kernel<kSweepFwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
-    case kSweepPlain: sweep_sell_kernel<kSweepPlain><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
-    case kSweepReadScaled: sweep_sell_kernel<kSweepReadScaled><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
-    default: sweep_sell_kernel<kSweepBwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+#define LISB_SWEEP_LAUNCH(M, B) sweep_sell_kernel<M, B><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_wptr, d_plen, d_wdep, d_sidx, d_sval, d_wd, wds, d_in, d_out, pout, d_ticket)
+    if (short_rows) {
+        switch (mode) {
+        case kSweepFwd: LISB_SWEEP_LAUNCH(kSweepFwd, 4); break;
+        case kSweepPlain: LISB_SWEEP_LAUNCH(kSweepPlain, 4); break;
+        case kSweepReadScaled: LISB_SWEEP_LAUNCH(kSweepReadScaled, 4); break;
+        default: LISB_SWEEP_LAUNCH(kSweepBwd, 4); break;
+        }
+    } else {
+        switch (mode) {
+        case kSweepFwd: LISB_SWEEP_LAUNCH(kSweepFwd, 8); break;
+        case kSweepPlain: LISB_SWEEP_LAUNCH(kSweepPlain, 8); break;
+        case kSweepReadScaled: LISB_SWEEP_LAUNCH(kSweepReadScaled, 8); break;
+        default: LISB_SWEEP_LAUNCH(kSweepBwd, 8); break;
+        }
     }
+#undef LISB_SWEEP_LAUNCH
     LISB_CHECK_LAUNCH();
     return 0;
 }

@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--dom", type=float, default=0.17)
     ap.add_argument("--slab", type=int, default=0, help="gm27/cg7: planes per rank of an (slab*N) x size x size box instead of size^3 per rank")
     ap.add_argument("--out", default="")
+    ap.add_argument("--maxiter", type=int, default=0, help="cap the iterations (a rate measurement, status 4)")
     a = ap.parse_args()
     ref = a.impl == "reference"
     if ref:
@@ -95,6 +96,8 @@ def main():
         opts = "-i bicgstab -p ssor -tol 1e-12 -maxiter 5000 " + a.opts
         what = f"banded unsymmetric n={gn}, 70 entries/row, |i-j|<=1e5, diag = {a.dom}*sum|offdiag|"
         flops_it = lambda nnz_g, n_g: 4.0 * nnz_g + 2.0 * 2.0 * nnz_g + 26.0 * n_g   # 2 products + 2 SSOR applies (~2 nnz each)
+    if a.maxiter:
+        opts += f" -maxiter {a.maxiter}"
     gen_s = time.time() - t0
     t0 = time.time()
     if ref:

@@ -66,6 +66,7 @@ cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaS
 cudaError_t cudaMemPrefetchAsync(const void *p, size_t n, int dev, cudaStream_t st) { (void)p; (void)n; (void)dev; (void)st; return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind k) { (void)k; memmove(d, s, n); return cudaSuccess; }
 /* peer memory / IPC: not available here, so the in-kernel halo exchange stays off and the staged transport runs */
 cudaError_t cudaDeviceGetPCIBusId(char *b, int len, int dev) { (void)dev; if (len > 0) b[0] = 0; return cudaErrorNotSupported; }
 cudaError_t cudaDeviceGetByPCIBusId(int *dev, const char *b) { (void)b; *dev = -1; return cudaErrorNotSupported; }
@@ -121,7 +122,7 @@ int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *off, const dou
 }
 int lisb200_spmv_jad(int n, int m, const int *jp, const int *perm, const int *i, const double *v, const double *x, double *y, void *s)
 { (void)s; if (n > 0) orc_spmv_jad(n, m, jp, perm, i, v, x, y, 1); return 0; }
-int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *bp, const int *bi, const double *v, const double *x, double *y, void *s)
+int lisb200_spmv_bsr_cols(int n, int ncols, int nr, int bnr, int bnc, const int *bp, const int *bi, const double *v, const double *x, double *y, void *s)
 {
     /* like the kernels, never read x beyond the vector: entries of a padded last block column are
      * structural zeros, but x[...] behind them does not exist */
@@ -133,7 +134,7 @@ int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *bp, const int *
         for (int bc = bp[b]; bc < bp[b + 1]; bc++)
             for (int j = 0; j < bnc; j++) {
                 const int c = bi[bc] * bnc + j;
-                const double xj = c < n ? x[c] : 0.0;
+                const double xj = c < ncols ? x[c] : 0.0;
                 for (int i = 0; i < bnr; i++) t[i] += v[(size_t)bc * bs + (size_t)j * bnr + i] * xj;
             }
         for (int i = 0; i < bnr; i++) if (b * bnr + i < n) y[b * bnr + i] = t[i];
@@ -227,6 +228,8 @@ int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const
     }
     return 0;
 }
+int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *bp, const int *bi, const double *v, const double *x, double *y, void *s)
+{ return lisb200_spmv_bsr_cols(n, n, nr, bnr, bnc, bp, bi, v, x, y, s); }
 /* slots are in dependency (level) order, so a sequential walk is a valid schedule */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int *wptr, const int *plen, const int *wdep,
                        const int *sidx, const double *sval, const double *wd, const double *in, double *out, double *scratch,

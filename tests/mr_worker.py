@@ -192,7 +192,7 @@ def main():
         o = H.Oracle()
         y_full = o.spmv("csr", ptr, idx, val, x)
         bvec = o.spmv("csr", ptr, idx, val, np.ones(gn))
-        for fmt in ("csr", "ell", "dia", "jad"):
+        for fmt in ("csr", "ell", "dia", "jad", "bsr", "csc"):
             h = L.shim_mv_open_dist(lis_b200.FMT[fmt], nl, lp, li, lv, 0)
             assert h >= 0, (fmt, h)
             assert L.shim_mv_set_x_local(h, np.ascontiguousarray(x[is_:ie])) == 0
@@ -200,7 +200,15 @@ def main():
                 assert L.shim_mv_matvec(h) == 0
             yl = np.zeros(nl)
             assert L.shim_mv_get_y_local(h, yl) == 0
-            if fmt == "dia":
+            if fmt == "csc":
+                # CSC sums a row in ascending LOCAL column order (halo columns come after the owned ones, as in the
+                # reference's MPI build): same products, another order than the one-process matrix
+                assert np.allclose(yl, y_full[is_:ie], rtol=1e-13, atol=1e-13 * np.abs(y_full).max())
+            elif fmt == "bsr":
+                # BSR adds a row's products block column by block column in first-seen block order; with local + halo
+                # numbering the blocks differ from the one-process matrix's: same products, another order
+                assert np.allclose(yl, y_full[is_:ie], rtol=1e-13, atol=1e-13 * np.abs(y_full).max())
+            elif fmt == "dia":
                 # DIA sums by ascending LOCAL offset, and halo columns are numbered after the owned
                 # ones (as in the reference's MPI build), so the order differs from the one-process
                 # run for rows that touch the lower halo: same products, different rounding
