@@ -802,12 +802,15 @@ int lisd_p2p_error(void) { return gp.h_error && *(volatile int *)gp.h_error; }
 
 typedef struct { cudaIpcMemHandle_t handle; long long stride; int ok; } p2p_msg;
 
-static void p2p_prepare(LIS_COMMTABLE t)  /* collective: every rank comes here at its first product on the table */
+/* collective: every rank comes here at its first CSR product on the table; local_ok: this rank's matrix takes the
+ * TMA row-block kernel (the plan depends on the local row lengths, so the ranks must agree before any of them
+ * switches to the in-kernel exchange) */
+static void p2p_prepare(LIS_COMMTABLE t, int local_ok)
 {
     const int me = t->rank, np_ = t->nranks;
     t->p2p = -1;
     if (!gp.probed) p2p_probe();
-    int ok = gp.ok, nn = 0;
+    int ok = gp.ok && local_ok, nn = 0;
     for (int k = 0; k < np_; k++) {
         const int ne = t->export_ptr[k + 1] - t->export_ptr[k], ni = t->import_ptr[k + 1] - t->import_ptr[k];
         if (k == me) continue;
@@ -874,11 +877,11 @@ static unsigned long long g_p2p_products = 0;
 unsigned long long lis_b200_p2p_products(void) { return g_p2p_products; }
 
 /* the table for the fused product on A (device pointer) and the epoch of this product, or NULL: use lisd_halo_exchange */
-const lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, unsigned long long *epoch)
+const lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, int local_ok, unsigned long long *epoch)
 {
     LIS_COMMTABLE t = A->commtable;
     if (t == NULL || g.nranks == 1 || !gp.enabled) return NULL;
-    if (t->p2p == 0) p2p_prepare(t);
+    if (t->p2p == 0) p2p_prepare(t, local_ok);
     if (t->p2p != 1) return NULL;
     *epoch = ++t->p2p_epoch;
     g_p2p_products++;

@@ -168,7 +168,7 @@ LIS_INT lisd_tri_solve(const lisd_tri *T, int mode, const double *d_wd, const do
 LIS_INT lisd_jacobi_dot(LIS_VECTOR r, LIS_VECTOR dinv, LIS_VECTOR z, LIS_SCALAR *rho);        /* z=r.*dinv; <r,z> */
 LIS_INT lisd_cg_update_jacobi(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_VECTOR x, LIS_VECTOR r, LIS_VECTOR dinv, LIS_VECTOR z,
                               LIS_REAL *nrm2_r, LIS_SCALAR *rho, int *fused_out);
-const struct lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, unsigned long long *epoch);   /* in-kernel halo exchange: table + epoch, or NULL */
+const struct lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, int local_ok, unsigned long long *epoch);   /* in-kernel halo exchange: table + epoch, or NULL */
 int     lisd_p2p_error(void);
 LIS_INT lisd_halo_reduce_raw(LIS_MATRIX A, double *d_y);                                         /* y[n..np) back to the owners, added in rank order */
 LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy);        /* y=Ax; <x,y> */

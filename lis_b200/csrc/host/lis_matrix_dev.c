@@ -336,10 +336,11 @@ LIS_INT lisd_matvec(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y)
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
     if (A->nprocs > 1 && A->commtable) {
-        if (M->type == LIS_MATRIX_CSR && !M->splited && M->csr.tma_rows) {
-            /* halo exchange inside the kernel over peer memory, where every rank can map its neighbours */
+        if (M->type == LIS_MATRIX_CSR && !M->splited) {
+            /* halo exchange inside the kernel over peer memory, where every rank can map its neighbours and every
+             * rank's slab takes the TMA row-block kernel (agreed on collectively at the first product) */
             unsigned long long epoch = 0;
-            const struct lisb200_p2p *tb = lisd_p2p_begin(A, &epoch);
+            const struct lisb200_p2p *tb = lisd_p2p_begin(A, M->csr.tma_rows != 0, &epoch);
             if (tb) {
                 if (M->ov_built == 0) overlap_plan(A, M);
                 const int lo = M->ov_built == 1 ? M->ov_lo : 0, hi = M->ov_built == 1 ? M->ov_hi : 0;
@@ -426,9 +427,9 @@ LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *do
     if (!err) err = lisd_vec_device(y);
     if (err) return err;
     if (A->nprocs > 1 && A->commtable) {
-        if (M->type == LIS_MATRIX_CSR && M->csr.tma_rows) {
+        if (M->type == LIS_MATRIX_CSR) {
             unsigned long long epoch = 0;
-            const struct lisb200_p2p *tb = lisd_p2p_begin(A, &epoch);
+            const struct lisb200_p2p *tb = lisd_p2p_begin(A, M->csr.tma_rows != 0, &epoch);
             if (tb) {
                 if (M->ov_built == 0) overlap_plan(A, M);
                 const int lo = M->ov_built == 1 ? M->ov_lo : 0, hi = M->ov_built == 1 ? M->ov_hi : 0;
