@@ -197,6 +197,9 @@ int lisb200_csr_get_diagonal(int n, const int *d_ptr, const int *d_idx, const do
  * the host between the two launches of a conversion.                                            */
 /* *d_out = longest row (ELL maxnzr, JAD maxnzr)            src/matrix/lis_matrix_ell.c:1000-1012 */
 int lisb200_csr_max_row_len(int n, const int *d_ptr, int *d_out, void *stream);
+/* *d_out = 1 when some row has its columns out of ascending order (the post-condition of lis_matrix_sort_csr,
+ * src/matrix/lis_matrix_csr.c:1486-1521), else 0: lets the DIA conversion skip the host sort of an input that is sorted */
+int lisb200_csr_rows_unsorted(int n, const int *d_ptr, const int *d_idx, int *d_out, void *stream);
 /* ELL: d_eval[j*ld+i], d_eidx[j*ld+i], unused slots (0.0, i)  src/matrix/lis_matrix_ell.c:1035-1052 */
 int lisb200_csr2ell(int n, int maxnzr, int ld, const int *d_ptr, const int *d_idx, const double *d_val,
                     int *d_eidx, double *d_eval, void *stream);

@@ -291,9 +291,25 @@ LIS_INT lisd_convert_from_csr(LIS_MATRIX Acsr, LIS_MATRIX Aout, int *done)
     case LIS_MATRIX_ELL: case LIS_MATRIX_DIA: case LIS_MATRIX_JAD: case LIS_MATRIX_BSR: break;
     default: return LIS_SUCCESS;
     }
-    if (Aout->matrix_type == LIS_MATRIX_DIA) lis_matrix_sort_csr(Acsr);       /* lis_matrix_dia.c:1217, mutates Ain like the reference */
     err = lisd_matrix_get(Acsr, &S);
     if (err) return err;
+    if (Aout->matrix_type == LIS_MATRIX_DIA && !Acsr->is_sorted) {
+        /* lis_matrix_dia.c:1217 sorts Ain's rows (and so do we, on the host arrays the caller sees); an input
+         * whose rows are ascending already -- checked on the mirror, 1 ms instead of seconds of host work at
+         * 512^3 -- only gets the flag */
+        int unsorted = 1, *d_flag = NULL;
+        if (!lisd_malloc((void **)&d_flag, 16)) {
+            lisd_mark_busy();
+            if (lisd_check(lisb200_csr_rows_unsorted(Acsr->n, S->csr.ptr, S->csr.idx, d_flag, lisd_stream()), "sortedness check") ||
+                lisd_download(&unsorted, d_flag, sizeof(int))) unsorted = 1;
+            lisd_free(d_flag);
+        }
+        if (unsorted) {
+            lis_matrix_sort_csr(Acsr);                     /* drops the mirror */
+            err = lisd_matrix_get(Acsr, &S);
+            if (err) return err;
+        } else Acsr->is_sorted = LIS_TRUE;
+    }
     *done = 1;
     switch (Aout->matrix_type) {
     case LIS_MATRIX_ELL: return dev_csr2ell(Acsr, S, Aout);

@@ -288,9 +288,35 @@ static int cv_sm_count() {
     return sms;
 }
 
+// *unsorted = 1 if some row's columns are not ascending (lis_matrix_sort_csr's post-condition, src/matrix/lis_matrix_csr.c:1486)
+__global__ void __launch_bounds__(kCvThreads)
+csr_unsorted_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx, int *unsorted)
+{
+    const int stride = gridDim.x * blockDim.x;
+    int bad = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        for (int j = ptr[i] + 1; j < ptr[i + 1]; ++j) bad |= idx[j - 1] > idx[j];
+    if (bad) *unsorted = 1;
+}
+
 }  // namespace lisb
 
 using namespace lisb;
+
+/* *d_out = 1 when some row of the CSR matrix has its columns out of ascending order, else 0 */
+extern "C" int lisb200_csr_rows_unsorted(int n, const int *d_ptr, const int *d_idx, int *d_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    if (n <= 0) return 0;
+    long long grid = ((long long)n + kCvThreads - 1) / kCvThreads;
+    const long long cap = (long long)cv_sm_count() * 16;
+    if (grid > cap) grid = cap;
+    csr_unsorted_kernel<<<(int)grid, kCvThreads, 0, st>>>(n, d_ptr, d_idx, d_out);
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int lisb200_csr_max_row_len(int n, const int *d_ptr, int *d_out, void *stream)
 {
