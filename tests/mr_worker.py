@@ -59,6 +59,26 @@ def overlap_case(rank, world, shim, lib):
             y2 = np.full(nl, np.nan)
             assert L.shim_mv_step_e2e_pipelined(h, np.ascontiguousarray(x[is_:ie]), y2) == 0
             H.assert_bits_equal(y2, want, f"rank {rank} host-buffer product ({kernel})")
+        if hasattr(lib, "lis_b200_set_p2p"):
+            # the halo exchange inside the kernel (real GPUs that can map each other; elsewhere the switch changes
+            # nothing) against the NCCL / staged exchange: same bits, over several epochs (both inbox buffers)
+            lib.lis_b200_p2p_products.restype = C.c_ulonglong
+            for on in (0, 1, 0, 1):
+                lib.lis_b200_set_p2p(on)
+                before = lib.lis_b200_p2p_products()
+                for seed in (11, 12, 13):
+                    x = H.rand_vec(gn, seed, "wide")
+                    want = o.spmv("csr", ptr, idx, val, x)[is_:ie]
+                    assert L.shim_mv_set_x_local(h, np.ascontiguousarray(x[is_:ie])) == 0
+                    assert L.shim_mv_matvec(h) == 0
+                    yl = np.zeros(nl)
+                    assert L.shim_mv_get_y_local(h, yl) == 0
+                    H.assert_bits_equal(yl, want, f"rank {rank} in-kernel exchange={on} ({kernel})")
+                used = lib.lis_b200_p2p_products() - before
+                assert on or used == 0
+                if kernel == "tile":
+                    assert used == 0                     # only the TMA row-block kernel carries the exchange
+            lib.lis_b200_set_p2p(1)
         L.shim_mv_close(h)
     try:
         lib.emu_launch_count.restype = C.c_long; lib.emu_launch_count.argtypes = [C.c_char_p]
