@@ -14,6 +14,7 @@ if [ $rc -ne 0 ]; then
   LIS_B200_NARROW=1 timeout 600 $TR8 --master-port 29603 bench.py --gpus 8 --steps 20 --warmup 3 > $O/r02_bench_8gpu_narrow.json 2> $O/r02_bench_8gpu_narrow.log; echo "bench8 narrowed rc=$?"
   grep -E "rank 0.*(ms/product|in-kernel|CG|e2e)|^8 GPUs" $O/r02_bench_8gpu_narrow.log | cut -c1-260 | head
 fi
+nvcc -arch=sm_100a -O3 -o /tmp/hop profiles/hop_latency.cu && /tmp/hop | tee $O/r02_hop_latency.txt
 rm -f $O/r02_configs_n8.jsonl
 timeout 600 $TR8 --master-port 29604 profiles/run_configs.py gm27 --size 768 --slab 96 --maxiter 600 --out $O/r02_configs_n8.jsonl 2>&1 | grep -E '^\{|Error|error' | cut -c1-700
 timeout 400 $TR8 --master-port 29605 profiles/run_configs.py su --size 10000000 --threads 2 --out $O/r02_configs_n8.jsonl 2>&1 | grep -E '^\{|Error|error' | cut -c1-700
