@@ -204,8 +204,9 @@ LIS_INT lis_psolve_hybrid(LIS_SOLVER solver, LIS_VECTOR b, LIS_VECTOR x)
  * brought to CSR and split like there (so the products switch to the D + L + U order); S is kept as a small CSR
  * matrix of its own, so the apply is one product on the CSR kernel and one axpyz:
  *   y = x - alpha * (S x)     ->  t = S x ;  y = (-alpha)*t + x      (same bits: the sign change is exact)
- * The transposed apply uses S^T through lis_matvech.  Level 0 (which rewrites the system as (I+S)A) and the
- * stationary solvers are not carried over. */
+ * The transposed apply uses S^T through lis_matvech: it sums S^T b and then scales, where the reference updates
+ * y[jj] -= w*u*t in place -- equal to rounding only (the forward apply is bit for bit).  Level 0 (which rewrites the
+ * system as (I+S)A) and the stationary solvers are not carried over. */
 static LIS_INT create_is(LIS_SOLVER solver, LIS_PRECON precon)
 {
     LIS_MATRIX A = solver->A;

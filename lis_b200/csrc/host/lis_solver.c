@@ -640,9 +640,14 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     if (output && A->my_rank == 0) {
         printf("precision             : %s\n", k_precision_atoi[precision]);
         printf("linear solver         : %s\n", k_solvername[nsolver]);
-        if (precon_type < LIS_PRECON_TYPE_LEN - 1) snprintf(buf, sizeof(buf), "%s", k_preconname[precon_type]);
+        /* src/solver/lis_solver.c:770-800: ILU carries its fill level ("Block" on block storage), -adds a suffix */
+        if (precon_type == LIS_PRECON_TYPE_ILU)
+            snprintf(buf, sizeof(buf), "%s%s(%d)", (A->matrix_type == LIS_MATRIX_BSR || A->matrix_type == LIS_MATRIX_VBR) ? "Block " : "",
+                     k_preconname[precon_type], (int)solver->options[LIS_OPTIONS_FILL]);
+        else if (precon_type < LIS_PRECON_TYPE_LEN - 1) snprintf(buf, sizeof(buf), "%s", k_preconname[precon_type]);
         else snprintf(buf, sizeof(buf), "user defined");
-        printf("preconditioner        : %s\n", buf);
+        if (solver->options[LIS_OPTIONS_ADDS] && precon_type) printf("preconditioner        : %s + Additive Schwarz\n", buf);
+        else printf("preconditioner        : %s\n", buf);
     }
     switch (conv_cond) {
     case LIS_CONV_COND_NRM2_R:
