@@ -280,6 +280,15 @@ int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_order, const in
                        const double *d_wd, const double *d_in, double *d_out, double *d_slot_scratch,
                        unsigned int *d_ticket, int ctas_per_sm, void *stream);
 
+/* The same sweep for factors with LONG rows (tens of kept entries per row): a warp per row.  The factor is given as
+ * CSR by slot -- entries of slot k at [d_rptr[k], d_rptr[k+1]) of d_ridx (neighbour slots) / d_rval, in the order the row
+ * sum must run -- with d_rdep[k] the row's neighbour latest in slot order (-1: none).  All neighbours of a row are polled
+ * at once; the products are then added in storage order (lane by lane): the bits of lisb200_sweep_sell and of the
+ * reference loops.  Modes, scratch and ticket as there; nslots need not be padded to warps. */
+int lisb200_sweep_rows(int mode, int n, int nslots, const int *d_order, const int *d_rptr, const int *d_rdep,
+                       const int *d_ridx, const double *d_rval, const double *d_wd, const double *d_in,
+                       double *d_out, double *d_slot_scratch, unsigned int *d_ticket, int ctas_per_sm, void *stream);
+
 /* ---- halo pack (row-partitioned SpMV)                   src/matrix/lis_matrix_mpi.c:905-951 */
 /* d_ws[i] = d_x[d_export_index[i]] */
 int lisb200_gather(int count, const int *d_index, const double *d_x, double *d_out, void *stream);

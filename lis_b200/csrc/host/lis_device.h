@@ -139,6 +139,8 @@ void    lisd_sweep_free(void *sweep);
 typedef struct lisd_perm {        /* rows in dependency-level order + the factor as SELL-32 slices in that order */
     int nslots;                   /* levels concatenated, each padded to a multiple of 32 */
     int short_rows;               /* no row keeps more than 4 entries: the narrow-batch kernel instantiation */
+    int row_warp;                 /* long rows: CSR by slot (d_rptr, d_rdep, d_sidx, d_sval), a warp per row */
+    int *d_rptr, *d_rdep;         /* row_warp: entries of slot k at [rptr[k], rptr[k+1]); its neighbour latest in slot order */
     int *d_order;                 /* slot -> row (or -1) */
     int *d_wptr;                  /* per warp of 32 slots: start of its slice (nslots/32 + 1 entries) */
     int *d_plen;                  /* per slot: kept entries of the row */

@@ -470,6 +470,7 @@ void lisd_perm_free(lisd_perm *p)
 {
     lisd_free(p->d_order); lisd_free(p->d_wptr); lisd_free(p->d_plen); lisd_free(p->d_wdep); lisd_free(p->d_sidx); lisd_free(p->d_sval);
     lisd_free(p->d_slots);
+    lisd_free(p->d_rptr); lisd_free(p->d_rdep);
     memset(p, 0, sizeof(*p));
 }
 
@@ -537,6 +538,51 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         sval = (double *)malloc(sizeof(double) * (total ? total : 1));
         if (!sidx || !sval) { LIS_SETERR_MEM(total * 12); goto done; }
     }
+    /* long rows (tens of kept entries: the banded matrix of config 4, ILU factors with fill): a warp per row on a
+     * CSR-by-slot copy instead of SELL slices and a thread per row (kernels/sweep.cu sweep_rowwarp_kernel) */
+    {
+        size_t kept = 0, nrows = 0;
+        for (size_t k = 0; k < nslots; k++) if (order[k] >= 0) { kept += (size_t)plen[k]; nrows++; }
+        const char *force = getenv("LIS_B200_SWEEP_KERNEL");
+        const int want = force ? strcmp(force, "rows") == 0 : (nrows > 0 && kept >= 12 * nrows);
+        if (want && kept <= 0x7fffff00u) {
+            int *rptr = (int *)malloc(sizeof(int) * (nslots + 1)), *rdep = (int *)malloc(sizeof(int) * (nslots ? nslots : 1));
+            int *ridx = (int *)malloc(sizeof(int) * (kept ? kept : 1));
+            double *rval = (double *)malloc(sizeof(double) * (kept ? kept : 1));
+            err = LIS_OUT_OF_MEMORY;
+            if (rptr && rdep && ridx && rval) {
+                size_t q = 0;
+                for (size_t k = 0; k < nslots; k++) {
+                    const int i = order[k];
+                    int latest = -1;
+                    rptr[k] = (int)q;
+                    if (i >= 0)
+                        for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++) {
+                            const int jj = idx[j];
+                            if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
+                            ridx[q] = slot_of[jj]; rval[q] = val[j]; q++;
+                            if (slot_of[jj] > latest) latest = slot_of[jj];
+                        }
+                    rdep[k] = latest;
+                }
+                rptr[nslots] = (int)q;
+                P->nslots = (int)nslots; P->row_warp = 1; P->short_rows = 0;
+                err = lisd_malloc((void **)&P->d_order, sizeof(int) * (nslots ? nslots : 1));
+                if (!err) err = lisd_upload(P->d_order, order, sizeof(int) * nslots);
+                if (!err) err = lisd_malloc((void **)&P->d_rptr, sizeof(int) * (nslots + 1));
+                if (!err) err = lisd_upload(P->d_rptr, rptr, sizeof(int) * (nslots + 1));
+                if (!err) err = lisd_malloc((void **)&P->d_rdep, sizeof(int) * (nslots ? nslots : 1));
+                if (!err) err = lisd_upload(P->d_rdep, rdep, sizeof(int) * nslots);
+                if (!err) err = lisd_malloc((void **)&P->d_sidx, sizeof(int) * (kept ? kept : 1));
+                if (!err) err = lisd_upload(P->d_sidx, ridx, sizeof(int) * kept);
+                if (!err) err = lisd_malloc((void **)&P->d_sval, sizeof(double) * (kept ? kept : 1));
+                if (!err) err = lisd_upload(P->d_sval, rval, sizeof(double) * kept);
+                if (!err) err = lisd_malloc((void **)&P->d_slots, sizeof(double) * 2 * (nslots ? nslots : 1));
+            } else LIS_SETERR_MEM(kept * 12);
+            free(rptr); free(rdep); free(ridx); free(rval);
+            goto done;
+        }
+    }
     /* pass 2: fill the slices; unused positions point at the row itself with a zero (never read) */
     for (size_t w = 0; w < nw; w++) {
         const int width = (wptr[w + 1] - wptr[w]) / 32;
@@ -584,6 +630,9 @@ int lisd_sweep_ctas(void);
 /* one sweep on a prepared factor; mode as in lisb200_sweep_sell; async on the library stream */
 int lisd_perm_sweep(const lisd_perm *P, int mode, int n, const double *d_wd, const double *d_in, double *d_out, unsigned int *d_ticket)
 {
+    if (P->row_warp)
+        return lisb200_sweep_rows(mode, n, P->nslots, P->d_order, P->d_rptr, P->d_rdep, P->d_sidx, P->d_sval,
+                                  d_wd, d_in, d_out, P->d_slots, d_ticket, lisd_sweep_ctas(), lisd_stream());
     return lisb200_sweep_sell(mode, n, P->nslots, P->d_order, P->d_wptr, P->d_plen, P->d_wdep, P->d_sidx, P->d_sval,
                               d_wd, d_in, d_out, P->d_slots, d_ticket, lisd_sweep_ctas() | (P->short_rows ? 0x100 : 0), lisd_stream());
 }

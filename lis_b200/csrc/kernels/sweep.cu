@@ -221,6 +221,77 @@ sweep_sell_kernel(int nslots, const int *__restrict__ order, const int *__restri
     }
 }
 
+// ---- long rows: a WARP per row ------------------------------------------------------------------
+// With tens of kept entries per row (the 70-per-row banded matrix of BASELINE config 4, ILU factors with
+// fill) a thread per row needs several poll batches one after the other, and a level holds only a few
+// thousand rows.  Here the 32 lanes of a warp hold the row's entries (the factor stays in CSR order by
+// slot: coalesced), all neighbours are polled at once, and the products are then added in STORAGE order
+// by walking the lanes with shuffles -- the same sequence of rounded operations as the thread-per-row
+// kernel and the reference loop.  A CTA takes tickets of 32 slots, its 4 warps take every fourth slot.
+constexpr int kRowWarpSlots = 32;
+
+template <int kMode>
+__global__ void __launch_bounds__(kSweepThreads, 8)
+sweep_rowwarp_kernel(int nslots, const int *__restrict__ order, const int *__restrict__ rptr, const int *__restrict__ rdep,
+                     const int *__restrict__ ridx, const double *__restrict__ rval,
+                     const double *__restrict__ wd, const double *__restrict__ wds,
+                     const double *__restrict__ in, double *__restrict__ out, double *pout, unsigned int *ticket)
+{
+    __shared__ unsigned int vblock[2];
+    constexpr bool kSub = kMode != kSweepBwd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) vblock[0] = atomicAdd(ticket, 1u);
+    __syncthreads();
+    for (int round = 0;; round ^= 1) {
+        const long long k0 = (long long)vblock[round] * kRowWarpSlots;
+        if (k0 >= nslots) break;
+        unsigned int next_ticket = 0;
+        if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
+        for (int k = (int)k0 + warp; k < (int)k0 + kRowWarpSlots && k < nslots; k += kSweepThreads / 32) {
+            const int i = order[k];
+            if (i < 0) continue;                                   // padding slot (uniform in the warp)
+            const int s = rptr[k], e = rptr[k + 1], dep = rdep[k];
+            const double inv = in[i];
+            const double wdv = (kMode == kSweepFwd || kMode == kSweepBwd) ? wd[i] : 0.0;
+            double t = kSub ? inv : 0.0;
+            bool waited = false;
+            for (int c = s; c < e; c += 64) {                      // two entries per lane per chunk
+                const int j0 = c + lane, j1 = c + 32 + lane;
+                const bool u0 = j0 < e, u1 = j1 < e;
+                const int d0 = u0 ? ridx[j0] : 0, d1 = u1 ? ridx[j1] : 0;
+                const double v0 = u0 ? rval[j0] : 0.0, v1 = u1 ? rval[j1] : 0.0;
+                double x0 = 0.0, x1 = 0.0;
+                bool p0 = u0, p1 = u1;
+                for (;;) {
+                    const unsigned long long b0 = p0 ? ld_poll(pout + d0) : kNotReady, b1 = p1 ? ld_poll(pout + d1) : kNotReady;
+                    if (p0 && b0 != kNotReady) { x0 = __longlong_as_double((long long)b0); p0 = false; }
+                    if (p1 && b1 != kNotReady) { x1 = __longlong_as_double((long long)b1); p1 = false; }
+                    if (!__any_sync(0xffffffffu, p0 || p1)) break;
+                    if (!waited) {
+                        // the whole warp waits on ONE address: the row's neighbour latest in slot order
+                        waited = true;
+                        if (dep >= 0) while (ld_poll(pout + dep) == kNotReady) { }
+                    }
+                }
+                if (kMode == kSweepReadScaled) { if (u0) x0 = mul(x0, wds[d0]); if (u1) x1 = mul(x1, wds[d1]); }
+                const double q0 = mul(v0, x0), q1 = mul(v1, x1);
+                const int cnt = min(64, e - c);
+                for (int q = 0; q < cnt; ++q) {                    // storage order: lane q of the first half, then the second
+                    const double pq = __shfl_sync(0xffffffffu, q < 32 ? q0 : q1, q & 31);
+                    t = kSub ? sub(t, pq) : add(t, pq);
+                }
+            }
+            if (lane == 0) {
+                const double r = kMode == kSweepFwd ? mul(t, wdv) : kMode == kSweepBwd ? sub(inv, mul(t, wdv)) : t;
+                st_publish(pout + k, r);
+                out[i] = r;
+            }
+        }
+        if (threadIdx.x == 0) vblock[round ^ 1] = next_ticket;
+        __syncthreads();
+    }
+}
+
 /* slot-ordered copy of a row-ordered vector (wd for the read-scaled mode) */
 __global__ void __launch_bounds__(256)
 gather_slots_kernel(int nslots, const int *__restrict__ order, const double *__restrict__ src, double *__restrict__ dst)
@@ -277,6 +348,40 @@ extern "C" int lisb200_sweep_sell(int mode, int n, int nslots, const int *d_orde
         }
     }
 #undef LISB_SWEEP_LAUNCH
+    LISB_CHECK_LAUNCH();
+    return 0;
+}
+
+/* the same sweep for factors with long rows: a warp per row; see include/lis_b200_kernels.h */
+extern "C" int lisb200_sweep_rows(int mode, int n, int nslots, const int *d_order, const int *d_rptr, const int *d_rdep,
+                                  const int *d_ridx, const double *d_rval, const double *d_wd, const double *d_in,
+                                  double *d_out, double *d_slot_scratch, unsigned int *d_ticket, int ctas_per_sm, void *stream)
+{
+    if (nslots <= 0 || n <= 0) return 0;
+    if (mode < 0 || mode > 3 || (mode != kSweepPlain && d_wd == nullptr) || d_slot_scratch == nullptr) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    double *pout = d_slot_scratch, *wds = d_slot_scratch + nslots;
+    int fill_grid = (nslots + 255) / 256;
+    if (fill_grid > sms * 8) fill_grid = sms * 8;
+    fill_not_ready_kernel<<<fill_grid, 256, 0, st>>>(nslots, pout);
+    if (mode == kSweepReadScaled) gather_slots_kernel<<<(nslots + 255) / 256, 256, 0, st>>>(nslots, d_order, d_wd, wds);
+    ctas_per_sm &= 0xff;
+    if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
+    int grid = (nslots + kRowWarpSlots - 1) / kRowWarpSlots;
+    if (grid > sms * ctas_per_sm) grid = sms * ctas_per_sm;
+    switch (mode) {
+    case kSweepFwd: sweep_rowwarp_kernel<kSweepFwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_rptr, d_rdep, d_ridx, d_rval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    case kSweepPlain: sweep_rowwarp_kernel<kSweepPlain><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_rptr, d_rdep, d_ridx, d_rval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    case kSweepReadScaled: sweep_rowwarp_kernel<kSweepReadScaled><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_rptr, d_rdep, d_ridx, d_rval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    default: sweep_rowwarp_kernel<kSweepBwd><<<grid, kSweepThreads, 0, st>>>(nslots, d_order, d_rptr, d_rdep, d_ridx, d_rval, d_wd, wds, d_in, d_out, pout, d_ticket); break;
+    }
     LISB_CHECK_LAUNCH();
     return 0;
 }

@@ -115,6 +115,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     for (int l = 0; l < 32; ++l) r |= (emu_shfl<int>(pred ? 1 : 0, l) ? 1u : 0u) << l;
     return r;
 }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }

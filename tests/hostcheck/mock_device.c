@@ -255,6 +255,26 @@ int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int 
     return 0;
 }
 
+int lisb200_sweep_rows(int mode, int n, int nslots, const int *order, const int *rptr, const int *rdep, const int *ridx, const double *rval,
+                       const double *wd, const double *in, double *out, double *scratch, unsigned int *ticket, int ctas, void *s)
+{
+    (void)ticket; (void)s; (void)ctas; (void)rdep;
+    double *pout = scratch;
+    for (int i = 0; i < n; i++) out[i] = NAN;
+    for (int k = 0; k < nslots; k++) pout[k] = NAN;
+    for (int k = 0; k < nslots; k++) {
+        const int i = order[k];
+        if (i < 0) continue;
+        double t = mode == 3 ? 0.0 : in[i];
+        for (int j = rptr[k]; j < rptr[k + 1]; j++) {
+            const int ks = ridx[j];
+            const double xv = mode == 2 ? pout[ks] * wd[order[ks]] : pout[ks];
+            if (mode == 3) t += rval[j] * xv; else t -= rval[j] * xv;
+        }
+        pout[k] = out[i] = mode == 0 ? t * wd[i] : mode == 3 ? in[i] - t * wd[i] : t;
+    }
+    return 0;
+}
 int lisb200_spmv_csr_tma_p2p(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y, int dot,
                              double *part, unsigned int *cnt, double *res, const lisb200_p2p *tb, unsigned long long ep, int lo, int hi, void *s)
 { (void)n; (void)r; (void)t; (void)st; (void)p; (void)i; (void)v; (void)x; (void)y; (void)dot; (void)part; (void)cnt; (void)res; (void)tb; (void)ep; (void)lo; (void)hi; (void)s;
