@@ -428,8 +428,11 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
             lib.lis_b200_set_overlap(0)
     # the halo exchange inside the SpMV kernel over peer memory (CUDA IPC + NVLink; the library's default where every
     # rank can map its neighbours): must reproduce the bits of the NCCL path on every rank, then both are timed
-    p2p_note = "not available (a GPU hidden from a rank, no peer access, or LIS_B200_P2P=0): NCCL send/recv"
+    p2p_note = "not tried (opt-in: --p2p / LIS_B200_P2P=1; enabling peer access slows every kernel of the process by ~20 %, DESIGN.md section 6): NCCL send/recv"
     try:
+        if not (args.p2p or os.environ.get("LIS_B200_P2P") == "1"):
+            raise StopIteration
+        p2p_note = "not available (a GPU hidden from a rank or no peer access): NCCL send/recv"
         lib.lis_b200_set_p2p(0)
         y_ref = torch.empty(n, dtype=torch.float64); y_p2p = torch.empty(n, dtype=torch.float64)
         assert Ls.shim_mv_matvec(h) == 0 and Ls.shim_mv_get_y_local(h, y_ref.data_ptr()) == 0
@@ -457,6 +460,8 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
             lib.lis_b200_set_p2p(0)
             if int(used.item()):
                 p2p_note = "off: the in-kernel exchange did not reproduce the bits"
+    except StopIteration:
+        pass
     except Exception as e:
         lib.lis_b200_set_p2p(0)
         p2p_note = f"off: {e!r}"
@@ -948,6 +953,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=0, help="edge of the CPU sample (0 = the workload's own grid)")
     ap.add_argument("--cg-iters", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--p2p", action="store_true", help="N>1: also time the halo exchange inside the kernel over peer memory")
     ap.add_argument("--no-cg-converge", action="store_true", help="skip the CG-to-1e-12 solve of BASELINE config 3")
     ap.add_argument("--no-format-extras", action="store_true", help="skip the ELL/DIA/JAD/BSR convert + lis_matvec extras")
     ap.add_argument("--watchdog", type=float, default=420.0, help="seconds the optional legs may take before the line is emitted without them")

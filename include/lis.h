@@ -642,7 +642,8 @@ LIS_INT lis_b200_set_overlap(LIS_INT on);
 /* partial scalars of dot/nrm2 across ranks: 0 = host control plane (default), 1 = ncclAllGather over NVLink */
 LIS_INT lis_b200_set_reduce(LIS_INT nccl);
 /* row-partitioned CSR products exchange their halo inside the SpMV kernel over peer memory (CUDA IPC + NVLink)
- * where every rank can map its neighbours' GPUs: 1 (default) use it, 0 always the NCCL send/recv exchange.
+ * where every rank can map its neighbours' GPUs: 1 use it, 0 (default; LIS_B200_P2P=1 turns it on) the NCCL send/recv
+ * exchange -- enabling peer access slows every other kernel of the process, see host/lis_comm.c.
  * Returns the old setting; call on every rank alike. */
 LIS_INT lis_b200_set_p2p(LIS_INT on);
 unsigned long long lis_b200_p2p_products(void);   /* products so far that took that path (diagnostics) */

@@ -756,11 +756,22 @@ LIS_INT lis_reduce(LIS_COMMTABLE commtable, LIS_SCALAR x[])
  * travel through the shm control plane), the neighbours' blocks mapped with cudaIpcOpenMemHandle, and the
  * table of addresses in device memory.  Anything missing -- a GPU hidden by CUDA_VISIBLE_DEVICES, no peer
  * access, an unsymmetric neighbour relation, LIS_B200_P2P=0 -- leaves the NCCL exchange in place. */
-static struct { int probed, ok, enabled; int *h_error, *d_error; } gp = { .enabled = 1 };
+static struct { int probed, ok, enabled; int *h_error, *d_error; } gp = { .enabled = -1 };
 
-/* 1: use the in-kernel exchange where it is available (default), 0: NCCL send/recv.  Returns the old setting.
+/* Measured on 2 B200s (profiles/r02_session11.sh): once a process has called cudaDeviceEnablePeerAccess -- which the
+ * legacy CUDA IPC route needs -- EVERY kernel of that process reading cudaMalloc memory slows down: the 512^3 CSR product
+ * takes 2.49 ms instead of 2.10 ms, whatever exchange is used.  NCCL's own NVLink transport (cuMem-based) has no such
+ * effect.  The in-kernel exchange is therefore opt-in (LIS_B200_P2P=1 / lis_b200_set_p2p(1)) until its inbox is mapped
+ * through the virtual-memory API alone. */
+static int p2p_enabled(void)
+{
+    if (gp.enabled < 0) { const char *e = getenv("LIS_B200_P2P"); gp.enabled = (e && e[0] == '1') ? 1 : 0; }
+    return gp.enabled;
+}
+
+/* 1: use the in-kernel exchange where it is available, 0 (default, see above): NCCL send/recv.  Returns the old setting.
  * Call on every rank alike. */
-LIS_INT lis_b200_set_p2p(LIS_INT on) { const int old = gp.enabled; gp.enabled = on ? 1 : 0; return old; }
+LIS_INT lis_b200_set_p2p(LIS_INT on) { const int old = p2p_enabled(); gp.enabled = on ? 1 : 0; return old; }
 
 static int all_agree(int mine)
 {
@@ -773,8 +784,7 @@ static int all_agree(int mine)
 static void p2p_probe(void)              /* collective */
 {
     gp.probed = 1; gp.ok = 0;
-    const char *e = getenv("LIS_B200_P2P");
-    int want = g.nccl_ok && lisd_available() && !(e && e[0] == '0');
+    int want = g.nccl_ok && lisd_available();
     char bus[32], all[LISC_MAXR][32];
     memset(bus, 0, sizeof(bus));
     if (want && cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), lisd_device_id()) != cudaSuccess) { cudaGetLastError(); want = 0; }
@@ -880,7 +890,7 @@ unsigned long long lis_b200_p2p_products(void) { return g_p2p_products; }
 const lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, int local_ok, unsigned long long *epoch)
 {
     LIS_COMMTABLE t = A->commtable;
-    if (t == NULL || g.nranks == 1 || !gp.enabled) return NULL;
+    if (t == NULL || g.nranks == 1 || !p2p_enabled()) return NULL;
     if (t->p2p == 0) p2p_prepare(t, local_ok);
     if (t->p2p != 1) return NULL;
     *epoch = ++t->p2p_epoch;
