@@ -362,6 +362,7 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
     hx.uniform_(-1, 1)
     assert Ls.shim_mv_set_x_local(h, hx.data_ptr()) == 0
     stream = torch.cuda.ExternalStream(lib.lis_b200_stream(), device=dev)
+    lib.lis_b200_set_p2p(0)          # the NCCL orders are timed before the neighbours' inboxes are ever mapped
     # interior rows overlap the halo exchange on a second stream (default): keep it only if every rank
     # gets the bits of the exchange-then-product order
     overlap_note = "interior rows on a second stream during the exchange (bits checked against exchange-then-product)"
@@ -428,12 +429,11 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
             lib.lis_b200_set_overlap(0)
     # the halo exchange inside the SpMV kernel over peer memory (CUDA IPC + NVLink; the library's default where every
     # rank can map its neighbours): must reproduce the bits of the NCCL path on every rank, then both are timed
-    p2p_note = "not tried (opt-in: --p2p / LIS_B200_P2P=1; enabling peer access slows every kernel of the process by ~20 %, DESIGN.md section 6): NCCL send/recv"
+    p2p_note = "not tried (--no-p2p)"
     try:
-        if not (args.p2p or os.environ.get("LIS_B200_P2P") == "1"):
+        if args.no_p2p:
             raise StopIteration
-        p2p_note = "not available (a GPU hidden from a rank or no peer access): NCCL send/recv"
-        lib.lis_b200_set_p2p(0)
+        p2p_note = "not available (a GPU hidden from a rank, no peer access between the GPUs, or LIS_B200_P2P=0): NCCL send/recv"
         y_ref = torch.empty(n, dtype=torch.float64); y_p2p = torch.empty(n, dtype=torch.float64)
         assert Ls.shim_mv_matvec(h) == 0 and Ls.shim_mv_get_y_local(h, y_ref.data_ptr()) == 0
         lib.lis_b200_set_p2p(1)
@@ -450,15 +450,24 @@ def run_b200_multi(args, grid, torch, dist, lis_b200, shim, dev, rank, world, lo
             s3, per3, ck3 = time_products(True)
             log(f"[rank {rank}] halo exchange inside the kernel (peer memory): {s3 * 1e3:.3f} ms/product; this rank min {per3[0]:.3f} median {per3[len(per3) // 2]:.3f} max {per3[-1]:.3f}")
             step_modes["in_kernel_exchange_ms"] = s3 * 1e3
+            # does the mapping itself cost the other kernels anything?  (cudaDeviceEnablePeerAccess did: +20 %)
+            lib.lis_b200_set_p2p(0)
+            lib.lis_b200_set_overlap(0)
+            s4, _, _ = time_products(False)
+            lib.lis_b200_set_overlap(1 if overlap_ok else 0)
+            step_modes["exchange_then_product_ms_with_inboxes_mapped"] = s4 * 1e3
+            log(f"[rank {rank}] exchange then product again, neighbours' inboxes still mapped: {s4 * 1e3:.3f} ms/product")
             if s3 <= step_s:
+                lib.lis_b200_set_p2p(1)
                 step_s, per, clocks = s3, per3, ck3
                 p2p_note = "on: pushes into the neighbours' inboxes, flags, interior rows first, halo columns from the inbox -- one launch per product; same bits as the NCCL path (checked)"
             else:
-                lib.lis_b200_set_p2p(0)
-                p2p_note = f"off: slower here ({s3 * 1e3:.3f} ms vs {step_s * 1e3:.3f} ms); bits equal"
+                Ls.shim_mv_p2p_release(h)
+                p2p_note = f"off: slower here ({s3 * 1e3:.3f} ms vs {step_s * 1e3:.3f} ms); bits equal; inboxes unmapped again"
         else:
             lib.lis_b200_set_p2p(0)
             if int(used.item()):
+                Ls.shim_mv_p2p_release(h)
                 p2p_note = "off: the in-kernel exchange did not reproduce the bits"
     except StopIteration:
         pass
@@ -953,7 +962,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=0, help="edge of the CPU sample (0 = the workload's own grid)")
     ap.add_argument("--cg-iters", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--p2p", action="store_true", help="N>1: also time the halo exchange inside the kernel over peer memory")
+    ap.add_argument("--no-p2p", action="store_true", help="N>1: do not try the halo exchange inside the kernel over peer memory")
     ap.add_argument("--no-cg-converge", action="store_true", help="skip the CG-to-1e-12 solve of BASELINE config 3")
     ap.add_argument("--no-format-extras", action="store_true", help="skip the ELL/DIA/JAD/BSR convert + lis_matvec extras")
     ap.add_argument("--watchdog", type=float, default=420.0, help="seconds the optional legs may take before the line is emitted without them")

@@ -642,11 +642,12 @@ LIS_INT lis_b200_set_overlap(LIS_INT on);
 /* partial scalars of dot/nrm2 across ranks: 0 = host control plane (default), 1 = ncclAllGather over NVLink */
 LIS_INT lis_b200_set_reduce(LIS_INT nccl);
 /* row-partitioned CSR products exchange their halo inside the SpMV kernel over peer memory (CUDA IPC + NVLink)
- * where every rank can map its neighbours' GPUs: 1 use it, 0 (default; LIS_B200_P2P=1 turns it on) the NCCL send/recv
- * exchange -- enabling peer access slows every other kernel of the process, see host/lis_comm.c.
+ * where every rank can map its neighbours' inbox (virtual-memory API, host/lis_peer.c): 1 (default) use it, 0 the NCCL
+ * send/recv exchange (also LIS_B200_P2P=0).
  * Returns the old setting; call on every rank alike. */
 LIS_INT lis_b200_set_p2p(LIS_INT on);
-unsigned long long lis_b200_p2p_products(void);   /* products so far that took that path (diagnostics) */
+unsigned long long lis_b200_p2p_products(void);
+LIS_INT lis_b200_p2p_release(LIS_MATRIX A);        /* unmap the neighbours' inboxes of A's communication table (collective) */   /* products so far that took that path (diagnostics) */
 /* lis_matvec enqueued on the library stream without waiting for it; lis_b200_sync (or any host-synchronous call) waits */
 LIS_INT lis_b200_matvec_async(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y);
 LIS_INT lis_b200_sync(void);

@@ -453,11 +453,24 @@ struct LIS_COMMTABLE_STRUCT {
     /* in-kernel halo exchange over peer memory (p2p_prepare): 0 not looked at yet, 1 ready, -1 not available */
     int p2p;
     unsigned long long p2p_epoch;             /* products done through the table */
-    double *p2p_inbox;                        /* [2][stride] doubles + [2][LISB200_P2P_MAX] flags, exported through CUDA IPC */
+    double *p2p_inbox;                        /* [2][stride] doubles + [2][LISB200_P2P_MAX] flags: one exportable block (host/lis_peer.c) */
+    size_t p2p_bytes; int p2p_fd; unsigned long long p2p_handle;
     void *p2p_peer_base[LISC_MAXR];           /* neighbours' inboxes mapped into this process */
+    size_t p2p_peer_bytes[LISC_MAXR];
     unsigned int *p2p_push_count;
     lisb200_p2p *d_p2p;                       /* the kernel's table, device */
 };
+
+static void p2p_release(LIS_COMMTABLE t)
+{
+    for (int k = 0; k < LISC_MAXR; k++)
+        if (t->p2p_peer_base[k]) { lisd_peer_unmap(t->p2p_peer_base[k], t->p2p_peer_bytes[k]); t->p2p_peer_base[k] = NULL; }
+    if (t->p2p_inbox) lisd_peer_free(t->p2p_inbox, t->p2p_bytes, t->p2p_fd, t->p2p_handle);
+    if (t->p2p_push_count) cudaFree(t->p2p_push_count);
+    if (t->d_p2p) cudaFree(t->d_p2p);
+    t->p2p_inbox = NULL; t->p2p_push_count = NULL; t->d_p2p = NULL; t->p2p_fd = -1;
+    cudaGetLastError();
+}
 
 void lisd_commtable_destroy(LIS_COMMTABLE t)
 {
@@ -467,12 +480,7 @@ void lisd_commtable_destroy(LIS_COMMTABLE t)
     lisd_free(t->d_ws);
     lisd_free(t->d_wr);
     free(t->peer_export_ptr); free(t->peer_n_export); free(t->h_stage);
-    if (t->p2p == 1) {
-        lisd_sync();
-        for (int k = 0; k < LISC_MAXR; k++) if (t->p2p_peer_base[k]) cudaIpcCloseMemHandle(t->p2p_peer_base[k]);
-        cudaFree(t->p2p_inbox); cudaFree(t->p2p_push_count); cudaFree(t->d_p2p);
-        cudaGetLastError();
-    }
+    if (t->p2p == 1) { lisd_sync(); p2p_release(t); }
     free(t);
 }
 
@@ -553,7 +561,7 @@ LIS_INT lisd_commtable_duplicate(LIS_MATRIX Ain, LIS_MATRIX Aout)
     memcpy(t, s, sizeof(*t));
     t->d_export_index = NULL; t->d_ws = NULL; t->d_wr = NULL;
     t->h_stage = NULL; t->h_stage_len = 0;
-    t->p2p = 0; t->p2p_epoch = 0; t->p2p_inbox = NULL; t->p2p_push_count = NULL; t->d_p2p = NULL;
+    t->p2p = 0; t->p2p_epoch = 0; t->p2p_inbox = NULL; t->p2p_push_count = NULL; t->d_p2p = NULL; t->p2p_fd = -1;
     memset(t->p2p_peer_base, 0, sizeof(t->p2p_peer_base));
     t->peer_export_ptr = (int *)malloc(sizeof(int) * (size_t)s->nranks * (size_t)(s->nranks + 1));
     t->peer_n_export = (int *)malloc(sizeof(int) * (size_t)s->nranks);
@@ -756,20 +764,21 @@ LIS_INT lis_reduce(LIS_COMMTABLE commtable, LIS_SCALAR x[])
  * travel through the shm control plane), the neighbours' blocks mapped with cudaIpcOpenMemHandle, and the
  * table of addresses in device memory.  Anything missing -- a GPU hidden by CUDA_VISIBLE_DEVICES, no peer
  * access, an unsymmetric neighbour relation, LIS_B200_P2P=0 -- leaves the NCCL exchange in place. */
-static struct { int probed, ok, enabled; int *h_error, *d_error; } gp = { .enabled = -1 };
+static struct { int probed, ok, enabled; int *h_error, *d_error; int peer_dev[LISC_MAXR]; } gp = { .enabled = -1 };
 
-/* Measured on 2 B200s (profiles/r02_session11.sh): once a process has called cudaDeviceEnablePeerAccess -- which the
- * legacy CUDA IPC route needs -- EVERY kernel of that process reading cudaMalloc memory slows down: the 512^3 CSR product
- * takes 2.49 ms instead of 2.10 ms, whatever exchange is used.  NCCL's own NVLink transport (cuMem-based) has no such
- * effect.  The in-kernel exchange is therefore opt-in (LIS_B200_P2P=1 / lis_b200_set_p2p(1)) until its inbox is mapped
- * through the virtual-memory API alone. */
+/* History (profiles/r02_session11.sh, 2 B200s): the first version mapped the inboxes with cudaIpcOpenMemHandle, which needs
+ * cudaDeviceEnablePeerAccess -- and once a process has made that call EVERY kernel of it that reads cudaMalloc memory slows
+ * down: the 512^3 CSR product took 2.49 ms instead of 2.10 ms whatever exchange was used.  The inbox is now one
+ * virtual-memory-API allocation (host/lis_peer.c: cuMemCreate + POSIX-fd handle, imported and mapped by the neighbours):
+ * nothing else becomes peer-accessible, as with NCCL's own buffers.  LIS_B200_P2P=0 / lis_b200_set_p2p(0) select the NCCL
+ * exchange. */
 static int p2p_enabled(void)
 {
-    if (gp.enabled < 0) { const char *e = getenv("LIS_B200_P2P"); gp.enabled = (e && e[0] == '1') ? 1 : 0; }
+    if (gp.enabled < 0) { const char *e = getenv("LIS_B200_P2P"); gp.enabled = (e && e[0] == '0') ? 0 : 1; }
     return gp.enabled;
 }
 
-/* 1: use the in-kernel exchange where it is available, 0 (default, see above): NCCL send/recv.  Returns the old setting.
+/* 1 (default): use the in-kernel exchange where it is available, 0: NCCL send/recv.  Returns the old setting.
  * Call on every rank alike. */
 LIS_INT lis_b200_set_p2p(LIS_INT on) { const int old = p2p_enabled(); gp.enabled = on ? 1 : 0; return old; }
 
@@ -784,21 +793,19 @@ static int all_agree(int mine)
 static void p2p_probe(void)              /* collective */
 {
     gp.probed = 1; gp.ok = 0;
-    int want = g.nccl_ok && lisd_available();
+    int want = g.nccl_ok && lisd_peer_available();
     char bus[32], all[LISC_MAXR][32];
     memset(bus, 0, sizeof(bus));
     if (want && cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), lisd_device_id()) != cudaSuccess) { cudaGetLastError(); want = 0; }
     if (shm_allgather(bus, sizeof(bus), all)) return;
     int ok = want;
     for (int k = 0; k < g.nranks && ok; k++) {
-        int dev = -1, can = 0;
+        int dev = -1;
+        gp.peer_dev[k] = -1;
         if (k == g.rank) continue;
-        if (all[k][0] == 0 || cudaDeviceGetByPCIBusId(&dev, all[k]) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-        if (dev == lisd_device_id()) { ok = 0; break; }                       /* two ranks on one GPU */
-        if (cudaDeviceCanAccessPeer(&can, lisd_device_id(), dev) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
-        const cudaError_t pe = cudaDeviceEnablePeerAccess(dev, 0);
-        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
-        cudaGetLastError();
+        if (all[k][0] == 0 || cudaDeviceGetByPCIBusId(&dev, all[k]) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }   /* hidden from this rank */
+        if (dev == lisd_device_id() || !lisd_peer_can_access(dev)) { ok = 0; break; }
+        gp.peer_dev[k] = dev;
     }
     if (ok && (cudaHostAlloc((void **)&gp.h_error, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
                cudaHostGetDevicePointer((void **)&gp.d_error, gp.h_error, 0) != cudaSuccess)) { cudaGetLastError(); ok = 0; }
@@ -810,7 +817,7 @@ static void p2p_probe(void)              /* collective */
 
 int lisd_p2p_error(void) { return gp.h_error && *(volatile int *)gp.h_error; }
 
-typedef struct { cudaIpcMemHandle_t handle; long long stride; int ok; } p2p_msg;
+typedef struct { long long stride; unsigned long long bytes; int ok; } p2p_msg;
 
 /* collective: every rank comes here at its first CSR product on the table; local_ok: this rank's matrix takes the
  * TMA row-block kernel (the plan depends on the local row lengths, so the ranks must agree before any of them
@@ -818,42 +825,57 @@ typedef struct { cudaIpcMemHandle_t handle; long long stride; int ok; } p2p_msg;
 static void p2p_prepare(LIS_COMMTABLE t, int local_ok)
 {
     const int me = t->rank, np_ = t->nranks;
+    static unsigned serial = 0;
+    char job[128];
+    int sock = -1, got[LISC_MAXR];
     t->p2p = -1;
     if (!gp.probed) p2p_probe();
     int ok = gp.ok && local_ok, nn = 0;
     for (int k = 0; k < np_; k++) {
         const int ne = t->export_ptr[k + 1] - t->export_ptr[k], ni = t->import_ptr[k + 1] - t->import_ptr[k];
+        got[k] = 0;
         if (k == me) continue;
         if ((ne > 0) != (ni > 0)) ok = 0;                     /* the double-buffer argument needs mutual neighbours */
         if (ne > 0) nn++;
     }
     if (nn == 0 || nn > LISB200_P2P_MAX) ok = 0;
-    p2p_msg mine, all[LISC_MAXR];
-    memset(&mine, 0, sizeof(mine));
+    /* my inbox: one exportable block; a socket to receive the neighbours' descriptors on */
+    snprintf(job, sizeof(job), "%.80s-%u", g.name[0] ? g.name + 1 : "job", ++serial);
     const long long stride = ((long long)t->n_import + 15) & ~15LL;
     const size_t bytes = sizeof(double) * (size_t)(2 * stride) + sizeof(unsigned long long) * 2 * LISB200_P2P_MAX + 64;
+    void *inbox = NULL;
     if (ok) {
-        if (cudaMalloc((void **)&t->p2p_inbox, bytes) != cudaSuccess || cudaMemset(t->p2p_inbox, 0, bytes) != cudaSuccess ||
-            cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&mine.handle, t->p2p_inbox) != cudaSuccess) {
-            cudaGetLastError(); ok = 0;
+        if (!lisd_peer_alloc(bytes, &inbox, &t->p2p_bytes, &t->p2p_fd, &t->p2p_handle)) ok = 0;
+        else {
+            t->p2p_inbox = (double *)inbox;
+            if (cudaMemset(inbox, 0, t->p2p_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); ok = 0; }
         }
     }
-    mine.stride = stride; mine.ok = ok;
-    if (shm_allgather(&mine, sizeof(mine), all)) ok = 0;
+    if (ok) { sock = lisd_fd_socket(job, me); if (sock < 0) ok = 0; }
+    p2p_msg mine, all[LISC_MAXR];
+    memset(&mine, 0, sizeof(mine));
+    mine.stride = stride; mine.bytes = (unsigned long long)t->p2p_bytes; mine.ok = ok;
+    if (shm_allgather(&mine, sizeof(mine), all)) ok = 0;      /* also the barrier: every socket is bound */
     for (int k = 0; k < np_; k++) if (!all[k].ok) ok = 0;
-    if (ok)
-        for (int k = 0; k < np_; k++) {
-            if (k == me || t->export_ptr[k + 1] == t->export_ptr[k]) continue;
-            if (cudaIpcOpenMemHandle(&t->p2p_peer_base[k], all[k].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                cudaGetLastError(); t->p2p_peer_base[k] = NULL; ok = 0; break;
-            }
+    if (ok) {
+        for (int k = 0; k < np_ && ok; k++)
+            if (k != me && t->export_ptr[k + 1] > t->export_ptr[k] && !lisd_fd_send(sock, job, k, me, t->p2p_fd)) ok = 0;
+        for (int r = 0; r < nn && ok; r++) {
+            int from = -1, fd = -1;
+            if (!lisd_fd_recv(sock, &from, &fd, 60000) || from < 0 || from >= np_ || from == me || got[from]) { ok = 0; break; }
+            got[from] = 1;
+            if (!lisd_peer_import(fd, (size_t)all[from].bytes, &t->p2p_peer_base[from])) { t->p2p_peer_base[from] = NULL; ok = 0; }
+            else t->p2p_peer_bytes[from] = (size_t)all[from].bytes;
+            close(fd);
         }
+    }
     lisb200_p2p tb;
     memset(&tb, 0, sizeof(tb));
     if (ok) {
         int s = 0;
         for (int k = 0; k < np_; k++) {
             if (k == me || t->export_ptr[k + 1] == t->export_ptr[k]) continue;
+            if (!t->p2p_peer_base[k]) { ok = 0; break; }
             tb.exp_start[s] = t->export_ptr[k];
             tb.nbr_rank[s] = k;
             tb.peer_inbox[s] = (double *)t->p2p_peer_base[k] + peer_import_offset(t, k, me);
@@ -866,6 +888,8 @@ static void p2p_prepare(LIS_COMMTABLE t, int local_ok)
         tb.inbox = t->p2p_inbox; tb.inbox_stride = stride;
         tb.my_flag = (const unsigned long long *)(t->p2p_inbox + 2 * stride);
         tb.error = gp.d_error;
+    }
+    if (ok) {
         if (cudaMalloc((void **)&t->p2p_push_count, 64) != cudaSuccess || cudaMemset(t->p2p_push_count, 0, 64) != cudaSuccess ||
             cudaMalloc((void **)&t->d_p2p, sizeof(tb)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
         else {
@@ -873,13 +897,22 @@ static void p2p_prepare(LIS_COMMTABLE t, int local_ok)
             if (cudaMemcpy(t->d_p2p, &tb, sizeof(tb), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); ok = 0; }
         }
     }
-    if (all_agree(ok)) { t->p2p = 1; t->p2p_epoch = 0; return; }
-    for (int k = 0; k < np_; k++) if (t->p2p_peer_base[k]) { cudaIpcCloseMemHandle(t->p2p_peer_base[k]); t->p2p_peer_base[k] = NULL; }
-    if (t->p2p_inbox) cudaFree(t->p2p_inbox);
-    if (t->p2p_push_count) cudaFree(t->p2p_push_count);
-    if (t->d_p2p) cudaFree(t->d_p2p);
-    t->p2p_inbox = NULL; t->p2p_push_count = NULL; t->d_p2p = NULL;
-    cudaGetLastError();
+    const int agreed = all_agree(ok);                         /* also: nobody closes a socket somebody still sends to */
+    if (sock >= 0) close(sock);
+    if (agreed) { t->p2p = 1; t->p2p_epoch = 0; return; }
+    p2p_release(t);
+}
+
+/* undo p2p_prepare for A's communication table (collective; the next product with the exchange enabled sets it up again) */
+LIS_INT lis_b200_p2p_release(LIS_MATRIX A)
+{
+    LIS_COMMTABLE t = A ? A->commtable : NULL;
+    if (t == NULL) return LIS_SUCCESS;
+    LIS_INT err = lisd_sync();
+    if (t->p2p == 1) p2p_release(t);
+    t->p2p = 0;
+    all_agree(1);                                   /* nobody unmaps while a neighbour's kernel may still push */
+    return err;
 }
 
 static unsigned long long g_p2p_products = 0;

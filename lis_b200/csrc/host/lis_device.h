@@ -172,6 +172,17 @@ LIS_INT lisd_cg_update_jacobi(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_
                               LIS_REAL *nrm2_r, LIS_SCALAR *rho, int *fused_out);
 const struct lisb200_p2p *lisd_p2p_begin(LIS_MATRIX A, int local_ok, unsigned long long *epoch);   /* in-kernel halo exchange: table + epoch, or NULL */
 int     lisd_p2p_error(void);
+/* host/lis_peer.c: one block of device memory the neighbours' GPUs can store into (virtual-memory API, no peer access for
+ * anything else) and the descriptor hand-over between the processes of the node */
+int     lisd_peer_available(void);
+int     lisd_peer_can_access(int peer_dev);
+int     lisd_peer_alloc(size_t bytes, void **ptr, size_t *size, int *fd, unsigned long long *handle);
+int     lisd_peer_import(int fd, size_t size, void **ptr);
+void    lisd_peer_unmap(void *ptr, size_t size);
+void    lisd_peer_free(void *ptr, size_t size, int fd, unsigned long long handle);
+int     lisd_fd_socket(const char *job, int rank);
+int     lisd_fd_send(int sock, const char *job, int to_rank, int my_rank, int fd);
+int     lisd_fd_recv(int sock, int *from_rank, int *fd, int timeout_ms);
 LIS_INT lisd_halo_reduce_raw(LIS_MATRIX A, double *d_y);                                         /* y[n..np) back to the owners, added in rank order */
 LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy);        /* y=Ax; <x,y> */
 LIS_INT lisd_cg_update(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_VECTOR x, LIS_VECTOR r, LIS_REAL *nrm2_r);

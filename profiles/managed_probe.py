@@ -49,6 +49,14 @@ if world > 1:
     dist.all_reduce(t)
     torch.cuda.synchronize()
     managed("after torch NCCL all_reduce")
+    if os.environ.get("PROBE_PEER") == "1":
+        rt.cudaDeviceCanAccessPeer.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int]
+        errs = []
+        for peer in range(torch.cuda.device_count()):
+            if peer != local:
+                errs.append(rt.cudaDeviceEnablePeerAccess(peer, 0))
+        rt.cudaGetLastError()
+        managed(f"after cudaDeviceEnablePeerAccess to {len(errs)} peers (rc {sorted(set(errs))})")
     # the library's own communicator + halo exchange path
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import lis_b200

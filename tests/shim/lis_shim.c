@@ -765,6 +765,14 @@ EXPORT int shim_mv_matvec_queue(int h, int iters)
 #endif
     return (int)err;
 }
+EXPORT int shim_mv_p2p_release(int h)
+{
+#ifdef LIS_B200_LIS_H
+    return (int)lis_b200_p2p_release(g_mv[h].A);
+#else
+    (void)h; return 0;
+#endif
+}
 EXPORT int shim_mv_matvech(int h) { return (int)lis_matvech(g_mv[h].A, g_mv[h].x, g_mv[h].y); }
 EXPORT int shim_mv_dot_xy(int h, double *out) { LIS_SCALAR s = 0; LIS_INT e = lis_vector_dot(g_mv[h].x, g_mv[h].y, &s); *out = s; return (int)e; }
 
