@@ -156,6 +156,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+// a plain (L1-cached, coherent at kernel boundaries and after an acquire) global load the compiler may schedule freely
+__device__ __forceinline__ double ld_global(const double *p) {
+    double v;
+    asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -169,6 +175,35 @@ __device__ __forceinline__ int halo_block_of(int v, int int_lo, int int_hi)
     if (v < ni) return int_lo + v;
     v -= ni;
     return v < int_lo ? v : v + ni;
+}
+
+// one row out of a staged block: entries [j, e) of sidx/sval in storage order; up to kGather gathers of x in flight per
+// thread; tail entries are clamped to the row's last entry and masked out of the sum.  kInbox: columns >= n are read from
+// the inbox (a pointer select and ONE kind of load: two predicated loads of different kinds made the compiler order the
+// gathers in two groups with the arithmetic in between; profiles/r02_bench_2gpu_vmm.log).  Cached loads of the inbox are
+// safe: nothing of it can sit in L1 (invalidated at kernel start and again by the flag acquire, never read before that).
+template <bool kInbox>
+__device__ __forceinline__ double csr_row_walk(const int *__restrict__ sidx, const double *__restrict__ sval, int j, int e,
+                                               const double *__restrict__ x, const double *inbox, int n)
+{
+    constexpr int kGather = 8;
+    double acc = 0.0;
+    for (; j < e; j += kGather) {
+        int c[kGather];
+        double v[kGather], xv[kGather];
+#pragma unroll
+        for (int k = 0; k < kGather; ++k) {
+            const int jj = min(j + k, e - 1);
+            c[k] = sidx[jj];
+            v[k] = sval[jj];
+        }
+#pragma unroll
+        for (int k = 0; k < kGather; ++k) xv[k] = kInbox ? ld_global(c[k] < n ? x + c[k] : inbox + c[k]) : __ldg(x + c[k]);
+#pragma unroll
+        for (int k = 0; k < kGather; ++k)
+            if (j + k < e) acc = add(acc, mul(v[k], xv[k]));
+    }
+    return acc;
 }
 
 template <int kRows, int kStages, bool kDot, bool kHalo>
@@ -280,25 +315,10 @@ csr_tma_kernel(int n, int nblocks, int tile, const int *__restrict__ ptr, const 
                 const int w = sptr[0] & ~3;
                 int j = sptr[tid] - w;
                 const int e = sptr[tid + 1] - w;
-                double acc = 0.0;
-                // up to kGather gathers of x in flight per thread; tail entries are clamped to
-                // the row's last entry and masked out of the sum, which stays in storage order
-                constexpr int kGather = 8;
-                for (; j < e; j += kGather) {
-                    int c[kGather];
-                    double v[kGather], xv[kGather];
-#pragma unroll
-                    for (int k = 0; k < kGather; ++k) {
-                        const int jj = min(j + k, e - 1);
-                        c[k] = sidx[jj];
-                        v[k] = sval[jj];
-                    }
-#pragma unroll
-                    for (int k = 0; k < kGather; ++k) xv[k] = (!kHalo || c[k] < n) ? __ldg(x + c[k]) : __ldcg(inbox + c[k]);
-#pragma unroll
-                    for (int k = 0; k < kGather; ++k)
-                        if (j + k < e) acc = add(acc, mul(v[k], xv[k]));
-                }
+                // interior blocks (all but the two boundary planes of a slab) take the plain read-only gather; only
+                // the blocks behind the flag wait pay for the two-source gather
+                const double acc = (kHalo && vb >= n_first) ? csr_row_walk<true>(sidx, sval, j, e, x, inbox, n)
+                                                            : csr_row_walk<false>(sidx, sval, j, e, x, inbox, n);
                 y[r] = acc;
                 if (kDot) dsum = add(dsum, mul(__ldg(dotx + r), acc));
             }

@@ -186,5 +186,6 @@ __forceinline__ void st_publish(double *p, double v) { *p = v; }
 __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { emu::spin_yield(); return *(const volatile unsigned long long *)p; }
 __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *)p = v; }
 __forceinline__ unsigned long long global_timer_ns() { return 0ull; }
+__forceinline__ double ld_global(const double *p) { return *p; }
 
 }  // namespace lisb

@@ -83,3 +83,14 @@ def test_row_partitioned_spmv_and_solvers_2gpu(built):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     launch(2, "gpu", timeout=600)
+
+
+@pytest.mark.gpu
+def test_interior_rows_overlap_and_in_kernel_exchange_2gpu(built):
+    """19 k rows per rank, an interior run of row blocks: products with the NCCL exchange (interior rows on a second stream)
+    and with the halo exchange inside the kernel over peer memory, both CSR kernels, against the one-process oracle bit for
+    bit; CG with the split fused step; the overlapped host-buffer product"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    launch(2, "overlap", timeout=600, extra_env={"LIS_B200_OVERLAP": "force"})
