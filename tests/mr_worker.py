@@ -83,8 +83,10 @@ def overlap_case(rank, world, shim, lib):
     try:
         lib.emu_launch_count.restype = C.c_long; lib.emu_launch_count.argtypes = [C.c_char_p]
         count = lambda: int(lib.emu_launch_count(b""))
+        have_count = True
     except AttributeError:
         count = lambda: -1
+        have_count = False                       # the product library keeps no launch log (emulator only)
     # CG on the same partition: q = A p with <p,q> fused, interior rows on the second stream during the
     # exchange, the dot assembled from the range shares.  Same iteration count as the oracle's
     # one-process CG and as the run without overlap; the overlapped run launches more kernels.
@@ -107,7 +109,7 @@ def overlap_case(rank, world, shim, lib):
         assert np.allclose(rh[:n_it + 1], ref["rhistory"][:n_it + 1], rtol=1e-6, atol=0), on
         runs[on] = (count() - c0, n_it)
     lib.lis_b200_set_overlap(1)
-    if runs[1][0] >= 0:
+    if have_count:
         assert runs[1][0] >= runs[0][0] + runs[1][1], ("overlapped CG did not split its products", runs)
     L.shim_mv_close(h)
     launches = count()
