@@ -309,3 +309,56 @@ def test_sweep_warp_per_row_for_long_rows(b200, oracle):
             H.assert_bits_equal(x, oracle.psolve(ptr, idx, val, b, "ssor", omega=1.2, nthreads=T), f"warp-per-row SSOR, {T} block(s)")
         finally:
             b200.set_threads(1)
+
+
+def test_in_kernel_halo_exchange_middle_slab_two_neighbours(oracle):
+    """the middle one of three slabs: two neighbours, two export segments, two flags to wait for and two to raise"""
+    import ctypes as C
+    import numpy as np
+    r = subprocess.run(["make", "-C", EMU_DIR, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lib = C.CDLL(os.path.join(EMU_DIR, "_build", "liblis_emu.so"))
+    vp = C.c_void_p
+    lib.lisb200_spmv_csr_tma_p2p.argtypes = [C.c_int] * 4 + [vp] * 5 + [C.c_int] + [vp] * 4 + [C.c_ulonglong, C.c_int, C.c_int, vp]
+    L, M, N = 18, 16, 16                            # 3 slabs of 6 planes of 256 rows
+    ptr, idx, val = H.poisson3d_7pt(L, M, N, sort=True)
+    nloc = L // 3 * M * N; plane = M * N
+    r0 = nloc                                       # the middle slab
+    p = ptr[r0:r0 + nloc + 1].astype(np.int64)
+    cols = idx[p[0]:p[-1]].astype(np.int64); vals = val[p[0]:p[-1]].copy()
+    halo = np.unique(cols[(cols < r0) | (cols >= r0 + nloc)])          # lower neighbour's plane, then the upper one's
+    loc = np.where((cols >= r0) & (cols < r0 + nloc), cols - r0, nloc + np.searchsorted(halo, cols)).astype(np.int32)
+    lp = (p - p[0]).astype(np.int32)
+    assert len(halo) == 2 * plane
+    # what the neighbours read from me: rank 0 my first plane, rank 2 my last plane (their halo order = ascending)
+    export = np.concatenate([np.arange(plane), np.arange(nloc - plane, nloc)]).astype(np.int32)
+    rng = np.random.default_rng(9)
+    stride = 2 * plane
+    for epoch in (1, 2, 3):
+        xg = rng.uniform(-1, 1, L * M * N)
+        yref = oracle.spmv("csr", ptr, idx, val, xg)
+        par = epoch & 1
+        mine = np.zeros(2 * stride + 40); mflags = mine[2 * stride:2 * stride + 32].view(np.uint64)
+        nb = {0: np.zeros(2 * 256 + 40), 2: np.zeros(2 * 256 + 40)}    # the neighbours' inboxes (stride 256)
+        nflags = {k: v[512:512 + 32].view(np.uint64) for k, v in nb.items()}
+        mine[par * stride:par * stride + 2 * plane] = xg[halo]          # both neighbours' pushes, by hand
+        mflags[par * 16 + 0] = epoch; mflags[par * 16 + 2] = epoch
+        tb = _P2PTable()
+        tb.n_nbr = 2; tb.n_export = len(export); tb.export_index = export.ctypes.data
+        tb.exp_start[0] = 0; tb.exp_start[1] = plane; tb.exp_start[2] = 2 * plane
+        tb.nbr_rank[0] = 0; tb.nbr_rank[1] = 2
+        for s, k in enumerate((0, 2)):
+            tb.peer_inbox[s] = nb[k].ctypes.data; tb.peer_stride[s] = 256
+            tb.peer_flag[s] = nflags[k].ctypes.data + 8 * 1            # my rank is 1
+        tb.inbox = mine.ctypes.data; tb.inbox_stride = stride; tb.my_flag = mflags.ctypes.data
+        cnt = np.zeros(16, np.uint32); err = np.zeros(4, np.int32)
+        tb.push_count = cnt.ctypes.data; tb.error = err.ctypes.data
+        x = xg[r0:r0 + nloc].copy(); y = np.zeros(nloc)
+        pp = np.concatenate([lp, np.zeros(4, np.int32)]); ii = np.concatenate([loc, np.zeros(8, np.int32)]); vv = np.concatenate([vals, np.zeros(8)])
+        rc = lib.lisb200_spmv_csr_tma_p2p(nloc, 256, 2048, 2, pp.ctypes.data, ii.ctypes.data, vv.ctypes.data, x.ctypes.data, y.ctypes.data,
+                                          0, None, None, None, C.addressof(tb), epoch, plane, nloc - plane, None)
+        assert rc == 0 and err[0] == 0
+        H.assert_bits_equal(y, yref[r0:r0 + nloc], f"middle slab, epoch {epoch}")
+        np.testing.assert_array_equal(nb[0][par * 256:par * 256 + plane], xg[r0:r0 + plane])
+        np.testing.assert_array_equal(nb[2][par * 256:par * 256 + plane], xg[r0 + nloc - plane:r0 + nloc])
+        assert nflags[0][par * 16 + 1] == epoch and nflags[2][par * 16 + 1] == epoch and cnt[0] == 0
