@@ -543,8 +543,12 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
     {
         size_t kept = 0, nrows = 0;
         for (size_t k = 0; k < nslots; k++) if (order[k] >= 0) { kept += (size_t)plen[k]; nrows++; }
+        /* opt-in only (LIS_B200_SWEEP_KERNEL=rows): measured on the 10 M x 70 banded matrix it LOSES to the thread-per-row
+         * kernel -- 37 vs 25 ms per BiCGSTAB+SSOR iteration at 16 blocks, 329 vs 261 at one (profiles/r02_configs_n1c.jsonl) --
+         * because a warp works through its rows one after the other and only ~4.7 k rows are in flight, which no longer
+         * hides the DRAM latency of each row's own loads; kept as a tested alternative */
         const char *force = getenv("LIS_B200_SWEEP_KERNEL");
-        const int want = force ? strcmp(force, "rows") == 0 : (nrows > 0 && kept >= 12 * nrows);
+        const int want = force && strcmp(force, "rows") == 0 && nrows > 0;
         if (want && kept <= 0x7fffff00u) {
             int *rptr = (int *)malloc(sizeof(int) * (nslots + 1)), *rdep = (int *)malloc(sizeof(int) * (nslots ? nslots : 1));
             int *ridx = (int *)malloc(sizeof(int) * (kept ? kept : 1));

@@ -290,13 +290,14 @@ def test_in_kernel_halo_exchange_two_slabs(oracle, with_dot, sms):
             os.environ["LISB_EMU_SMS"] = env_old
 
 
-def test_sweep_warp_per_row_for_long_rows(b200, oracle):
-    """factors with tens of kept entries per row take the warp-per-row sweep kernel (sweep_rowwarp_kernel: all neighbours of a
+def test_sweep_warp_per_row_for_long_rows(b200, oracle, monkeypatch):
+    """LIS_B200_SWEEP_KERNEL=rows: the warp-per-row sweep kernel (sweep_rowwarp_kernel: all neighbours of a
     row polled at once, products added lane by lane in storage order): same bits as the oracle's sequential sweep, for the
     serial sweep and for block-SSOR; rows longer than one 64-entry chunk included (the long row of random_csr)"""
     import ctypes as C
     lib = C.CDLL(os.path.join(EMU_DIR, "_build", "liblis_emu.so"))
     lib.emu_launch_count.restype = C.c_long; lib.emu_launch_count.argtypes = [C.c_char_p]
+    monkeypatch.setenv("LIS_B200_SWEEP_KERNEL", "rows")
     ptr, idx, val = H.random_csr(260, 30, 77)
     b = H.rand_vec(260, 5, "wide")
     for T in (1, 3):
@@ -304,8 +305,7 @@ def test_sweep_warp_per_row_for_long_rows(b200, oracle):
         try:
             before = lib.emu_launch_count(b"sweep_rowwarp_kernel")
             x = b200.psolve(ptr, idx, val, b, "-p ssor -ssor_omega 1.2")
-            if T == 1:      # with 3 blocks the dropped couplings leave short rows: the thread-per-row kernel takes those
-                assert lib.emu_launch_count(b"sweep_rowwarp_kernel") - before == 2, "expected the warp-per-row kernel for both sweeps"
+            assert lib.emu_launch_count(b"sweep_rowwarp_kernel") - before == 2, "expected the warp-per-row kernel for both sweeps"
             H.assert_bits_equal(x, oracle.psolve(ptr, idx, val, b, "ssor", omega=1.2, nthreads=T), f"warp-per-row SSOR, {T} block(s)")
         finally:
             b200.set_threads(1)
