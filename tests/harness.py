@@ -61,12 +61,6 @@ def ref_shim(kind: str):
 
 
 # ------------------------------------------------------------------ matrices
-def _stencil_csr(dims, offsets_fn, sort=False):
-    """Generic lexicographic stencil builder; offsets_fn(coords, dims) -> list of (col, val) in
-    the driver's storage order."""
-    raise NotImplementedError
-
-
 def poisson1d(n):
     """test/spmvtest1.c:139-146: rows (i-1, i+1, i) with values (-1, -1, 2)."""
     ptr = [0]
