@@ -517,3 +517,36 @@ def test_psd_update_and_vbr_partition(built):
     cuts = [row[k] for k in range(nr.value + 1)]
     assert nr.value == nc.value and cuts[0] == 0 and cuts[-1] == n and cuts == sorted(set(cuts))
     lib.lis_vector_destroy(v); lib.lis_matrix_destroy(A)
+
+
+def test_descriptor_hand_over_between_ranks(built):
+    """host/lis_peer.c: the file descriptors of the exportable inbox blocks travel as SCM_RIGHTS messages over abstract unix
+    datagram sockets, one socket per rank.  Here: two 'ranks' in one process, a pipe's read end handed from rank 0 to rank 1
+    and from rank 1 to rank 0; what is written into the pipes comes out of the received descriptors."""
+    import ctypes as C
+    import lis_b200
+    lib = lis_b200.load_library()
+    lib.lisd_fd_socket.argtypes = [C.c_char_p, C.c_int]
+    lib.lisd_fd_send.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.lisd_fd_recv.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    job = f"pytest-{os.getpid()}".encode()
+    s0, s1 = lib.lisd_fd_socket(job, 0), lib.lisd_fd_socket(job, 1)
+    assert s0 >= 0 and s1 >= 0
+    assert lib.lisd_fd_socket(job, 1) < 0                      # the name is taken: a second bind must fail
+    r0, w0 = os.pipe(); r1, w1 = os.pipe()
+    try:
+        assert lib.lisd_fd_send(s0, job, 1, 0, r0) == 1 and lib.lisd_fd_send(s1, job, 0, 1, r1) == 1
+        frm, fd = C.c_int(-1), C.c_int(-1)
+        assert lib.lisd_fd_recv(s1, C.byref(frm), C.byref(fd), 2000) == 1 and frm.value == 0 and fd.value not in (r0, -1)
+        os.write(w0, b"from rank 0")
+        assert os.read(fd.value, 64) == b"from rank 0"
+        os.close(fd.value)
+        assert lib.lisd_fd_recv(s0, C.byref(frm), C.byref(fd), 2000) == 1 and frm.value == 1
+        os.write(w1, b"from rank 1")
+        assert os.read(fd.value, 64) == b"from rank 1"
+        os.close(fd.value)
+        assert lib.lisd_fd_recv(s0, C.byref(frm), C.byref(fd), 50) == 0          # nothing queued: times out
+        assert lib.lisd_peer_available() == 0                   # no CUDA device here: the exchange stays on the fallback
+    finally:
+        for f in (r0, w0, r1, w1, s0, s1):
+            os.close(f)
