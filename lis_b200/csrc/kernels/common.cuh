@@ -33,6 +33,12 @@ __device__ __forceinline__ double2 ld_stream2(const double2 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// 256-bit streaming load (sm_100: LDG.E.256): four doubles, address 32-byte aligned
+__device__ __forceinline__ double4 ld_stream4d(const double *p) {
+    double4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ int ld_stream(const int *p) {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));

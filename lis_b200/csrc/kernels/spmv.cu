@@ -523,7 +523,7 @@ constexpr int kBsrTileDoubles = 4096;     // products per shared-memory window (
 // 2-way for the even row lengths of stencils, where the block-major layout of the first version was
 // 8-way (32-byte blocks 7 blocks apart; profiles/r02_ncu_bsr_v2.txt).
 template <int R, int C>
-__global__ void __launch_bounds__(kBsrRows)
+__global__ void __launch_bounds__(kBsrRows, 4)
 bsr_tile_kernel(int n, int ncols, int nr, const int *__restrict__ bptr, const int *__restrict__ bidx,
                 const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
 {
@@ -536,6 +536,7 @@ bsr_tile_kernel(int n, int ncols, int nr, const int *__restrict__ bptr, const in
     constexpr int kUnroll = 4;                                 // steps whose loads are in flight together
     __shared__ __align__(16) double prod[W];
     const int tid = threadIdx.x;
+    const bool aligned32 = ((reinterpret_cast<uintptr_t>(val) & 31) | (reinterpret_cast<uintptr_t>(x) & 15)) == 0;
     const int br0 = blockIdx.x * kBsrRows;
     const int brend = min(br0 + kBsrRows, nr);
     const int bi = br0 + tid;
@@ -551,6 +552,45 @@ bsr_tile_kernel(int n, int ncols, int nr, const int *__restrict__ bptr, const in
         const long long e0 = wb * BS;
         const int cnt = (int)(wbend - wb) * BS;                // elements in this window
         // ---- phase 1: products of the window's elements, kUnroll steps of loads in flight together
+        if (R == 2 && C == 2 && aligned32) {
+            // the reference's default shape: a thread takes a whole block -- ONE 256-bit load of its four values
+            // (32 lanes: 1 KB contiguous), one index load, one 128-bit load of its x pair -- half the load
+            // instructions and L1 requests of the two-elements-per-thread path below (which ran at 84 % of the
+            // L1 throughput, profiles/r02_ncu_bsr_jad_v2.txt)
+            constexpr int kBlkSteps = (WB + kBsrRows - 1) / kBsrRows;            // 4
+            const int nblk = (int)(wbend - wb);
+            double4 a[kBlkSteps];
+            int bc[kBlkSteps];
+#pragma unroll
+            for (int u = 0; u < kBlkSteps; ++u) {
+                const int bl = tid + u * kBsrRows;
+                bc[u] = -1;
+                a[u] = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (bl < nblk) {
+                    a[u] = ld_stream4d(val + e0 + 4 * (long long)bl);
+                    bc[u] = __ldg(bidx + wb + bl) * 2;
+                }
+            }
+            double2 xx[kBlkSteps];
+#pragma unroll
+            for (int u = 0; u < kBlkSteps; ++u) {
+                xx[u] = make_double2(0.0, 0.0);
+                if (bc[u] >= 0) {
+                    // a padded last block column holds structural zeros; x behind them does not exist
+                    if (bc[u] + 1 < ncols) xx[u] = __ldg(reinterpret_cast<const double2 *>(x + bc[u]));
+                    else xx[u].x = __ldg(x + bc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBlkSteps; ++u)
+                if (bc[u] >= 0) {
+                    const int bl = tid + u * kBsrRows;
+                    prod[0 * WB + bl] = mul(a[u].x, xx[u].x);
+                    prod[1 * WB + bl] = mul(a[u].y, xx[u].x);
+                    prod[2 * WB + bl] = mul(a[u].z, xx[u].y);
+                    prod[3 * WB + bl] = mul(a[u].w, xx[u].y);
+                }
+        } else
         for (int s0 = 0; s0 < kSteps; s0 += kUnroll) {
             double a0[kUnroll], a1[kUnroll];
             int bcol[kUnroll], off[kUnroll];

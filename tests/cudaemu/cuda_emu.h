@@ -134,6 +134,7 @@ namespace lisb {
 
 __forceinline__ double ld_stream(const double *p) { return *p; }
 __forceinline__ int ld_stream(const int *p) { return *p; }
+__forceinline__ double4 ld_stream4d(const double *p) { emu::check_aligned(p, 32, "ld_stream4d: address not 32-byte aligned"); double4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
 __forceinline__ double2 ld_stream2(const double2 *p) { emu::check_aligned(p, 16, "ld_stream2: address not 16-byte aligned"); return *p; }
 __forceinline__ int4 ld_stream4(const int4 *p) { emu::check_aligned(p, 16, "ld_stream4: address not 16-byte aligned"); return *p; }
 __forceinline__ int2 ld_stream2(const int2 *p) { emu::check_aligned(p, 8, "ld_stream2(int2): address not 8-byte aligned"); return *p; }
