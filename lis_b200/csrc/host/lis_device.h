@@ -187,7 +187,8 @@ LIS_INT lisd_halo_reduce_raw(LIS_MATRIX A, double *d_y);                        
 LIS_INT lisd_matvec_dot(LIS_MATRIX A, LIS_VECTOR x, LIS_VECTOR y, LIS_SCALAR *dot_xy);        /* y=Ax; <x,y> */
 LIS_INT lisd_cg_update(LIS_SCALAR alpha, LIS_VECTOR p, LIS_VECTOR q, LIS_VECTOR x, LIS_VECTOR r, LIS_REAL *nrm2_r);
 LIS_INT lisd_dot2(LIS_VECTOR a, LIS_VECTOR b, LIS_SCALAR out[2]);                             /* <a,b>, <a,a> */
-LIS_INT lisd_axpy_nrm2(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_REAL *nrm2);         /* y+=alpha x; ||y|| */
+LIS_INT lisd_axpy_nrm2(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_REAL *nrm2);
+LIS_INT lisd_axpy_dot(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR u, LIS_SCALAR *dot);    /* y+=alpha x; <y,u> */         /* y+=alpha x; ||y|| */
 LIS_INT lisd_bicgstab_p(LIS_SCALAR omega, LIS_SCALAR beta, LIS_VECTOR v, LIS_VECTOR r, LIS_VECTOR p);   /* p=r+beta(p-omega v) */
 LIS_INT lisd_bicgstab_update(LIS_SCALAR alpha, LIS_SCALAR omega, LIS_VECTOR phat, LIS_VECTOR shat, LIS_VECTOR t,
                              LIS_VECTOR x, LIS_VECTOR r, LIS_REAL *nrm2);                      /* x,r updates; ||r|| */

@@ -251,6 +251,17 @@ LIS_INT lis_host_mgs(LIS_VECTOR *v, LIS_INT i, LIS_SCALAR *hcol, LIS_REAL *nrm)
         CHK(lisd_dev_scalars_fetch(0, (int)i));
         CHK(lis_vector_nrm2(w, nrm));                                              /* waits for the stream */
         for (k = 0; k < i; k++) hcol[k] = lisd_fetched((int)k);
+    } else if (fuse_enabled() && lisd_nranks() > 1 && i >= 1 && !(mode && strcmp(mode, "chain") == 0)) {
+        /* row-partitioned: every coefficient has to be combined across the ranks on the host, so each link waits --
+         * but the axpy still shares its pass over w with the dot of the next link (or the closing norm): i+1 passes
+         * over w instead of 2i+1, same kernels and trees as the separate calls, same bits */
+        CHK(lis_vector_dot(w, v[0], &t));
+        hcol[0] = t;
+        for (k = 0; k + 1 < i; k++) {
+            CHK(lisd_axpy_dot(-hcol[k], v[k], w, v[k + 1], &t));
+            hcol[k + 1] = t;
+        }
+        CHK(lisd_axpy_nrm2(-hcol[i - 1], v[i - 1], w, nrm));
     } else {
         for (k = 0; k < i; k++) {
             CHK(lis_vector_dot(w, v[k], &t));

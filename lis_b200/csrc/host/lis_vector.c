@@ -495,6 +495,25 @@ LIS_INT lisd_axpy_nrm2(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_REAL *n
     return LIS_SUCCESS;
 }
 
+/* y += alpha*x ; *dot = <y,u> over all ranks  (one pass; waits) -- a Gram-Schmidt link of a row-partitioned GMRES,
+ * where the coefficient is a host scalar that was combined across the ranks */
+LIS_INT lisd_axpy_dot(LIS_SCALAR alpha, LIS_VECTOR x, LIS_VECTOR y, LIS_VECTOR u, LIS_SCALAR *dot)
+{
+    LISD_PREP2(x, y, "axpy+dot");
+    { LIS_INT e_ = lis_vector_check_same(x, u); if (e_) return e_; e_ = lisd_vec_device(u); if (e_) return e_; }
+    if (!all_aligned16(x->value, y->value, u->value, NULL, NULL)) {
+        LIS_INT e_ = lisd_axpy(alpha, x, y);
+        return e_ ? e_ : lis_vector_dot(y, u, dot);
+    }
+    double *partial = lisd_partial(0);
+    if (partial == NULL) { LIS_SETERR_MEM(0); return LIS_ERR_OUT_OF_MEMORY; }
+    lisd_mark_busy();
+    LIS_INT err = lisd_check(lisb200_mgs_step(0, x->n, NULL, alpha, x->value, y->value, u->value, partial, lisd_counter(),
+                                              lisd_scalar_dev(0), lisd_stream()), "axpy+dot");
+    if (err) return err;
+    return lisd_reduce_finish(dot, 1, 0);
+}
+
 /* p = r + beta*(p - omega*v) */
 LIS_INT lisd_bicgstab_p(LIS_SCALAR omega, LIS_SCALAR beta, LIS_VECTOR v, LIS_VECTOR r, LIS_VECTOR p)
 {
