@@ -7,13 +7,19 @@ matrix of the reference's test/spmvtest3.c, 512^3 per GPU, CSR, fp64.
 A "step" is one y = A x over the whole matrix.  `value` is the device-timed throughput with
 A, x and y resident in HBM (CUDA events on the launching stream, K launches back to back; the
 matrix is ~14 GB, >100x the L2, so no flush is needed between steps).  `e2e` is the same
-product through the public lis.h call (lis_matvec) with HOST buffers: x is copied in from
-pinned host memory and y copied back out every step.  `roofline` is for the CSR kernel against
-the measured HBM copy bandwidth; `cpu_baseline` / `--impl reference` time the reference's own
-OpenMP lis_matvec (compiled from the reference sources into oracle/_ref) on the host cores.
+product through the public API with HOST buffers: x is copied in from pinned host memory and
+y copied back out every step.  `roofline` is for the CSR kernel against the measured HBM copy
+bandwidth (`traffic` from profiles/ncu_traffic.json); `cpu_baseline` / `--impl reference` time the
+reference's own OpenMP lis_matvec (compiled from the reference sources into oracle/_ref) on every
+host core on the same 512^3 matrix.  At N=1 `extra` also carries BASELINE config 3 at its stated
+size: CG + Jacobi on test3.c's 512^3 system to 1e-12, iteration count and residual history against
+the reference's stored run (tests/golden/cg_poisson_512.npz).
 
-N > 1 (torchrun, one rank per GPU): the grid is 512 x 512 x (512*N), row-partitioned into N
-slabs of 512^3 rows (weak scaling) with the halo planes exchanged before every product.
+N > 1 (torchrun, one rank per GPU, every GPU visible to every rank): the grid is
+512 x 512 x (512*N), row-partitioned into N slabs of 512^3 rows (weak scaling) with the halo planes
+exchanged for every product -- by NCCL before the product, by NCCL while the interior rows run, or
+inside the SpMV kernel over peer memory; each order is adopted only if every rank reproduces the
+bits of the first, and the fastest is reported.
 """
 from __future__ import annotations
 
