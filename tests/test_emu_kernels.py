@@ -42,6 +42,7 @@ test_hybrid_preconditioner = G2.test_hybrid_preconditioner
 test_ilut_preconditioner = G2.test_ilut_preconditioner
 test_is_preconditioner = G2.test_is_preconditioner
 test_gram_schmidt_fused_chain_same_bits = G2.test_gram_schmidt_fused_chain_same_bits
+test_queued_products_same_bits_as_synchronous_calls = G2.test_queued_products_same_bits_as_synchronous_calls
 test_device_conversion_same_arrays_as_host = G2.test_device_conversion_same_arrays_as_host
 test_device_conversion_falls_back_to_host_builder = G2.test_device_conversion_falls_back_to_host_builder
 test_blas1_elementwise_bit_exact = G.test_blas1_elementwise_bit_exact

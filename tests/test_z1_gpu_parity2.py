@@ -97,6 +97,30 @@ def test_matvec_host_pipelined_default_chunks(b200, oracle):
         L.shim_mv_close(h)
 
 
+def test_queued_products_same_bits_as_synchronous_calls(b200, oracle):
+    """lis_b200_matvec_async: products enqueued back to back with one synchronisation at the end (what bench.py's
+    device-timed multi-GPU leg does) leave the bits of lis_matvec in y"""
+    import ctypes as C
+    ptr, idx, val = H.poisson3d_7pt(20, 17, 15, sort=True)
+    n = len(ptr) - 1
+    L = b200.lib
+    vp = C.c_void_p
+    L.shim_mv_open.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.shim_mv_set_x.argtypes = [C.c_int, vp]; L.shim_mv_get_xy.argtypes = [C.c_int, vp, vp]
+    h = L.shim_mv_open(1, n, ptr.ctypes.data, idx.ctypes.data, val.ctypes.data, 0, 0, 0)
+    assert h >= 0
+    try:
+        x = H.rand_vec(n, 21, "wide")
+        assert L.shim_mv_set_x(h, x.ctypes.data) == 0
+        assert L.shim_mv_matvec_queue(h, 5) == 0
+        xo = np.zeros(n); y = np.zeros(n)
+        assert L.shim_mv_get_xy(h, xo.ctypes.data, y.ctypes.data) == 0
+        H.assert_bits_equal(y, oracle.spmv("csr", ptr, idx, val, x), "queued products")
+        H.assert_bits_equal(xo, x, "x untouched")
+    finally:
+        L.shim_mv_close(h)
+
+
 def _conv_cases():
     yield "poisson3d_7pt_sorted", H.poisson3d_7pt(17, 13, 11, sort=True)
     yield "poisson3d_7pt_unsorted", H.poisson3d_7pt(12, 9, 10)
