@@ -60,4 +60,5 @@ LIS_INT lis_vector_check_same(LIS_VECTOR x, LIS_VECTOR y);
 #ifdef __cplusplus
 }
 #endif
+LIS_INT lis_host_matrix_scale_like(LIS_MATRIX C, LIS_VECTOR Dv, LIS_INT action);   /* lis_matrix.c */
 #endif

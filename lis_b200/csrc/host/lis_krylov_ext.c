@@ -896,6 +896,12 @@ static LIS_INT stationary(LIS_SOLVER solver, int kind)
 {
     LIS_MATRIX A = solver->A, S = A;
     LIS_INT err;
+    if (kind != 0 && A->matrix_type != LIS_MATRIX_CSR && solver->precon && solver->precon->is_copy && solver->precon->A &&
+        solver->precon->A->matrix_type == LIS_MATRIX_CSR && solver->precon->A->is_splited) {
+        /* -p ssor already sweeps on a private split copy: the reference has ONE split matrix for both (so the two share
+         * WD, whoever set it first under the same tag: lis_solver_sor.c, lis_precon_ssor.c) -- share it here too */
+        return stationary_run(solver, kind, solver->precon->A);
+    }
     if (kind != 0 && A->matrix_type != LIS_MATRIX_CSR) {
         if (A->matrix_type == LIS_MATRIX_BSR || A->matrix_type == LIS_MATRIX_BSC || A->matrix_type == LIS_MATRIX_VBR) {
             LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "Gauss-Seidel / SOR on block storage (BSR/BSC/VBR) is not available; use a scalar format\n");

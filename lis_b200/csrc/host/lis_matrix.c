@@ -703,17 +703,47 @@ LIS_INT lis_matrix_set_values(LIS_INT flag, LIS_INT n, LIS_SCALAR value[], LIS_M
     return LIS_SUCCESS;
 }
 
+/* the factors lis_matrix_scale left in Dv (1/d or 1/sqrt|d|), applied to another CSR matrix with the same rows -- the
+ * private split copy the sweeps of SSOR/GS/SOR run on under -storage <scalar format> (host/lis_precon.c create_ssor) */
+LIS_INT lis_host_matrix_scale_like(LIS_MATRIX C, LIS_VECTOR Dv, LIS_INT action)
+{
+    const LIS_INT n = C->n;
+    if (C->matrix_type != LIS_MATRIX_CSR || C->nprocs > 1) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
+    LIS_SCALAR *d = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(n > 0 ? n : 1));
+    if (d == NULL) { LIS_SETERR_MEM(n * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
+    LIS_INT err = n > 0 ? lis_vector_get_values(Dv, Dv->is + Dv->origin, n, d) : LIS_SUCCESS;
+    if (err) { free(d); return err; }
+    const int symm = action == LIS_SCALE_SYMM_DIAG;
+    if (C->is_splited) {
+        for (LIS_INT i = 0; i < n; i++) {
+            C->D->value[i] = 1.0;
+            for (LIS_INT j = C->L->ptr[i]; j < C->L->ptr[i + 1]; j++) { if (symm) C->L->value[j] = C->L->value[j] * d[i] * d[C->L->index[j]]; else C->L->value[j] *= d[i]; }
+            for (LIS_INT j = C->U->ptr[i]; j < C->U->ptr[i + 1]; j++) { if (symm) C->U->value[j] = C->U->value[j] * d[i] * d[C->U->index[j]]; else C->U->value[j] *= d[i]; }
+        }
+    } else {
+        for (LIS_INT i = 0; i < n; i++)
+            for (LIS_INT j = C->ptr[i]; j < C->ptr[i + 1]; j++) { if (symm) C->value[j] = C->value[j] * d[i] * d[C->index[j]]; else C->value[j] *= d[i]; }
+    }
+    free(d);
+    lisd_matrix_drop(C);                            /* mirror and sweep schedule are rebuilt from the scaled arrays */
+    C->is_scaled = LIS_TRUE;
+    return LIS_SUCCESS;
+}
+
 /* -scale: A <- D^-1 A, b <- D^-1 b (LIS_SCALE_JACOBI) or A <- D^-1/2 A D^-1/2, b <- D^-1/2 b
  * (LIS_SCALE_SYMM_DIAG), D = diag(A); the scaling vector stays in Dv (src/matrix/lis_matrix_ops.c:579-712,
  * CSR loops src/matrix/lis_matrix_csr.c:607-693).  Once per solve, on the host arrays the caller sees
- * (they stay scaled, A->is_scaled, like in the reference); the device mirror is dropped.  CSR, one process. */
+ * (they stay scaled, A->is_scaled, like in the reference); the device mirror is dropped.  One process; CSR (also split),
+ * and unsplit CSC / ELL / DIA / JAD / BSR. */
 LIS_INT lis_matrix_scale(LIS_MATRIX A, LIS_VECTOR B, LIS_VECTOR Dv, LIS_INT action)
 {
     const LIS_INT n = A->n;
     LIS_INT err = lis_host_matrix_check_input(A);
     if (err) return err;
-    if (A->matrix_type != LIS_MATRIX_CSR || A->nprocs > 1) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale needs a CSR matrix on one process (scaling runs before -storage converts)\n");
+    const LIS_INT mt = A->matrix_type;
+    const int other_fmt = mt == LIS_MATRIX_ELL || mt == LIS_MATRIX_DIA || mt == LIS_MATRIX_JAD || mt == LIS_MATRIX_BSR || mt == LIS_MATRIX_CSC;
+    if ((mt != LIS_MATRIX_CSR && !(other_fmt && !A->is_splited)) || A->nprocs > 1) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale needs a CSR, CSC, ELL, DIA, JAD or BSR matrix on one process\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (action != LIS_SCALE_JACOBI && action != LIS_SCALE_SYMM_DIAG) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
@@ -723,7 +753,52 @@ LIS_INT lis_matrix_scale(LIS_MATRIX A, LIS_VECTOR B, LIS_VECTOR Dv, LIS_INT acti
     if (d == NULL) { LIS_SETERR_MEM(n * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
     err = n > 0 ? lis_vector_get_values(Dv, Dv->is + Dv->origin, n, d) : LIS_SUCCESS;
     if (err) { free(d); return err; }
-    if (action == LIS_SCALE_SYMM_DIAG) {
+    if (other_fmt) {
+        /* the other formats, each with the expression of its reference loop (the order of the multiplications differs
+         * between them): lis_matrix_scale[_symm]_{ell,dia,jad,bsr,csc}, src/matrix/lis_matrix_<fmt>.c */
+        const int symm = action == LIS_SCALE_SYMM_DIAG;
+        for (LIS_INT i = 0; i < n; i++) d[i] = symm ? 1.0 / sqrt(fabs(d[i])) : 1.0 / d[i];
+        if (mt == LIS_MATRIX_ELL) {
+            for (LIS_INT j = 0; j < A->maxnzr; j++)
+                for (LIS_INT i = 0; i < n; i++) {
+                    const size_t o = (size_t)j * n + i;
+                    if (symm) A->value[o] *= d[i] * d[A->index[o]]; else A->value[o] *= d[i];
+                }
+        } else if (mt == LIS_MATRIX_DIA) {
+            for (LIS_INT j = 0; j < A->nnd; j++) {
+                const LIS_INT jj = A->index[j], is = jj < 0 ? -jj : 0, ie = jj > 0 ? n - jj : n;
+                for (LIS_INT i = is; i < ie; i++) {
+                    const size_t o = (size_t)j * n + i;
+                    if (symm) A->value[o] *= d[i] * d[i + jj]; else A->value[o] *= d[i];
+                }
+            }
+        } else if (mt == LIS_MATRIX_JAD) {
+            for (LIS_INT j = 0; j < A->maxnzr; j++) {
+                LIS_INT k = 0;
+                for (LIS_INT i = A->ptr[j]; i < A->ptr[j + 1]; i++, k++) {
+                    if (symm) A->value[i] *= d[A->row[k]] * d[A->index[i]]; else A->value[i] *= d[A->row[k]];
+                }
+            }
+        } else if (mt == LIS_MATRIX_BSR) {
+            const LIS_INT bnr = A->bnr, bnc = A->bnc, bs = bnr * bnc;
+            for (LIS_INT bi = 0; bi < A->nr; bi++)
+                for (LIS_INT bj = A->bptr[bi]; bj < A->bptr[bi + 1]; bj++) {
+                    const LIS_INT bjj = A->bindex[bj];
+                    for (LIS_INT j = 0; j < bnc; j++)
+                        for (LIS_INT i = 0; i < bnr; i++) {
+                            const LIS_INT r = bi * bnr + i, c = bjj * bnc + j;
+                            if (r >= n || c >= n) continue;         /* padding of the last block row / column: structural zeros */
+                            const size_t o = (size_t)bj * bs + (size_t)j * bnr + i;
+                            if (symm) A->value[o] *= d[r] * d[c]; else A->value[o] *= d[r];
+                        }
+                }
+        } else {                                                    /* CSC */
+            for (LIS_INT i = 0; i < n; i++)
+                for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
+                    if (symm) A->value[j] = A->value[j] * d[i] * d[A->index[j]]; else A->value[j] *= d[A->index[j]];
+                }
+        }
+    } else if (action == LIS_SCALE_SYMM_DIAG) {
         for (LIS_INT i = 0; i < n; i++) d[i] = 1.0 / sqrt(fabs(d[i]));
         if (A->is_splited) {
             for (LIS_INT i = 0; i < n; i++) {

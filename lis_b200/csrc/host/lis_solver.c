@@ -617,6 +617,8 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     /* system scaling (src/solver/lis_solver.c:636-721): the stationary solvers with a preconditioner
      * always work on D^-1 A; -scale jacobi|symm_diag on request (CG turns jacobi into symm_diag to keep
      * the matrix symmetric).  A and b stay scaled afterwards, exactly as there. */
+    const LIS_INT was_scaled = A->is_scaled;
+    LIS_INT scaled_with = LIS_SCALE_JACOBI;
     if (precon_type == LIS_PRECON_TYPE_IS) {
         /* I+S works on the unit-diagonal system D^-1 A (:613-641) */
         if (solver->d == NULL) err = lis_vector_duplicate(A, &solver->d);
@@ -628,9 +630,15 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     } else if (scale) {
         if (solver->d == NULL) err = lis_vector_duplicate(A, &solver->d);
         if (scale == LIS_SCALE_JACOBI && nsolver == LIS_SOLVER_CG) scale = LIS_SCALE_SYMM_DIAG;
+        scaled_with = scale;
         if (!err && !A->is_scaled) err = lis_matrix_scale(A, b, solver->d, scale);
         else if (!err && !b->is_scaled) err = lis_vector_pmul(b, solver->d, b);
     }
+    /* SSOR / GS / SOR with -storage <scalar format> sweep on a private split CSR copy of the matrix made when the
+     * preconditioner was created, i.e. before this scaling: the reference's split matrix IS the scaled one (with WD still
+     * from the unscaled diagonal, as there), so the copy gets the same factors */
+    if (!err && !was_scaled && A->is_scaled && precon && precon->is_copy && precon->A && precon->A != A)
+        err = lis_host_matrix_scale_like(precon->A, solver->d, scaled_with);
     if (err) { lis_vector_destroy(xx); lis_free(rhistory); solver->retcode = err; return err; }
 
     /* -storage: converts A in place */
