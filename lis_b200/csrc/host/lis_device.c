@@ -453,6 +453,30 @@ void lisd_vec_host(LIS_VECTOR v)
     v->b200_resident = 0;
 }
 
+/* Host view of a vector's values for the one-off host passes (I/O, the diagonal of a non-CSR matrix, print).
+ * Managed / host storage: v->value itself, migrated to the host first.  Device-only storage (b200_managed == 2, the
+ * fallback when managed memory is refused): a heap copy -- filled from the device when `load` is set -- that
+ * lisd_vec_host_done writes back when `store` is set, and frees.  NULL (with the error set) when that copy fails. */
+LIS_SCALAR *lisd_vec_host_view(LIS_VECTOR v, int load)
+{
+    if (v->b200_managed != 2) { lisd_vec_host(v); return v->value; }
+    const size_t bytes = (size_t)(v->b200_capacity > 0 ? v->b200_capacity : 1) * sizeof(LIS_SCALAR);
+    LIS_SCALAR *h = (LIS_SCALAR *)malloc(bytes);
+    if (h == NULL) { LIS_SETERR_MEM(bytes); return NULL; }
+    if (lisd_sync() != LIS_SUCCESS) { free(h); return NULL; }
+    if (load && lisd_download(h, v->value, bytes) != LIS_SUCCESS) { free(h); return NULL; }
+    return h;
+}
+
+LIS_INT lisd_vec_host_done(LIS_VECTOR v, LIS_SCALAR *view, int store)
+{
+    if (view == NULL || view == v->value) return LIS_SUCCESS;
+    LIS_INT err = LIS_SUCCESS;
+    if (store) err = lisd_upload(v->value, view, (size_t)(v->b200_capacity > 0 ? v->b200_capacity : 1) * sizeof(LIS_SCALAR));
+    free(view);
+    return err;
+}
+
 /* ---- reductions ------------------------------------------------------------------------ */
 double *lisd_partial(size_t slots)
 {

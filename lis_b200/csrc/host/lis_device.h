@@ -54,6 +54,8 @@ LIS_INT lisd_aux_join(void);
 /* ---- vectors: residency tracking of managed storage ---- */
 LIS_INT lisd_vec_device(LIS_VECTOR v);              /* make resident before a kernel touches it */
 void    lisd_vec_host(LIS_VECTOR v);                /* host is about to read/write v->value */
+LIS_SCALAR *lisd_vec_host_view(LIS_VECTOR v, int load);                      /* v->value, or a heap copy of device-only storage */
+LIS_INT lisd_vec_host_done(LIS_VECTOR v, LIS_SCALAR *view, int store);       /* writes the copy back (store) and frees it */
 
 /* ---- reductions ---- */
 double       *lisd_partial(size_t slots);           /* device scratch, grown on demand */

@@ -63,19 +63,20 @@ static LIS_INT read_mm_vec_body(FILE *f, LIS_VECTOR v, LIS_INT gn, int isbin)
 {
     char buf[LINE_MAX_LEN];
     const int swap = isbin && host_little_endian() != isbin - 1;
-    lisd_vec_host(v);
+    LIS_SCALAR *hv = lisd_vec_host_view(v, 1);
+    if (hv == NULL) return LIS_ERR_OUT_OF_MEMORY;
     for (LIS_INT i = 0; i < gn; i++) {
         int idx; double val;
         if (isbin) {
             mmb_vec_t r;
-            if (fread(&r, sizeof(r), 1, f) != 1) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
+            if (fread(&r, sizeof(r), 1, f) != 1) { lisd_vec_host_done(v, hv, 0); LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
             if (swap) { bswap_bytes(&r.i, sizeof(r.i)); bswap_bytes(&r.value, sizeof(r.value)); }
             idx = (int)r.i; val = (double)r.value;
-        } else if (fgets(buf, sizeof(buf), f) == NULL || sscanf(buf, "%d %lg", &idx, &val) != 2) { LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
+        } else if (fgets(buf, sizeof(buf), f) == NULL || sscanf(buf, "%d %lg", &idx, &val) != 2) { lisd_vec_host_done(v, hv, 0); LIS_SETERR_FIO; return LIS_ERR_FILE_IO; }
         idx--;
-        if (idx >= v->is && idx < v->ie) v->value[idx - v->is] = val;
+        if (idx >= v->is && idx < v->ie) hv[idx - v->is] = val;
     }
-    return LIS_SUCCESS;
+    return lisd_vec_host_done(v, hv, 1);
 }
 
 static LIS_INT input_mm(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, FILE *f)
@@ -340,13 +341,16 @@ LIS_INT lis_input_vector(LIS_VECTOR v, char *filename)
             rewind(f);
             err = lis_vector_set_size(v, 0, cnt);
         }
+        LIS_SCALAR *hv = err ? NULL : lisd_vec_host_view(v, 1);
+        if (!err && hv == NULL) err = LIS_ERR_OUT_OF_MEMORY;
         if (!err) {
-            lisd_vec_host(v);
             for (LIS_INT i = 0; i < v->gn; i++) {
                 double d;
                 if (fgets(buf, sizeof(buf), f) == NULL || sscanf(buf, "%lg", &d) != 1) { LIS_SETERR_FIO; err = LIS_ERR_FILE_IO; break; }
-                if (i >= v->is && i < v->ie) v->value[i - v->is] = d;
+                if (i >= v->is && i < v->ie) hv[i - v->is] = d;
             }
+            const LIS_INT err2 = lisd_vec_host_done(v, hv, err == LIS_SUCCESS);
+            if (!err) err = err2;
         }
     }
     fclose(f);
@@ -393,11 +397,13 @@ LIS_INT lis_output_vector(LIS_VECTOR v, LIS_INT format, char *filename)
  * LIS_FMT_MMB: same header with a sixth field (1 + little-endian), records in binary. */
 static void write_mm_vec(FILE *f, LIS_VECTOR v, LIS_INT format)
 {
-    lisd_vec_host(v);
+    LIS_SCALAR *hv = lisd_vec_host_view(v, 1);
+    if (hv == NULL) return;
     for (LIS_INT i = 0; i < v->n; i++) {
-        if (format == LIS_FMT_MM) fprintf(f, "%d %28.20e\n", (int)(v->is + i + 1), (double)v->value[i]);
-        else { mmb_vec_t r; memset(&r, 0, sizeof(r)); r.i = v->is + i + 1; r.value = v->value[i]; fwrite(&r, sizeof(r), 1, f); }
+        if (format == LIS_FMT_MM) fprintf(f, "%d %28.20e\n", (int)(v->is + i + 1), (double)hv[i]);
+        else { mmb_vec_t r; memset(&r, 0, sizeof(r)); r.i = v->is + i + 1; r.value = hv[i]; fwrite(&r, sizeof(r), 1, f); }
     }
+    lisd_vec_host_done(v, hv, 0);
 }
 
 LIS_INT lis_output(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_INT format, char *path)

@@ -979,6 +979,7 @@ LIS_INT lis_matrix_merge(LIS_MATRIX A)
 /* ------------------------------------------------------------------ diagonal
  * d[i] = A(i,i): first stored (i,i) entry, 0 when absent; D->value when split
  * (src/matrix/lis_matrix_ops.c:727-780 and the per-format get_diagonal loops). */
+static LIS_INT host_get_diagonal(LIS_MATRIX A, LIS_SCALAR *v);
 LIS_INT lis_matrix_get_diagonal(LIS_MATRIX A, LIS_VECTOR d)
 {
     LIS_INT err = matrix_check(A, CHECK_ALL);
@@ -1001,8 +1002,16 @@ LIS_INT lis_matrix_get_diagonal(LIS_MATRIX A, LIS_VECTOR d)
         return lisd_sync();
     }
     /* other formats: a one-off host pass over the caller-visible arrays */
-    lisd_vec_host(d);
-    LIS_SCALAR *v = d->value;
+    LIS_SCALAR *v = lisd_vec_host_view(d, 0);
+    if (v == NULL) return LIS_ERR_OUT_OF_MEMORY;
+    err = host_get_diagonal(A, v);
+    const LIS_INT err2 = lisd_vec_host_done(d, v, err == LIS_SUCCESS);
+    return err ? err : err2;
+}
+
+static LIS_INT host_get_diagonal(LIS_MATRIX A, LIS_SCALAR *v)
+{
+    const LIS_INT n = A->n;
     if (A->is_splited) {
         for (LIS_INT i = 0; i < n; i++) v[i] = A->D->value[i];
         return LIS_SUCCESS;

@@ -268,10 +268,11 @@ LIS_INT lis_vector_gather(LIS_VECTOR v, LIS_SCALAR value[])
 
 LIS_INT lis_vector_print(LIS_VECTOR x)
 {
-    lisd_vec_host(x);
+    LIS_SCALAR *hv = lisd_vec_host_view(x, 1);
+    if (hv == NULL) return LIS_ERR_OUT_OF_MEMORY;
     for (LIS_INT i = 0; i < x->n; i++)
-        printf("%6d  %e\n", (int)(i + x->is + x->origin), (double)x->value[i]);
-    return LIS_SUCCESS;
+        printf("%6d  %e\n", (int)(i + x->is + x->origin), (double)hv[i]);
+    return lisd_vec_host_done(x, hv, 0);
 }
 
 /* ------------------------------------------------------------------ BLAS-1 on the device */

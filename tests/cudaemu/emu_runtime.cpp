@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <sys/mman.h>
 #include <ucontext.h>
+#include <execinfo.h>
+#include <signal.h>
 #include <unistd.h>
 #include <map>
 #include <set>
@@ -213,8 +215,15 @@ static void run_block(dim3 grid, dim3 block, unsigned bx)
 
 static std::map<std::string, long> g_launches;      /* kernel expression as written at the launch site -> count */
 
+/* Plain device memory (cudaMalloc) is not addressable from the host on the real machine.  Here it is host memory, so a
+ * host-side dereference would silently work; to make it fault like the real thing the pages of every cudaMalloc block
+ * are PROT_NONE except while a kernel runs or the runtime itself copies / fills (DeviceAccess).  Managed and pinned
+ * blocks stay open.  LISB_EMU_PROTECT=0 switches the protection off. */
+struct DeviceAccess { DeviceAccess(); ~DeviceAccess(); };
+
 void launch(const char *name, dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &body)
 {
+    DeviceAccess open_device;
     g_launches[name] += 1;
     if (g_running) fail("nested kernel launch");
     if (grid.y != 1 || grid.z != 1) fail("only 1-D grids are emulated");
@@ -246,11 +255,81 @@ static void *guarded_alloc(size_t bytes)
     return p;
 }
 
+static std::set<void *> g_device_only;             /* cudaMalloc blocks (keys of g_allocs) */
+static int g_device_open = 0;
+static bool protect_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("LISB_EMU_PROTECT"); on = !(e && e[0] == '0'); }
+    return on != 0;
+}
+/* with memory protection keys (x86 PKU) every device block carries one key and opening / closing the device is a
+ * register write; without them each block is mprotect'ed */
+static int g_pkey = -2;                           /* -2: not tried, -1: unavailable */
+static void device_pages(void *p, int prot)
+{
+    const Alloc &a = g_allocs[p];
+    mprotect(a.base, a.len - (size_t)sysconf(_SC_PAGESIZE), prot);
+}
+static void device_set(int prot)
+{
+    if (g_pkey >= 0) pkey_set(g_pkey, prot == PROT_NONE ? PKEY_DISABLE_ACCESS : 0);
+    else for (void *p : g_device_only) device_pages(p, prot);
+}
+DeviceAccess::DeviceAccess()
+{
+    if (g_device_open++ == 0 && protect_enabled()) device_set(PROT_READ | PROT_WRITE);
+}
+DeviceAccess::~DeviceAccess()
+{
+    if (--g_device_open == 0 && protect_enabled()) device_set(PROT_NONE);
+}
+/* a fault inside a closed device block: say so (with the host call chain) before dying with the SIGSEGV the tests expect */
+static void on_segv(int sig, siginfo_t *si, void *)
+{
+    const char *addr = (const char *)si->si_addr;
+    for (void *p : g_device_only) {
+        const Alloc &a = g_allocs[p];
+        if (addr >= (const char *)a.base && addr < (const char *)a.base + a.len) {
+            static const char msg[] = "cuda_emu: the host touched plain device memory (cudaMalloc) outside a kernel or runtime copy\n";
+            if (write(2, msg, sizeof(msg) - 1) < 0) {}
+            void *bt[32];
+            backtrace_symbols_fd(bt, backtrace(bt, 32), 2);
+            break;
+        }
+    }
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+static void *device_alloc(size_t bytes)
+{
+    static bool hooked = false;
+    if (!hooked && protect_enabled()) {
+        hooked = true;
+        struct sigaction sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.sa_sigaction = on_segv;
+        sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+        sigaction(SIGSEGV, &sa, nullptr);
+    }
+    if (g_pkey == -2 && protect_enabled()) g_pkey = pkey_alloc(0, g_device_open == 0 ? PKEY_DISABLE_ACCESS : 0);
+    void *p = guarded_alloc(bytes);
+    if (p && protect_enabled()) {
+        g_device_only.insert(p);
+        if (g_pkey >= 0) {
+            const Alloc &a = g_allocs[p];
+            if (pkey_mprotect(a.base, a.len - (size_t)sysconf(_SC_PAGESIZE), PROT_READ | PROT_WRITE, g_pkey) != 0) { fprintf(stderr, "cuda_emu: pkey_mprotect failed\n"); abort(); }
+        } else if (g_device_open == 0) device_pages(p, PROT_NONE);
+    }
+    return p;
+}
+
 static void guarded_free(void *p)
 {
     if (!p) return;
     auto it = g_allocs.find(p);
     if (it == g_allocs.end()) { fprintf(stderr, "cuda_emu: cudaFree of an unknown pointer %p\n", p); abort(); }
+    g_device_only.erase(p);
     munmap(it->second.base, it->second.len);
     g_allocs.erase(it);
 }
@@ -326,6 +405,7 @@ static void emu_flush(cudaStream_t s, cudaEvent_t upto)
             g_event_on.erase(q[k].marker);
             if (q[k].marker == upto) { ++k; break; }
         } else {
+            emu::DeviceAccess open_device;
             memmove(q[k].dst, q[k].src, q[k].n);
         }
     }
@@ -376,22 +456,22 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t e) { emu_need_event(e, "cudaEventSynchronize"); return emu_wait_event(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { emu_need_event(e, "cudaEventDestroy"); emu_wait_event(e); g_live_events.erase(e); return cudaSuccess; }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = emu::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = emu::device_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int) { *p = emu::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void *p) { emu_flush_all(); emu::guarded_free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { return cudaMalloc(p, n); }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { *p = emu::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void *p) { emu_flush_all(); emu::guarded_free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int) { *d = h; return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind, cudaStream_t st)
 {
     emu_need_stream(st, "cudaMemcpyAsync");
     if (emu_is_lazy(st)) g_lazy[st].push_back(EmuOp{d, s, n, nullptr});
-    else memmove(d, s, n);
+    else { emu::DeviceAccess open_device; memmove(d, s, n); }
     return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) { emu_flush_all(); memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { emu_need_stream(st, "cudaMemsetAsync"); memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind) { emu_flush_all(); emu::DeviceAccess open_device; memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { emu_need_stream(st, "cudaMemsetAsync"); emu::DeviceAccess open_device; memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { emu::DeviceAccess open_device; memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemPrefetchAsync(const void *, size_t, int, cudaStream_t st) { emu_need_stream(st, "cudaMemPrefetchAsync"); return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
 /* peer memory / IPC: not available here, so the in-kernel halo exchange stays off and the staged transport runs */

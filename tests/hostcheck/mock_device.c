@@ -14,6 +14,7 @@
  * build reproduces the SERIAL reference bit for bit -- which is exactly what makes it a sharp
  * check of the host control flow against the compiled reference.
  */
+#define _GNU_SOURCE
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -53,20 +54,111 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int f)
 { (void)f; if (++g_nevent >= MOCK_MAXH) abort(); g_event_live[g_nevent] = 1; *e = (cudaEvent_t)(size_t)g_nevent; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { mock_need_event(e, "cudaEventRecord"); mock_need_stream(s, "cudaEventRecord"); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { mock_need_event(e, "cudaEventDestroy"); g_event_live[(size_t)e] = 0; return cudaSuccess; }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int f) { (void)f; return cudaMalloc(p, n); }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int f) { (void)f; return cudaMalloc(p, n); }
+/* Plain device memory (cudaMalloc) cannot be dereferenced by the host on the real machine.  Here it would silently
+ * work, so its pages are PROT_NONE except while a mock "kernel" or a runtime copy / fill runs (DEV_OPEN): product host
+ * code that reads or writes such a block directly dies with SIGSEGV (and a line on stderr) instead of passing.  Managed
+ * and pinned blocks are ordinary heap memory.  MOCK_PROTECT=0 switches this off. */
+#include <sys/mman.h>
+#include <unistd.h>
+#include <signal.h>
+#include <execinfo.h>
+/* one reserved arena, page-granular first-fit with reuse of freed blocks: opening / closing the device is ONE mprotect */
+#define MOCK_ARENA ((size_t)1 << 36)
+typedef struct mock_blk { struct mock_blk *next; char *base; size_t len; int live; } mock_blk;
+static mock_blk *g_blocks = NULL;
+static char *g_arena = NULL;
+static size_t g_top = 0;
+static int g_open_depth = 0;
+static int mock_protect(void)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("MOCK_PROTECT"); on = !(e && e[0] == '0'); }
+    return on;
+}
+/* with memory protection keys (x86 PKU) the arena's pages carry one key and opening / closing is a register write;
+ * without them it is one mprotect over the used part of the arena */
+static int g_pkey = -2;                          /* -2: not tried, -1: unavailable */
+static void mock_pages(int prot)
+{
+    if (g_pkey >= 0) pkey_set(g_pkey, prot == PROT_NONE ? PKEY_DISABLE_ACCESS : 0);
+    else if (g_top) mprotect(g_arena, g_top, prot);
+}
+static int mock_open(void) { if (g_open_depth++ == 0 && mock_protect()) mock_pages(PROT_READ | PROT_WRITE); return 0; }
+static void mock_close(int *unused) { (void)unused; if (--g_open_depth == 0 && mock_protect()) mock_pages(PROT_NONE); }
+#define DEV_OPEN int dev_scope_ __attribute__((cleanup(mock_close), unused)) = mock_open()
+static void mock_on_segv(int sig, siginfo_t *si, void *ctx)
+{
+    (void)ctx;
+    const char *a = (const char *)si->si_addr;
+    if (g_arena && a >= g_arena && a < g_arena + MOCK_ARENA) {
+        static const char msg[] = "mock_device: the host touched plain device memory (cudaMalloc) outside a kernel or runtime copy\n";
+        void *bt[32];
+        if (write(2, msg, sizeof(msg) - 1) < 0) {}
+        backtrace_symbols_fd(bt, backtrace(bt, 32), 2);
+    }
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+cudaError_t cudaMalloc(void **p, size_t n)
+{
+    if (!mock_protect()) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+    if (g_arena == NULL) {
+        struct sigaction sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.sa_sigaction = mock_on_segv;
+        sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+        sigaction(SIGSEGV, &sa, NULL);
+        g_arena = (char *)mmap(NULL, MOCK_ARENA, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (g_arena == MAP_FAILED) { g_arena = NULL; *p = NULL; return cudaErrorMemoryAllocation; }
+        g_pkey = pkey_alloc(0, g_open_depth == 0 ? PKEY_DISABLE_ACCESS : 0);
+    }
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE), len = ((n ? n : 1) + page - 1) / page * page;
+    mock_blk *b;
+    for (b = g_blocks; b; b = b->next) if (!b->live && b->len >= len && b->len <= 2 * len) break;
+    if (b == NULL) {
+        if (g_top + len > MOCK_ARENA) { *p = NULL; return cudaErrorMemoryAllocation; }
+        b = (mock_blk *)malloc(sizeof(mock_blk));
+        if (b == NULL) { *p = NULL; return cudaErrorMemoryAllocation; }
+        b->base = g_arena + g_top; b->len = len; b->next = g_blocks; g_blocks = b;
+        g_top += len;
+        if (g_pkey >= 0 && pkey_mprotect(b->base, len, PROT_READ | PROT_WRITE, g_pkey) != 0) { fprintf(stderr, "mock_device: pkey_mprotect failed\n"); abort(); }
+    }
+    b->live = 1;
+    {
+        DEV_OPEN;
+        memset(b->base, 0xCD, b->len);              /* fresh device memory is not zero */
+    }
+    *p = b->base;
+    return cudaSuccess;
+}
+cudaError_t cudaMallocManaged(void **p, size_t n, unsigned int f) { (void)f; *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void *p)
+{
+    if (p == NULL) return cudaSuccess;
+    if (g_arena && (char *)p >= g_arena && (char *)p < g_arena + MOCK_ARENA) {
+        for (mock_blk *b = g_blocks; b; b = b->next)
+            if (b->base == (char *)p) {
+                if (!b->live) { fprintf(stderr, "mock_device: cudaFree of a block that is already free (%p)\n", p); abort(); }
+                b->live = 0;
+                madvise(b->base, b->len, MADV_DONTNEED);
+                return cudaSuccess;
+            }
+        fprintf(stderr, "mock_device: cudaFree of an unknown device pointer %p\n", p); abort();
+    }
+    free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int f) { (void)f; *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int f) { (void)f; *d = h; return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, enum cudaMemcpyKind k, cudaStream_t st)
-{ (void)k; mock_need_stream(st, "cudaMemcpyAsync"); memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { mock_need_stream(st, "cudaMemsetAsync"); memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+{ (void)k; mock_need_stream(st, "cudaMemcpyAsync"); DEV_OPEN; memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { mock_need_stream(st, "cudaMemsetAsync"); DEV_OPEN; memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { DEV_OPEN; memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemPrefetchAsync(const void *p, size_t n, int dev, cudaStream_t st) { (void)p; (void)n; (void)dev; (void)st; return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = *t = (size_t)1 << 40; return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind k) { (void)k; memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, enum cudaMemcpyKind k) { (void)k; DEV_OPEN; memmove(d, s, n); return cudaSuccess; }
 /* peer memory / IPC: not available here, so the in-kernel halo exchange stays off and the staged transport runs */
 cudaError_t cudaDeviceGetPCIBusId(char *b, int len, int dev) { (void)dev; if (len > 0) b[0] = 0; return cudaErrorNotSupported; }
 cudaError_t cudaDeviceGetByPCIBusId(int *dev, const char *b) { (void)b; *dev = -1; return cudaErrorNotSupported; }
@@ -78,31 +170,31 @@ cudaError_t cudaIpcCloseMemHandle(void *p) { (void)p; return cudaErrorNotSupport
 
 
 /* ------------------------------------------------------------------ kernel C-ABI on the oracle */
-int lisb200_sm_count(void) { return 1; }
+int lisb200_sm_count(void) { DEV_OPEN; return 1; }
 const char *lisb200_error_string(int code) { (void)code; return "mock device error"; }
-int lisb200_reduce_slots(void) { return 16; }
-int lisb200_spmv_csr_dot_slots(int n) { (void)n; return 16; }
+int lisb200_reduce_slots(void) { DEV_OPEN; return 16; }
+int lisb200_spmv_csr_dot_slots(int n) { DEV_OPEN; (void)n; return 16; }
 
 int lisb200_spmv_csr(int n, const int *p, const int *i, const double *v, const double *x, double *y, void *s)
-{ (void)s; if (n > 0) orc_spmv_csr(n, p, i, v, x, y); return 0; }
+{ DEV_OPEN; (void)s; if (n > 0) orc_spmv_csr(n, p, i, v, x, y); return 0; }
 int lisb200_spmv_csr_tma_plan(int n, const int *h_ptr, int *r, int *t, int *st)
-{ (void)n; (void)h_ptr; (void)r; (void)t; (void)st; return 1; }     /* the mock has one CSR "kernel" */
+{ DEV_OPEN; (void)n; (void)h_ptr; (void)r; (void)t; (void)st; return 1; }     /* the mock has one CSR "kernel" */
 int lisb200_spmv_csr_tma(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y, void *s)
-{ (void)r; (void)t; (void)st; return lisb200_spmv_csr(n, p, i, v, x, y, s); }
+{ DEV_OPEN; (void)r; (void)t; (void)st; return lisb200_spmv_csr(n, p, i, v, x, y, s); }
 int lisb200_spmv_csr_split(int n, const double *d, const int *lp, const int *li, const double *lv,
                            const int *up, const int *ui, const double *uv, const double *x, double *y, void *s)
-{ (void)s; if (n > 0) orc_spmv_csr_split(n, d, lp, li, lv, up, ui, uv, x, y); return 0; }
+{ DEV_OPEN; (void)s; if (n > 0) orc_spmv_csr_split(n, d, lp, li, lv, up, ui, uv, x, y); return 0; }
 int lisb200_spmv_csr_dot(int n, const int *p, const int *i, const double *v, const double *x, double *y,
                          double *partial, unsigned int *counter, double *result, void *s)
-{ (void)partial; (void)counter; lisb200_spmv_csr(n, p, i, v, x, y, s); *result = orc_dot(n, x, y, 1); return 0; }
+{ DEV_OPEN; (void)partial; (void)counter; lisb200_spmv_csr(n, p, i, v, x, y, s); *result = orc_dot(n, x, y, 1); return 0; }
 int lisb200_spmv_csr_tma_dot(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y,
                              double *partial, unsigned int *counter, double *result, void *s)
-{ (void)r; (void)t; (void)st; return lisb200_spmv_csr_dot(n, p, i, v, x, y, partial, counter, result, s); }
+{ DEV_OPEN; (void)r; (void)t; (void)st; return lisb200_spmv_csr_dot(n, p, i, v, x, y, partial, counter, result, s); }
 int lisb200_spmv_csr_tma_dot_rows(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y,
                                   const double *dotx, double *partial, unsigned int *counter, double *result, void *s)
-{ (void)r; (void)t; (void)st; (void)partial; (void)counter; lisb200_spmv_csr(n, p, i, v, x, y, s); *result = n > 0 ? orc_dot(n, dotx, y, 1) : 0.0; return 0; }
+{ DEV_OPEN; (void)r; (void)t; (void)st; (void)partial; (void)counter; lisb200_spmv_csr(n, p, i, v, x, y, s); *result = n > 0 ? orc_dot(n, dotx, y, 1) : 0.0; return 0; }
 int lisb200_spmv_ell(int n, int m, int ld, const int *i, const double *v, const double *x, double *y, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     for (int r = 0; r < n; r++) y[r] = 0.0;
     for (int j = 0; j < m; j++)
@@ -110,7 +202,7 @@ int lisb200_spmv_ell(int n, int m, int ld, const int *i, const double *v, const 
     return 0;
 }
 int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *off, const double *v, const double *x, double *y, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     for (int r = 0; r < n; r++) y[r] = 0.0;
     for (int j = 0; j < nnd; j++) {
@@ -121,9 +213,9 @@ int lisb200_spmv_dia(int n, int xlen, int nnd, int ld, const int *off, const dou
     return 0;
 }
 int lisb200_spmv_jad(int n, int m, const int *jp, const int *perm, const int *i, const double *v, const double *x, double *y, void *s)
-{ (void)s; if (n > 0) orc_spmv_jad(n, m, jp, perm, i, v, x, y, 1); return 0; }
+{ DEV_OPEN; (void)s; if (n > 0) orc_spmv_jad(n, m, jp, perm, i, v, x, y, 1); return 0; }
 int lisb200_spmv_bsr_cols(int n, int ncols, int nr, int bnr, int bnc, const int *bp, const int *bi, const double *v, const double *x, double *y, void *s)
-{
+{ DEV_OPEN;
     /* like the kernels, never read x beyond the vector: entries of a padded last block column are
      * structural zeros, but x[...] behind them does not exist */
     (void)s;
@@ -142,24 +234,24 @@ int lisb200_spmv_bsr_cols(int n, int ncols, int nr, int bnr, int bnc, const int 
     return 0;
 }
 
-int lisb200_copy(int n, const double *x, double *y, void *s) { (void)s; memmove(y, x, sizeof(double) * (size_t)(n > 0 ? n : 0)); return 0; }
-int lisb200_axpy(int n, double a, const double *x, double *y, void *s) { (void)s; orc_axpy(n, a, x, y); return 0; }
-int lisb200_axpy_dev(int n, const double *da, double sc, const double *x, double *y, void *s) { (void)s; orc_axpy(n, sc * *da, x, y); return 0; }
-int lisb200_xpay(int n, const double *x, double a, double *y, void *s) { (void)s; orc_xpay(n, x, a, y); return 0; }
-int lisb200_axpyz(int n, double a, const double *x, const double *y, double *z, void *s) { (void)s; orc_axpyz(n, a, x, y, z); return 0; }
-int lisb200_scale(int n, double a, double *x, void *s) { (void)s; orc_scale(n, a, x); return 0; }
-int lisb200_pmul(int n, const double *x, const double *y, double *z, void *s) { (void)s; orc_pmul(n, x, y, z); return 0; }
-int lisb200_pdiv(int n, const double *x, const double *y, double *z, void *s) { (void)s; orc_pdiv(n, x, y, z); return 0; }
-int lisb200_set_all(int n, double a, double *x, void *s) { (void)s; for (int i = 0; i < n; i++) x[i] = a; return 0; }
-int lisb200_abs(int n, double *x, void *s) { (void)s; orc_abs(n, x); return 0; }
-int lisb200_reciprocal(int n, double *x, void *s) { (void)s; orc_reciprocal(n, x); return 0; }
-int lisb200_shift(int n, double g, double *x, void *s) { (void)s; orc_shift(n, g, x); return 0; }
-int lisb200_swap(int n, double *x, double *y, void *s) { (void)s; for (int i = 0; i < n; i++) { double t = x[i]; x[i] = y[i]; y[i] = t; } return 0; }
-int lisb200_gather(int c, const int *idx, const double *x, double *out, void *s) { (void)s; for (int i = 0; i < c; i++) out[i] = x[idx[i]]; return 0; }
-int lisb200_scatter_add(int c, const int *idx, const double *src, double *y, void *s) { (void)s; for (int i = 0; i < c; i++) y[idx[i]] += src[i]; return 0; }
+int lisb200_copy(int n, const double *x, double *y, void *s) { DEV_OPEN; (void)s; memmove(y, x, sizeof(double) * (size_t)(n > 0 ? n : 0)); return 0; }
+int lisb200_axpy(int n, double a, const double *x, double *y, void *s) { DEV_OPEN; (void)s; orc_axpy(n, a, x, y); return 0; }
+int lisb200_axpy_dev(int n, const double *da, double sc, const double *x, double *y, void *s) { DEV_OPEN; (void)s; orc_axpy(n, sc * *da, x, y); return 0; }
+int lisb200_xpay(int n, const double *x, double a, double *y, void *s) { DEV_OPEN; (void)s; orc_xpay(n, x, a, y); return 0; }
+int lisb200_axpyz(int n, double a, const double *x, const double *y, double *z, void *s) { DEV_OPEN; (void)s; orc_axpyz(n, a, x, y, z); return 0; }
+int lisb200_scale(int n, double a, double *x, void *s) { DEV_OPEN; (void)s; orc_scale(n, a, x); return 0; }
+int lisb200_pmul(int n, const double *x, const double *y, double *z, void *s) { DEV_OPEN; (void)s; orc_pmul(n, x, y, z); return 0; }
+int lisb200_pdiv(int n, const double *x, const double *y, double *z, void *s) { DEV_OPEN; (void)s; orc_pdiv(n, x, y, z); return 0; }
+int lisb200_set_all(int n, double a, double *x, void *s) { DEV_OPEN; (void)s; for (int i = 0; i < n; i++) x[i] = a; return 0; }
+int lisb200_abs(int n, double *x, void *s) { DEV_OPEN; (void)s; orc_abs(n, x); return 0; }
+int lisb200_reciprocal(int n, double *x, void *s) { DEV_OPEN; (void)s; orc_reciprocal(n, x); return 0; }
+int lisb200_shift(int n, double g, double *x, void *s) { DEV_OPEN; (void)s; orc_shift(n, g, x); return 0; }
+int lisb200_swap(int n, double *x, double *y, void *s) { DEV_OPEN; (void)s; for (int i = 0; i < n; i++) { double t = x[i]; x[i] = y[i]; y[i] = t; } return 0; }
+int lisb200_gather(int c, const int *idx, const double *x, double *out, void *s) { DEV_OPEN; (void)s; for (int i = 0; i < c; i++) out[i] = x[idx[i]]; return 0; }
+int lisb200_scatter_add(int c, const int *idx, const double *src, double *y, void *s) { DEV_OPEN; (void)s; for (int i = 0; i < c; i++) y[idx[i]] += src[i]; return 0; }
 
 int lisb200_reduce(int kind, int n, const double *x, const double *y, double *partial, unsigned int *counter, double *result, void *s)
-{
+{ DEV_OPEN;
     (void)partial; (void)counter; (void)s;
     switch (kind) {
     case 0: *result = orc_dot(n, x, y, 1); break;
@@ -172,41 +264,41 @@ int lisb200_reduce(int kind, int n, const double *x, const double *y, double *pa
     return 0;
 }
 int lisb200_dot2(int n, const double *a, const double *b, double *partial, unsigned int *counter, double *r2, void *s)
-{ (void)partial; (void)counter; (void)s; r2[0] = orc_dot(n, a, b, 1); r2[1] = orc_dot(n, a, a, 1); return 0; }
+{ DEV_OPEN; (void)partial; (void)counter; (void)s; r2[0] = orc_dot(n, a, b, 1); r2[1] = orc_dot(n, a, a, 1); return 0; }
 int lisb200_cg_update(int n, double alpha, const double *p, const double *q, double *x, double *r,
                       double *partial, unsigned int *counter, double *rr, void *s)
-{ (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); *rr = orc_dot(n, r, r, 1); return 0; }
+{ DEV_OPEN; (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); *rr = orc_dot(n, r, r, 1); return 0; }
 int lisb200_cg_update_jacobi(int n, double alpha, const double *p, const double *q, double *x, double *r, const double *dinv, double *z,
                              double *partial, unsigned int *counter, double *rr_rho, void *s)
-{
+{ DEV_OPEN;
     (void)partial; (void)counter; (void)s;
     orc_axpy(n, alpha, p, x); orc_axpy(n, -alpha, q, r); rr_rho[0] = orc_dot(n, r, r, 1);
     orc_pmul(n, r, dinv, z); rr_rho[1] = orc_dot(n, r, z, 1);
     return 0;
 }
 int lisb200_jacobi_dot(int n, const double *r, const double *dinv, double *z, double *partial, unsigned int *counter, double *rho, void *s)
-{ (void)partial; (void)counter; (void)s; orc_pmul(n, r, dinv, z); *rho = orc_dot(n, r, z, 1); return 0; }
+{ DEV_OPEN; (void)partial; (void)counter; (void)s; orc_pmul(n, r, dinv, z); *rho = orc_dot(n, r, z, 1); return 0; }
 int lisb200_mgs_step(int norm, int n, const double *da, double sc, const double *v, double *w, const double *u,
                      double *partial, unsigned int *counter, double *result, void *s)
-{ (void)partial; (void)counter; (void)s; orc_axpy(n, da ? sc * *da : sc, v, w); *result = orc_dot(n, w, norm ? w : u, 1); return 0; }
+{ DEV_OPEN; (void)partial; (void)counter; (void)s; orc_axpy(n, da ? sc * *da : sc, v, w); *result = orc_dot(n, w, norm ? w : u, 1); return 0; }
 int lisb200_bicgstab_p(int n, double omega, double beta, const double *v, const double *r, double *p, void *s)
-{ (void)s; orc_axpy(n, -omega, v, p); orc_xpay(n, r, beta, p); return 0; }
+{ DEV_OPEN; (void)s; orc_axpy(n, -omega, v, p); orc_xpay(n, r, beta, p); return 0; }
 int lisb200_bicgstab_update(int n, double alpha, double omega, const double *phat, const double *shat, const double *t,
                             double *x, double *r, double *partial, unsigned int *counter, double *rr, void *s)
-{ (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, phat, x); orc_axpy(n, omega, shat, x); orc_axpy(n, -omega, t, r); *rr = orc_dot(n, r, r, 1); return 0; }
+{ DEV_OPEN; (void)partial; (void)counter; (void)s; orc_axpy(n, alpha, phat, x); orc_axpy(n, omega, shat, x); orc_axpy(n, -omega, t, r); *rr = orc_dot(n, r, r, 1); return 0; }
 int lisb200_csr_shift_diagonal(int n, const int *p, const int *ix, double *v, double sigma, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     for (int i = 0; i < n; i++)
         for (int j = p[i]; j < p[i + 1]; j++) if (ix[j] == i) { v[j] -= sigma; break; }
     return 0;
 }
 int lisb200_csr_get_diagonal(int n, const int *p, const int *i, const double *v, double *d, void *s)
-{ (void)s; if (n > 0) orc_csr_get_diagonal(n, p, i, v, d); return 0; }
+{ DEV_OPEN; (void)s; if (n > 0) orc_csr_get_diagonal(n, p, i, v, d); return 0; }
 
 int lisb200_ssor_forward_level(int nrows, const int *rows, const int *lp, const int *li, const double *lv,
                                const double *wd, const int *bs, const double *b, double *x, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     for (int k = 0; k < nrows; k++) {
         const int i = rows[k];
@@ -218,7 +310,7 @@ int lisb200_ssor_forward_level(int nrows, const int *rows, const int *lp, const 
 }
 int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const int *ui, const double *uv,
                                 const double *wd, const int *bs, const int *be, double *x, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     for (int k = 0; k < nrows; k++) {
         const int i = rows[k];
@@ -229,12 +321,12 @@ int lisb200_ssor_backward_level(int nrows, const int *rows, const int *up, const
     return 0;
 }
 int lisb200_spmv_bsr(int n, int nr, int bnr, int bnc, const int *bp, const int *bi, const double *v, const double *x, double *y, void *s)
-{ return lisb200_spmv_bsr_cols(n, n, nr, bnr, bnc, bp, bi, v, x, y, s); }
+{ DEV_OPEN; return lisb200_spmv_bsr_cols(n, n, nr, bnr, bnc, bp, bi, v, x, y, s); }
 /* slots are in dependency (level) order, so a sequential walk is a valid schedule */
 int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int *wptr, const int *plen, const int *wdep,
                        const int *sidx, const double *sval, const double *wd, const double *in, double *out, double *scratch,
                        unsigned int *ticket, int ctas, void *s)
-{
+{ DEV_OPEN;
     (void)ticket; (void)s; (void)ctas; (void)wdep;
     double *pout = scratch;
     for (int i = 0; i < n; i++) out[i] = NAN;
@@ -257,7 +349,7 @@ int lisb200_sweep_sell(int mode, int n, int nslots, const int *order, const int 
 
 int lisb200_sweep_rows(int mode, int n, int nslots, const int *order, const int *rptr, const int *rdep, const int *ridx, const double *rval,
                        const double *wd, const double *in, double *out, double *scratch, unsigned int *ticket, int ctas, void *s)
-{
+{ DEV_OPEN;
     (void)ticket; (void)s; (void)ctas; (void)rdep;
     double *pout = scratch;
     for (int i = 0; i < n; i++) out[i] = NAN;
@@ -277,16 +369,16 @@ int lisb200_sweep_rows(int mode, int n, int nslots, const int *order, const int 
 }
 int lisb200_spmv_csr_tma_p2p(int n, int r, int t, int st, const int *p, const int *i, const double *v, const double *x, double *y, int dot,
                              double *part, unsigned int *cnt, double *res, const lisb200_p2p *tb, unsigned long long ep, int lo, int hi, void *s)
-{ (void)n; (void)r; (void)t; (void)st; (void)p; (void)i; (void)v; (void)x; (void)y; (void)dot; (void)part; (void)cnt; (void)res; (void)tb; (void)ep; (void)lo; (void)hi; (void)s;
+{ DEV_OPEN; (void)n; (void)r; (void)t; (void)st; (void)p; (void)i; (void)v; (void)x; (void)y; (void)dot; (void)part; (void)cnt; (void)res; (void)tb; (void)ep; (void)lo; (void)hi; (void)s;
   return 1; }                     /* never reached: the mock runtime offers no peer memory */
 
 /* ---- device-side format conversion (kernels/convert.cu): plain sequential restatements ---- */
 int lisb200_csr_rows_unsorted(int n, const int *p, const int *ix, int *out, void *s)
-{ (void)s; *out = 0; for (int i = 0; i < n; i++) for (int j = p[i] + 1; j < p[i + 1]; j++) if (ix[j - 1] > ix[j]) *out = 1; return 0; }
+{ DEV_OPEN; (void)s; *out = 0; for (int i = 0; i < n; i++) for (int j = p[i] + 1; j < p[i + 1]; j++) if (ix[j - 1] > ix[j]) *out = 1; return 0; }
 int lisb200_csr_max_row_len(int n, const int *p, int *out, void *s)
-{ (void)s; int m = 0; for (int i = 0; i < n; i++) if (p[i + 1] - p[i] > m) m = p[i + 1] - p[i]; *out = m; return 0; }
+{ DEV_OPEN; (void)s; int m = 0; for (int i = 0; i < n; i++) if (p[i + 1] - p[i] > m) m = p[i + 1] - p[i]; *out = m; return 0; }
 int lisb200_csr2ell(int n, int m, int ld, const int *p, const int *ix, const double *v, int *ei, double *ev, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     for (int i = 0; i < n; i++)
         for (int j = 0; j < m; j++) {
@@ -295,9 +387,9 @@ int lisb200_csr2ell(int n, int m, int ld, const int *p, const int *ix, const dou
         }
     return 0;
 }
-int lisb200_dia_segments(int n, int np) { return (int)(((long long)n + np + 1023) / 1024); }
+int lisb200_dia_segments(int n, int np) { DEV_OPEN; return (int)(((long long)n + np + 1023) / 1024); }
 int lisb200_csr2dia_mark(int n, int np, const int *p, const int *ix, unsigned char *f, int *sc, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     const long long span = (long long)n + np;
     memset(f, 0, (size_t)span);
@@ -311,7 +403,7 @@ int lisb200_csr2dia_mark(int n, int np, const int *p, const int *ix, unsigned ch
 }
 int lisb200_csr2dia_fill(int n, int np, int nnd, int ld, const int *p, const int *ix, const double *v, const unsigned char *f,
                          const int *sb, const int *sc, int *off, double *dv, void *s)
-{
+{ DEV_OPEN;
     (void)s; (void)sb; (void)sc;
     int k = 0;
     for (long long q = 0; q < (long long)n + np; q++) if (f[q]) off[k++] = (int)(q - n);
@@ -325,10 +417,10 @@ int lisb200_csr2dia_fill(int n, int np, int nnd, int ld, const int *p, const int
     }
     return 0;
 }
-int lisb200_jad_ctas(int n) { return n > 0 ? (n + 4095) / 4096 : 0; }
-int lisb200_jad_bins(void) { return 256; }
+int lisb200_jad_ctas(int n) { DEV_OPEN; return n > 0 ? (n + 4095) / 4096 : 0; }
+int lisb200_jad_bins(void) { DEV_OPEN; return 256; }
 int lisb200_csr2jad_hist(int n, int m, const int *p, int *tab, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     memset(tab, 0, sizeof(int) * 256 * (size_t)lisb200_jad_ctas(n));
     for (int i = 0; i < n; i++) tab[(size_t)(i / 4096) * 256 + (m - (p[i + 1] - p[i]))]++;
@@ -336,7 +428,7 @@ int lisb200_csr2jad_hist(int n, int m, const int *p, int *tab, void *s)
 }
 int lisb200_csr2jad_fill(int n, int m, const int *p, const int *ix, const double *v, const int *base, const int *jp,
                          int *perm, int *ji, double *jv, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     int *run = (int *)malloc(sizeof(int) * 256 * (size_t)(lisb200_jad_ctas(n) + 1));
     memcpy(run, base, sizeof(int) * 256 * (size_t)lisb200_jad_ctas(n));
@@ -346,7 +438,7 @@ int lisb200_csr2jad_fill(int n, int m, const int *p, const int *ix, const double
         for (int j = 0; j < p[perm[q] + 1] - p[perm[q]]; j++) { ji[jp[j] + q] = ix[p[perm[q]] + j]; jv[jp[j] + q] = v[p[perm[q]] + j]; }
     return 0;
 }
-int lisb200_bsr_max_blocks(void) { return 64; }
+int lisb200_bsr_max_blocks(void) { DEV_OPEN; return 64; }
 static int mock_bsr_row(int n, int bi, int bnr, int bnc, const int *p, const int *ix, int *seen)
 {
     int cnt = 0;
@@ -359,7 +451,7 @@ static int mock_bsr_row(int n, int bi, int bnr, int bnc, const int *p, const int
     return cnt;
 }
 int lisb200_csr2bsr_count(int n, int nr, int bnr, int bnc, const int *p, const int *ix, int *count, int *over, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     int seen[64];
     *over = 0;
@@ -368,7 +460,7 @@ int lisb200_csr2bsr_count(int n, int nr, int bnr, int bnc, const int *p, const i
 }
 int lisb200_csr2bsr_fill(int n, int nr, int bnr, int bnc, const int *p, const int *ix, const double *v, const int *bp,
                          int *bi_out, double *bv, void *s)
-{
+{ DEV_OPEN;
     (void)s;
     const int bs = bnr * bnc;
     for (int bi = 0; bi < nr; bi++) {

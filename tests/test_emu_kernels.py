@@ -115,7 +115,7 @@ vp = C.c_void_p
 def dev(a):
     p = vp()
     assert lib.cudaMalloc(C.byref(p), C.c_size_t(a.nbytes)) == 0
-    C.memmove(p, a.ctypes.data, a.nbytes)
+    assert lib.cudaMemcpy(p, vp(a.ctypes.data), C.c_size_t(a.nbytes), 1) == 0
     return p
 n = 300
 ptr = np.arange(0, 3 * n + 1, 3, dtype=np.int32)
@@ -130,13 +130,20 @@ if what == "misaligned_ptr":
     d_ptr = vp(d_ptr.value + 4)
 rc = lib.lisb200_spmv_csr_tma(n - (1 if what == "misaligned_ptr" else 0), 256, 1024, 2, d_ptr, d_idx, d_val, d_x, d_y, None)
 print("rc", rc)
+if what == "host_deref":
+    print((C.c_double * n).from_address(d_y.value)[0])      # plain device memory read from the host
+if what == "ok":
+    back = np.zeros(n); assert lib.cudaMemcpy(vp(back.ctypes.data), d_y, C.c_size_t(back.nbytes), 2) == 0
+    assert (back == 3.0).all()
 """
 
 
-@pytest.mark.parametrize("what,expect", [("ok", 0), ("misaligned_ptr", "abort"), ("short_y", "segv")])
+@pytest.mark.parametrize("what,expect", [("ok", 0), ("misaligned_ptr", "abort"), ("short_y", "segv"), ("host_deref", "segv")])
 def test_emulator_catches_misalignment_and_overrun(b200, what, expect):
     """a TMA bulk copy from a 4-byte-aligned row-pointer slice aborts; an output vector
-    that is 8 entries short makes the kernel write into the guard page behind it"""
+    that is 8 entries short makes the kernel write into the guard page behind it; the host
+    reading a cudaMalloc block directly faults (its pages are open only while a kernel or a
+    runtime copy runs)"""
     import signal
     import sys
     r = subprocess.run([sys.executable, "-c", _NEG, os.path.join(EMU_DIR, "_build", "liblis_emu.so"), what],
