@@ -197,8 +197,9 @@ int lisb200_csr_get_diagonal(int n, const int *d_ptr, const int *d_idx, const do
  * the host between the two launches of a conversion.                                            */
 /* *d_out = longest row (ELL maxnzr, JAD maxnzr)            src/matrix/lis_matrix_ell.c:1000-1012 */
 int lisb200_csr_max_row_len(int n, const int *d_ptr, int *d_out, void *stream);
-/* *d_out = 1 when some row has its columns out of ascending order (the post-condition of lis_matrix_sort_csr,
- * src/matrix/lis_matrix_csr.c:1486-1521), else 0: lets the DIA conversion skip the host sort of an input that is sorted */
+/* *d_out = 1 when some row has its columns out of STRICTLY ascending order (the post-condition of lis_matrix_sort_csr,
+ * src/matrix/lis_matrix_csr.c:1486-1521, for a matrix without repeated columns), else 0: lets the DIA conversion skip the
+ * host sort of an input that is sorted; a repeated column takes the host sort, which decides which copy DIA keeps */
 int lisb200_csr_rows_unsorted(int n, const int *d_ptr, const int *d_idx, int *d_out, void *stream);
 /* ELL: d_eval[j*ld+i], d_eidx[j*ld+i], unused slots (0.0, i)  src/matrix/lis_matrix_ell.c:1035-1052 */
 int lisb200_csr2ell(int n, int maxnzr, int ld, const int *d_ptr, const int *d_idx, const double *d_val,

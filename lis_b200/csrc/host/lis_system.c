@@ -355,23 +355,51 @@ DEFINE_HEAPSORT(lis_sort_i, NO_DECL, NO_SWAP, LESS)
 
 #define D_DECL , LIS_SCALAR *d1
 #define D_SWAP(i, j) { LIS_SCALAR *d_ = d1 + is; LIS_SCALAR s_ = d_[i]; d_[i] = d_[j]; d_[j] = s_; }
-DEFINE_HEAPSORT(lis_sort_id_heap, D_DECL, D_SWAP, LESS)
 
 #define I_DECL , LIS_INT *i2
 #define I_SWAP(i, j) { LIS_INT *b_ = i2 + is; LIS_INT s_ = b_[i]; b_[i] = b_[j]; b_[j] = s_; }
 DEFINE_HEAPSORT(lis_sort_ii, I_DECL, I_SWAP, LESS)
 DEFINE_HEAPSORT(lis_sortr_ii, I_DECL, I_SWAP, GREATER)
 
-/* rows of sparse matrices are short: insertion sort first, heap sort for long ones */
+/* Keys ascending, the satellite carried along.  Rows of sparse matrices mostly arrive strictly ascending: one pass
+ * and out.  Otherwise the partition scheme is the reference's (src/system/lis_sort.c:90-118: the middle element is
+ * parked at the end and is the pivot value, a two-sided scan swaps out-of-place pairs, both sides are sorted the same
+ * way), because among EQUAL keys the final order is a property of the scheme: a row that stores a column twice must end
+ * with the same copy last as there -- CSR -> DIA / VBR keep that one.  Explicit stack, smaller side first. */
 void lis_sort_id(LIS_INT is, LIS_INT ie, LIS_INT *i1, LIS_SCALAR *d1)
 {
-    const LIS_INT n = ie - is + 1;
-    if (n < 2) return;
-    if (n > 64) { lis_sort_id_heap(is, ie, i1, d1); return; }
-    for (LIS_INT j = is + 1; j <= ie; j++) {
-        const LIS_INT c = i1[j]; const LIS_SCALAR v = d1[j];
-        LIS_INT k = j - 1;
-        while (k >= is && i1[k] > c) { i1[k + 1] = i1[k]; d1[k + 1] = d1[k]; k--; }
-        i1[k + 1] = c; d1[k + 1] = v;
+    if (ie <= is) return;
+    LIS_INT k = is + 1;
+    while (k <= ie && i1[k - 1] < i1[k]) k++;
+    if (k > ie) return;
+    LIS_INT lo_stack[96], hi_stack[96];
+    int top = 0;
+    lo_stack[0] = is; hi_stack[0] = ie; top = 1;
+    while (top > 0) {
+        LIS_INT lo = lo_stack[--top], hi = hi_stack[top];
+        while (lo < hi) {
+            const LIS_INT mid = (lo + hi) / 2;
+            const LIS_INT pivot = i1[mid];
+            { const LIS_INT t = i1[mid]; i1[mid] = i1[hi]; i1[hi] = t; }
+            { const LIS_SCALAR t = d1[mid]; d1[mid] = d1[hi]; d1[hi] = t; }
+            LIS_INT i = lo, j = hi;
+            while (i <= j) {
+                while (i1[i] < pivot) i++;
+                while (i1[j] > pivot) j--;
+                if (i <= j) {
+                    const LIS_INT t = i1[i]; i1[i] = i1[j]; i1[j] = t;
+                    const LIS_SCALAR u = d1[i]; d1[i] = d1[j]; d1[j] = u;
+                    i++; j--;
+                }
+            }
+            /* [lo, j] and [i, hi] remain; the larger one waits on the stack */
+            if (j - lo < hi - i) {
+                if (i < hi) { lo_stack[top] = i; hi_stack[top] = hi; top++; }
+                hi = j;
+            } else {
+                if (lo < j) { lo_stack[top] = lo; hi_stack[top] = j; top++; }
+                lo = i;
+            }
+        }
     }
 }

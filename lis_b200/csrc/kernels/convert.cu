@@ -288,14 +288,16 @@ static int cv_sm_count() {
     return sms;
 }
 
-// *unsorted = 1 if some row's columns are not ascending (lis_matrix_sort_csr's post-condition, src/matrix/lis_matrix_csr.c:1486)
+// *unsorted = 1 if some row's columns are not STRICTLY ascending.  A repeated column also sends the matrix through the host
+// sort (lis_matrix_sort_csr, src/matrix/lis_matrix_csr.c:1486): which of the copies ends last is a property of that sort,
+// and the DIA conversion keeps the last one.
 __global__ void __launch_bounds__(kCvThreads)
 csr_unsorted_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ idx, int *unsorted)
 {
     const int stride = gridDim.x * blockDim.x;
     int bad = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        for (int j = ptr[i] + 1; j < ptr[i + 1]; ++j) bad |= idx[j - 1] > idx[j];
+        for (int j = ptr[i] + 1; j < ptr[i + 1]; ++j) bad |= idx[j - 1] >= idx[j];
     if (bad) *unsorted = 1;
 }
 

@@ -374,7 +374,7 @@ int lisb200_spmv_csr_tma_p2p(int n, int r, int t, int st, const int *p, const in
 
 /* ---- device-side format conversion (kernels/convert.cu): plain sequential restatements ---- */
 int lisb200_csr_rows_unsorted(int n, const int *p, const int *ix, int *out, void *s)
-{ DEV_OPEN; (void)s; *out = 0; for (int i = 0; i < n; i++) for (int j = p[i] + 1; j < p[i + 1]; j++) if (ix[j - 1] > ix[j]) *out = 1; return 0; }
+{ DEV_OPEN; (void)s; *out = 0; for (int i = 0; i < n; i++) for (int j = p[i] + 1; j < p[i + 1]; j++) if (ix[j - 1] >= ix[j]) *out = 1; return 0; }
 int lisb200_csr_max_row_len(int n, const int *p, int *out, void *s)
 { DEV_OPEN; (void)s; int m = 0; for (int i = 0; i < n; i++) if (p[i + 1] - p[i] > m) m = p[i + 1] - p[i]; *out = m; return 0; }
 int lisb200_csr2ell(int n, int m, int ld, const int *p, const int *ix, const double *v, int *ei, double *ev, void *s)

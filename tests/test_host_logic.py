@@ -435,13 +435,26 @@ def test_option_parsing_matches_reference(b200, ref_serial):
 
 
 def test_sort_id_matches_reference(b200, ref_serial):
+    """also among EQUAL keys: the order the satellites end in is a property of the reference's partition scheme
+    (src/system/lis_sort.c:90-118), and CSR -> DIA / VBR keep the copy that ends last"""
     rng = np.random.default_rng(2)
     for n in (0, 1, 2, 7, 64, 65, 500):
-        keys = rng.permutation(n * 3)[:n]           # distinct keys: the order of duplicates is unspecified
+        keys = rng.permutation(n * 3)[:n]
         vals = rng.standard_normal(n)
         gk, gv = b200.sort_id(keys, vals)
         rk, rv = ref_serial.sort_id(keys, vals)
         assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
+    for t in range(400):
+        n = int(rng.integers(1, 300))
+        keys = rng.integers(0, int(rng.integers(1, 400)), n).astype(np.int32)
+        if t % 5 == 0:
+            keys = np.sort(keys)
+        if t % 7 == 0:
+            keys = np.sort(keys)[::-1].copy()
+        vals = rng.standard_normal(n)
+        gk, gv = b200.sort_id(keys, vals)
+        rk, rv = ref_serial.sort_id(keys, vals)
+        assert np.array_equal(gk, rk) and np.array_equal(gv, rv), (t, n)
 
 
 def test_error_codes_host_side(built):

@@ -151,6 +151,28 @@ def test_system_scaling_in_other_formats(hc, ref_serial, fmt):
         assert np.abs(g["x"] - r["x"]).max() < 1e-9, opts
 
 
+def test_duplicate_entries_keep_the_reference_copy(hc, ref_serial):
+    """a CSR matrix that stores the same (i, j) more than once, rows unsorted: CSR/ELL/JAD/COO/CSC/BSR/BSC/DNS products
+    add every copy in storage order, DIA and VBR keep ONE copy -- whichever the row sort leaves last, which is why
+    lis_sort_id follows the reference's partition scheme.  (MSR: the reference reads past its arrays on a duplicated
+    diagonal entry; not compared.)"""
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        n = 57 + trial * 13
+        ptr, idx, val = [0], [], []
+        for i in range(n):
+            cols = rng.integers(max(0, i - 6), min(n, i + 7), int(rng.integers(1, 9)))
+            cols = np.concatenate([cols, cols[:int(rng.integers(0, 3))]])
+            rng.shuffle(cols)
+            idx += list(cols); val += list(rng.standard_normal(len(cols))); ptr.append(len(idx))
+        ptr, idx, val = np.array(ptr, np.int32), np.array(idx, np.int32), np.array(val)
+        x = rng.standard_normal(n)
+        for fmt in ("csr", "ell", "jad", "dia", "vbr", "coo", "bsr", "csc", "bsc", "dns"):
+            g = hc.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2)
+            r = ref_serial.spmv(fmt, ptr, idx, val, x, bnr=2, bnc=2)
+            H.assert_bits_equal(g[0], r[0], f"duplicates trial {trial} {fmt}")
+
+
 @pytest.mark.parametrize("fmt", FORMATS)
 def test_solve_in_every_storage_format(hc, ref_serial, fmt):
     """-storage converts the matrix in place before the solve (lis_matrix_convert_self); the matrix
