@@ -742,17 +742,31 @@ LIS_INT lis_matrix_scale(LIS_MATRIX A, LIS_VECTOR B, LIS_VECTOR Dv, LIS_INT acti
     if (err) return err;
     const LIS_INT mt = A->matrix_type;
     const int other_fmt = mt == LIS_MATRIX_ELL || mt == LIS_MATRIX_DIA || mt == LIS_MATRIX_JAD || mt == LIS_MATRIX_BSR || mt == LIS_MATRIX_CSC;
-    if ((mt != LIS_MATRIX_CSR && !(other_fmt && !A->is_splited)) || A->nprocs > 1) {
-        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale needs a CSR, CSC, ELL, DIA, JAD or BSR matrix on one process\n");
+    if ((mt != LIS_MATRIX_CSR && !(other_fmt && !A->is_splited)) || (A->nprocs > 1 && mt != LIS_MATRIX_CSR)) {
+        LIS_SETERR(LIS_ERR_NOT_IMPLEMENTED, "-scale needs a CSR, CSC, ELL, DIA, JAD or BSR matrix (row-partitioned: CSR)\n");
         return LIS_ERR_NOT_IMPLEMENTED;
     }
     if (action != LIS_SCALE_JACOBI && action != LIS_SCALE_SYMM_DIAG) { LIS_SETERR_IMP; return LIS_ERR_NOT_IMPLEMENTED; }
     err = lis_matrix_get_diagonal(A, Dv);
     if (err) return err;
-    LIS_SCALAR *d = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(n > 0 ? n : 1));
-    if (d == NULL) { LIS_SETERR_MEM(n * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
+    const LIS_INT np = A->np > n ? A->np : n;
+    LIS_SCALAR *d = (LIS_SCALAR *)malloc(sizeof(LIS_SCALAR) * (size_t)(np > 0 ? np : 1));
+    if (d == NULL) { LIS_SETERR_MEM(np * sizeof(LIS_SCALAR)); return LIS_OUT_OF_MEMORY; }
     err = n > 0 ? lis_vector_get_values(Dv, Dv->is + Dv->origin, n, d) : LIS_SUCCESS;
     if (err) { free(d); return err; }
+    if (A->nprocs > 1 && action == LIS_SCALE_SYMM_DIAG) {
+        /* row-partitioned: the columns of the halo need the diagonal entries their owners hold -- one halo exchange
+         * of the diagonal, like lis_send_recv(A->commtable, d) at src/matrix/lis_matrix_ops.c:604 (collective) */
+        double *d_tmp = NULL;
+        err = lisd_malloc((void **)&d_tmp, sizeof(double) * (size_t)(np > 0 ? np : 1));
+        if (!err && n > 0) err = lisd_upload(d_tmp, d, sizeof(double) * (size_t)n);
+        if (!err) err = lisd_halo_exchange_raw(A, d_tmp);
+        if (!err) err = lisd_sync();
+        if (!err && np > n) err = lisd_download(d + n, d_tmp + n, sizeof(double) * (size_t)(np - n));
+        if (d_tmp) lisd_free(d_tmp);
+        if (err) { free(d); return err; }
+        for (LIS_INT i = n; i < np; i++) d[i] = 1.0 / sqrt(fabs(d[i]));
+    }
     if (other_fmt) {
         /* the other formats, each with the expression of its reference loop (the order of the multiplications differs
          * between them): lis_matrix_scale[_symm]_{ell,dia,jad,bsr,csc}, src/matrix/lis_matrix_<fmt>.c */
