@@ -756,12 +756,12 @@ LIS_INT lis_reduce(LIS_COMMTABLE commtable, LIS_SCALAR x[])
 
 /* ------------------------------------------------------------------ halo exchange inside the SpMV kernel
  * One process per GPU; where every rank's GPU can map its neighbours' memory (all GPUs visible to every process,
- * peer access over NVLink, CUDA IPC) the row-partitioned CSR product needs no pack kernel, no NCCL group and no
+ * NVLink peers, the CUDA virtual-memory API) the row-partitioned CSR product needs no pack kernel, no NCCL group and no
  * unpack copy: kernels/spmv.cu (csr_tma_kernel<.., kHalo>) stores the exported x entries straight into the
  * neighbours' inboxes, raises a flag there, runs the rows that read no halo entry, waits for the neighbours'
  * flags and reads the halo columns from its own inbox.  This file sets up what the kernel needs, once per
- * communication table: inbox + flags (one cudaMalloc block, exported with cudaIpcGetMemHandle, the handles
- * travel through the shm control plane), the neighbours' blocks mapped with cudaIpcOpenMemHandle, and the
+ * communication table: inbox + flags (one cuMemCreate block exported as a POSIX file descriptor, which travels to
+ * the neighbours over a unix socket -- host/lis_peer.c), the neighbours' blocks imported and mapped, and the
  * table of addresses in device memory.  Anything missing -- a GPU hidden by CUDA_VISIBLE_DEVICES, no peer
  * access, an unsymmetric neighbour relation, LIS_B200_P2P=0 -- leaves the NCCL exchange in place. */
 static struct { int probed, ok, enabled; int *h_error, *d_error; int peer_dev[LISC_MAXR]; } gp = { .enabled = -1 };
