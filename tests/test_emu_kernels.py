@@ -33,6 +33,7 @@ test_spmv_bsr_block_shapes = G.test_spmv_bsr_block_shapes
 test_spmv_csr_split_order = G.test_spmv_csr_split_order
 test_spmv_long_rows = G.test_spmv_long_rows
 test_scaling_and_additive_schwarz_follow_the_reference = G2.test_scaling_and_additive_schwarz_follow_the_reference
+test_scaling_in_other_formats_follows_the_reference = G2.test_scaling_in_other_formats_follows_the_reference
 test_bicgstab_fused_updates_same_bits = G2.test_bicgstab_fused_updates_same_bits
 test_cg_carried_jacobi_step_same_bits = G2.test_cg_carried_jacobi_step_same_bits
 test_other_formats_spmv_bits = G2.test_other_formats_spmv_bits
