@@ -481,6 +481,7 @@ void lisd_perm_free(lisd_perm *p)
  * kernel publishes and polls in slot order).  blk_lo/blk_hi (or NULL): per row, the range of columns
  * the row keeps; couplings outside are the ones the block sweep drops (src/matrix/lis_matrix_csr.c:1590,
  * 1601) and are left out here.  wdep[w]: of all neighbours the warp's rows read, the slot latest in slot order. */
+int lisd_sweep_ahead(int maxlen);
 LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
                         const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, const int *blk_lo, const int *blk_hi)
 {
@@ -537,6 +538,28 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         sidx = (int *)malloc(sizeof(int) * (total ? total : 1));
         sval = (double *)malloc(sizeof(double) * (total ? total : 1));
         if (!sidx || !sval) { LIS_SETERR_MEM(total * 12); goto done; }
+    }
+    /* How far ahead of its last neighbour a warp leaves the cheap one-address wait.  0: it waits for wdep itself (the
+     * latest neighbour), then needs one more L2 round trip to collect the neighbours that were missing at its first
+     * poll -- two dependent round trips per level.  a > 0: it waits for the latest neighbour of the warp that holds
+     * its latest neighbour (applied a times), which is published about a levels earlier, and from then on polls its
+     * own missing neighbours directly: the result of the level before is seen by the first poll that reaches L2 after
+     * it, one round trip per level, at the price of 3-8x the polling traffic for the warps at the sweep front only.
+     * The kernel is the same -- the wait address is a hint, the loop that collects the neighbours decides.
+     * Measured (CG + SSOR, 256^3 7-point, 363 iterations, profiles/r02_sweep_ahead.txt): a = 0: 2.494, a = 1: 2.349,
+     * a = 2: 2.354 ms per iteration, same iteration count and residual bits.  Default: 1 for factors with short rows
+     * (<= 4 kept entries, the stencil case that was measured), 0 otherwise; LIS_B200_SWEEP_AHEAD overrides. */
+    {
+        const int ahead = lisd_sweep_ahead(maxlen);
+        if (ahead > 0 && nw > 0) {
+            int *chain = (int *)malloc(sizeof(int) * nw);
+            if (!chain) { LIS_SETERR_MEM(nw * 4); goto done; }
+            memcpy(chain, wdep, sizeof(int) * nw);
+            for (int a = 0; a < ahead; a++)
+                for (size_t w = 0; w < nw; w++)
+                    if (wdep[w] >= 0) wdep[w] = chain[(size_t)wdep[w] >> 5];
+            free(chain);
+        }
     }
     /* long rows (tens of kept entries: the banded matrix of config 4, ILU factors with fill): a warp per row on a
      * CSR-by-slot copy instead of SELL slices and a thread per row (kernels/sweep.cu sweep_rowwarp_kernel) */
@@ -628,6 +651,14 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
 done:
     free(order); free(plen); free(slot_of); free(wptr); free(wdep); free(sidx); free(sval);
     return err;
+}
+
+/* LIS_B200_SWEEP_AHEAD (see lisd_perm_build) */
+int lisd_sweep_ahead(int maxlen)
+{
+    const char *e = getenv("LIS_B200_SWEEP_AHEAD");          /* read per schedule build: once per preconditioner */
+    int v = e && e[0] >= '0' && e[0] <= '9' ? atoi(e) : (maxlen <= 4 ? 1 : 0);
+    return v > 8 ? 8 : v;
 }
 
 int lisd_sweep_ctas(void);
