@@ -54,6 +54,7 @@ test_empty_vector = G.test_empty_vector
 test_get_diagonal = G.test_get_diagonal
 test_psolve_ssor_bit_exact = G.test_psolve_ssor_bit_exact
 test_psolve_ssor_level_launch_path = G.test_psolve_ssor_level_launch_path
+test_psolve_sweep_look_ahead_same_bits = G.test_psolve_sweep_look_ahead_same_bits
 test_psolve_ssor_repeated_sweeps = G.test_psolve_ssor_repeated_sweeps
 test_psolve_jacobi_bit_exact = G.test_psolve_jacobi_bit_exact
 test_bicg_default_solver = G.test_bicg_default_solver

@@ -173,6 +173,26 @@ def test_psolve_ssor_bit_exact(b200, oracle, nthreads):
         b200.set_threads(1)
 
 
+@pytest.mark.parametrize("ahead", ["0", "1", "3"])
+def test_psolve_sweep_look_ahead_same_bits(b200, oracle, monkeypatch, ahead):
+    """LIS_B200_SWEEP_AHEAD: which published slot ends a warp's one-address wait (its latest neighbour, or that
+    neighbour's latest neighbour, ...) is a scheduling hint only -- SSOR and ILU sweeps keep their bits, for one block
+    and for three"""
+    monkeypatch.setenv("LIS_B200_SWEEP_AHEAD", ahead)
+    for name, (ptr, idx, val), _ in matrices():
+        if "empty" in name:
+            continue
+        b = H.rand_vec(len(ptr) - 1, 67, "wide")
+        for t in (1, 3):
+            b200.set_threads(t)
+            try:
+                x = b200.psolve(ptr, idx, val, b, "-p ssor -ssor_omega 1.2")
+                xo = oracle.psolve(ptr, idx, val, b, "ssor", omega=1.2, nthreads=t)
+                H.assert_bits_equal(x, xo, f"ssor/{name}/ahead={ahead}/T={t}")
+            finally:
+                b200.set_threads(1)
+
+
 def test_psolve_ssor_level_launch_path(b200, oracle, monkeypatch):
     """LIS_B200_SSOR=levels: one launch per level instead of the one-launch sweep; same bits"""
     monkeypatch.setenv("LIS_B200_SSOR", "levels")
