@@ -611,8 +611,7 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     }
     rhistory[0] = 1.0;
 
-    p_c_time = 0.0;
-    itime = lis_wtime();
+    p_c_time = lis_wtime();                    /* "matrix creation": the scaling block, as there (:612-743) */
 
     /* system scaling (src/solver/lis_solver.c:636-721): the stationary solvers with a preconditioner
      * always work on D^-1 A; -scale jacobi|symm_diag on request (CG turns jacobi into symm_diag to keep
@@ -640,6 +639,8 @@ LIS_INT lis_solve_kernel(LIS_MATRIX A, LIS_VECTOR b, LIS_VECTOR x, LIS_SOLVER so
     if (!err && !was_scaled && A->is_scaled && precon && precon->is_copy && precon->A && precon->A != A)
         err = lis_host_matrix_scale_like(precon->A, solver->d, scaled_with);
     if (err) { lis_vector_destroy(xx); lis_free(rhistory); solver->retcode = err; return err; }
+    p_c_time = lis_wtime() - p_c_time;
+    itime = lis_wtime();
 
     /* -storage: converts A in place */
     err = lis_matrix_convert_self(solver);
