@@ -36,6 +36,8 @@ LIS_INT lis_host_transpose(LIS_INT n, LIS_INT ncols, const LIS_INT *ptr, const L
 /* emulated OpenMP thread count of the reference (-omp_num_threads N): the SSOR block count */
 int  lis_host_num_threads(void);
 void lis_host_set_num_threads(int n);
+int  lis_host_worker_count(void);                 /* real host threads for set-up passes (LIS_B200_HOST_THREADS) */
+void lis_host_parallel_for(size_t count, size_t grain, void (*fn)(size_t lo, size_t hi, void *ctx), void *ctx);
 
 /* preconditioner registry / solver helpers */
 LIS_INT lis_host_precon_type_end(void);

@@ -914,36 +914,67 @@ static LIS_INT diag_create(LIS_MATRIX A, LIS_MATRIX_DIAG *Dout)
 
 LIS_INT lis_host_diag_create(LIS_MATRIX A, LIS_MATRIX_DIAG *Dout) { return diag_create(A, Dout); }
 
-/* src/matrix/lis_matrix_csr.c:764-949 (serial branch): storage order kept inside L and U,
- * the last diagonal entry of a row wins, halo columns (>= n) land in U */
+/* D, L, U of a CSR matrix (src/matrix/lis_matrix_csr.c:764-949, serial branch): storage order kept inside L and U,
+ * the last diagonal entry of a row wins, halo columns (>= n) land in U.  Two passes over the rows on the host worker
+ * threads -- count, (serial prefix sums), fill. */
+typedef struct { LIS_MATRIX A; LIS_INT *lp, *up; LIS_MATRIX_CORE L, U; LIS_MATRIX_DIAG D; } split_ctx;
+
+static void split_count_rows(size_t r0, size_t r1, void *ctx)
+{
+    split_ctx *c = (split_ctx *)ctx;
+    const LIS_MATRIX A = c->A;
+    for (size_t r = r0; r < r1; r++) {
+        const LIS_INT i = (LIS_INT)r;
+        LIS_INT nl = 0, nu = 0;
+        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
+            if (A->index[j] < i) nl++;
+            else if (A->index[j] > i) nu++;
+        }
+        c->lp[i + 1] = nl; c->up[i + 1] = nu;
+    }
+}
+
+static void split_fill_rows(size_t r0, size_t r1, void *ctx)
+{
+    split_ctx *c = (split_ctx *)ctx;
+    const LIS_MATRIX A = c->A;
+    for (size_t r = r0; r < r1; r++) {
+        const LIS_INT i = (LIS_INT)r;
+        LIS_INT kl = c->L->ptr[i], ku = c->U->ptr[i];
+        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
+            const LIS_INT col = A->index[j];
+            if (col < i) { c->L->index[kl] = col; c->L->value[kl] = A->value[j]; kl++; }
+            else if (col > i) { c->U->index[ku] = col; c->U->value[ku] = A->value[j]; ku++; }
+            else c->D->value[i] = A->value[j];
+        }
+    }
+}
+
 static LIS_INT split_csr(LIS_MATRIX A)
 {
     const LIS_INT n = A->n;
-    LIS_INT nnzl = 0, nnzu = 0, err;
-    for (LIS_INT i = 0; i < n; i++)
-        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
-            if (A->index[j] < i) nnzl++;
-            else if (A->index[j] > i) nnzu++;
-        }
+    LIS_INT err;
+    split_ctx c = { A, NULL, NULL, NULL, NULL, NULL };
+    c.lp = (LIS_INT *)malloc(sizeof(LIS_INT) * ((size_t)n + 1));
+    c.up = (LIS_INT *)malloc(sizeof(LIS_INT) * ((size_t)n + 1));
+    if (!c.lp || !c.up) { free(c.lp); free(c.up); LIS_SETERR_MEM(n * sizeof(LIS_INT)); return LIS_OUT_OF_MEMORY; }
+    c.lp[0] = 0; c.up[0] = 0;
+    lis_host_parallel_for((size_t)n, 65536, split_count_rows, &c);
+    for (LIS_INT i = 0; i < n; i++) { c.lp[i + 1] += c.lp[i]; c.up[i + 1] += c.up[i]; }
+    const LIS_INT nnzl = c.lp[n], nnzu = c.up[n];
     LIS_MATRIX_CORE L = (LIS_MATRIX_CORE)lis_calloc(sizeof(struct LIS_MATRIX_CORE_STRUCT), "lis_matrix_split::L");
     LIS_MATRIX_CORE U = (LIS_MATRIX_CORE)lis_calloc(sizeof(struct LIS_MATRIX_CORE_STRUCT), "lis_matrix_split::U");
     LIS_MATRIX_DIAG D = NULL;
-    if (!L || !U) { lis_free2(2, L, U); LIS_SETERR_MEM(sizeof(struct LIS_MATRIX_CORE_STRUCT)); return LIS_OUT_OF_MEMORY; }
+    if (!L || !U) { lis_free2(2, L, U); free(c.lp); free(c.up); LIS_SETERR_MEM(sizeof(struct LIS_MATRIX_CORE_STRUCT)); return LIS_OUT_OF_MEMORY; }
     err = lis_matrix_malloc_csr(n, nnzl, &L->ptr, &L->index, &L->value);
     if (!err) err = lis_matrix_malloc_csr(n, nnzu, &U->ptr, &U->index, &U->value);
     if (!err) err = diag_create(A, &D);
-    if (err) { core_destroy(L); core_destroy(U); return err; }
-    nnzl = 0; nnzu = 0;
-    L->ptr[0] = 0; U->ptr[0] = 0;
-    for (LIS_INT i = 0; i < n; i++) {
-        for (LIS_INT j = A->ptr[i]; j < A->ptr[i + 1]; j++) {
-            const LIS_INT c = A->index[j];
-            if (c < i) { L->index[nnzl] = c; L->value[nnzl] = A->value[j]; nnzl++; }
-            else if (c > i) { U->index[nnzu] = c; U->value[nnzu] = A->value[j]; nnzu++; }
-            else D->value[i] = A->value[j];
-        }
-        L->ptr[i + 1] = nnzl; U->ptr[i + 1] = nnzu;
-    }
+    if (err) { core_destroy(L); core_destroy(U); free(c.lp); free(c.up); return err; }
+    memcpy(L->ptr, c.lp, sizeof(LIS_INT) * ((size_t)n + 1));
+    memcpy(U->ptr, c.up, sizeof(LIS_INT) * ((size_t)n + 1));
+    free(c.lp); free(c.up);
+    c.L = L; c.U = U; c.D = D;
+    lis_host_parallel_for((size_t)n, 65536, split_fill_rows, &c);
     L->nnz = nnzl; U->nnz = nnzu;
     A->L = L; A->U = U; A->D = D;
     return LIS_SUCCESS;

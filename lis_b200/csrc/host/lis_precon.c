@@ -71,6 +71,7 @@ LIS_INT lis_precon_register_free(void)
 }
 
 LIS_INT lis_host_ssor_prepare(LIS_MATRIX A);
+static double setup_tick(const char *what, double t0);
 
 /* WD = 1/(scale*D), remembered under `tag` (A->use_wd) like the reference does
  * (lis_precon_ssor.c:79-90, lis_solver_gs.c, lis_solver_sor.c) */
@@ -136,13 +137,17 @@ static LIS_INT create_ssor(LIS_SOLVER solver, LIS_PRECON precon)
         precon->is_copy = LIS_TRUE;
         return LIS_SUCCESS;
     }
+    double tk = setup_tick(NULL, 0.0);
     err = lis_matrix_split(A);
     if (err) return err;
+    tk = setup_tick("split", tk);
     err = lis_host_set_wd(A, w, 1, LIS_SOLVER_SOR);
     if (err) return err;
     precon->A = A;
     precon->is_copy = LIS_FALSE;
-    return lis_host_ssor_prepare(A);      /* upload D/L/U and build the level schedule now, not in the first sweep */
+    err = lis_host_ssor_prepare(A);       /* upload D/L/U and build the level schedule now, not in the first sweep */
+    setup_tick("WD + mirror + schedule", tk);
+    return err;
 }
 
 /* -p hybrid: M^-1 b = a few steps of another solver on the same matrix (src/precon/lis_precon_hybrid.c:54-135).
@@ -482,6 +487,62 @@ void lisd_perm_free(lisd_perm *p)
  * the row keeps; couplings outside are the ones the block sweep drops (src/matrix/lis_matrix_csr.c:1590,
  * 1601) and are left out here.  wdep[w]: of all neighbours the warp's rows read, the slot latest in slot order. */
 int lisd_sweep_ahead(int maxlen);
+static double setup_tick(const char *what, double t0);
+
+/* the two passes of lisd_perm_build over a range of warps (32 slots each); disjoint outputs per warp */
+typedef struct {
+    const int *order; int *plen; const int *slot_of; const int *wptr; int *wdep; int *width; int *sidx; double *sval;
+    const LIS_INT *ptr, *idx; const LIS_SCALAR *val; const int *blk_lo, *blk_hi; int unused;
+} perm_ctx;
+
+static void perm_count_warps(size_t w0, size_t w1, void *ctx)
+{
+    perm_ctx *c = (perm_ctx *)ctx;
+    for (size_t w = w0; w < w1; w++) {
+        int width = 0, latest = -1;
+        for (int lane = 0; lane < 32; lane++) {
+            const size_t k = w * 32 + (size_t)lane;
+            const int i = c->order[k];
+            int cnt = 0;
+            if (i >= 0)
+                for (LIS_INT j = c->ptr[i]; j < c->ptr[i + 1]; j++) {
+                    const int jj = c->idx[j];
+                    if (c->blk_lo && (jj < c->blk_lo[i] || jj >= c->blk_hi[i])) continue;
+                    cnt++;
+                    if (c->slot_of[jj] > latest) latest = c->slot_of[jj];
+                }
+            c->plen[k] = cnt;
+            if (cnt > width) width = cnt;
+        }
+        c->width[w] = width;
+        c->wdep[w] = latest;
+    }
+}
+
+static void perm_fill_warps(size_t w0, size_t w1, void *ctx)
+{
+    perm_ctx *c = (perm_ctx *)ctx;
+    for (size_t w = w0; w < w1; w++) {
+        const int width = (c->wptr[w + 1] - c->wptr[w]) / 32;
+        for (int lane = 0; lane < 32; lane++) {
+            const int i = c->order[w * 32 + (size_t)lane];
+            int q = 0;
+            if (i >= 0)
+                for (LIS_INT j = c->ptr[i]; j < c->ptr[i + 1]; j++) {
+                    const int jj = c->idx[j];
+                    if (c->blk_lo && (jj < c->blk_lo[i] || jj >= c->blk_hi[i])) continue;
+                    c->sidx[(size_t)c->wptr[w] + 32 * (size_t)q + (size_t)lane] = c->slot_of[jj];
+                    c->sval[(size_t)c->wptr[w] + 32 * (size_t)q + (size_t)lane] = c->val[j];
+                    q++;
+                }
+            for (; q < width; q++) {
+                c->sidx[(size_t)c->wptr[w] + 32 * (size_t)q + (size_t)lane] = (int)(w * 32 + (size_t)lane);
+                c->sval[(size_t)c->wptr[w] + 32 * (size_t)q + (size_t)lane] = 0.0;
+            }
+        }
+    }
+}
+
 LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const int *rows,
                         const LIS_INT *ptr, const LIS_INT *idx, const LIS_SCALAR *val, const int *blk_lo, const int *blk_hi)
 {
@@ -497,6 +558,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
     int *sidx = NULL;
     double *sval = NULL;
     LIS_INT err = LIS_OUT_OF_MEMORY;
+    double tk = setup_tick(NULL, 0.0);
     if (!order || !plen || !slot_of || !wptr || !wdep) { LIS_SETERR_MEM(nslots * 12); goto done; }
     {
         size_t k = 0;
@@ -508,37 +570,28 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
             }
         }
     }
-    /* pass 1: kept entries per row, slice widths, the warp's latest neighbour */
+    tk = setup_tick("  slot order", tk);
+    /* pass 1: kept entries per row, slice widths, the warp's latest neighbour (host worker threads over the warps) */
     int maxlen = 0;
     {
+        int *width = (int *)malloc(sizeof(int) * (nw ? nw : 1));
+        if (!width) { LIS_SETERR_MEM(nw * 4); goto done; }
+        perm_ctx c = { order, plen, slot_of, wptr, wdep, width, NULL, NULL, ptr, idx, val, blk_lo, blk_hi, 0 };
+        lis_host_parallel_for(nw, 2048, perm_count_warps, &c);
         size_t total = 0;
         for (size_t w = 0; w < nw; w++) {
-            int width = 0, latest = -1;
-            for (int lane = 0; lane < 32; lane++) {
-                const size_t k = w * 32 + (size_t)lane;
-                const int i = order[k];
-                int cnt = 0;
-                if (i >= 0)
-                    for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++) {
-                        const int jj = idx[j];
-                        if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
-                        cnt++;
-                        if (slot_of[jj] > latest) latest = slot_of[jj];
-                    }
-                plen[k] = cnt;
-                if (cnt > width) width = cnt;
-                if (cnt > maxlen) maxlen = cnt;
-            }
             wptr[w] = (int)total;
-            wdep[w] = latest;
-            total += (size_t)32 * (size_t)width;
-            if (total > 0x7fffff00u) { LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "sweep schedule too large\n"); err = LIS_ERR_OUT_OF_MEMORY; goto done; }
+            if (width[w] > maxlen) maxlen = width[w];
+            total += (size_t)32 * (size_t)width[w];
+            if (total > 0x7fffff00u) { free(width); LIS_SETERR(LIS_ERR_OUT_OF_MEMORY, "sweep schedule too large\n"); err = LIS_ERR_OUT_OF_MEMORY; goto done; }
         }
+        free(width);
         wptr[nw] = (int)total;
         sidx = (int *)malloc(sizeof(int) * (total ? total : 1));
         sval = (double *)malloc(sizeof(double) * (total ? total : 1));
         if (!sidx || !sval) { LIS_SETERR_MEM(total * 12); goto done; }
     }
+    tk = setup_tick("  pass 1 (count)", tk);
     /* How far ahead of its last neighbour a warp leaves the cheap one-address wait.  0: it waits for wdep itself (the
      * latest neighbour), then needs one more L2 round trip to collect the neighbours that were missing at its first
      * poll -- two dependent round trips per level.  a > 0: it waits for the latest neighbour of the warp that holds
@@ -611,25 +664,11 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         }
     }
     /* pass 2: fill the slices; unused positions point at the row itself with a zero (never read) */
-    for (size_t w = 0; w < nw; w++) {
-        const int width = (wptr[w + 1] - wptr[w]) / 32;
-        for (int lane = 0; lane < 32; lane++) {
-            const int i = order[w * 32 + (size_t)lane];
-            int q = 0;
-            if (i >= 0)
-                for (LIS_INT j = ptr[i]; j < ptr[i + 1]; j++) {
-                    const int jj = idx[j];
-                    if (blk_lo && (jj < blk_lo[i] || jj >= blk_hi[i])) continue;
-                    sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = slot_of[jj];
-                    sval[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = val[j];
-                    q++;
-                }
-            for (; q < width; q++) {
-                sidx[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = (int)(w * 32 + (size_t)lane);
-                sval[(size_t)wptr[w] + 32 * (size_t)q + (size_t)lane] = 0.0;
-            }
-        }
+    {
+        perm_ctx c = { order, plen, slot_of, wptr, wdep, NULL, sidx, sval, ptr, idx, val, blk_lo, blk_hi, 0 };
+        lis_host_parallel_for(nw, 2048, perm_fill_warps, &c);
     }
+    tk = setup_tick("  pass 2 (fill)", tk);
     P->nslots = (int)nslots;
     P->short_rows = maxlen <= 4;
     {
@@ -648,6 +687,7 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
         if (!err) err = lisd_upload(P->d_sval, sval, sizeof(double) * total);
         if (!err) err = lisd_malloc((void **)&P->d_slots, sizeof(double) * 2 * (nslots ? nslots : 1));     /* slot-ordered results + wd */
     }
+    tk = setup_tick("  upload", tk);
 done:
     free(order); free(plen); free(slot_of); free(wptr); free(wdep); free(sidx); free(sval);
     return err;
@@ -716,9 +756,20 @@ static int sweep_blocks(int n)
     return nb;
 }
 
+/* LIS_B200_TRACE_SETUP=1: wall time of each phase of the schedule build on stderr */
+static double setup_tick(const char *what, double t0)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("LIS_B200_TRACE_SETUP"); on = e && e[0] == '1'; }
+    const double t = lis_wtime();
+    if (on && what) fprintf(stderr, "lis_b200 setup: %-28s %8.3f s\n", what, t - t0);
+    return t;
+}
+
 static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
 {
     const int n = A->n;
+    double tk = setup_tick(NULL, 0.0);
     lisd_sweep *S = (lisd_sweep *)calloc(1, sizeof(lisd_sweep));
     int *bs = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     int *be = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
@@ -745,12 +796,15 @@ static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
         if (l + 1 > nlev) nlev = l + 1;
     }
     S->nlev_f = nlev;
+    tk = setup_tick("forward levels", tk);
     S->h_fptr = lisd_order_by_level(n, lvl, nlev, rows);
     if (!S->h_fptr) goto fail;
+    tk = setup_tick("forward counting sort", tk);
     err = lisd_malloc((void **)&S->d_frows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_frows, rows, sizeof(int) * (size_t)n);
     if (!err) err = lisd_perm_build(&S->pf, n, nlev, S->h_fptr, rows, A->L->ptr, A->L->index, A->L->value, bs, be);
     if (err) goto fail;
+    tk = setup_tick("forward slices + upload", tk);
     /* backward: row i waits for every U neighbour inside its block */
     nlev = 0;
     for (int i = n - 1; i >= 0; i--) {
@@ -765,11 +819,13 @@ static LIS_INT sweep_build(LIS_MATRIX A, int nb, lisd_sweep **out)
     }
     S->nlev_b = nlev;
     S->h_bptr = lisd_order_by_level(n, lvl, nlev, rows);
+    tk = setup_tick("backward levels + sort", tk);
     err = LIS_OUT_OF_MEMORY;
     if (!S->h_bptr) goto fail;
     err = lisd_malloc((void **)&S->d_brows, sizeof(int) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_upload(S->d_brows, rows, sizeof(int) * (size_t)n);
     if (!err) err = lisd_perm_build(&S->pb, n, nlev, S->h_bptr, rows, A->U->ptr, A->U->index, A->U->value, bs, be);
+    tk = setup_tick("backward slices + upload", tk);
     if (!err) err = lisd_malloc((void **)&S->d_w, sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (!err) err = lisd_malloc((void **)&S->d_ticket, 64);
     if (!err) err = lisd_malloc((void **)&S->d_blk_start, sizeof(int) * (size_t)(n > 0 ? n : 1));

@@ -215,6 +215,43 @@ static int g_num_threads = 1;
 
 const lis_arg_t *lis_host_args(int *count) { *count = g_nargs; return g_args; }
 int lis_host_num_threads(void) { return g_num_threads; }
+
+/* ---------------------------------------------------------------- host worker threads for one-off set-up passes
+ * (sweep schedule, conversions): fn(lo, hi, ctx) over disjoint chunks of [0, count).  Not the emulated OpenMP thread
+ * count above (that one decides block partitions and so results); this one only spreads work whose result does not
+ * depend on it.  LIS_B200_HOST_THREADS overrides (1 = inline); small ranges run inline. */
+#include <pthread.h>
+#include <unistd.h>
+typedef struct { void (*fn)(size_t, size_t, void *); void *ctx; size_t lo, hi; } host_chunk_t;
+static void *host_chunk_run(void *p) { host_chunk_t *c = (host_chunk_t *)p; c->fn(c->lo, c->hi, c->ctx); return NULL; }
+
+int lis_host_worker_count(void)
+{
+    const char *e = getenv("LIS_B200_HOST_THREADS");
+    long t = e && e[0] >= '1' && e[0] <= '9' ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+    if (t < 1) t = 1;
+    if (t > 32) t = 32;
+    return (int)t;
+}
+
+void lis_host_parallel_for(size_t count, size_t grain, void (*fn)(size_t lo, size_t hi, void *ctx), void *ctx)
+{
+    int nt = lis_host_worker_count();
+    if (grain < 1) grain = 1;
+    if ((size_t)nt > count / grain) nt = (int)(count / grain);
+    if (nt <= 1) { if (count) fn(0, count, ctx); return; }
+    pthread_t tid[32];
+    host_chunk_t ch[32];
+    int started[32];
+    for (int k = 0; k < nt; k++) {
+        ch[k].fn = fn; ch[k].ctx = ctx;
+        ch[k].lo = count * (size_t)k / (size_t)nt;
+        ch[k].hi = count * (size_t)(k + 1) / (size_t)nt;
+        started[k] = k + 1 < nt && pthread_create(&tid[k], NULL, host_chunk_run, &ch[k]) == 0;
+    }
+    for (int k = 0; k < nt; k++) if (!started[k]) host_chunk_run(&ch[k]);       /* the last chunk, and any that got no thread */
+    for (int k = 0; k < nt; k++) if (started[k]) pthread_join(tid[k], NULL);
+}
 void lis_host_set_num_threads(int n) { g_num_threads = n > 0 ? n : 1; }
 LIS_INT lis_b200_set_num_threads(LIS_INT nthreads)
 {

@@ -151,6 +151,20 @@ def test_system_scaling_in_other_formats(hc, ref_serial, fmt):
         assert np.abs(g["x"] - r["x"]).max() < 1e-9, opts
 
 
+def test_threaded_setup_passes_same_results(hc, ref_serial):
+    """the split and the sweep schedule are built by host worker threads once a matrix is large enough (65536 rows per
+    chunk): CG + SSOR and BiCGSTAB + ILU on 64^3 (262144 rows, 4 chunks here) reproduce the serial reference bit for bit"""
+    ptr, idx, val = H.poisson3d_7pt(64, 64, 64)
+    n = len(ptr) - 1
+    b, _ = ref_serial.spmv("csr", ptr, idx, val, np.ones(n))
+    for opts in ("-i cg -p ssor -maxiter 12", "-i bicgstab -p ilu -maxiter 6"):
+        g = hc.solve(ptr, idx, val, b, opts)
+        r = ref_serial.solve(ptr, idx, val, b, opts)
+        assert (g["err"], g["status"], g["iter"]) == (r["err"], r["status"], r["iter"]), (opts, g["err"], g["status"], g["iter"], r["iter"])
+        H.assert_bits_equal(g["rhistory"], r["rhistory"], f"{opts} residual history")
+        H.assert_bits_equal(g["x"], r["x"], f"{opts} solution")
+
+
 def test_duplicate_entries_keep_the_reference_copy(hc, ref_serial):
     """a CSR matrix that stores the same (i, j) more than once, rows unsorted: CSR/ELL/JAD/COO/CSC/BSR/BSC/DNS products
     add every copy in storage order, DIA and VBR keep ONE copy -- whichever the row sort leaves last, which is why
