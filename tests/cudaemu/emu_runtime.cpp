@@ -312,7 +312,10 @@ static void *device_alloc(size_t bytes)
         sa.sa_flags = SA_SIGINFO | SA_NODEFER;
         sigaction(SIGSEGV, &sa, nullptr);
     }
-    if (g_pkey == -2 && protect_enabled()) g_pkey = pkey_alloc(0, g_device_open == 0 ? PKEY_DISABLE_ACCESS : 0);
+    if (g_pkey == -2 && protect_enabled()) {
+        const char *e = getenv("LISB_EMU_PKEY");           /* LISB_EMU_PKEY=0: take the mprotect path */
+        g_pkey = (e && e[0] == '0') ? -1 : pkey_alloc(0, g_device_open == 0 ? PKEY_DISABLE_ACCESS : 0);
+    }
     void *p = guarded_alloc(bytes);
     if (p && protect_enabled()) {
         g_device_only.insert(p);

@@ -110,7 +110,7 @@ cudaError_t cudaMalloc(void **p, size_t n)
         sigaction(SIGSEGV, &sa, NULL);
         g_arena = (char *)mmap(NULL, MOCK_ARENA, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (g_arena == MAP_FAILED) { g_arena = NULL; *p = NULL; return cudaErrorMemoryAllocation; }
-        g_pkey = pkey_alloc(0, g_open_depth == 0 ? PKEY_DISABLE_ACCESS : 0);
+        { const char *e = getenv("MOCK_PKEY"); g_pkey = (e && e[0] == '0') ? -1 : pkey_alloc(0, g_open_depth == 0 ? PKEY_DISABLE_ACCESS : 0); }   /* MOCK_PKEY=0: take the mprotect path */
     }
     const size_t page = (size_t)sysconf(_SC_PAGESIZE), len = ((n ? n : 1) + page - 1) / page * page;
     mock_blk *b;
