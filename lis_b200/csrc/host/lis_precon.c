@@ -495,6 +495,23 @@ typedef struct {
     const LIS_INT *ptr, *idx; const LIS_SCALAR *val; const int *blk_lo, *blk_hi; int unused;
 } perm_ctx;
 
+typedef struct { int *order; int *slot_of; const int *lptr; const int *rows; const size_t *koff; int nlev; } slot_ctx;
+
+static void perm_slot_order(size_t k0, size_t k1, void *ctx)
+{
+    slot_ctx *c = (slot_ctx *)ctx;
+    int lo = 0, hi = c->nlev;                       /* the level that owns slot k0 */
+    while (hi - lo > 1) { const int mid = lo + (hi - lo) / 2; if (c->koff[mid] <= k0) lo = mid; else hi = mid; }
+    int l = lo;
+    for (size_t k = k0; k < k1; k++) {
+        while (k >= c->koff[l + 1]) l++;
+        const size_t r = k - c->koff[l];
+        const int cnt = c->lptr[l + 1] - c->lptr[l];
+        if (r < (size_t)cnt) { const int row = c->rows[c->lptr[l] + (int)r]; c->order[k] = row; c->slot_of[row] = (int)k; }
+        else c->order[k] = -1;
+    }
+}
+
 static void perm_count_warps(size_t w0, size_t w1, void *ctx)
 {
     perm_ctx *c = (perm_ctx *)ctx;
@@ -561,14 +578,14 @@ LIS_INT lisd_perm_build(lisd_perm *P, int n, int nlev, const int *lptr, const in
     double tk = setup_tick(NULL, 0.0);
     if (!order || !plen || !slot_of || !wptr || !wdep) { LIS_SETERR_MEM(nslots * 12); goto done; }
     {
-        size_t k = 0;
-        for (int l = 0; l < nlev; l++) {
-            const int cnt = lptr[l + 1] - lptr[l], padded = (cnt + 31) & ~31;
-            for (int r = 0; r < padded; r++, k++) {
-                order[k] = r < cnt ? rows[lptr[l] + r] : -1;
-                if (r < cnt) slot_of[order[k]] = (int)k;
-            }
-        }
+        /* slot order: level l owns the slots [koff[l], koff[l+1]), its rows first, then -1 up to the multiple of 32 */
+        size_t *koff = (size_t *)malloc(sizeof(size_t) * ((size_t)nlev + 1));
+        if (!koff) { LIS_SETERR_MEM(nlev * 8); goto done; }
+        koff[0] = 0;
+        for (int l = 0; l < nlev; l++) koff[l + 1] = koff[l] + (size_t)((lptr[l + 1] - lptr[l] + 31) & ~31);
+        slot_ctx c = { order, slot_of, lptr, rows, koff, nlev };
+        lis_host_parallel_for(nslots, 65536, perm_slot_order, &c);
+        free(koff);
     }
     tk = setup_tick("  slot order", tk);
     /* pass 1: kept entries per row, slice widths, the warp's latest neighbour (host worker threads over the warps) */
